@@ -1,0 +1,207 @@
+"""Generate the committed golden fixtures by running the UNMODIFIED reference (container only).
+
+    python tests/golden/make_golden.py
+
+/root/reference's in-tree modules (tools/cnn_tools.py, tools/operators.py, tools/stochastic_pyqg.py,
+models/*.py) are imported as-is on top of oracle/pyqg_shim.py (pyqg itself is not installable here, see
+oracle/pyqg_shim.py header).  The outputs written next to this file are what tests/ compare against on
+machines where /root/reference does not exist (the GPU box).
+
+Fixtures
+--------
+weights_{gan,vae,gz_mean,gz_var}.npz  shipped nx=48 networks (Google-Colab/{GAN,VAE,GZ}/*.pt) as float32 arrays
+                                      keyed by the state-dict names, + x_std / y_std from the json scalers
+closure_48.npz     q (2,48,48), injected latent noise, and the reference classes' predict_snapshot /
+                   predict_mean_snapshot / __call__ outputs for GAN, VAE, GZ
+coupled_48.npz     3 steps of reference ``stochastic_QGModel`` + ``CVAERegression`` (AR1 nsteps=1 and nsteps=4;
+                   constant nsteps=2) with recorded noise and states
+operators_128.npz  Operator1/2/5, cut_off, fft_interpolate, PV_subgrid_forcing(none, 3/2-rule) on a 128^2 field
+samplers.npz       AR1 / constant sampler sequences
+"""
+import os
+import shutil
+import sys
+import tempfile
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_import  # noqa: E402
+
+ref_import.import_reference()
+import pyqg  # noqa: E402  (the shim)
+from pyqg_generative.tools import cnn_tools, operators  # noqa: E402
+from pyqg_generative.tools.stochastic_pyqg import stochastic_QGModel, AR1_sampler, constant_sampler  # noqa: E402
+from pyqg_generative.tools.parameters import EDDY_PARAMS  # noqa: E402
+from pyqg_generative.models.cgan_regression import CGANRegression  # noqa: E402
+from pyqg_generative.models.cvae_regression import CVAERegression  # noqa: E402
+from pyqg_generative.models.mean_var_model import MeanVarModel  # noqa: E402
+
+COLAB = os.path.join(ref_import.REFERENCE_ROOT, 'Google-Colab')
+
+
+def synthetic_q(n, seed, slope=-1.5):
+    """Gaussian random field with the shipped x_scale stds (7.78e-6 / 1.05e-6), red spectrum, truncated at 0.65*pi/dx."""
+    rng = np.random.RandomState(seed)
+    m = pyqg.QGModel(nx=n, log_level=0)
+    out = []
+    for std in (7.784383342368528e-06, 1.0471941322975908e-06):
+        h = np.fft.rfftn(rng.randn(n, n))
+        amp = np.where(m.wv > 0, (m.wv / m.dk + 1.0) ** slope, 0.0) * (m.wv * m.dx <= 0.65 * np.pi)
+        f = np.fft.irfftn(h * amp)
+        out.append(f / f.std() * std)
+    return np.stack(out).astype('float32').astype('float64')   # exactly representable in f32 -> small fixtures
+
+
+def save_weights():
+    def dump(pt, name, folder):
+        sd = torch.load(os.path.join(COLAB, folder, pt), map_location='cpu')
+        arrs = {k: v.numpy() for k, v in sd.items()}
+        xs = cnn_tools.ChannelwiseScaler().read('x_scale.json', os.path.join(COLAB, folder))
+        ys = cnn_tools.ChannelwiseScaler().read('y_scale.json', os.path.join(COLAB, folder))
+        arrs['x_std'] = xs.std.reshape(-1)
+        arrs['y_std'] = ys.std.reshape(-1)
+        np.savez_compressed(os.path.join(HERE, name), **arrs)
+    dump('G.pt', 'weights_gan.npz', 'GAN')
+    dump('decoder.pt', 'weights_vae.npz', 'VAE')
+    dump('net_mean.pt', 'weights_gz_mean.npz', 'GZ')
+    dump('net_var.pt', 'weights_gz_var.npz', 'GZ')
+
+
+def load_reference_models():
+    tmp = tempfile.mkdtemp(prefix='qgb_gan_')
+    for f in os.listdir(os.path.join(COLAB, 'GAN')):
+        shutil.copy(os.path.join(COLAB, 'GAN', f), tmp)
+    # D.pt is a missing large blob; the discriminator is never used at inference
+    torch.manual_seed(0)
+    torch.save(cnn_tools.DCGAN_discriminator(6, bn='None', nx=48).state_dict(), os.path.join(tmp, 'D.pt'))
+    gan = CGANRegression(folder=tmp, nx=48)
+    vae = CVAERegression(folder=os.path.join(COLAB, 'VAE'))
+    gz = MeanVarModel(folder=os.path.join(COLAB, 'GZ'))
+    return gan, vae, gz
+
+
+class _M(object):
+    """Minimal model view consumed by predict_snapshot / __call__ (reads m.q, m.ny, m.nx, sampler)."""
+
+
+def closure_fixture(gan, vae, gz):
+    n = 48
+    q = synthetic_q(n, 11)
+    rng = np.random.RandomState(5)
+    z32 = rng.randn(1, 2, n, n).astype('float32')
+    z64 = rng.randn(2, n, n)
+    m = _M()
+    m.q, m.ny, m.nx = q, n, n
+    out = dict(q=q.astype('float32'), z32=z32, z64=z64)
+    out['gan_snapshot'] = gan.predict_snapshot(m, z32)
+    out['vae_snapshot'] = vae.predict_snapshot(m, z32)
+    out['gz_snapshot'] = gz.predict_snapshot(m, z64)
+    out['gz_mean_snapshot'] = gz.predict_mean_snapshot(m)
+    # __call__ with seeded host RNG (np.random.randn is what generate_latent_noise draws from)
+    for name, model in (('gan', gan), ('vae', vae), ('gz', gz)):
+        m.sampling_type = 'AR1'
+        m.noise_sampler = AR1_sampler(1)
+        np.random.seed(77)
+        out[name + '_call'] = model(m)
+        out[name + '_call_noise'] = np.array(m.noise_sampler.noise)
+    # batched forward of the generator itself (torch API surface: generate(x, z))
+    xb = torch.as_tensor(rng.randn(3, 2, n, n).astype('float32'))
+    zb = torch.as_tensor(rng.randn(3, 2, n, n).astype('float32'))
+    gan.G.eval()
+    with torch.no_grad():
+        out['generate_x'] = xb.numpy()
+        out['generate_z'] = zb.numpy()
+        out['gan_generate'] = gan.generate(xb, zb).numpy()
+    np.savez_compressed(os.path.join(HERE, 'closure_48.npz'), **out)
+
+
+def coupled_fixture(vae):
+    n = 48
+    params = dict(EDDY_PARAMS.nx(n)._update({'dt': 7200.0, 'log_level': 0}))
+    out = {}
+    for tag, sampling, nsteps in (('ar1_1', 'AR1', 1), ('ar1_4', 'AR1', 4), ('const_2', 'constant', 2)):
+        p = dict(params)
+        p['parameterization'] = vae
+        np.random.seed(3)
+        m = stochastic_QGModel(p, sampling, nsteps)
+        m.q = synthetic_q(n, 21)
+        m._invert()
+        qs, zs, dqs = [m.q.copy()], [], []
+        np.random.seed(123)
+        for _ in range(4):
+            m._step_forward()
+            qs.append(m.q.copy())
+            zs.append(np.array(m.noise_sampler.noise).copy())
+            dqs.append(np.array(m.PV_forcing).copy())
+        out[tag + '_q'] = np.stack(qs)
+        out[tag + '_noise'] = np.stack(zs)
+        out[tag + '_forcing'] = np.stack(dqs)
+    np.savez_compressed(os.path.join(HERE, 'coupled_48.npz'), **out)
+
+
+def operators_fixture():
+    n = 128
+    q = synthetic_q(n, 31, slope=-1.0)
+    params = dict(EDDY_PARAMS.nx(n))
+    params.pop('nx')
+    out = dict(q=q.astype('float32'))
+    for nc in (32, 48, 64):
+        for name in ('Operator1', 'Operator2', 'Operator5', 'cut_off'):
+            out['%s_%d' % (name, nc)] = getattr(operators, name)(q, nc)
+    x = np.random.RandomState(1).randn(2, 48, 48)
+    out['interp_in'] = x
+    out['interp_48_72'] = operators.fft_interpolate(x, 48, 72)
+    out['interp_48_32'] = operators.fft_interpolate(x, 48, 32)
+    for opname in ('Operator1', 'Operator2', 'Operator5'):
+        for dealias, tag in (('none', 'none'), ('3/2-rule', '32')):
+            forcing, mf, m = operators.PV_subgrid_forcing(q, 64, getattr(operators, opname), dict(params), dealias)
+            out['S_%s_%s' % (opname, tag)] = forcing
+            if dealias == 'none':
+                out['qf_%s' % opname] = mf.q
+                out['uf_%s' % opname] = mf.u
+                out['vf_%s' % opname] = mf.v
+                out['pf_%s' % opname] = mf.p
+    np.savez_compressed(os.path.join(HERE, 'operators_128.npz'), **out)
+
+
+def samplers_fixture():
+    out = {}
+    for n in (1, 4, -1):
+        s = AR1_sampler(n)
+        rng = np.random.RandomState(9)
+        seq, xi = [], []
+        for _ in range(6):
+            def gen():
+                v = rng.randn(3)
+                xi.append(v)
+                return v
+            s.update(gen)
+            seq.append(np.array(s.noise))
+        out['ar1_%d' % n] = np.stack(seq)
+        out['ar1_%d_xi' % n] = np.stack(xi)
+    for n in (1, 3):
+        s = constant_sampler(n)
+        rng = np.random.RandomState(9)
+        seq, flags = [], []
+        for _ in range(8):
+            flags.append(s.update(lambda: rng.randn(3)))
+            seq.append(np.array(s.noise))
+        out['const_%d' % n] = np.stack(seq)
+        out['const_%d_flags' % n] = np.array(flags)
+    np.savez_compressed(os.path.join(HERE, 'samplers.npz'), **out)
+
+
+if __name__ == '__main__':
+    save_weights()
+    gan, vae, gz = load_reference_models()
+    closure_fixture(gan, vae, gz)
+    coupled_fixture(vae)
+    operators_fixture()
+    samplers_fixture()
+    for f in sorted(os.listdir(HERE)):
+        print('%10d  %s' % (os.path.getsize(os.path.join(HERE, f)), f))
