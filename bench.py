@@ -1,0 +1,284 @@
+#!/usr/bin/env python
+"""bench.py -- ensemble-member-steps/s of the online-simulation hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # B200 arm (this repository's engine)
+    python bench.py --impl reference --gpus N ...            # reference CPU implementation (oracle port) on host cores
+
+Workload (BASELINE.json configs[2]): nx=64 eddy configuration, dt=14400 s, CGAN closure (AndrewCNN 4->2), 1024 ensemble
+members PER GPU (weak scaling: members are independent, no data-path collective), synthetic developed-turbulence-like
+initial states and random-init generator weights of the named shapes, shipped x/y scalers, white latent noise each
+step (sampling 'constant', nsteps=1 as in scripts/run_parameterized.py:50).  A "step" is one model time step of every
+member: spectral step kernel + noise + 8 convolution layers + denormalisation.
+
+Timed region: W untimed warm-up steps (W >= 3 also completes the Adams-Bashforth start-up), then exactly K steps
+bracketed by barrier + cudaDeviceSynchronize, CUDA events on the launching stream, max over ranks.  State + activations
+(> 5 GB) exceed the 126 MB L2, so no explicit flush is needed (config.l2: "inputs larger than L2").
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'ensemble_member_steps_per_s'
+UNIT = 'member-steps/s'
+NX, DT = 64, 14400.0
+X_STD = [7.784383342368528e-06, 1.0471941322975908e-06]      # Google-Colab/GAN/x_scale.json
+Y_STD = [7.60611105349307e-12, 1.656513061486578e-13]         # Google-Colab/GAN/y_scale.json
+MAC_PER_PIXEL = [12800, 204800, 18432, 9216, 9216, 9216, 9216, 576]   # SURVEY.md Appendix B (GAN/VAE generator)
+
+
+def synthetic_states(members, n, seed):
+    """Gaussian random fields with the shipped x_scale stds and a red spectrum truncated at 0.65*pi/dx."""
+    rng = np.random.RandomState(seed)
+    dk = 2 * np.pi / 1e6
+    ll = dk * np.append(np.arange(0., n / 2), np.arange(-n / 2, 0.))
+    kk = dk * np.arange(0., n // 2 + 1)
+    k, l = np.meshgrid(kk, ll)
+    wv = np.sqrt(k ** 2 + l ** 2)
+    amp = np.where(wv > 0, (wv / dk + 1.0) ** -1.5, 0.0) * (wv * (1e6 / n) <= 0.65 * np.pi)
+    out = np.empty((members, 2, n, n))
+    for z, std in enumerate(X_STD):
+        h = np.fft.rfftn(rng.randn(members, n, n), axes=(-2, -1)) * amp
+        f = np.fft.irfftn(h, s=(n, n), axes=(-2, -1))
+        out[:, z] = f / f.std(axis=(-2, -1), keepdims=True) * std
+    return out
+
+
+def clock_sampler(stop, samples, device):
+    q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    while not stop.is_set():
+        try:
+            out = subprocess.run(['nvidia-smi', '-i', str(device), '--query-gpu=' + q, '--format=csv,noheader,nounits'],
+                                 capture_output=True, text=True, timeout=5).stdout.strip()
+            if out:
+                samples.append([x.strip() for x in out.split(',')])
+        except Exception:
+            pass
+        stop.wait(0.2)
+
+
+def summarize_clocks(samples):
+    if not samples:
+        return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+    sm = sorted(float(s[0]) for s in samples if s[0].replace('.', '').isdigit())
+    names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+    reasons = [n for i, n in enumerate(names) if any(len(s) > 3 + i and s[3 + i].lower().startswith('active') for s in samples)]
+    return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': float(samples[0][1]) if samples[0][1].replace('.', '').isdigit() else None,
+            'power_w_max': max(float(s[2]) for s in samples if s[2].replace('.', '').isdigit()) if samples else None,
+            'samples': len(samples), 'reasons': reasons}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            return json.load(f), 'measured'
+    except Exception:
+        return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0}, 'fallback'
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# reference CPU implementation of the path (oracle port): pyqg shim step + AndrewCNN on CPU torch, all host threads
+# ------------------------------------------------------------------------------------------------------------------
+class CpuEnsemble(object):
+    def __init__(self, members, sd, seed=0):
+        import torch
+        from oracle import cnn_ref, pyqg_shim
+        self.torch, self.cnn_ref = torch, cnn_ref
+        self.sd = sd
+        q0 = synthetic_states(members, NX, seed)
+        self.models = []
+        for b in range(members):
+            m = pyqg_shim.QGModel(nx=NX, dt=DT, log_level=0, parameterization=_Slot())
+            m.q = q0[b]
+            self.models.append(m)
+        self.rng = np.random.RandomState(seed + 1)
+
+    def step(self):
+        q = np.stack([m.q for m in self.models])
+        z = self.rng.randn(len(self.models), 2, NX, NX).astype('float32')        # constant sampler, nsteps=1
+        dq = self.cnn_ref.predict_snapshot('gan', [self.sd], X_STD, Y_STD, q, z)   # apply_function + generate
+        dq = self.cnn_ref.demean(dq)
+        for b, m in enumerate(self.models):
+            m.q_parameterization.dq = dq[b]
+            m._step_forward()
+
+
+class _Slot(object):
+    parameterization_type = 'q_parameterization'
+    dq = None
+
+    def __call__(self, m):
+        return self.dq
+
+
+def cpu_baseline(sample_members, steps, warmup, sd):
+    import torch
+    ens = CpuEnsemble(sample_members, sd)
+    for _ in range(warmup):
+        ens.step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ens.step()
+    dt = time.perf_counter() - t0
+    return sample_members * steps / dt, dt / steps * 1e3, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return 0
+    from oracle import cnn_ref
+    sd = cnn_ref.random_state_dict(4, 2, seed=0)
+    sample = args.ref_members
+    value, ms, cores = cpu_baseline(sample, args.steps, args.warmup, sd)
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f64 spectral step + f32 CNN', 'data': 'synthetic',
+        'config': {'workload': 'nx=64 eddy + CGAN closure (configs[2]); each step = %d members (bounded sample of the '
+                               '1024-member ensemble)' % sample, 'nx': NX, 'dt': DT, 'closure': 'gan'},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                         'sample': '%d members x %d steps, oracle/pyqg_shim.py + oracle/cnn_ref.py (CPU torch, %d threads); '
+                                   'pyqg itself is not installable here' % (sample, args.steps, cores)},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    from pyqg_generative_b200 import _lib, build, parallel
+    build.build()
+    rank, world, local = parallel.init_from_env()
+    torch.cuda.set_device(local)
+    from oracle import cnn_ref                      # only for the synthetic random-init weights and cpu_baseline
+    from pyqg_generative_b200.models.cgan_regression import CGANRegression
+    from pyqg_generative_b200.tools.cnn_tools import ChannelwiseScaler
+    from pyqg_generative_b200.tools.stochastic_pyqg import stochastic_QGModel
+
+    B = args.members
+    count, offset = B, rank * B                     # weak scaling: every GPU integrates ``members`` members
+    sd = cnn_ref.random_state_dict(4, 2, seed=0)
+    gan = CGANRegression(folder='/nonexistent', nx=NX, precision=args.precision)
+    gan.G.load_state_dict(sd)
+    gan.x_scale, gan.y_scale = ChannelwiseScaler(), ChannelwiseScaler()
+    gan.x_scale.std = np.array(X_STD, 'float32').reshape(1, 2, 1, 1)
+    gan.y_scale.std = np.array(Y_STD, 'float32').reshape(1, 2, 1, 1)
+    params = dict(nx=NX, dt=DT, log_level=0, tmax=1e12, tavestart=1e12, members=count, member_offset=offset,
+                  device=local, parameterization=gan, precision=args.precision, seed=2024)
+    m = stochastic_QGModel(params, 'constant', 1)
+    q0 = synthetic_states(count, NX, 1234 + rank)
+    m.set_q(q0)
+    lib, h, stream = m._lib, m._h, m._stream()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+
+    _lib.check(lib.qgb_step(h, max(args.warmup, 3), stream), h)
+    barrier()
+    # ---- device-resident timed region -------------------------------------------------------------------------
+    samples, stop = [], threading.Event()
+    th = threading.Thread(target=clock_sampler, args=(stop, samples, local), daemon=True)
+    th.start()
+    _lib.check(lib.qgb_profile_begin(h, 0, 1), h)              # layer 2 (128->64, 5x5): 75 % of the FLOPs
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    _lib.check(lib.qgb_step(h, args.steps, stream), h)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - l0
+    pms, pl, pim = ctypes.c_double(), ctypes.c_int64(), ctypes.c_int64()
+    _lib.check(lib.qgb_profile_end(h, ctypes.byref(pms), ctypes.byref(pl), ctypes.byref(pim)), h)
+    stop.set()
+    th.join(timeout=2)
+    ms = parallel.allreduce_max(ms)
+    value = world * count * args.steps / (ms * 1e-3)
+    ke, cfl, flags = m.diagnostics()
+    healthy = bool(np.isfinite(ke).all() and not flags.any())
+
+    # ---- end-to-end through the host-buffer C-ABI call: H2D q, one step, D2H q, every step ------------------------
+    qin = torch.from_numpy(q0).pin_memory()
+    qout = torch.empty_like(qin).pin_memory()
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    _lib.check(lib.qgb_step_host(h, qin.data_ptr(), qout.data_ptr(), 1, stream), h)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        _lib.check(lib.qgb_step_host(h, qin.data_ptr(), qout.data_ptr(), 1, stream), h)
+        qin, qout = qout, qin
+    barrier()
+    e2e_s = parallel.allreduce_max(time.perf_counter() - t0)
+    e2e_value = world * count * e2e_steps / e2e_s
+    nbytes = int(q0.nbytes)
+
+    if rank != 0:
+        return 0
+    peaks, which = measured_peaks()
+    flops_per_image = 2.0 * MAC_PER_PIXEL[1] * NX * NX
+    achieved = (flops_per_image * pim.value / max(pl.value, 1)) / (pms.value / max(pl.value, 1) * 1e-3) / 1e12 if pl.value else 0.0
+    peak = peaks['bf16_tflops_sustained']
+    cpu_v, cpu_ms, cores = cpu_baseline(args.ref_members, args.cpu_steps, 1, sd)
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+        'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f64 spectral step + %s CNN' % ('f16x3/f16 tcgen05 (f32 accumulate)' if args.precision == 'tc' else 'f32 FFMA'),
+        'data': 'synthetic',
+        'config': {'workload': 'nx=64 eddy + CGAN closure, %d members per GPU (configs[2])' % count, 'nx': NX, 'dt': DT,
+                   'members_per_gpu': count, 'closure': 'gan', 'sampling': 'constant/1', 'precision': args.precision,
+                   'l2': 'inputs larger than L2 (state + activations > 5 GB)', 'state_healthy': healthy},
+        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': nbytes, 'd2h_bytes_per_step': nbytes,
+                'steps': e2e_steps, 'call': 'qgb_step_host (pinned host q in, 1 step, host q out)'},
+        'gpu_launches': int(launches),
+        'clocks': summarize_clocks(samples),
+        'roofline': {'bound': 'tensor', 'kernel': 'conv layer 2 (128->64, 5x5), %s' % args.precision,
+                     'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
+                     'peak_source': '%s bf16_tflops_sustained' % which, 'traffic': None,
+                     'launch_ms': pms.value / max(pl.value, 1), 'launches': int(pl.value),
+                     'share_of_step': pms.value / ms if ms else None},
+        'cpu_baseline': {'value': cpu_v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                         'sample': '%d members x %d steps of the same workload, oracle/pyqg_shim.py + oracle/cnn_ref.py '
+                                   '(CPU torch, %d threads)' % (args.ref_members, args.cpu_steps, cores)},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', type=str, default='b200')
+    ap.add_argument('--members', type=int, default=1024)
+    ap.add_argument('--precision', type=str, default=os.environ.get('QGB_PRECISION', 'auto'))
+    ap.add_argument('--ref-members', type=int, default=16)
+    ap.add_argument('--cpu-steps', type=int, default=8)
+    ap.add_argument('--e2e-steps', type=int, default=10)
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+    if args.precision == 'auto':
+        args.precision = 'fp32'
+    return run_b200(args)
+
+
+if __name__ == '__main__':
+    sys.exit(main())

@@ -1,0 +1,173 @@
+/* qgb200.h -- C ABI of libqgb200.so, the B200-native (sm_100a) ensemble engine behind the
+ * pyqg_generative online-simulation hot path.
+ *
+ * Every entry point takes plain pointers and sizes (no torch / numpy types).  A pointer argument flagged
+ * ``on_device`` may be a CUDA device pointer (borrowed for the duration of the call, work is enqueued on
+ * ``stream``) or a host pointer (the library stages it with cudaMemcpyAsync on ``stream`` and synchronises the
+ * stream before returning when data flows back to the host).
+ *
+ * Each function cites the reference interface it replaces.  Paths are relative to the reference repository
+ * (m2lines/pyqg_generative); "pyqg:" means upstream pyqg 0.7.2, the un-vendored dependency that owns the
+ * dynamical-core arithmetic.
+ *
+ * Return value: 0 on success, a negative QGB_E* code otherwise; qgb_last_error() gives the message.
+ * A handle is bound to one device and is not thread-safe (the reference is single-threaded per member,
+ * pyfftw threads=1).  Numerical blow-up of a member is DATA (qgb_diag flags), never an error code.
+ */
+#ifndef QGB200_H
+#define QGB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct qgb_handle qgb_handle;
+
+enum { QGB_OK = 0, QGB_EINVAL = -1, QGB_ECUDA = -2, QGB_ESTATE = -3, QGB_EUNSUPPORTED = -4 };
+
+/* Model configuration = the pyqg.QGModel keyword arguments the reference passes
+ * (pyqg_generative/tools/parameters.py:36-37, tools/simulate.py:118-126, pyqg: Model.__init__/QGModel.__init__)
+ * plus the ensemble geometry. */
+typedef struct qgb_config {
+  int32_t nx;            /* grid points per side (ny == nx); 32/48/64/96 fused path, 128/256 multi-pass path */
+  int32_t members;       /* ensemble members resident on this device */
+  int32_t member_offset; /* global id of local member 0: Philox streams are keyed by the GLOBAL member id so a
+                            run is invariant to how members are sharded over GPUs */
+  int32_t device;        /* CUDA device ordinal */
+  double L;              /* domain size [m]                 (pyqg default 1e6) */
+  double dt;             /* time step [s]                   (tools/parameters.py:18-29 table) */
+  double rek;            /* bottom drag [1/s]               (5.787e-7 eddy, 7e-8 jet) */
+  double filterfac;      /* exponential filter factor       (23.6; 1e20 = sharp cut-off, tools/simulate.py:231) */
+  double beta;           /* planetary vorticity gradient    (1.5e-11 eddy, 1e-11 jet) */
+  double rd;             /* deformation radius [m]          (15000) */
+  double delta;          /* layer thickness ratio H1/H2     (0.25 eddy, 0.1 jet) */
+  double H1;             /* upper layer thickness [m]       (500) */
+  double U1, U2;         /* background zonal flow [m/s]     (0.025, 0) */
+} qgb_config;
+
+/* Fill *cfg with the pyqg 0.7.2 defaults (eddy configuration at nx=64, dt=7200). */
+void qgb_default_config(qgb_config* cfg);
+
+/* pyqg: QGModel.__init__ (called at tools/stochastic_pyqg.py:78-79, tools/simulate.py:83,121,125).
+ * Builds grids, inversion matrix, filter, FFT plans, state and history for cfg->members members. */
+int qgb_create(const qgb_config* cfg, qgb_handle** out);
+void qgb_destroy(qgb_handle* h);
+const char* qgb_last_error(const qgb_handle* h); /* h may be NULL: last error of a failed qgb_create */
+
+/* field ids for qgb_get */
+enum {
+  QGB_F_Q = 0,       /* double  (B,2,N,N)          potential vorticity                      (m.q)  */
+  QGB_F_QH = 1,      /* complex (B,2,N,N/2+1)      its rfft2                                (m.qh) */
+  QGB_F_PH = 2,      /* complex (B,2,N,N/2+1)      streamfunction, valid after qgb_invert   (m.ph) */
+  QGB_F_U = 3,       /* double  (B,2,N,N)          anomaly zonal velocity, after qgb_invert (m.u)  */
+  QGB_F_V = 4,       /* double  (B,2,N,N)                                                   (m.v)  */
+  QGB_F_DQHDT = 5,   /* complex (B,2,N,N/2+1)      tendency used by the latest step         (m.dqhdt) */
+  QGB_F_FORCING = 6, /* double  (B,2,N,N)          demeaned closure output                  (m.PV_forcing,
+                                                   models/parameterization.py:23-34) */
+  QGB_F_NOISE = 7,   /* float   (B,2,N,N) [gan/vae] or double (B,2,N,N) [gz]  latent noise   (m.noise_sampler.noise) */
+  QGB_F_P = 8        /* double  (B,2,N,N)          streamfunction in physical space (m.p, pyqg _calc_derived_fields) */
+};
+
+/* pyqg kernel ``q`` setter (relied on at tools/operators.py:232-233, tools/simulate.py:131-132): copies q and
+ * refreshes qh = rfft2(q).  Does not touch the time-stepping history.  q: double (B,2,N,N). */
+int qgb_set_q(qgb_handle* h, const double* q, int on_device, void* stream);
+/* pyqg: Model._initialize_time: t=0, tc=0, Adams-Bashforth restart (Euler, AB2, AB3). */
+int qgb_reset_time(qgb_handle* h);
+int qgb_get(qgb_handle* h, int field, void* out, int on_device, void* stream);
+/* pyqg: PseudoSpectralKernel._invert (explicit calls tools/simulate.py:132,168; tools/operators.py:233). */
+int qgb_invert(qgb_handle* h, void* stream);
+/* pyqg: Model._step_forward x nsteps = _invert, _do_advection, _do_friction, _do_q_subgrid_parameterization
+ * (closure evaluated on device if one is loaded), _forward_timestep.  This is the body of
+ * ``for t in m.run_with_snapshots(...)`` at tools/simulate.py:137. */
+int qgb_step(qgb_handle* h, int nsteps, void* stream);
+int qgb_get_time(qgb_handle* h, double* t, int64_t* tc);
+
+/* ---- closure (CNN subgrid parameterization) ------------------------------------------------------------ */
+enum { QGB_CLOSURE_NONE = 0, QGB_CLOSURE_GAN = 1, QGB_CLOSURE_VAE = 2, QGB_CLOSURE_GZ = 3, QGB_CLOSURE_OLS = 4,
+       QGB_CLOSURE_RAW = 5 /* bare network for qgb_cnn_forward only: any cin/cout, not coupled to qgb_step */ };
+enum { QGB_SAMPLER_AR1 = 0, QGB_SAMPLER_CONSTANT = 1, QGB_SAMPLER_DETERMINISTIC = 2 };
+enum { QGB_PREC_FP32 = 0,  /* fp32 FFMA direct convolution (bit-for-bit deterministic, parity reference) */
+       QGB_PREC_TC = 1     /* tcgen05 implicit GEMM, fp16 split precision (<=1e-3 rel. of the fp32 reference) */ };
+
+/* One AndrewCNN (tools/cnn_tools.py:125-182) in eval mode with BatchNorm folded to a per-channel affine
+ * (scale = gamma/sqrt(running_var+eps), shift = beta - running_mean*scale), laid out as torch stores it. */
+typedef struct qgb_cnn_layer {
+  int32_t cin, cout, ksize;
+  int32_t relu_bn;       /* 1: conv -> ReLU -> affine (make_block, cnn_tools.py:79-98); 0: bare conv (last layer) */
+  const float* weight;   /* (cout, cin, ksize, ksize) */
+  const float* bias;     /* (cout) */
+  const float* bn_scale; /* (cout) or NULL */
+  const float* bn_shift; /* (cout) or NULL */
+} qgb_cnn_layer;
+
+/* Load network ``net`` (0: generator / decoder / mean net / OLS net; 1: GZ variance net) for closure ``kind``.
+ * Replaces load_GAN / load_model / load_mean / load_var (models/cgan_regression.py:109-131,
+ * models/cvae_regression.py:91-102, models/mean_var_model.py:82-100, models/ols_model.py:59-66).
+ * Host pointers; the library packs and uploads. */
+int qgb_cnn_load(qgb_handle* h, int kind, int net, int nlayers, const qgb_cnn_layer* layers);
+/* ChannelwiseScaler stds (tools/cnn_tools.py:524-528 normalize/denormalize), model_weight
+ * (WeightedParameterization, tools/simulate.py:242) */
+int qgb_closure_config(qgb_handle* h, const float x_std[2], const float y_std[2], double weight, int precision);
+/* stochastic_QGModel(sampling_type, nsteps) (tools/stochastic_pyqg.py:78-88); n_mean = M of predict_mean_snapshot
+ * for the 'deterministic' sampler (models/cgan_regression.py:164-171, default 100). */
+int qgb_set_sampler(qgb_handle* h, int kind, int nsteps, int n_mean);
+int qgb_seed(qgb_handle* h, uint64_t seed);
+/* Parity injection: white noise xi used by the NEXT sampler update instead of Philox (what generate_latent_noise
+ * would have drawn, models/cgan_regression.py:154-155, models/mean_var_model.py:102-103).
+ * dtype 0: float (B,2,N,N), 1: double (B,2,N,N).  Passing NULL clears the injection. */
+int qgb_set_latent(qgb_handle* h, const void* xi, int dtype, int on_device, void* stream);
+/* Parameterization.__call__(m) on the current state (models/parameterization.py:23-34): sampler update,
+ * predict_snapshot, result kept as forcing (read it with QGB_F_FORCING). */
+int qgb_closure_eval(qgb_handle* h, void* stream);
+/* Generic pyqg QParameterization support (pyqg: Model._do_q_subgrid_parameterization; e.g. the inline ``Laplace``
+ * closure at tools/simulate.py:207-225 or Weighted/Composite wrappers): install an externally computed forcing
+ * dq: double (B,2,N,N) that the NEXT qgb_step adds as rfft2(dq) (used as given, not demeaned).  It is consumed by
+ * one step.  Passing NULL clears it. */
+int qgb_set_forcing(qgb_handle* h, const double* dq, int on_device, void* stream);
+/* generate(x, z) / net.forward (models/cgan_regression.py:133-137, tools/cnn_tools.py:164-176): raw network
+ * forward on caller data.  x: float (batch, cin, ny, nx) -> y: float (batch, cout, ny, nx); softplus!=0 applies
+ * VarCNN's softplus (models/mean_var_model.py:14-17). */
+int qgb_cnn_forward(qgb_handle* h, int net, const float* x, float* y, int batch, int ny, int nx, int softplus,
+                    int precision, int on_device, void* stream);
+
+/* ---- host-buffer convenience used by the end-to-end path ------------------------------------------------
+ * set_q(host) -> nsteps -> get q(host) in one call (the reference exchanges q / dq with the host every step,
+ * tools/cnn_tools.py:720-723). */
+int qgb_step_host(qgb_handle* h, const double* q_in_host, double* q_out_host, int nsteps, void* stream);
+
+/* ---- diagnostics ------------------------------------------------------------------------------------------
+ * pyqg: QGModel._calc_ke, _calc_cfl (logged every twrite steps; assert cfl<1), per member.
+ * ke, cfl: double (B); flags: int32 (B), bit0 = non-finite state, bit1 = cfl >= 1.  Any pointer may be NULL. */
+int qgb_diag(qgb_handle* h, double* ke, double* cfl, int32_t* flags, int on_device, void* stream);
+/* pyqg diagnostics KEspec = wv2*|ph|^2/M^2 and Ensspec = |qh|^2/M^2 summed over local members:
+ * double (2, N, N/2+1) each (the accumulators that are all-reduced over NCCL by the Python layer). */
+int qgb_diag_spectra(qgb_handle* h, double* kespec_sum, double* ensspec_sum, int on_device, void* stream);
+
+/* ---- coarse-graining operators (stateless; tools/operators.py) -------------------------------------------
+ * op: 1 = Operator1 (cut_off + model filter, :204-205), 2 = Operator2 (cut_off + gaussian, :207-208),
+ *     5 = Operator5 (cut_off only, :216-217, :117-132).  in: double (batch, n, n) -> out: double (batch, nc, nc). */
+int qgb_operator(int device, int op, int n, int nc, int batch, const double* in, double* out, int on_device,
+                 void* stream);
+/* PV_subgrid_forcing(q, nc, operator, pyqg_params, dealias='none') (tools/operators.py:283-287) for a batch of
+ * hi-res snapshots q: double (batch,2,n,n).  Outputs (batch,2,nc,nc) double, any may be NULL:
+ * forcing S, and the coarse model's q, u, v, psi (apply_operator_to_model, :219-236). */
+int qgb_subgrid_forcing(const qgb_config* cfg, int op, int nc, int batch, const double* q, double* forcing,
+                        double* qf, double* uf, double* vf, double* pf, int on_device, void* stream);
+
+/* Device-side timing of ONE network layer inside the running step loop (bench.py's roofline line): between
+ * qgb_profile_begin and qgb_profile_end every launch of layer ``layer`` of network ``net`` is bracketed by CUDA events on
+ * the launching stream.  qgb_profile_end synchronises, returns the summed duration [ms], the number of launches and
+ * the images processed by them, and stops profiling. */
+int qgb_profile_begin(qgb_handle* h, int net, int layer);
+int qgb_profile_end(qgb_handle* h, double* total_ms, int64_t* launches, int64_t* images);
+
+/* number of kernels launched by this library in this process (bench.py's gpu_launches) */
+int64_t qgb_launch_count(void);
+const char* qgb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QGB200_H */

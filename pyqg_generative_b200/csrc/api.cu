@@ -1,0 +1,778 @@
+// api.cu -- C ABI of libqgb200.so (see include/qgb200.h) and the host-side engine that sequences the sm_100a kernels.
+// No torch, no CPU fallback: every numerical entry point launches CUDA kernels and fails loudly otherwise.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/qgb200.h"
+#include "closure.cuh"
+#include "cnn_tc.cuh"
+#include "operators.cuh"
+#include "qg_host.hpp"
+#include "spectral.cuh"
+
+using namespace qgb;
+
+static std::atomic<long long> g_launches{0};
+static thread_local std::string g_create_error;
+#define QGB_COUNT_LAUNCH() (g_launches.fetch_add(1, std::memory_order_relaxed))
+
+namespace {
+
+struct DevNetLayer {
+  int cin = 0, cout = 0, ks = 0, relu_bn = 0, cout_pad = 0;
+  float *wp = nullptr, *bias = nullptr, *bn_s = nullptr, *bn_t = nullptr;
+};
+struct DevNet {
+  std::vector<DevNetLayer> layers;
+  TcNet tc;  // tcgen05 packing of the same network (cnn_tc.cuh); empty when the architecture is not supported
+  bool loaded() const { return !layers.empty(); }
+};
+
+}  // namespace
+
+struct qgb_handle {
+  qgb_config cfg;
+  HostTables ht;
+  Tables T;
+  std::string err;
+  // device tables
+  cplx* d_tw = nullptr; short* d_pos = nullptr; double *d_kv = nullptr, *d_lv = nullptr, *d_a = nullptr, *d_filtr = nullptr;
+  // state
+  cplx* qh = nullptr; double* q = nullptr; cplx* hist[3] = {nullptr, nullptr, nullptr};
+  cplx* ph = nullptr; double *u = nullptr, *v = nullptr, *p = nullptr, *red = nullptr;
+  double *d_ke = nullptr, *d_cfl = nullptr; int* d_flags = nullptr;
+  double *d_kespec = nullptr, *d_ensspec = nullptr;
+  long long tc = 0; double t = 0.0; int ablevel = 0;
+  int nthreads = 256; size_t smem = 0; int grid = 0;
+  // closure
+  int kind = QGB_CLOSURE_NONE; int precision = QGB_PREC_FP32;
+  DevNet nets[2];
+  float x_std[2] = {1.f, 1.f}, y_std[2] = {1.f, 1.f}; double weight = 1.0;
+  int sampler = QGB_SAMPLER_AR1, sampler_nsteps = 1, n_mean = 100;
+  bool noise_init = false; long long const_counter = 0; uint32_t draw = 0; uint64_t seed = 0x5eed5eedULL;
+  float* xin = nullptr;     // (B, cin0, N, N) closure input: normalised q [+ latent z for gan/vae]
+  int xin_c = 0; bool x_valid = false;
+  double* z64 = nullptr;    // gz latent (B,2,N,N)
+  void* xi_inj = nullptr; int xi_dtype = 0; bool xi_set = false;  // injected white noise (device copy)
+  float* ynet[2] = {nullptr, nullptr};  // network outputs (B,2,N,N)
+  float* yacc = nullptr;    // deterministic-mode accumulator
+  double* dq = nullptr;     // closure forcing (B,2,N,N), not demeaned
+  double* dq_dm = nullptr;  // demeaned copy served to qgb_get
+  bool dq_valid = false;
+  double* dq_ext = nullptr; bool ext_set = false;  // externally supplied forcing (qgb_set_forcing)
+  float* act[2] = {nullptr, nullptr}; size_t act_floats = 0; int act_chunk = 0;  // fp32 path ping-pong activations
+  TcWorkspace tcw;
+  int nsm = 148;
+  // per-layer profiling (qgb_profile_begin/end)
+  int prof_net = -1, prof_layer = -1; long long prof_images = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+};
+
+namespace {
+
+int fail(qgb_handle* h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define CUDA_TRY(h, expr)                                                                        \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess) return fail(h, QGB_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+template <typename T>
+cudaError_t dalloc(T** p, size_t n) { return cudaMalloc((void**)p, n * sizeof(T)); }
+
+template <typename T>
+cudaError_t upload(T** p, const std::vector<T>& v) {
+  cudaError_t e = dalloc(p, v.size());
+  if (e != cudaSuccess) return e;
+  return cudaMemcpy(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+inline cudaStream_t S(void* s) { return (cudaStream_t)s; }
+inline size_t nreal(const qgb_handle* h) { return (size_t)h->cfg.members * 2 * h->ht.N * h->ht.N; }
+inline size_t ncplx(const qgb_handle* h) { return (size_t)h->cfg.members * 2 * h->ht.N * h->ht.NK; }
+
+StepIO base_io(qgb_handle* h) {
+  StepIO io;
+  std::memset(&io, 0, sizeof(io));
+  io.qh = h->qh; io.q = h->q;
+  io.Hi_over_H[0] = h->ht.Hi_over_H[0]; io.Hi_over_H[1] = h->ht.Hi_over_H[1];
+  io.x_std[0] = h->x_std[0]; io.x_std[1] = h->x_std[1];
+  return io;
+}
+
+int launch_program(qgb_handle* h, const StepIO& io, int prog, cudaStream_t st) {
+  qg_program_kernel<<<h->grid, h->nthreads, h->smem, st>>>(h->T, io, prog, h->cfg.members);
+  QGB_COUNT_LAUNCH();
+  CUDA_TRY(h, cudaGetLastError());
+  return QGB_OK;
+}
+
+void set_cnn_io(qgb_handle* h, StepIO& io) {
+  if (h->kind != QGB_CLOSURE_NONE && h->xin) {
+    io.cnn_x = h->xin;
+    io.cnn_mstride = (long long)h->xin_c * h->ht.N * h->ht.N;
+  }
+}
+
+// ---- fp32 network forward over ``batch`` images resident on the device -------------------------------------
+int net_forward_fp32(qgb_handle* h, const DevNet& net, const float* x, long long x_bs, float* y, long long y_bs,
+                     int batch, int ny, int nx, int softplus, int accumulate, cudaStream_t st) {
+  int maxc = 0;
+  for (auto& L : net.layers) maxc = L.cout > maxc ? L.cout : maxc;
+  const size_t per_img = (size_t)maxc * ny * nx;
+  // ping-pong activations sized for a chunk of images
+  int chunk = batch < 64 ? batch : 64;
+  if (h->act_floats < per_img * chunk) {
+    for (int i = 0; i < 2; ++i) { if (h->act[i]) cudaFree(h->act[i]); h->act[i] = nullptr; }
+    CUDA_TRY(h, dalloc(&h->act[0], per_img * chunk));
+    CUDA_TRY(h, dalloc(&h->act[1], per_img * chunk));
+    h->act_floats = per_img * chunk;
+  }
+  const int tiles_x = (nx + kConvTile - 1) / kConvTile, tiles_y = (ny + kConvTile - 1) / kConvTile;
+  for (int b0 = 0; b0 < batch; b0 += chunk) {
+    const int nb = batch - b0 < chunk ? batch - b0 : chunk;
+    const float* in = x + (long long)b0 * x_bs;
+    long long in_bs = x_bs;
+    for (size_t li = 0; li < net.layers.size(); ++li) {
+      const DevNetLayer& L = net.layers[li];
+      const bool last = li + 1 == net.layers.size();
+      float* out = last ? y + (long long)b0 * y_bs : h->act[li & 1];
+      const long long out_bs = last ? y_bs : (long long)L.cout * ny * nx;
+      const int sp = last ? softplus : 0, acc = last ? accumulate : 0;
+      const bool small = L.cout <= 4;
+      const int co_t = small ? 2 : 32;
+      dim3 grid(tiles_x * tiles_y, (L.cout + co_t - 1) / co_t, nb);
+      const bool prof = h->prof_layer == (int)li && h->prof_net == (int)(&net - h->nets);
+      cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+      if (prof) { cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventRecord(ev0, st); }
+#define QGB_CONV(KS, CT)                                                                                         \
+  conv_ffma_kernel<KS, CT><<<grid, 256, 0, st>>>(in, in_bs, out, out_bs, L.wp, L.bias, L.bn_s, L.bn_t, L.cin, L.cout, \
+                                                 L.cout_pad, ny, nx, tiles_x, L.relu_bn, sp, acc)
+      if (L.ks == 5 && !small) QGB_CONV(5, 32);
+      else if (L.ks == 5) QGB_CONV(5, 2);
+      else if (L.ks == 3 && !small) QGB_CONV(3, 32);
+      else if (L.ks == 3) QGB_CONV(3, 2);
+      else if (L.ks == 1 && !small) QGB_CONV(1, 32);
+      else if (L.ks == 1) QGB_CONV(1, 2);
+      else return fail(h, QGB_EUNSUPPORTED, "kernel size %d not supported (1, 3, 5)", L.ks);
+#undef QGB_CONV
+      QGB_COUNT_LAUNCH();
+      CUDA_TRY(h, cudaGetLastError());
+      if (prof) { cudaEventRecord(ev1, st); h->prof_events.emplace_back(ev0, ev1); h->prof_images += nb; }
+      in = out;
+      in_bs = out_bs;
+    }
+  }
+  return QGB_OK;
+}
+
+int net_forward(qgb_handle* h, int net, const float* x, long long x_bs, float* y, long long y_bs, int batch, int ny,
+                int nx, int softplus, int accumulate, int precision, cudaStream_t st) {
+  if (precision == QGB_PREC_TC) {
+    if (!h->nets[net].tc.ready) return fail(h, QGB_EUNSUPPORTED, "tcgen05 path: network architecture not supported");
+    std::string e;
+    int rc = tc_forward(h->nets[net].tc, h->tcw, x, x_bs, y, y_bs, batch, ny, nx, softplus, accumulate, h->nsm, st, &e);
+    if (rc != 0) return fail(h, rc, "%s", e.c_str());
+    g_launches.fetch_add(tc_launches_per_forward(h->nets[net].tc), std::memory_order_relaxed);
+    return QGB_OK;
+  }
+  return net_forward_fp32(h, h->nets[net], x, x_bs, y, y_bs, batch, ny, nx, softplus, accumulate, st);
+}
+
+template <typename T>
+int launch_latent(qgb_handle* h, T* z, long long mstride, double a, double b, int replace, cudaStream_t st) {
+  const int npix = h->ht.N * h->ht.N;
+  const long long total = (long long)h->cfg.members * 2 * ((npix + 3) / 4);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  const T* inj = h->xi_set ? (const T*)h->xi_inj : nullptr;
+  latent_update_kernel<T><<<blocks, 256, 0, st>>>(z, mstride, npix, h->cfg.members, h->cfg.member_offset, h->seed,
+                                                   h->draw, (T)a, (T)b, replace, inj);
+  QGB_COUNT_LAUNCH();
+  CUDA_TRY(h, cudaGetLastError());
+  h->draw++;
+  return QGB_OK;
+}
+
+// white-noise draw (+AR1 blend) into the latent storage of the active closure
+int draw_latent(qgb_handle* h, double a, double b, int replace, cudaStream_t st) {
+  const long long npix = (long long)h->ht.N * h->ht.N;
+  if (h->kind == QGB_CLOSURE_GAN || h->kind == QGB_CLOSURE_VAE) {
+    if (h->xi_set && h->xi_dtype != 0) return fail(h, QGB_ESTATE, "injected latent must be float32 for gan/vae");
+    return launch_latent<float>(h, h->xin + 2 * npix, 4 * npix, a, b, replace, st);
+  }
+  if (h->kind == QGB_CLOSURE_GZ) {
+    if (h->xi_set && h->xi_dtype != 1) return fail(h, QGB_ESTATE, "injected latent must be float64 for gz");
+    return launch_latent<double>(h, h->z64, 2 * npix, a, b, replace, st);
+  }
+  return QGB_OK;  // ols: generate_latent_noise returns 0 (models/ols_model.py:68-69)
+}
+
+// Parameterization.__call__ body.  Returns via *computed whether a new forcing was produced.
+int closure_update(qgb_handle* h, cudaStream_t st) {
+  if (h->kind == QGB_CLOSURE_NONE) return fail(h, QGB_ESTATE, "no closure loaded");
+  if (!h->nets[0].loaded() || (h->kind == QGB_CLOSURE_GZ && !h->nets[1].loaded()))
+    return fail(h, QGB_ESTATE, "closure weights not loaded");
+  const int N = h->ht.N, B = h->cfg.members;
+  const long long npix = (long long)N * N, total = (long long)B * 2 * npix;
+  if (!h->x_valid) {
+    StepIO io = base_io(h);
+    set_cnn_io(h, io);
+    int rc = launch_program(h, io, PROG_EMIT_X, st);
+    if (rc) return rc;
+    h->x_valid = true;
+  }
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  const long long x_bs = (long long)h->xin_c * npix;
+  bool compute = true;
+  if (h->sampler == QGB_SAMPLER_DETERMINISTIC) {
+    // predict_mean_snapshot: mean of M generator samples (gan/vae); the mean net (gz); the net itself (ols)
+    if (h->kind == QGB_CLOSURE_GAN || h->kind == QGB_CLOSURE_VAE) {
+      if (!h->yacc) CUDA_TRY(h, dalloc(&h->yacc, (size_t)total));
+      for (int m = 0; m < h->n_mean; ++m) {
+        int rc = draw_latent(h, 0.0, 1.0, 1, st);
+        if (rc) return rc;
+        rc = net_forward(h, 0, h->xin, x_bs, h->yacc, 2 * npix, B, N, N, 0, m > 0, h->precision, st);
+        if (rc) return rc;
+      }
+      finish_plain_kernel<<<blocks, 256, 0, st>>>(h->yacc, h->dq, (int)npix, total, h->y_std[0], h->y_std[1],
+                                                   h->weight, 1.0f / (float)h->n_mean);
+      QGB_COUNT_LAUNCH();
+    } else if (h->kind == QGB_CLOSURE_GZ) {
+      int rc = net_forward(h, 0, h->xin, x_bs, h->ynet[0], 2 * npix, B, N, N, 0, 0, h->precision, st);
+      if (rc) return rc;
+      finish_gz_kernel<<<blocks, 256, 0, st>>>(h->ynet[0], nullptr, nullptr, h->dq, (int)npix, total, h->y_std[0],
+                                                h->y_std[1], h->weight, 0);
+      QGB_COUNT_LAUNCH();
+    } else {
+      int rc = net_forward(h, 0, h->xin, x_bs, h->ynet[0], 2 * npix, B, N, N, 0, 0, h->precision, st);
+      if (rc) return rc;
+      finish_plain_kernel<<<blocks, 256, 0, st>>>(h->ynet[0], h->dq, (int)npix, total, h->y_std[0], h->y_std[1],
+                                                   h->weight, 1.0f);
+      QGB_COUNT_LAUNCH();
+    }
+    CUDA_TRY(h, cudaGetLastError());
+    h->dq_valid = true;
+    return QGB_OK;
+  }
+  // ---- noise sampler update (tools/stochastic_pyqg.py:30-72) ----
+  if (h->sampler == QGB_SAMPLER_AR1) {
+    if (h->noise_init) {
+      double a = 1.0, b = 0.0;
+      if (h->sampler_nsteps > 0) {
+        a = 1.0 - 1.0 / h->sampler_nsteps;
+        b = std::sqrt(1.0 / h->sampler_nsteps * (2.0 - 1.0 / h->sampler_nsteps));
+      }
+      int rc = draw_latent(h, a, b, 0, st);
+      if (rc) return rc;
+    } else {
+      int rc = draw_latent(h, 0.0, 1.0, 1, st);
+      if (rc) return rc;
+      h->noise_init = true;
+    }
+  } else {  // constant sampler
+    if (h->noise_init) {
+      if (h->const_counter % h->sampler_nsteps == 0) {
+        int rc = draw_latent(h, 0.0, 1.0, 1, st);
+        if (rc) return rc;
+        h->const_counter = 1;
+      } else {
+        h->const_counter += 1;
+        compute = false;
+      }
+    } else {
+      int rc = draw_latent(h, 0.0, 1.0, 1, st);
+      if (rc) return rc;
+      h->noise_init = true;
+      h->const_counter = 1;
+    }
+  }
+  h->xi_set = false;  // an injected xi is consumed by one sampler update
+  if (!compute && h->dq_valid) return QGB_OK;
+  // ---- predict_snapshot ----
+  if (h->kind == QGB_CLOSURE_GZ) {
+    int rc = net_forward(h, 0, h->xin, x_bs, h->ynet[0], 2 * npix, B, N, N, 0, 0, h->precision, st);
+    if (rc) return rc;
+    rc = net_forward(h, 1, h->xin, x_bs, h->ynet[1], 2 * npix, B, N, N, 1, 0, h->precision, st);
+    if (rc) return rc;
+    finish_gz_kernel<<<blocks, 256, 0, st>>>(h->ynet[0], h->ynet[1], h->z64, h->dq, (int)npix, total, h->y_std[0],
+                                              h->y_std[1], h->weight, 1);
+  } else {
+    int rc = net_forward(h, 0, h->xin, x_bs, h->ynet[0], 2 * npix, B, N, N, 0, 0, h->precision, st);
+    if (rc) return rc;
+    finish_plain_kernel<<<blocks, 256, 0, st>>>(h->ynet[0], h->dq, (int)npix, total, h->y_std[0], h->y_std[1],
+                                                 h->weight, 1.0f);
+  }
+  QGB_COUNT_LAUNCH();
+  CUDA_TRY(h, cudaGetLastError());
+  h->dq_valid = true;
+  return QGB_OK;
+}
+
+int ensure_closure_buffers(qgb_handle* h) {
+  const size_t npix = (size_t)h->ht.N * h->ht.N, B = h->cfg.members;
+  const int cin0 = (h->kind == QGB_CLOSURE_GAN || h->kind == QGB_CLOSURE_VAE) ? 4 : 2;
+  if (h->xin && h->xin_c != cin0) { cudaFree(h->xin); h->xin = nullptr; }
+  if (!h->xin) {
+    CUDA_TRY(h, dalloc(&h->xin, B * cin0 * npix));
+    CUDA_TRY(h, cudaMemset(h->xin, 0, B * cin0 * npix * sizeof(float)));
+    h->xin_c = cin0;
+    h->x_valid = false;
+  }
+  if (h->kind == QGB_CLOSURE_GZ && !h->z64) CUDA_TRY(h, dalloc(&h->z64, B * 2 * npix));
+  for (int i = 0; i < 2; ++i)
+    if (!h->ynet[i]) CUDA_TRY(h, dalloc(&h->ynet[i], B * 2 * npix));
+  if (!h->dq) {
+    CUDA_TRY(h, dalloc(&h->dq, B * 2 * npix));
+    CUDA_TRY(h, dalloc(&h->dq_dm, B * 2 * npix));
+  }
+  return QGB_OK;
+}
+
+void free_net(DevNet& n) {
+  for (auto& L : n.layers) { cudaFree(L.wp); cudaFree(L.bias); cudaFree(L.bn_s); cudaFree(L.bn_t); }
+  n.layers.clear();
+  tc_free_net(n.tc);
+}
+
+}  // namespace
+
+// =============================================================================================== C ABI ====
+extern "C" {
+
+void qgb_default_config(qgb_config* c) {
+  std::memset(c, 0, sizeof(*c));
+  c->nx = 64; c->members = 1; c->member_offset = 0; c->device = 0;
+  c->L = 1e6; c->dt = 7200.0; c->rek = 5.787e-7; c->filterfac = 23.6; c->beta = 1.5e-11; c->rd = 15000.0;
+  c->delta = 0.25; c->H1 = 500.0; c->U1 = 0.025; c->U2 = 0.0;
+}
+
+const char* qgb_version(void) { return "qgb200 0.1 (sm_100a)"; }
+int64_t qgb_launch_count(void) { return (int64_t)g_launches.load(); }
+const char* qgb_last_error(const qgb_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int qgb_create(const qgb_config* cfg, qgb_handle** out) {
+  if (!cfg || !out) return fail(nullptr, QGB_EINVAL, "null argument");
+  *out = nullptr;
+  if (cfg->members < 1) return fail(nullptr, QGB_EINVAL, "members must be >= 1");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, QGB_ECUDA, "no CUDA device available (%s): libqgb200 has no CPU fallback", cudaGetErrorString(e));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, QGB_EINVAL, "device %d out of range", cfg->device);
+  qgb_handle* h = new qgb_handle();
+  h->cfg = *cfg;
+  if (!build_host_tables(*cfg, h->ht)) {
+    delete h;
+    return fail(nullptr, QGB_EINVAL, "nx=%d unsupported: must be even with prime factors 2 and 3", cfg->nx);
+  }
+#define CR(expr)                                                                     \
+  do {                                                                               \
+    cudaError_t _e = (expr);                                                         \
+    if (_e != cudaSuccess) {                                                         \
+      fail(nullptr, QGB_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(_e));      \
+      qgb_destroy(h);                                                                \
+      return QGB_ECUDA;                                                              \
+    }                                                                                \
+  } while (0)
+  CR(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  CR(cudaGetDeviceProperties(&prop, cfg->device));
+  h->nsm = prop.multiProcessorCount;
+  h->nthreads = cfg->nx >= 96 ? 512 : 256;
+  h->smem = program_smem_bytes(h->ht.N, h->ht.P, h->nthreads);
+  if (h->smem > (size_t)prop.sharedMemPerBlockOptin) {
+    fail(nullptr, QGB_EUNSUPPORTED, "nx=%d needs %zu B of shared memory per CTA (> %zu): the fused path covers nx<=96",
+         cfg->nx, h->smem, (size_t)prop.sharedMemPerBlockOptin);
+    qgb_destroy(h);
+    return QGB_EUNSUPPORTED;
+  }
+  CR(cudaFuncSetAttribute(qg_program_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+  h->grid = cfg->members;
+  CR(upload(&h->d_tw, h->ht.tw));
+  CR(upload(&h->d_pos, h->ht.pos));
+  CR(upload(&h->d_kv, h->ht.kv));
+  CR(upload(&h->d_lv, h->ht.lv));
+  CR(upload(&h->d_a, h->ht.a));
+  CR(upload(&h->d_filtr, h->ht.filtr));
+  fill_tables(h->ht, h->T, h->d_tw, h->d_pos, h->d_kv, h->d_lv, h->d_a, h->d_filtr);
+  const size_t nr = nreal(h), nc = ncplx(h), B = cfg->members;
+  CR(dalloc(&h->qh, nc)); CR(cudaMemset(h->qh, 0, nc * sizeof(cplx)));
+  CR(dalloc(&h->q, nr)); CR(cudaMemset(h->q, 0, nr * sizeof(double)));
+  for (int i = 0; i < 3; ++i) { CR(dalloc(&h->hist[i], nc)); CR(cudaMemset(h->hist[i], 0, nc * sizeof(cplx))); }
+  CR(dalloc(&h->red, B * 4));
+  CR(dalloc(&h->d_ke, B)); CR(dalloc(&h->d_cfl, B)); CR(dalloc(&h->d_flags, B));
+#undef CR
+  *out = h;
+  return QGB_OK;
+}
+
+void qgb_destroy(qgb_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->cfg.device);
+  cudaFree(h->d_tw); cudaFree(h->d_pos); cudaFree(h->d_kv); cudaFree(h->d_lv); cudaFree(h->d_a); cudaFree(h->d_filtr);
+  cudaFree(h->qh); cudaFree(h->q);
+  for (int i = 0; i < 3; ++i) cudaFree(h->hist[i]);
+  cudaFree(h->ph); cudaFree(h->u); cudaFree(h->v); cudaFree(h->p); cudaFree(h->red);
+  cudaFree(h->d_ke); cudaFree(h->d_cfl); cudaFree(h->d_flags); cudaFree(h->d_kespec); cudaFree(h->d_ensspec);
+  cudaFree(h->xin); cudaFree(h->z64); cudaFree(h->xi_inj); cudaFree(h->ynet[0]); cudaFree(h->ynet[1]);
+  cudaFree(h->yacc); cudaFree(h->dq_ext); cudaFree(h->dq); cudaFree(h->dq_dm); cudaFree(h->act[0]); cudaFree(h->act[1]);
+  free_net(h->nets[0]); free_net(h->nets[1]);
+  tc_free_workspace(h->tcw);
+  delete h;
+}
+
+int qgb_reset_time(qgb_handle* h) {
+  if (!h) return QGB_EINVAL;
+  h->tc = 0; h->t = 0.0; h->ablevel = 0;
+  h->noise_init = false; h->const_counter = 0; h->dq_valid = false;
+  return QGB_OK;
+}
+
+int qgb_get_time(qgb_handle* h, double* t, int64_t* tc) {
+  if (!h) return QGB_EINVAL;
+  if (t) *t = h->t;
+  if (tc) *tc = h->tc;
+  return QGB_OK;
+}
+
+int qgb_set_q(qgb_handle* h, const double* q, int on_device, void* stream) {
+  if (!h || !q) return fail(h, QGB_EINVAL, "null argument");
+  cudaStream_t st = S(stream);
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  CUDA_TRY(h, cudaMemcpyAsync(h->q, q, nreal(h) * sizeof(double),
+                              on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+  StepIO io = base_io(h);
+  set_cnn_io(h, io);
+  int rc = launch_program(h, io, PROG_SET_Q, st);
+  if (rc) return rc;
+  h->x_valid = io.cnn_x != nullptr;
+  if (!on_device) CUDA_TRY(h, cudaStreamSynchronize(st));  // the host buffer may be reused by the caller
+  return QGB_OK;
+}
+
+int qgb_invert(qgb_handle* h, void* stream) {
+  if (!h) return QGB_EINVAL;
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  if (!h->ph) {
+    CUDA_TRY(h, dalloc(&h->ph, ncplx(h)));
+    CUDA_TRY(h, dalloc(&h->u, nreal(h)));
+    CUDA_TRY(h, dalloc(&h->v, nreal(h)));
+    CUDA_TRY(h, dalloc(&h->p, nreal(h)));
+  }
+  StepIO io = base_io(h);
+  io.ph_out = h->ph; io.u_out = h->u; io.v_out = h->v; io.p_out = h->p;
+  return launch_program(h, io, PROG_INVERT, S(stream));
+}
+
+int qgb_step(qgb_handle* h, int nsteps, void* stream) {
+  if (!h || nsteps < 0) return fail(h, QGB_EINVAL, "bad argument");
+  cudaStream_t st = S(stream);
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  for (int s = 0; s < nsteps; ++s) {
+    StepIO io = base_io(h);
+    set_cnn_io(h, io);
+    int prog = PROG_STEP;
+    if (h->ext_set) {
+      io.dq = h->dq_ext;
+      prog = PROG_STEP_DQ_RAW;
+      h->ext_set = false;
+    } else if (h->kind != QGB_CLOSURE_NONE) {
+      int rc = closure_update(h, st);
+      if (rc) return rc;
+      io.dq = h->dq;
+      prog = PROG_STEP_DQ;
+    }
+    const int cur = (int)(h->tc % 3), prev = (int)((h->tc + 2) % 3), pprev = (int)((h->tc + 1) % 3);
+    io.d_cur = h->hist[cur]; io.d_p = h->hist[prev]; io.d_pp = h->hist[pprev];
+    ab_coefficients(h->ablevel, h->cfg.dt, io.dt1, io.dt2, io.dt3);
+    int rc = launch_program(h, io, prog, st);
+    if (rc) return rc;
+    if (h->ablevel < 2) h->ablevel++;
+    h->tc += 1;
+    h->t += h->cfg.dt;
+    h->x_valid = io.cnn_x != nullptr;
+  }
+  return QGB_OK;
+}
+
+int qgb_step_host(qgb_handle* h, const double* q_in, double* q_out, int nsteps, void* stream) {
+  if (!h) return QGB_EINVAL;
+  int rc = QGB_OK;
+  if (q_in) rc = qgb_set_q(h, q_in, 0, stream);
+  if (rc) return rc;
+  rc = qgb_step(h, nsteps, stream);
+  if (rc) return rc;
+  if (q_out) rc = qgb_get(h, QGB_F_Q, q_out, 0, stream);
+  return rc;
+}
+
+int qgb_get(qgb_handle* h, int field, void* out, int on_device, void* stream) {
+  if (!h || !out) return fail(h, QGB_EINVAL, "null argument");
+  cudaStream_t st = S(stream);
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  const void* src = nullptr;
+  size_t bytes = 0;
+  switch (field) {
+    case QGB_F_Q: src = h->q; bytes = nreal(h) * sizeof(double); break;
+    case QGB_F_QH: src = h->qh; bytes = ncplx(h) * sizeof(cplx); break;
+    case QGB_F_PH: src = h->ph; bytes = ncplx(h) * sizeof(cplx); break;
+    case QGB_F_U: src = h->u; bytes = nreal(h) * sizeof(double); break;
+    case QGB_F_V: src = h->v; bytes = nreal(h) * sizeof(double); break;
+    case QGB_F_P: src = h->p; bytes = nreal(h) * sizeof(double); break;
+    case QGB_F_DQHDT: src = h->hist[(h->tc + 2) % 3]; bytes = ncplx(h) * sizeof(cplx); break;
+    case QGB_F_FORCING: {
+      if (!h->dq_valid) return fail(h, QGB_ESTATE, "no closure forcing has been computed yet");
+      demean_kernel<<<h->cfg.members * 2, 256, 0, st>>>(h->dq, h->dq_dm, h->ht.N * h->ht.N);
+      QGB_COUNT_LAUNCH();
+      CUDA_TRY(h, cudaGetLastError());
+      src = h->dq_dm; bytes = nreal(h) * sizeof(double);
+      break;
+    }
+    case QGB_F_NOISE: {
+      if (!h->noise_init) return fail(h, QGB_ESTATE, "latent noise not initialised");
+      const size_t npix = (size_t)h->ht.N * h->ht.N;
+      if (h->kind == QGB_CLOSURE_GZ) { src = h->z64; bytes = nreal(h) * sizeof(double); break; }
+      if (h->kind == QGB_CLOSURE_GAN || h->kind == QGB_CLOSURE_VAE) {
+        // strided gather of channels 2,3 of the closure input
+        CUDA_TRY(h, cudaMemcpy2DAsync(out, 2 * npix * sizeof(float), h->xin + 2 * npix, 4 * npix * sizeof(float),
+                                      2 * npix * sizeof(float), h->cfg.members,
+                                      on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+        if (!on_device) CUDA_TRY(h, cudaStreamSynchronize(st));
+        return QGB_OK;
+      }
+      return fail(h, QGB_ESTATE, "closure has no latent noise");
+    }
+    default: return fail(h, QGB_EINVAL, "unknown field %d", field);
+  }
+  if (!src) return fail(h, QGB_ESTATE, "field %d not available (call qgb_invert first)", field);
+  CUDA_TRY(h, cudaMemcpyAsync(out, src, bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+  if (!on_device) CUDA_TRY(h, cudaStreamSynchronize(st));
+  return QGB_OK;
+}
+
+// ---- closure ------------------------------------------------------------------------------------------------
+int qgb_cnn_load(qgb_handle* h, int kind, int net, int nlayers, const qgb_cnn_layer* layers) {
+  if (!h || !layers || nlayers < 1 || net < 0 || net > 1) return fail(h, QGB_EINVAL, "bad argument");
+  if (kind < QGB_CLOSURE_GAN || kind > QGB_CLOSURE_RAW) return fail(h, QGB_EINVAL, "unknown closure kind %d", kind);
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  for (int i = 1; i < nlayers; ++i)
+    if (layers[i].cin != layers[i - 1].cout) return fail(h, QGB_EINVAL, "layer %d: cin does not match previous cout", i);
+  if (kind != QGB_CLOSURE_RAW) {
+    const int cin0 = (kind == QGB_CLOSURE_GAN || kind == QGB_CLOSURE_VAE) ? 4 : 2;
+    if (layers[0].cin != cin0) return fail(h, QGB_EINVAL, "first layer must have %d input channels, got %d", cin0, layers[0].cin);
+    if (layers[nlayers - 1].cout != 2) return fail(h, QGB_EINVAL, "last layer must have 2 output channels");
+    if (h->kind != kind) { free_net(h->nets[0]); free_net(h->nets[1]); h->dq_valid = false; h->noise_init = false; }
+    h->kind = kind;
+  }
+  DevNet& N = h->nets[net];
+  free_net(N);
+  for (int i = 0; i < nlayers; ++i) {
+    const qgb_cnn_layer& L = layers[i];
+    if (!L.weight || !L.bias) return fail(h, QGB_EINVAL, "layer %d: null weight/bias", i);
+    if (L.relu_bn && (!L.bn_scale || !L.bn_shift)) return fail(h, QGB_EINVAL, "layer %d: null batch-norm affine", i);
+    DevNetLayer D;
+    D.cin = L.cin; D.cout = L.cout; D.ks = L.ksize; D.relu_bn = L.relu_bn;
+    const int co_t = L.cout <= 4 ? 2 : 32;
+    D.cout_pad = (L.cout + co_t - 1) / co_t * co_t;
+    const int kk = L.ksize * L.ksize;
+    std::vector<float> wp((size_t)L.cin * kk * D.cout_pad, 0.f);
+    for (int co = 0; co < L.cout; ++co)
+      for (int ci = 0; ci < L.cin; ++ci)
+        for (int t = 0; t < kk; ++t) wp[((size_t)ci * kk + t) * D.cout_pad + co] = L.weight[((size_t)co * L.cin + ci) * kk + t];
+    std::vector<float> bias(L.bias, L.bias + L.cout), s(L.cout, 1.f), tt(L.cout, 0.f);
+    if (L.relu_bn) { s.assign(L.bn_scale, L.bn_scale + L.cout); tt.assign(L.bn_shift, L.bn_shift + L.cout); }
+    CUDA_TRY(h, upload(&D.wp, wp));
+    CUDA_TRY(h, upload(&D.bias, bias));
+    CUDA_TRY(h, upload(&D.bn_s, s));
+    CUDA_TRY(h, upload(&D.bn_t, tt));
+    N.layers.push_back(D);
+  }
+  std::string e;
+  tc_pack_net(N.tc, nlayers, layers, &e);  // leaves N.tc.ready == false if the architecture is not the AndrewCNN default
+  return kind == QGB_CLOSURE_RAW ? QGB_OK : ensure_closure_buffers(h);
+}
+
+int qgb_closure_config(qgb_handle* h, const float x_std[2], const float y_std[2], double weight, int precision) {
+  if (!h || !x_std || !y_std) return fail(h, QGB_EINVAL, "null argument");
+  if (precision != QGB_PREC_FP32 && precision != QGB_PREC_TC) return fail(h, QGB_EINVAL, "unknown precision %d", precision);
+  h->x_std[0] = x_std[0]; h->x_std[1] = x_std[1];
+  h->y_std[0] = y_std[0]; h->y_std[1] = y_std[1];
+  h->weight = weight;
+  h->precision = precision;
+  h->x_valid = false;
+  return QGB_OK;
+}
+
+int qgb_set_sampler(qgb_handle* h, int kind, int nsteps, int n_mean) {
+  if (!h) return QGB_EINVAL;
+  if (kind < QGB_SAMPLER_AR1 || kind > QGB_SAMPLER_DETERMINISTIC) return fail(h, QGB_EINVAL, "Unknown sampling type");
+  if (kind == QGB_SAMPLER_CONSTANT && nsteps < 1) return fail(h, QGB_EINVAL, "constant sampler needs nsteps >= 1");
+  if (nsteps == 0) return fail(h, QGB_EINVAL, "nsteps must be non-zero");
+  h->sampler = kind; h->sampler_nsteps = nsteps; h->n_mean = n_mean > 0 ? n_mean : 100;
+  h->noise_init = false; h->const_counter = 0;
+  return QGB_OK;
+}
+
+int qgb_seed(qgb_handle* h, uint64_t seed) {
+  if (!h) return QGB_EINVAL;
+  h->seed = seed; h->draw = 0;
+  return QGB_OK;
+}
+
+int qgb_set_latent(qgb_handle* h, const void* xi, int dtype, int on_device, void* stream) {
+  if (!h) return QGB_EINVAL;
+  if (!xi) { h->xi_set = false; return QGB_OK; }
+  if (dtype != 0 && dtype != 1) return fail(h, QGB_EINVAL, "dtype must be 0 (float) or 1 (double)");
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  const size_t bytes = nreal(h) * (dtype ? 8 : 4);
+  if (!h->xi_inj) CUDA_TRY(h, cudaMalloc(&h->xi_inj, nreal(h) * 8));
+  CUDA_TRY(h, cudaMemcpyAsync(h->xi_inj, xi, bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, S(stream)));
+  if (!on_device) CUDA_TRY(h, cudaStreamSynchronize(S(stream)));
+  h->xi_dtype = dtype; h->xi_set = true;
+  return QGB_OK;
+}
+
+int qgb_set_forcing(qgb_handle* h, const double* dq, int on_device, void* stream) {
+  if (!h) return QGB_EINVAL;
+  if (!dq) { h->ext_set = false; return QGB_OK; }
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  if (!h->dq_ext) CUDA_TRY(h, dalloc(&h->dq_ext, nreal(h)));
+  CUDA_TRY(h, cudaMemcpyAsync(h->dq_ext, dq, nreal(h) * sizeof(double),
+                              on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, S(stream)));
+  if (!on_device) CUDA_TRY(h, cudaStreamSynchronize(S(stream)));
+  h->ext_set = true;
+  return QGB_OK;
+}
+
+int qgb_profile_begin(qgb_handle* h, int net, int layer) {
+  if (!h || net < 0 || net > 1 || layer < 0) return fail(h, QGB_EINVAL, "bad argument");
+  for (auto& e : h->prof_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+  h->prof_events.clear();
+  h->prof_net = net; h->prof_layer = layer; h->prof_images = 0;
+  return QGB_OK;
+}
+
+int qgb_profile_end(qgb_handle* h, double* total_ms, int64_t* launches, int64_t* images) {
+  if (!h) return QGB_EINVAL;
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  double tot = 0.0;
+  for (auto& e : h->prof_events) {
+    CUDA_TRY(h, cudaEventSynchronize(e.second));
+    float ms = 0.f;
+    CUDA_TRY(h, cudaEventElapsedTime(&ms, e.first, e.second));
+    tot += ms;
+    cudaEventDestroy(e.first); cudaEventDestroy(e.second);
+  }
+  if (total_ms) *total_ms = tot;
+  if (launches) *launches = (int64_t)h->prof_events.size();
+  if (images) *images = (int64_t)h->prof_images;
+  h->prof_events.clear();
+  h->prof_net = -1; h->prof_layer = -1; h->prof_images = 0;
+  return QGB_OK;
+}
+
+int qgb_closure_eval(qgb_handle* h, void* stream) {
+  if (!h) return QGB_EINVAL;
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  return closure_update(h, S(stream));
+}
+
+int qgb_cnn_forward(qgb_handle* h, int net, const float* x, float* y, int batch, int ny, int nx, int softplus,
+                    int precision, int on_device, void* stream) {
+  if (!h || !x || !y || batch < 1 || ny < 1 || nx < 1 || net < 0 || net > 1) return fail(h, QGB_EINVAL, "bad argument");
+  if (!h->nets[net].loaded()) return fail(h, QGB_ESTATE, "network %d not loaded", net);
+  cudaStream_t st = S(stream);
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  const int cin = h->nets[net].layers.front().cin, cout = h->nets[net].layers.back().cout;
+  const long long x_bs = (long long)cin * ny * nx, y_bs = (long long)cout * ny * nx;
+  if (on_device) return net_forward(h, net, x, x_bs, y, y_bs, batch, ny, nx, softplus, 0, precision, st);
+  float *dx = nullptr, *dy = nullptr;
+  CUDA_TRY(h, dalloc(&dx, (size_t)batch * x_bs));
+  cudaError_t e = dalloc(&dy, (size_t)batch * y_bs);
+  if (e != cudaSuccess) { cudaFree(dx); return fail(h, QGB_ECUDA, "cudaMalloc failed: %s", cudaGetErrorString(e)); }
+  int rc = QGB_OK;
+  e = cudaMemcpyAsync(dx, x, (size_t)batch * x_bs * 4, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) rc = net_forward(h, net, dx, x_bs, dy, y_bs, batch, ny, nx, softplus, 0, precision, st);
+  if (e == cudaSuccess && rc == QGB_OK) e = cudaMemcpyAsync(y, dy, (size_t)batch * y_bs * 4, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(dx); cudaFree(dy);
+  if (e != cudaSuccess) return fail(h, QGB_ECUDA, "cnn_forward: %s", cudaGetErrorString(e));
+  return rc;
+}
+
+// ---- diagnostics ----------------------------------------------------------------------------------------------
+int qgb_diag(qgb_handle* h, double* ke, double* cfl, int32_t* flags, int on_device, void* stream) {
+  if (!h) return QGB_EINVAL;
+  cudaStream_t st = S(stream);
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  StepIO io = base_io(h);
+  io.red_out = h->red;
+  int rc = launch_program(h, io, PROG_DIAG, st);
+  if (rc) return rc;
+  const int B = h->cfg.members;
+  diag_finish_kernel<<<(B + 127) / 128, 128, 0, st>>>(h->red, B, h->cfg.dt / h->ht.dx, h->d_ke, h->d_cfl, h->d_flags);
+  QGB_COUNT_LAUNCH();
+  CUDA_TRY(h, cudaGetLastError());
+  const cudaMemcpyKind kd = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  if (ke) CUDA_TRY(h, cudaMemcpyAsync(ke, h->d_ke, B * sizeof(double), kd, st));
+  if (cfl) CUDA_TRY(h, cudaMemcpyAsync(cfl, h->d_cfl, B * sizeof(double), kd, st));
+  if (flags) CUDA_TRY(h, cudaMemcpyAsync(flags, h->d_flags, B * sizeof(int), kd, st));
+  if (!on_device) CUDA_TRY(h, cudaStreamSynchronize(st));
+  return QGB_OK;
+}
+
+int qgb_diag_spectra(qgb_handle* h, double* kespec, double* ensspec, int on_device, void* stream) {
+  if (!h) return QGB_EINVAL;
+  cudaStream_t st = S(stream);
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  const int n = 2 * h->ht.N * h->ht.NK;
+  if (!h->d_kespec) { CUDA_TRY(h, dalloc(&h->d_kespec, (size_t)n)); CUDA_TRY(h, dalloc(&h->d_ensspec, (size_t)n)); }
+  spectra_kernel<<<(n + 127) / 128, 128, 0, st>>>(h->T, h->qh, h->cfg.members, h->d_kespec, h->d_ensspec);
+  QGB_COUNT_LAUNCH();
+  CUDA_TRY(h, cudaGetLastError());
+  const cudaMemcpyKind kd = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  if (kespec) CUDA_TRY(h, cudaMemcpyAsync(kespec, h->d_kespec, n * sizeof(double), kd, st));
+  if (ensspec) CUDA_TRY(h, cudaMemcpyAsync(ensspec, h->d_ensspec, n * sizeof(double), kd, st));
+  if (!on_device) CUDA_TRY(h, cudaStreamSynchronize(st));
+  return QGB_OK;
+}
+
+// ---- coarse-graining (operators.cuh) -----------------------------------------------------------------------------
+int qgb_operator(int device, int op, int n, int nc, int batch, const double* in, double* out, int on_device,
+                 void* stream) {
+  std::string e;
+  long long launches = 0;
+  int rc = op_coarsegrain(device, op, n, nc, batch, in, out, on_device, S(stream), &launches, &e);
+  g_launches.fetch_add(launches, std::memory_order_relaxed);
+  if (rc) return fail(nullptr, rc, "%s", e.c_str());
+  return QGB_OK;
+}
+
+int qgb_subgrid_forcing(const qgb_config* cfg, int op, int nc, int batch, const double* q, double* forcing,
+                        double* qf, double* uf, double* vf, double* pf, int on_device, void* stream) {
+  std::string e;
+  long long launches = 0;
+  int rc = op_subgrid_forcing(cfg, op, nc, batch, q, forcing, qf, uf, vf, pf, on_device, S(stream), &launches, &e);
+  g_launches.fetch_add(launches, std::memory_order_relaxed);
+  if (rc) return fail(nullptr, rc, "%s", e.c_str());
+  return QGB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,558 @@
+// qg_core.cuh -- per-member spectral time step of the two-layer QG model, written as a sequence of
+// barrier-separated PHASES over one member's fields held in shared memory.
+//
+// The same phase functions are compiled twice:
+//   * by nvcc into the sm_100a kernels of spectral.cu (one CTA per ensemble member; phases separated by
+//     __syncthreads()), which is the product path;
+//   * by g++ into tests/emu (a thread-by-thread host emulation used ONLY by the CPU test-suite to check the
+//     index arithmetic against the oracle before any GPU time is spent).
+//
+// What is computed (pyqg 0.7.2 PseudoSpectralKernel; call sites in the reference:
+// pyqg_generative/tools/simulate.py:132,137,168 and tools/operators.py:229-234,303-305,323-326):
+//   _invert                ph = A qh ; uh = -il ph ; vh = ik ph ; u,v = irfft2
+//   _do_advection          uq=(u+Ubg)q ; vq=v q ; dqhdt = -(ik uqh + il vqh + ikQy ph)
+//   _do_friction           dqhdt[1] += rek wv2 ph[1]
+//   _do_q_subgrid_param.   dqhdt += rfft2(dq)          (dq demeaned == zeroing its (0,0) mode,
+//                                                        models/parameterization.py:25)
+//   _forward_timestep      qh = filtr (qh + dt1 dqhdt + dt2 dqhdt_p + dt3 dqhdt_pp) ; q = irfft2(qh)
+//
+// FFT design: two REAL fields are packed as one COMPLEX N x N transform (u+iv, uq+ivq, q1+iq2, dq1+idq2), so a
+// step costs 6 complex 2-D FFTs.  Transforms are in-place mixed-radix (4,2,3) decimation-in-frequency forward
+// (natural in -> digit-reversed out) and decimation-in-time inverse (digit-reversed in -> natural out); spectral
+// data therefore lives in shared memory at permuted positions (pos_of_freq) and is never reordered.  The row pitch
+// is N+1 complex numbers so both row and column passes are bank-conflict free for 16-byte accesses.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define QGB_HD __host__ __device__ __forceinline__
+#else
+#define QGB_HD inline
+#endif
+
+namespace qgb {
+
+struct alignas(16) cplx {
+  double x, y;
+};
+
+QGB_HD cplx cmake(double x, double y) { cplx r; r.x = x; r.y = y; return r; }
+QGB_HD cplx cadd(cplx a, cplx b) { return cmake(a.x + b.x, a.y + b.y); }
+QGB_HD cplx csub(cplx a, cplx b) { return cmake(a.x - b.x, a.y - b.y); }
+QGB_HD cplx cmul(cplx a, cplx b) { return cmake(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+QGB_HD cplx cmulc(cplx a, cplx b) { return cmake(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }  // a*conj(b)
+QGB_HD cplx cconj(cplx a) { return cmake(a.x, -a.y); }
+QGB_HD cplx cscale(cplx a, double s) { return cmake(a.x * s, a.y * s); }
+QGB_HD cplx cmuli(cplx a, double c) { return cmake(-c * a.y, c * a.x); }  // (i c) * a
+
+constexpr int kMaxStages = 8;
+
+// Member-independent tables (device pointers in the kernels, host pointers in the emulation)
+struct Tables {
+  int N, NK, P;  // grid size, N/2+1, shared-memory row pitch (complex elements)
+  int nstages;
+  int radix[kMaxStages];
+  const cplx* tw;          // [N]      exp(-2 pi i t / N)
+  const short* pos;        // [N]      position of frequency index f after the forward transform
+  const double* kv;        // [NK]     zonal wavenumbers  kk
+  const double* lv;        // [N]      meridional wavenumbers ll (FFT order)
+  const double* a;         // [4][N*NK] inversion matrix a00,a01,a10,a11 (pyqg _initialize_inversion_matrix)
+  const double* filtr;     // [N*NK]   exponential filter (pyqg _initialize_filter)
+  double Ubg[2], Qy[2], rek, inv_M;
+};
+
+struct StepIO {
+  cplx* qh;             // (B,2,N,NK)  in/out
+  double* q;            // (B,2,N,N)   in/out
+  cplx* d_cur;          // (B,2,N,NK)  tendency of this step (becomes dqhdt_p)
+  const cplx* d_p;      // dqhdt_p
+  const cplx* d_pp;     // dqhdt_pp
+  const double* dq;     // (B,2,N,N) closure forcing or nullptr
+  float* cnn_x;         // closure input: member stride cnn_mstride floats, channel stride N*N; or nullptr
+  long long cnn_mstride;
+  float x_std[2];
+  double dt1, dt2, dt3;
+  // invert / diagnostics outputs (may be null)
+  cplx* ph_out;
+  double* u_out;
+  double* v_out;
+  double* p_out;
+  double* red_out;      // (B,4): ke, max|u+U|, max|v|, nonfinite count
+  double Hi_over_H[2];
+};
+
+// Per-CTA context: shared-memory views + which member this CTA owns
+struct Ctx {
+  const Tables& T;   // lives in kernel parameter (constant) space on the device
+  const StepIO& io;
+  cplx* buf;      // [N*P]
+  cplx* tw;       // [N]   shared copy of the twiddles
+  short* pos;     // [N]   shared copy of the position map
+  double* red;    // [4*nthreads] reduction scratch (diagnostic program only)
+  int member;
+};
+
+// ------------------------------------------------------------------------------------------------------
+// 1-D FFT stage over ``nlines`` lines of the shared buffer.  es = element stride, ls = line stride.
+// Forward stage (sub-FFT length n, radix r, m = n/r):  y[k1] = w_n^{j2 k1} * sum_j1 w_r^{j1 k1} x[j1 m + j2]
+// stored in place at k1 m + j2.  The inverse stage is its exact adjoint (conjugate twiddles, then conj DFT_r).
+// ------------------------------------------------------------------------------------------------------
+QGB_HD void fft_stage(cplx* buf, const cplx* tw, int N, int es, int ls, int nlines, int r, int n, bool inverse,
+                      int tid, int nt) {
+  const int m = n / r;
+  const int nb = N / r;
+  const int tws = N / n;
+  const int items = nlines * nb;
+  const int step = m * es;
+  const double sgn = inverse ? 1.0 : -1.0;
+  for (int i = tid; i < items; i += nt) {
+    const int b = i / nlines;
+    const int line = i - b * nlines;
+    const int blk = b / m;
+    const int j2 = b - blk * m;
+    cplx* p = buf + line * ls + (blk * n + j2) * es;
+    if (r == 4) {
+      cplx x0 = p[0], x1 = p[step], x2 = p[2 * step], x3 = p[3 * step];
+      if (inverse) {
+        x1 = cmulc(x1, tw[j2 * tws]);
+        x2 = cmulc(x2, tw[2 * j2 * tws]);
+        x3 = cmulc(x3, tw[3 * j2 * tws]);
+      }
+      cplx t0 = cadd(x0, x2), t1 = csub(x0, x2), t2 = cadd(x1, x3), d = csub(x1, x3);
+      cplx t3 = cmake(-sgn * d.y, sgn * d.x);  // (sgn*i) * d   (forward: -i, inverse: +i)
+      cplx y0 = cadd(t0, t2), y2 = csub(t0, t2), y1 = cadd(t1, t3), y3 = csub(t1, t3);
+      if (!inverse) {
+        y1 = cmul(y1, tw[j2 * tws]);
+        y2 = cmul(y2, tw[2 * j2 * tws]);
+        y3 = cmul(y3, tw[3 * j2 * tws]);
+      }
+      p[0] = y0; p[step] = y1; p[2 * step] = y2; p[3 * step] = y3;
+    } else if (r == 2) {
+      cplx x0 = p[0], x1 = p[step];
+      if (inverse) x1 = cmulc(x1, tw[j2 * tws]);
+      cplx y0 = cadd(x0, x1), y1 = csub(x0, x1);
+      if (!inverse) y1 = cmul(y1, tw[j2 * tws]);
+      p[0] = y0; p[step] = y1;
+    } else {  // r == 3
+      cplx x0 = p[0], x1 = p[step], x2 = p[2 * step];
+      if (inverse) {
+        x1 = cmulc(x1, tw[j2 * tws]);
+        x2 = cmulc(x2, tw[2 * j2 * tws]);
+      }
+      const double h = 0.86602540378443864676;  // sqrt(3)/2
+      cplx s = cadd(x1, x2), d = csub(x1, x2);
+      cplx m1 = cmake(x0.x - 0.5 * s.x, x0.y - 0.5 * s.y);
+      cplx m2 = cmake(-sgn * h * d.y, sgn * h * d.x);  // (sgn*i*h) * d
+      cplx y0 = cadd(x0, s), y1 = cadd(m1, m2), y2 = csub(m1, m2);
+      if (!inverse) {
+        y1 = cmul(y1, tw[j2 * tws]);
+        y2 = cmul(y2, tw[2 * j2 * tws]);
+      }
+      p[0] = y0; p[step] = y1; p[2 * step] = y2;
+    }
+  }
+}
+
+// number of barrier-separated phases of one 2-D transform
+QGB_HD int fft2d_phases(const Tables& T) { return 2 * T.nstages; }
+
+// phase ``ph`` (0 .. 2*nstages-1) of the 2-D transform of the whole N x N buffer
+QGB_HD void fft2d_phase(const Ctx& c, int ph, bool inverse, int tid, int nt) {
+  const Tables& T = c.T;
+  const int S = T.nstages;
+  const int pass = ph / S;  // 0: along x (rows), 1: along y (columns)
+  int s = ph - pass * S;
+  if (inverse) s = S - 1 - s;
+  int n = T.N;
+  for (int i = 0; i < s; ++i) n /= T.radix[i];
+  const int es = pass == 0 ? 1 : T.P;
+  const int ls = pass == 0 ? T.P : 1;
+  fft_stage(c.buf, c.tw, T.N, es, ls, T.N, T.radix[s], n, inverse, tid, nt);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// pointwise phases
+// ------------------------------------------------------------------------------------------------------
+QGB_HD void ph_init(const Ctx& c, int tid, int nt) {
+  for (int i = tid; i < c.T.N; i += nt) {
+    c.tw[i] = c.T.tw[i];
+    c.pos[i] = c.T.pos[i];
+  }
+}
+
+// streamfunction of layer z at half-plane entry (l,k):  ph = a[z][0] qh0 + a[z][1] qh1   (pyqg _invert)
+QGB_HD cplx half_ph(const Ctx& c, const cplx* qh, int z, int idx) {
+  const int NN = c.T.N * c.T.NK;
+  const cplx q0 = qh[idx], q1 = qh[NN + idx];
+  const double a0 = c.T.a[(2 * z) * NN + idx], a1 = c.T.a[(2 * z + 1) * NN + idx];
+  return cmake(a0 * q0.x + a1 * q1.x, a0 * q0.y + a1 * q1.y);
+}
+
+// uh = -il ph, vh = ik ph packed as uh + i vh at a half-plane entry
+QGB_HD void half_uv(const Ctx& c, const cplx* qh, int z, int l, int k, cplx& uh, cplx& vh) {
+  const cplx ph = half_ph(c, qh, z, l * c.T.NK + k);
+  const double lv = c.T.lv[l], kv = c.T.kv[k];
+  uh = cmake(lv * ph.y, -lv * ph.x);
+  vh = cmake(-kv * ph.y, kv * ph.x);
+}
+
+// Fill the buffer with E(A') + i E(B') where A,B are two half-plane spectra given by ``get(l,k,A,B)``,
+// ' symmetrises the self-conjugate columns k=0,N/2 (what a c2r transform does implicitly by dropping the
+// imaginary part there) and E is the Hermitian extension to the full plane.
+template <class Get>
+QGB_HD void build_packed(const Ctx& c, Get get, int tid, int nt) {
+  const int N = c.T.N, P = c.T.P, H = N / 2;
+  for (int i = tid; i < N * N; i += nt) {
+    const int l = i / N, k = i - l * N;
+    const int lm = l == 0 ? 0 : N - l;
+    cplx A, B;
+    if (k <= H) {
+      get(l, k, A, B);
+      if (k == 0 || k == H) {
+        cplx A2, B2;
+        get(lm, k, A2, B2);
+        A = cmake(0.5 * (A.x + A2.x), 0.5 * (A.y - A2.y));
+        B = cmake(0.5 * (B.x + B2.x), 0.5 * (B.y - B2.y));
+      }
+    } else {
+      get(lm, N - k, A, B);
+      A = cconj(A);
+      B = cconj(B);
+    }
+    c.buf[c.pos[l] * P + c.pos[k]] = cmake(A.x - B.y, A.y + B.x);
+  }
+}
+
+struct GetUV {
+  const Ctx& c; const cplx* qh; int z;
+  QGB_HD void operator()(int l, int k, cplx& A, cplx& B) const { half_uv(c, qh, z, l, k, A, B); }
+};
+struct GetQ {
+  const Ctx& c; const cplx* qh;
+  QGB_HD void operator()(int l, int k, cplx& A, cplx& B) const {
+    const int idx = l * c.T.NK + k;
+    A = qh[idx];
+    B = qh[c.T.N * c.T.NK + idx];
+  }
+};
+struct GetP {
+  const Ctx& c; const cplx* qh;
+  QGB_HD void operator()(int l, int k, cplx& A, cplx& B) const {
+    const int idx = l * c.T.NK + k;
+    A = half_ph(c, qh, 0, idx);
+    B = half_ph(c, qh, 1, idx);
+  }
+};
+
+QGB_HD const cplx* member_qh(const Ctx& c) { return c.io.qh + (long long)c.member * 2 * c.T.N * c.T.NK; }
+
+QGB_HD void ph_build_uv(const Ctx& c, int z, int tid, int nt) {
+  GetUV g{c, member_qh(c), z};
+  build_packed(c, g, tid, nt);
+}
+QGB_HD void ph_build_q(const Ctx& c, int tid, int nt) {
+  GetQ g{c, member_qh(c)};
+  build_packed(c, g, tid, nt);
+}
+QGB_HD void ph_build_p(const Ctx& c, int tid, int nt) {
+  GetP g{c, member_qh(c)};
+  build_packed(c, g, tid, nt);
+}
+
+// buf = (u + Ubg) q + i v q        (pyqg _do_advection, physical-space products)
+QGB_HD void ph_products(const Ctx& c, int z, int tid, int nt) {
+  const int N = c.T.N, P = c.T.P;
+  const double* q = c.io.q + ((long long)c.member * 2 + z) * N * N;
+  const double s = c.T.inv_M, U = c.T.Ubg[z];
+  for (int i = tid; i < N * N; i += nt) {
+    const int y = i / N, x = i - y * N;
+    cplx w = c.buf[y * P + x];
+    const double qq = q[i];
+    c.buf[y * P + x] = cmake((w.x * s + U) * qq, (w.y * s) * qq);
+  }
+}
+
+// split a packed forward transform W = FFT(a + i b) into the two half-plane spectra
+QGB_HD void unpack_pair(const Ctx& c, int l, int k, cplx& A, cplx& B) {
+  const int N = c.T.N, P = c.T.P;
+  const int lm = l == 0 ? 0 : N - l, km = k == 0 ? 0 : N - k;
+  const cplx w1 = c.buf[c.pos[l] * P + c.pos[k]];
+  const cplx w2 = c.buf[c.pos[lm] * P + c.pos[km]];
+  A = cmake(0.5 * (w1.x + w2.x), 0.5 * (w1.y - w2.y));
+  B = cmake(0.5 * (w1.y + w2.y), -0.5 * (w1.x - w2.x));
+}
+
+// dqhdt_z = -(ik uqh + il vqh + ikQy ph) (+ rek wv2 ph for the bottom layer) -> d_cur
+QGB_HD void ph_tendency(const Ctx& c, int z, int tid, int nt) {
+  const int N = c.T.N, NK = c.T.NK;
+  const cplx* qh = member_qh(c);
+  cplx* d = c.io.d_cur + ((long long)c.member * 2 + z) * N * NK;
+  for (int i = tid; i < N * NK; i += nt) {
+    const int l = i / NK, k = i - l * NK;
+    cplx uqh, vqh;
+    unpack_pair(c, l, k, uqh, vqh);
+    const cplx ph = half_ph(c, qh, z, i);
+    const double kv = c.T.kv[k], lv = c.T.lv[l];
+    const cplx t1 = cmuli(uqh, kv), t2 = cmuli(vqh, lv), t3 = cmuli(ph, kv * c.T.Qy[z]);
+    cplx r = cmake(-(t1.x + t2.x + t3.x), -(t1.y + t2.y + t3.y));
+    if (z == 1 && c.T.rek != 0.0) {
+      const double f = c.T.rek * (kv * kv + lv * lv);
+      r.x += f * ph.x;
+      r.y += f * ph.y;
+    }
+    d[i] = r;
+  }
+}
+
+// buf = dq1 + i dq2
+QGB_HD void ph_load_pair(const Ctx& c, const double* f, int tid, int nt) {
+  const int N = c.T.N, P = c.T.P;
+  const double* f0 = f + (long long)c.member * 2 * N * N;
+  const double* f1 = f0 + N * N;
+  for (int i = tid; i < N * N; i += nt) {
+    const int y = i / N, x = i - y * N;
+    c.buf[y * P + x] = cmake(f0[i], f1[i]);
+  }
+}
+
+// (+ rfft2(dq) with its mean removed) ; Adams-Bashforth update with the exponential filter
+QGB_HD void ph_update(const Ctx& c, bool has_dq, bool demean, int tid, int nt) {
+  const int N = c.T.N, NK = c.T.NK, NN = N * NK;
+  const long long mo = (long long)c.member * 2 * NN;
+  cplx* qh = c.io.qh + mo;
+  cplx* d = c.io.d_cur + mo;
+  const cplx* dp = c.io.d_p + mo;
+  const cplx* dpp = c.io.d_pp + mo;
+  const double dt1 = c.io.dt1, dt2 = c.io.dt2, dt3 = c.io.dt3;
+  for (int i = tid; i < NN; i += nt) {
+    cplx f0 = cmake(0, 0), f1 = cmake(0, 0);
+    if (has_dq && !(demean && i == 0)) {
+      const int l = i / NK, k = i - l * NK;
+      unpack_pair(c, l, k, f0, f1);
+    }
+    const double fl = c.T.filtr[i];
+    for (int z = 0; z < 2; ++z) {
+      const cplx f = z == 0 ? f0 : f1;
+      const int j = z * NN + i;
+      const cplx dd = cadd(d[j], f);
+      d[j] = dd;
+      const cplx q0 = qh[j], a = dp[j], b = dpp[j];
+      qh[j] = cmake(fl * (q0.x + dt1 * dd.x + dt2 * a.x + dt3 * b.x), fl * (q0.y + dt1 * dd.y + dt2 * a.y + dt3 * b.y));
+    }
+  }
+}
+
+// q = irfft2(qh) (real/imag of the packed inverse), also emits the fp32 normalised closure input
+QGB_HD void ph_emit_q(const Ctx& c, int tid, int nt) {
+  const int N = c.T.N, P = c.T.P;
+  double* q = c.io.q + (long long)c.member * 2 * N * N;
+  const double s = c.T.inv_M;
+  float* x = c.io.cnn_x ? c.io.cnn_x + (long long)c.member * c.io.cnn_mstride : nullptr;
+  for (int i = tid; i < N * N; i += nt) {
+    const int y = i / N, xx = i - y * N;
+    const cplx w = c.buf[y * P + xx];
+    const double q0 = w.x * s, q1 = w.y * s;
+    q[i] = q0;
+    q[N * N + i] = q1;
+    if (x) {  // x_scale.normalize(m.q.astype('float32'))  (models/cgan_regression.py:158)
+      x[i] = (float)q0 / c.io.x_std[0];
+      x[N * N + i] = (float)q1 / c.io.x_std[1];
+    }
+  }
+}
+
+// closure input from the current q without touching the spectral state
+QGB_HD void ph_emit_x_only(const Ctx& c, int tid, int nt) {
+  const int N = c.T.N;
+  const double* q = c.io.q + (long long)c.member * 2 * N * N;
+  float* x = c.io.cnn_x + (long long)c.member * c.io.cnn_mstride;
+  for (int i = tid; i < 2 * N * N; i += nt) x[i] = (float)q[i] / c.io.x_std[i / (N * N)];
+}
+
+// qh = rfft2(q) from the packed forward transform (pyqg ``q`` setter)
+QGB_HD void ph_store_qh(const Ctx& c, int tid, int nt) {
+  const int N = c.T.N, NK = c.T.NK, NN = N * NK;
+  cplx* qh = c.io.qh + (long long)c.member * 2 * NN;
+  for (int i = tid; i < NN; i += nt) {
+    const int l = i / NK, k = i - l * NK;
+    cplx a, b;
+    unpack_pair(c, l, k, a, b);
+    qh[i] = a;
+    qh[NN + i] = b;
+  }
+}
+
+QGB_HD void ph_store_uv(const Ctx& c, int z, int tid, int nt) {
+  const int N = c.T.N, P = c.T.P;
+  const long long o = ((long long)c.member * 2 + z) * N * N;
+  const double s = c.T.inv_M;
+  for (int i = tid; i < N * N; i += nt) {
+    const int y = i / N, x = i - y * N;
+    const cplx w = c.buf[y * P + x];
+    if (c.io.u_out) c.io.u_out[o + i] = w.x * s;
+    if (c.io.v_out) c.io.v_out[o + i] = w.y * s;
+  }
+}
+
+QGB_HD void ph_store_ph(const Ctx& c, int tid, int nt) {
+  const int NN = c.T.N * c.T.NK;
+  const cplx* qh = member_qh(c);
+  cplx* out = c.io.ph_out + (long long)c.member * 2 * NN;
+  for (int i = tid; i < NN; i += nt) {
+    out[i] = half_ph(c, qh, 0, i);
+    out[NN + i] = half_ph(c, qh, 1, i);
+  }
+}
+
+QGB_HD void ph_store_p(const Ctx& c, int tid, int nt) {
+  const int N = c.T.N, P = c.T.P;
+  double* p = c.io.p_out + (long long)c.member * 2 * N * N;
+  const double s = c.T.inv_M;
+  for (int i = tid; i < N * N; i += nt) {
+    const int y = i / N, x = i - y * N;
+    const cplx w = c.buf[y * P + x];
+    p[i] = w.x * s;
+    p[N * N + i] = w.y * s;
+  }
+}
+
+// diagnostics partials: red[0*nt+tid] ke, [1] max|u+U|, [2] max|v|, [3] non-finite count
+QGB_HD void ph_red_clear(const Ctx& c, int tid, int nt) {
+  for (int j = 0; j < 4; ++j) c.red[j * nt + tid] = 0.0;
+}
+QGB_HD void ph_red_ke(const Ctx& c, int tid, int nt) {  // pyqg _calc_ke via spec_var(wv*ph)
+  const int N = c.T.N, NK = c.T.NK, NN = N * NK;
+  const cplx* qh = member_qh(c);
+  double acc = 0.0, bad = 0.0;
+  for (int i = tid; i < NN; i += nt) {
+    const int l = i / NK, k = i - l * NK;
+    const double wv2 = c.T.kv[k] * c.T.kv[k] + c.T.lv[l] * c.T.lv[l];
+    const double wgt = (k == 0 || k == NK - 1) ? 1.0 : 2.0;
+    for (int z = 0; z < 2; ++z) {
+      const cplx ph = half_ph(c, qh, z, i);
+      acc += 0.5 * c.io.Hi_over_H[z] * wgt * wv2 * (ph.x * ph.x + ph.y * ph.y);
+      const cplx qq = qh[z * NN + i];
+      if (!(fabs(qq.x) < 1e300) || !(fabs(qq.y) < 1e300)) bad += 1.0;
+    }
+  }
+  c.red[0 * nt + tid] += acc * c.T.inv_M * c.T.inv_M;
+  c.red[3 * nt + tid] += bad;
+}
+QGB_HD void ph_red_uv(const Ctx& c, int z, int tid, int nt) {  // pyqg _calc_cfl numerator
+  const int N = c.T.N, P = c.T.P;
+  const double s = c.T.inv_M, U = c.T.Ubg[z];
+  double mu = c.red[1 * nt + tid], mv = c.red[2 * nt + tid];
+  for (int i = tid; i < N * N; i += nt) {
+    const int y = i / N, x = i - y * N;
+    const cplx w = c.buf[y * P + x];
+    mu = fmax(mu, fabs(w.x * s + U));
+    mv = fmax(mv, fabs(w.y * s));
+  }
+  c.red[1 * nt + tid] = mu;
+  c.red[2 * nt + tid] = mv;
+}
+QGB_HD void ph_red_final(const Ctx& c, int tid, int nt) {
+  if (tid != 0) return;
+  double ke = 0, mu = 0, mv = 0, bad = 0;
+  for (int t = 0; t < nt; ++t) {
+    ke += c.red[t];
+    mu = fmax(mu, c.red[nt + t]);
+    mv = fmax(mv, c.red[2 * nt + t]);
+    bad += c.red[3 * nt + t];
+  }
+  double* o = c.io.red_out + (long long)c.member * 4;
+  o[0] = ke; o[1] = mu; o[2] = mv; o[3] = bad;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// programs: ordered phase lists.  ``phase`` selects which phase runs; returns the number of phases.
+// ------------------------------------------------------------------------------------------------------
+// PROG_STEP_DQ removes the mean of dq (closure output, models/parameterization.py:25); PROG_STEP_DQ_RAW adds dq as given
+enum Program { PROG_STEP = 0, PROG_STEP_DQ = 1, PROG_SET_Q = 2, PROG_INVERT = 3, PROG_DIAG = 4, PROG_EMIT_X = 5, PROG_STEP_DQ_RAW = 6 };
+
+#define QGB_RUN(stmt)        \
+  do {                       \
+    if (_n == phase) { stmt; } \
+    ++_n;                    \
+  } while (0)
+#define QGB_FFT(inv)                                                    \
+  do {                                                                  \
+    for (int _f = 0; _f < F; ++_f) QGB_RUN(fft2d_phase(c, _f, inv, tid, nt)); \
+  } while (0)
+
+QGB_HD int run_program(const Ctx& c, int prog, int phase, int tid, int nt) {
+  int _n = 0;
+  const int F = fft2d_phases(c.T);
+  QGB_RUN(ph_init(c, tid, nt));
+  const bool with_dq = prog == PROG_STEP_DQ || prog == PROG_STEP_DQ_RAW;
+  if (prog == PROG_STEP || with_dq) {
+    for (int z = 0; z < 2; ++z) {
+      QGB_RUN(ph_build_uv(c, z, tid, nt));
+      QGB_FFT(true);
+      QGB_RUN(ph_products(c, z, tid, nt));
+      QGB_FFT(false);
+      QGB_RUN(ph_tendency(c, z, tid, nt));
+    }
+    if (with_dq) {
+      QGB_RUN(ph_load_pair(c, c.io.dq, tid, nt));
+      QGB_FFT(false);
+    }
+    QGB_RUN(ph_update(c, with_dq, prog == PROG_STEP_DQ, tid, nt));
+    QGB_RUN(ph_build_q(c, tid, nt));
+    QGB_FFT(true);
+    QGB_RUN(ph_emit_q(c, tid, nt));
+  } else if (prog == PROG_SET_Q) {
+    QGB_RUN(ph_load_pair(c, c.io.q, tid, nt));
+    QGB_FFT(false);
+    QGB_RUN(ph_store_qh(c, tid, nt));
+    if (c.io.cnn_x) QGB_RUN(ph_emit_x_only(c, tid, nt));
+  } else if (prog == PROG_INVERT) {
+    if (c.io.ph_out) QGB_RUN(ph_store_ph(c, tid, nt));
+    for (int z = 0; z < 2; ++z) {
+      QGB_RUN(ph_build_uv(c, z, tid, nt));
+      QGB_FFT(true);
+      QGB_RUN(ph_store_uv(c, z, tid, nt));
+    }
+    if (c.io.p_out) {
+      QGB_RUN(ph_build_p(c, tid, nt));
+      QGB_FFT(true);
+      QGB_RUN(ph_store_p(c, tid, nt));
+    }
+  } else if (prog == PROG_DIAG) {
+    QGB_RUN(ph_red_clear(c, tid, nt));
+    QGB_RUN(ph_red_ke(c, tid, nt));
+    for (int z = 0; z < 2; ++z) {
+      QGB_RUN(ph_build_uv(c, z, tid, nt));
+      QGB_FFT(true);
+      QGB_RUN(ph_red_uv(c, z, tid, nt));
+    }
+    QGB_RUN(ph_red_final(c, tid, nt));
+  } else if (prog == PROG_EMIT_X) {
+    QGB_RUN(ph_emit_x_only(c, tid, nt));
+  }
+  return _n;
+}
+
+// ---- host-side plan construction (shared by the library and the emulation) ---------------------------
+inline bool make_radix_plan(int N, int* radix, int* nstages) {
+  int n = N, s = 0;
+  while (n % 4 == 0 && s < kMaxStages) { radix[s++] = 4; n /= 4; }
+  while (n % 2 == 0 && s < kMaxStages) { radix[s++] = 2; n /= 2; }
+  while (n % 3 == 0 && s < kMaxStages) { radix[s++] = 3; n /= 3; }
+  *nstages = s;
+  return n == 1;
+}
+
+// position of frequency f after the in-place forward transform
+inline int pos_of_freq(int N, const int* radix, int nstages, int f) {
+  int pos = 0, span = N;
+  for (int s = 0; s < nstages; ++s) {
+    span /= radix[s];
+    pos += (f % radix[s]) * span;
+    f /= radix[s];
+  }
+  return pos;
+}
+
+}  // namespace qgb

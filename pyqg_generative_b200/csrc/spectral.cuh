@@ -1,0 +1,76 @@
+// spectral.cuh -- sm_100a kernels wrapping the per-member phase programs of qg_core.cuh.
+// One CTA owns one ensemble member for the whole program; the packed complex field (N x (N+1) complex128) stays in
+// shared memory between phases (N=64: 66.5 KB -> 3 CTAs/SM; N=96: 149 KB -> 1 CTA/SM).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "qg_core.cuh"
+
+namespace qgb {
+
+inline size_t program_smem_bytes(int N, int P, int nthreads) {
+  size_t b = (size_t)N * P * sizeof(cplx);  // buf
+  b += (size_t)N * sizeof(cplx);            // twiddles
+  b += ((size_t)N * sizeof(short) + 15) / 16 * 16;
+  b += 4 * (size_t)nthreads * sizeof(double);  // reduction scratch
+  return b;
+}
+
+__global__ void __launch_bounds__(512) qg_program_kernel(const __grid_constant__ Tables T,
+                                                         const __grid_constant__ StepIO io, int prog, int members) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx* buf = reinterpret_cast<cplx*>(smem_raw);
+  cplx* tw = buf + (size_t)T.N * T.P;
+  short* pos = reinterpret_cast<short*>(tw + T.N);
+  double* red = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(pos) + ((size_t)T.N * sizeof(short) + 15) / 16 * 16);
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int m = blockIdx.x; m < members; m += gridDim.x) {
+    Ctx c{T, io, buf, tw, pos, red, m};
+    const int nph = run_program(c, prog, -1, tid, nt);
+    for (int ph = 0; ph < nph; ++ph) {
+      run_program(c, prog, ph, tid, nt);
+      __syncthreads();
+    }
+  }
+}
+
+// ke / cfl / flags from the per-member reduction record written by PROG_DIAG
+__global__ void diag_finish_kernel(const double* __restrict__ red, int members, double dt_over_dx, double* ke,
+                                   double* cfl, int* flags) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= members) return;
+  const double k = red[4 * m], c = fmax(red[4 * m + 1], red[4 * m + 2]) * dt_over_dx;
+  if (ke) ke[m] = k;
+  if (cfl) cfl[m] = c;
+  if (flags) {
+    int f = 0;
+    if (red[4 * m + 3] != 0.0 || !(k == k) || !(c == c)) f |= 1;
+    if (!(c < 1.0)) f |= 2;
+    flags[m] = f;
+  }
+}
+
+// pyqg diagnostics KEspec = wv2 |ph|^2 / M^2, Ensspec = |qh|^2 / M^2, summed over the local members
+__global__ void spectra_kernel(const __grid_constant__ Tables T, const cplx* __restrict__ qh, int members,
+                               double* __restrict__ kespec, double* __restrict__ ensspec) {
+  const int NN = T.N * T.NK;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * NN) return;
+  const int z = i / NN, idx = i - z * NN;
+  const int l = idx / T.NK, k = idx - l * T.NK;
+  const double wv2 = T.kv[k] * T.kv[k] + T.lv[l] * T.lv[l];
+  const double a0 = T.a[(2 * z) * NN + idx], a1 = T.a[(2 * z + 1) * NN + idx];
+  double ke = 0.0, en = 0.0;
+  for (int m = 0; m < members; ++m) {
+    const cplx q0 = qh[(long long)m * 2 * NN + idx], q1 = qh[(long long)m * 2 * NN + NN + idx];
+    const double px = a0 * q0.x + a1 * q1.x, py = a0 * q0.y + a1 * q1.y;
+    ke += wv2 * (px * px + py * py);
+    const cplx qq = z == 0 ? q0 : q1;
+    en += qq.x * qq.x + qq.y * qq.y;
+  }
+  const double s = T.inv_M * T.inv_M;
+  if (kespec) kespec[i] = ke * s;
+  if (ensspec) ensspec[i] = en * s;
+}
+
+}  // namespace qgb

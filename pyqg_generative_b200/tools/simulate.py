@@ -1,0 +1,183 @@
+"""Driver entry points of pyqg_generative/tools/simulate.py for the batched GPU engine.
+
+``run_simulation(pyqg_params, parameterization, q_init, sampling_freq)`` (:108-145) and
+``set_initial_condition(m)`` (:147-168) keep the reference signatures; ``pyqg_params`` may additionally carry
+``members`` (ensemble size on this GPU), ``member_offset``, ``device``, ``precision`` and ``seed``.
+xarray / NetCDF export (to_dataset, drop_vars, concat_in_time :16-60) is a "next" row: snapshots
+are returned as a dict of numpy arrays with the same variable names and a leading ``run`` axis, float32 like
+``drop_vars`` produces, and become an xarray.Dataset when xarray is importable.
+"""
+import json
+import os
+
+import numpy as np
+
+from .parameters import ANDREW_1000_STEPS, DAY
+from .stochastic_pyqg import EnsembleQGModel, stochastic_QGModel
+
+
+def set_initial_condition(m, rng=None):
+    """JAMES-paper initial condition (:147-168), drawn independently for every member."""
+    rng = np.random if rng is None else rng
+    B = m.members
+    q2d = 1e-7 * rng.rand(B, m.ny, m.nx)
+    q2d -= q2d.mean(axis=(-2, -1), keepdims=True)
+    q2d *= np.sqrt(m.nx * m.ny / 64 ** 2)
+    q1d = 1e-6 * (np.ones((1, m.ny, 1)) * rng.rand(B, 1, m.nx))
+    q1d -= q1d.mean(axis=(-2, -1), keepdims=True)
+    q1d *= np.sqrt(m.nx / 64)
+    noise = q1d + q2d
+    Xf = np.fft.rfftn(noise, axes=(-2, -1))
+    noise = np.fft.irfftn(Xf * (m.wv < np.pi / (m.L / 32)), axes=(-2, -1))
+    m.set_q(np.stack([noise, np.zeros_like(noise)], axis=1))
+    m._invert()
+
+
+def snapshot(m):
+    """The physical-space variables ``drop_vars(m.to_dataset())`` keeps (:16-36), float32, shape (run,lev,y,x)."""
+    m._invert()
+    return dict(q=np.asarray(m.q, 'float32'), u=np.asarray(m.u, 'float32'), v=np.asarray(m.v, 'float32'),
+                psi=np.asarray(m.p, 'float32'), time=np.float64(m.t / 86400.))
+
+
+def concat_in_time(snaps):
+    out = {k: np.stack([s[k] for s in snaps], axis=1 if np.ndim(snaps[0][k]) else 0) for k in ('q', 'u', 'v', 'psi')}
+    out['time'] = np.array([s['time'] for s in snaps])
+    return out
+
+
+def to_xarray(d, attrs=None):
+    """dict from ``run_simulation`` -> xarray.Dataset with dims (run,time,lev,y,x) if xarray is installed."""
+    try:
+        import xarray as xr
+    except ImportError:
+        return d
+    ds = xr.Dataset({k: xr.DataArray(d[k], dims=['run', 'time', 'lev', 'y', 'x']) for k in ('q', 'u', 'v', 'psi')})
+    ds['time'] = xr.DataArray(d['time'], dims=['time'], attrs={'units': 'days'})
+    for k in ('KEspec', 'Ensspec'):
+        if k in d:
+            ds[k] = xr.DataArray(d[k], dims=['lev', 'l', 'k'])
+    ds.attrs.update(attrs or {})
+    return ds
+
+
+def run_simulation(pyqg_params, parameterization=None, q_init=None, sampling_freq=ANDREW_1000_STEPS, rng=None):
+    """Reference :108-145.  ``parameterization`` = dict(self=closure, sampling='AR1'|'constant'|'deterministic', nsteps=int)."""
+    pyqg_params = dict(pyqg_params)
+    pyqg_params['tmax'] = float(pyqg_params['tmax'])
+    if parameterization is None:
+        m = EnsembleQGModel(**pyqg_params)
+    else:
+        params = dict(pyqg_params)
+        params['parameterization'] = parameterization['self']
+        m = stochastic_QGModel(params, parameterization['sampling'], parameterization['nsteps'])
+        m.squeeze = False
+    set_initial_condition(m, rng)
+    snaps = []
+    if q_init is not None:
+        m.set_q(np.asarray(q_init, dtype='float64'))
+        m._invert()
+        snaps.append(snapshot(m))
+    for t in m.run_with_snapshots(tsnapint=sampling_freq):
+        snaps.append(snapshot(m))
+    ds = concat_in_time(snaps)
+    ke, en, count = m.spectra_sums()
+    if count:
+        ds['KEspec'], ds['Ensspec'] = ke / count, en / count
+    ds['attrs'] = {'pyqg_params': str(pyqg_params)}
+    ds['model'] = m
+    return ds
+
+
+def generate_subgrid_forcing(Nc, pyqg_params, sampling_freq=ANDREW_1000_STEPS, operators=None, dealias='none', rng=None):
+    """Reference :62-106: run a hi-res ensemble and coarse-grain every ``sampling_freq`` seconds.
+    Returns {'<Operator>-<nc>': dict(q_forcing_advection, q, u, v, psi, time)} with float32 arrays (run,time,lev,y,x)."""
+    from . import operators as ops
+    if operators is None:
+        operators = [ops.Operator1, ops.Operator2]
+    pyqg_params = dict(pyqg_params)
+    pyqg_params['tmax'] = float(pyqg_params['tmax'])
+    m = EnsembleQGModel(**pyqg_params)
+    set_initial_condition(m, rng)
+    out = {}
+    phys = {k: pyqg_params[k] for k in ('rek', 'delta', 'beta', 'rd', 'H1', 'U1', 'U2', 'L', 'filterfac') if k in pyqg_params}
+    for t in m.run_with_snapshots(tsnapint=sampling_freq):
+        qdns = m.device_q()
+        for op in operators:
+            for nc in Nc:
+                forcing, mf = ops.PV_subgrid_forcing(qdns, nc, op, phys, dealias, return_fields=True)
+                rec = dict(q_forcing_advection=forcing, q=mf['q'], u=mf['u'], v=mf['v'], psi=mf['psi'])
+                rec = {k: np.asarray(v, 'float32') for k, v in rec.items()}
+                rec['time'] = m.t / 86400.
+                out.setdefault('%s-%d' % (op.__name__, nc), []).append(rec)
+    for key, recs in out.items():
+        d = {k: np.stack([r[k] for r in recs], axis=1) for k in ('q_forcing_advection', 'q', 'u', 'v', 'psi')}
+        d['time'] = np.array([r['time'] for r in recs])
+        d['attrs'] = {'pyqg_params': str(pyqg_params)}
+        out[key] = d
+    return out
+
+
+def _load_model(folder='model'):
+    from ..models.cgan_regression import CGANRegression
+    from ..models.cvae_regression import CVAERegression
+    from ..models.mean_var_model import MeanVarModel
+    from ..models.ols_model import OLSModel
+    classes = dict(CGANRegression=CGANRegression, CVAERegression=CVAERegression, MeanVarModel=MeanVarModel,
+                   OLSModel=OLSModel)
+    with open(os.path.join(folder, 'model_args.json')) as f:
+        model_args = json.load(f)
+    name = model_args.pop('model')
+    if name not in classes:
+        raise ValueError('model %s is not on the accelerated path' % name)
+    model_args.setdefault('folder', folder)
+    return classes[name](**model_args)
+
+
+def main(argv=None):
+    """CLI with the flags of the reference ``simulate.py`` (:175-189) that lie on the accelerated path."""
+    import argparse
+    import ast
+    p = argparse.ArgumentParser()
+    p.add_argument('--pyqg_params', type=str, default=str({}))
+    p.add_argument('--ensemble_member', type=int, default=0)
+    p.add_argument('--members', type=int, default=1, help='ensemble members integrated together on this GPU')
+    p.add_argument('--forcing', type=str, default='no')
+    p.add_argument('--sampling_freq', type=int, default=ANDREW_1000_STEPS)
+    p.add_argument('--reference', type=str, default='no')
+    p.add_argument('--parameterization', type=str, default='no')
+    p.add_argument('--subfolder', type=str, default='')
+    p.add_argument('--sampling', type=str, default='AR1')
+    p.add_argument('--nsteps', type=int, default=1)
+    p.add_argument('--model_weight', type=float, default=1.0)
+    p.add_argument('--model_folder', type=str, default='model')
+    p.add_argument('--precision', type=str, default='fp32')
+    args = p.parse_args(argv)
+    params = dict(ast.literal_eval(args.pyqg_params))
+    params.setdefault('members', args.members)
+    params.setdefault('member_offset', args.ensemble_member)
+    if args.subfolder:
+        os.makedirs(args.subfolder, exist_ok=True)
+
+    def save(ds, path):
+        ds = {k: v for k, v in ds.items() if isinstance(v, np.ndarray)}
+        np.savez_compressed(path, **ds)
+
+    if args.forcing == 'yes':
+        out = generate_subgrid_forcing([32, 48, 64, 96, 128], params, args.sampling_freq)
+        for key, ds in out.items():
+            os.makedirs(key, exist_ok=True)
+            save(ds, os.path.join(key, '%d.npz' % args.ensemble_member))
+    if args.reference == 'yes':
+        save(run_simulation(params, sampling_freq=args.sampling_freq),
+             os.path.join(args.subfolder, '%d.npz' % args.ensemble_member))
+    if args.parameterization == 'yes':
+        params['precision'] = args.precision
+        model = args.model_weight * _load_model(args.model_folder)
+        par = dict(self=model, sampling=args.sampling, nsteps=args.nsteps)
+        save(run_simulation(params, par, sampling_freq=args.sampling_freq),
+             os.path.join(args.subfolder, '%d.npz' % args.ensemble_member))
+
+
+if __name__ == '__main__':
+    main()

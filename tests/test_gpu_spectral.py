@@ -1,0 +1,156 @@
+"""GPU parity of the fused spectral step (csrc/qg_core.cuh + spectral.cuh) against the oracle, through the C ABI.
+Tolerance: BASELINE.json north_star -- spectral-state relative error <= 1e-10 per step in fp64."""
+import numpy as np
+import pytest
+
+from oracle import operators_ref as opr
+from oracle import pyqg_shim
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def rel(a, b):
+    return np.abs(a - b).max() / np.abs(b).max()
+
+
+def make(nx, members, **kw):
+    from pyqg_generative_b200.tools.stochastic_pyqg import EnsembleQGModel
+    kw.setdefault('log_level', 0)
+    return EnsembleQGModel(members=members, nx=nx, **kw)
+
+
+@pytest.mark.parametrize('N,dt,phys', [
+    (64, 14400., {}), (48, 14400., dict(rek=7e-8, delta=0.1, beta=1e-11)), (96, 7200., {}), (32, 14400., {})])
+def test_set_q_invert_and_steps_match_oracle(N, dt, phys):
+    rng = np.random.RandomState(N)
+    B = 3
+    m = make(N, B, dt=dt, **phys)
+    q0 = rng.randn(B, 2, N, N) * np.array([7e-6, 1e-6])[None, :, None, None]   # white noise: full Nyquist content
+    m.q = q0
+    refs = []
+    for b in range(B):
+        o = pyqg_shim.QGModel(nx=N, dt=dt, log_level=0, **phys)
+        o.q = q0[b]
+        o._invert()
+        o._calc_derived_fields()
+        refs.append(o)
+    assert np.array_equal(m.q, q0)                      # q setter round trip is exact (notebook 3-2-dealiasing:88)
+    m._invert()
+    qh, ph, u, v, p = m.qh, m.ph, m.u, m.v, m.p
+    for b, o in enumerate(refs):
+        assert rel(qh[b], o.qh) < TOL and rel(ph[b], o.ph) < TOL
+        assert rel(u[b], o.u) < TOL and rel(v[b], o.v) < TOL and rel(p[b], o.p) < TOL
+    for step in range(5):                               # Euler, AB2, AB3, AB3, AB3
+        m._step_forward()
+        q, qh, d = m.q, m.qh, m.dqhdt
+        for b, o in enumerate(refs):
+            o._step_forward()
+            assert rel(q[b], o.q) < TOL and rel(qh[b], o.qh) < TOL and rel(d[b], o.dqhdt_p) < TOL, (step, b)
+    assert m.tc == 5 and abs(m.t - 5 * dt) < 1e-6
+    ke, cfl, flags = m.diagnostics()
+    for b, o in enumerate(refs):
+        o._invert()
+        assert abs(ke[b] - o._calc_ke()) < 1e-10 * o._calc_ke() and abs(cfl[b] - o._calc_cfl()) < 1e-10
+    assert not flags.any()
+
+
+def test_many_steps_in_one_call_equal_single_steps_and_oracle_ke():
+    """1500 free-running steps from the JAMES initial condition: the linear-instability phase is not chaotic yet
+    (SURVEY.md section 7 'Chaos'), so the state itself must still agree with the oracle."""
+    N, dt = 64, 14400.
+    np.random.seed(5)
+    o = pyqg_shim.QGModel(nx=N, dt=dt, log_level=0)
+    opr.set_initial_condition(o)
+    m = make(N, 2, dt=dt)
+    m.q = o.q
+    m._step_forward(1500)
+    for _ in range(1500):
+        o._step_forward()
+    assert m.tc == 1500
+    q = m.q
+    assert np.array_equal(q[0], q[1])
+    assert rel(q[0], o.q) < 1e-8
+    o._invert()
+    assert abs(m.diagnostics()[0][0] - o._calc_ke()) < 1e-9 * o._calc_ke()
+
+
+def test_host_callback_parameterization_and_weighting():
+    from pyqg_generative_b200.models.parameterization import QParameterization
+    N, dt = 32, 14400.
+    rng = np.random.RandomState(2)
+    dq = rng.randn(2, N, N) * 1e-12 + 2e-12
+
+    class Const(QParameterization):
+        def __call__(self, mm):
+            assert np.asarray(mm.q).shape[-3:] == (2, N, N)
+            return dq
+    q0 = rng.randn(2, N, N) * 1e-6
+    m = make(N, 2, dt=dt, parameterization=0.5 * Const())
+    m.q = q0
+    o = pyqg_shim.QGModel(nx=N, dt=dt, log_level=0, parameterization=0.5 * _OracleConst(dq))
+    o.q = q0
+    for _ in range(3):
+        m._step_forward()
+        o._step_forward()
+    assert rel(m.q[1], o.q) < TOL
+
+
+class _OracleConst(pyqg_shim.QParameterization):
+    def __init__(self, dq):
+        self.dq = dq
+
+    def __call__(self, m):
+        return self.dq
+
+
+def test_run_with_snapshots_cadence_and_log():
+    N, dt = 32, 14400.
+    m = make(N, 2, dt=dt, tmax=40 * dt, twrite=10, log_level=1, tavestart=20 * dt, taveint=5 * dt)
+    np.random.seed(0)
+    from pyqg_generative_b200.tools.simulate import set_initial_condition
+    set_initial_condition(m)
+    times = [t for t in m.run_with_snapshots(tsnapint=8 * dt)]
+    assert np.allclose(times, [8 * dt * i for i in range(1, 6)])
+    assert [s for s, _, _, _ in m.log] == [10, 20, 30, 40]
+    ke, en, count = m.spectra_sums()
+    assert count == 2 * 5 and ke.shape == (2, N, N // 2 + 1) and (ke >= 0).all()
+    kespec = 0
+    for b in range(2):
+        o = pyqg_shim.QGModel(nx=N, dt=dt, log_level=0)
+        o.q = m.q[b]
+        o._invert()
+        kespec = kespec + o.wv2 * np.abs(o.ph) ** 2 / o.M ** 2
+    from pyqg_generative_b200 import _lib
+    k1, e1 = np.empty(ke.size), np.empty(ke.size)
+    _lib.check(m._lib.qgb_diag_spectra(m._h, k1.ctypes.data, e1.ctypes.data, 0, m._stream()), m._h)
+    assert rel(k1.reshape(ke.shape), kespec) < 1e-10
+
+
+def test_blow_up_is_flagged_not_fatal():
+    N = 32
+    m = make(N, 3, dt=14400.)
+    q = np.random.RandomState(0).randn(3, 2, N, N) * 1e-6
+    q[1] *= 1e6            # absurd amplitude: CFL >> 1, goes non-finite within a few steps
+    m.q = q
+    m._step_forward(60)
+    ke, cfl, flags = m.diagnostics()
+    assert flags[1] != 0 and flags[0] == 0 and flags[2] == 0
+    assert np.isfinite(ke[0]) and np.isfinite(ke[2])
+
+
+def test_full_size_ensemble_members_are_independent_and_identical():
+    """BASELINE config size (1024 members at 64^2): replicated initial condition -> every member must produce the same
+    bits, and member 0 must match the oracle."""
+    N, dt, B = 64, 14400., 1024
+    np.random.seed(7)
+    o = pyqg_shim.QGModel(nx=N, dt=dt, log_level=0)
+    opr.set_initial_condition(o)
+    m = make(N, B, dt=dt)
+    m.q = o.q
+    m._step_forward(3)
+    for _ in range(3):
+        o._step_forward()
+    q = m.q
+    assert rel(q[0], o.q) < TOL
+    assert (q == q[0][None]).all()

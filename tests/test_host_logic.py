@@ -1,0 +1,116 @@
+"""Host-side logic that needs no GPU: configuration tables, samplers, weight packing (BatchNorm folding), sharding."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden, golden_state_dict
+from oracle import cnn_ref
+
+
+def test_parameters_match_reference_tables():
+    from pyqg_generative_b200.tools.parameters import EDDY_PARAMS, JET_PARAMS, ANDREW_1000_STEPS, YEAR
+    assert EDDY_PARAMS.nx(256)['dt'] == 3600 and EDDY_PARAMS.nx(96)['dt'] == 7200 and EDDY_PARAMS.nx(48)['dt'] == 14400
+    assert EDDY_PARAMS['nx'] == 64 and 'dt' in EDDY_PARAMS and EDDY_PARAMS['tmax'] == 10 * YEAR
+    assert JET_PARAMS['rek'] == 7e-08 and JET_PARAMS['delta'] == 0.1 and JET_PARAMS['beta'] == 1e-11
+    assert ANDREW_1000_STEPS == 3600000
+    p = EDDY_PARAMS.nx(48)._update({'tmax': 1.0})
+    assert p['tmax'] == 1.0 and EDDY_PARAMS['tmax'] != 1.0
+
+
+def test_samplers_reproduce_reference_sequences():
+    from pyqg_generative_b200.tools.stochastic_pyqg import AR1_sampler, constant_sampler
+    g = golden('samplers.npz')
+    for n in (1, 4, -1):
+        s, xi = AR1_sampler(n), list(g['ar1_%d_xi' % n])
+        for i in range(6):
+            assert s.update(lambda: xi[i]) is True
+            assert np.array_equal(s.noise, g['ar1_%d' % n][i])
+    for n in (1, 3):
+        s, rng = constant_sampler(n), np.random.RandomState(9)
+        flags = []
+        for i in range(8):
+            flags.append(s.update(lambda: rng.randn(3)))
+            assert np.array_equal(s.noise, g['const_%d' % n][i])
+        assert flags == list(g['const_%d_flags' % n])
+
+
+def test_unknown_sampling_type_raises_like_reference():
+    from pyqg_generative_b200.tools.stochastic_pyqg import stochastic_QGModel
+    with pytest.raises(ValueError, match='Unknown sampling type'):
+        stochastic_QGModel(dict(nx=64), 'bogus', 1)
+
+
+def test_state_dict_loading_and_batchnorm_folding():
+    from pyqg_generative_b200.tools.cnn_tools import AndrewCNN
+    sd, _, _ = golden_state_dict('weights_gan.npz')
+    net = AndrewCNN(4, 2)
+    assert net.load_state_dict(sd) == '<All keys matched successfully>'
+    assert sorted(net.state_dict()) == sorted(sd)
+    layers = net.layers()
+    assert [(L['cin'], L['cout'], L['ksize']) for L in layers] == \
+        [(4, 128, 5), (128, 64, 5), (64, 32, 3), (32, 32, 3), (32, 32, 3), (32, 32, 3), (32, 32, 3), (32, 2, 3)]
+    # the folded per-layer arithmetic reproduces the oracle network on CPU (pure torch check of the packing)
+    x = torch.randn(2, 4, 16, 16, generator=torch.Generator().manual_seed(0))
+    y = x
+    import torch.nn.functional as F
+    for L in layers:
+        p = L['ksize'] // 2
+        y = F.conv2d(F.pad(y, (p, p, p, p), mode='circular'), torch.as_tensor(L['weight']), torch.as_tensor(L['bias']))
+        if L['relu_bn']:
+            y = F.relu(y) * torch.as_tensor(L['bn_scale'])[None, :, None, None] + torch.as_tensor(L['bn_shift'])[None, :, None, None]
+    ref = cnn_ref.andrew_cnn_forward(sd, x)
+    assert (y - ref).abs().max() <= 2e-5 * ref.abs().max()
+    with pytest.raises(RuntimeError):
+        net.load_state_dict({'conv.0.weight': torch.zeros(1)})
+    with pytest.raises(NotImplementedError):
+        AndrewCNN(4, 2, div=True)
+
+
+def test_scaler_reads_reference_json(tmp_path):
+    from conftest import write_model_folder
+    from pyqg_generative_b200.tools.cnn_tools import ChannelwiseScaler
+    folder = write_model_folder(tmp_path, 'gan')
+    s = ChannelwiseScaler().read('x_scale.json', folder)
+    assert s.std.shape == (1, 2, 1, 1) and s.std.dtype == np.float32
+    assert np.allclose(s.std.ravel(), [7.784383e-06, 1.0471941e-06], rtol=1e-6)
+    X = np.ones((3, 2, 4, 4), 'float32')
+    assert np.allclose(s.denormalize(s.normalize(X)), X)
+    s.write('copy.json', folder)
+    assert np.array_equal(ChannelwiseScaler().read('copy.json', folder).std, s.std)
+
+
+def test_pyqg_parameterization_algebra():
+    from pyqg_generative_b200.models.parameterization import QParameterization, WeightedParameterization
+
+    class P(QParameterization):
+        def __call__(self, m):
+            return np.ones((2, 4, 4))
+    w = 0.5 * P()
+    assert isinstance(w, WeightedParameterization) and w.parameterization_type == 'q_parameterization'
+    assert np.all(w(None) == 0.5) and np.all((P() + w)(None) == 1.5)
+
+
+def test_generator_not_implemented_raises_like_reference(tmp_path):
+    from pyqg_generative_b200.models.cgan_regression import CGANRegression
+    with pytest.raises(ValueError, match='generator not implemented'):
+        CGANRegression(generator='DeepInversion', folder=str(tmp_path))
+
+
+def test_member_sharding_is_a_partition():
+    from pyqg_generative_b200.parallel import shard_members
+    for total in (1, 7, 64, 1024):
+        for world in (1, 2, 3, 8):
+            blocks = [shard_members(total, r, world) for r in range(world)]
+            assert sum(c for c, _ in blocks) == total
+            assert all(blocks[r][1] + blocks[r][0] == blocks[r + 1][1] for r in range(world - 1))
+            assert max(c for c, _ in blocks) - min(c for c, _ in blocks) <= 1
+
+
+def test_isotropic_spectrum_integrates_to_total():
+    from pyqg_generative_b200.parallel import calc_ispec
+    from oracle import pyqg_shim
+    m = pyqg_shim.QGModel(nx=64, log_level=0)
+    spec = np.exp(-(m.wv / (8 * m.dk)) ** 2)
+    kr, s = calc_ispec(m.k, m.l, spec, averaging=False)
+    inside = m.wv < kr[-1] + (kr[1] - kr[0]) / 2
+    assert abs(s.sum() * (kr[1] - kr[0]) - spec[inside & (m.wv >= (kr[0] - (kr[1] - kr[0]) / 2))].sum()) < 1e-9 * spec.sum()

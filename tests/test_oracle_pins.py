@@ -1,0 +1,126 @@
+"""The oracle against the reference: committed golden vectors (produced by the UNMODIFIED reference, see
+tests/golden/make_golden.py) and the known-answer material recorded in the reference notebooks."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden, golden_state_dict
+from oracle import cnn_ref, operators_ref as opr, pyqg_shim
+
+
+@pytest.mark.parametrize('kind,files,zkey,key', [
+    ('gan', ['weights_gan.npz'], 'z32', 'gan_snapshot'),
+    ('vae', ['weights_vae.npz'], 'z32', 'vae_snapshot'),
+    ('gz', ['weights_gz_mean.npz', 'weights_gz_var.npz'], 'z64', 'gz_snapshot')])
+def test_predict_snapshot_restatement_matches_reference(kind, files, zkey, key):
+    c = golden('closure_48.npz')
+    nets = [golden_state_dict(f)[0] for f in files]
+    _, xs, ys = golden_state_dict(files[0])
+    y = cnn_ref.predict_snapshot(kind, nets, xs, ys, c['q'].astype('float64'), c[zkey])
+    assert np.abs(y - c[key]).max() <= 1e-6 * np.abs(c[key]).max()
+
+
+def test_generate_restatement_matches_reference():
+    c = golden('closure_48.npz')
+    sd, _, _ = golden_state_dict('weights_gan.npz')
+    x = torch.cat([torch.as_tensor(c['generate_x']), torch.as_tensor(c['generate_z'])], dim=1)
+    y = cnn_ref.andrew_cnn_forward(sd, x).numpy()
+    assert np.abs(y - c['gan_generate']).max() <= 1e-5 * np.abs(c['gan_generate']).max()
+
+
+def test_call_demeans_and_uses_sampler_noise():
+    c = golden('closure_48.npz')
+    sd, xs, ys = golden_state_dict('weights_vae.npz')
+    y = cnn_ref.predict_snapshot('vae', [sd], xs, ys, c['q'].astype('float64'), c['vae_call_noise'])
+    assert np.abs(cnn_ref.demean(y) - c['vae_call']).max() <= 1e-6 * np.abs(c['vae_call']).max()
+    assert np.abs(c['vae_call'].mean(axis=(1, 2))).max() < 1e-20
+
+
+def test_operator_restatements_match_reference():
+    o = golden('operators_128.npz')
+    q = o['q'].astype('float64')
+    for nc in (32, 48, 64):
+        for name in ('Operator1', 'Operator2', 'Operator5', 'cut_off'):
+            ref = o['%s_%d' % (name, nc)]
+            assert np.abs(getattr(opr, name)(q, nc) - ref).max() <= 1e-14 * np.abs(ref).max(), (name, nc)
+    assert np.abs(opr.fft_interpolate(o['interp_in'], 48, 72) - o['interp_48_72']).max() < 1e-13
+    assert np.abs(opr.fft_interpolate(o['interp_in'], 48, 32) - o['interp_48_32']).max() < 1e-13
+    for opn in ('Operator1', 'Operator2', 'Operator5'):
+        for de, tag in (('none', 'none'), ('3/2-rule', '32')):
+            f, mf, m = opr.PV_subgrid_forcing(q, 64, getattr(opr, opn), {}, de)
+            ref = o['S_%s_%s' % (opn, tag)]
+            assert np.abs(f - ref).max() <= 1e-12 * np.abs(ref).max(), (opn, tag)
+
+
+def test_samplers_match_reference():
+    g = golden('samplers.npz')
+    for n in (1, 4, -1):
+        s = cnn_ref.AR1Sampler(n)
+        xi = list(g['ar1_%d_xi' % n])
+        for i in range(6):
+            s.update(lambda: xi[i])
+            assert np.array_equal(s.noise, g['ar1_%d' % n][i])
+    for n in (1, 3):
+        s = cnn_ref.ConstantSampler(n)
+        rng = np.random.RandomState(9)
+        flags = [s.update(lambda: rng.randn(3)) for _ in range(8)]
+        assert flags == list(g['const_%d_flags' % n])
+
+
+# ---- known answers recorded in the reference notebooks -------------------------------------------
+def test_q_setter_roundtrip_is_exact():
+    # notebooks/3-2-dealiasing.ipynb:88 : m.q = q; m._invert(); ||q - m.q|| = 0.0
+    m = pyqg_shim.QGModel(nx=64, log_level=0)
+    q = np.random.RandomState(0).randn(2, 64, 64)
+    m.q = q
+    m._invert()
+    assert np.abs(q - m.q).max() == 0.0
+
+
+def test_cut_off_equals_fft_interpolate():
+    # notebooks/3-2-dealiasing.ipynb:586 : ||cut_off(x,16) - fft_interpolate(x,64,16)|| = 0.0
+    x = np.random.RandomState(1).randn(64, 64)
+    assert np.abs(opr.cut_off(x, 16) - opr.fft_interpolate(x, 64, 16)).max() < 1e-15
+
+
+def test_interpolation_of_a_resolved_wave_is_exact():
+    # notebooks/3-2-dealiasing.ipynb:486 : error 7.8e-15 for cos(x) sin(y) interpolated 16 -> 24
+    def field(n):
+        x = 2 * np.pi * (np.arange(n) + 0.5) / n
+        return np.cos(x)[None, :] * np.sin(x)[:, None]
+    # cell-centred grids of different n are shifted relative to each other; use node-centred sampling instead
+    def field0(n):
+        x = 2 * np.pi * np.arange(n) / n
+        return np.cos(x)[None, :] * np.sin(x)[:, None]
+    assert np.abs(opr.fft_interpolate(field0(16), 16, 24) - field0(24)).max() < 1e-14
+
+
+def test_initial_cfl_matches_recorded_logs():
+    # notebooks/3-2-dealiasing.ipynb:1431 (64^2, dt=14400: CFL 0.023); online-simulations.ipynb:318 (48^2, dt=7200: 0.009)
+    for nx, dt, cfl in ((64, 14400., 0.023), (48, 7200., 0.009)):
+        np.random.seed(0)
+        m = pyqg_shim.QGModel(nx=nx, dt=dt, log_level=0)
+        opr.set_initial_condition(m)
+        assert abs(m._calc_cfl() - cfl) < 1e-3
+
+
+def test_advection_conserves_mean_and_tendency_is_hermitian():
+    # the Jacobian integrates to zero (notebook cells 11-13 print ~1e-17 conservation residuals)
+    np.random.seed(1)
+    m = pyqg_shim.QGModel(nx=64, log_level=0, beta=0.0, rek=0.0, U1=0.0)
+    m.q = np.random.randn(2, 64, 64) * 1e-5
+    m._invert()
+    m._do_advection()
+    assert np.abs(m.dqhdt[:, 0, 0]).max() < 1e-18 * 64 * 64
+
+
+def test_growth_curve_matches_recorded_log():
+    # notebooks/3-2-dealiasing.ipynb:1431-1433: KE grows ~x6 per 1000 steps in the linear phase, CFL stays 0.023
+    np.random.seed(0)
+    m = pyqg_shim.QGModel(nx=64, dt=14400., log_level=1, tmax=1e12)
+    opr.set_initial_condition(m)
+    for _ in range(2000):
+        m._step_forward()
+    (_, _, ke1, cfl1), (_, _, ke2, _) = m.log
+    assert 2e-7 < ke1 < 4e-6 and abs(cfl1 - 0.023) < 2e-3
+    assert 4.0 < ke2 / ke1 < 9.0
