@@ -29,24 +29,27 @@ def conv_indices(state_dict):
     return idx
 
 
-def andrew_cnn_forward(state_dict, x, final_softplus=False):
+def andrew_cnn_forward(state_dict, x, final_softplus=False, dtype=torch.float32):
     """AndrewCNN.forward in eval mode: 8x [circular 'same' conv -> ReLU -> BatchNorm2d(running stats)],
     the last block is the bare conv (cnn_tools.py:137-160).  ``x``: torch float32 (B, Cin, ny, nx)."""
     idx = conv_indices(state_dict)
+    if dtype != torch.float32:   # float64 evaluation: used by tests to separate rounding noise from real errors
+        state_dict = {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in state_dict.items()}
+        x = x.to(dtype)
     with torch.no_grad():
         for n, i in enumerate(idx):
-            w = state_dict['conv.%d.weight' % i].float()
+            w = state_dict['conv.%d.weight' % i]
             b = state_dict.get('conv.%d.bias' % i)
             p = w.shape[-1] // 2
-            x = F.conv2d(F.pad(x, (p, p, p, p), mode='circular'), w, None if b is None else b.float())
+            x = F.conv2d(F.pad(x, (p, p, p, p), mode='circular'), w, None if b is None else b)
             if n < len(idx) - 1:
                 x = F.relu(x)
                 j = i + 2
                 if 'conv.%d.running_mean' % j in state_dict:
-                    x = F.batch_norm(x, state_dict['conv.%d.running_mean' % j].float(),
-                                     state_dict['conv.%d.running_var' % j].float(),
-                                     state_dict['conv.%d.weight' % j].float(),
-                                     state_dict['conv.%d.bias' % j].float(), False, 0.0, BN_EPS)
+                    x = F.batch_norm(x, state_dict['conv.%d.running_mean' % j],
+                                     state_dict['conv.%d.running_var' % j],
+                                     state_dict['conv.%d.weight' % j],
+                                     state_dict['conv.%d.bias' % j], False, 0.0, BN_EPS)
         if final_softplus:
             x = F.softplus(x)
     return x

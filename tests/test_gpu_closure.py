@@ -10,7 +10,7 @@ from conftest import golden, golden_state_dict, write_model_folder
 from oracle import cnn_ref
 
 pytestmark = pytest.mark.gpu
-FP32_TOL = 1e-5
+FP32_TOL = 5e-5      # fp32 vs fp32 with a different summation order (measured: 4e-6 .. 2.4e-5 with the shipped nets)
 
 
 def rel(a, b):
@@ -26,6 +26,9 @@ def test_generator_forward_matches_reference_output():
     x = torch.cat([torch.as_tensor(c['generate_x']), torch.as_tensor(c['generate_z'])], dim=1)
     y = net(x.cuda()).cpu().numpy()
     assert rel(y, c['gan_generate']) < FP32_TOL
+    # rounding-noise check: against a float64 evaluation the kernel is no worse than torch's own fp32 CPU kernels
+    y64 = cnn_ref.andrew_cnn_forward(sd, x, dtype=torch.float64).numpy()
+    assert rel(y, y64) < 3 * rel(c['gan_generate'], y64) + 1e-6
 
 
 @pytest.mark.parametrize('shape', [(2, 64, 64), (1, 96, 96), (3, 40, 24), (1, 16, 16), (2, 7, 9)])
