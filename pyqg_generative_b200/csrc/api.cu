@@ -186,6 +186,9 @@ int net_forward(qgb_handle* h, int net, const float* x, long long x_bs, float* y
   if (precision == QGB_PREC_TC) {
     if (!h->nets[net].tc.ready) return fail(h, QGB_EUNSUPPORTED, "tcgen05 path: network architecture not supported");
     std::string e;
+    h->tcw.prof_layer = (h->prof_net == net) ? h->prof_layer : -1;
+    h->tcw.prof_events = &h->prof_events;
+    h->tcw.prof_images = &h->prof_images;
     int rc = tc_forward(h->nets[net].tc, h->tcw, x, x_bs, y, y_bs, batch, ny, nx, softplus, accumulate, h->nsm, st, &e);
     if (rc != 0) return fail(h, rc, "%s", e.c_str());
     g_launches.fetch_add(tc_launches_per_forward(h->nets[net].tc), std::memory_order_relaxed);

@@ -172,3 +172,52 @@ def test_error_paths_match_reference_exceptions(tmp_path):
         EnsembleQGModel(members=1, nx=192)                # fused path covers nx <= 96
     with pytest.raises(ValueError):
         EnsembleQGModel(members=1, nx=50)                 # 50 = 2 * 5^2: unsupported radix
+
+
+# ---- tcgen05 implicit-GEMM path (fp16 split precision): north_star tolerance <= 1e-3 relative -------------------------
+TC_TOL = 1e-3
+
+
+@pytest.mark.parametrize('shape,cin', [((2, 64, 64), 4), ((3, 48, 48), 4), ((1, 96, 96), 2), ((5, 16, 16), 4), ((2, 32, 48), 2)])
+def test_tensor_core_network_matches_fp32_oracle(shape, cin):
+    from pyqg_generative_b200.tools.cnn_tools import AndrewCNN
+    B, ny, nx = shape
+    sd = cnn_ref.random_state_dict(cin, 2, seed=ny + cin)
+    net = AndrewCNN(cin, 2, precision='tc')
+    net.load_state_dict(sd)
+    x = torch.randn(B, cin, ny, nx, generator=torch.Generator().manual_seed(2))
+    ref = cnn_ref.andrew_cnn_forward(sd, x).numpy()
+    y = net(x.cuda()).cpu().numpy()
+    assert np.isfinite(y).all()
+    assert rel(y, ref) < TC_TOL, rel(y, ref)
+    l2 = np.sqrt(((y - ref) ** 2).sum() / (ref ** 2).sum())
+    assert l2 < TC_TOL
+    y_sp = net.forward(x.cuda(), softplus=True).cpu().numpy()
+    assert rel(y_sp, cnn_ref.andrew_cnn_forward(sd, x, final_softplus=True).numpy()) < TC_TOL
+
+
+def test_tensor_core_path_with_shipped_weights_and_coupled_step(tmp_path):
+    from pyqg_generative_b200.models.cgan_regression import CGANRegression
+    from pyqg_generative_b200.models.mean_var_model import MeanVarModel
+    from pyqg_generative_b200.tools.stochastic_pyqg import stochastic_QGModel
+    c = golden('closure_48.npz')
+    gan = CGANRegression(folder=write_model_folder(tmp_path, 'gan'), nx=48, precision='tc')
+    m = _M()
+    m.q, m.ny, m.nx = c['q'].astype('float64'), 48, 48
+    y = gan.predict_snapshot(m, c['z32'])
+    l2 = np.sqrt(((y - c['gan_snapshot']) ** 2).sum() / (c['gan_snapshot'] ** 2).sum())
+    assert l2 < TC_TOL and rel(y, c['gan_snapshot']) < 2 * TC_TOL, (l2, rel(y, c['gan_snapshot']))
+    gz = MeanVarModel(folder=write_model_folder(tmp_path, 'gz'), precision='tc')
+    yg = gz.predict_snapshot(m, c['z64'])
+    assert np.sqrt(((yg - c['gz_snapshot']) ** 2).sum() / (c['gz_snapshot'] ** 2).sum()) < TC_TOL
+    # device-coupled step in tensor-core precision against the fp32 engine path
+    out = {}
+    for prec in ('fp32', 'tc'):
+        g = CGANRegression(folder=write_model_folder(tmp_path, 'gan'), nx=48, precision=prec)
+        mm = stochastic_QGModel(dict(nx=48, dt=7200.0, log_level=0, members=3, parameterization=g, precision=prec), 'AR1', 1)
+        mm.q = c['q'].astype('float64')
+        mm.set_latent(np.concatenate([c['z32']] * 3))
+        mm._step_forward()
+        out[prec] = (mm.PV_forcing, mm.q)
+    assert rel(out['tc'][0], out['fp32'][0]) < 2 * TC_TOL
+    assert rel(out['tc'][1], out['fp32'][1]) < 1e-4
