@@ -37,14 +37,16 @@ MAC_PER_PIXEL = [12800, 204800, 18432, 9216, 9216, 9216, 9216, 576]   # SURVEY.m
 
 
 def synthetic_states(members, n, seed):
-    """Gaussian random fields with the shipped x_scale stds and a red spectrum truncated at 0.65*pi/dx."""
+    """Developed-turbulence-like states: Gaussian random fields with the shipped x_scale stds and a q-amplitude
+    spectrum ~ kappa^0.5 truncated at 0.65*pi/dx, which gives KE ~ 5e-4 and CFL ~ 0.2 at dt=14400 -- the saturated
+    values recorded in notebooks/3-2-dealiasing.ipynb:1434-1440."""
     rng = np.random.RandomState(seed)
     dk = 2 * np.pi / 1e6
     ll = dk * np.append(np.arange(0., n / 2), np.arange(-n / 2, 0.))
     kk = dk * np.arange(0., n // 2 + 1)
     k, l = np.meshgrid(kk, ll)
     wv = np.sqrt(k ** 2 + l ** 2)
-    amp = np.where(wv > 0, (wv / dk + 1.0) ** -1.5, 0.0) * (wv * (1e6 / n) <= 0.65 * np.pi)
+    amp = np.sqrt(wv / dk) * (wv * (1e6 / n) <= 0.65 * np.pi)
     out = np.empty((members, 2, n, n))
     for z, std in enumerate(X_STD):
         h = np.fft.rfftn(rng.randn(members, n, n), axes=(-2, -1)) * amp
@@ -276,7 +278,7 @@ def main():
     if args.impl == 'reference':
         return run_reference(args)
     if args.precision == 'auto':
-        args.precision = 'fp32'
+        args.precision = 'tc'
     return run_b200(args)
 
 

@@ -24,7 +24,7 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return OUT
     nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
-    cmd = [nvcc] + FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', OUT, SRC, '-lcuda']
+    cmd = [nvcc] + FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', OUT, SRC]
     print(' '.join(cmd), file=sys.stderr)
     subprocess.check_call(cmd)
     return OUT

@@ -21,6 +21,7 @@
 // Layer 1 (Cin = 4 or 2) is too thin for a K=16 MMA, so a small pre-pass writes its 5x5 im2col (K = 100 -> 128) in the
 // same layout and the layer runs as a 1x1 convolution through the same kernel.
 #pragma once
+#include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -63,6 +64,17 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// TMA tensor-tile load (3-D box) global -> shared (SASS: UTMALDG); ``tmap`` points at a __grid_constant__ CUtensorMap
+__device__ __forceinline__ void tma_load_3d(void* dst, const void* tmap, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+          smem_u32(dst)),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
                : "memory");
@@ -93,6 +105,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr)
       : "memory");
 }
+// one elected lane of a fully converged warp (same lane every time for the same mask)
+__device__ __forceinline__ uint32_t elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "@px mov.s32 %0, 1;\n\t}"
+      : "+r"(pred));
+  return pred;
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 }  // namespace ptx
 
@@ -114,7 +136,7 @@ enum { TC_OUT_HI = 0, TC_OUT_HILO = 1, TC_OUT_FINAL = 2 };
 struct TcConvParams {
   const __half* in_hi; const __half* in_lo;  // [img][J_in][HP][WP][8]
   int J_in, HP, WP;
-  const __half* w;                           // [chunk][tap][plane][4][COUT][8]
+  const __half* w;                           // [chunk][tap][4][plane][COUT][8]
   const float* bias; const float* bn_s; const float* bn_t;
   float inv_wscale; int relu_bn;
   __half* out_hi; __half* out_lo; int out_pad, out_J;   // [img][out_J][ny+2*out_pad][nx+2*out_pad][8]
@@ -132,7 +154,11 @@ struct TcCfg {
   static constexpr int A_STAGE = PLANES * 4 * HY * HX * 16;
   static constexpr int W_STAGE = PLANES * 4 * COUT * 16;
   static constexpr int NW = (COUT >= 128) ? 4 : 8;
-  static constexpr int NCOLS_USED = 2 * T * COUT;
+  // 3-pass layers with a narrow N concatenate [w_hi | w_lo] along N:  D[:, :COUT] += a_hi w_hi + a_lo w_hi,
+  // D[:, COUT:] += a_hi w_lo  (two MMAs instead of three -> fewer shared-memory reads of the A operand)
+  static constexpr bool NCAT = (PASSES == 3) && (COUT <= 32);
+  static constexpr int DCOLS = NCAT ? 2 * COUT : COUT;       // TMEM columns per M-tile
+  static constexpr int NCOLS_USED = 2 * T * DCOLS;
   static constexpr int NCOLS = NCOLS_USED <= 32 ? 32 : NCOLS_USED <= 64 ? 64 : NCOLS_USED <= 128 ? 128 : NCOLS_USED <= 256 ? 256 : 512;
   static constexpr int SMEM = 2 * A_STAGE + NW * W_STAGE + 3 * COUT * 4 + 256;
   static_assert(NCOLS_USED <= 512, "accumulators exceed TMEM");
@@ -141,8 +167,16 @@ struct TcCfg {
 
 __device__ __forceinline__ float softplus_f(float v) { return v > 20.f ? v : log1pf(expf(v)); }
 
+// Activation tensor maps: the buffer [img*J][HP][WP][8 x fp16] is described to the TMA engine as a 3-D tensor of 32-bit
+// words (WP*4, HP, img*J); one box (HX*4, HY, 4) = the tile + halo of one 32-channel chunk lands in shared memory as
+// [4][HY][HX][16 B], exactly the K-major no-swizzle UMMA layout.
+struct TcMaps {
+  CUtensorMap hi, lo;
+};
+
 template <int CIN, int COUT, int KS, int PASSES, int T, int OUTMODE>
-__global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__ TcConvParams P) {
+__global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__ TcConvParams P,
+                                                         const __grid_constant__ TcMaps M) {
   using C = TcCfg<CIN, COUT, KS, PASSES, T>;
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* sA = smem;
@@ -170,6 +204,10 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc(tmem_slot, C::NCOLS);
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&M.hi);
+    if (C::PLANES == 2) ptx::prefetch_tmap(&M.lo);
+  }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -185,14 +223,13 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
       for (int c = 0; c < C::NCHUNK; ++c, ++ia) {
         const uint32_t s = ia & 1, par = (ia >> 1) & 1;
         ptx::mbar_wait(&a_empty[s], par ^ 1);
-        if (lane == 0) ptx::mbar_arrive_expect_tx(&a_full[s], C::A_STAGE);
-        __syncwarp();
-        for (int idx = lane; idx < C::PLANES * 4 * C::HY; idx += 32) {
-          const int pl = idx / (4 * C::HY), j = (idx / C::HY) % 4, hy = idx % C::HY;
-          const __half* src = (pl ? P.in_lo : P.in_hi) +
-                              ((((long long)img * P.J_in + c * 4 + j) * P.HP + y0 + hy) * P.WP + x0) * 8;
-          ptx::bulk_g2s(sA + s * C::A_STAGE + ((pl * 4 + j) * C::HY + hy) * C::HX * 16, src, C::HX * 16, &a_full[s]);
+        if (lane == 0) {
+          ptx::mbar_arrive_expect_tx(&a_full[s], C::A_STAGE);
+          ptx::tma_load_3d(sA + s * C::A_STAGE, &M.hi, x0 * 4, y0, img * P.J_in + c * 4, &a_full[s]);
+          if (C::PLANES == 2)
+            ptx::tma_load_3d(sA + s * C::A_STAGE + 4 * C::HY * C::HX * 16, &M.lo, x0 * 4, y0, img * P.J_in + c * 4, &a_full[s]);
         }
+        __syncwarp();
       }
     }
   } else if (warp == 2) {
@@ -210,48 +247,64 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer: a single thread drives the tensor core ======================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(128, COUT);
-      const uint32_t sA_u = ptx::smem_u32(sA), sW_u = ptx::smem_u32(sW);
-      uint32_t ia = 0, iw = 0, it = 0;
-      for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x, ++it) {
-        const uint32_t as = it & 1;
-        ptx::mbar_wait(&acc_empty[as], ((it >> 1) & 1) ^ 1);
+    // ===================== MMA issuer: the warp stays converged, one elected lane drives the tensor core ==========
+    constexpr uint32_t idesc = make_idesc_f16(128, COUT);
+    constexpr uint32_t idesc_cat = make_idesc_f16(128, C::DCOLS);
+    constexpr uint32_t A_LBO = C::HY * C::HX, A_SBO = C::HX;                 // in 16-byte units
+    constexpr uint32_t B_LBO = C::PLANES * COUT, B_SBO = 8;                   // weight slab layout [j][plane][COUT][8]
+    constexpr uint32_t a_hi32 = A_SBO | (1u << 14), b_hi32 = B_SBO | (1u << 14);   // upper descriptor words
+    const uint32_t sA_u = ptx::smem_u32(sA) >> 4, sW_u = ptx::smem_u32(sW) >> 4;
+    uint32_t ia = 0, iw = 0, it = 0;
+    for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x, ++it) {
+      const uint32_t as = it & 1;
+      ptx::mbar_wait(&acc_empty[as], ((it >> 1) & 1) ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t dbase = tmem_base + as * (T * C::DCOLS);
+      for (int c = 0; c < C::NCHUNK; ++c, ++ia) {
+        const uint32_t sa = ia & 1;
+        ptx::mbar_wait(&a_full[sa], (ia >> 1) & 1);
         ptx::tc_fence_after();
-        for (int c = 0; c < C::NCHUNK; ++c, ++ia) {
-          const uint32_t sa = ia & 1;
-          ptx::mbar_wait(&a_full[sa], (ia >> 1) & 1);
+        for (int tap = 0; tap < C::TAPS; ++tap, ++iw) {
+          const uint32_t sw = iw % C::NW;
+          ptx::mbar_wait(&w_full[sw], (iw / C::NW) & 1);
           ptx::tc_fence_after();
-          for (int tap = 0; tap < C::TAPS; ++tap, ++iw) {
-            const uint32_t sw = iw % C::NW;
-            ptx::mbar_wait(&w_full[sw], (iw / C::NW) & 1);
-            ptx::tc_fence_after();
+          if (ptx::elect_one_sync()) {
             const int dy = tap / KS, dx = tap % KS;
+            const uint32_t a0 = (sA_u + sa * (C::A_STAGE >> 4) + dy * C::HX + dx) | (A_LBO << 16);
+            const uint32_t b0 = (sW_u + sw * (C::W_STAGE >> 4)) | (B_LBO << 16);
+            const uint32_t acc0 = (c | tap) ? 1u : 0u;
 #pragma unroll
             for (int t = 0; t < T; ++t) {
-              const uint32_t d = tmem_base + as * (T * COUT) + t * COUT;
+              const uint32_t d = dbase + t * C::DCOLS;
 #pragma unroll
               for (int ks = 0; ks < 2; ++ks) {
-                const uint32_t a_hi = sA_u + sa * C::A_STAGE + (((2 * ks) * C::HY + dy) * C::HX + 8 * t + dx) * 16;
-                const uint32_t b_hi = sW_u + sw * C::W_STAGE + (2 * ks) * COUT * 16;
-                const uint64_t adesc = make_smem_desc(a_hi, C::HY * C::HX * 16, C::HX * 16);
-                const uint64_t bdesc = make_smem_desc(b_hi, COUT * 16, 128);
-                const uint32_t first = (c == 0 && tap == 0 && ks == 0) ? 0u : 1u;
-                ptx::mma_f16(d, adesc, bdesc, idesc, first);
-                if (PASSES == 3) {
-                  const uint64_t adesc_lo = make_smem_desc(a_hi + 4 * C::HY * C::HX * 16, C::HY * C::HX * 16, C::HX * 16);
-                  const uint64_t bdesc_lo = make_smem_desc(b_hi + 4 * COUT * 16, COUT * 16, 128);
-                  ptx::mma_f16(d, adesc_lo, bdesc, idesc, 1u);
-                  ptx::mma_f16(d, adesc, bdesc_lo, idesc, 1u);
+                const uint64_t adesc = ((uint64_t)a_hi32 << 32) | (a0 + 2 * ks * A_LBO + 8 * t);
+                const uint64_t bdesc = ((uint64_t)b_hi32 << 32) | (b0 + 2 * ks * B_LBO);
+                const uint32_t first = ks ? 1u : acc0;
+                if (PASSES == 1) {
+                  ptx::mma_f16(d, adesc, bdesc, idesc, first);
+                } else {
+                  const uint64_t adesc_lo = ((uint64_t)a_hi32 << 32) | (a0 + (4 + 2 * ks) * A_LBO + 8 * t);
+                  if (C::NCAT) {
+                    ptx::mma_f16(d, adesc, bdesc, idesc_cat, first);       // a_hi x [w_hi | w_lo]
+                    ptx::mma_f16(d, adesc_lo, bdesc, idesc, 1u);           // a_lo x  w_hi
+                  } else {
+                    const uint64_t bdesc_lo = ((uint64_t)b_hi32 << 32) | (b0 + 2 * ks * B_LBO + COUT);
+                    ptx::mma_f16(d, adesc, bdesc, idesc, first);
+                    ptx::mma_f16(d, adesc_lo, bdesc, idesc, 1u);
+                    ptx::mma_f16(d, adesc, bdesc_lo, idesc, 1u);
+                  }
                 }
               }
             }
-            ptx::tc_commit(&w_empty[sw]);        // weight slab free once these MMAs have read it
+            ptx::tc_commit(&w_empty[sw]);                                   // weight slab free once these MMAs have read it
+            if (tap == C::TAPS - 1) {
+              ptx::tc_commit(&a_empty[sa]);                                 // activation chunk free
+              if (c == C::NCHUNK - 1) ptx::tc_commit(&acc_full[as]);        // tile complete -> epilogue
+            }
           }
-          ptx::tc_commit(&a_empty[sa]);          // activation chunk free
+          __syncwarp();
         }
-        ptx::tc_commit(&acc_full[as]);           // accumulators of this tile complete -> epilogue
       }
     }
   } else if (warp >= 4) {
@@ -270,11 +323,18 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
 #pragma unroll 1
       for (int t = 0; t < T; ++t) {
         const int x = x0 + 8 * t + pcol;
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * (T * COUT) + t * COUT;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * (T * C::DCOLS) + t * C::DCOLS;
 #pragma unroll 1
         for (int n0 = 0; n0 < COUT; n0 += 16) {
           uint32_t rr[16];
           ptx::tmem_ld16(taddr + n0, rr);
+          if (C::NCAT) {
+            uint32_t r2[16];
+            ptx::tmem_ld16(taddr + COUT + n0, r2);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) rr[i] = __float_as_uint(__uint_as_float(rr[i]) + __uint_as_float(r2[i]));
+          }
           ptx::tmem_ld_wait();
           if (t == T - 1 && n0 + 16 >= COUT) {     // last read of this accumulator set: hand it back to the MMA warp
             ptx::tc_fence_before();
@@ -403,7 +463,7 @@ inline void tc_free_workspace(TcWorkspace& w) {
 }
 inline int tc_launches_per_forward(const TcNet& n) { return n.ready ? (int)n.layers.size() + 1 : 0; }
 
-// Pack one layer: weights -> [chunk][tap][plane][4][cout_p][8] fp16 (hi [, lo]) scaled by 2^k, epilogue vectors padded.
+// Pack one layer: weights -> [chunk][tap][4][plane][cout_p][8] fp16 (hi [, lo]) scaled by 2^k, epilogue vectors padded.
 inline bool tc_pack_layer(TcLayer& L, int cin_p, int cout_p, int ks, int passes, int real_cin, int real_cout,
                           const std::vector<float>& wdense /* [real_cout][real_cin][ks*ks] */, const float* bias,
                           const float* bn_s, const float* bn_t, int relu_bn) {
@@ -430,8 +490,8 @@ inline bool tc_pack_layer(TcLayer& L, int cin_p, int cout_p, int ks, int passes,
             if (ci < real_cin && co < real_cout) v = wdense[((size_t)co * real_cin + ci) * taps + tap] * scale;
             const __half h = __float2half_rn(v);
             const size_t base = ((size_t)(c * taps + tap) * planes) * 4 * cout_p * 8;
-            pk[base + ((size_t)(0 * 4 + j) * cout_p + co) * 8 + e] = h;
-            if (planes == 2) pk[base + ((size_t)(1 * 4 + j) * cout_p + co) * 8 + e] = __float2half_rn(v - __half2float(h));
+            pk[base + ((size_t)(j * planes + 0) * cout_p + co) * 8 + e] = h;
+            if (planes == 2) pk[base + ((size_t)(j * planes + 1) * cout_p + co) * 8 + e] = __float2half_rn(v - __half2float(h));
           }
   std::vector<float> b(cout_p, 0.f), s(cout_p, 1.f), t(cout_p, 0.f);
   for (int i = 0; i < real_cout; ++i) {
@@ -482,9 +542,41 @@ inline int tc_pack_net(TcNet& n, int nlayers, const qgb_cnn_layer* L, std::strin
   return 0;
 }
 
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline PFN_tmapEncodeTiled tmap_encoder() {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (PFN_tmapEncodeTiled)p;
+  }
+  return fn;
+}
+// 3-D map over an activation plane [nj][HP][WP][8 halves] viewed as uint32 words, box = (hx*4, hy, 4)
+inline bool tc_make_map(CUtensorMap* m, const __half* base, int WP, int HP, long long nj, int hx, int hy) {
+  PFN_tmapEncodeTiled enc = tmap_encoder();
+  if (!enc) return false;
+  cuuint64_t gdim[3] = {(cuuint64_t)WP * 4, (cuuint64_t)HP, (cuuint64_t)nj};
+  cuuint64_t gstr[2] = {(cuuint64_t)WP * 16, (cuuint64_t)HP * WP * 16};
+  cuuint32_t box[3] = {(cuuint32_t)hx * 4, (cuuint32_t)hy, 4};
+  cuuint32_t estr[3] = {1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int CIN, int COUT, int KS, int PASSES, int T, int OUTMODE>
-inline cudaError_t tc_launch(const TcConvParams& P, int nsm, cudaStream_t st) {
+inline cudaError_t tc_launch(const TcConvParams& P, int nimg, int nsm, cudaStream_t st) {
   using C = TcCfg<CIN, COUT, KS, PASSES, T>;
+  TcMaps M;
+  if (!tc_make_map(&M.hi, P.in_hi, P.WP, P.HP, (long long)nimg * P.J_in, C::HX, C::HY)) return cudaErrorInvalidValue;
+  if (C::PLANES == 2) {
+    if (!tc_make_map(&M.lo, P.in_lo, P.WP, P.HP, (long long)nimg * P.J_in, C::HX, C::HY)) return cudaErrorInvalidValue;
+  } else {
+    M.lo = M.hi;
+  }
   auto kern = conv_tc_kernel<CIN, COUT, KS, PASSES, T, OUTMODE>;
   static bool configured = false;
   if (!configured) {
@@ -493,15 +585,15 @@ inline cudaError_t tc_launch(const TcConvParams& P, int nsm, cudaStream_t st) {
     configured = true;
   }
   const int grid = P.num_tiles < nsm ? P.num_tiles : nsm;
-  kern<<<grid, 256, C::SMEM, st>>>(P);
+  kern<<<grid, 256, C::SMEM, st>>>(P, M);
   return cudaGetLastError();
 }
 
 template <int CIN, int COUT, int KS, int PASSES, int OUTMODE>
-inline cudaError_t tc_launch_T(int T, const TcConvParams& P, int nsm, cudaStream_t st) {
-  if (T == 4) return tc_launch<CIN, COUT, KS, PASSES, 4, OUTMODE>(P, nsm, st);
-  if (T == 3) return tc_launch<CIN, COUT, KS, PASSES, 3, OUTMODE>(P, nsm, st);
-  return tc_launch<CIN, COUT, KS, PASSES, 2, OUTMODE>(P, nsm, st);
+inline cudaError_t tc_launch_T(int T, const TcConvParams& P, int nimg, int nsm, cudaStream_t st) {
+  if (T == 4) return tc_launch<CIN, COUT, KS, PASSES, 4, OUTMODE>(P, nimg, nsm, st);
+  if (T == 3) return tc_launch<CIN, COUT, KS, PASSES, 3, OUTMODE>(P, nimg, nsm, st);
+  return tc_launch<CIN, COUT, KS, PASSES, 2, OUTMODE>(P, nimg, nsm, st);
 }
 
 inline int tc_forward(const TcNet& net, TcWorkspace& ws, const float* x, long long x_bs, float* y, long long y_bs,
@@ -559,11 +651,11 @@ inline int tc_forward(const TcNet& net, TcWorkspace& ws, const float* x, long lo
       if (prof) { cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventRecord(ev0, st); }
       cudaError_t e;
       if (li == 0) {
-        e = net.kp == 128 ? tc_launch<128, 128, 1, 3, 2, TC_OUT_HI>(P, nsm, st) : tc_launch<64, 128, 1, 3, 2, TC_OUT_HI>(P, nsm, st);
-      } else if (li == 1) e = tc_launch_T<128, 64, 5, 1, TC_OUT_HILO>(T, P, nsm, st);
-      else if (li == 2) e = tc_launch_T<64, 32, 3, 3, TC_OUT_HILO>(T, P, nsm, st);
-      else if (li < 7) e = tc_launch_T<32, 32, 3, 3, TC_OUT_HILO>(T, P, nsm, st);
-      else e = tc_launch_T<32, 16, 3, 3, TC_OUT_FINAL>(T, P, nsm, st);
+        e = net.kp == 128 ? tc_launch<128, 128, 1, 3, 2, TC_OUT_HI>(P, nb, nsm, st) : tc_launch<64, 128, 1, 3, 2, TC_OUT_HI>(P, nb, nsm, st);
+      } else if (li == 1) e = tc_launch_T<128, 64, 5, 1, TC_OUT_HILO>(T, P, nb, nsm, st);
+      else if (li == 2) e = tc_launch_T<64, 32, 3, 3, TC_OUT_HILO>(T, P, nb, nsm, st);
+      else if (li < 7) e = tc_launch_T<32, 32, 3, 3, TC_OUT_HILO>(T, P, nb, nsm, st);
+      else e = tc_launch_T<32, 16, 3, 3, TC_OUT_FINAL>(T, P, nb, nsm, st);
       if (prof) { cudaEventRecord(ev1, st); ws.prof_events->emplace_back(ev0, ev1); *ws.prof_images += nb; }
       if (e != cudaSuccess) { *err = std::string("tcgen05 conv launch failed: ") + cudaGetErrorString(e); return QGB_ECUDA; }
     }
