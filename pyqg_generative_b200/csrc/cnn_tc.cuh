@@ -11,12 +11,15 @@
 // fp16; error ~2^-22), fp32 accumulation throughout.  Weights are pre-scaled per layer by a power of two so they sit
 // in the fp16 normal range; the epilogue undoes the scale exactly.
 //
-// Data layout.  Activations live in HBM as  [image][C/8][ny+2p][nx+2p][8] fp16  (hi plane, optional lo plane): the
-// innermost 16 B are 8 consecutive channels of one pixel, the circular halo (p = padding of the CONSUMING layer) is
+// Data layout.  Activations live in HBM as  [image][C/32][ny+2p][nx+2p][32] fp16  (hi plane, optional lo plane): the
+// innermost 64 B are 32 consecutive channels of one pixel, the circular halo (p = padding of the CONSUMING layer) is
 // materialised by the producing epilogue, so every tap of the consumer is a plain in-bounds box.  A CTA tile is
-// 16 rows x 8T columns (T accumulators of 128 pixels).  With this layout the tile + halo, loaded ONCE per 32-channel
-// chunk, serves all KSxKS taps: tap (dy,dx), K-step ks and M-tile t are just a different start address of the SAME
-// no-swizzle K-major canonical UMMA layout  ((8,16),(8,2)) : ((16 B, row pitch), (1, channel-chunk pitch)).
+// 16 rows x 8T columns (T accumulators of 128 pixels).  The tile + halo of one 32-channel chunk is loaded ONCE by a
+// 4-D TMA box with the 64-byte swizzle and serves all KSxKS taps: tap (dy,dx), K-step ks and M-tile t are just a
+// different start address of the SAME K-major SWIZZLE_64B canonical UMMA layout (8 pixel rows of 64 B per atom, next
+// image row at the stride byte offset).  Because a pixel row is 64 B, every tap shift keeps the 8x16 B core matrices
+// bank-conflict free (the first version used 16 B pixel rows: shifted core matrices straddled two 128 B lines and the
+// tensor pipe sat at 41 %, profiles/r1_conv_l2_noswizzle.md).
 //
 // Layer 1 (Cin = 4 or 2) is too thin for a K=16 MMA, so a small pre-pass writes its 5x5 im2col (K = 100 -> 128) in the
 // same layout and the layer runs as a 1x1 convolution through the same kernel.
@@ -27,6 +30,7 @@
 #include <stdint.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -70,6 +74,13 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const void* tmap, int c0,
       "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
           smem_u32(dst)),
       "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const void* tmap, int c0, int c1, int c2, int c3, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+          smem_u32(dst)),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
       : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const void* tmap) {
@@ -134,12 +145,12 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
 enum { TC_OUT_HI = 0, TC_OUT_HILO = 1, TC_OUT_FINAL = 2 };
 
 struct TcConvParams {
-  const __half* in_hi; const __half* in_lo;  // [img][J_in][HP][WP][8]
-  int J_in, HP, WP;
+  const __half* in_hi; const __half* in_lo;  // [img][nch_in][HP][WP][32]
+  int nch_in, HP, WP;
   const __half* w;                           // [chunk][tap][4][plane][COUT][8]
   const float* bias; const float* bn_s; const float* bn_t;
   float inv_wscale; int relu_bn;
-  __half* out_hi; __half* out_lo; int out_pad, out_J;   // [img][out_J][ny+2*out_pad][nx+2*out_pad][8]
+  __half* out_hi; __half* out_lo; int out_pad, out_nch;   // [img][out_nch][ny+2*out_pad][nx+2*out_pad][32]
   float* out_f32; long long out_bs; int out_c, softplus, accumulate;
   int ny, nx, tiles_y, tiles_x, num_tiles;
 };
@@ -151,25 +162,29 @@ struct TcCfg {
   static constexpr int PLANES = PASSES == 3 ? 2 : 1;
   static constexpr int HY = 16 + KS - 1;
   static constexpr int HX = 8 * T + KS - 1;
-  static constexpr int A_STAGE = PLANES * 4 * HY * HX * 16;
-  static constexpr int W_STAGE = PLANES * 4 * COUT * 16;
-  static constexpr int NW = (COUT >= 128) ? 4 : 8;
+  static constexpr int A_BYTES = HY * HX * 64;                        // one plane of one 32-channel chunk
+  static constexpr int A_PLANE = (A_BYTES + 1023) / 1024 * 1024;      // swizzle atoms need aligned plane bases
+  static constexpr int A_STAGE = PLANES * A_PLANE;
+  static constexpr int A_TX = PLANES * A_BYTES;
+  static constexpr int W_TAP = PLANES * 4 * COUT * 16;            // one (chunk, tap) weight slab
+  static constexpr int W_STAGE = KS * W_TAP;                      // a pipeline stage holds one tap ROW (KS taps)
+  static constexpr int NW = (KS == 5) ? 3 : 4;
   // 3-pass layers with a narrow N concatenate [w_hi | w_lo] along N:  D[:, :COUT] += a_hi w_hi + a_lo w_hi,
   // D[:, COUT:] += a_hi w_lo  (two MMAs instead of three -> fewer shared-memory reads of the A operand)
   static constexpr bool NCAT = (PASSES == 3) && (COUT <= 32);
   static constexpr int DCOLS = NCAT ? 2 * COUT : COUT;       // TMEM columns per M-tile
   static constexpr int NCOLS_USED = 2 * T * DCOLS;
   static constexpr int NCOLS = NCOLS_USED <= 32 ? 32 : NCOLS_USED <= 64 ? 64 : NCOLS_USED <= 128 ? 128 : NCOLS_USED <= 256 ? 256 : 512;
-  static constexpr int SMEM = 2 * A_STAGE + NW * W_STAGE + 3 * COUT * 4 + 256;
+  static constexpr int SMEM = 2 * A_STAGE + NW * W_STAGE + 3 * COUT * 4 + 256 + 1024;
   static_assert(NCOLS_USED <= 512, "accumulators exceed TMEM");
   static_assert(CIN % 32 == 0 && COUT % 16 == 0, "bad channel counts");
 };
 
 __device__ __forceinline__ float softplus_f(float v) { return v > 20.f ? v : log1pf(expf(v)); }
 
-// Activation tensor maps: the buffer [img*J][HP][WP][8 x fp16] is described to the TMA engine as a 3-D tensor of 32-bit
-// words (WP*4, HP, img*J); one box (HX*4, HY, 4) = the tile + halo of one 32-channel chunk lands in shared memory as
-// [4][HY][HX][16 B], exactly the K-major no-swizzle UMMA layout.
+// Activation tensor maps: the buffer [img*nch][HP][WP][32 x fp16] is a 4-D tensor (32, WP, HP, img*nch); one box
+// (32, HX, HY, 1) with CU_TENSOR_MAP_SWIZZLE_64B = the tile + halo of one 32-channel chunk lands in shared memory as
+// [HY][HX][64 B] with 16-byte chunks XOR-swizzled by address bits 7-8 -- the K-major SWIZZLE_64B UMMA layout.
 struct TcMaps {
   CUtensorMap hi, lo;
 };
@@ -178,7 +193,8 @@ template <int CIN, int COUT, int KS, int PASSES, int T, int OUTMODE>
 __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__ TcConvParams P,
                                                          const __grid_constant__ TcMaps M) {
   using C = TcCfg<CIN, COUT, KS, PASSES, T>;
-  extern __shared__ __align__(128) unsigned char smem[];
+  extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
+  unsigned char* smem = tc_smem_raw + ((1024u - (ptx::smem_u32(tc_smem_raw) & 1023u)) & 1023u);
   unsigned char* sA = smem;
   unsigned char* sW = smem + 2 * C::A_STAGE;
   float* sEpi = reinterpret_cast<float*>(sW + C::NW * C::W_STAGE);          // bias | bn_s | bn_t
@@ -224,10 +240,9 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
         const uint32_t s = ia & 1, par = (ia >> 1) & 1;
         ptx::mbar_wait(&a_empty[s], par ^ 1);
         if (lane == 0) {
-          ptx::mbar_arrive_expect_tx(&a_full[s], C::A_STAGE);
-          ptx::tma_load_3d(sA + s * C::A_STAGE, &M.hi, x0 * 4, y0, img * P.J_in + c * 4, &a_full[s]);
-          if (C::PLANES == 2)
-            ptx::tma_load_3d(sA + s * C::A_STAGE + 4 * C::HY * C::HX * 16, &M.lo, x0 * 4, y0, img * P.J_in + c * 4, &a_full[s]);
+          ptx::mbar_arrive_expect_tx(&a_full[s], C::A_TX);
+          ptx::tma_load_4d(sA + s * C::A_STAGE, &M.hi, 0, x0, y0, img * P.nch_in + c, &a_full[s]);
+          if (C::PLANES == 2) ptx::tma_load_4d(sA + s * C::A_STAGE + C::A_PLANE, &M.lo, 0, x0, y0, img * P.nch_in + c, &a_full[s]);
         }
         __syncwarp();
       }
@@ -237,11 +252,11 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
     if (lane == 0) {
       uint32_t iw = 0;
       for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
-        for (int ct = 0; ct < C::NCHUNK * C::TAPS; ++ct, ++iw) {
+        for (int cr = 0; cr < C::NCHUNK * KS; ++cr, ++iw) {
           const uint32_t s = iw % C::NW, par = (iw / C::NW) & 1;
           ptx::mbar_wait(&w_empty[s], par ^ 1);
           ptx::mbar_arrive_expect_tx(&w_full[s], C::W_STAGE);
-          ptx::bulk_g2s(sW + s * C::W_STAGE, reinterpret_cast<const unsigned char*>(P.w) + (size_t)ct * C::W_STAGE,
+          ptx::bulk_g2s(sW + s * C::W_STAGE, reinterpret_cast<const unsigned char*>(P.w) + (size_t)cr * C::W_STAGE,
                         C::W_STAGE, &w_full[s]);
         }
       }
@@ -250,9 +265,11 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
     // ===================== MMA issuer: the warp stays converged, one elected lane drives the tensor core ==========
     constexpr uint32_t idesc = make_idesc_f16(128, COUT);
     constexpr uint32_t idesc_cat = make_idesc_f16(128, C::DCOLS);
-    constexpr uint32_t A_LBO = C::HY * C::HX, A_SBO = C::HX;                 // in 16-byte units
-    constexpr uint32_t B_LBO = C::PLANES * COUT, B_SBO = 8;                   // weight slab layout [j][plane][COUT][8]
-    constexpr uint32_t a_hi32 = A_SBO | (1u << 14), b_hi32 = B_SBO | (1u << 14);   // upper descriptor words
+    // A: K-major SWIZZLE_64B (layout type 4): pixel rows of 64 B, 8-row groups (= next image row) at SBO = HX*64 B
+    // B: K-major no swizzle: weight slab [j][plane][COUT][8]: 8 couts x 16 B per core matrix, next j at LBO
+    constexpr uint32_t A_SBO = C::HX * 4;                                       // in 16-byte units
+    constexpr uint32_t B_LBO = C::PLANES * COUT, B_SBO = 8;
+    constexpr uint32_t a_hi32 = A_SBO | (1u << 14) | (4u << 29), b_hi32 = B_SBO | (1u << 14);   // upper descriptor words
     const uint32_t sA_u = ptx::smem_u32(sA) >> 4, sW_u = ptx::smem_u32(sW) >> 4;
     uint32_t ia = 0, iw = 0, it = 0;
     for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x, ++it) {
@@ -264,41 +281,50 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
         const uint32_t sa = ia & 1;
         ptx::mbar_wait(&a_full[sa], (ia >> 1) & 1);
         ptx::tc_fence_after();
-        for (int tap = 0; tap < C::TAPS; ++tap, ++iw) {
+#pragma unroll
+        for (int dy = 0; dy < KS; ++dy, ++iw) {
           const uint32_t sw = iw % C::NW;
           ptx::mbar_wait(&w_full[sw], (iw / C::NW) & 1);
           ptx::tc_fence_after();
           if (ptx::elect_one_sync()) {
-            const int dy = tap / KS, dx = tap % KS;
-            const uint32_t a0 = (sA_u + sa * (C::A_STAGE >> 4) + dy * C::HX + dx) | (A_LBO << 16);
-            const uint32_t b0 = (sW_u + sw * (C::W_STAGE >> 4)) | (B_LBO << 16);
-            const uint32_t acc0 = (c | tap) ? 1u : 0u;
+            // Issue order: consecutive MMAs go to DIFFERENT accumulators (t inner).  The 64 B swizzle is a pure function
+            // of the shared-memory ADDRESS bits (verified on B200: a non-zero 'matrix base offset' gives wrong results),
+            // so shifted tap windows need no descriptor fix-up.
+            const uint32_t a_row = sA_u + sa * (C::A_STAGE >> 4) + dy * C::HX * 4;
+            const uint32_t b_row = (sW_u + sw * (C::W_STAGE >> 4)) | (B_LBO << 16);
 #pragma unroll
-            for (int t = 0; t < T; ++t) {
-              const uint32_t d = dbase + t * C::DCOLS;
+            for (int dx = 0; dx < KS; ++dx) {
+              const uint32_t a0 = a_row + dx * 4;
+              const uint32_t b0 = b_row + dx * (C::W_TAP >> 4);
+              const uint32_t acc0 = (c | dy | dx) ? 1u : 0u;
 #pragma unroll
               for (int ks = 0; ks < 2; ++ks) {
-                const uint64_t adesc = ((uint64_t)a_hi32 << 32) | (a0 + 2 * ks * A_LBO + 8 * t);
                 const uint64_t bdesc = ((uint64_t)b_hi32 << 32) | (b0 + 2 * ks * B_LBO);
                 const uint32_t first = ks ? 1u : acc0;
-                if (PASSES == 1) {
-                  ptx::mma_f16(d, adesc, bdesc, idesc, first);
-                } else {
-                  const uint64_t adesc_lo = ((uint64_t)a_hi32 << 32) | (a0 + (4 + 2 * ks) * A_LBO + 8 * t);
-                  if (C::NCAT) {
-                    ptx::mma_f16(d, adesc, bdesc, idesc_cat, first);       // a_hi x [w_hi | w_lo]
-                    ptx::mma_f16(d, adesc_lo, bdesc, idesc, 1u);           // a_lo x  w_hi
-                  } else {
+#pragma unroll
+                for (int t = 0; t < T; ++t) {
+                  const uint64_t adesc = ((uint64_t)a_hi32 << 32) | ((a0 + 32 * t + 2 * ks) & 0x3FFFu) | (1u << 16);
+                  ptx::mma_f16(dbase + t * C::DCOLS, adesc, bdesc, C::NCAT ? idesc_cat : idesc, first);
+                }
+                if (PASSES == 3) {
+#pragma unroll
+                  for (int t = 0; t < T; ++t) {
+                    const uint64_t adesc_lo = ((uint64_t)a_hi32 << 32) | ((a0 + 32 * t + 2 * ks + (C::A_PLANE >> 4)) & 0x3FFFu) | (1u << 16);
+                    ptx::mma_f16(dbase + t * C::DCOLS, adesc_lo, bdesc, idesc, 1u);
+                  }
+                  if (!C::NCAT) {
                     const uint64_t bdesc_lo = ((uint64_t)b_hi32 << 32) | (b0 + 2 * ks * B_LBO + COUT);
-                    ptx::mma_f16(d, adesc, bdesc, idesc, first);
-                    ptx::mma_f16(d, adesc_lo, bdesc, idesc, 1u);
-                    ptx::mma_f16(d, adesc, bdesc_lo, idesc, 1u);
+#pragma unroll
+                    for (int t = 0; t < T; ++t) {
+                      const uint64_t adesc = ((uint64_t)a_hi32 << 32) | ((a0 + 32 * t + 2 * ks) & 0x3FFFu) | (1u << 16);
+                      ptx::mma_f16(dbase + t * C::DCOLS, adesc, bdesc_lo, idesc, 1u);
+                    }
                   }
                 }
               }
             }
-            ptx::tc_commit(&w_empty[sw]);                                   // weight slab free once these MMAs have read it
-            if (tap == C::TAPS - 1) {
+            ptx::tc_commit(&w_empty[sw]);                                   // weight row free once these MMAs have read it
+            if (dy == KS - 1) {
               ptx::tc_commit(&a_empty[sa]);                                 // activation chunk free
               if (c == C::NCHUNK - 1) ptx::tc_commit(&acc_full[as]);        // tile complete -> epilogue
             }
@@ -377,10 +403,10 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
                   lo[e] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
                 }
               }
-              const int j = (n0 >> 3) + jj;
+              const int chunk = n0 >> 5, within = (n0 & 31) + jj * 8;
               for (int a = 0; a < nys; ++a)
                 for (int b = 0; b < nxs; ++b) {
-                  const long long off = ((((long long)img * P.out_J + j) * HPo + ys[a]) * WPo + xs[b]) * 8;
+                  const long long off = ((((long long)img * P.out_nch + chunk) * HPo + ys[a]) * WPo + xs[b]) * 32 + within;
                   *reinterpret_cast<uint4*>(P.out_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                   if (OUTMODE == TC_OUT_HILO) *reinterpret_cast<uint4*>(P.out_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                 }
@@ -396,25 +422,28 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
 }
 
 // Layer-1 pre-pass: 5x5 circular im2col of the fp32 network input (B, CIN0, ny, nx) into the canonical activation
-// layout [img][KP/8][ny][nx][8] (hi and lo planes), K index = tap*CIN0 + channel, zero padded to KP.
+// layout [img][KP/32][ny][nx][32] (hi and lo planes), K index = tap*CIN0 + channel, zero padded to KP.
+// One thread per 16 B (8 K values); 4 consecutive threads write the 64 B of one pixel.
 __global__ void im2col5_kernel(const float* __restrict__ x, long long x_bs, int cin0, int KP, __half* __restrict__ out_hi,
                                __half* __restrict__ out_lo, int batch, int ny, int nx) {
-  const int J = KP / 8;
-  const long long total = (long long)batch * J * ny * nx;
+  const int NCH = KP / 32;
+  const long long total = (long long)batch * NCH * ny * nx * 4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int xx = (int)(i % nx), yy = (int)((i / nx) % ny), j = (int)((i / ((long long)nx * ny)) % J);
-    const int img = (int)(i / ((long long)nx * ny * J));
+    const int j4 = (int)(i & 3);
+    const long long pix = i >> 2;
+    const int xx = (int)(pix % nx), yy = (int)((pix / nx) % ny), ch = (int)((pix / ((long long)nx * ny)) % NCH);
+    const int img = (int)(pix / ((long long)nx * ny * NCH));
     uint32_t hi[4], lo[4];
     float f[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const int kk = j * 8 + e, tap = kk / cin0, ch = kk - tap * cin0;
+      const int kk = ch * 32 + j4 * 8 + e, tap = kk / cin0, cc = kk - tap * cin0;
       float v = 0.f;
       if (tap < 25) {
         int sy = yy + tap / 5 - 2, sx = xx + tap % 5 - 2;
         sy = sy < 0 ? sy + ny : (sy >= ny ? sy - ny : sy);
         sx = sx < 0 ? sx + nx : (sx >= nx ? sx - nx : sx);
-        v = x[(long long)img * x_bs + ((long long)ch * ny + sy) * nx + sx];
+        v = x[(long long)img * x_bs + ((long long)cc * ny + sy) * nx + sx];
       }
       f[e] = v;
     }
@@ -555,25 +584,25 @@ inline PFN_tmapEncodeTiled tmap_encoder() {
   }
   return fn;
 }
-// 3-D map over an activation plane [nj][HP][WP][8 halves] viewed as uint32 words, box = (hx*4, hy, 4)
-inline bool tc_make_map(CUtensorMap* m, const __half* base, int WP, int HP, long long nj, int hx, int hy) {
+// 4-D map over an activation plane [nchunks][HP][WP][32 halves], box = (32, hx, hy, 1), 64-byte swizzle
+inline bool tc_make_map(CUtensorMap* m, const __half* base, int WP, int HP, long long nchunks, int hx, int hy) {
   PFN_tmapEncodeTiled enc = tmap_encoder();
   if (!enc) return false;
-  cuuint64_t gdim[3] = {(cuuint64_t)WP * 4, (cuuint64_t)HP, (cuuint64_t)nj};
-  cuuint64_t gstr[2] = {(cuuint64_t)WP * 16, (cuuint64_t)HP * WP * 16};
-  cuuint32_t box[3] = {(cuuint32_t)hx * 4, (cuuint32_t)hy, 4};
-  cuuint32_t estr[3] = {1, 1, 1};
-  return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  cuuint64_t gdim[4] = {32, (cuuint64_t)WP, (cuuint64_t)HP, (cuuint64_t)nchunks};
+  cuuint64_t gstr[3] = {64, (cuuint64_t)WP * 64, (cuuint64_t)HP * WP * 64};
+  cuuint32_t box[4] = {32, (cuuint32_t)hx, (cuuint32_t)hy, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 template <int CIN, int COUT, int KS, int PASSES, int T, int OUTMODE>
 inline cudaError_t tc_launch(const TcConvParams& P, int nimg, int nsm, cudaStream_t st) {
   using C = TcCfg<CIN, COUT, KS, PASSES, T>;
   TcMaps M;
-  if (!tc_make_map(&M.hi, P.in_hi, P.WP, P.HP, (long long)nimg * P.J_in, C::HX, C::HY)) return cudaErrorInvalidValue;
+  if (!tc_make_map(&M.hi, P.in_hi, P.WP, P.HP, (long long)nimg * P.nch_in, C::HX, C::HY)) return cudaErrorInvalidValue;
   if (C::PLANES == 2) {
-    if (!tc_make_map(&M.lo, P.in_lo, P.WP, P.HP, (long long)nimg * P.J_in, C::HX, C::HY)) return cudaErrorInvalidValue;
+    if (!tc_make_map(&M.lo, P.in_lo, P.WP, P.HP, (long long)nimg * P.nch_in, C::HX, C::HY)) return cudaErrorInvalidValue;
   } else {
     M.lo = M.hi;
   }
@@ -617,7 +646,7 @@ inline int tc_forward(const TcNet& net, TcWorkspace& ws, const float* x, long lo
   for (int b0 = 0; b0 < batch; b0 += chunk) {
     const int nb = batch - b0 < chunk ? batch - b0 : chunk;
     {
-      const long long total = (long long)nb * (net.kp / 8) * ny * nx;
+      const long long total = (long long)nb * (net.kp / 8) * ny * nx;   // one thread per 16 B
       int blocks = (int)((total + 255) / 256);
       if (blocks > nsm * 16) blocks = nsm * 16;
       im2col5_kernel<<<blocks, 256, 0, st>>>(x + (long long)b0 * x_bs, x_bs, net.cin0, net.kp, a0h, a0l, nb, ny, nx);
@@ -629,12 +658,12 @@ inline int tc_forward(const TcNet& net, TcWorkspace& ws, const float* x, long lo
       P.w = L.w; P.bias = L.bias; P.bn_s = L.bn_s; P.bn_t = L.bn_t; P.inv_wscale = L.inv_wscale; P.relu_bn = L.relu_bn;
       P.ny = ny; P.nx = nx; P.tiles_y = ny / 16;
       P.out_f32 = nullptr; P.out_bs = 0; P.out_c = 0; P.softplus = 0; P.accumulate = 0;
-      P.out_hi = P.out_lo = nullptr; P.out_pad = 0; P.out_J = 0;
+      P.out_hi = P.out_lo = nullptr; P.out_pad = 0; P.out_nch = 0;
       const int Tl = li == 0 ? 2 : T;
       P.tiles_x = nx / (8 * Tl);
       P.num_tiles = nb * P.tiles_y * P.tiles_x;
       const int pad = L.ks / 2;
-      P.J_in = L.cin / 8; P.HP = ny + 2 * pad; P.WP = nx + 2 * pad;
+      P.nch_in = L.cin / 32; P.HP = ny + 2 * pad; P.WP = nx + 2 * pad;
       // buffer rotation: a0 -> ping(hi) -> pong(hi,lo) -> ping(hi,lo) -> pong -> ping -> pong -> ping -> y
       if (li == 0) { P.in_hi = a0h; P.in_lo = a0l; }
       else if (li & 1) { P.in_hi = ping_h; P.in_lo = ping_l; }
@@ -642,7 +671,7 @@ inline int tc_forward(const TcNet& net, TcWorkspace& ws, const float* x, long lo
       if (li < 7) {
         if (li & 1) { P.out_hi = pong_h; P.out_lo = pong_l; } else { P.out_hi = ping_h; P.out_lo = ping_l; }
         P.out_pad = net.layers[li + 1].ks / 2;
-        P.out_J = L.cout / 8;
+        P.out_nch = L.cout / 32;
       } else {
         P.out_f32 = y + (long long)b0 * y_bs; P.out_bs = y_bs; P.out_c = L.real_cout; P.softplus = softplus; P.accumulate = accumulate;
       }
