@@ -191,7 +191,7 @@ int net_forward(qgb_handle* h, int net, const float* x, long long x_bs, float* y
     h->tcw.prof_images = &h->prof_images;
     int rc = tc_forward(h->nets[net].tc, h->tcw, x, x_bs, y, y_bs, batch, ny, nx, softplus, accumulate, h->nsm, st, &e);
     if (rc != 0) return fail(h, rc, "%s", e.c_str());
-    g_launches.fetch_add(tc_launches_per_forward(h->nets[net].tc), std::memory_order_relaxed);
+    g_launches.fetch_add(h->tcw.last_launches, std::memory_order_relaxed);
     return QGB_OK;
   }
   return net_forward_fp32(h, h->nets[net], x, x_bs, y, y_bs, batch, ny, nx, softplus, accumulate, st);

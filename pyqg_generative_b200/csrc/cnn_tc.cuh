@@ -190,7 +190,7 @@ struct TcMaps {
 };
 
 template <int CIN, int COUT, int KS, int PASSES, int T, int OUTMODE>
-__global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__ TcConvParams P,
+__global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__ TcConvParams P,
                                                          const __grid_constant__ TcMaps M) {
   using C = TcCfg<CIN, COUT, KS, PASSES, T>;
   extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(&a_full[i], 1); ptx::mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < C::NW; ++i) { ptx::mbar_init(&w_full[i], 1); ptx::mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], 128); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], 256); }
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc(tmem_slot, C::NCOLS);
@@ -336,6 +336,7 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
   } else if (warp >= 4) {
     // ===================== epilogue: TMEM -> registers -> bias/ReLU/BN -> fp16 hi/lo (or fp32) -> HBM ==============
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int half = (warp - 4) >> 2;             // two warps share a lane quarter and split the (t, 16-column) items
     const int m = q * 32 + lane;                  // accumulator row = pixel inside the 16 x 8 M-tile
     const int prow = m >> 3, pcol = m & 7;
     uint32_t it = 0;
@@ -346,12 +347,13 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
       ptx::mbar_wait(&acc_full[as], (it >> 1) & 1);
       ptx::tc_fence_after();
       const int y = y0 + prow;
+      constexpr int NB16 = COUT / 16, ITEMS = T * NB16;
 #pragma unroll 1
-      for (int t = 0; t < T; ++t) {
+      for (int item = half; item < ITEMS; item += 2) {
+        const int t = item / NB16, n0 = (item - t * NB16) * 16;
         const int x = x0 + 8 * t + pcol;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * (T * C::DCOLS) + t * C::DCOLS;
-#pragma unroll 1
-        for (int n0 = 0; n0 < COUT; n0 += 16) {
+        {
           uint32_t rr[16];
           ptx::tmem_ld16(taddr + n0, rr);
           if (C::NCAT) {
@@ -362,7 +364,7 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
             for (int i = 0; i < 16; ++i) rr[i] = __float_as_uint(__uint_as_float(rr[i]) + __uint_as_float(r2[i]));
           }
           ptx::tmem_ld_wait();
-          if (t == T - 1 && n0 + 16 >= COUT) {     // last read of this accumulator set: hand it back to the MMA warp
+          if (item + 2 >= ITEMS) {                 // last read of this accumulator set by this thread: hand it back
             ptx::tc_fence_before();
             ptx::mbar_arrive(&acc_empty[as]);
           }
@@ -423,30 +425,35 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
 
 // Layer-1 pre-pass: 5x5 circular im2col of the fp32 network input (B, CIN0, ny, nx) into the canonical activation
 // layout [img][KP/32][ny][nx][32] (hi and lo planes), K index = tap*CIN0 + channel, zero padded to KP.
-// One thread per 16 B (8 K values); 4 consecutive threads write the 64 B of one pixel.
-__global__ void im2col5_kernel(const float* __restrict__ x, long long x_bs, int cin0, int KP, __half* __restrict__ out_hi,
-                               __half* __restrict__ out_lo, int batch, int ny, int nx) {
-  const int NCH = KP / 32;
-  const long long total = (long long)batch * NCH * ny * nx * 4;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int j4 = (int)(i & 3);
-    const long long pix = i >> 2;
-    const int xx = (int)(pix % nx), yy = (int)((pix / nx) % ny), ch = (int)((pix / ((long long)nx * ny)) % NCH);
-    const int img = (int)(pix / ((long long)nx * ny * NCH));
-    uint32_t hi[4], lo[4];
+// One CTA = IM2COL_ROWS image rows of one image: the (rows+4) x (nx+4) x CIN0 input window is staged in shared memory
+// (circular wrap applied once), then every thread emits 16-byte pieces (8 K values); 4 consecutive threads write the
+// 64 contiguous bytes of one pixel, so global stores are fully coalesced.
+constexpr int IM2COL_ROWS = 4;
+__global__ void __launch_bounds__(256) im2col5_kernel(const float* __restrict__ x, long long x_bs, int cin0, int KP,
+                                                      __half* __restrict__ out_hi, __half* __restrict__ out_lo, int ny, int nx) {
+  extern __shared__ float s_in[];                         // [cin0][IM2COL_ROWS+4][nx+4]
+  const int NCH = KP / 32, W = nx + 4, R = IM2COL_ROWS + 4;
+  const int img = blockIdx.y, y0 = blockIdx.x * IM2COL_ROWS;
+  const float* xb = x + (long long)img * x_bs;
+  for (int i = threadIdx.x; i < cin0 * R * W; i += blockDim.x) {
+    const int c = i / (R * W), r = (i / W) % R, col = i % W;
+    int sy = y0 + r - 2, sx = col - 2;
+    sy = sy < 0 ? sy + ny : (sy >= ny ? sy - ny : sy);
+    sx = sx < 0 ? sx + nx : (sx >= nx ? sx - nx : sx);
+    s_in[i] = xb[((long long)c * ny + sy) * nx + sx];
+  }
+  __syncthreads();
+  const int per_chunk = IM2COL_ROWS * nx * 4;             // 16-byte pieces per 32-K chunk
+  for (int i = threadIdx.x; i < NCH * per_chunk; i += blockDim.x) {
+    const int ch = i / per_chunk, rem = i - ch * per_chunk;
+    const int j4 = rem & 3, xx = (rem >> 2) % nx, ry = (rem >> 2) / nx;
     float f[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int kk = ch * 32 + j4 * 8 + e, tap = kk / cin0, cc = kk - tap * cin0;
-      float v = 0.f;
-      if (tap < 25) {
-        int sy = yy + tap / 5 - 2, sx = xx + tap % 5 - 2;
-        sy = sy < 0 ? sy + ny : (sy >= ny ? sy - ny : sy);
-        sx = sx < 0 ? sx + nx : (sx >= nx ? sx - nx : sx);
-        v = x[(long long)img * x_bs + ((long long)cc * ny + sy) * nx + sx];
-      }
-      f[e] = v;
+      f[e] = tap < 25 ? s_in[(cc * R + ry + tap / 5) * W + xx + tap % 5] : 0.f;
     }
+    uint32_t hi[4], lo[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const __half h0 = __float2half_rn(f[2 * e]), h1 = __float2half_rn(f[2 * e + 1]);
@@ -454,8 +461,9 @@ __global__ void im2col5_kernel(const float* __restrict__ x, long long x_bs, int 
       hi[e] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
       lo[e] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
     }
-    *reinterpret_cast<uint4*>(out_hi + i * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    *reinterpret_cast<uint4*>(out_lo + i * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    const long long off = ((((long long)img * NCH + ch) * ny + y0 + ry) * nx + xx) * 32 + j4 * 8;
+    *reinterpret_cast<uint4*>(out_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(out_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   }
 }
 
@@ -480,6 +488,7 @@ struct TcWorkspace {
   int prof_layer = -1;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>>* prof_events = nullptr;
   long long* prof_images = nullptr;
+  long long last_launches = 0;   // kernels launched by the latest tc_forward
 };
 
 inline void tc_free_net(TcNet& n) {
@@ -614,7 +623,7 @@ inline cudaError_t tc_launch(const TcConvParams& P, int nimg, int nsm, cudaStrea
     configured = true;
   }
   const int grid = P.num_tiles < nsm ? P.num_tiles : nsm;
-  kern<<<grid, 256, C::SMEM, st>>>(P, M);
+  kern<<<grid, 384, C::SMEM, st>>>(P, M);
   return cudaGetLastError();
 }
 
@@ -630,7 +639,13 @@ inline int tc_forward(const TcNet& net, TcWorkspace& ws, const float* x, long lo
   if (!net.ready) { *err = "tcgen05 path: network not packed"; return QGB_EUNSUPPORTED; }
   if (ny % 16 || nx % 16) { *err = "tcgen05 path needs ny and nx to be multiples of 16 (use precision='fp32')"; return QGB_EUNSUPPORTED; }
   const int T = nx % 32 == 0 ? 4 : (nx % 24 == 0 ? 3 : 2);
-  const int chunk = batch < 128 ? batch : 128;
+  // Images per launch: large launches amortise the persistent-CTA ramp/tail (measured on B200, 64^2: 128 -> 150 k,
+  // 1024 -> 162 k member-steps/s); the workspace is capped at ~6 GB.
+  static int max_chunk = 0;
+  if (!max_chunk) { const char* e = getenv("QGB_TC_CHUNK"); max_chunk = e ? atoi(e) : 1024; if (max_chunk < 1) max_chunk = 1024; }
+  const size_t per_img = (2 * (size_t)net.kp * ny * nx + 128 * (size_t)(ny + 4) * (nx + 4) + 160 * (size_t)(ny + 2) * (nx + 2)) * 2;
+  int chunk = batch < max_chunk ? batch : max_chunk;
+  while (chunk > 1 && (size_t)chunk * per_img > (6ull << 30)) chunk = (chunk + 1) / 2;
   // workspace: a0 (im2col, hi/lo), ping (<=128 ch, halo 2), pong (<=64 ch, halo 1)
   const size_t need[6] = {(size_t)chunk * net.kp * ny * nx, (size_t)chunk * net.kp * ny * nx,
                           (size_t)chunk * 128 * (ny + 4) * (nx + 4), (size_t)chunk * 32 * (ny + 2) * (nx + 2),
@@ -642,15 +657,16 @@ inline int tc_forward(const TcNet& net, TcWorkspace& ws, const float* x, long lo
       if (cudaMalloc(&ws.buf[i], need[i] * sizeof(__half)) != cudaSuccess) { *err = "cudaMalloc failed (tc workspace)"; return QGB_ECUDA; }
       ws.halves[i] = need[i];
     }
+  ws.last_launches = 0;
   __half *a0h = ws.buf[0], *a0l = ws.buf[1], *ping_h = ws.buf[2], *ping_l = ws.buf[3], *pong_h = ws.buf[4], *pong_l = ws.buf[5];
   for (int b0 = 0; b0 < batch; b0 += chunk) {
     const int nb = batch - b0 < chunk ? batch - b0 : chunk;
     {
-      const long long total = (long long)nb * (net.kp / 8) * ny * nx;   // one thread per 16 B
-      int blocks = (int)((total + 255) / 256);
-      if (blocks > nsm * 16) blocks = nsm * 16;
-      im2col5_kernel<<<blocks, 256, 0, st>>>(x + (long long)b0 * x_bs, x_bs, net.cin0, net.kp, a0h, a0l, nb, ny, nx);
+      dim3 grid(ny / IM2COL_ROWS, nb);
+      const size_t sh = (size_t)net.cin0 * (IM2COL_ROWS + 4) * (nx + 4) * sizeof(float);
+      im2col5_kernel<<<grid, 256, sh, st>>>(x + (long long)b0 * x_bs, x_bs, net.cin0, net.kp, a0h, a0l, ny, nx);
       if (cudaGetLastError() != cudaSuccess) { *err = "im2col launch failed"; return QGB_ECUDA; }
+      ws.last_launches += 1;
     }
     for (int li = 0; li < 8; ++li) {
       const TcLayer& L = net.layers[li];
@@ -686,6 +702,7 @@ inline int tc_forward(const TcNet& net, TcWorkspace& ws, const float* x, long lo
       else if (li < 7) e = tc_launch_T<32, 32, 3, 3, TC_OUT_HILO>(T, P, nb, nsm, st);
       else e = tc_launch_T<32, 16, 3, 3, TC_OUT_FINAL>(T, P, nb, nsm, st);
       if (prof) { cudaEventRecord(ev1, st); ws.prof_events->emplace_back(ev0, ev1); *ws.prof_images += nb; }
+      ws.last_launches += 1;
       if (e != cudaSuccess) { *err = std::string("tcgen05 conv launch failed: ") + cudaGetErrorString(e); return QGB_ECUDA; }
     }
   }
