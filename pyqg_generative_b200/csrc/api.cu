@@ -50,6 +50,7 @@ struct qgb_handle {
   double *d_kespec = nullptr, *d_ensspec = nullptr;
   long long tc = 0; double t = 0.0; int ablevel = 0;
   int nthreads = 256; size_t smem = 0; int grid = 0;
+  bool large = false; cplx* scratch = nullptr; double* red_scratch = nullptr;   // cluster path for nx > 96
   // closure
   int kind = QGB_CLOSURE_NONE; int precision = QGB_PREC_FP32;
   DevNet nets[2];
@@ -116,6 +117,23 @@ StepIO base_io(qgb_handle* h) {
 }
 
 int launch_program(qgb_handle* h, const StepIO& io, int prog, cudaStream_t st) {
+  if (h->large) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(h->grid);
+    cfg.blockDim = dim3(h->nthreads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kClusterSize;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CUDA_TRY(h, cudaLaunchKernelEx(&cfg, qg_program_cluster_kernel, h->T, io, prog, h->cfg.members, h->scratch, h->red_scratch));
+    QGB_COUNT_LAUNCH();
+    return QGB_OK;
+  }
   qg_program_kernel<<<h->grid, h->nthreads, h->smem, st>>>(h->T, io, prog, h->cfg.members);
   QGB_COUNT_LAUNCH();
   CUDA_TRY(h, cudaGetLastError());
@@ -400,14 +418,24 @@ int qgb_create(const qgb_config* cfg, qgb_handle** out) {
   h->nsm = prop.multiProcessorCount;
   h->nthreads = cfg->nx >= 96 ? 512 : 256;
   h->smem = program_smem_bytes(h->ht.N, h->ht.P, h->nthreads);
-  if (h->smem > (size_t)prop.sharedMemPerBlockOptin) {
-    fail(nullptr, QGB_EUNSUPPORTED, "nx=%d needs %zu B of shared memory per CTA (> %zu): the fused path covers nx<=96",
-         cfg->nx, h->smem, (size_t)prop.sharedMemPerBlockOptin);
+  h->large = h->smem > (size_t)prop.sharedMemPerBlockOptin;
+  if (h->large && cfg->nx > 1024) {
+    fail(nullptr, QGB_EUNSUPPORTED, "nx=%d unsupported (the cluster path covers nx <= 1024)", cfg->nx);
     qgb_destroy(h);
     return QGB_EUNSUPPORTED;
   }
-  CR(cudaFuncSetAttribute(qg_program_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+  if (!h->large) CR(cudaFuncSetAttribute(qg_program_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
   h->grid = cfg->members;
+  if (h->large) {
+    // one cluster of kClusterSize CTAs per member, persistent over members when the ensemble exceeds the machine
+    h->nthreads = 512;
+    int clusters = (2 * h->nsm) / kClusterSize;
+    if (clusters > cfg->members) clusters = cfg->members;
+    if (clusters < 1) clusters = 1;
+    h->grid = clusters * kClusterSize;
+    CR(dalloc(&h->scratch, (size_t)cfg->members * h->ht.N * h->ht.P));
+    CR(dalloc(&h->red_scratch, (size_t)cfg->members * 4 * kClusterSize * h->nthreads));
+  }
   CR(upload(&h->d_tw, h->ht.tw));
   CR(upload(&h->d_pos, h->ht.pos));
   CR(upload(&h->d_kv, h->ht.kv));
@@ -430,7 +458,7 @@ void qgb_destroy(qgb_handle* h) {
   if (!h) return;
   cudaSetDevice(h->cfg.device);
   cudaFree(h->d_tw); cudaFree(h->d_pos); cudaFree(h->d_kv); cudaFree(h->d_lv); cudaFree(h->d_a); cudaFree(h->d_filtr);
-  cudaFree(h->qh); cudaFree(h->q);
+  cudaFree(h->qh); cudaFree(h->q); cudaFree(h->scratch); cudaFree(h->red_scratch);
   for (int i = 0; i < 3; ++i) cudaFree(h->hist[i]);
   cudaFree(h->ph); cudaFree(h->u); cudaFree(h->v); cudaFree(h->p); cudaFree(h->red);
   cudaFree(h->d_ke); cudaFree(h->d_cfl); cudaFree(h->d_flags); cudaFree(h->d_kespec); cudaFree(h->d_ensspec);

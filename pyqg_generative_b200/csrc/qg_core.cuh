@@ -175,6 +175,7 @@ QGB_HD void fft2d_phase(const Ctx& c, int ph, bool inverse, int tid, int nt) {
 // pointwise phases
 // ------------------------------------------------------------------------------------------------------
 QGB_HD void ph_init(const Ctx& c, int tid, int nt) {
+  if (c.tw == c.T.tw) return;   // large-N path: tables are used in place (global memory), nothing to stage
   for (int i = tid; i < c.T.N; i += nt) {
     c.tw[i] = c.T.tw[i];
     c.pos[i] = c.T.pos[i];

@@ -34,6 +34,38 @@ __global__ void __launch_bounds__(512) qg_program_kernel(const __grid_constant__
   }
 }
 
+// Large grids (N = 128, 256: the packed field is 0.26 / 1.0 MB and no longer fits one CTA's shared memory): the SAME phase
+// programs run with the working field in a per-member global-memory scratch (L2 resident: 64 members x 1 MB at 256^2)
+// and a thread-block CLUSTER of kClusterSize CTAs per member.  Threads are numbered across the cluster, phases are separated
+// by the hardware cluster barrier (release/acquire at cluster scope, which also invalidates L1), tables are read in place.
+constexpr int kClusterSize = 8;
+
+__device__ __forceinline__ void cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+
+__global__ void __launch_bounds__(512) qg_program_cluster_kernel(const __grid_constant__ Tables T,
+                                                                 const __grid_constant__ StepIO io, int prog, int members,
+                                                                 cplx* scratch, double* red_scratch) {
+  const int rank = (int)cluster_ctarank();
+  const int ncl = gridDim.x / kClusterSize, cl = blockIdx.x / kClusterSize;
+  const int tid = rank * blockDim.x + threadIdx.x, nt = kClusterSize * blockDim.x;
+  for (int m = cl; m < members; m += ncl) {
+    Ctx c{T, io, scratch + (size_t)m * T.N * T.P, const_cast<cplx*>(T.tw), const_cast<short*>(T.pos),
+          red_scratch + (size_t)m * 4 * nt, m};
+    const int nph = run_program(c, prog, -1, tid, nt);
+    for (int ph = 0; ph < nph; ++ph) {
+      run_program(c, prog, ph, tid, nt);
+      cluster_barrier();
+    }
+  }
+}
+
 // ke / cfl / flags from the per-member reduction record written by PROG_DIAG
 __global__ void diag_finish_kernel(const double* __restrict__ red, int members, double dt_over_dx, double* ke,
                                    double* cfl, int* flags) {

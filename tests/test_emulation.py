@@ -31,7 +31,8 @@ def rel(a, b):
     return np.abs(a - b).max() / np.abs(b).max()
 
 
-@pytest.mark.parametrize('N,dt,jet', [(64, 14400., False), (48, 7200., True), (96, 7200., False), (32, 14400., False)])
+@pytest.mark.parametrize('N,dt,jet', [(64, 14400., False), (48, 7200., True), (96, 7200., False), (32, 14400., False),
+                                      (128, 7200., True)])
 def test_programs_match_oracle(emu_lib, N, dt, jet):
     rng = np.random.RandomState(N)
     phys = dict(rek=7e-8, delta=0.1, beta=1e-11) if jet else dict(rek=5.787e-7, delta=0.25, beta=1.5e-11)

@@ -169,7 +169,7 @@ def test_error_paths_match_reference_exceptions(tmp_path):
     with pytest.raises(RuntimeError):
         m.closure_eval()                                  # no closure loaded
     with pytest.raises(NotImplementedError):
-        EnsembleQGModel(members=1, nx=192)                # fused path covers nx <= 96
+        EnsembleQGModel(members=1, nx=2048)               # cluster path covers nx <= 1024
     with pytest.raises(ValueError):
         EnsembleQGModel(members=1, nx=50)                 # 50 = 2 * 5^2: unsupported radix
 

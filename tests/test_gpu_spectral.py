@@ -21,7 +21,8 @@ def make(nx, members, **kw):
 
 
 @pytest.mark.parametrize('N,dt,phys', [
-    (64, 14400., {}), (48, 14400., dict(rek=7e-8, delta=0.1, beta=1e-11)), (96, 7200., {}), (32, 14400., {})])
+    (64, 14400., {}), (48, 14400., dict(rek=7e-8, delta=0.1, beta=1e-11)), (96, 7200., {}), (32, 14400., {}),
+    (128, 7200., {}), (256, 3600., dict(rek=7e-8, delta=0.1, beta=1e-11))])     # 128/256: thread-block-cluster path
 def test_set_q_invert_and_steps_match_oracle(N, dt, phys):
     rng = np.random.RandomState(N)
     B = 3
