@@ -116,7 +116,8 @@ StepIO base_io(qgb_handle* h) {
   return io;
 }
 
-int launch_program(qgb_handle* h, const StepIO& io, int prog, cudaStream_t st) {
+int launch_program(qgb_handle* h, const StepIO& io, int prog, cudaStream_t st, const Tables* Tov = nullptr) {
+  const Tables& TT = Tov ? *Tov : h->T;
   if (h->large) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(h->grid);
@@ -130,11 +131,11 @@ int launch_program(qgb_handle* h, const StepIO& io, int prog, cudaStream_t st) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    CUDA_TRY(h, cudaLaunchKernelEx(&cfg, qg_program_cluster_kernel, h->T, io, prog, h->cfg.members, h->scratch, h->red_scratch));
+    CUDA_TRY(h, cudaLaunchKernelEx(&cfg, qg_program_cluster_kernel, TT, io, prog, h->cfg.members, h->scratch, h->red_scratch));
     QGB_COUNT_LAUNCH();
     return QGB_OK;
   }
-  qg_program_kernel<<<h->grid, h->nthreads, h->smem, st>>>(h->T, io, prog, h->cfg.members);
+  qg_program_kernel<<<h->grid, h->nthreads, h->smem, st>>>(TT, io, prog, h->cfg.members);
   QGB_COUNT_LAUNCH();
   CUDA_TRY(h, cudaGetLastError());
   return QGB_OK;
@@ -785,24 +786,115 @@ int qgb_diag_spectra(qgb_handle* h, double* kespec, double* ensspec, int on_devi
   return QGB_OK;
 }
 
-// ---- coarse-graining (operators.cuh) -----------------------------------------------------------------------------
+// ---- coarse-graining (operators.cuh + the phase programs) --------------------------------------------------------
+namespace {
+struct HandleGuard {
+  qgb_handle* h = nullptr;
+  ~HandleGuard() { if (h) qgb_destroy(h); }
+};
+int grid_for(long long n) { long long b = (n + 255) / 256; return (int)(b > 148 * 16 ? 148 * 16 : (b < 1 ? 1 : b)); }
+Tables no_background(const Tables& T) {   // advect(var, u, v) uses anomaly velocities and no beta / drag terms
+  Tables t = T;
+  t.Ubg[0] = t.Ubg[1] = 0.0; t.Qy[0] = t.Qy[1] = 0.0; t.rek = 0.0;
+  return t;
+}
+}  // namespace
+
 int qgb_operator(int device, int op, int n, int nc, int batch, const double* in, double* out, int on_device,
                  void* stream) {
-  std::string e;
-  long long launches = 0;
-  int rc = op_coarsegrain(device, op, n, nc, batch, in, out, on_device, S(stream), &launches, &e);
-  g_launches.fetch_add(launches, std::memory_order_relaxed);
-  if (rc) return fail(nullptr, rc, "%s", e.c_str());
+  if (!in || !out || batch < 1) return fail(nullptr, QGB_EINVAL, "bad argument");
+  if (op != 1 && op != 2 && op != 5) return fail(nullptr, QGB_EINVAL, "operator %d not supported (1, 2, 5)", op);
+  if (nc % 2 != 0) return fail(nullptr, QGB_EINVAL, "nc must be even");
+  if (nc > n || nc < 4) return fail(nullptr, QGB_EINVAL, "nc must satisfy 4 <= nc <= n");
+  cudaStream_t st = S(stream);
+  const int pairs = (batch + 1) / 2;
+  qgb_config cf, cc;
+  qgb_default_config(&cf);
+  cf.device = device; cf.members = pairs; cf.nx = n;
+  cc = cf; cc.nx = nc;
+  HandleGuard gf, gc;
+  int rc = qgb_create(&cf, &gf.h);
+  if (rc) return rc;
+  rc = qgb_create(&cc, &gc.h);
+  if (rc) return rc;
+  qgb_handle *hf = gf.h, *hc = gc.h;
+  const cudaMemcpyKind kin = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  const cudaMemcpyKind kout = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  CUDA_TRY(nullptr, cudaMemsetAsync(hf->q, 0, nreal(hf) * sizeof(double), st));
+  CUDA_TRY(nullptr, cudaMemcpyAsync(hf->q, in, (size_t)batch * n * n * sizeof(double), kin, st));
+  StepIO io = base_io(hf);
+  rc = launch_program(hf, io, PROG_SET_Q, st);                       // rfft2 of the field pairs
+  if (rc) return fail(nullptr, rc, "%s", hf->err.c_str());
+  const long long tot = (long long)2 * pairs * nc * (nc / 2 + 1);
+  trunc_filter_kernel<<<grid_for(tot), 256, 0, st>>>(hf->qh, hc->qh, 2 * pairs, n, nc, op, cf.L, 1.0);
+  QGB_COUNT_LAUNCH();
+  CUDA_TRY(nullptr, cudaGetLastError());
+  StepIO ioc = base_io(hc);
+  rc = launch_program(hc, ioc, PROG_C2R, st);                        // irfft2 on the coarse grid
+  if (rc) return fail(nullptr, rc, "%s", hc->err.c_str());
+  CUDA_TRY(nullptr, cudaMemcpyAsync(out, hc->q, (size_t)batch * nc * nc * sizeof(double), kout, st));
+  CUDA_TRY(nullptr, cudaStreamSynchronize(st));
   return QGB_OK;
 }
 
 int qgb_subgrid_forcing(const qgb_config* cfg, int op, int nc, int batch, const double* q, double* forcing,
                         double* qf, double* uf, double* vf, double* pf, int on_device, void* stream) {
-  std::string e;
-  long long launches = 0;
-  int rc = op_subgrid_forcing(cfg, op, nc, batch, q, forcing, qf, uf, vf, pf, on_device, S(stream), &launches, &e);
-  g_launches.fetch_add(launches, std::memory_order_relaxed);
-  if (rc) return fail(nullptr, rc, "%s", e.c_str());
+  if (!cfg || !q || batch < 1) return fail(nullptr, QGB_EINVAL, "bad argument");
+  if (op != 1 && op != 2 && op != 5) return fail(nullptr, QGB_EINVAL, "operator %d not supported (1, 2, 5)", op);
+  const int n = cfg->nx;
+  if (nc % 2 != 0) return fail(nullptr, QGB_EINVAL, "nc must be even");
+  if (nc > n || nc < 4) return fail(nullptr, QGB_EINVAL, "nc must satisfy 4 <= nc <= n");
+  cudaStream_t st = S(stream);
+  qgb_config cf = *cfg, cc = *cfg;
+  cf.members = batch; cc.members = batch; cc.nx = nc;
+  HandleGuard gf, gc;
+  int rc = qgb_create(&cf, &gf.h);
+  if (rc) return rc;
+  rc = qgb_create(&cc, &gc.h);
+  if (rc) return rc;
+  qgb_handle *hf = gf.h, *hc = gc.h;
+  const cudaMemcpyKind kin = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  const cudaMemcpyKind kout = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  const Tables T0f = no_background(hf->T), T0c = no_background(hc->T);
+  const long long totc = (long long)2 * batch * nc * (nc / 2 + 1);
+#define OPRUN(h, io, prog, tov)                                              \
+  do {                                                                       \
+    int _rc = launch_program(h, io, prog, st, tov);                          \
+    if (_rc) return fail(nullptr, _rc, "%s", (h)->err.c_str());              \
+  } while (0)
+  // fine grid: qh = rfft2(q); adv_f_h = ik (uq)_h + il (vq)_h with u, v from the fine inversion (apply_operator_to_model(q, 1, id))
+  CUDA_TRY(nullptr, cudaMemcpyAsync(hf->q, q, nreal(hf) * sizeof(double), kin, st));
+  StepIO io = base_io(hf);
+  OPRUN(hf, io, PROG_SET_Q, nullptr);
+  io.d_cur = hf->hist[0];
+  OPRUN(hf, io, PROG_ADVECT, &T0f);                                   // hist[0] = -adv_f_h
+  // coarse grid: qf_h = op(q)_h ; S_f = op(adv_f)_h
+  trunc_filter_kernel<<<grid_for(totc), 256, 0, st>>>(hf->qh, hc->qh, 2 * batch, n, nc, op, cf.L, 1.0);
+  trunc_filter_kernel<<<grid_for(totc), 256, 0, st>>>(hf->hist[0], hc->hist[1], 2 * batch, n, nc, op, cf.L, -1.0);
+  g_launches.fetch_add(2, std::memory_order_relaxed);
+  CUDA_TRY(nullptr, cudaGetLastError());
+  StepIO ioc = base_io(hc);
+  OPRUN(hc, ioc, PROG_C2R, nullptr);                                  // qf = irfft2(qf_h)
+  rc = qgb_invert(hc, stream);                                        // psi_f, u_f, v_f (apply_operator_to_model)
+  if (rc) return fail(nullptr, rc, "%s", hc->err.c_str());
+  ioc.d_cur = hc->hist[0];
+  OPRUN(hc, ioc, PROG_ADVECT, &T0c);                                  // hist[0] = -adv_c_h
+  caxpby_kernel<<<grid_for(totc), 256, 0, st>>>(hc->hist[0], hc->hist[1], hc->hist[2], totc, -1.0, -1.0);
+  QGB_COUNT_LAUNCH();
+  CUDA_TRY(nullptr, cudaGetLastError());
+  if (qf) CUDA_TRY(nullptr, cudaMemcpyAsync(qf, hc->q, nreal(hc) * sizeof(double), kout, st));
+  if (uf) CUDA_TRY(nullptr, cudaMemcpyAsync(uf, hc->u, nreal(hc) * sizeof(double), kout, st));
+  if (vf) CUDA_TRY(nullptr, cudaMemcpyAsync(vf, hc->v, nreal(hc) * sizeof(double), kout, st));
+  if (pf) CUDA_TRY(nullptr, cudaMemcpyAsync(pf, hc->p, nreal(hc) * sizeof(double), kout, st));
+  if (forcing) {
+    StepIO iof = base_io(hc);
+    iof.qh = hc->hist[2];
+    iof.q = hc->u;                                                    // reuse a real buffer for irfft2(forcing_h)
+    OPRUN(hc, iof, PROG_C2R, nullptr);
+    CUDA_TRY(nullptr, cudaMemcpyAsync(forcing, hc->u, nreal(hc) * sizeof(double), kout, st));
+  }
+#undef OPRUN
+  CUDA_TRY(nullptr, cudaStreamSynchronize(st));
   return QGB_OK;
 }
 

@@ -1,12 +1,52 @@
-// operators.cuh -- coarse-graining operators (placeholder until the kernels land)
+// operators.cuh -- pointwise kernels of the coarse-graining path (pyqg_generative/tools/operators.py).
+// The FFTs, inversions and Jacobians are the phase programs of qg_core.cuh (PROG_SET_Q = rfft2 of a field pair,
+// PROG_C2R = irfft2, PROG_INVERT, PROG_ADVECT); this file adds the spectral truncation + filter between the fine and the
+// coarse grid and small complex-array helpers.  Host sequencing lives in api.cu (qgb_operator, qgb_subgrid_forcing).
 #pragma once
 #include <cuda_runtime.h>
-#include <string>
-#include "../../include/qgb200.h"
+
+#include "qg_core.cuh"
+
 namespace qgb {
-inline int op_coarsegrain(int, int, int, int, int, const double*, double*, int, cudaStream_t, long long*, std::string* e) {
-  *e = "coarse-graining kernels not built"; return QGB_EUNSUPPORTED; }
-inline int op_subgrid_forcing(const qgb_config*, int, int, int, const double*, double*, double*, double*, double*, double*,
-                              int, cudaStream_t, long long*, std::string* e) {
-  *e = "coarse-graining kernels not built"; return QGB_EUNSUPPORTED; }
+
+// cut_off (operators.py:117-132) followed by the operator's filter, in spectral space:
+//   out[b][z][lc][kc] = in[b][z][lf][kc] / ratio^2 * filt(lc,kc),   lf = lc (lc < n) or lc + N - nc (lc >= n), n = nc/2
+//   with trunc[n,0] = 0 and trunc[:,n] = 0 (FILTER_2h_HARMONICS, :126-130)
+// op 1: pyqg exponential filter of a DEFAULT coarse model (model_filter :92-99 builds pyqg.QGModel(nx=nc): filterfac 23.6)
+// op 2: gauss_filter(X, nc//2) :84-90  -> exp(-wv^2 (2 dx_c)^2 / 24);   op 5: no filter
+__global__ void trunc_filter_kernel(const cplx* __restrict__ in, cplx* __restrict__ out, int fields, int N, int nc, int op,
+                                    double L, double sign) {
+  const int NK = N / 2 + 1, nkc = nc / 2 + 1, n = nc / 2;
+  const long long total = (long long)fields * nc * nkc;
+  const double pi = 3.14159265358979323846;
+  const double dk = 2.0 * pi / L, dxc = L / nc, r2 = ((double)N / nc) * ((double)N / nc);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int kc = (int)(i % nkc), lc = (int)((i / nkc) % nc);
+    const long long f = i / ((long long)nkc * nc);
+    cplx v = cmake(0.0, 0.0);
+    if (!(kc == n) && !(lc == n && kc == 0)) {
+      const int lf = lc < n ? lc : lc + N - nc;
+      v = in[(f * N + lf) * NK + kc];
+      const double kk = dk * kc, ll = dk * (lc < n ? lc : lc - nc);
+      double filt = 1.0;
+      if (op == 1) {
+        const double wvx = sqrt((kk * dxc) * (kk * dxc) + (ll * dxc) * (ll * dxc));
+        if (wvx > 0.65 * pi) { const double d = wvx - 0.65 * pi; filt = exp(-23.6 * d * d * d * d); }
+      } else if (op == 2) {
+        filt = exp(-(kk * kk + ll * ll) * (2.0 * dxc) * (2.0 * dxc) / 24.0);
+      }
+      const double s = sign * filt / r2;
+      v = cmake(v.x * s, v.y * s);
+    }
+    out[i] = v;
+  }
+}
+
+// out = sa*a + sb*b on complex arrays (forcing_h = adv_coarse_h - op(adv_fine)_h)
+__global__ void caxpby_kernel(const cplx* __restrict__ a, const cplx* __restrict__ b, cplx* __restrict__ out, long long n,
+                              double sa, double sb) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = cmake(sa * a[i].x + sb * b[i].x, sa * a[i].y + sb * b[i].y);
+}
+
 }  // namespace qgb

@@ -470,7 +470,10 @@ QGB_HD void ph_red_final(const Ctx& c, int tid, int nt) {
 // programs: ordered phase lists.  ``phase`` selects which phase runs; returns the number of phases.
 // ------------------------------------------------------------------------------------------------------
 // PROG_STEP_DQ removes the mean of dq (closure output, models/parameterization.py:25); PROG_STEP_DQ_RAW adds dq as given
-enum Program { PROG_STEP = 0, PROG_STEP_DQ = 1, PROG_SET_Q = 2, PROG_INVERT = 3, PROG_DIAG = 4, PROG_EMIT_X = 5, PROG_STEP_DQ_RAW = 6 };
+// PROG_ADVECT: d_cur = -(ik uqh + il vqh + ikQy ph) [+ friction] without time stepping (tools/operators.py:249-252 ``advect`` when
+// the tables carry Ubg = Qy = rek = 0);  PROG_C2R: q = irfft2(qh) for arbitrary half-plane spectra (tools/operators.py:132)
+enum Program { PROG_STEP = 0, PROG_STEP_DQ = 1, PROG_SET_Q = 2, PROG_INVERT = 3, PROG_DIAG = 4, PROG_EMIT_X = 5, PROG_STEP_DQ_RAW = 6,
+               PROG_ADVECT = 7, PROG_C2R = 8 };
 
 #define QGB_RUN(stmt)        \
   do {                       \
@@ -500,6 +503,18 @@ QGB_HD int run_program(const Ctx& c, int prog, int phase, int tid, int nt) {
       QGB_FFT(false);
     }
     QGB_RUN(ph_update(c, with_dq, prog == PROG_STEP_DQ, tid, nt));
+    QGB_RUN(ph_build_q(c, tid, nt));
+    QGB_FFT(true);
+    QGB_RUN(ph_emit_q(c, tid, nt));
+  } else if (prog == PROG_ADVECT) {
+    for (int z = 0; z < 2; ++z) {
+      QGB_RUN(ph_build_uv(c, z, tid, nt));
+      QGB_FFT(true);
+      QGB_RUN(ph_products(c, z, tid, nt));
+      QGB_FFT(false);
+      QGB_RUN(ph_tendency(c, z, tid, nt));
+    }
+  } else if (prog == PROG_C2R) {
     QGB_RUN(ph_build_q(c, tid, nt));
     QGB_FFT(true);
     QGB_RUN(ph_emit_q(c, tid, nt));
