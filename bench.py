@@ -231,6 +231,9 @@ def run_b200(args):
     e2e_value = world * count * e2e_steps / e2e_s
     nbytes = int(q0.nbytes)
 
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
     if rank != 0:
         return 0
     peaks, which = measured_peaks()
@@ -252,7 +255,10 @@ def run_b200(args):
         'clocks': summarize_clocks(samples),
         'roofline': {'bound': 'tensor', 'kernel': 'conv layer 2 (128->64, 5x5), %s' % args.precision,
                      'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
-                     'peak_source': '%s bf16_tflops_sustained' % which, 'traffic': None,
+                     'peak_source': '%s bf16_tflops_sustained' % which,
+                     'traffic': 2.305e9 * (pim.value / max(pl.value, 1)) / 1024.0,
+                     'traffic_source': 'dram__bytes_read+write of one ncu --set full capture, 2.305 GB per 1024-image launch '
+                                       '(profiles/r1_final_ncu_full.md); algorithmic activation bytes are 2.35 GB',
                      'launch_ms': pms.value / max(pl.value, 1), 'launches': int(pl.value),
                      'share_of_step': pms.value / ms if ms else None},
         'cpu_baseline': {'value': cpu_v, 'unit': UNIT, 'cores': cores, 'kind': 'port',

@@ -228,3 +228,32 @@ def test_tensor_core_path_with_shipped_weights_and_coupled_step(tmp_path):
         out[prec] = (mm.PV_forcing, mm.q)
     assert rel(out['tc'][0], out['fp32'][0]) < 2 * TC_TOL
     assert rel(out['tc'][1], out['fp32'][1]) < 1e-4
+
+
+def test_ols_closure_and_driver_entry_points(tmp_path):
+    """OLSModel (deterministic CNN) + run_simulation / generate_subgrid_forcing drivers (tools/simulate.py:62-145)."""
+    from pyqg_generative_b200.models.ols_model import OLSModel
+    from pyqg_generative_b200.tools import operators as ops
+    from pyqg_generative_b200.tools.parameters import EDDY_PARAMS
+    from pyqg_generative_b200.tools.simulate import generate_subgrid_forcing, run_simulation
+    c = golden('closure_48.npz')
+    ols = OLSModel(folder=write_model_folder(tmp_path, 'ols'))          # net.pt = the shipped GZ mean network
+    m = _M()
+    m.q, m.ny, m.nx = c['q'].astype('float64'), 48, 48
+    assert rel(ols.predict_snapshot(m), c['gz_mean_snapshot']) < FP32_TOL
+    m.sampling_type = 'deterministic'
+    assert rel(ols(m), cnn_ref.demean(c['gz_mean_snapshot'])) < FP32_TOL
+    # parameterized ensemble run, 3 members, 2 snapshots
+    params = dict(EDDY_PARAMS.nx(48)._update({'tmax': 20 * 14400.0, 'log_level': 0, 'members': 3, 'seed': 1}))
+    np.random.seed(0)
+    ds = run_simulation(params, dict(self=0.5 * ols, sampling='constant', nsteps=1), sampling_freq=10 * 14400)
+    assert ds['q'].shape == (3, 2, 2, 48, 48) and ds['q'].dtype == np.float32 and np.isfinite(ds['q']).all()
+    assert np.allclose(ds['time'], [10 * 14400 / 86400., 20 * 14400 / 86400.])
+    # forcing-dataset generation: hi-res 128^2 ensemble coarse-grained to 32 and 48 with Operator1 / Operator2
+    hires = dict(EDDY_PARAMS.nx(128)._update({'tmax': 4 * 7200.0, 'log_level': 0, 'members': 2}))
+    np.random.seed(1)
+    out = generate_subgrid_forcing([32, 48], hires, sampling_freq=2 * 7200)
+    assert sorted(out) == ['Operator1-32', 'Operator1-48', 'Operator2-32', 'Operator2-48']
+    d = out['Operator2-48']
+    assert d['q_forcing_advection'].shape == (2, 2, 2, 48, 48) and d['q'].dtype == np.float32
+    assert np.isfinite(d['q_forcing_advection']).all() and np.abs(d['q_forcing_advection']).max() > 0
