@@ -21,8 +21,9 @@
 // bank-conflict free (the first version used 16 B pixel rows: shifted core matrices straddled two 128 B lines and the
 // tensor pipe sat at 41 %, profiles/r1_conv_l2_noswizzle.md).
 //
-// Layer 1 (Cin = 4 or 2) is too thin for a K=16 MMA, so a small pre-pass writes its 5x5 im2col (K = 100 -> 128) in the
-// same layout and the layer runs as a 1x1 convolution through the same kernel.
+// Layer 1 (Cin = 4 or 2) is too thin for a K=16 MMA: it runs as a 1x1 convolution over its 5x5 im2col (K = 100 -> 128),
+// which four extra "builder" warps write straight into the shared-memory operand stages from the raw fp32 input
+// (template parameter FUSE), so the im2col tensor never exists in HBM.
 #pragma once
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -31,6 +32,7 @@
 
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -116,6 +118,8 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 // one elected lane of a fully converged warp (same lane every time for the same mask)
 __device__ __forceinline__ uint32_t elect_one_sync() {
   uint32_t pred = 0;
@@ -152,6 +156,7 @@ struct TcConvParams {
   float inv_wscale; int relu_bn;
   __half* out_hi; __half* out_lo; int out_pad, out_nch;   // [img][out_nch][ny+2*out_pad][nx+2*out_pad][32]
   float* out_f32; long long out_bs; int out_c, softplus, accumulate;
+  const float* x_f32; long long x_bs;          // fused layer-1 variant: raw network input (B, cin0, ny, nx) fp32
   int ny, nx, tiles_y, tiles_x, num_tiles;
 };
 
@@ -175,7 +180,7 @@ struct TcCfg {
   static constexpr int DCOLS = NCAT ? 2 * COUT : COUT;       // TMEM columns per M-tile
   static constexpr int NCOLS_USED = 2 * T * DCOLS;
   static constexpr int NCOLS = NCOLS_USED <= 32 ? 32 : NCOLS_USED <= 64 ? 64 : NCOLS_USED <= 128 ? 128 : NCOLS_USED <= 256 ? 256 : 512;
-  static constexpr int SMEM = 2 * A_STAGE + NW * W_STAGE + 3 * COUT * 4 + 256 + 1024;
+  static constexpr int SMEM = 2 * A_STAGE + NW * W_STAGE + 3 * COUT * 4 + 256 + 1024 + 6400;
   static_assert(NCOLS_USED <= 512, "accumulators exceed TMEM");
   static_assert(CIN % 32 == 0 && COUT % 16 == 0, "bad channel counts");
 };
@@ -189,9 +194,13 @@ struct TcMaps {
   CUtensorMap hi, lo;
 };
 
-template <int CIN, int COUT, int KS, int PASSES, int T, int OUTMODE>
-__global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__ TcConvParams P,
-                                                         const __grid_constant__ TcMaps M) {
+// FUSE = 0: activations arrive by TMA.  FUSE = cin0 (4 or 2): layer 1 -- four extra warps BUILD the 5x5 im2col operand
+// (K = 25*cin0 padded to CIN, fp16 hi/lo planes, SWIZZLE_64B layout) straight into the shared-memory stages from the raw
+// fp32 network input, so the im2col tensor never exists in HBM.
+template <int CIN, int COUT, int KS, int PASSES, int T, int OUTMODE, int FUSE = 0>
+__global__ void __launch_bounds__(FUSE ? 512 : 384, 1) conv_tc_kernel(const __grid_constant__ TcConvParams P,
+                                                                      const __grid_constant__ TcMaps M) {
+  static_assert(FUSE == 0 || (KS == 1 && T == 2 && PASSES == 3), "fused im2col is the layer-1 configuration");
   using C = TcCfg<CIN, COUT, KS, PASSES, T>;
   extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
   unsigned char* smem = tc_smem_raw + ((1024u - (ptx::smem_u32(tc_smem_raw) & 1023u)) & 1023u);
@@ -206,6 +215,7 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
   uint64_t* acc_full = bars + 4 + 2 * C::NW;   // [2]
   uint64_t* acc_empty = acc_full + 2;          // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* s_x = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + 256);   // FUSE: [cin0][20][20] input window
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < COUT; i += blockDim.x) {
@@ -214,13 +224,13 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
     sEpi[2 * COUT + i] = P.relu_bn ? P.bn_t[i] : 0.f;
   }
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&a_full[i], 1); ptx::mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&a_full[i], FUSE ? 128 : 1); ptx::mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < C::NW; ++i) { ptx::mbar_init(&w_full[i], 1); ptx::mbar_init(&w_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], 256); }
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc(tmem_slot, C::NCOLS);
-  if (warp == 0 && lane == 0) {
+  if (!FUSE && warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&M.hi);
     if (C::PLANES == 2) ptx::prefetch_tmap(&M.lo);
   }
@@ -230,7 +240,57 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
   const int tiles_per_img = P.tiles_y * P.tiles_x;
 
-  if (warp == 0) {
+  if (FUSE && warp >= 12) {
+    // ===================== A builders (layer 1): im2col of the raw input, written swizzled into the A stages =========
+    constexpr int F = FUSE ? FUSE : 1;
+    const int bt = threadIdx.x - 384;
+    uint32_t ia = 0;
+    for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+      const int img = tile / tiles_per_img, r = tile - img * tiles_per_img;
+      const int y0 = (r / P.tiles_x) * 16, x0 = (r % P.tiles_x) * 16;
+      ptx::named_bar_sync(1, 128);                       // the previous tile's window is no longer being read
+      for (int i = bt; i < F * 400; i += 128) {
+        const int cc = i / 400, rr = (i / 20) % 20, col = i % 20;
+        int sy = y0 + rr - 2, sx = x0 + col - 2;
+        sy = sy < 0 ? sy + P.ny : (sy >= P.ny ? sy - P.ny : sy);
+        sx = sx < 0 ? sx + P.nx : (sx >= P.nx ? sx - P.nx : sx);
+        s_x[i] = P.x_f32[(long long)img * P.x_bs + ((long long)cc * P.ny + sy) * P.nx + sx];
+      }
+      ptx::named_bar_sync(1, 128);
+#pragma unroll
+      for (int c = 0; c < C::NCHUNK; ++c, ++ia) {
+        const uint32_t s = ia & 1, par = (ia >> 1) & 1;
+        ptx::mbar_wait(&a_empty[s], par ^ 1);
+        unsigned char* stage = sA + s * C::A_STAGE;
+#pragma unroll
+        for (int pp = 0; pp < 2; ++pp) {
+          const int p = bt + 128 * pp, py = p >> 4, px = p & 15;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int e2 = 0; e2 < 4; ++e2) {
+              float f[2];
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int kk = c * 32 + j * 8 + e2 * 2 + h, tap = kk / F, cc = kk % F;
+                f[h] = tap < 25 ? s_x[(cc * 20 + py + tap / 5) * 20 + px + tap % 5] : 0.f;
+              }
+              const __half h0 = __float2half_rn(f[0]), h1 = __float2half_rn(f[1]);
+              const __half l0 = __float2half_rn(f[0] - __half2float(h0)), l1 = __float2half_rn(f[1] - __half2float(h1));
+              hi[e2] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+              lo[e2] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+            }
+            unsigned char* dst = stage + p * 64 + ((j ^ ((p >> 1) & 3)) << 4);     // 64-byte swizzle: chunk ^= address bits 7-8
+            *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(dst + C::A_PLANE) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
+        }
+        ptx::fence_proxy_async_smem();                   // generic-proxy stores -> visible to the tensor core (async proxy)
+        ptx::mbar_arrive(&a_full[s]);
+      }
+    }
+  } else if (!FUSE && warp == 0) {
     // ===================== A producer: tile + halo of one 32-channel chunk per stage (TMA bulk copies) ============
     uint32_t ia = 0;
     for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
@@ -333,7 +393,7 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
         }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 12) {
     // ===================== epilogue: TMEM -> registers -> bias/ReLU/BN -> fp16 hi/lo (or fp32) -> HBM ==============
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
     const int half = (warp - 4) >> 2;             // two warps share a lane quarter and split the (t, 16-column) items
@@ -423,50 +483,6 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
   if (warp == 1) ptx::tmem_dealloc(tmem_base, C::NCOLS);
 }
 
-// Layer-1 pre-pass: 5x5 circular im2col of the fp32 network input (B, CIN0, ny, nx) into the canonical activation
-// layout [img][KP/32][ny][nx][32] (hi and lo planes), K index = tap*CIN0 + channel, zero padded to KP.
-// One CTA = IM2COL_ROWS image rows of one image: the (rows+4) x (nx+4) x CIN0 input window is staged in shared memory
-// (circular wrap applied once), then every thread emits 16-byte pieces (8 K values); 4 consecutive threads write the
-// 64 contiguous bytes of one pixel, so global stores are fully coalesced.
-constexpr int IM2COL_ROWS = 4;
-__global__ void __launch_bounds__(256) im2col5_kernel(const float* __restrict__ x, long long x_bs, int cin0, int KP,
-                                                      __half* __restrict__ out_hi, __half* __restrict__ out_lo, int ny, int nx) {
-  extern __shared__ float s_in[];                         // [cin0][IM2COL_ROWS+4][nx+4]
-  const int NCH = KP / 32, W = nx + 4, R = IM2COL_ROWS + 4;
-  const int img = blockIdx.y, y0 = blockIdx.x * IM2COL_ROWS;
-  const float* xb = x + (long long)img * x_bs;
-  for (int i = threadIdx.x; i < cin0 * R * W; i += blockDim.x) {
-    const int c = i / (R * W), r = (i / W) % R, col = i % W;
-    int sy = y0 + r - 2, sx = col - 2;
-    sy = sy < 0 ? sy + ny : (sy >= ny ? sy - ny : sy);
-    sx = sx < 0 ? sx + nx : (sx >= nx ? sx - nx : sx);
-    s_in[i] = xb[((long long)c * ny + sy) * nx + sx];
-  }
-  __syncthreads();
-  const int per_chunk = IM2COL_ROWS * nx * 4;             // 16-byte pieces per 32-K chunk
-  for (int i = threadIdx.x; i < NCH * per_chunk; i += blockDim.x) {
-    const int ch = i / per_chunk, rem = i - ch * per_chunk;
-    const int j4 = rem & 3, xx = (rem >> 2) % nx, ry = (rem >> 2) / nx;
-    float f[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int kk = ch * 32 + j4 * 8 + e, tap = kk / cin0, cc = kk - tap * cin0;
-      f[e] = tap < 25 ? s_in[(cc * R + ry + tap / 5) * W + xx + tap % 5] : 0.f;
-    }
-    uint32_t hi[4], lo[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const __half h0 = __float2half_rn(f[2 * e]), h1 = __float2half_rn(f[2 * e + 1]);
-      const __half l0 = __float2half_rn(f[2 * e] - __half2float(h0)), l1 = __float2half_rn(f[2 * e + 1] - __half2float(h1));
-      hi[e] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-      lo[e] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
-    }
-    const long long off = ((((long long)img * NCH + ch) * ny + y0 + ry) * nx + xx) * 32 + j4 * 8;
-    *reinterpret_cast<uint4*>(out_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    *reinterpret_cast<uint4*>(out_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-  }
-}
-
 // ------------------------------------------------------------------------------------------------ host side ----
 struct TcLayer {
   int cin = 0, cout = 0, ks = 0, relu_bn = 0;   // MMA-level shapes (padded): cin multiple of 32, cout = MMA N
@@ -499,7 +515,7 @@ inline void tc_free_net(TcNet& n) {
 inline void tc_free_workspace(TcWorkspace& w) {
   for (int i = 0; i < 6; ++i) { cudaFree(w.buf[i]); w.buf[i] = nullptr; w.halves[i] = 0; }
 }
-inline int tc_launches_per_forward(const TcNet& n) { return n.ready ? (int)n.layers.size() + 1 : 0; }
+inline int tc_launches_per_forward(const TcNet& n) { return n.ready ? (int)n.layers.size() : 0; }
 
 // Pack one layer: weights -> [chunk][tap][4][plane][cout_p][8] fp16 (hi [, lo]) scaled by 2^k, epilogue vectors padded.
 inline bool tc_pack_layer(TcLayer& L, int cin_p, int cout_p, int ks, int passes, int real_cin, int real_cout,
@@ -605,17 +621,20 @@ inline bool tc_make_map(CUtensorMap* m, const __half* base, int WP, int HP, long
              CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int CIN, int COUT, int KS, int PASSES, int T, int OUTMODE>
+template <int CIN, int COUT, int KS, int PASSES, int T, int OUTMODE, int FUSE = 0>
 inline cudaError_t tc_launch(const TcConvParams& P, int nimg, int nsm, cudaStream_t st) {
   using C = TcCfg<CIN, COUT, KS, PASSES, T>;
   TcMaps M;
-  if (!tc_make_map(&M.hi, P.in_hi, P.WP, P.HP, (long long)nimg * P.nch_in, C::HX, C::HY)) return cudaErrorInvalidValue;
-  if (C::PLANES == 2) {
+  if (FUSE) {
+    std::memset(&M, 0, sizeof(M));
+  } else if (!tc_make_map(&M.hi, P.in_hi, P.WP, P.HP, (long long)nimg * P.nch_in, C::HX, C::HY)) {
+    return cudaErrorInvalidValue;
+  } else if (C::PLANES == 2) {
     if (!tc_make_map(&M.lo, P.in_lo, P.WP, P.HP, (long long)nimg * P.nch_in, C::HX, C::HY)) return cudaErrorInvalidValue;
   } else {
     M.lo = M.hi;
   }
-  auto kern = conv_tc_kernel<CIN, COUT, KS, PASSES, T, OUTMODE>;
+  auto kern = conv_tc_kernel<CIN, COUT, KS, PASSES, T, OUTMODE, FUSE>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
@@ -623,7 +642,7 @@ inline cudaError_t tc_launch(const TcConvParams& P, int nimg, int nsm, cudaStrea
     configured = true;
   }
   const int grid = P.num_tiles < nsm ? P.num_tiles : nsm;
-  kern<<<grid, 384, C::SMEM, st>>>(P, M);
+  kern<<<grid, FUSE ? 512 : 384, C::SMEM, st>>>(P, M);
   return cudaGetLastError();
 }
 
@@ -643,11 +662,11 @@ inline int tc_forward(const TcNet& net, TcWorkspace& ws, const float* x, long lo
   // 1024 -> 162 k member-steps/s); the workspace is capped at ~6 GB.
   static int max_chunk = 0;
   if (!max_chunk) { const char* e = getenv("QGB_TC_CHUNK"); max_chunk = e ? atoi(e) : 1024; if (max_chunk < 1) max_chunk = 1024; }
-  const size_t per_img = (2 * (size_t)net.kp * ny * nx + 128 * (size_t)(ny + 4) * (nx + 4) + 160 * (size_t)(ny + 2) * (nx + 2)) * 2;
+  const size_t per_img = (128 * (size_t)(ny + 4) * (nx + 4) + 160 * (size_t)(ny + 2) * (nx + 2)) * 2;
   int chunk = batch < max_chunk ? batch : max_chunk;
   while (chunk > 1 && (size_t)chunk * per_img > (6ull << 30)) chunk = (chunk + 1) / 2;
   // workspace: a0 (im2col, hi/lo), ping (<=128 ch, halo 2), pong (<=64 ch, halo 1)
-  const size_t need[6] = {(size_t)chunk * net.kp * ny * nx, (size_t)chunk * net.kp * ny * nx,
+  const size_t need[6] = {16, 16,   // (the im2col tensor of layer 1 is built on the fly in shared memory)
                           (size_t)chunk * 128 * (ny + 4) * (nx + 4), (size_t)chunk * 32 * (ny + 2) * (nx + 2),
                           (size_t)chunk * 64 * (ny + 2) * (nx + 2), (size_t)chunk * 64 * (ny + 2) * (nx + 2)};
   for (int i = 0; i < 6; ++i)
@@ -661,19 +680,13 @@ inline int tc_forward(const TcNet& net, TcWorkspace& ws, const float* x, long lo
   __half *a0h = ws.buf[0], *a0l = ws.buf[1], *ping_h = ws.buf[2], *ping_l = ws.buf[3], *pong_h = ws.buf[4], *pong_l = ws.buf[5];
   for (int b0 = 0; b0 < batch; b0 += chunk) {
     const int nb = batch - b0 < chunk ? batch - b0 : chunk;
-    {
-      dim3 grid(ny / IM2COL_ROWS, nb);
-      const size_t sh = (size_t)net.cin0 * (IM2COL_ROWS + 4) * (nx + 4) * sizeof(float);
-      im2col5_kernel<<<grid, 256, sh, st>>>(x + (long long)b0 * x_bs, x_bs, net.cin0, net.kp, a0h, a0l, ny, nx);
-      if (cudaGetLastError() != cudaSuccess) { *err = "im2col launch failed"; return QGB_ECUDA; }
-      ws.last_launches += 1;
-    }
     for (int li = 0; li < 8; ++li) {
       const TcLayer& L = net.layers[li];
       TcConvParams P;
       P.w = L.w; P.bias = L.bias; P.bn_s = L.bn_s; P.bn_t = L.bn_t; P.inv_wscale = L.inv_wscale; P.relu_bn = L.relu_bn;
       P.ny = ny; P.nx = nx; P.tiles_y = ny / 16;
       P.out_f32 = nullptr; P.out_bs = 0; P.out_c = 0; P.softplus = 0; P.accumulate = 0;
+      P.x_f32 = x + (long long)b0 * x_bs; P.x_bs = x_bs;
       P.out_hi = P.out_lo = nullptr; P.out_pad = 0; P.out_nch = 0;
       const int Tl = li == 0 ? 2 : T;
       P.tiles_x = nx / (8 * Tl);
@@ -696,7 +709,7 @@ inline int tc_forward(const TcNet& net, TcWorkspace& ws, const float* x, long lo
       if (prof) { cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventRecord(ev0, st); }
       cudaError_t e;
       if (li == 0) {
-        e = net.kp == 128 ? tc_launch<128, 128, 1, 3, 2, TC_OUT_HI>(P, nb, nsm, st) : tc_launch<64, 128, 1, 3, 2, TC_OUT_HI>(P, nb, nsm, st);
+        e = net.kp == 128 ? tc_launch<128, 128, 1, 3, 2, TC_OUT_HI, 4>(P, nb, nsm, st) : tc_launch<64, 128, 1, 3, 2, TC_OUT_HI, 2>(P, nb, nsm, st);
       } else if (li == 1) e = tc_launch_T<128, 64, 5, 1, TC_OUT_HILO>(T, P, nb, nsm, st);
       else if (li == 2) e = tc_launch_T<64, 32, 3, 3, TC_OUT_HILO>(T, P, nb, nsm, st);
       else if (li < 7) e = tc_launch_T<32, 32, 3, 3, TC_OUT_HILO>(T, P, nb, nsm, st);
