@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -50,6 +51,7 @@ struct qgb_handle {
   double *d_kespec = nullptr, *d_ensspec = nullptr;
   long long tc = 0; double t = 0.0; int ablevel = 0;
   int nthreads = 256; size_t smem = 0; int grid = 0;
+  bool fixed = false;   // compile-time specialised step kernel available for this nx
   bool large = false; cplx* scratch = nullptr; double* red_scratch = nullptr;   // cluster path for nx > 96
   // closure
   int kind = QGB_CLOSURE_NONE; int precision = QGB_PREC_FP32;
@@ -133,6 +135,18 @@ int launch_program(qgb_handle* h, const StepIO& io, int prog, cudaStream_t st, c
     cfg.numAttrs = 1;
     CUDA_TRY(h, cudaLaunchKernelEx(&cfg, qg_program_cluster_kernel, TT, io, prog, h->cfg.members, h->scratch, h->red_scratch));
     QGB_COUNT_LAUNCH();
+    return QGB_OK;
+  }
+  const bool is_step = prog == PROG_STEP || prog == PROG_STEP_DQ || prog == PROG_STEP_DQ_RAW;
+  if (is_step && h->fixed) {
+    switch (h->ht.N) {
+      case 32: qg_step_fixed_kernel<32, 256><<<h->grid, 256, h->smem, st>>>(TT, io, prog, h->cfg.members); break;
+      case 48: qg_step_fixed_kernel<48, 256><<<h->grid, 256, h->smem, st>>>(TT, io, prog, h->cfg.members); break;
+      case 64: qg_step_fixed_kernel<64, 256><<<h->grid, 256, h->smem, st>>>(TT, io, prog, h->cfg.members); break;
+      default: qg_step_fixed_kernel<96, 512><<<h->grid, 512, h->smem, st>>>(TT, io, prog, h->cfg.members); break;
+    }
+    QGB_COUNT_LAUNCH();
+    CUDA_TRY(h, cudaGetLastError());
     return QGB_OK;
   }
   qg_program_kernel<<<h->grid, h->nthreads, h->smem, st>>>(TT, io, prog, h->cfg.members);
@@ -426,6 +440,13 @@ int qgb_create(const qgb_config* cfg, qgb_handle** out) {
     return QGB_EUNSUPPORTED;
   }
   if (!h->large) CR(cudaFuncSetAttribute(qg_program_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+  h->fixed = !h->large && (cfg->nx == 32 || cfg->nx == 48 || cfg->nx == 64 || cfg->nx == 96) && !getenv("QGB_GENERIC_STEP");
+  if (h->fixed) {
+    if (cfg->nx == 32) CR(cudaFuncSetAttribute(qg_step_fixed_kernel<32, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+    if (cfg->nx == 48) CR(cudaFuncSetAttribute(qg_step_fixed_kernel<48, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+    if (cfg->nx == 64) CR(cudaFuncSetAttribute(qg_step_fixed_kernel<64, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+    if (cfg->nx == 96) CR(cudaFuncSetAttribute(qg_step_fixed_kernel<96, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+  }
   h->grid = cfg->members;
   if (h->large) {
     // one cluster of kClusterSize CTAs per member, persistent over members when the ensemble exceeds the machine

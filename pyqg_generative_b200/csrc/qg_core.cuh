@@ -82,8 +82,10 @@ struct StepIO {
   double Hi_over_H[2];
 };
 
-// Per-CTA context: shared-memory views + which member this CTA owns
-struct Ctx {
+// Per-CTA context: shared-memory views + which member this CTA owns.  CN > 0 fixes the grid size at compile time
+// (the specialised step kernels of spectral.cuh: all index divisions become shifts / multiplies); CN = 0 reads it from T.
+template <int CN>
+struct CtxT {
   const Tables& T;   // lives in kernel parameter (constant) space on the device
   const StepIO& io;
   cplx* buf;      // [N*P]
@@ -91,15 +93,20 @@ struct Ctx {
   short* pos;     // [N]   shared copy of the position map
   double* red;    // [4*nthreads] reduction scratch (diagnostic program only)
   int member;
+  QGB_HD int N() const { return CN ? CN : T.N; }
+  QGB_HD int NK() const { return CN ? CN / 2 + 1 : T.NK; }
+  QGB_HD int P() const { return CN ? CN + 1 : T.P; }
 };
+using Ctx = CtxT<0>;
 
 // ------------------------------------------------------------------------------------------------------
 // 1-D FFT stage over ``nlines`` lines of the shared buffer.  es = element stride, ls = line stride.
 // Forward stage (sub-FFT length n, radix r, m = n/r):  y[k1] = w_n^{j2 k1} * sum_j1 w_r^{j1 k1} x[j1 m + j2]
 // stored in place at k1 m + j2.  The inverse stage is its exact adjoint (conjugate twiddles, then conj DFT_r).
 // ------------------------------------------------------------------------------------------------------
-QGB_HD void fft_stage(cplx* buf, const cplx* tw, int N, int es, int ls, int nlines, int r, int n, bool inverse,
-                      int tid, int nt) {
+template <int r>
+QGB_HD void fft_stage_r(cplx* buf, const cplx* tw, int N, int es, int ls, int nlines, int n, bool inverse,
+                        int tid, int nt) {
   const int m = n / r;
   const int nb = N / r;
   const int tws = N / n;
@@ -154,45 +161,56 @@ QGB_HD void fft_stage(cplx* buf, const cplx* tw, int N, int es, int ls, int nlin
   }
 }
 
+QGB_HD void fft_stage(cplx* buf, const cplx* tw, int N, int es, int ls, int nlines, int r, int n, bool inverse,
+                      int tid, int nt) {
+  if (r == 4) fft_stage_r<4>(buf, tw, N, es, ls, nlines, n, inverse, tid, nt);
+  else if (r == 2) fft_stage_r<2>(buf, tw, N, es, ls, nlines, n, inverse, tid, nt);
+  else fft_stage_r<3>(buf, tw, N, es, ls, nlines, n, inverse, tid, nt);
+}
+
 // number of barrier-separated phases of one 2-D transform
 QGB_HD int fft2d_phases(const Tables& T) { return 2 * T.nstages; }
 
 // phase ``ph`` (0 .. 2*nstages-1) of the 2-D transform of the whole N x N buffer
-QGB_HD void fft2d_phase(const Ctx& c, int ph, bool inverse, int tid, int nt) {
+template <class C>
+QGB_HD void fft2d_phase(const C& c, int ph, bool inverse, int tid, int nt) {
   const Tables& T = c.T;
   const int S = T.nstages;
   const int pass = ph / S;  // 0: along x (rows), 1: along y (columns)
   int s = ph - pass * S;
   if (inverse) s = S - 1 - s;
-  int n = T.N;
+  int n = c.N();
   for (int i = 0; i < s; ++i) n /= T.radix[i];
-  const int es = pass == 0 ? 1 : T.P;
-  const int ls = pass == 0 ? T.P : 1;
-  fft_stage(c.buf, c.tw, T.N, es, ls, T.N, T.radix[s], n, inverse, tid, nt);
+  const int es = pass == 0 ? 1 : c.P();
+  const int ls = pass == 0 ? c.P() : 1;
+  fft_stage(c.buf, c.tw, c.N(), es, ls, c.N(), T.radix[s], n, inverse, tid, nt);
 }
 
 // ------------------------------------------------------------------------------------------------------
 // pointwise phases
 // ------------------------------------------------------------------------------------------------------
-QGB_HD void ph_init(const Ctx& c, int tid, int nt) {
+template <class C>
+QGB_HD void ph_init(const C& c, int tid, int nt) {
   if (c.tw == c.T.tw) return;   // large-N path: tables are used in place (global memory), nothing to stage
-  for (int i = tid; i < c.T.N; i += nt) {
+  for (int i = tid; i < c.N(); i += nt) {
     c.tw[i] = c.T.tw[i];
     c.pos[i] = c.T.pos[i];
   }
 }
 
 // streamfunction of layer z at half-plane entry (l,k):  ph = a[z][0] qh0 + a[z][1] qh1   (pyqg _invert)
-QGB_HD cplx half_ph(const Ctx& c, const cplx* qh, int z, int idx) {
-  const int NN = c.T.N * c.T.NK;
+template <class C>
+QGB_HD cplx half_ph(const C& c, const cplx* qh, int z, int idx) {
+  const int NN = c.N() * c.NK();
   const cplx q0 = qh[idx], q1 = qh[NN + idx];
   const double a0 = c.T.a[(2 * z) * NN + idx], a1 = c.T.a[(2 * z + 1) * NN + idx];
   return cmake(a0 * q0.x + a1 * q1.x, a0 * q0.y + a1 * q1.y);
 }
 
 // uh = -il ph, vh = ik ph packed as uh + i vh at a half-plane entry
-QGB_HD void half_uv(const Ctx& c, const cplx* qh, int z, int l, int k, cplx& uh, cplx& vh) {
-  const cplx ph = half_ph(c, qh, z, l * c.T.NK + k);
+template <class C>
+QGB_HD void half_uv(const C& c, const cplx* qh, int z, int l, int k, cplx& uh, cplx& vh) {
+  const cplx ph = half_ph(c, qh, z, l * c.NK() + k);
   const double lv = c.T.lv[l], kv = c.T.kv[k];
   uh = cmake(lv * ph.y, -lv * ph.x);
   vh = cmake(-kv * ph.y, kv * ph.x);
@@ -201,9 +219,9 @@ QGB_HD void half_uv(const Ctx& c, const cplx* qh, int z, int l, int k, cplx& uh,
 // Fill the buffer with E(A') + i E(B') where A,B are two half-plane spectra given by ``get(l,k,A,B)``,
 // ' symmetrises the self-conjugate columns k=0,N/2 (what a c2r transform does implicitly by dropping the
 // imaginary part there) and E is the Hermitian extension to the full plane.
-template <class Get>
-QGB_HD void build_packed(const Ctx& c, Get get, int tid, int nt) {
-  const int N = c.T.N, P = c.T.P, H = N / 2;
+template <class C, class Get>
+QGB_HD void build_packed(const C& c, Get get, int tid, int nt) {
+  const int N = c.N(), P = c.P(), H = N / 2;
   for (int i = tid; i < N * N; i += nt) {
     const int l = i / N, k = i - l * N;
     const int lm = l == 0 ? 0 : N - l;
@@ -225,45 +243,53 @@ QGB_HD void build_packed(const Ctx& c, Get get, int tid, int nt) {
   }
 }
 
+template <class C>
 struct GetUV {
-  const Ctx& c; const cplx* qh; int z;
+  const C& c; const cplx* qh; int z;
   QGB_HD void operator()(int l, int k, cplx& A, cplx& B) const { half_uv(c, qh, z, l, k, A, B); }
 };
+template <class C>
 struct GetQ {
-  const Ctx& c; const cplx* qh;
+  const C& c; const cplx* qh;
   QGB_HD void operator()(int l, int k, cplx& A, cplx& B) const {
-    const int idx = l * c.T.NK + k;
+    const int idx = l * c.NK() + k;
     A = qh[idx];
-    B = qh[c.T.N * c.T.NK + idx];
+    B = qh[c.N() * c.NK() + idx];
   }
 };
+template <class C>
 struct GetP {
-  const Ctx& c; const cplx* qh;
+  const C& c; const cplx* qh;
   QGB_HD void operator()(int l, int k, cplx& A, cplx& B) const {
-    const int idx = l * c.T.NK + k;
+    const int idx = l * c.NK() + k;
     A = half_ph(c, qh, 0, idx);
     B = half_ph(c, qh, 1, idx);
   }
 };
 
-QGB_HD const cplx* member_qh(const Ctx& c) { return c.io.qh + (long long)c.member * 2 * c.T.N * c.T.NK; }
+template <class C>
+QGB_HD const cplx* member_qh(const C& c) { return c.io.qh + (long long)c.member * 2 * c.N() * c.NK(); }
 
-QGB_HD void ph_build_uv(const Ctx& c, int z, int tid, int nt) {
-  GetUV g{c, member_qh(c), z};
+template <class C>
+QGB_HD void ph_build_uv(const C& c, int z, int tid, int nt) {
+  GetUV<C> g{c, member_qh(c), z};
   build_packed(c, g, tid, nt);
 }
-QGB_HD void ph_build_q(const Ctx& c, int tid, int nt) {
-  GetQ g{c, member_qh(c)};
+template <class C>
+QGB_HD void ph_build_q(const C& c, int tid, int nt) {
+  GetQ<C> g{c, member_qh(c)};
   build_packed(c, g, tid, nt);
 }
-QGB_HD void ph_build_p(const Ctx& c, int tid, int nt) {
-  GetP g{c, member_qh(c)};
+template <class C>
+QGB_HD void ph_build_p(const C& c, int tid, int nt) {
+  GetP<C> g{c, member_qh(c)};
   build_packed(c, g, tid, nt);
 }
 
 // buf = (u + Ubg) q + i v q        (pyqg _do_advection, physical-space products)
-QGB_HD void ph_products(const Ctx& c, int z, int tid, int nt) {
-  const int N = c.T.N, P = c.T.P;
+template <class C>
+QGB_HD void ph_products(const C& c, int z, int tid, int nt) {
+  const int N = c.N(), P = c.P();
   const double* q = c.io.q + ((long long)c.member * 2 + z) * N * N;
   const double s = c.T.inv_M, U = c.T.Ubg[z];
   for (int i = tid; i < N * N; i += nt) {
@@ -275,8 +301,9 @@ QGB_HD void ph_products(const Ctx& c, int z, int tid, int nt) {
 }
 
 // split a packed forward transform W = FFT(a + i b) into the two half-plane spectra
-QGB_HD void unpack_pair(const Ctx& c, int l, int k, cplx& A, cplx& B) {
-  const int N = c.T.N, P = c.T.P;
+template <class C>
+QGB_HD void unpack_pair(const C& c, int l, int k, cplx& A, cplx& B) {
+  const int N = c.N(), P = c.P();
   const int lm = l == 0 ? 0 : N - l, km = k == 0 ? 0 : N - k;
   const cplx w1 = c.buf[c.pos[l] * P + c.pos[k]];
   const cplx w2 = c.buf[c.pos[lm] * P + c.pos[km]];
@@ -285,8 +312,9 @@ QGB_HD void unpack_pair(const Ctx& c, int l, int k, cplx& A, cplx& B) {
 }
 
 // dqhdt_z = -(ik uqh + il vqh + ikQy ph) (+ rek wv2 ph for the bottom layer) -> d_cur
-QGB_HD void ph_tendency(const Ctx& c, int z, int tid, int nt) {
-  const int N = c.T.N, NK = c.T.NK;
+template <class C>
+QGB_HD void ph_tendency(const C& c, int z, int tid, int nt) {
+  const int N = c.N(), NK = c.NK();
   const cplx* qh = member_qh(c);
   cplx* d = c.io.d_cur + ((long long)c.member * 2 + z) * N * NK;
   for (int i = tid; i < N * NK; i += nt) {
@@ -307,8 +335,9 @@ QGB_HD void ph_tendency(const Ctx& c, int z, int tid, int nt) {
 }
 
 // buf = dq1 + i dq2
-QGB_HD void ph_load_pair(const Ctx& c, const double* f, int tid, int nt) {
-  const int N = c.T.N, P = c.T.P;
+template <class C>
+QGB_HD void ph_load_pair(const C& c, const double* f, int tid, int nt) {
+  const int N = c.N(), P = c.P();
   const double* f0 = f + (long long)c.member * 2 * N * N;
   const double* f1 = f0 + N * N;
   for (int i = tid; i < N * N; i += nt) {
@@ -318,8 +347,9 @@ QGB_HD void ph_load_pair(const Ctx& c, const double* f, int tid, int nt) {
 }
 
 // (+ rfft2(dq) with its mean removed) ; Adams-Bashforth update with the exponential filter
-QGB_HD void ph_update(const Ctx& c, bool has_dq, bool demean, int tid, int nt) {
-  const int N = c.T.N, NK = c.T.NK, NN = N * NK;
+template <class C>
+QGB_HD void ph_update(const C& c, bool has_dq, bool demean, int tid, int nt) {
+  const int N = c.N(), NK = c.NK(), NN = N * NK;
   const long long mo = (long long)c.member * 2 * NN;
   cplx* qh = c.io.qh + mo;
   cplx* d = c.io.d_cur + mo;
@@ -345,8 +375,9 @@ QGB_HD void ph_update(const Ctx& c, bool has_dq, bool demean, int tid, int nt) {
 }
 
 // q = irfft2(qh) (real/imag of the packed inverse), also emits the fp32 normalised closure input
-QGB_HD void ph_emit_q(const Ctx& c, int tid, int nt) {
-  const int N = c.T.N, P = c.T.P;
+template <class C>
+QGB_HD void ph_emit_q(const C& c, int tid, int nt) {
+  const int N = c.N(), P = c.P();
   double* q = c.io.q + (long long)c.member * 2 * N * N;
   const double s = c.T.inv_M;
   float* x = c.io.cnn_x ? c.io.cnn_x + (long long)c.member * c.io.cnn_mstride : nullptr;
@@ -364,16 +395,18 @@ QGB_HD void ph_emit_q(const Ctx& c, int tid, int nt) {
 }
 
 // closure input from the current q without touching the spectral state
-QGB_HD void ph_emit_x_only(const Ctx& c, int tid, int nt) {
-  const int N = c.T.N;
+template <class C>
+QGB_HD void ph_emit_x_only(const C& c, int tid, int nt) {
+  const int N = c.N();
   const double* q = c.io.q + (long long)c.member * 2 * N * N;
   float* x = c.io.cnn_x + (long long)c.member * c.io.cnn_mstride;
   for (int i = tid; i < 2 * N * N; i += nt) x[i] = (float)q[i] / c.io.x_std[i / (N * N)];
 }
 
 // qh = rfft2(q) from the packed forward transform (pyqg ``q`` setter)
-QGB_HD void ph_store_qh(const Ctx& c, int tid, int nt) {
-  const int N = c.T.N, NK = c.T.NK, NN = N * NK;
+template <class C>
+QGB_HD void ph_store_qh(const C& c, int tid, int nt) {
+  const int N = c.N(), NK = c.NK(), NN = N * NK;
   cplx* qh = c.io.qh + (long long)c.member * 2 * NN;
   for (int i = tid; i < NN; i += nt) {
     const int l = i / NK, k = i - l * NK;
@@ -384,8 +417,9 @@ QGB_HD void ph_store_qh(const Ctx& c, int tid, int nt) {
   }
 }
 
-QGB_HD void ph_store_uv(const Ctx& c, int z, int tid, int nt) {
-  const int N = c.T.N, P = c.T.P;
+template <class C>
+QGB_HD void ph_store_uv(const C& c, int z, int tid, int nt) {
+  const int N = c.N(), P = c.P();
   const long long o = ((long long)c.member * 2 + z) * N * N;
   const double s = c.T.inv_M;
   for (int i = tid; i < N * N; i += nt) {
@@ -396,8 +430,9 @@ QGB_HD void ph_store_uv(const Ctx& c, int z, int tid, int nt) {
   }
 }
 
-QGB_HD void ph_store_ph(const Ctx& c, int tid, int nt) {
-  const int NN = c.T.N * c.T.NK;
+template <class C>
+QGB_HD void ph_store_ph(const C& c, int tid, int nt) {
+  const int NN = c.N() * c.NK();
   const cplx* qh = member_qh(c);
   cplx* out = c.io.ph_out + (long long)c.member * 2 * NN;
   for (int i = tid; i < NN; i += nt) {
@@ -406,8 +441,9 @@ QGB_HD void ph_store_ph(const Ctx& c, int tid, int nt) {
   }
 }
 
-QGB_HD void ph_store_p(const Ctx& c, int tid, int nt) {
-  const int N = c.T.N, P = c.T.P;
+template <class C>
+QGB_HD void ph_store_p(const C& c, int tid, int nt) {
+  const int N = c.N(), P = c.P();
   double* p = c.io.p_out + (long long)c.member * 2 * N * N;
   const double s = c.T.inv_M;
   for (int i = tid; i < N * N; i += nt) {
@@ -419,11 +455,13 @@ QGB_HD void ph_store_p(const Ctx& c, int tid, int nt) {
 }
 
 // diagnostics partials: red[0*nt+tid] ke, [1] max|u+U|, [2] max|v|, [3] non-finite count
-QGB_HD void ph_red_clear(const Ctx& c, int tid, int nt) {
+template <class C>
+QGB_HD void ph_red_clear(const C& c, int tid, int nt) {
   for (int j = 0; j < 4; ++j) c.red[j * nt + tid] = 0.0;
 }
-QGB_HD void ph_red_ke(const Ctx& c, int tid, int nt) {  // pyqg _calc_ke via spec_var(wv*ph)
-  const int N = c.T.N, NK = c.T.NK, NN = N * NK;
+template <class C>
+QGB_HD void ph_red_ke(const C& c, int tid, int nt) {  // pyqg _calc_ke via spec_var(wv*ph)
+  const int N = c.N(), NK = c.NK(), NN = N * NK;
   const cplx* qh = member_qh(c);
   double acc = 0.0, bad = 0.0;
   for (int i = tid; i < NN; i += nt) {
@@ -440,8 +478,9 @@ QGB_HD void ph_red_ke(const Ctx& c, int tid, int nt) {  // pyqg _calc_ke via spe
   c.red[0 * nt + tid] += acc * c.T.inv_M * c.T.inv_M;
   c.red[3 * nt + tid] += bad;
 }
-QGB_HD void ph_red_uv(const Ctx& c, int z, int tid, int nt) {  // pyqg _calc_cfl numerator
-  const int N = c.T.N, P = c.T.P;
+template <class C>
+QGB_HD void ph_red_uv(const C& c, int z, int tid, int nt) {  // pyqg _calc_cfl numerator
+  const int N = c.N(), P = c.P();
   const double s = c.T.inv_M, U = c.T.Ubg[z];
   double mu = c.red[1 * nt + tid], mv = c.red[2 * nt + tid];
   for (int i = tid; i < N * N; i += nt) {
@@ -453,7 +492,8 @@ QGB_HD void ph_red_uv(const Ctx& c, int z, int tid, int nt) {  // pyqg _calc_cfl
   c.red[1 * nt + tid] = mu;
   c.red[2 * nt + tid] = mv;
 }
-QGB_HD void ph_red_final(const Ctx& c, int tid, int nt) {
+template <class C>
+QGB_HD void ph_red_final(const C& c, int tid, int nt) {
   if (tid != 0) return;
   double ke = 0, mu = 0, mv = 0, bad = 0;
   for (int t = 0; t < nt; ++t) {
@@ -485,7 +525,8 @@ enum Program { PROG_STEP = 0, PROG_STEP_DQ = 1, PROG_SET_Q = 2, PROG_INVERT = 3,
     for (int _f = 0; _f < F; ++_f) QGB_RUN(fft2d_phase(c, _f, inv, tid, nt)); \
   } while (0)
 
-QGB_HD int run_program(const Ctx& c, int prog, int phase, int tid, int nt) {
+template <class C>
+QGB_HD int run_program(const C& c, int prog, int phase, int tid, int nt) {
   int _n = 0;
   const int F = fft2d_phases(c.T);
   QGB_RUN(ph_init(c, tid, nt));

@@ -34,6 +34,86 @@ __global__ void __launch_bounds__(512) qg_program_kernel(const __grid_constant__
   }
 }
 
+// ---- compile-time specialised time step -------------------------------------------------------------------------
+// The generic kernel above interprets the phase list with run-time N; ncu showed 89 % of its instructions were integer
+// index arithmetic (divisions by N, phase decoding).  For the production sizes the step is unrolled at compile time:
+// same phase functions, N / radix plan / stage sequence are constants.
+template <int CN> struct FixedPlan;
+template <> struct FixedPlan<32> { static constexpr int S = 3; static constexpr int R0 = 4, R1 = 4, R2 = 2, R3 = 1; };
+template <> struct FixedPlan<48> { static constexpr int S = 3; static constexpr int R0 = 4, R1 = 4, R2 = 3, R3 = 1; };
+template <> struct FixedPlan<64> { static constexpr int S = 3; static constexpr int R0 = 4, R1 = 4, R2 = 4, R3 = 1; };
+template <> struct FixedPlan<96> { static constexpr int S = 4; static constexpr int R0 = 4, R1 = 4, R2 = 2, R3 = 3; };
+
+template <int CN, int PASS, int STAGE, bool INV>
+__device__ __forceinline__ void fixed_stage(const CtxT<CN>& c, int tid, int nt) {
+  using PL = FixedPlan<CN>;
+  constexpr int R = STAGE == 0 ? PL::R0 : STAGE == 1 ? PL::R1 : STAGE == 2 ? PL::R2 : PL::R3;
+  constexpr int n = STAGE == 0 ? CN : STAGE == 1 ? CN / PL::R0 : STAGE == 2 ? CN / (PL::R0 * PL::R1) : CN / (PL::R0 * PL::R1 * PL::R2);
+  constexpr int es = PASS == 0 ? 1 : CN + 1, ls = PASS == 0 ? CN + 1 : 1;
+  fft_stage_r<R>(c.buf, c.tw, CN, es, ls, CN, n, INV, tid, nt);
+  __syncthreads();
+}
+template <int CN, int PASS, bool INV>
+__device__ __forceinline__ void fixed_pass(const CtxT<CN>& c, int tid, int nt) {
+  using PL = FixedPlan<CN>;
+  if (!INV) {
+    fixed_stage<CN, PASS, 0, INV>(c, tid, nt);
+    fixed_stage<CN, PASS, 1, INV>(c, tid, nt);
+    fixed_stage<CN, PASS, 2, INV>(c, tid, nt);
+    if (PL::S == 4) fixed_stage<CN, PASS, 3, INV>(c, tid, nt);
+  } else {
+    if (PL::S == 4) fixed_stage<CN, PASS, 3, INV>(c, tid, nt);
+    fixed_stage<CN, PASS, 2, INV>(c, tid, nt);
+    fixed_stage<CN, PASS, 1, INV>(c, tid, nt);
+    fixed_stage<CN, PASS, 0, INV>(c, tid, nt);
+  }
+}
+template <int CN, bool INV>
+__device__ __forceinline__ void fixed_fft2d(const CtxT<CN>& c, int tid, int nt) {
+  fixed_pass<CN, 0, INV>(c, tid, nt);
+  fixed_pass<CN, 1, INV>(c, tid, nt);
+}
+
+// prog: PROG_STEP, PROG_STEP_DQ or PROG_STEP_DQ_RAW
+template <int CN, int NT>
+__global__ void __launch_bounds__(NT) qg_step_fixed_kernel(const __grid_constant__ Tables T, const __grid_constant__ StepIO io,
+                                                           int prog, int members) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx* buf = reinterpret_cast<cplx*>(smem_raw);
+  cplx* tw = buf + (size_t)CN * (CN + 1);
+  short* pos = reinterpret_cast<short*>(tw + CN);
+  const int tid = threadIdx.x;
+  const bool with_dq = prog != PROG_STEP;
+  for (int m = blockIdx.x; m < members; m += gridDim.x) {
+    CtxT<CN> c{T, io, buf, tw, pos, nullptr, m};
+    ph_init(c, tid, NT);
+    __syncthreads();
+#pragma unroll 1
+    for (int z = 0; z < 2; ++z) {
+      ph_build_uv(c, z, tid, NT);
+      __syncthreads();
+      fixed_fft2d<CN, true>(c, tid, NT);
+      ph_products(c, z, tid, NT);
+      __syncthreads();
+      fixed_fft2d<CN, false>(c, tid, NT);
+      ph_tendency(c, z, tid, NT);
+      __syncthreads();
+    }
+    if (with_dq) {
+      ph_load_pair(c, io.dq, tid, NT);
+      __syncthreads();
+      fixed_fft2d<CN, false>(c, tid, NT);
+    }
+    ph_update(c, with_dq, prog == PROG_STEP_DQ, tid, NT);
+    __syncthreads();
+    ph_build_q(c, tid, NT);
+    __syncthreads();
+    fixed_fft2d<CN, true>(c, tid, NT);
+    ph_emit_q(c, tid, NT);
+    __syncthreads();
+  }
+}
+
 // Large grids (N = 128, 256: the packed field is 0.26 / 1.0 MB and no longer fits one CTA's shared memory): the SAME phase
 // programs run with the working field in a per-member global-memory scratch (L2 resident: 64 members x 1 MB at 256^2)
 // and a thread-block CLUSTER of kClusterSize CTAs per member.  Threads are numbered across the cluster, phases are separated
