@@ -136,6 +136,10 @@ int qgb_cnn_forward(qgb_handle* h, int net, const float* x, float* y, int batch,
  * set_q(host) -> nsteps -> get q(host) in one call (the reference exchanges q / dq with the host every step,
  * tools/cnn_tools.py:720-723). */
 int qgb_step_host(qgb_handle* h, const double* q_in_host, double* q_out_host, int nsteps, void* stream);
+/* Pipelined variant: enqueues H2D(q_in) -> rfft2 -> nsteps -> D2H(q_out) on ``stream`` and returns WITHOUT synchronising.
+ * q_in / q_out must be pinned host memory and stay valid until the caller synchronises the stream.  Several handles
+ * (member groups) driven on different streams overlap their PCIe transfers with each other's kernels. */
+int qgb_step_host_async(qgb_handle* h, const double* q_in_host, double* q_out_host, int nsteps, void* stream);
 
 /* ---- diagnostics ------------------------------------------------------------------------------------------
  * pyqg: QGModel._calc_ke, _calc_cfl (logged every twrite steps; assert cfl<1), per member.

@@ -50,6 +50,7 @@ SYMBOLS = {
     'qgb_set_forcing': (_i, [_vp, _vp, _i, _vp]),
     'qgb_cnn_forward': (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     'qgb_step_host': (_i, [_vp, _vp, _vp, _i, _vp]),
+    'qgb_step_host_async': (_i, [_vp, _vp, _vp, _i, _vp]),
     'qgb_diag': (_i, [_vp, _vp, _vp, _vp, _i, _vp]),
     'qgb_diag_spectra': (_i, [_vp, _vp, _vp, _i, _vp]),
     'qgb_operator': (_i, [_i, _i, _i, _i, _i, _vp, _vp, _i, _vp]),

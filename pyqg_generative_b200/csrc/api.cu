@@ -576,6 +576,24 @@ int qgb_step_host(qgb_handle* h, const double* q_in, double* q_out, int nsteps, 
   return rc;
 }
 
+int qgb_step_host_async(qgb_handle* h, const double* q_in, double* q_out, int nsteps, void* stream) {
+  if (!h) return QGB_EINVAL;
+  cudaStream_t st = S(stream);
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  if (q_in) {
+    CUDA_TRY(h, cudaMemcpyAsync(h->q, q_in, nreal(h) * sizeof(double), cudaMemcpyHostToDevice, st));
+    StepIO io = base_io(h);
+    set_cnn_io(h, io);
+    int rc = launch_program(h, io, PROG_SET_Q, st);
+    if (rc) return rc;
+    h->x_valid = io.cnn_x != nullptr;
+  }
+  int rc = qgb_step(h, nsteps, stream);
+  if (rc) return rc;
+  if (q_out) CUDA_TRY(h, cudaMemcpyAsync(q_out, h->q, nreal(h) * sizeof(double), cudaMemcpyDeviceToHost, st));
+  return QGB_OK;
+}
+
 int qgb_get(qgb_handle* h, int field, void* out, int on_device, void* stream) {
   if (!h || !out) return fail(h, QGB_EINVAL, "null argument");
   cudaStream_t st = S(stream);

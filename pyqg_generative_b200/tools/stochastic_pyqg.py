@@ -450,6 +450,18 @@ class EnsembleQGModel(object):
         for _ in self.run_with_snapshots(tsnapint=1e30):
             pass
 
+    def step_host(self, q_in, q_out, nsteps=1, stream=None, wait=True):
+        """Host-buffer step: upload ``q_in`` (pinned CPU torch tensor or numpy array, (B,2,ny,nx) float64), advance
+        ``nsteps``, download q into ``q_out``.  With ``wait=False`` the call only enqueues work on ``stream`` (a
+        torch.cuda.Stream); drive several member groups on different streams to overlap PCIe transfers and kernels."""
+        def ptr(a):
+            return a.data_ptr() if hasattr(a, 'data_ptr') else a.ctypes.data
+        s = (stream.cuda_stream if stream is not None else self._stream())
+        fn = self._lib.qgb_step_host if wait else self._lib.qgb_step_host_async
+        _lib.check(fn(self._h, ptr(q_in), ptr(q_out), int(nsteps), s), self._h)
+        self.tc += int(nsteps)
+        self.t += int(nsteps) * self.dt
+
     def reset_time(self):
         _lib.check(self._lib.qgb_reset_time(self._h), self._h)
         self._sync_time()

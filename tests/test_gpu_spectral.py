@@ -155,3 +155,31 @@ def test_full_size_ensemble_members_are_independent_and_identical():
     q = m.q
     assert rel(q[0], o.q) < TOL
     assert (q == q[0][None]).all()
+
+
+def test_host_buffer_stepping_sync_and_pipelined():
+    """qgb_step_host / qgb_step_host_async (the end-to-end path of bench.py) equal set_q + step + get."""
+    import torch
+    N, dt, B = 48, 14400., 4
+    rng = np.random.RandomState(4)
+    q0 = rng.randn(B, 2, N, N) * 1e-6
+    ref = make(N, B, dt=dt)
+    ref.q = q0
+    ref._step_forward(3)
+    a = make(N, B, dt=dt)
+    qout = np.empty_like(q0)
+    a.step_host(q0, qout, 3)
+    assert np.array_equal(qout, ref.q) and a.tc == 3
+    # two member groups on two streams, pinned buffers, no host synchronisation in between
+    groups = []
+    for g in range(2):
+        mg = make(N, 2, dt=dt)
+        qi = torch.from_numpy(q0[2 * g:2 * g + 2].copy()).pin_memory()
+        qo = torch.empty_like(qi).pin_memory()
+        groups.append((mg, qi, qo, torch.cuda.Stream()))
+    for mg, qi, qo, st in groups:
+        mg.step_host(qi, qo, 3, stream=st, wait=False)
+    for mg, qi, qo, st in groups:
+        st.synchronize()
+    got = np.concatenate([g[2].numpy() for g in groups])
+    assert np.array_equal(got, ref.q)
