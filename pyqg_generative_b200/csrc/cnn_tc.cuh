@@ -38,6 +38,10 @@
 
 #include "../../include/qgb200.h"
 
+#ifndef QGB_TC_NW_OVERRIDE
+#define QGB_TC_NW_OVERRIDE 0
+#endif
+
 namespace qgb {
 
 // ------------------------------------------------------------------------------------------ PTX wrappers ----
@@ -173,7 +177,7 @@ struct TcCfg {
   static constexpr int A_TX = PLANES * A_BYTES;
   static constexpr int W_TAP = PLANES * 4 * COUT * 16;            // one (chunk, tap) weight slab
   static constexpr int W_STAGE = KS * W_TAP;                      // a pipeline stage holds one tap ROW (KS taps)
-  static constexpr int NW = (KS == 5) ? 3 : 4;
+  static constexpr int NW = QGB_TC_NW_OVERRIDE ? QGB_TC_NW_OVERRIDE : ((KS == 5) ? 3 : 4);
   // 3-pass layers with a narrow N concatenate [w_hi | w_lo] along N:  D[:, :COUT] += a_hi w_hi + a_lo w_hi,
   // D[:, COUT:] += a_hi w_lo  (two MMAs instead of three -> fewer shared-memory reads of the A operand)
   static constexpr bool NCAT = (PASSES == 3) && (COUT <= 32);
@@ -332,6 +336,9 @@ __global__ void __launch_bounds__(FUSE ? 512 : 384, 1) conv_tc_kernel(const __gr
     constexpr uint32_t a_hi32 = A_SBO | (1u << 14) | (4u << 29), b_hi32 = B_SBO | (1u << 14);   // upper descriptor words
     const uint32_t sA_u = ptx::smem_u32(sA) >> 4, sW_u = ptx::smem_u32(sW) >> 4;
     uint32_t ia = 0, iw = 0, it = 0;
+    // The elected lane runs the WHOLE persistent loop (barrier waits included): no per-row elect / reconvergence, so the
+    // tensor-pipe queue does not drain between tap rows.
+    if (ptx::elect_one_sync()) {
     for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x, ++it) {
       const uint32_t as = it & 1;
       ptx::mbar_wait(&acc_empty[as], ((it >> 1) & 1) ^ 1);
@@ -346,7 +353,7 @@ __global__ void __launch_bounds__(FUSE ? 512 : 384, 1) conv_tc_kernel(const __gr
           const uint32_t sw = iw % C::NW;
           ptx::mbar_wait(&w_full[sw], (iw / C::NW) & 1);
           ptx::tc_fence_after();
-          if (ptx::elect_one_sync()) {
+          {
             // Issue order: consecutive MMAs go to DIFFERENT accumulators (t inner).  The 64 B swizzle is a pure function
             // of the shared-memory ADDRESS bits (verified on B200: a non-zero 'matrix base offset' gives wrong results),
             // so shifted tap windows need no descriptor fix-up.
@@ -389,10 +396,11 @@ __global__ void __launch_bounds__(FUSE ? 512 : 384, 1) conv_tc_kernel(const __gr
               if (c == C::NCHUNK - 1) ptx::tc_commit(&acc_full[as]);        // tile complete -> epilogue
             }
           }
-          __syncwarp();
         }
       }
     }
+    }
+    __syncwarp();
   } else if (warp >= 4 && warp < 12) {
     // ===================== epilogue: TMEM -> registers -> bias/ReLU/BN -> fp16 hi/lo (or fp32) -> HBM ==============
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
