@@ -202,7 +202,7 @@ struct TcMaps {
 // (K = 25*cin0 padded to CIN, fp16 hi/lo planes, SWIZZLE_64B layout) straight into the shared-memory stages from the raw
 // fp32 network input, so the im2col tensor never exists in HBM.
 template <int CIN, int COUT, int KS, int PASSES, int T, int OUTMODE, int FUSE = 0>
-__global__ void __launch_bounds__(FUSE ? 512 : 384, 1) conv_tc_kernel(const __grid_constant__ TcConvParams P,
+__global__ void __launch_bounds__(FUSE ? 640 : 384, 1) conv_tc_kernel(const __grid_constant__ TcConvParams P,
                                                                       const __grid_constant__ TcMaps M) {
   static_assert(FUSE == 0 || (KS == 1 && T == 2 && PASSES == 3), "fused im2col is the layer-1 configuration");
   using C = TcCfg<CIN, COUT, KS, PASSES, T>;
@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(FUSE ? 512 : 384, 1) conv_tc_kernel(const __gr
     sEpi[2 * COUT + i] = P.relu_bn ? P.bn_t[i] : 0.f;
   }
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&a_full[i], FUSE ? 128 : 1); ptx::mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&a_full[i], FUSE ? 256 : 1); ptx::mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < C::NW; ++i) { ptx::mbar_init(&w_full[i], 1); ptx::mbar_init(&w_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], 256); }
     ptx::fence_barrier_init();
@@ -246,49 +246,70 @@ __global__ void __launch_bounds__(FUSE ? 512 : 384, 1) conv_tc_kernel(const __gr
 
   if (FUSE && warp >= 12) {
     // ===================== A builders (layer 1): im2col of the raw input, written swizzled into the A stages =========
+    // 8 warps, one pixel of the 16x16 tile per thread.  The input window is staged as [row][col][4] floats so one tap of a
+    // pixel is ONE 16-byte shared-memory load; fp32 -> fp16 hi/lo uses the packed half2 conversions.
     constexpr int F = FUSE ? FUSE : 1;
-    const int bt = threadIdx.x - 384;
+    const int bt = threadIdx.x - 384;                    // 0..255
+    const int py = bt >> 4, px = bt & 15;
+    float4* s_x4 = reinterpret_cast<float4*>(s_x);
     uint32_t ia = 0;
     for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
       const int img = tile / tiles_per_img, r = tile - img * tiles_per_img;
       const int y0 = (r / P.tiles_x) * 16, x0 = (r % P.tiles_x) * 16;
-      ptx::named_bar_sync(1, 128);                       // the previous tile's window is no longer being read
-      for (int i = bt; i < F * 400; i += 128) {
-        const int cc = i / 400, rr = (i / 20) % 20, col = i % 20;
+      ptx::named_bar_sync(1, 256);                       // the previous tile's window is no longer being read
+      for (int i = bt; i < 400; i += 256) {
+        const int rr = i / 20, col = i % 20;
         int sy = y0 + rr - 2, sx = x0 + col - 2;
         sy = sy < 0 ? sy + P.ny : (sy >= P.ny ? sy - P.ny : sy);
         sx = sx < 0 ? sx + P.nx : (sx >= P.nx ? sx - P.nx : sx);
-        s_x[i] = P.x_f32[(long long)img * P.x_bs + ((long long)cc * P.ny + sy) * P.nx + sx];
+        const float* src = P.x_f32 + (long long)img * P.x_bs + (long long)sy * P.nx + sx;
+        const long long cs = (long long)P.ny * P.nx;
+        float4 v;
+        v.x = src[0];
+        v.y = src[cs];
+        v.z = F > 2 ? src[2 * cs] : 0.f;
+        v.w = F > 2 ? src[3 * cs] : 0.f;
+        s_x4[i] = v;
       }
-      ptx::named_bar_sync(1, 128);
+      ptx::named_bar_sync(1, 256);
 #pragma unroll
       for (int c = 0; c < C::NCHUNK; ++c, ++ia) {
         const uint32_t s = ia & 1, par = (ia >> 1) & 1;
         ptx::mbar_wait(&a_empty[s], par ^ 1);
         unsigned char* stage = sA + s * C::A_STAGE;
 #pragma unroll
-        for (int pp = 0; pp < 2; ++pp) {
-          const int p = bt + 128 * pp, py = p >> 4, px = p & 15;
+        for (int j = 0; j < 4; ++j) {
+          // 8 K values of this 16-byte piece: K index kk = tap*F + channel
+          float f[8];
+          if (F == 4) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint32_t hi[4], lo[4];
-#pragma unroll
-            for (int e2 = 0; e2 < 4; ++e2) {
-              float f[2];
-#pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const int kk = c * 32 + j * 8 + e2 * 2 + h, tap = kk / F, cc = kk % F;
-                f[h] = tap < 25 ? s_x[(cc * 20 + py + tap / 5) * 20 + px + tap % 5] : 0.f;
-              }
-              const __half h0 = __float2half_rn(f[0]), h1 = __float2half_rn(f[1]);
-              const __half l0 = __float2half_rn(f[0] - __half2float(h0)), l1 = __float2half_rn(f[1] - __half2float(h1));
-              hi[e2] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-              lo[e2] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+            for (int h = 0; h < 2; ++h) {
+              const int tap = (c * 32 + j * 8) / 4 + h;
+              float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (tap < 25) v = s_x4[(py + tap / 5) * 20 + px + tap % 5];
+              f[4 * h] = v.x; f[4 * h + 1] = v.y; f[4 * h + 2] = v.z; f[4 * h + 3] = v.w;
             }
-            unsigned char* dst = stage + p * 64 + ((j ^ ((p >> 1) & 3)) << 4);     // 64-byte swizzle: chunk ^= address bits 7-8
-            *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<uint4*>(dst + C::A_PLANE) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          } else {
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              const int tap = (c * 32 + j * 8) / 2 + h;
+              float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (tap < 25) v = s_x4[(py + tap / 5) * 20 + px + tap % 5];
+              f[2 * h] = v.x; f[2 * h + 1] = v.y;
+            }
           }
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int e2 = 0; e2 < 4; ++e2) {
+            const __half2 h2 = __floats2half2_rn(f[2 * e2], f[2 * e2 + 1]);
+            const float2 back = __half22float2(h2);
+            const __half2 l2 = __floats2half2_rn(f[2 * e2] - back.x, f[2 * e2 + 1] - back.y);
+            hi[e2] = *reinterpret_cast<const uint32_t*>(&h2);
+            lo[e2] = *reinterpret_cast<const uint32_t*>(&l2);
+          }
+          unsigned char* dst = stage + bt * 64 + ((j ^ ((bt >> 1) & 3)) << 4);   // 64-byte swizzle: chunk ^= address bits 7-8
+          *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(dst + C::A_PLANE) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
         ptx::fence_proxy_async_smem();                   // generic-proxy stores -> visible to the tensor core (async proxy)
         ptx::mbar_arrive(&a_full[s]);
@@ -650,7 +671,7 @@ inline cudaError_t tc_launch(const TcConvParams& P, int nimg, int nsm, cudaStrea
     configured = true;
   }
   const int grid = P.num_tiles < nsm ? P.num_tiles : nsm;
-  kern<<<grid, FUSE ? 512 : 384, C::SMEM, st>>>(P, M);
+  kern<<<grid, FUSE ? 640 : 384, C::SMEM, st>>>(P, M);
   return cudaGetLastError();
 }
 
