@@ -253,25 +253,33 @@ __global__ void __launch_bounds__(FUSE ? 640 : 384, 1) conv_tc_kernel(const __gr
     const int py = bt >> 4, px = bt & 15;
     float4* s_x4 = reinterpret_cast<float4*>(s_x);
     uint32_t ia = 0;
-    for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
-      const int img = tile / tiles_per_img, r = tile - img * tiles_per_img;
-      const int y0 = (r / P.tiles_x) * 16, x0 = (r % P.tiles_x) * 16;
-      ptx::named_bar_sync(1, 256);                       // the previous tile's window is no longer being read
-      for (int i = bt; i < 400; i += 256) {
+    // window entries this thread stages: i = bt and bt + 256 (400 entries of [row][col] x 4 channels); the NEXT tile's
+    // entries are fetched into registers before the current tile is built, hiding the global-memory latency
+    auto fetch = [&](int tile, int i) -> float4 {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (tile < P.num_tiles && i < 400) {
+        const int img = tile / tiles_per_img, r = tile - img * tiles_per_img;
+        const int y0 = (r / P.tiles_x) * 16, x0 = (r % P.tiles_x) * 16;
         const int rr = i / 20, col = i % 20;
         int sy = y0 + rr - 2, sx = x0 + col - 2;
         sy = sy < 0 ? sy + P.ny : (sy >= P.ny ? sy - P.ny : sy);
         sx = sx < 0 ? sx + P.nx : (sx >= P.nx ? sx - P.nx : sx);
         const float* src = P.x_f32 + (long long)img * P.x_bs + (long long)sy * P.nx + sx;
         const long long cs = (long long)P.ny * P.nx;
-        float4 v;
         v.x = src[0];
         v.y = src[cs];
-        v.z = F > 2 ? src[2 * cs] : 0.f;
-        v.w = F > 2 ? src[3 * cs] : 0.f;
-        s_x4[i] = v;
+        if (F > 2) { v.z = src[2 * cs]; v.w = src[3 * cs]; }
       }
+      return v;
+    };
+    float4 w0 = fetch(blockIdx.x, bt), w1 = fetch(blockIdx.x, bt + 256);
+    for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+      ptx::named_bar_sync(1, 256);                       // the previous tile's window is no longer being read
+      s_x4[bt] = w0;
+      if (bt + 256 < 400) s_x4[bt + 256] = w1;
       ptx::named_bar_sync(1, 256);
+      w0 = fetch(tile + gridDim.x, bt);
+      w1 = fetch(tile + gridDim.x, bt + 256);
 #pragma unroll
       for (int c = 0; c < C::NCHUNK; ++c, ++ia) {
         const uint32_t s = ia & 1, par = (ia >> 1) & 1;
@@ -458,11 +466,26 @@ __global__ void __launch_bounds__(FUSE ? 640 : 384, 1) conv_tc_kernel(const __gr
             ptx::mbar_arrive(&acc_empty[as]);
           }
           float v[16];
+          {   // per-channel epilogue constants: 16-byte shared-memory loads (shared-memory bandwidth is what bounds the MMAs)
+            const float4* eb = reinterpret_cast<const float4*>(sEpi + n0);
+            const float4* es = reinterpret_cast<const float4*>(sEpi + COUT + n0);
+            const float4* et = reinterpret_cast<const float4*>(sEpi + 2 * COUT + n0);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float a = __uint_as_float(rr[i]) * P.inv_wscale + sEpi[n0 + i];
-            if (P.relu_bn) a = fmaxf(a, 0.f) * sEpi[COUT + n0 + i] + sEpi[2 * COUT + n0 + i];
-            v[i] = a;
+            for (int i4 = 0; i4 < 4; ++i4) {
+              const float4 b = eb[i4];
+              float a0 = __uint_as_float(rr[4 * i4 + 0]) * P.inv_wscale + b.x;
+              float a1 = __uint_as_float(rr[4 * i4 + 1]) * P.inv_wscale + b.y;
+              float a2 = __uint_as_float(rr[4 * i4 + 2]) * P.inv_wscale + b.z;
+              float a3 = __uint_as_float(rr[4 * i4 + 3]) * P.inv_wscale + b.w;
+              if (P.relu_bn) {
+                const float4 sc = es[i4], sh = et[i4];
+                a0 = fmaxf(a0, 0.f) * sc.x + sh.x;
+                a1 = fmaxf(a1, 0.f) * sc.y + sh.y;
+                a2 = fmaxf(a2, 0.f) * sc.z + sh.z;
+                a3 = fmaxf(a3, 0.f) * sc.w + sh.w;
+              }
+              v[4 * i4 + 0] = a0; v[4 * i4 + 1] = a1; v[4 * i4 + 2] = a2; v[4 * i4 + 3] = a3;
+            }
           }
           if (OUTMODE == TC_OUT_FINAL) {
             for (int i = 0; i < 16; ++i) {
