@@ -154,11 +154,15 @@ int qgb_diag_spectra(qgb_handle* h, double* kespec_sum, double* ensspec_sum, int
  *     5 = Operator5 (cut_off only, :216-217, :117-132).  in: double (batch, n, n) -> out: double (batch, nc, nc). */
 int qgb_operator(int device, int op, int n, int nc, int batch, const double* in, double* out, int on_device,
                  void* stream);
-/* PV_subgrid_forcing(q, nc, operator, pyqg_params, dealias='none') (tools/operators.py:283-287) for a batch of
- * hi-res snapshots q: double (batch,2,n,n).  Outputs (batch,2,nc,nc) double, any may be NULL:
- * forcing S, and the coarse model's q, u, v, psi (apply_operator_to_model, :219-236). */
-int qgb_subgrid_forcing(const qgb_config* cfg, int op, int nc, int batch, const double* q, double* forcing,
+/* PV_subgrid_forcing(q, nc, operator, pyqg_params, dealias) (tools/operators.py:283-287) for a batch of hi-res
+ * snapshots q: double (batch,2,n,n).  dealias: 0 = 'none', 2 = '3/2-rule' (advect :249-268 through fft_interpolate to the
+ * 3n/2 grid and back; what generate_subgrid_forcing uses, tools/simulate.py:90-92).  Outputs (batch,2,nc,nc) double, any may
+ * be NULL: forcing S, and the coarse model's q, u, v, psi (apply_operator_to_model, :219-236). */
+int qgb_subgrid_forcing(const qgb_config* cfg, int op, int nc, int dealias, int batch, const double* q, double* forcing,
                         double* qf, double* uf, double* vf, double* pf, int on_device, void* stream);
+/* fft_interpolate(x, n, N, truncate_2h=True) (tools/operators.py:134-190): spectral interpolation (N > n) or truncation
+ * (N < n) of real fields.  in: double (batch, n, n) -> out: double (batch, N, N). */
+int qgb_fft_interpolate(int device, int n, int N, int batch, const double* in, double* out, int on_device, void* stream);
 
 /* Device-side timing of ONE network layer inside the running step loop (bench.py's roofline line): between
  * qgb_profile_begin and qgb_profile_end every launch of layer ``layer`` of network ``net`` is bracketed by CUDA events on

@@ -54,7 +54,8 @@ SYMBOLS = {
     'qgb_diag': (_i, [_vp, _vp, _vp, _vp, _i, _vp]),
     'qgb_diag_spectra': (_i, [_vp, _vp, _vp, _i, _vp]),
     'qgb_operator': (_i, [_i, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
-    'qgb_subgrid_forcing': (_i, [ctypes.POINTER(QgbConfig), _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    'qgb_subgrid_forcing': (_i, [ctypes.POINTER(QgbConfig), _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    'qgb_fft_interpolate': (_i, [_i, _i, _i, _i, _vp, _vp, _i, _vp]),
     'qgb_profile_begin': (_i, [_vp, _i, _i]),
     'qgb_profile_end': (_i, [_vp, ctypes.POINTER(_d), ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]),
     'qgb_launch_count': (ctypes.c_int64, []),

@@ -439,7 +439,14 @@ int qgb_create(const qgb_config* cfg, qgb_handle** out) {
     qgb_destroy(h);
     return QGB_EUNSUPPORTED;
   }
-  if (!h->large) CR(cudaFuncSetAttribute(qg_program_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+  if (!h->large) {
+    // the opt-in limit is a per-function, process-wide attribute: only ever raise it (handles of several grid sizes coexist)
+    static size_t generic_smem_limit = 0;
+    if (h->smem > generic_smem_limit) {
+      CR(cudaFuncSetAttribute(qg_program_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+      generic_smem_limit = h->smem;
+    }
+  }
   h->fixed = !h->large && (cfg->nx == 32 || cfg->nx == 48 || cfg->nx == 64 || cfg->nx == 96) && !getenv("QGB_GENERIC_STEP");
   if (h->fixed) {
     if (cfg->nx == 32) CR(cudaFuncSetAttribute(qg_step_fixed_kernel<32, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
@@ -839,6 +846,77 @@ Tables no_background(const Tables& T) {   // advect(var, u, v) uses anomaly velo
 }
 }  // namespace
 
+namespace {
+// advect(var, u, v, '3/2-rule') (tools/operators.py:258-266) for B members on the n-grid, all fields device-resident:
+// adv_h (B,2,n,n/2+1) = ik * F(I_n(I_N(q) I_N(u))) + il * F(I_n(I_N(q) I_N(v))),  N = 3n/2, I = fft_interpolate.
+int advect_dealiased(const qgb_config& base, int n, int B, const double* q, const double* u, const double* v, cplx* adv_h,
+                     cudaStream_t st) {
+  const int N = (3 * n) / 2;
+  qgb_config c3n = base, c3N = base, c2N = base;
+  c3n.nx = n; c3n.members = 3 * B;
+  c3N.nx = N; c3N.members = 3 * B;
+  c2N.nx = N; c2N.members = 2 * B;
+  HandleGuard g3n, g3N, g2N;
+  int rc;
+  if ((rc = qgb_create(&c3n, &g3n.h))) return rc;
+  if ((rc = qgb_create(&c3N, &g3N.h))) return rc;
+  if ((rc = qgb_create(&c2N, &g2N.h))) return rc;
+  qgb_handle *h3n = g3n.h, *h3N = g3N.h, *h2N = g2N.h;
+  const size_t fn = (size_t)B * 2 * n * n, fN = (size_t)B * 2 * N * N;
+  CUDA_TRY(nullptr, cudaMemcpyAsync(h3n->q, q, fn * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  CUDA_TRY(nullptr, cudaMemcpyAsync(h3n->q + fn, u, fn * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  CUDA_TRY(nullptr, cudaMemcpyAsync(h3n->q + 2 * fn, v, fn * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  StepIO io = base_io(h3n);
+  if ((rc = launch_program(h3n, io, PROG_SET_Q, st))) return fail(nullptr, rc, "%s", h3n->err.c_str());
+  const double up = ((double)N / n) * ((double)N / n);
+  resample_kernel<<<grid_for((long long)6 * B * N * (N / 2 + 1)), 256, 0, st>>>(h3n->qh, h3N->qh, 6 * B, n, N, up);
+  StepIO ioN = base_io(h3N);
+  if ((rc = launch_program(h3N, ioN, PROG_C2R, st))) return fail(nullptr, rc, "%s", h3N->err.c_str());
+  rmul_kernel<<<grid_for((long long)fN), 256, 0, st>>>(h3N->q, h3N->q + fN, h2N->q, (long long)fN);            // q u
+  rmul_kernel<<<grid_for((long long)fN), 256, 0, st>>>(h3N->q, h3N->q + 2 * fN, h2N->q + fN, (long long)fN);   // q v
+  StepIO io2 = base_io(h2N);
+  if ((rc = launch_program(h2N, io2, PROG_SET_Q, st))) return fail(nullptr, rc, "%s", h2N->err.c_str());
+  // back to the n grid (reuse h3n->qh as scratch: first 2B members), then the spectral divergence
+  resample_kernel<<<grid_for((long long)4 * B * n * (n / 2 + 1)), 256, 0, st>>>(h2N->qh, h3n->qh, 4 * B, N, n, 1.0 / up);
+  const size_t cn = (size_t)B * 2 * n * (n / 2 + 1);
+  spectral_div_kernel<<<grid_for((long long)cn), 256, 0, st>>>(h3n->qh, h3n->qh + cn, adv_h, 2 * B, n, base.L);
+  g_launches.fetch_add(5, std::memory_order_relaxed);
+  CUDA_TRY(nullptr, cudaGetLastError());
+  CUDA_TRY(nullptr, cudaStreamSynchronize(st));     // the temporary handles are released on return
+  return QGB_OK;
+}
+}  // namespace
+
+int qgb_fft_interpolate(int device, int n, int N, int batch, const double* in, double* out, int on_device, void* stream) {
+  if (!in || !out || batch < 1) return fail(nullptr, QGB_EINVAL, "bad argument");
+  if (n % 2 != 0 || N % 2 != 0) return fail(nullptr, QGB_EINVAL, "Grid sizes (n,N) must be even");
+  cudaStream_t st = S(stream);
+  const int pairs = (batch + 1) / 2;
+  qgb_config ca, cb;
+  qgb_default_config(&ca);
+  ca.device = device; ca.members = pairs; ca.nx = n;
+  cb = ca; cb.nx = N;
+  HandleGuard ga, gb;
+  int rc;
+  if ((rc = qgb_create(&ca, &ga.h))) return rc;
+  if ((rc = qgb_create(&cb, &gb.h))) return rc;
+  const cudaMemcpyKind kin = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  const cudaMemcpyKind kout = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  CUDA_TRY(nullptr, cudaMemsetAsync(ga.h->q, 0, nreal(ga.h) * sizeof(double), st));
+  CUDA_TRY(nullptr, cudaMemcpyAsync(ga.h->q, in, (size_t)batch * n * n * sizeof(double), kin, st));
+  StepIO io = base_io(ga.h);
+  if ((rc = launch_program(ga.h, io, PROG_SET_Q, st))) return fail(nullptr, rc, "%s", ga.h->err.c_str());
+  const double sc = ((double)N / n) * ((double)N / n);
+  resample_kernel<<<grid_for((long long)2 * pairs * N * (N / 2 + 1)), 256, 0, st>>>(ga.h->qh, gb.h->qh, 2 * pairs, n, N, sc);
+  QGB_COUNT_LAUNCH();
+  CUDA_TRY(nullptr, cudaGetLastError());
+  StepIO iob = base_io(gb.h);
+  if ((rc = launch_program(gb.h, iob, PROG_C2R, st))) return fail(nullptr, rc, "%s", gb.h->err.c_str());
+  CUDA_TRY(nullptr, cudaMemcpyAsync(out, gb.h->q, (size_t)batch * N * N * sizeof(double), kout, st));
+  CUDA_TRY(nullptr, cudaStreamSynchronize(st));
+  return QGB_OK;
+}
+
 int qgb_operator(int device, int op, int n, int nc, int batch, const double* in, double* out, int on_device,
                  void* stream) {
   if (!in || !out || batch < 1) return fail(nullptr, QGB_EINVAL, "bad argument");
@@ -876,9 +954,10 @@ int qgb_operator(int device, int op, int n, int nc, int batch, const double* in,
   return QGB_OK;
 }
 
-int qgb_subgrid_forcing(const qgb_config* cfg, int op, int nc, int batch, const double* q, double* forcing,
+int qgb_subgrid_forcing(const qgb_config* cfg, int op, int nc, int dealias, int batch, const double* q, double* forcing,
                         double* qf, double* uf, double* vf, double* pf, int on_device, void* stream) {
   if (!cfg || !q || batch < 1) return fail(nullptr, QGB_EINVAL, "bad argument");
+  if (dealias != 0 && dealias != 2) return fail(nullptr, QGB_EINVAL, "dealias should be none or 3/2-rule");
   if (op != 1 && op != 2 && op != 5) return fail(nullptr, QGB_EINVAL, "operator %d not supported (1, 2, 5)", op);
   const int n = cfg->nx;
   if (nc % 2 != 0) return fail(nullptr, QGB_EINVAL, "nc must be even");
@@ -906,10 +985,19 @@ int qgb_subgrid_forcing(const qgb_config* cfg, int op, int nc, int batch, const 
   StepIO io = base_io(hf);
   OPRUN(hf, io, PROG_SET_Q, nullptr);
   io.d_cur = hf->hist[0];
-  OPRUN(hf, io, PROG_ADVECT, &T0f);                                   // hist[0] = -adv_f_h
+  double fine_sign = -1.0;
+  if (dealias == 0) {
+    OPRUN(hf, io, PROG_ADVECT, &T0f);                                 // hist[0] = -adv_f_h
+  } else {
+    rc = qgb_invert(hf, stream);                                      // u, v of the fine model
+    if (rc) return fail(nullptr, rc, "%s", hf->err.c_str());
+    rc = advect_dealiased(cf, n, batch, hf->q, hf->u, hf->v, hf->hist[0], st);   // hist[0] = +adv_f_h (3/2-rule)
+    if (rc) return rc;
+    fine_sign = 1.0;
+  }
   // coarse grid: qf_h = op(q)_h ; S_f = op(adv_f)_h
   trunc_filter_kernel<<<grid_for(totc), 256, 0, st>>>(hf->qh, hc->qh, 2 * batch, n, nc, op, cf.L, 1.0);
-  trunc_filter_kernel<<<grid_for(totc), 256, 0, st>>>(hf->hist[0], hc->hist[1], 2 * batch, n, nc, op, cf.L, -1.0);
+  trunc_filter_kernel<<<grid_for(totc), 256, 0, st>>>(hf->hist[0], hc->hist[1], 2 * batch, n, nc, op, cf.L, fine_sign);
   g_launches.fetch_add(2, std::memory_order_relaxed);
   CUDA_TRY(nullptr, cudaGetLastError());
   StepIO ioc = base_io(hc);
@@ -917,8 +1005,15 @@ int qgb_subgrid_forcing(const qgb_config* cfg, int op, int nc, int batch, const 
   rc = qgb_invert(hc, stream);                                        // psi_f, u_f, v_f (apply_operator_to_model)
   if (rc) return fail(nullptr, rc, "%s", hc->err.c_str());
   ioc.d_cur = hc->hist[0];
-  OPRUN(hc, ioc, PROG_ADVECT, &T0c);                                  // hist[0] = -adv_c_h
-  caxpby_kernel<<<grid_for(totc), 256, 0, st>>>(hc->hist[0], hc->hist[1], hc->hist[2], totc, -1.0, -1.0);
+  double coarse_sign = -1.0;
+  if (dealias == 0) {
+    OPRUN(hc, ioc, PROG_ADVECT, &T0c);                                // hist[0] = -adv_c_h
+  } else {
+    rc = advect_dealiased(cc, nc, batch, hc->q, hc->u, hc->v, hc->hist[0], st);
+    if (rc) return rc;
+    coarse_sign = 1.0;
+  }
+  caxpby_kernel<<<grid_for(totc), 256, 0, st>>>(hc->hist[0], hc->hist[1], hc->hist[2], totc, coarse_sign, -1.0);
   QGB_COUNT_LAUNCH();
   CUDA_TRY(nullptr, cudaGetLastError());
   if (qf) CUDA_TRY(nullptr, cudaMemcpyAsync(qf, hc->q, nreal(hc) * sizeof(double), kout, st));

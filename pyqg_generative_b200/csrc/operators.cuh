@@ -42,6 +42,50 @@ __global__ void trunc_filter_kernel(const cplx* __restrict__ in, cplx* __restric
   }
 }
 
+// fft_interpolate (operators.py:134-190) in spectral space between half-plane arrays of two grid sizes (either direction):
+//   out[f][lo][ko] = scale * in[f][ls][ko]  for the nn = min(n_src,n_dst)/2 lowest wavenumbers of each sign,
+//   zero elsewhere, with the 2h harmonics removed (truncate_2h): column ko = nn and the entry (l = -nn, k = 0).
+__global__ void resample_kernel(const cplx* __restrict__ in, cplx* __restrict__ out, int fields, int n_src, int n_dst,
+                                double scale) {
+  const int nk_src = n_src / 2 + 1, nk_dst = n_dst / 2 + 1, nn = (n_src < n_dst ? n_src : n_dst) / 2;
+  const long long total = (long long)fields * n_dst * nk_dst;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ko = (int)(i % nk_dst), lo = (int)((i / nk_dst) % n_dst);
+    const long long f = i / ((long long)nk_dst * n_dst);
+    cplx v = cmake(0.0, 0.0);
+    if (ko < nn) {
+      int ls = -1;
+      if (lo < nn) ls = lo;
+      else if (lo >= n_dst - nn) ls = lo - n_dst + n_src;
+      if (ls >= 0 && !(ko == 0 && lo == n_dst - nn)) {      // (l = -nn, k = 0) has no phase: removed
+        const cplx a = in[(f * n_src + ls) * nk_src + ko];
+        v = cmake(a.x * scale, a.y * scale);
+      }
+    }
+    out[i] = v;
+  }
+}
+
+// out[b] = a[b] * c[b] elementwise on real arrays (products on the 3/2 grid)
+__global__ void rmul_kernel(const double* __restrict__ a, const double* __restrict__ c, double* __restrict__ out, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = a[i] * c[i];
+}
+
+// spectral divergence (operators.py:241-247): out[f][l][k] = i k fx[f][l][k] + i l fy[f][l][k] on a half-plane grid of size n
+__global__ void spectral_div_kernel(const cplx* __restrict__ fx, const cplx* __restrict__ fy, cplx* __restrict__ out,
+                                    int fields, int n, double L) {
+  const int nk = n / 2 + 1;
+  const double dk = 2.0 * 3.14159265358979323846 / L;
+  const long long total = (long long)fields * n * nk;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % nk), l = (int)((i / nk) % n);
+    const double kv = dk * k, lv = dk * (l < n / 2 ? l : l - n);
+    const cplx a = fx[i], b = fy[i];
+    out[i] = cmake(-(kv * a.y + lv * b.y), kv * a.x + lv * b.x);
+  }
+}
+
 // out = sa*a + sb*b on complex arrays (forcing_h = adv_coarse_h - op(adv_fine)_h)
 __global__ void caxpby_kernel(const cplx* __restrict__ a, const cplx* __restrict__ b, cplx* __restrict__ out, long long n,
                               double sa, double sb) {

@@ -5,7 +5,8 @@
 signatures.  Inputs may be numpy arrays (2-D field, (nlev,ny,nx) like the reference's ``array_format`` numpy branch, or
 any leading batch axes) or CUDA torch tensors (processed in place on the device, a CUDA tensor is returned).
 All FFTs / truncations / Jacobians run in libqgb200 (qgb_operator, qgb_subgrid_forcing).
-Not built: Operator3 (gcm_filters), the 2/3- and 3/2-rule dealiased ``advect``.
+``fft_interpolate`` (:134-190) and the '3/2-rule' dealiased forcing (``advect`` :258-266) are built as well.
+Not built: Operator3 (gcm_filters), Operator4, the '2/3-rule'.
 """
 import ctypes
 
@@ -69,6 +70,26 @@ def Operator5(X, nc):
     return _run_operator(5, X, nc)
 
 
+def fft_interpolate(x, n, N, truncate_2h=True):
+    """Reference :134-190: spectral interpolation n -> N (either direction) of 2-D / 3-D (or batched) real fields."""
+    import torch
+    if not truncate_2h:
+        raise NotImplementedError('truncate_2h=False is not built')
+    x = np.ascontiguousarray(np.asarray(x, dtype=np.float64))
+    if x.shape[-2] != n or x.shape[-1] != n:
+        raise ValueError('Input variable must be n*n points')
+    if n % 2 != 0 or N % 2 != 0:
+        raise ValueError('Grid sizes (n,N) must be even')
+    if not torch.cuda.is_available():
+        raise RuntimeError('fft_interpolate needs a CUDA device: libqgb200 has no CPU fallback')
+    batch = int(np.prod(x.shape[:-2])) if x.ndim > 2 else 1
+    out = np.empty(x.shape[:-2] + (N, N))
+    dev = torch.cuda.current_device()
+    _lib.check(_lib.load().qgb_fft_interpolate(dev, n, N, batch, x.ctypes.data, out.ctypes.data, 0,
+                                               torch.cuda.current_stream(dev).cuda_stream))
+    return out
+
+
 _OP_ID = {'Operator1': 1, 'Operator2': 2, 'Operator5': 5, 'cut_off': 5}
 
 
@@ -89,8 +110,11 @@ def PV_subgrid_forcing(q, nc, operator, pyqg_params, dealias='none', return_fiel
     q, u, v, p of the coarse model, ``m`` is None (the fine model is never materialised) -- or ``(forcing, dict)`` with
     the coarse fields when ``return_fields`` is True."""
     import torch
-    if dealias != 'none':
-        raise NotImplementedError("dealias=%r: only 'none' is built (2/3- and 3/2-rule are a next row)" % (dealias,))
+    if dealias not in ('none', '3/2-rule'):
+        if dealias == '2/3-rule':
+            raise NotImplementedError("dealias='2/3-rule' is not built ('none' and '3/2-rule' are)")
+        raise ValueError('dealias should be none or 2/3-rule or 3/2-rule')
+    dealias_id = 0 if dealias == 'none' else 2
     op = _OP_ID.get(getattr(operator, '__name__', str(operator)))
     if op is None:
         raise NotImplementedError('operator %r is not on the accelerated path (Operator1, Operator2, Operator5)' % (operator,))
@@ -117,7 +141,7 @@ def PV_subgrid_forcing(q, nc, operator, pyqg_params, dealias='none', return_fiel
     cfg = _config(pyqg_params, n)
     cfg.device = dev
     stream = torch.cuda.current_stream(dev).cuda_stream
-    _lib.check(lib.qgb_subgrid_forcing(ctypes.byref(cfg), op, nc, B, src, ptrs[0], ptrs[1], ptrs[2], ptrs[3], ptrs[4],
+    _lib.check(lib.qgb_subgrid_forcing(ctypes.byref(cfg), op, nc, dealias_id, B, src, ptrs[0], ptrs[1], ptrs[2], ptrs[3], ptrs[4],
                                        on_dev, stream))
     if cuda_in:
         outs = [o.cpu().numpy() for o in outs]

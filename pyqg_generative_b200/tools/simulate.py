@@ -89,12 +89,15 @@ def run_simulation(pyqg_params, parameterization=None, q_init=None, sampling_fre
     return ds
 
 
-def generate_subgrid_forcing(Nc, pyqg_params, sampling_freq=ANDREW_1000_STEPS, operators=None, dealias='none', rng=None):
-    """Reference :62-106: run a hi-res ensemble and coarse-grain every ``sampling_freq`` seconds.
-    Returns {'<Operator>-<nc>': dict(q_forcing_advection, q, u, v, psi, time)} with float32 arrays (run,time,lev,y,x)."""
+def generate_subgrid_forcing(Nc, pyqg_params, sampling_freq=ANDREW_1000_STEPS, operators=None, dealias='3/2-rule', rng=None):
+    """Reference :62-106: run a hi-res ensemble and coarse-grain every ``sampling_freq`` seconds.  Defaults follow the
+    reference ([Operator2, Operator5], '3/2-rule', keys '<Operator>-<nc>-dealias'); the published datasets used
+    ``operators=[Operator1, Operator2], dealias='none'`` (scripts/train_parameterizations.py:28), keys '<Operator>-<nc>'.
+    Returns {key: dict(q_forcing_advection, q, u, v, psi, time)} with float32 arrays (run,time,lev,y,x)."""
     from . import operators as ops
     if operators is None:
-        operators = [ops.Operator1, ops.Operator2]
+        operators = [ops.Operator2, ops.Operator5]
+    suffix = '' if dealias == 'none' else '-dealias'
     pyqg_params = dict(pyqg_params)
     pyqg_params['tmax'] = float(pyqg_params['tmax'])
     m = EnsembleQGModel(**pyqg_params)
@@ -109,7 +112,7 @@ def generate_subgrid_forcing(Nc, pyqg_params, sampling_freq=ANDREW_1000_STEPS, o
                 rec = dict(q_forcing_advection=forcing, q=mf['q'], u=mf['u'], v=mf['v'], psi=mf['psi'])
                 rec = {k: np.asarray(v, 'float32') for k, v in rec.items()}
                 rec['time'] = m.t / 86400.
-                out.setdefault('%s-%d' % (op.__name__, nc), []).append(rec)
+                out.setdefault('%s-%d%s' % (op.__name__, nc, suffix), []).append(rec)
     for key, recs in out.items():
         d = {k: np.stack([r[k] for r in recs], axis=1) for k in ('q_forcing_advection', 'q', 'u', 'v', 'psi')}
         d['time'] = np.array([r['time'] for r in recs])

@@ -252,8 +252,15 @@ def test_ols_closure_and_driver_entry_points(tmp_path):
     # forcing-dataset generation: hi-res 128^2 ensemble coarse-grained to 32 and 48 with Operator1 / Operator2
     hires = dict(EDDY_PARAMS.nx(128)._update({'tmax': 4 * 7200.0, 'log_level': 0, 'members': 2}))
     np.random.seed(1)
-    out = generate_subgrid_forcing([32, 48], hires, sampling_freq=2 * 7200)
+    out = generate_subgrid_forcing([32, 48], hires, sampling_freq=2 * 7200, operators=[ops.Operator1, ops.Operator2],
+                                   dealias='none')
     assert sorted(out) == ['Operator1-32', 'Operator1-48', 'Operator2-32', 'Operator2-48']
+    np.random.seed(1)
+    out32 = generate_subgrid_forcing([48], hires, sampling_freq=2 * 7200)           # reference defaults: 3/2-rule
+    assert sorted(out32) == ['Operator2-48-dealias', 'Operator5-48-dealias']
+    a, b = out['Operator2-48']['q_forcing_advection'], out32['Operator2-48-dealias']['q_forcing_advection']
+    assert np.array_equal(out['Operator2-48']['q'], out32['Operator2-48-dealias']['q'])    # same run, same coarse q
+    assert 0 < np.abs(a - b).max() < 0.5 * np.abs(a).max()                          # dealiasing changes S moderately
     d = out['Operator2-48']
     assert d['q_forcing_advection'].shape == (2, 2, 2, 48, 48) and d['q'].dtype == np.float32
     assert np.isfinite(d['q_forcing_advection']).all() and np.abs(d['q_forcing_advection']).max() > 0

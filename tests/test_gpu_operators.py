@@ -39,8 +39,14 @@ def test_subgrid_forcing_matches_reference_outputs():
         assert rel(forcing, o['S_%s_none' % name]) < 1e-9, name
         assert rel(mf.q, o['qf_%s' % name]) < TOL and rel(mf.u, o['uf_%s' % name]) < TOL
         assert rel(mf.v, o['vf_%s' % name]) < TOL and rel(mf.p, o['pf_%s' % name]) < TOL
+        f32, _, _ = ops.PV_subgrid_forcing(q, 64, getattr(ops, name), params, dealias='3/2-rule')
+        assert rel(f32, o['S_%s_32' % name]) < 1e-9, name              # 3/2-rule: 128 -> 192 and 64 -> 96 and back
     with pytest.raises(NotImplementedError):
-        ops.PV_subgrid_forcing(q, 64, ops.Operator1, params, dealias='3/2-rule')
+        ops.PV_subgrid_forcing(q, 64, ops.Operator1, params, dealias='2/3-rule')
+    assert rel(ops.fft_interpolate(o['interp_in'], 48, 72), o['interp_48_72']) < TOL
+    assert rel(ops.fft_interpolate(o['interp_in'], 48, 32), o['interp_48_32']) < TOL
+    x = np.random.RandomState(1).randn(64, 64)                        # notebooks/3-2-dealiasing.ipynb:586
+    assert rel(ops.cut_off(x, 16), ops.fft_interpolate(x, 64, 16)) < 1e-13
 
 
 def test_hires_256_to_64_batched_on_device():
