@@ -52,6 +52,7 @@ struct qgb_handle {
   long long tc = 0; double t = 0.0; int ablevel = 0;
   int nthreads = 256; size_t smem = 0; int grid = 0;
   bool fixed = false;   // compile-time specialised step kernel available for this nx
+  int nt64 = 384;
   bool large = false; cplx* scratch = nullptr; double* red_scratch = nullptr;   // cluster path for nx > 96
   // closure
   int kind = QGB_CLOSURE_NONE; int precision = QGB_PREC_FP32;
@@ -142,7 +143,11 @@ int launch_program(qgb_handle* h, const StepIO& io, int prog, cudaStream_t st, c
     switch (h->ht.N) {
       case 32: qg_step_fixed_kernel<32, 256><<<h->grid, 256, h->smem, st>>>(TT, io, prog, h->cfg.members); break;
       case 48: qg_step_fixed_kernel<48, 256><<<h->grid, 256, h->smem, st>>>(TT, io, prog, h->cfg.members); break;
-      case 64: qg_step_fixed_kernel<64, 256><<<h->grid, 256, h->smem, st>>>(TT, io, prog, h->cfg.members); break;
+      case 64:
+        if (h->nt64 == 512) qg_step_fixed_kernel<64, 512><<<h->grid, 512, h->smem, st>>>(TT, io, prog, h->cfg.members);
+        else if (h->nt64 == 384) qg_step_fixed_kernel<64, 384><<<h->grid, 384, h->smem, st>>>(TT, io, prog, h->cfg.members);
+        else qg_step_fixed_kernel<64, 256><<<h->grid, 256, h->smem, st>>>(TT, io, prog, h->cfg.members);
+        break;
       default: qg_step_fixed_kernel<96, 512><<<h->grid, 512, h->smem, st>>>(TT, io, prog, h->cfg.members); break;
     }
     QGB_COUNT_LAUNCH();
@@ -451,7 +456,13 @@ int qgb_create(const qgb_config* cfg, qgb_handle** out) {
   if (h->fixed) {
     if (cfg->nx == 32) CR(cudaFuncSetAttribute(qg_step_fixed_kernel<32, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
     if (cfg->nx == 48) CR(cudaFuncSetAttribute(qg_step_fixed_kernel<48, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
-    if (cfg->nx == 64) CR(cudaFuncSetAttribute(qg_step_fixed_kernel<64, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+    if (cfg->nx == 64) {
+      const char* e = getenv("QGB_STEP_NT");
+      h->nt64 = e ? atoi(e) : 384;   // measured on B200: 256 -> 0.370 ms, 384 -> 0.299 ms, 512 -> 0.301 ms per 1024 members
+      CR(cudaFuncSetAttribute(qg_step_fixed_kernel<64, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+      CR(cudaFuncSetAttribute(qg_step_fixed_kernel<64, 384>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+      CR(cudaFuncSetAttribute(qg_step_fixed_kernel<64, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+    }
     if (cfg->nx == 96) CR(cudaFuncSetAttribute(qg_step_fixed_kernel<96, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
   }
   h->grid = cfg->members;
