@@ -56,28 +56,62 @@ def synthetic_states(members, n, seed):
 
 
 def clock_sampler(stop, samples, device):
+    """Sample SM clock, power and clock-event (throttle) reasons DURING the timed region: NVML every 20 ms, falling back to
+    the nvidia-smi query of /opt/skills/guides/B200_PROFILING.md."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        uuid = None
+        try:
+            import torch
+            uuid = str(torch.cuda.get_device_properties(device).uuid)
+        except Exception:
+            pass
+        h = None
+        if uuid:
+            for cand in ('GPU-' + uuid, uuid):
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(cand.encode() if isinstance(cand, str) else cand)
+                    break
+                except Exception:
+                    h = None
+        if h is None:
+            h = pynvml.nvmlDeviceGetHandleByIndex(device)
+        mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        get_reasons = getattr(pynvml, 'nvmlDeviceGetCurrentClocksEventReasons', None) or \
+            getattr(pynvml, 'nvmlDeviceGetCurrentClocksThrottleReasons')
+        bits = {'hw_slowdown': 0x8, 'sw_power_cap': 0x4, 'hw_thermal_slowdown': 0x40, 'sw_thermal_slowdown': 0x20}
+        while not stop.is_set():
+            r = int(get_reasons(h))
+            samples.append({'sm': float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), 'max': float(mx),
+                            'power': pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0,
+                            'reasons': [k for k, b in bits.items() if r & b]})
+            stop.wait(0.02)
+        return
+    except Exception:
+        pass
     q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
     while not stop.is_set():
         try:
             out = subprocess.run(['nvidia-smi', '-i', str(device), '--query-gpu=' + q, '--format=csv,noheader,nounits'],
                                  capture_output=True, text=True, timeout=5).stdout.strip()
-            if out:
-                samples.append([x.strip() for x in out.split(',')])
+            f = [x.strip() for x in out.split(',')]
+            samples.append({'sm': float(f[0]), 'max': float(f[1]), 'power': float(f[2]),
+                            'reasons': [n for i, n in enumerate(names) if f[3 + i].lower().startswith('active')]})
         except Exception:
             pass
-        stop.wait(0.2)
+        stop.wait(0.1)
 
 
 def summarize_clocks(samples):
     if not samples:
-        return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-    sm = sorted(float(s[0]) for s in samples if s[0].replace('.', '').isdigit())
-    names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-    reasons = [n for i, n in enumerate(names) if any(len(s) > 3 + i and s[3 + i].lower().startswith('active') for s in samples)]
-    return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': float(samples[0][1]) if samples[0][1].replace('.', '').isdigit() else None,
-            'power_w_max': max(float(s[2]) for s in samples if s[2].replace('.', '').isdigit()) if samples else None,
-            'samples': len(samples), 'reasons': reasons}
+        return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no clock samples (NVML and nvidia-smi unavailable)']}
+    sm = sorted(s['sm'] for s in samples)
+    reasons = sorted({r for s in samples for r in s['reasons']})
+    return {'sm_mhz': sm[len(sm) // 2], 'sm_min_mhz': sm[0], 'sm_max_mhz': samples[0]['max'],
+            'power_w_max': max(s['power'] for s in samples), 'samples': len(samples), 'reasons': reasons}
 
 
 def measured_peaks():
@@ -295,7 +329,7 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', type=str, default='b200')
     ap.add_argument('--members', type=int, default=1024)
