@@ -89,7 +89,8 @@ enum { QGB_CLOSURE_NONE = 0, QGB_CLOSURE_GAN = 1, QGB_CLOSURE_VAE = 2, QGB_CLOSU
        QGB_CLOSURE_RAW = 5 /* bare network for qgb_cnn_forward only: any cin/cout, not coupled to qgb_step */ };
 enum { QGB_SAMPLER_AR1 = 0, QGB_SAMPLER_CONSTANT = 1, QGB_SAMPLER_DETERMINISTIC = 2 };
 enum { QGB_PREC_FP32 = 0,  /* fp32 FFMA direct convolution (bit-for-bit deterministic, parity reference) */
-       QGB_PREC_TC = 1     /* tcgen05 implicit GEMM, fp16 split precision (<=1e-3 rel. of the fp32 reference) */ };
+       QGB_PREC_TC = 1,    /* tcgen05 implicit GEMM, fp16 split precision (<=1e-3 rel. of the fp32 reference) */
+       QGB_PREC_TC_FAST = 2 /* same with a single-pass layer 2: ~30 % faster, error up to ~2e-3 with the shipped VAE/GZ nets */ };
 
 /* One AndrewCNN (tools/cnn_tools.py:125-182) in eval mode with BatchNorm folded to a per-channel affine
  * (scale = gamma/sqrt(running_var+eps), shift = beta - running_mean*scale), laid out as torch stores it. */

@@ -13,7 +13,8 @@ QGB_OK, QGB_EINVAL, QGB_ECUDA, QGB_ESTATE, QGB_EUNSUPPORTED = 0, -1, -2, -3, -4
 (F_Q, F_QH, F_PH, F_U, F_V, F_DQHDT, F_FORCING, F_NOISE, F_P) = range(9)
 CLOSURE_NONE, CLOSURE_GAN, CLOSURE_VAE, CLOSURE_GZ, CLOSURE_OLS, CLOSURE_RAW = range(6)
 SAMPLER_AR1, SAMPLER_CONSTANT, SAMPLER_DETERMINISTIC = range(3)
-PREC_FP32, PREC_TC = 0, 1
+PREC_FP32, PREC_TC, PREC_TC_FAST = 0, 1, 2
+PRECISIONS = {'fp32': PREC_FP32, 'tc': PREC_TC, 'tc_fast': PREC_TC_FAST}
 
 
 class QgbConfig(ctypes.Structure):

@@ -221,13 +221,14 @@ int net_forward_fp32(qgb_handle* h, const DevNet& net, const float* x, long long
 
 int net_forward(qgb_handle* h, int net, const float* x, long long x_bs, float* y, long long y_bs, int batch, int ny,
                 int nx, int softplus, int accumulate, int precision, cudaStream_t st) {
-  if (precision == QGB_PREC_TC) {
+  if (precision == QGB_PREC_TC || precision == QGB_PREC_TC_FAST) {
     if (!h->nets[net].tc.ready) return fail(h, QGB_EUNSUPPORTED, "tcgen05 path: network architecture not supported");
     std::string e;
     h->tcw.prof_layer = (h->prof_net == net) ? h->prof_layer : -1;
     h->tcw.prof_events = &h->prof_events;
     h->tcw.prof_images = &h->prof_images;
-    int rc = tc_forward(h->nets[net].tc, h->tcw, x, x_bs, y, y_bs, batch, ny, nx, softplus, accumulate, h->nsm, st, &e);
+    int rc = tc_forward(h->nets[net].tc, h->tcw, x, x_bs, y, y_bs, batch, ny, nx, softplus, accumulate, h->nsm, st, &e,
+                        precision == QGB_PREC_TC_FAST);
     if (rc != 0) return fail(h, rc, "%s", e.c_str());
     g_launches.fetch_add(h->tcw.last_launches, std::memory_order_relaxed);
     return QGB_OK;
@@ -700,7 +701,7 @@ int qgb_cnn_load(qgb_handle* h, int kind, int net, int nlayers, const qgb_cnn_la
 
 int qgb_closure_config(qgb_handle* h, const float x_std[2], const float y_std[2], double weight, int precision) {
   if (!h || !x_std || !y_std) return fail(h, QGB_EINVAL, "null argument");
-  if (precision != QGB_PREC_FP32 && precision != QGB_PREC_TC) return fail(h, QGB_EINVAL, "unknown precision %d", precision);
+  if (precision < QGB_PREC_FP32 || precision > QGB_PREC_TC_FAST) return fail(h, QGB_EINVAL, "unknown precision %d", precision);
   h->x_std[0] = x_std[0]; h->x_std[1] = x_std[1];
   h->y_std[0] = y_std[0]; h->y_std[1] = y_std[1];
   h->weight = weight;

@@ -6,9 +6,11 @@
 // BatchNorm2d), :125-176 (AndrewCNN), models/mean_var_model.py:14-17 (softplus head).
 //
 // Precision plan ("plain TF32 fails the 1e-3 bound"): operands are fp16 (11-bit significand, same as
-// TF32, at twice the tensor rate).  Layer 2 (128->64, 5x5, 75 % of the FLOPs) runs ONE pass on fp16 activations and
-// weights; every other layer runs the 3-pass split  a*w ~= a_hi*w_hi + a_lo*w_hi + a_hi*w_lo  (a = a_hi + a_lo, both
-// fp16; error ~2^-22), fp32 accumulation throughout.  Weights are pre-scaled per layer by a power of two so they sit
+// TF32, at twice the tensor rate).  Every layer but the second runs the 3-pass split  a*w ~= a_hi*w_hi + a_lo*w_hi + a_hi*w_lo
+// (a = a_hi + a_lo, both fp16; error ~2^-22), fp32 accumulation throughout.  Layer 2 (128->64, 5x5, 75 % of the FLOPs) runs
+// TWO passes, (a_hi + a_lo)*w_hi: with the shipped networks the rounding of its ACTIVATIONS to 11 bits alone costs up to
+// 1.8e-3 relative (VAE decoder, GZ mean net; measured, profiles/r1_tc_precision.md) while rounding its weights costs
+// 2-5e-4.  A single-pass variant (QGB_PREC_TC_FAST) is kept for networks where that is acceptable.  Weights are pre-scaled per layer by a power of two so they sit
 // in the fp16 normal range; the epilogue undoes the scale exactly.
 //
 // Data layout.  Activations live in HBM as  [image][C/32][ny+2p][nx+2p][32] fp16  (hi plane, optional lo plane): the
@@ -168,23 +170,25 @@ template <int CIN, int COUT, int KS, int PASSES, int T>
 struct TcCfg {
   static constexpr int NCHUNK = CIN / 32;
   static constexpr int TAPS = KS * KS;
-  static constexpr int PLANES = PASSES == 3 ? 2 : 1;
+  // PASSES 1: a_hi w_hi;  2: (a_hi + a_lo) w_hi;  3: a_hi w_hi + a_lo w_hi + a_hi w_lo
+  static constexpr int PLANES = PASSES >= 2 ? 2 : 1;      // activation planes (hi [, lo])
+  static constexpr int WPLANES = PASSES == 3 ? 2 : 1;     // weight planes
   static constexpr int HY = 16 + KS - 1;
   static constexpr int HX = 8 * T + KS - 1;
   static constexpr int A_BYTES = HY * HX * 64;                        // one plane of one 32-channel chunk
   static constexpr int A_PLANE = (A_BYTES + 1023) / 1024 * 1024;      // swizzle atoms need aligned plane bases
   static constexpr int A_STAGE = PLANES * A_PLANE;
   static constexpr int A_TX = PLANES * A_BYTES;
-  static constexpr int W_TAP = PLANES * 4 * COUT * 16;            // one (chunk, tap) weight slab
+  static constexpr int W_TAP = WPLANES * 4 * COUT * 16;           // one (chunk, tap) weight slab
   static constexpr int W_STAGE = KS * W_TAP;                      // a pipeline stage holds one tap ROW (KS taps)
-  static constexpr int NW = QGB_TC_NW_OVERRIDE ? QGB_TC_NW_OVERRIDE : ((KS == 5) ? 3 : 4);
+  static constexpr int NW = QGB_TC_NW_OVERRIDE ? QGB_TC_NW_OVERRIDE : ((KS == 5) ? (PASSES == 2 ? 2 : 3) : 4);
   // 3-pass layers with a narrow N concatenate [w_hi | w_lo] along N:  D[:, :COUT] += a_hi w_hi + a_lo w_hi,
   // D[:, COUT:] += a_hi w_lo  (two MMAs instead of three -> fewer shared-memory reads of the A operand)
   static constexpr bool NCAT = (PASSES == 3) && (COUT <= 32);
   static constexpr int DCOLS = NCAT ? 2 * COUT : COUT;       // TMEM columns per M-tile
   static constexpr int NCOLS_USED = 2 * T * DCOLS;
   static constexpr int NCOLS = NCOLS_USED <= 32 ? 32 : NCOLS_USED <= 64 ? 64 : NCOLS_USED <= 128 ? 128 : NCOLS_USED <= 256 ? 256 : 512;
-  static constexpr int SMEM = 2 * A_STAGE + NW * W_STAGE + 3 * COUT * 4 + 256 + 1024 + 6400;
+  static constexpr int SMEM = 2 * A_STAGE + NW * W_STAGE + 3 * COUT * 4 + 256 + 1024;   // + 6400 for the FUSE window
   static_assert(NCOLS_USED <= 512, "accumulators exceed TMEM");
   static_assert(CIN % 32 == 0 && COUT % 16 == 0, "bad channel counts");
 };
@@ -361,7 +365,7 @@ __global__ void __launch_bounds__(FUSE ? 640 : 384, 1) conv_tc_kernel(const __gr
     // A: K-major SWIZZLE_64B (layout type 4): pixel rows of 64 B, 8-row groups (= next image row) at SBO = HX*64 B
     // B: K-major no swizzle: weight slab [j][plane][COUT][8]: 8 couts x 16 B per core matrix, next j at LBO
     constexpr uint32_t A_SBO = C::HX * 4;                                       // in 16-byte units
-    constexpr uint32_t B_LBO = C::PLANES * COUT, B_SBO = 8;
+    constexpr uint32_t B_LBO = C::WPLANES * COUT, B_SBO = 8;
     constexpr uint32_t a_hi32 = A_SBO | (1u << 14) | (4u << 29), b_hi32 = B_SBO | (1u << 14);   // upper descriptor words
     const uint32_t sA_u = ptx::smem_u32(sA) >> 4, sW_u = ptx::smem_u32(sW) >> 4;
     uint32_t ia = 0, iw = 0, it = 0;
@@ -402,13 +406,13 @@ __global__ void __launch_bounds__(FUSE ? 640 : 384, 1) conv_tc_kernel(const __gr
                   const uint64_t adesc = ((uint64_t)a_hi32 << 32) | ((a0 + 32 * t + 2 * ks) & 0x3FFFu) | (1u << 16);
                   ptx::mma_f16(dbase + t * C::DCOLS, adesc, bdesc, C::NCAT ? idesc_cat : idesc, first);
                 }
-                if (PASSES == 3) {
+                if (PASSES >= 2) {
 #pragma unroll
                   for (int t = 0; t < T; ++t) {
                     const uint64_t adesc_lo = ((uint64_t)a_hi32 << 32) | ((a0 + 32 * t + 2 * ks + (C::A_PLANE >> 4)) & 0x3FFFu) | (1u << 16);
                     ptx::mma_f16(dbase + t * C::DCOLS, adesc_lo, bdesc, idesc, 1u);
                   }
-                  if (!C::NCAT) {
+                  if (PASSES == 3 && !C::NCAT) {
                     const uint64_t bdesc_lo = ((uint64_t)b_hi32 << 32) | (b0 + 2 * ks * B_LBO + COUT);
 #pragma unroll
                     for (int t = 0; t < T; ++t) {
@@ -689,12 +693,12 @@ inline cudaError_t tc_launch(const TcConvParams& P, int nimg, int nsm, cudaStrea
   auto kern = conv_tc_kernel<CIN, COUT, KS, PASSES, T, OUTMODE, FUSE>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM + (FUSE ? 6400 : 0));
     if (e != cudaSuccess) return e;
     configured = true;
   }
   const int grid = P.num_tiles < nsm ? P.num_tiles : nsm;
-  kern<<<grid, FUSE ? 640 : 384, C::SMEM, st>>>(P, M);
+  kern<<<grid, FUSE ? 640 : 384, C::SMEM + (FUSE ? 6400 : 0), st>>>(P, M);
   return cudaGetLastError();
 }
 
@@ -706,7 +710,8 @@ inline cudaError_t tc_launch_T(int T, const TcConvParams& P, int nimg, int nsm, 
 }
 
 inline int tc_forward(const TcNet& net, TcWorkspace& ws, const float* x, long long x_bs, float* y, long long y_bs,
-                      int batch, int ny, int nx, int softplus, int accumulate, int nsm, cudaStream_t st, std::string* err) {
+                      int batch, int ny, int nx, int softplus, int accumulate, int nsm, cudaStream_t st, std::string* err,
+                      bool fast_l2 = false) {
   if (!net.ready) { *err = "tcgen05 path: network not packed"; return QGB_EUNSUPPORTED; }
   if (ny % 16 || nx % 16) { *err = "tcgen05 path needs ny and nx to be multiples of 16 (use precision='fp32')"; return QGB_EUNSUPPORTED; }
   const int T = nx % 32 == 0 ? 4 : (nx % 24 == 0 ? 3 : 2);
@@ -714,12 +719,12 @@ inline int tc_forward(const TcNet& net, TcWorkspace& ws, const float* x, long lo
   // 1024 -> 162 k member-steps/s); the workspace is capped at ~6 GB.
   static int max_chunk = 0;
   if (!max_chunk) { const char* e = getenv("QGB_TC_CHUNK"); max_chunk = e ? atoi(e) : 1024; if (max_chunk < 1) max_chunk = 1024; }
-  const size_t per_img = (128 * (size_t)(ny + 4) * (nx + 4) + 160 * (size_t)(ny + 2) * (nx + 2)) * 2;
+  const size_t per_img = (256 * (size_t)(ny + 4) * (nx + 4) + 128 * (size_t)(ny + 2) * (nx + 2)) * 2;
   int chunk = batch < max_chunk ? batch : max_chunk;
   while (chunk > 1 && (size_t)chunk * per_img > (6ull << 30)) chunk = (chunk + 1) / 2;
   // workspace: a0 (im2col, hi/lo), ping (<=128 ch, halo 2), pong (<=64 ch, halo 1)
   const size_t need[6] = {16, 16,   // (the im2col tensor of layer 1 is built on the fly in shared memory)
-                          (size_t)chunk * 128 * (ny + 4) * (nx + 4), (size_t)chunk * 32 * (ny + 2) * (nx + 2),
+                          (size_t)chunk * 128 * (ny + 4) * (nx + 4), (size_t)chunk * 128 * (ny + 4) * (nx + 4),
                           (size_t)chunk * 64 * (ny + 2) * (nx + 2), (size_t)chunk * 64 * (ny + 2) * (nx + 2)};
   for (int i = 0; i < 6; ++i)
     if (ws.halves[i] < need[i]) {
@@ -761,8 +766,9 @@ inline int tc_forward(const TcNet& net, TcWorkspace& ws, const float* x, long lo
       if (prof) { cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventRecord(ev0, st); }
       cudaError_t e;
       if (li == 0) {
-        e = net.kp == 128 ? tc_launch<128, 128, 1, 3, 2, TC_OUT_HI, 4>(P, nb, nsm, st) : tc_launch<64, 128, 1, 3, 2, TC_OUT_HI, 2>(P, nb, nsm, st);
-      } else if (li == 1) e = tc_launch_T<128, 64, 5, 1, TC_OUT_HILO>(T, P, nb, nsm, st);
+        if (fast_l2) e = net.kp == 128 ? tc_launch<128, 128, 1, 3, 2, TC_OUT_HI, 4>(P, nb, nsm, st) : tc_launch<64, 128, 1, 3, 2, TC_OUT_HI, 2>(P, nb, nsm, st);
+        else e = net.kp == 128 ? tc_launch<128, 128, 1, 3, 2, TC_OUT_HILO, 4>(P, nb, nsm, st) : tc_launch<64, 128, 1, 3, 2, TC_OUT_HILO, 2>(P, nb, nsm, st);
+      } else if (li == 1) e = fast_l2 ? tc_launch_T<128, 64, 5, 1, TC_OUT_HILO>(T, P, nb, nsm, st) : tc_launch_T<128, 64, 5, 2, TC_OUT_HILO>(T, P, nb, nsm, st);
       else if (li == 2) e = tc_launch_T<64, 32, 3, 3, TC_OUT_HILO>(T, P, nb, nsm, st);
       else if (li < 7) e = tc_launch_T<32, 32, 3, 3, TC_OUT_HILO>(T, P, nb, nsm, st);
       else e = tc_launch_T<32, 16, 3, 3, TC_OUT_FINAL>(T, P, nb, nsm, st);

@@ -92,5 +92,5 @@ class DeviceClosure(Parameterization):
             _lib.check(lib.qgb_cnn_load(model._h, self.closure_kind, i, len(arr), arr), model._h)
         xs = (ctypes.c_float * 2)(*[float(v) for v in np.asarray(self.x_scale.std).reshape(-1)[:2]])
         ys = (ctypes.c_float * 2)(*[float(v) for v in np.asarray(self.y_scale.std).reshape(-1)[:2]])
-        prec = {'fp32': _lib.PREC_FP32, 'tc': _lib.PREC_TC}[precision]
+        prec = _lib.PRECISIONS[precision]
         _lib.check(lib.qgb_closure_config(model._h, xs, ys, float(weight), prec), model._h)

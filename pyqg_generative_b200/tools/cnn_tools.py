@@ -185,7 +185,7 @@ class AndrewCNN(object):
             dev = torch.cuda.current_device()
         xd = x.to(device='cuda:%d' % dev, dtype=torch.float32).contiguous()
         y = torch.empty((x.shape[0], self.n_out, x.shape[2], x.shape[3]), dtype=torch.float32, device=xd.device)
-        prec = {'fp32': _lib.PREC_FP32, 'tc': _lib.PREC_TC}[precision or self.precision]
+        prec = _lib.PRECISIONS[precision or self.precision]
         h = self._engine(dev)
         stream = torch.cuda.current_stream(xd.device).cuda_stream
         _lib.check(_lib.load().qgb_cnn_forward(h, 0, xd.data_ptr(), y.data_ptr(), x.shape[0], x.shape[2], x.shape[3],
