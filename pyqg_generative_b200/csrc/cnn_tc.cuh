@@ -29,6 +29,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -116,6 +117,15 @@ __device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same with e4m3 inputs (K = 32 per instruction): the low halves of the split-precision activations only need ~4 bits
+__device__ __forceinline__ void mma_f8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -166,20 +176,25 @@ struct TcConvParams {
   int ny, nx, tiles_y, tiles_x, num_tiles;
 };
 
-template <int CIN, int COUT, int KS, int PASSES, int T>
+// LO8: the low halves of the activations travel as e4m3 (value * 2^11, 1 byte per element, SWIZZLE_32B rows) and their pass
+// a_lo x w_hi runs as ONE kind::f8f6f4 MMA per 32 channels against an e4m3 copy of the weights (w * 2^-11): the product only
+// needs ~4 significant bits (it is 2^-11 of the result), costs half the shared-memory reads and half the HBM bytes.
+template <int CIN, int COUT, int KS, int PASSES, int T, bool LO8 = false>
 struct TcCfg {
   static constexpr int NCHUNK = CIN / 32;
   static constexpr int TAPS = KS * KS;
   // PASSES 1: a_hi w_hi;  2: (a_hi + a_lo) w_hi;  3: a_hi w_hi + a_lo w_hi + a_hi w_lo
   static constexpr int PLANES = PASSES >= 2 ? 2 : 1;      // activation planes (hi [, lo])
-  static constexpr int WPLANES = PASSES == 3 ? 2 : 1;     // weight planes
+  static constexpr int WPLANES = PASSES == 3 ? 2 : 1;     // fp16 weight planes
   static constexpr int HY = 16 + KS - 1;
   static constexpr int HX = 8 * T + KS - 1;
-  static constexpr int A_BYTES = HY * HX * 64;                        // one plane of one 32-channel chunk
+  static constexpr int A_BYTES = HY * HX * 64;                        // hi plane of one 32-channel chunk
   static constexpr int A_PLANE = (A_BYTES + 1023) / 1024 * 1024;      // swizzle atoms need aligned plane bases
-  static constexpr int A_STAGE = PLANES * A_PLANE;
-  static constexpr int A_TX = PLANES * A_BYTES;
-  static constexpr int W_TAP = WPLANES * 4 * COUT * 16;           // one (chunk, tap) weight slab
+  static constexpr int A_LO_BYTES = PLANES == 2 ? (LO8 ? HY * HX * 32 : A_BYTES) : 0;
+  static constexpr int A_STAGE = A_PLANE + (A_LO_BYTES + 1023) / 1024 * 1024;
+  static constexpr int A_TX = A_BYTES + A_LO_BYTES;
+  static constexpr int W16 = WPLANES * 4 * COUT * 16;                 // fp16 part of one (chunk, tap) weight slab
+  static constexpr int W_TAP = W16 + (LO8 ? 2 * COUT * 16 : 0);       // + e4m3 part [2][COUT][16 B]
   static constexpr int W_STAGE = KS * W_TAP;                      // a pipeline stage holds one tap ROW (KS taps)
   static constexpr int NW = QGB_TC_NW_OVERRIDE ? QGB_TC_NW_OVERRIDE : ((KS == 5) ? (PASSES == 2 ? 2 : 3) : 4);
   // 3-pass layers with a narrow N concatenate [w_hi | w_lo] along N:  D[:, :COUT] += a_hi w_hi + a_lo w_hi,
@@ -209,7 +224,8 @@ template <int CIN, int COUT, int KS, int PASSES, int T, int OUTMODE, int FUSE = 
 __global__ void __launch_bounds__(FUSE ? 640 : 384, 1) conv_tc_kernel(const __grid_constant__ TcConvParams P,
                                                                       const __grid_constant__ TcMaps M) {
   static_assert(FUSE == 0 || (KS == 1 && T == 2 && PASSES == 3), "fused im2col is the layer-1 configuration");
-  using C = TcCfg<CIN, COUT, KS, PASSES, T>;
+  constexpr bool LO8 = !FUSE && PASSES >= 2;
+  using C = TcCfg<CIN, COUT, KS, PASSES, T, LO8>;
   extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
   unsigned char* smem = tc_smem_raw + ((1024u - (ptx::smem_u32(tc_smem_raw) & 1023u)) & 1023u);
   unsigned char* sA = smem;
@@ -392,6 +408,8 @@ __global__ void __launch_bounds__(FUSE ? 640 : 384, 1) conv_tc_kernel(const __gr
             // so shifted tap windows need no descriptor fix-up.
             const uint32_t a_row = sA_u + sa * (C::A_STAGE >> 4) + dy * C::HX * 4;
             const uint32_t b_row = (sW_u + sw * (C::W_STAGE >> 4)) | (B_LBO << 16);
+            const uint32_t a_row8 = sA_u + sa * (C::A_STAGE >> 4) + (C::A_PLANE >> 4) + dy * C::HX * 2;   // e4m3 lo plane
+            const uint32_t b_row8 = sW_u + sw * (C::W_STAGE >> 4) + (C::W16 >> 4);
 #pragma unroll
             for (int dx = 0; dx < KS; ++dx) {
               const uint32_t a0 = a_row + dx * 4;
@@ -406,20 +424,31 @@ __global__ void __launch_bounds__(FUSE ? 640 : 384, 1) conv_tc_kernel(const __gr
                   const uint64_t adesc = ((uint64_t)a_hi32 << 32) | ((a0 + 32 * t + 2 * ks) & 0x3FFFu) | (1u << 16);
                   ptx::mma_f16(dbase + t * C::DCOLS, adesc, bdesc, C::NCAT ? idesc_cat : idesc, first);
                 }
-                if (PASSES >= 2) {
+                if (PASSES >= 2 && !LO8) {
 #pragma unroll
                   for (int t = 0; t < T; ++t) {
                     const uint64_t adesc_lo = ((uint64_t)a_hi32 << 32) | ((a0 + 32 * t + 2 * ks + (C::A_PLANE >> 4)) & 0x3FFFu) | (1u << 16);
                     ptx::mma_f16(dbase + t * C::DCOLS, adesc_lo, bdesc, idesc, 1u);
                   }
-                  if (PASSES == 3 && !C::NCAT) {
-                    const uint64_t bdesc_lo = ((uint64_t)b_hi32 << 32) | (b0 + 2 * ks * B_LBO + COUT);
+                }
+                if (PASSES == 3 && !C::NCAT) {
+                  const uint64_t bdesc_lo = ((uint64_t)b_hi32 << 32) | (b0 + 2 * ks * B_LBO + COUT);
 #pragma unroll
-                    for (int t = 0; t < T; ++t) {
-                      const uint64_t adesc = ((uint64_t)a_hi32 << 32) | ((a0 + 32 * t + 2 * ks) & 0x3FFFu) | (1u << 16);
-                      ptx::mma_f16(dbase + t * C::DCOLS, adesc, bdesc_lo, idesc, 1u);
-                    }
+                  for (int t = 0; t < T; ++t) {
+                    const uint64_t adesc = ((uint64_t)a_hi32 << 32) | ((a0 + 32 * t + 2 * ks) & 0x3FFFu) | (1u << 16);
+                    ptx::mma_f16(dbase + t * C::DCOLS, adesc, bdesc_lo, idesc, 1u);
                   }
+                }
+              }
+              if (LO8) {
+                // a_lo (e4m3, SWIZZLE_32B rows of 32 channels) x w (e4m3, [2][COUT][16 B]): one K=32 MMA per M-tile
+                constexpr uint32_t a8_hi32 = (uint32_t)(C::HX * 2) | (1u << 14) | (6u << 29);
+                const uint32_t a8 = a_row8 + dx * 2;
+                const uint64_t bdesc8 = ((uint64_t)b_hi32 << 32) | ((b_row8 + dx * (C::W_TAP >> 4)) | ((uint32_t)COUT << 16));
+#pragma unroll
+                for (int t = 0; t < T; ++t) {
+                  const uint64_t adesc8 = ((uint64_t)a8_hi32 << 32) | ((a8 + 16 * t) & 0x3FFFu) | (1u << 16);
+                  ptx::mma_f8(dbase + t * C::DCOLS, adesc8, bdesc8, idesc, 1u);
                 }
               }
             }
@@ -508,27 +537,31 @@ __global__ void __launch_bounds__(FUSE ? 640 : 384, 1) conv_tc_kernel(const __gr
             ys[0] = y + op; xs[0] = x + op;
             if (y < op) ys[nys++] = y + op + P.ny; else if (y >= P.ny - op) ys[nys++] = y + op - P.ny;
             if (x < op) xs[nxs++] = x + op + P.nx; else if (x >= P.nx - op) xs[nxs++] = x + op - P.nx;
+            uint32_t hi[8], lo8[4];
 #pragma unroll
-            for (int jj = 0; jj < 2; ++jj) {
-              uint32_t hi[4], lo[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float f0 = v[jj * 8 + 2 * e], f1 = v[jj * 8 + 2 * e + 1];
-                const __half h0 = __float2half_rn(f0), h1 = __float2half_rn(f1);
-                hi[e] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-                if (OUTMODE == TC_OUT_HILO) {
-                  const __half l0 = __float2half_rn(f0 - __half2float(h0)), l1 = __float2half_rn(f1 - __half2float(h1));
-                  lo[e] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
-                }
+            for (int e = 0; e < 8; ++e) {
+              const float f0 = v[2 * e], f1 = v[2 * e + 1];
+              const __half2 h2 = __floats2half2_rn(f0, f1);
+              hi[e] = *reinterpret_cast<const uint32_t*>(&h2);
+              if (OUTMODE == TC_OUT_HILO) {
+                // low half as e4m3 of (f - hi) * 2^11 (the consumer's e4m3 weights carry the 2^-11)
+                const float2 back = __half22float2(h2);
+                const unsigned short p = __nv_cvt_float2_to_fp8x2(make_float2((f0 - back.x) * 2048.f, (f1 - back.y) * 2048.f),
+                                                                  __NV_SATFINITE, __NV_E4M3);
+                if (e & 1) lo8[e >> 1] |= (uint32_t)p << 16; else lo8[e >> 1] = p;
               }
-              const int chunk = n0 >> 5, within = (n0 & 31) + jj * 8;
-              for (int a = 0; a < nys; ++a)
-                for (int b = 0; b < nxs; ++b) {
-                  const long long off = ((((long long)img * P.out_nch + chunk) * HPo + ys[a]) * WPo + xs[b]) * 32 + within;
-                  *reinterpret_cast<uint4*>(P.out_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                  if (OUTMODE == TC_OUT_HILO) *reinterpret_cast<uint4*>(P.out_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                }
             }
+            const int chunk = n0 >> 5, within = n0 & 31;
+            for (int a = 0; a < nys; ++a)
+              for (int b = 0; b < nxs; ++b) {
+                const long long pix = (((long long)img * P.out_nch + chunk) * HPo + ys[a]) * WPo + xs[b];
+                uint4* dh = reinterpret_cast<uint4*>(P.out_hi + pix * 32 + within);
+                dh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                dh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                if (OUTMODE == TC_OUT_HILO)
+                  *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(P.out_lo) + pix * 32 + within) =
+                      make_uint4(lo8[0], lo8[1], lo8[2], lo8[3]);
+              }
           }
         }
       }
@@ -552,6 +585,7 @@ struct TcNet {
   int cin0 = 0;          // real input channels of the network (4 or 2)
   int kp = 0;            // padded im2col K of layer 1 (128 or 64)
   std::vector<TcLayer> layers;
+  TcLayer l2_fast;       // layer 2 packed for the single-pass variant (QGB_PREC_TC_FAST)
 };
 struct TcWorkspace {
   __half* buf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // a0_hi, a0_lo, ping hi/lo, pong hi/lo
@@ -565,6 +599,8 @@ struct TcWorkspace {
 
 inline void tc_free_net(TcNet& n) {
   for (auto& L : n.layers) { cudaFree(L.w); cudaFree(L.bias); cudaFree(L.bn_s); cudaFree(L.bn_t); }
+  cudaFree(n.l2_fast.w); cudaFree(n.l2_fast.bias); cudaFree(n.l2_fast.bn_s); cudaFree(n.l2_fast.bn_t);
+  n.l2_fast = TcLayer();
   n.layers.clear();
   n.ready = false;
 }
@@ -574,7 +610,7 @@ inline void tc_free_workspace(TcWorkspace& w) {
 inline int tc_launches_per_forward(const TcNet& n) { return n.ready ? (int)n.layers.size() : 0; }
 
 // Pack one layer: weights -> [chunk][tap][4][plane][cout_p][8] fp16 (hi [, lo]) scaled by 2^k, epilogue vectors padded.
-inline bool tc_pack_layer(TcLayer& L, int cin_p, int cout_p, int ks, int passes, int real_cin, int real_cout,
+inline bool tc_pack_layer(TcLayer& L, int cin_p, int cout_p, int ks, int passes, bool lo8, int real_cin, int real_cout,
                           const std::vector<float>& wdense /* [real_cout][real_cin][ks*ks] */, const float* bias,
                           const float* bn_s, const float* bn_t, int relu_bn) {
   L.cin = cin_p; L.cout = cout_p; L.ks = ks; L.relu_bn = relu_bn; L.real_cout = real_cout; L.passes = passes;
@@ -589,9 +625,14 @@ inline bool tc_pack_layer(TcLayer& L, int cin_p, int cout_p, int ks, int passes,
   }
   const float scale = std::ldexp(1.0f, k);
   L.inv_wscale = std::ldexp(1.0f, -k);
-  std::vector<__half> pk((size_t)nchunk * taps * planes * 4 * cout_p * 8, __float2half(0.f));
+  // slab per (chunk, tap): fp16 [4 j][planes][cout_p][8]  followed (lo8) by e4m3 [2 kc][cout_p][16] = w * scale * 2^-11
+  const size_t w16 = (size_t)planes * 4 * cout_p * 16, w8 = lo8 ? (size_t)2 * cout_p * 16 : 0, slab = w16 + w8;
+  std::vector<unsigned char> pk((size_t)nchunk * taps * slab, 0);
   for (int c = 0; c < nchunk; ++c)
-    for (int tap = 0; tap < taps; ++tap)
+    for (int tap = 0; tap < taps; ++tap) {
+      unsigned char* base = pk.data() + (size_t)(c * taps + tap) * slab;
+      __half* b16 = reinterpret_cast<__half*>(base);
+      unsigned char* b8 = base + w16;
       for (int j = 0; j < 4; ++j)
         for (int co = 0; co < cout_p; ++co)
           for (int e = 0; e < 8; ++e) {
@@ -599,17 +640,19 @@ inline bool tc_pack_layer(TcLayer& L, int cin_p, int cout_p, int ks, int passes,
             float v = 0.f;
             if (ci < real_cin && co < real_cout) v = wdense[((size_t)co * real_cin + ci) * taps + tap] * scale;
             const __half h = __float2half_rn(v);
-            const size_t base = ((size_t)(c * taps + tap) * planes) * 4 * cout_p * 8;
-            pk[base + ((size_t)(j * planes + 0) * cout_p + co) * 8 + e] = h;
-            if (planes == 2) pk[base + ((size_t)(j * planes + 1) * cout_p + co) * 8 + e] = __float2half_rn(v - __half2float(h));
+            b16[((size_t)(j * planes + 0) * cout_p + co) * 8 + e] = h;
+            if (planes == 2) b16[((size_t)(j * planes + 1) * cout_p + co) * 8 + e] = __float2half_rn(v - __half2float(h));
+            if (lo8) b8[((size_t)(ci % 32 / 16) * cout_p + co) * 16 + (ci % 16)] =
+                (unsigned char)__nv_cvt_float_to_fp8(v * (1.0f / 2048.0f), __NV_SATFINITE, __NV_E4M3);
           }
+    }
   std::vector<float> b(cout_p, 0.f), s(cout_p, 1.f), t(cout_p, 0.f);
   for (int i = 0; i < real_cout; ++i) {
     b[i] = bias[i];
     if (relu_bn) { s[i] = bn_s[i]; t[i] = bn_t[i]; }
   }
-  if (cudaMalloc(&L.w, pk.size() * sizeof(__half)) != cudaSuccess) return false;
-  if (cudaMemcpy(L.w, pk.data(), pk.size() * sizeof(__half), cudaMemcpyHostToDevice) != cudaSuccess) return false;
+  if (cudaMalloc(&L.w, pk.size()) != cudaSuccess) return false;
+  if (cudaMemcpy(L.w, pk.data(), pk.size(), cudaMemcpyHostToDevice) != cudaSuccess) return false;
   for (auto pr : {std::make_pair(&L.bias, &b), std::make_pair(&L.bn_s, &s), std::make_pair(&L.bn_t, &t)}) {
     if (cudaMalloc(pr.first, cout_p * sizeof(float)) != cudaSuccess) return false;
     if (cudaMemcpy(*pr.first, pr.second->data(), cout_p * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) return false;
@@ -638,15 +681,17 @@ inline int tc_pack_net(TcNet& n, int nlayers, const qgb_cnn_layer* L, std::strin
     for (int co = 0; co < 128; ++co)
       for (int ch = 0; ch < n.cin0; ++ch)
         for (int tap = 0; tap < 25; ++tap) wd[(size_t)co * K + tap * n.cin0 + ch] = L[0].weight[((size_t)co * n.cin0 + ch) * 25 + tap];
-    if (!tc_pack_layer(n.layers[0], n.kp, 128, 1, 3, K, 128, wd, L[0].bias, L[0].bn_scale, L[0].bn_shift, 1)) { *err = "cuda"; return QGB_ECUDA; }
+    if (!tc_pack_layer(n.layers[0], n.kp, 128, 1, 3, false, K, 128, wd, L[0].bias, L[0].bn_scale, L[0].bn_shift, 1)) { *err = "cuda"; return QGB_ECUDA; }
   }
   for (int i = 1; i < 8; ++i) {
     const int taps = ks[i] * ks[i];
     std::vector<float> wd(L[i].weight, L[i].weight + (size_t)cout[i] * cin[i] * taps);
     const int cout_p = i == 7 ? 16 : cout[i];
-    const int passes = i == 1 ? 1 : 3;
-    if (!tc_pack_layer(n.layers[i], cin[i], cout_p, ks[i], passes, cin[i], cout[i], wd, L[i].bias, L[i].bn_scale,
+    const int passes = i == 1 ? 2 : 3;          // layer 2: (a_hi + a_lo) w_hi ; others: full split precision
+    if (!tc_pack_layer(n.layers[i], cin[i], cout_p, ks[i], passes, true, cin[i], cout[i], wd, L[i].bias, L[i].bn_scale,
                        L[i].bn_shift, i < 7)) { *err = "cuda"; return QGB_ECUDA; }
+    if (i == 1 && !tc_pack_layer(n.l2_fast, cin[i], cout_p, ks[i], 1, false, cin[i], cout[i], wd, L[i].bias, L[i].bn_scale,
+                                 L[i].bn_shift, 1)) { *err = "cuda"; return QGB_ECUDA; }
   }
   n.ready = true;
   return 0;
@@ -677,16 +722,29 @@ inline bool tc_make_map(CUtensorMap* m, const __half* base, int WP, int HP, long
              CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// 4-D map over an e4m3 lo plane [nchunks][HP][WP][32 bytes], box = (32, hx, hy, 1), 32-byte swizzle
+inline bool tc_make_map8(CUtensorMap* m, const void* base, int WP, int HP, long long nchunks, int hx, int hy) {
+  PFN_tmapEncodeTiled enc = tmap_encoder();
+  if (!enc) return false;
+  cuuint64_t gdim[4] = {32, (cuuint64_t)WP, (cuuint64_t)HP, (cuuint64_t)nchunks};
+  cuuint64_t gstr[3] = {32, (cuuint64_t)WP * 32, (cuuint64_t)HP * WP * 32};
+  cuuint32_t box[4] = {32, (cuuint32_t)hx, (cuuint32_t)hy, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int CIN, int COUT, int KS, int PASSES, int T, int OUTMODE, int FUSE = 0>
 inline cudaError_t tc_launch(const TcConvParams& P, int nimg, int nsm, cudaStream_t st) {
-  using C = TcCfg<CIN, COUT, KS, PASSES, T>;
+  constexpr bool LO8 = !FUSE && PASSES >= 2;
+  using C = TcCfg<CIN, COUT, KS, PASSES, T, LO8>;
   TcMaps M;
   if (FUSE) {
     std::memset(&M, 0, sizeof(M));
   } else if (!tc_make_map(&M.hi, P.in_hi, P.WP, P.HP, (long long)nimg * P.nch_in, C::HX, C::HY)) {
     return cudaErrorInvalidValue;
   } else if (C::PLANES == 2) {
-    if (!tc_make_map(&M.lo, P.in_lo, P.WP, P.HP, (long long)nimg * P.nch_in, C::HX, C::HY)) return cudaErrorInvalidValue;
+    if (!tc_make_map8(&M.lo, P.in_lo, P.WP, P.HP, (long long)nimg * P.nch_in, C::HX, C::HY)) return cudaErrorInvalidValue;
   } else {
     M.lo = M.hi;
   }
@@ -738,7 +796,7 @@ inline int tc_forward(const TcNet& net, TcWorkspace& ws, const float* x, long lo
   for (int b0 = 0; b0 < batch; b0 += chunk) {
     const int nb = batch - b0 < chunk ? batch - b0 : chunk;
     for (int li = 0; li < 8; ++li) {
-      const TcLayer& L = net.layers[li];
+      const TcLayer& L = (li == 1 && fast_l2) ? net.l2_fast : net.layers[li];
       TcConvParams P;
       P.w = L.w; P.bias = L.bias; P.bn_s = L.bn_s; P.bn_t = L.bn_t; P.inv_wscale = L.inv_wscale; P.relu_bn = L.relu_bn;
       P.ny = ny; P.nx = nx; P.tiles_y = ny / 16;
