@@ -313,12 +313,12 @@ def run_b200(args):
         'roofline': {'bound': 'tensor', 'kernel': 'conv layer 2 (128->64, 5x5), %s' % args.precision,
                      'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
                      'peak_source': '%s bf16_tflops_sustained' % which,
-                     'traffic': (3.529e9 if args.precision == 'tc' else 2.305e9) * (pim.value / max(pl.value, 1)) / 1024.0,
-                     'traffic_source': 'dram__bytes_read+write of one ncu --set full capture, 3.53 GB (tc) or 2.305 GB (tc_fast) per 1024-image launch '
+                     'traffic': (2.638e9 if args.precision == 'tc' else 2.02e9) * (pim.value / max(pl.value, 1)) / 1024.0,
+                     'traffic_source': 'dram__bytes_read+write of one ncu --set full capture, 2.64 GB (tc) per 1024-image launch '
                                        '(profiles/r1_final_ncu_full.md); equal to the algorithmic activation bytes',
-                     'issued_frac': (achieved * (2.0 if args.precision == 'tc' else 1.0)) / peak,
-                     'issued_note': 'tc runs layer 2 in two fp16 passes (a_hi + a_lo) x w_hi to meet the 1e-3 tolerance: issued MMA '
-                                    'work is 2x the algorithmic flops; tc_fast (one pass) is ~30 % faster but reaches 1.3e-3 on the shipped VAE',
+                     'issued_frac': (achieved * (1.5 if args.precision == 'tc' else 1.0)) / peak,
+                     'issued_note': 'tc runs layer 2 as a_hi x w_hi (fp16) + a_lo x w (e4m3, half cost) to meet the 1e-3 tolerance: issued MMA '
+                                    'work is 1.5x the algorithmic flops in bf16-equivalents; tc_fast (hi pass only) reaches 1.3e-3 on the shipped VAE',
                      'launch_ms': pms.value / max(pl.value, 1), 'launches': int(pl.value),
                      'share_of_step': pms.value / ms if ms else None},
         'cpu_baseline': {'value': cpu_v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
