@@ -167,7 +167,7 @@ enum { TC_OUT_HI = 0, TC_OUT_HILO = 1, TC_OUT_FINAL = 2 };
 struct TcConvParams {
   const __half* in_hi; const __half* in_lo;  // [img][nch_in][HP][WP][32]
   int nch_in, HP, WP;
-  const __half* w;                           // [chunk][tap][4][plane][COUT][8]
+  const __half* w;                           // [chunk][tap column] weight stages, see tc_pack_layer
   const float* bias; const float* bn_s; const float* bn_t;
   float inv_wscale; int relu_bn;
   __half* out_hi; __half* out_lo; int out_pad, out_nch;   // [img][out_nch][ny+2*out_pad][nx+2*out_pad][32]
@@ -179,33 +179,48 @@ struct TcConvParams {
 // LO8: the low halves of the activations travel as e4m3 (value * 2^11, 1 byte per element, SWIZZLE_32B rows) and their pass
 // a_lo x w_hi runs as ONE kind::f8f6f4 MMA per 32 channels against an e4m3 copy of the weights (w * 2^-11): the product only
 // needs ~4 significant bits (it is 2^-11 of the result), costs half the shared-memory reads and half the HBM bytes.
-template <int CIN, int COUT, int KS, int PASSES, int T, bool LO8 = false>
+template <int CIN, int COUT, int KS, int PASSES, int T, bool LO8 = false, int NH = 1>
 struct TcCfg {
   static constexpr int NCHUNK = CIN / 32;
   static constexpr int TAPS = KS * KS;
   // PASSES 1: a_hi w_hi;  2: (a_hi + a_lo) w_hi;  3: a_hi w_hi + a_lo w_hi + a_hi w_lo
   static constexpr int PLANES = PASSES >= 2 ? 2 : 1;      // activation planes (hi [, lo])
   static constexpr int WPLANES = PASSES == 3 ? 2 : 1;     // fp16 weight planes
-  static constexpr int HY = 16 + KS - 1;
+  // ROW STACKING (NH > 1).  With both operands in shared memory an M=128 MMA costs max(N/2, (128+N)/4) clocks: the 4 KB
+  // A operand is re-read by every instruction, so N = 64 runs at 2/3 of the tensor rate and only N >= 128 reaches it
+  // (profiles/r1_mma_rate_microbench.txt).  COUT is 64 or less, so N is widened with OUTPUT ROWS instead: an M-tile takes
+  // every NH-th image row (the descriptor's stride-byte-offset is NH image rows), accumulator column block h holds output
+  // row g*NH + h, and the MMA for vertical window shift s multiplies the shared A window by the weights of ALL taps
+  // ky = s - h that are valid, concatenated along N (they are adjacent in shared memory because a weight stage stores a
+  // tap COLUMN in descending ky).  KS + NH - 1 shifts replace KS*NH row taps; for the 5x5 layer with NH = 2 that is
+  // 352 instead of 480 clocks per (tap column, K step) and the tensor pipe is busy 91 % of the time instead of 67 %.
+  static constexpr int HY = 16 * NH + KS - 1;
   static constexpr int HX = 8 * T + KS - 1;
+  static constexpr int NSHIFT = KS + NH - 1;
   static constexpr int A_BYTES = HY * HX * 64;                        // hi plane of one 32-channel chunk
   static constexpr int A_PLANE = (A_BYTES + 1023) / 1024 * 1024;      // swizzle atoms need aligned plane bases
   static constexpr int A_LO_BYTES = PLANES == 2 ? (LO8 ? HY * HX * 32 : A_BYTES) : 0;
   static constexpr int A_STAGE = A_PLANE + (A_LO_BYTES + 1023) / 1024 * 1024;
   static constexpr int A_TX = A_BYTES + A_LO_BYTES;
-  static constexpr int W16 = WPLANES * 4 * COUT * 16;                 // fp16 part of one (chunk, tap) weight slab
-  static constexpr int W_TAP = W16 + (LO8 ? 2 * COUT * 16 : 0);       // + e4m3 part [2][COUT][16 B]
-  static constexpr int W_STAGE = KS * W_TAP;                      // a pipeline stage holds one tap ROW (KS taps)
-  static constexpr int NW = QGB_TC_NW_OVERRIDE ? QGB_TC_NW_OVERRIDE : ((KS == 5) ? (PASSES == 2 ? 2 : 3) : 4);
   // 3-pass layers with a narrow N concatenate [w_hi | w_lo] along N:  D[:, :COUT] += a_hi w_hi + a_lo w_hi,
   // D[:, COUT:] += a_hi w_lo  (two MMAs instead of three -> fewer shared-memory reads of the A operand)
   static constexpr bool NCAT = (PASSES == 3) && (COUT <= 32);
-  static constexpr int DCOLS = NCAT ? 2 * COUT : COUT;       // TMEM columns per M-tile
+  static constexpr int NF = NCAT ? 2 * COUT : COUT;            // accumulator columns (= B rows) per stacked row
+  static constexpr int WROWS = NCAT ? NF : WPLANES * COUT;     // fp16 B rows per (K chunk, tap)
+  static constexpr int B_LBO = KS * WROWS;                     // 16-byte units between the 8-element K chunks
+  static constexpr int B8_LBO = KS * NF;
+  static constexpr int W16 = 4 * KS * WROWS * 16;              // fp16 part of one (chunk, tap column) weight stage
+  static constexpr int W_STAGE = W16 + (LO8 ? 2 * KS * NF * 16 : 0);   // + e4m3 part [2][KS][NF][16 B]
+  static constexpr int NW = QGB_TC_NW_OVERRIDE ? QGB_TC_NW_OVERRIDE : ((KS == 5) ? (PASSES == 2 ? 2 : 3) : 4);
+  static constexpr int DCOLS = NH * NF;                        // TMEM columns per M-tile
   static constexpr int NCOLS_USED = 2 * T * DCOLS;
   static constexpr int NCOLS = NCOLS_USED <= 32 ? 32 : NCOLS_USED <= 64 ? 64 : NCOLS_USED <= 128 ? 128 : NCOLS_USED <= 256 ? 256 : 512;
   static constexpr int SMEM = 2 * A_STAGE + NW * W_STAGE + 3 * COUT * 4 + 256 + 1024;   // + 6400 for the FUSE window
   static_assert(NCOLS_USED <= 512, "accumulators exceed TMEM");
   static_assert(CIN % 32 == 0 && COUT % 16 == 0, "bad channel counts");
+  static_assert(NH == 1 || NH <= KS, "the first MMA of a tile must cover every stacked row");
+  static_assert(NCAT || WPLANES == 1 || KS == 1, "separate w_lo pass is only laid out for 1x1 (layer 1)");
+  static_assert(NH * NF <= 256, "MMA N exceeds 256");
 };
 
 __device__ __forceinline__ float softplus_f(float v) { return v > 20.f ? v : log1pf(expf(v)); }
@@ -220,12 +235,12 @@ struct TcMaps {
 // FUSE = 0: activations arrive by TMA.  FUSE = cin0 (4 or 2): layer 1 -- four extra warps BUILD the 5x5 im2col operand
 // (K = 25*cin0 padded to CIN, fp16 hi/lo planes, SWIZZLE_64B layout) straight into the shared-memory stages from the raw
 // fp32 network input, so the im2col tensor never exists in HBM.
-template <int CIN, int COUT, int KS, int PASSES, int T, int OUTMODE, int FUSE = 0>
+template <int CIN, int COUT, int KS, int PASSES, int T, int OUTMODE, int FUSE = 0, int NH = 1>
 __global__ void __launch_bounds__(FUSE ? 640 : 384, 1) conv_tc_kernel(const __grid_constant__ TcConvParams P,
                                                                       const __grid_constant__ TcMaps M) {
-  static_assert(FUSE == 0 || (KS == 1 && T == 2 && PASSES == 3), "fused im2col is the layer-1 configuration");
+  static_assert(FUSE == 0 || (KS == 1 && T == 2 && PASSES == 3 && NH == 1), "fused im2col is the layer-1 configuration");
   constexpr bool LO8 = !FUSE && PASSES >= 2;
-  using C = TcCfg<CIN, COUT, KS, PASSES, T, LO8>;
+  using C = TcCfg<CIN, COUT, KS, PASSES, T, LO8, NH>;
   extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
   unsigned char* smem = tc_smem_raw + ((1024u - (ptx::smem_u32(tc_smem_raw) & 1023u)) & 1023u);
   unsigned char* sA = smem;
@@ -348,7 +363,7 @@ __global__ void __launch_bounds__(FUSE ? 640 : 384, 1) conv_tc_kernel(const __gr
     uint32_t ia = 0;
     for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
       const int img = tile / tiles_per_img, r = tile - img * tiles_per_img;
-      const int y0 = (r / P.tiles_x) * 16, x0 = (r % P.tiles_x) * 8 * T;
+      const int y0 = (r / P.tiles_x) * 16 * NH, x0 = (r % P.tiles_x) * 8 * T;
       for (int c = 0; c < C::NCHUNK; ++c, ++ia) {
         const uint32_t s = ia & 1, par = (ia >> 1) & 1;
         ptx::mbar_wait(&a_empty[s], par ^ 1);
@@ -361,7 +376,7 @@ __global__ void __launch_bounds__(FUSE ? 640 : 384, 1) conv_tc_kernel(const __gr
       }
     }
   } else if (warp == 2) {
-    // ===================== W producer: one (chunk, tap) weight slab per stage =======================================
+    // ===================== W producer: one (chunk, tap column) weight slab per stage ================================
     if (lane == 0) {
       uint32_t iw = 0;
       for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
@@ -376,17 +391,16 @@ __global__ void __launch_bounds__(FUSE ? 640 : 384, 1) conv_tc_kernel(const __gr
     }
   } else if (warp == 1) {
     // ===================== MMA issuer: the warp stays converged, one elected lane drives the tensor core ==========
-    constexpr uint32_t idesc = make_idesc_f16(128, COUT);
-    constexpr uint32_t idesc_cat = make_idesc_f16(128, C::DCOLS);
-    // A: K-major SWIZZLE_64B (layout type 4): pixel rows of 64 B, 8-row groups (= next image row) at SBO = HX*64 B
-    // B: K-major no swizzle: weight slab [j][plane][COUT][8]: 8 couts x 16 B per core matrix, next j at LBO
-    constexpr uint32_t A_SBO = C::HX * 4;                                       // in 16-byte units
-    constexpr uint32_t B_LBO = C::WPLANES * COUT, B_SBO = 8;
+    // A: K-major SWIZZLE_64B (layout type 4): pixel rows of 64 B, 8-row groups (= NH image rows further) at the SBO
+    // B: K-major no swizzle: weight stage [j][ky descending][WROWS][8]: 8 rows x 16 B per core matrix, next j at LBO
+    constexpr uint32_t A_SBO = NH * C::HX * 4;                                  // in 16-byte units
+    constexpr uint32_t B_LBO = C::B_LBO, B_SBO = 8;
     constexpr uint32_t a_hi32 = A_SBO | (1u << 14) | (4u << 29), b_hi32 = B_SBO | (1u << 14);   // upper descriptor words
+    constexpr uint32_t a8_hi32 = (uint32_t)(NH * C::HX * 2) | (1u << 14) | (6u << 29);           // e4m3 plane: SWIZZLE_32B
     const uint32_t sA_u = ptx::smem_u32(sA) >> 4, sW_u = ptx::smem_u32(sW) >> 4;
     uint32_t ia = 0, iw = 0, it = 0;
     // The elected lane runs the WHOLE persistent loop (barrier waits included): no per-row elect / reconvergence, so the
-    // tensor-pipe queue does not drain between tap rows.
+    // tensor-pipe queue does not drain between tap columns.
     if (ptx::elect_one_sync()) {
     for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x, ++it) {
       const uint32_t as = it & 1;
@@ -398,65 +412,71 @@ __global__ void __launch_bounds__(FUSE ? 640 : 384, 1) conv_tc_kernel(const __gr
         ptx::mbar_wait(&a_full[sa], (ia >> 1) & 1);
         ptx::tc_fence_after();
 #pragma unroll
-        for (int dy = 0; dy < KS; ++dy, ++iw) {
+        for (int dx = 0; dx < KS; ++dx, ++iw) {
           const uint32_t sw = iw % C::NW;
           ptx::mbar_wait(&w_full[sw], (iw / C::NW) & 1);
           ptx::tc_fence_after();
-          {
-            // Issue order: consecutive MMAs go to DIFFERENT accumulators (t inner).  The 64 B swizzle is a pure function
-            // of the shared-memory ADDRESS bits (verified on B200: a non-zero 'matrix base offset' gives wrong results),
-            // so shifted tap windows need no descriptor fix-up.
-            const uint32_t a_row = sA_u + sa * (C::A_STAGE >> 4) + dy * C::HX * 4;
-            const uint32_t b_row = (sW_u + sw * (C::W_STAGE >> 4)) | (B_LBO << 16);
-            const uint32_t a_row8 = sA_u + sa * (C::A_STAGE >> 4) + (C::A_PLANE >> 4) + dy * C::HX * 2;   // e4m3 lo plane
-            const uint32_t b_row8 = sW_u + sw * (C::W_STAGE >> 4) + (C::W16 >> 4);
+          // The 64 B swizzle is a pure function of the shared-memory ADDRESS bits (verified on B200: a non-zero 'matrix
+          // base offset' gives wrong results), so shifted tap windows need no descriptor fix-up.
+          const uint32_t a_col = sA_u + sa * (C::A_STAGE >> 4) + dx * 4;
+          const uint32_t a_col8 = sA_u + sa * (C::A_STAGE >> 4) + (C::A_PLANE >> 4) + dx * 2;   // e4m3 lo plane
+          const uint32_t b_col = sW_u + sw * (C::W_STAGE >> 4);
+          const uint32_t b_col8 = b_col + (C::W16 >> 4);
 #pragma unroll
-            for (int dx = 0; dx < KS; ++dx) {
-              const uint32_t a0 = a_row + dx * 4;
-              const uint32_t b0 = b_row + dx * (C::W_TAP >> 4);
-              const uint32_t acc0 = (c | dy | dx) ? 1u : 0u;
+          for (int si = 0; si < C::NSHIFT; ++si) {
+            // vertical window shift s = ky + h.  The first shift issued covers every stacked row (it initialises the
+            // accumulators), the others follow in ascending order.
+            constexpr int S0 = KS - 1;
+            const int s = si == 0 ? S0 : (si <= S0 ? si - 1 : si);
+            const int h_min = s > KS - 1 ? s - (KS - 1) : 0, h_max = s < NH - 1 ? s : NH - 1, nv = h_max - h_min + 1;
+            const int pos = (KS - 1) - (s - h_min);                 // weight block of ky = s - h_min (descending ky order)
+            const uint32_t a0 = a_col + s * C::HX * 4;
+            const uint32_t dcol = dbase + h_min * C::NF;
+            const uint32_t idesc_n = make_idesc_f16(128, C::NF * nv);
+            const uint32_t acc0 = (c | dx | si) ? 1u : 0u;
 #pragma unroll
-              for (int ks = 0; ks < 2; ++ks) {
-                const uint64_t bdesc = ((uint64_t)b_hi32 << 32) | (b0 + 2 * ks * B_LBO);
-                const uint32_t first = ks ? 1u : acc0;
+            for (int ks = 0; ks < 2; ++ks) {
+              const uint32_t b0 = b_col + 2 * ks * B_LBO + pos * C::WROWS;
+              const uint64_t bdesc = ((uint64_t)b_hi32 << 32) | b0 | (B_LBO << 16);
+              const uint32_t first = ks ? 1u : acc0;
+#pragma unroll
+              for (int t = 0; t < T; ++t) {
+                const uint64_t adesc = ((uint64_t)a_hi32 << 32) | ((a0 + 32 * t + 2 * ks) & 0x3FFFu) | (1u << 16);
+                ptx::mma_f16(dcol + t * C::DCOLS, adesc, bdesc, idesc_n, first);
+              }
+              if (PASSES >= 2 && !LO8) {        // fp16 low-half plane (layer 1, NH = 1)
+#pragma unroll
+                for (int t = 0; t < T; ++t) {
+                  const uint64_t adesc_lo = ((uint64_t)a_hi32 << 32) | ((a0 + 32 * t + 2 * ks + (C::A_PLANE >> 4)) & 0x3FFFu) | (1u << 16);
+                  ptx::mma_f16(dcol + t * C::DCOLS, adesc_lo, bdesc, make_idesc_f16(128, COUT), 1u);
+                }
+              }
+              if (PASSES == 3 && !C::NCAT) {    // a_hi x w_lo as its own MMA (layer 1, NH = 1)
+                const uint64_t bdesc_lo = ((uint64_t)b_hi32 << 32) | (b0 + COUT) | (B_LBO << 16);
 #pragma unroll
                 for (int t = 0; t < T; ++t) {
                   const uint64_t adesc = ((uint64_t)a_hi32 << 32) | ((a0 + 32 * t + 2 * ks) & 0x3FFFu) | (1u << 16);
-                  ptx::mma_f16(dbase + t * C::DCOLS, adesc, bdesc, C::NCAT ? idesc_cat : idesc, first);
-                }
-                if (PASSES >= 2 && !LO8) {
-#pragma unroll
-                  for (int t = 0; t < T; ++t) {
-                    const uint64_t adesc_lo = ((uint64_t)a_hi32 << 32) | ((a0 + 32 * t + 2 * ks + (C::A_PLANE >> 4)) & 0x3FFFu) | (1u << 16);
-                    ptx::mma_f16(dbase + t * C::DCOLS, adesc_lo, bdesc, idesc, 1u);
-                  }
-                }
-                if (PASSES == 3 && !C::NCAT) {
-                  const uint64_t bdesc_lo = ((uint64_t)b_hi32 << 32) | (b0 + 2 * ks * B_LBO + COUT);
-#pragma unroll
-                  for (int t = 0; t < T; ++t) {
-                    const uint64_t adesc = ((uint64_t)a_hi32 << 32) | ((a0 + 32 * t + 2 * ks) & 0x3FFFu) | (1u << 16);
-                    ptx::mma_f16(dbase + t * C::DCOLS, adesc, bdesc_lo, idesc, 1u);
-                  }
-                }
-              }
-              if (LO8) {
-                // a_lo (e4m3, SWIZZLE_32B rows of 32 channels) x w (e4m3, [2][COUT][16 B]): one K=32 MMA per M-tile
-                constexpr uint32_t a8_hi32 = (uint32_t)(C::HX * 2) | (1u << 14) | (6u << 29);
-                const uint32_t a8 = a_row8 + dx * 2;
-                const uint64_t bdesc8 = ((uint64_t)b_hi32 << 32) | ((b_row8 + dx * (C::W_TAP >> 4)) | ((uint32_t)COUT << 16));
-#pragma unroll
-                for (int t = 0; t < T; ++t) {
-                  const uint64_t adesc8 = ((uint64_t)a8_hi32 << 32) | ((a8 + 16 * t) & 0x3FFFu) | (1u << 16);
-                  ptx::mma_f8(dbase + t * C::DCOLS, adesc8, bdesc8, idesc, 1u);
+                  ptx::mma_f16(dcol + t * C::DCOLS, adesc, bdesc_lo, make_idesc_f16(128, COUT), 1u);
                 }
               }
             }
-            ptx::tc_commit(&w_empty[sw]);                                   // weight row free once these MMAs have read it
-            if (dy == KS - 1) {
-              ptx::tc_commit(&a_empty[sa]);                                 // activation chunk free
-              if (c == C::NCHUNK - 1) ptx::tc_commit(&acc_full[as]);        // tile complete -> epilogue
+            if (LO8) {
+              // a_lo (e4m3, SWIZZLE_32B rows of 32 channels) x w (e4m3, [2][ky][NF][16 B]): one K=32 MMA per M-tile.  With
+              // N-concatenated weights the e4m3 rows of the w_lo half are zero (stacked rows must stay NF columns apart).
+              const uint32_t a8 = a_col8 + s * C::HX * 2;
+              const uint32_t n8 = (NH > 1 || !C::NCAT) ? C::NF * nv : COUT;
+              const uint64_t bdesc8 = ((uint64_t)b_hi32 << 32) | (b_col8 + pos * C::NF) | ((uint32_t)C::B8_LBO << 16);
+#pragma unroll
+              for (int t = 0; t < T; ++t) {
+                const uint64_t adesc8 = ((uint64_t)a8_hi32 << 32) | ((a8 + 16 * t) & 0x3FFFu) | (1u << 16);
+                ptx::mma_f8(dcol + t * C::DCOLS, adesc8, bdesc8, make_idesc_f16(128, n8), 1u);
+              }
             }
+          }
+          ptx::tc_commit(&w_empty[sw]);                                   // weight column free once these MMAs have read it
+          if (dx == KS - 1) {
+            ptx::tc_commit(&a_empty[sa]);                                 // activation chunk free
+            if (c == C::NCHUNK - 1) ptx::tc_commit(&acc_full[as]);        // tile complete -> epilogue
           }
         }
       }
@@ -467,22 +487,21 @@ __global__ void __launch_bounds__(FUSE ? 640 : 384, 1) conv_tc_kernel(const __gr
     // ===================== epilogue: TMEM -> registers -> bias/ReLU/BN -> fp16 hi/lo (or fp32) -> HBM ==============
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
     const int half = (warp - 4) >> 2;             // two warps share a lane quarter and split the (t, 16-column) items
-    const int m = q * 32 + lane;                  // accumulator row = pixel inside the 16 x 8 M-tile
-    const int prow = m >> 3, pcol = m & 7;
+    const int m = q * 32 + lane;                  // accumulator row = pixel of the M-tile: 16 row groups x 8 columns
+    const int prow = m >> 3, pcol = m & 7;        // (row group g covers image rows g*NH .. g*NH + NH-1, one per column block)
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x, ++it) {
       const int img = tile / tiles_per_img, r = tile - img * tiles_per_img;
-      const int y0 = (r / P.tiles_x) * 16, x0 = (r % P.tiles_x) * 8 * T;
+      const int y0 = (r / P.tiles_x) * 16 * NH, x0 = (r % P.tiles_x) * 8 * T;
       const uint32_t as = it & 1;
       ptx::mbar_wait(&acc_full[as], (it >> 1) & 1);
       ptx::tc_fence_after();
-      const int y = y0 + prow;
-      constexpr int NB16 = COUT / 16, ITEMS = T * NB16;
+      constexpr int NB16 = COUT / 16, ITEMS = T * NH * NB16;
 #pragma unroll 1
       for (int item = half; item < ITEMS; item += 2) {
-        const int t = item / NB16, n0 = (item - t * NB16) * 16;
-        const int x = x0 + 8 * t + pcol;
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * (T * C::DCOLS) + t * C::DCOLS;
+        const int t = item / (NH * NB16), hn = item - t * (NH * NB16), hrow = hn / NB16, n0 = (hn - hrow * NB16) * 16;
+        const int x = x0 + 8 * t + pcol, y = y0 + prow * NH + hrow;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * (T * C::DCOLS) + t * C::DCOLS + hrow * C::NF;
         {
           uint32_t rr[16];
           ptx::tmem_ld16(taddr + n0, rr);
@@ -609,12 +628,17 @@ inline void tc_free_workspace(TcWorkspace& w) {
 }
 inline int tc_launches_per_forward(const TcNet& n) { return n.ready ? (int)n.layers.size() : 0; }
 
-// Pack one layer: weights -> [chunk][tap][4][plane][cout_p][8] fp16 (hi [, lo]) scaled by 2^k, epilogue vectors padded.
+// Pack one layer.  Weight stage = one (32-channel chunk, tap COLUMN kx): fp16 [4 j][ky descending][WROWS][8] (values scaled
+// by 2^k; WROWS = [w_hi | w_lo] x cout_p for the N-concatenated layers, [plane][cout_p] otherwise) followed (lo8) by
+// e4m3 [2 kc][ky descending][NF][16] = w * 2^k * 2^-11 (rows of the w_lo half stay zero).  Descending ky makes the
+// weights of the row-stacked MMA (taps ky = s - h, h ascending) one contiguous B operand.  Epilogue vectors are padded.
 inline bool tc_pack_layer(TcLayer& L, int cin_p, int cout_p, int ks, int passes, bool lo8, int real_cin, int real_cout,
                           const std::vector<float>& wdense /* [real_cout][real_cin][ks*ks] */, const float* bias,
                           const float* bn_s, const float* bn_t, int relu_bn) {
   L.cin = cin_p; L.cout = cout_p; L.ks = ks; L.relu_bn = relu_bn; L.real_cout = real_cout; L.passes = passes;
   const int taps = ks * ks, planes = passes == 3 ? 2 : 1, nchunk = cin_p / 32;
+  const bool ncat = passes == 3 && cout_p <= 32;
+  const int nf = ncat ? 2 * cout_p : cout_p, wrows = ncat ? nf : planes * cout_p;
   float maxabs = 0.f;
   for (float v : wdense) maxabs = std::fmax(maxabs, std::fabs(v));
   int k = 0;
@@ -625,26 +649,28 @@ inline bool tc_pack_layer(TcLayer& L, int cin_p, int cout_p, int ks, int passes,
   }
   const float scale = std::ldexp(1.0f, k);
   L.inv_wscale = std::ldexp(1.0f, -k);
-  // slab per (chunk, tap): fp16 [4 j][planes][cout_p][8]  followed (lo8) by e4m3 [2 kc][cout_p][16] = w * scale * 2^-11
-  const size_t w16 = (size_t)planes * 4 * cout_p * 16, w8 = lo8 ? (size_t)2 * cout_p * 16 : 0, slab = w16 + w8;
-  std::vector<unsigned char> pk((size_t)nchunk * taps * slab, 0);
+  const size_t w16 = (size_t)4 * ks * wrows * 16, w8 = lo8 ? (size_t)2 * ks * nf * 16 : 0, slab = w16 + w8;
+  std::vector<unsigned char> pk((size_t)nchunk * ks * slab, 0);
   for (int c = 0; c < nchunk; ++c)
-    for (int tap = 0; tap < taps; ++tap) {
-      unsigned char* base = pk.data() + (size_t)(c * taps + tap) * slab;
+    for (int kx = 0; kx < ks; ++kx) {
+      unsigned char* base = pk.data() + (size_t)(c * ks + kx) * slab;
       __half* b16 = reinterpret_cast<__half*>(base);
       unsigned char* b8 = base + w16;
-      for (int j = 0; j < 4; ++j)
-        for (int co = 0; co < cout_p; ++co)
-          for (int e = 0; e < 8; ++e) {
-            const int ci = c * 32 + j * 8 + e;
-            float v = 0.f;
-            if (ci < real_cin && co < real_cout) v = wdense[((size_t)co * real_cin + ci) * taps + tap] * scale;
-            const __half h = __float2half_rn(v);
-            b16[((size_t)(j * planes + 0) * cout_p + co) * 8 + e] = h;
-            if (planes == 2) b16[((size_t)(j * planes + 1) * cout_p + co) * 8 + e] = __float2half_rn(v - __half2float(h));
-            if (lo8) b8[((size_t)(ci % 32 / 16) * cout_p + co) * 16 + (ci % 16)] =
-                (unsigned char)__nv_cvt_float_to_fp8(v * (1.0f / 2048.0f), __NV_SATFINITE, __NV_E4M3);
-          }
+      for (int ky = 0; ky < ks; ++ky) {
+        const int pos = ks - 1 - ky, tap = ky * ks + kx;
+        for (int j = 0; j < 4; ++j)
+          for (int co = 0; co < cout_p; ++co)
+            for (int e = 0; e < 8; ++e) {
+              const int ci = c * 32 + j * 8 + e;
+              float v = 0.f;
+              if (ci < real_cin && co < real_cout) v = wdense[((size_t)co * real_cin + ci) * taps + tap] * scale;
+              const __half h = __float2half_rn(v);
+              b16[(((size_t)j * ks + pos) * wrows + co) * 8 + e] = h;
+              if (planes == 2) b16[(((size_t)j * ks + pos) * wrows + cout_p + co) * 8 + e] = __float2half_rn(v - __half2float(h));
+              if (lo8) b8[(((size_t)(ci % 32 / 16) * ks + pos) * nf + co) * 16 + (ci % 16)] =
+                  (unsigned char)__nv_cvt_float_to_fp8(v * (1.0f / 2048.0f), __NV_SATFINITE, __NV_E4M3);
+            }
+      }
     }
   std::vector<float> b(cout_p, 0.f), s(cout_p, 1.f), t(cout_p, 0.f);
   for (int i = 0; i < real_cout; ++i) {
@@ -734,10 +760,10 @@ inline bool tc_make_map8(CUtensorMap* m, const void* base, int WP, int HP, long 
              CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int CIN, int COUT, int KS, int PASSES, int T, int OUTMODE, int FUSE = 0>
+template <int CIN, int COUT, int KS, int PASSES, int T, int OUTMODE, int FUSE = 0, int NH = 1>
 inline cudaError_t tc_launch(const TcConvParams& P, int nimg, int nsm, cudaStream_t st) {
   constexpr bool LO8 = !FUSE && PASSES >= 2;
-  using C = TcCfg<CIN, COUT, KS, PASSES, T, LO8>;
+  using C = TcCfg<CIN, COUT, KS, PASSES, T, LO8, NH>;
   TcMaps M;
   if (FUSE) {
     std::memset(&M, 0, sizeof(M));
@@ -748,7 +774,7 @@ inline cudaError_t tc_launch(const TcConvParams& P, int nimg, int nsm, cudaStrea
   } else {
     M.lo = M.hi;
   }
-  auto kern = conv_tc_kernel<CIN, COUT, KS, PASSES, T, OUTMODE, FUSE>;
+  auto kern = conv_tc_kernel<CIN, COUT, KS, PASSES, T, OUTMODE, FUSE, NH>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM + (FUSE ? 6400 : 0));
@@ -760,10 +786,27 @@ inline cudaError_t tc_launch(const TcConvParams& P, int nimg, int nsm, cudaStrea
   return cudaGetLastError();
 }
 
+// Tile shape of a layer: NH stacked rows (tile height 16*NH) x T M-tiles of 8 columns.  TMEM holds 2 x T x NH x NF columns.
+struct TcTile { int nh, t; };
+template <int COUT, int PASSES>
+inline TcTile tc_pick_tile(int ny, int nx) {
+  constexpr int NF = (PASSES == 3 && COUT <= 32) ? 2 * COUT : COUT;
+  static int force_nh = -1;
+  if (force_nh < 0) { const char* e = getenv("QGB_TC_NH"); force_nh = e ? atoi(e) : 0; }
+  if (force_nh != 1) {
+    if (ny % 32 == 0 && nx % 16 == 0 && 2 * 2 * 2 * NF <= 512) return {2, 2};
+    if (NF == 64 && PASSES != 3 && ny % 48 == 0) return {3, 1};
+  }
+  return {1, nx % 32 == 0 ? 4 : (nx % 24 == 0 ? 3 : 2)};
+}
 template <int CIN, int COUT, int KS, int PASSES, int OUTMODE>
-inline cudaError_t tc_launch_T(int T, const TcConvParams& P, int nimg, int nsm, cudaStream_t st) {
-  if (T == 4) return tc_launch<CIN, COUT, KS, PASSES, 4, OUTMODE>(P, nimg, nsm, st);
-  if (T == 3) return tc_launch<CIN, COUT, KS, PASSES, 3, OUTMODE>(P, nimg, nsm, st);
+inline cudaError_t tc_launch_T(TcTile tl, const TcConvParams& P, int nimg, int nsm, cudaStream_t st) {
+  if (tl.nh == 2) return tc_launch<CIN, COUT, KS, PASSES, 2, OUTMODE, 0, 2>(P, nimg, nsm, st);
+  if constexpr (COUT == 64 && PASSES != 3) {
+    if (tl.nh == 3) return tc_launch<CIN, COUT, KS, PASSES, 1, OUTMODE, 0, 3>(P, nimg, nsm, st);
+  }
+  if (tl.t == 4) return tc_launch<CIN, COUT, KS, PASSES, 4, OUTMODE>(P, nimg, nsm, st);
+  if (tl.t == 3) return tc_launch<CIN, COUT, KS, PASSES, 3, OUTMODE>(P, nimg, nsm, st);
   return tc_launch<CIN, COUT, KS, PASSES, 2, OUTMODE>(P, nimg, nsm, st);
 }
 
@@ -772,7 +815,6 @@ inline int tc_forward(const TcNet& net, TcWorkspace& ws, const float* x, long lo
                       bool fast_l2 = false) {
   if (!net.ready) { *err = "tcgen05 path: network not packed"; return QGB_EUNSUPPORTED; }
   if (ny % 16 || nx % 16) { *err = "tcgen05 path needs ny and nx to be multiples of 16 (use precision='fp32')"; return QGB_EUNSUPPORTED; }
-  const int T = nx % 32 == 0 ? 4 : (nx % 24 == 0 ? 3 : 2);
   // Images per launch: large launches amortise the persistent-CTA ramp/tail (measured on B200, 64^2: 128 -> 150 k,
   // 1024 -> 162 k member-steps/s); the workspace is capped at ~6 GB.
   static int max_chunk = 0;
@@ -799,12 +841,16 @@ inline int tc_forward(const TcNet& net, TcWorkspace& ws, const float* x, long lo
       const TcLayer& L = (li == 1 && fast_l2) ? net.l2_fast : net.layers[li];
       TcConvParams P;
       P.w = L.w; P.bias = L.bias; P.bn_s = L.bn_s; P.bn_t = L.bn_t; P.inv_wscale = L.inv_wscale; P.relu_bn = L.relu_bn;
-      P.ny = ny; P.nx = nx; P.tiles_y = ny / 16;
+      P.ny = ny; P.nx = nx;
       P.out_f32 = nullptr; P.out_bs = 0; P.out_c = 0; P.softplus = 0; P.accumulate = 0;
       P.x_f32 = x + (long long)b0 * x_bs; P.x_bs = x_bs;
       P.out_hi = P.out_lo = nullptr; P.out_pad = 0; P.out_nch = 0;
-      const int Tl = li == 0 ? 2 : T;
-      P.tiles_x = nx / (8 * Tl);
+      TcTile tl = {1, 2};                                        // layer 1 (fused im2col): 16 x 16 tiles
+      if (li == 1) tl = fast_l2 ? tc_pick_tile<64, 1>(ny, nx) : tc_pick_tile<64, 2>(ny, nx);
+      else if (li >= 2 && li < 7) tl = tc_pick_tile<32, 3>(ny, nx);
+      else if (li == 7) tl = tc_pick_tile<16, 3>(ny, nx);
+      P.tiles_y = ny / (16 * tl.nh);
+      P.tiles_x = nx / (8 * tl.t);
       P.num_tiles = nb * P.tiles_y * P.tiles_x;
       const int pad = L.ks / 2;
       P.nch_in = L.cin / 32; P.HP = ny + 2 * pad; P.WP = nx + 2 * pad;
@@ -826,10 +872,10 @@ inline int tc_forward(const TcNet& net, TcWorkspace& ws, const float* x, long lo
       if (li == 0) {
         if (fast_l2) e = net.kp == 128 ? tc_launch<128, 128, 1, 3, 2, TC_OUT_HI, 4>(P, nb, nsm, st) : tc_launch<64, 128, 1, 3, 2, TC_OUT_HI, 2>(P, nb, nsm, st);
         else e = net.kp == 128 ? tc_launch<128, 128, 1, 3, 2, TC_OUT_HILO, 4>(P, nb, nsm, st) : tc_launch<64, 128, 1, 3, 2, TC_OUT_HILO, 2>(P, nb, nsm, st);
-      } else if (li == 1) e = fast_l2 ? tc_launch_T<128, 64, 5, 1, TC_OUT_HILO>(T, P, nb, nsm, st) : tc_launch_T<128, 64, 5, 2, TC_OUT_HILO>(T, P, nb, nsm, st);
-      else if (li == 2) e = tc_launch_T<64, 32, 3, 3, TC_OUT_HILO>(T, P, nb, nsm, st);
-      else if (li < 7) e = tc_launch_T<32, 32, 3, 3, TC_OUT_HILO>(T, P, nb, nsm, st);
-      else e = tc_launch_T<32, 16, 3, 3, TC_OUT_FINAL>(T, P, nb, nsm, st);
+      } else if (li == 1) e = fast_l2 ? tc_launch_T<128, 64, 5, 1, TC_OUT_HILO>(tl, P, nb, nsm, st) : tc_launch_T<128, 64, 5, 2, TC_OUT_HILO>(tl, P, nb, nsm, st);
+      else if (li == 2) e = tc_launch_T<64, 32, 3, 3, TC_OUT_HILO>(tl, P, nb, nsm, st);
+      else if (li < 7) e = tc_launch_T<32, 32, 3, 3, TC_OUT_HILO>(tl, P, nb, nsm, st);
+      else e = tc_launch_T<32, 16, 3, 3, TC_OUT_FINAL>(tl, P, nb, nsm, st);
       if (prof) { cudaEventRecord(ev1, st); ws.prof_events->emplace_back(ev0, ev1); *ws.prof_images += nb; }
       ws.last_launches += 1;
       if (e != cudaSuccess) { *err = std::string("tcgen05 conv launch failed: ") + cudaGetErrorString(e); return QGB_ECUDA; }
