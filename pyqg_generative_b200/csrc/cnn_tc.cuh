@@ -146,6 +146,12 @@ __device__ __forceinline__ uint32_t elect_one_sync() {
       : "+r"(pred));
   return pred;
 }
+// 256-bit global store (SASS: STG.E.ENL2.256): one whole 32-byte sector per lane
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t* r) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
+               "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 }  // namespace ptx
 
@@ -496,92 +502,98 @@ __global__ void __launch_bounds__(FUSE ? 640 : 384, 1) conv_tc_kernel(const __gr
       const uint32_t as = it & 1;
       ptx::mbar_wait(&acc_full[as], (it >> 1) & 1);
       ptx::tc_fence_after();
-      constexpr int NB16 = COUT / 16, ITEMS = T * NH * NB16;
+      // An item is CW channels of one pixel: 32 where the output is an activation plane, so that every global store is a
+      // whole 32-byte sector (hi: 64 B = two 256-bit stores, e4m3 lo: 32 B = one).  With 16-byte stores of half sectors the
+      // epilogue alone ran at 2.7 TB/s and was the critical path of every layer but the second (profiles/r1_history.md).
+      constexpr int CW = (COUT >= 32 && OUTMODE != TC_OUT_FINAL) ? 32 : 16;
+      constexpr int NBW = COUT / CW, ITEMS = T * NH * NBW;
 #pragma unroll 1
       for (int item = half; item < ITEMS; item += 2) {
-        const int t = item / (NH * NB16), hn = item - t * (NH * NB16), hrow = hn / NB16, n0 = (hn - hrow * NB16) * 16;
+        const int t = item / (NH * NBW), hn = item - t * (NH * NBW), hrow = hn / NBW, n0 = (hn - hrow * NBW) * CW;
         const int x = x0 + 8 * t + pcol, y = y0 + prow * NH + hrow;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * (T * C::DCOLS) + t * C::DCOLS + hrow * C::NF;
-        {
-          uint32_t rr[16];
-          ptx::tmem_ld16(taddr + n0, rr);
-          if (C::NCAT) {
-            uint32_t r2[16];
-            ptx::tmem_ld16(taddr + COUT + n0, r2);
-            ptx::tmem_ld_wait();
+        uint32_t rr[CW];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) rr[i] = __float_as_uint(__uint_as_float(rr[i]) + __uint_as_float(r2[i]));
-          }
+        for (int l = 0; l < CW / 16; ++l) ptx::tmem_ld16(taddr + n0 + 16 * l, reinterpret_cast<uint32_t(&)[16]>(rr[16 * l]));
+        if (C::NCAT) {
+          uint32_t r2[CW];
+#pragma unroll
+          for (int l = 0; l < CW / 16; ++l) ptx::tmem_ld16(taddr + COUT + n0 + 16 * l, reinterpret_cast<uint32_t(&)[16]>(r2[16 * l]));
           ptx::tmem_ld_wait();
-          if (item + 2 >= ITEMS) {                 // last read of this accumulator set by this thread: hand it back
-            ptx::tc_fence_before();
-            ptx::mbar_arrive(&acc_empty[as]);
-          }
-          float v[16];
-          {   // per-channel epilogue constants: 16-byte shared-memory loads (shared-memory bandwidth is what bounds the MMAs)
-            const float4* eb = reinterpret_cast<const float4*>(sEpi + n0);
-            const float4* es = reinterpret_cast<const float4*>(sEpi + COUT + n0);
-            const float4* et = reinterpret_cast<const float4*>(sEpi + 2 * COUT + n0);
 #pragma unroll
-            for (int i4 = 0; i4 < 4; ++i4) {
-              const float4 b = eb[i4];
-              float a0 = __uint_as_float(rr[4 * i4 + 0]) * P.inv_wscale + b.x;
-              float a1 = __uint_as_float(rr[4 * i4 + 1]) * P.inv_wscale + b.y;
-              float a2 = __uint_as_float(rr[4 * i4 + 2]) * P.inv_wscale + b.z;
-              float a3 = __uint_as_float(rr[4 * i4 + 3]) * P.inv_wscale + b.w;
-              if (P.relu_bn) {
-                const float4 sc = es[i4], sh = et[i4];
-                a0 = fmaxf(a0, 0.f) * sc.x + sh.x;
-                a1 = fmaxf(a1, 0.f) * sc.y + sh.y;
-                a2 = fmaxf(a2, 0.f) * sc.z + sh.z;
-                a3 = fmaxf(a3, 0.f) * sc.w + sh.w;
-              }
-              v[4 * i4 + 0] = a0; v[4 * i4 + 1] = a1; v[4 * i4 + 2] = a2; v[4 * i4 + 3] = a3;
+          for (int i = 0; i < CW; ++i) rr[i] = __float_as_uint(__uint_as_float(rr[i]) + __uint_as_float(r2[i]));
+        }
+        ptx::tmem_ld_wait();
+        if (item + 2 >= ITEMS) {                 // last read of this accumulator set by this thread: hand it back
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(&acc_empty[as]);
+        }
+        float v[CW];
+        {   // per-channel epilogue constants: 16-byte shared-memory loads (shared-memory bandwidth is what bounds the MMAs)
+          const float4* eb = reinterpret_cast<const float4*>(sEpi + n0);
+          const float4* es = reinterpret_cast<const float4*>(sEpi + COUT + n0);
+          const float4* et = reinterpret_cast<const float4*>(sEpi + 2 * COUT + n0);
+#pragma unroll
+          for (int i4 = 0; i4 < CW / 4; ++i4) {
+            const float4 b = eb[i4];
+            float a0 = __uint_as_float(rr[4 * i4 + 0]) * P.inv_wscale + b.x;
+            float a1 = __uint_as_float(rr[4 * i4 + 1]) * P.inv_wscale + b.y;
+            float a2 = __uint_as_float(rr[4 * i4 + 2]) * P.inv_wscale + b.z;
+            float a3 = __uint_as_float(rr[4 * i4 + 3]) * P.inv_wscale + b.w;
+            if (P.relu_bn) {
+              const float4 sc = es[i4], sh = et[i4];
+              a0 = fmaxf(a0, 0.f) * sc.x + sh.x;
+              a1 = fmaxf(a1, 0.f) * sc.y + sh.y;
+              a2 = fmaxf(a2, 0.f) * sc.z + sh.z;
+              a3 = fmaxf(a3, 0.f) * sc.w + sh.w;
+            }
+            v[4 * i4 + 0] = a0; v[4 * i4 + 1] = a1; v[4 * i4 + 2] = a2; v[4 * i4 + 3] = a3;
+          }
+        }
+        if (OUTMODE == TC_OUT_FINAL) {
+          for (int i = 0; i < CW; ++i) {
+            const int n = n0 + i;
+            if (n < P.out_c) {
+              float a = v[i];
+              if (P.softplus) a = softplus_f(a);
+              float* o = P.out_f32 + (long long)img * P.out_bs + ((long long)n * P.ny + y) * P.nx + x;
+              *o = P.accumulate ? *o + a : a;
             }
           }
-          if (OUTMODE == TC_OUT_FINAL) {
-            for (int i = 0; i < 16; ++i) {
-              const int n = n0 + i;
-              if (n < P.out_c) {
-                float a = v[i];
-                if (P.softplus) a = softplus_f(a);
-                float* o = P.out_f32 + (long long)img * P.out_bs + ((long long)n * P.ny + y) * P.nx + x;
-                *o = P.accumulate ? *o + a : a;
-              }
-            }
-          } else {
-            const int op = P.out_pad, HPo = P.ny + 2 * op, WPo = P.nx + 2 * op;
-            // circular halo: rows / columns within ``op`` of a border are also written to the wrapped positions
-            int ys[2], xs[2], nys = 1, nxs = 1;
-            ys[0] = y + op; xs[0] = x + op;
-            if (y < op) ys[nys++] = y + op + P.ny; else if (y >= P.ny - op) ys[nys++] = y + op - P.ny;
-            if (x < op) xs[nxs++] = x + op + P.nx; else if (x >= P.nx - op) xs[nxs++] = x + op - P.nx;
-            uint32_t hi[8], lo8[4];
+        } else {
+          const int op = P.out_pad, HPo = P.ny + 2 * op, WPo = P.nx + 2 * op;
+          // circular halo: rows / columns within ``op`` of a border are also written to the wrapped positions
+          int ys[2], xs[2], nys = 1, nxs = 1;
+          ys[0] = y + op; xs[0] = x + op;
+          if (y < op) ys[nys++] = y + op + P.ny; else if (y >= P.ny - op) ys[nys++] = y + op - P.ny;
+          if (x < op) xs[nxs++] = x + op + P.nx; else if (x >= P.nx - op) xs[nxs++] = x + op - P.nx;
+          uint32_t hi[CW / 2], lo8[CW / 4];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const float f0 = v[2 * e], f1 = v[2 * e + 1];
-              const __half2 h2 = __floats2half2_rn(f0, f1);
-              hi[e] = *reinterpret_cast<const uint32_t*>(&h2);
+          for (int e = 0; e < CW / 2; ++e) {
+            const float f0 = v[2 * e], f1 = v[2 * e + 1];
+            const __half2 h2 = __floats2half2_rn(f0, f1);
+            hi[e] = *reinterpret_cast<const uint32_t*>(&h2);
+            if (OUTMODE == TC_OUT_HILO) {
+              // low half as e4m3 of (f - hi) * 2^11 (the consumer's e4m3 weights carry the 2^-11)
+              const float2 back = __half22float2(h2);
+              const unsigned short p = __nv_cvt_float2_to_fp8x2(make_float2((f0 - back.x) * 2048.f, (f1 - back.y) * 2048.f),
+                                                                __NV_SATFINITE, __NV_E4M3);
+              if (e & 1) lo8[e >> 1] |= (uint32_t)p << 16; else lo8[e >> 1] = p;
+            }
+          }
+          const int chunk = n0 >> 5, within = n0 & 31;
+          for (int a = 0; a < nys; ++a)
+            for (int b = 0; b < nxs; ++b) {
+              const long long pix = (((long long)img * P.out_nch + chunk) * HPo + ys[a]) * WPo + xs[b];
+              __half* dh = P.out_hi + pix * 32 + within;
+#pragma unroll
+              for (int l = 0; l < CW / 16; ++l) ptx::st_global_v8(dh + 16 * l, &hi[8 * l]);
               if (OUTMODE == TC_OUT_HILO) {
-                // low half as e4m3 of (f - hi) * 2^11 (the consumer's e4m3 weights carry the 2^-11)
-                const float2 back = __half22float2(h2);
-                const unsigned short p = __nv_cvt_float2_to_fp8x2(make_float2((f0 - back.x) * 2048.f, (f1 - back.y) * 2048.f),
-                                                                  __NV_SATFINITE, __NV_E4M3);
-                if (e & 1) lo8[e >> 1] |= (uint32_t)p << 16; else lo8[e >> 1] = p;
+                unsigned char* dl = reinterpret_cast<unsigned char*>(P.out_lo) + pix * 32 + within;
+                if (CW == 32) ptx::st_global_v8(dl, lo8);
+                else *reinterpret_cast<uint4*>(dl) = make_uint4(lo8[0], lo8[1], lo8[2], lo8[3]);
               }
             }
-            const int chunk = n0 >> 5, within = n0 & 31;
-            for (int a = 0; a < nys; ++a)
-              for (int b = 0; b < nxs; ++b) {
-                const long long pix = (((long long)img * P.out_nch + chunk) * HPo + ys[a]) * WPo + xs[b];
-                uint4* dh = reinterpret_cast<uint4*>(P.out_hi + pix * 32 + within);
-                dh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                dh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-                if (OUTMODE == TC_OUT_HILO)
-                  *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(P.out_lo) + pix * 32 + within) =
-                      make_uint4(lo8[0], lo8[1], lo8[2], lo8[3]);
-              }
-          }
         }
       }
     }
