@@ -174,8 +174,7 @@ struct TcConvParams {
   const __half* in_hi; const __half* in_lo;  // [img][nch_in][HP][WP][32]
   int nch_in, HP, WP;
   const __half* w;                           // [chunk][tap column] weight stages, see tc_pack_layer
-  const float* bias; const float* bn_s; const float* bn_t;
-  float inv_wscale; int relu_bn;
+  float inv_wscale; int relu;
   __half* out_hi; __half* out_lo; int out_pad, out_nch;   // [img][out_nch][ny+2*out_pad][nx+2*out_pad][32]
   float* out_f32; long long out_bs; int out_c, softplus, accumulate;
   const float* x_f32; long long x_bs;          // fused layer-1 variant: raw network input (B, cin0, ny, nx) fp32
@@ -218,10 +217,19 @@ struct TcCfg {
   static constexpr int W16 = 4 * KS * WROWS * 16;              // fp16 part of one (chunk, tap column) weight stage
   static constexpr int W_STAGE = W16 + (LO8 ? 2 * KS * NF * 16 : 0);   // + e4m3 part [2][KS][NF][16 B]
   static constexpr int NW = QGB_TC_NW_OVERRIDE ? QGB_TC_NW_OVERRIDE : ((KS == 5) ? (PASSES == 2 ? 2 : 3) : 4);
+  // thin layers: every weight stage of the layer fits the ring -> loaded once per CTA and kept (re-fetching them per tile
+  // doubled the L2 -> SM traffic of the 32 -> 32 layers: 453 MB of weights against 481 MB of activations per launch)
+  static constexpr bool W_RESIDENT = NCHUNK * KS <= NW;
   static constexpr int DCOLS = NH * NF;                        // TMEM columns per M-tile
-  static constexpr int NCOLS_USED = 2 * T * DCOLS;
+  static constexpr int NACC = (4 * T * DCOLS <= 512) ? 4 : 2;    // accumulator ring: MMA of tile i+NACC waits for epilogue i
+  static constexpr int NCOLS_USED = NACC * T * DCOLS;
   static constexpr int NCOLS = NCOLS_USED <= 32 ? 32 : NCOLS_USED <= 64 ? 64 : NCOLS_USED <= 128 ? 128 : NCOLS_USED <= 256 ? 256 : 512;
-  static constexpr int SMEM = 2 * A_STAGE + NW * W_STAGE + 3 * COUT * 4 + 256 + 1024;   // + 6400 for the FUSE window
+  // activation ring: as deep as shared memory allows (2..4 stages).  Thin layers (one 32-channel chunk per tile) spend
+  // less time on a stage than a TMA round trip to HBM takes, so they need more than one load in flight.
+  static constexpr int SMEM_FIXED = NW * W_STAGE + 1536 + 256 + 1024 + 6400;
+  static constexpr int NA_FIT = (232448 - SMEM_FIXED) / A_STAGE;
+  static constexpr int NA = NA_FIT >= 4 ? 4 : (NA_FIT >= 3 ? 3 : 2);
+  static constexpr int SMEM = NA * A_STAGE + NW * W_STAGE + 1536 + 256 + 1024;   // + 6400 for the FUSE window
   static_assert(NCOLS_USED <= 512, "accumulators exceed TMEM");
   static_assert(CIN % 32 == 0 && COUT % 16 == 0, "bad channel counts");
   static_assert(NH == 1 || NH <= KS, "the first MMA of a tile must cover every stacked row");
@@ -237,41 +245,51 @@ __device__ __forceinline__ float softplus_f(float v) { return v > 20.f ? v : log
 struct TcMaps {
   CUtensorMap hi, lo;
 };
+// Epilogue: y = relu(acc / wscale + b) * s + t  (eval-mode BatchNorm after the ReLU).  The constants travel as a kernel
+// parameter.  Layers with COUT <= 32 keep them in REGISTERS for the whole persistent loop, with the BN scale folded on the
+// host into the layer's own weights and bias (relu(z) s = sign(s) relu(|s| z); the sign goes into the next layer's weights)
+// so that two constants per channel remain.  A first version read bias / scale / shift from shared memory everywhere: 24
+// LDS.128 per 32 channels took 25 % of the shared-memory data pipe that the MMAs' operand reads saturate in the thin
+// layers (ncu l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld, profiles/r1_history.md).  The wide layers (1 and 2) spend
+// 10-40x more MMA time per epilogue item and keep the three constants in shared memory, unfolded.  The SHIFT is never
+// folded forward: storing relu(|s| z) without it costs up to 16x in absolute precision where the ReLU output has a large
+// mean (measured 1.2e-3 on the shipped VAE decoder instead of 4e-4).
+struct TcEpi {
+  float b[128], s[128], t[128];
+};
 
 // FUSE = 0: activations arrive by TMA.  FUSE = cin0 (4 or 2): layer 1 -- four extra warps BUILD the 5x5 im2col operand
 // (K = 25*cin0 padded to CIN, fp16 hi/lo planes, SWIZZLE_64B layout) straight into the shared-memory stages from the raw
 // fp32 network input, so the im2col tensor never exists in HBM.
 template <int CIN, int COUT, int KS, int PASSES, int T, int OUTMODE, int FUSE = 0, int NH = 1>
 __global__ void __launch_bounds__(FUSE ? 640 : 384, 1) conv_tc_kernel(const __grid_constant__ TcConvParams P,
-                                                                      const __grid_constant__ TcMaps M) {
+                                                                      const __grid_constant__ TcMaps M,
+                                                                      const __grid_constant__ TcEpi E) {
   static_assert(FUSE == 0 || (KS == 1 && T == 2 && PASSES == 3 && NH == 1), "fused im2col is the layer-1 configuration");
   constexpr bool LO8 = !FUSE && PASSES >= 2;
   using C = TcCfg<CIN, COUT, KS, PASSES, T, LO8, NH>;
   extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
   unsigned char* smem = tc_smem_raw + ((1024u - (ptx::smem_u32(tc_smem_raw) & 1023u)) & 1023u);
   unsigned char* sA = smem;
-  unsigned char* sW = smem + 2 * C::A_STAGE;
-  float* sEpi = reinterpret_cast<float*>(sW + C::NW * C::W_STAGE);          // bias | bn_s | bn_t
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(sEpi) + 3 * COUT * 4);
-  uint64_t* a_full = bars;            // [2]
-  uint64_t* a_empty = bars + 2;       // [2]
-  uint64_t* w_full = bars + 4;        // [NW]
-  uint64_t* w_empty = bars + 4 + C::NW;
-  uint64_t* acc_full = bars + 4 + 2 * C::NW;   // [2]
-  uint64_t* acc_empty = acc_full + 2;          // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  unsigned char* sW = smem + C::NA * C::A_STAGE;
+  float* sEpi = reinterpret_cast<float*>(sW + C::NW * C::W_STAGE);          // bias | scale | shift (only read when COUT > 32)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(sEpi) + 1536);
+  uint64_t* a_full = bars;            // [NA]
+  uint64_t* a_empty = bars + C::NA;   // [NA]
+  uint64_t* w_full = bars + 2 * C::NA;        // [NW]
+  uint64_t* w_empty = bars + 2 * C::NA + C::NW;
+  uint64_t* acc_full = bars + 2 * C::NA + 2 * C::NW;   // [NACC]
+  uint64_t* acc_empty = acc_full + C::NACC;    // [NACC]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + C::NACC);
   float* s_x = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + 256);   // FUSE: [cin0][20][20] input window
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < COUT; i += blockDim.x) {
-    sEpi[i] = P.bias[i];
-    sEpi[COUT + i] = P.relu_bn ? P.bn_s[i] : 1.f;
-    sEpi[2 * COUT + i] = P.relu_bn ? P.bn_t[i] : 0.f;
-  }
+  constexpr bool BREG = COUT <= 32;             // epilogue constants in registers
+  if (!BREG) for (int i = threadIdx.x; i < COUT; i += blockDim.x) { sEpi[i] = E.b[i]; sEpi[COUT + i] = E.s[i]; sEpi[2 * COUT + i] = E.t[i]; }
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&a_full[i], FUSE ? 256 : 1); ptx::mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < C::NA; ++i) { ptx::mbar_init(&a_full[i], FUSE ? 256 : 1); ptx::mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < C::NW; ++i) { ptx::mbar_init(&w_full[i], 1); ptx::mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], 256); }
+    for (int i = 0; i < C::NACC; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], 256); }
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc(tmem_slot, C::NCOLS);
@@ -323,7 +341,7 @@ __global__ void __launch_bounds__(FUSE ? 640 : 384, 1) conv_tc_kernel(const __gr
       w1 = fetch(tile + gridDim.x, bt + 256);
 #pragma unroll
       for (int c = 0; c < C::NCHUNK; ++c, ++ia) {
-        const uint32_t s = ia & 1, par = (ia >> 1) & 1;
+        const uint32_t s = ia % C::NA, par = (ia / C::NA) & 1;
         ptx::mbar_wait(&a_empty[s], par ^ 1);
         unsigned char* stage = sA + s * C::A_STAGE;
 #pragma unroll
@@ -371,7 +389,7 @@ __global__ void __launch_bounds__(FUSE ? 640 : 384, 1) conv_tc_kernel(const __gr
       const int img = tile / tiles_per_img, r = tile - img * tiles_per_img;
       const int y0 = (r / P.tiles_x) * 16 * NH, x0 = (r % P.tiles_x) * 8 * T;
       for (int c = 0; c < C::NCHUNK; ++c, ++ia) {
-        const uint32_t s = ia & 1, par = (ia >> 1) & 1;
+        const uint32_t s = ia % C::NA, par = (ia / C::NA) & 1;
         ptx::mbar_wait(&a_empty[s], par ^ 1);
         if (lane == 0) {
           ptx::mbar_arrive_expect_tx(&a_full[s], C::A_TX);
@@ -383,7 +401,12 @@ __global__ void __launch_bounds__(FUSE ? 640 : 384, 1) conv_tc_kernel(const __gr
     }
   } else if (warp == 2) {
     // ===================== W producer: one (chunk, tap column) weight slab per stage ================================
-    if (lane == 0) {
+    if (lane == 0 && C::W_RESIDENT) {
+      for (int cr = 0; cr < C::NCHUNK * KS; ++cr) {
+        ptx::mbar_arrive_expect_tx(&w_full[cr], C::W_STAGE);
+        ptx::bulk_g2s(sW + cr * C::W_STAGE, reinterpret_cast<const unsigned char*>(P.w) + (size_t)cr * C::W_STAGE, C::W_STAGE, &w_full[cr]);
+      }
+    } else if (lane == 0) {
       uint32_t iw = 0;
       for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
         for (int cr = 0; cr < C::NCHUNK * KS; ++cr, ++iw) {
@@ -409,18 +432,18 @@ __global__ void __launch_bounds__(FUSE ? 640 : 384, 1) conv_tc_kernel(const __gr
     // tensor-pipe queue does not drain between tap columns.
     if (ptx::elect_one_sync()) {
     for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x, ++it) {
-      const uint32_t as = it & 1;
-      ptx::mbar_wait(&acc_empty[as], ((it >> 1) & 1) ^ 1);
+      const uint32_t as = it % C::NACC;
+      ptx::mbar_wait(&acc_empty[as], ((it / C::NACC) & 1) ^ 1);
       ptx::tc_fence_after();
       const uint32_t dbase = tmem_base + as * (T * C::DCOLS);
       for (int c = 0; c < C::NCHUNK; ++c, ++ia) {
-        const uint32_t sa = ia & 1;
-        ptx::mbar_wait(&a_full[sa], (ia >> 1) & 1);
+        const uint32_t sa = ia % C::NA;
+        ptx::mbar_wait(&a_full[sa], (ia / C::NA) & 1);
         ptx::tc_fence_after();
 #pragma unroll
         for (int dx = 0; dx < KS; ++dx, ++iw) {
-          const uint32_t sw = iw % C::NW;
-          ptx::mbar_wait(&w_full[sw], (iw / C::NW) & 1);
+          const uint32_t sw = C::W_RESIDENT ? (uint32_t)(c * KS + dx) : iw % C::NW;
+          ptx::mbar_wait(&w_full[sw], C::W_RESIDENT ? 0u : (iw / C::NW) & 1);
           ptx::tc_fence_after();
           // The 64 B swizzle is a pure function of the shared-memory ADDRESS bits (verified on B200: a non-zero 'matrix
           // base offset' gives wrong results), so shifted tap windows need no descriptor fix-up.
@@ -479,7 +502,7 @@ __global__ void __launch_bounds__(FUSE ? 640 : 384, 1) conv_tc_kernel(const __gr
               }
             }
           }
-          ptx::tc_commit(&w_empty[sw]);                                   // weight column free once these MMAs have read it
+          if (!C::W_RESIDENT) ptx::tc_commit(&w_empty[sw]);               // weight column free once these MMAs have read it
           if (dx == KS - 1) {
             ptx::tc_commit(&a_empty[sa]);                                 // activation chunk free
             if (c == C::NCHUNK - 1) ptx::tc_commit(&acc_full[as]);        // tile complete -> epilogue
@@ -496,20 +519,34 @@ __global__ void __launch_bounds__(FUSE ? 640 : 384, 1) conv_tc_kernel(const __gr
     const int m = q * 32 + lane;                  // accumulator row = pixel of the M-tile: 16 row groups x 8 columns
     const int prow = m >> 3, pcol = m & 7;        // (row group g covers image rows g*NH .. g*NH + NH-1, one per column block)
     uint32_t it = 0;
+    float bb[BREG ? COUT : 1], tt[BREG ? COUT : 1];
+    if (BREG) {
+#pragma unroll
+      for (int i = 0; i < COUT; ++i) { bb[i] = E.b[i]; tt[i] = E.t[i]; }
+    }
     for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x, ++it) {
       const int img = tile / tiles_per_img, r = tile - img * tiles_per_img;
       const int y0 = (r / P.tiles_x) * 16 * NH, x0 = (r % P.tiles_x) * 8 * T;
-      const uint32_t as = it & 1;
-      ptx::mbar_wait(&acc_full[as], (it >> 1) & 1);
+      const uint32_t as = it % C::NACC;
+      ptx::mbar_wait(&acc_full[as], (it / C::NACC) & 1);
       ptx::tc_fence_after();
       // An item is CW channels of one pixel: 32 where the output is an activation plane, so that every global store is a
       // whole 32-byte sector (hi: 64 B = two 256-bit stores, e4m3 lo: 32 B = one).  With 16-byte stores of half sectors the
       // epilogue alone ran at 2.7 TB/s and was the critical path of every layer but the second (profiles/r1_history.md).
       constexpr int CW = (COUT >= 32 && OUTMODE != TC_OUT_FINAL) ? 32 : 16;
-      constexpr int NBW = COUT / CW, ITEMS = T * NH * NBW;
+      // The two warps of a lane quarter split the pixel blocks (M-tile t, stacked row h) when their number is even, else the
+      // channel blocks; the channel-block loop is unrolled so the channel offset n0 is a compile-time register index.
+      constexpr int NBW = COUT / CW, NPB = T * NH;
+      constexpr bool SPLIT_PB = (NPB % 2 == 0) || (NBW % 2 != 0);
 #pragma unroll 1
-      for (int item = half; item < ITEMS; item += 2) {
-        const int t = item / (NH * NBW), hn = item - t * (NH * NBW), hrow = hn / NBW, n0 = (hn - hrow * NBW) * CW;
+      for (int pb = SPLIT_PB ? half : 0; pb < NPB; pb += SPLIT_PB ? 2 : 1) {
+      const int t = pb / NH, hrow = pb - t * NH;
+#pragma unroll
+      for (int nb = 0; nb < NBW; ++nb) {
+        if (!SPLIT_PB && (nb & 1) != half) continue;
+        constexpr int NB_STEP = SPLIT_PB ? 1 : 2;
+        const bool last_item = (SPLIT_PB ? pb + 2 >= NPB : pb == NPB - 1) && (nb + NB_STEP >= NBW);
+        const int n0 = nb * CW;
         const int x = x0 + 8 * t + pcol, y = y0 + prow * NH + hrow;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * (T * C::DCOLS) + t * C::DCOLS + hrow * C::NF;
         uint32_t rr[CW];
@@ -524,30 +561,32 @@ __global__ void __launch_bounds__(FUSE ? 640 : 384, 1) conv_tc_kernel(const __gr
           for (int i = 0; i < CW; ++i) rr[i] = __float_as_uint(__uint_as_float(rr[i]) + __uint_as_float(r2[i]));
         }
         ptx::tmem_ld_wait();
-        if (item + 2 >= ITEMS) {                 // last read of this accumulator set by this thread: hand it back
+        if (last_item) {                         // last read of this accumulator set by this thread: hand it back
           ptx::tc_fence_before();
           ptx::mbar_arrive(&acc_empty[as]);
         }
         float v[CW];
-        {   // per-channel epilogue constants: 16-byte shared-memory loads (shared-memory bandwidth is what bounds the MMAs)
+        if (BREG) {
+#pragma unroll
+          for (int i = 0; i < CW; ++i) {
+            const float a = fmaf(__uint_as_float(rr[i]), P.inv_wscale, bb[n0 + i]);
+            v[i] = P.relu ? fmaxf(a, 0.f) + tt[n0 + i] : a;
+          }
+        } else {
           const float4* eb = reinterpret_cast<const float4*>(sEpi + n0);
           const float4* es = reinterpret_cast<const float4*>(sEpi + COUT + n0);
           const float4* et = reinterpret_cast<const float4*>(sEpi + 2 * COUT + n0);
 #pragma unroll
           for (int i4 = 0; i4 < CW / 4; ++i4) {
-            const float4 b = eb[i4];
-            float a0 = __uint_as_float(rr[4 * i4 + 0]) * P.inv_wscale + b.x;
-            float a1 = __uint_as_float(rr[4 * i4 + 1]) * P.inv_wscale + b.y;
-            float a2 = __uint_as_float(rr[4 * i4 + 2]) * P.inv_wscale + b.z;
-            float a3 = __uint_as_float(rr[4 * i4 + 3]) * P.inv_wscale + b.w;
-            if (P.relu_bn) {
-              const float4 sc = es[i4], sh = et[i4];
-              a0 = fmaxf(a0, 0.f) * sc.x + sh.x;
-              a1 = fmaxf(a1, 0.f) * sc.y + sh.y;
-              a2 = fmaxf(a2, 0.f) * sc.z + sh.z;
-              a3 = fmaxf(a3, 0.f) * sc.w + sh.w;
-            }
-            v[4 * i4 + 0] = a0; v[4 * i4 + 1] = a1; v[4 * i4 + 2] = a2; v[4 * i4 + 3] = a3;
+            const float4 b = eb[i4], sc = es[i4], sh = et[i4];
+            const float a0 = __uint_as_float(rr[4 * i4 + 0]) * P.inv_wscale + b.x;
+            const float a1 = __uint_as_float(rr[4 * i4 + 1]) * P.inv_wscale + b.y;
+            const float a2 = __uint_as_float(rr[4 * i4 + 2]) * P.inv_wscale + b.z;
+            const float a3 = __uint_as_float(rr[4 * i4 + 3]) * P.inv_wscale + b.w;
+            v[4 * i4 + 0] = P.relu ? fmaxf(a0, 0.f) * sc.x + sh.x : a0;
+            v[4 * i4 + 1] = P.relu ? fmaxf(a1, 0.f) * sc.y + sh.y : a1;
+            v[4 * i4 + 2] = P.relu ? fmaxf(a2, 0.f) * sc.z + sh.z : a2;
+            v[4 * i4 + 3] = P.relu ? fmaxf(a3, 0.f) * sc.w + sh.w : a3;
           }
         }
         if (OUTMODE == TC_OUT_FINAL) {
@@ -596,6 +635,7 @@ __global__ void __launch_bounds__(FUSE ? 640 : 384, 1) conv_tc_kernel(const __gr
             }
         }
       }
+      }
     }
   }
   ptx::tc_fence_before();
@@ -605,10 +645,10 @@ __global__ void __launch_bounds__(FUSE ? 640 : 384, 1) conv_tc_kernel(const __gr
 
 // ------------------------------------------------------------------------------------------------ host side ----
 struct TcLayer {
-  int cin = 0, cout = 0, ks = 0, relu_bn = 0;   // MMA-level shapes (padded): cin multiple of 32, cout = MMA N
+  int cin = 0, cout = 0, ks = 0, relu = 0;      // MMA-level shapes (padded): cin multiple of 32, cout = MMA N
   int real_cout = 0, passes = 3;
   __half* w = nullptr;
-  float *bias = nullptr, *bn_s = nullptr, *bn_t = nullptr;
+  TcEpi epi;
   float inv_wscale = 1.f;
 };
 struct TcNet {
@@ -629,8 +669,8 @@ struct TcWorkspace {
 };
 
 inline void tc_free_net(TcNet& n) {
-  for (auto& L : n.layers) { cudaFree(L.w); cudaFree(L.bias); cudaFree(L.bn_s); cudaFree(L.bn_t); }
-  cudaFree(n.l2_fast.w); cudaFree(n.l2_fast.bias); cudaFree(n.l2_fast.bn_s); cudaFree(n.l2_fast.bn_t);
+  for (auto& L : n.layers) cudaFree(L.w);
+  cudaFree(n.l2_fast.w);
   n.l2_fast = TcLayer();
   n.layers.clear();
   n.ready = false;
@@ -646,8 +686,8 @@ inline int tc_launches_per_forward(const TcNet& n) { return n.ready ? (int)n.lay
 // weights of the row-stacked MMA (taps ky = s - h, h ascending) one contiguous B operand.  Epilogue vectors are padded.
 inline bool tc_pack_layer(TcLayer& L, int cin_p, int cout_p, int ks, int passes, bool lo8, int real_cin, int real_cout,
                           const std::vector<float>& wdense /* [real_cout][real_cin][ks*ks] */, const float* bias,
-                          const float* bn_s, const float* bn_t, int relu_bn) {
-  L.cin = cin_p; L.cout = cout_p; L.ks = ks; L.relu_bn = relu_bn; L.real_cout = real_cout; L.passes = passes;
+                          const float* bnscale, const float* shift, int relu) {
+  L.cin = cin_p; L.cout = cout_p; L.ks = ks; L.relu = relu; L.real_cout = real_cout; L.passes = passes;
   const int taps = ks * ks, planes = passes == 3 ? 2 : 1, nchunk = cin_p / 32;
   const bool ncat = passes == 3 && cout_p <= 32;
   const int nf = ncat ? 2 * cout_p : cout_p, wrows = ncat ? nf : planes * cout_p;
@@ -684,17 +724,13 @@ inline bool tc_pack_layer(TcLayer& L, int cin_p, int cout_p, int ks, int passes,
             }
       }
     }
-  std::vector<float> b(cout_p, 0.f), s(cout_p, 1.f), t(cout_p, 0.f);
-  for (int i = 0; i < real_cout; ++i) {
-    b[i] = bias[i];
-    if (relu_bn) { s[i] = bn_s[i]; t[i] = bn_t[i]; }
+  for (int i = 0; i < 128; ++i) {
+    L.epi.b[i] = i < real_cout ? bias[i] : 0.f;
+    L.epi.s[i] = (relu && i < real_cout) ? bnscale[i] : 1.f;
+    L.epi.t[i] = (relu && i < real_cout) ? shift[i] : 0.f;
   }
   if (cudaMalloc(&L.w, pk.size()) != cudaSuccess) return false;
   if (cudaMemcpy(L.w, pk.data(), pk.size(), cudaMemcpyHostToDevice) != cudaSuccess) return false;
-  for (auto pr : {std::make_pair(&L.bias, &b), std::make_pair(&L.bn_s, &s), std::make_pair(&L.bn_t, &t)}) {
-    if (cudaMalloc(pr.first, cout_p * sizeof(float)) != cudaSuccess) return false;
-    if (cudaMemcpy(*pr.first, pr.second->data(), cout_p * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) return false;
-  }
   return true;
 }
 
@@ -712,24 +748,47 @@ inline int tc_pack_net(TcNet& n, int nlayers, const qgb_cnn_layer* L, std::strin
   n.cin0 = L[0].cin;
   n.kp = n.cin0 == 4 ? 128 : 64;
   n.layers.resize(8);
+  // BatchNorm scale folding for the thin layers (COUT <= 32, epilogue constants in registers).  Layer i computes
+  // y = relu(z) * s + t per channel (z = conv + bias).  With a = |s|, g = sign(s): relu(z) * s = g * relu(a z), so a scales
+  // the layer's weight rows and bias, the epilogue stores  yhat = relu(a z) + g t  and the next layer's weights take the
+  // sign, w'[co][ci] = w[co][ci] * g[ci]  (y = g * yhat).  Layers 1 and 2 keep scale and shift in the epilogue.
+  auto folded = [&](int i) { return i >= 0 && i < 7 && cout[i] <= 32; };
+  auto bn_abs = [&](int i, int c) { return folded(i) ? std::fabs(L[i].bn_scale[c]) : 1.f; };
+  auto bn_sgn = [&](int i, int c) { return (folded(i) && L[i].bn_scale[c] < 0.f) ? -1.f : 1.f; };
+  auto epi_scale = [&](int i) {
+    std::vector<float> v(cout[i], 1.f);
+    if (i < 7 && !folded(i)) for (int c = 0; c < cout[i]; ++c) v[c] = L[i].bn_scale[c];
+    return v;
+  };
+  auto epi_shift = [&](int i) {
+    std::vector<float> v(cout[i], 0.f);
+    if (i < 7) for (int c = 0; c < cout[i]; ++c) v[c] = L[i].bn_shift[c] * bn_sgn(i, c);
+    return v;
+  };
   // layer 1 as a 1x1 convolution over the im2col tensor: K index = tap*cin0 + ch
   {
     const int K = 25 * n.cin0;
-    std::vector<float> wd((size_t)128 * K);
+    std::vector<float> wd((size_t)128 * K), sf = epi_scale(0), tf = epi_shift(0);
     for (int co = 0; co < 128; ++co)
       for (int ch = 0; ch < n.cin0; ++ch)
         for (int tap = 0; tap < 25; ++tap) wd[(size_t)co * K + tap * n.cin0 + ch] = L[0].weight[((size_t)co * n.cin0 + ch) * 25 + tap];
-    if (!tc_pack_layer(n.layers[0], n.kp, 128, 1, 3, false, K, 128, wd, L[0].bias, L[0].bn_scale, L[0].bn_shift, 1)) { *err = "cuda"; return QGB_ECUDA; }
+    if (!tc_pack_layer(n.layers[0], n.kp, 128, 1, 3, false, K, 128, wd, L[0].bias, sf.data(), tf.data(), 1)) { *err = "cuda"; return QGB_ECUDA; }
   }
   for (int i = 1; i < 8; ++i) {
     const int taps = ks[i] * ks[i];
-    std::vector<float> wd(L[i].weight, L[i].weight + (size_t)cout[i] * cin[i] * taps);
+    std::vector<float> wd((size_t)cout[i] * cin[i] * taps), bf(cout[i]), sf = epi_scale(i), tf = epi_shift(i);
+    for (int co = 0; co < cout[i]; ++co) {
+      for (int ci = 0; ci < cin[i]; ++ci)
+        for (int tap = 0; tap < taps; ++tap) {
+          const size_t idx = ((size_t)co * cin[i] + ci) * taps + tap;
+          wd[idx] = L[i].weight[idx] * bn_sgn(i - 1, ci) * bn_abs(i, co);
+        }
+      bf[co] = L[i].bias[co] * bn_abs(i, co);
+    }
     const int cout_p = i == 7 ? 16 : cout[i];
     const int passes = i == 1 ? 2 : 3;          // layer 2: (a_hi + a_lo) w_hi ; others: full split precision
-    if (!tc_pack_layer(n.layers[i], cin[i], cout_p, ks[i], passes, true, cin[i], cout[i], wd, L[i].bias, L[i].bn_scale,
-                       L[i].bn_shift, i < 7)) { *err = "cuda"; return QGB_ECUDA; }
-    if (i == 1 && !tc_pack_layer(n.l2_fast, cin[i], cout_p, ks[i], 1, false, cin[i], cout[i], wd, L[i].bias, L[i].bn_scale,
-                                 L[i].bn_shift, 1)) { *err = "cuda"; return QGB_ECUDA; }
+    if (!tc_pack_layer(n.layers[i], cin[i], cout_p, ks[i], passes, true, cin[i], cout[i], wd, bf.data(), sf.data(), tf.data(), i < 7)) { *err = "cuda"; return QGB_ECUDA; }
+    if (i == 1 && !tc_pack_layer(n.l2_fast, cin[i], cout_p, ks[i], 1, false, cin[i], cout[i], wd, bf.data(), sf.data(), tf.data(), 1)) { *err = "cuda"; return QGB_ECUDA; }
   }
   n.ready = true;
   return 0;
@@ -773,7 +832,7 @@ inline bool tc_make_map8(CUtensorMap* m, const void* base, int WP, int HP, long 
 }
 
 template <int CIN, int COUT, int KS, int PASSES, int T, int OUTMODE, int FUSE = 0, int NH = 1>
-inline cudaError_t tc_launch(const TcConvParams& P, int nimg, int nsm, cudaStream_t st) {
+inline cudaError_t tc_launch(const TcConvParams& P, const TcEpi& E, int nimg, int nsm, cudaStream_t st) {
   constexpr bool LO8 = !FUSE && PASSES >= 2;
   using C = TcCfg<CIN, COUT, KS, PASSES, T, LO8, NH>;
   TcMaps M;
@@ -794,32 +853,37 @@ inline cudaError_t tc_launch(const TcConvParams& P, int nimg, int nsm, cudaStrea
     configured = true;
   }
   const int grid = P.num_tiles < nsm ? P.num_tiles : nsm;
-  kern<<<grid, FUSE ? 640 : 384, C::SMEM + (FUSE ? 6400 : 0), st>>>(P, M);
+  kern<<<grid, FUSE ? 640 : 384, C::SMEM + (FUSE ? 6400 : 0), st>>>(P, M, E);
   return cudaGetLastError();
 }
 
 // Tile shape of a layer: NH stacked rows (tile height 16*NH) x T M-tiles of 8 columns.  TMEM holds 2 x T x NH x NF columns.
 struct TcTile { int nh, t; };
 template <int COUT, int PASSES>
-inline TcTile tc_pick_tile(int ny, int nx) {
+inline TcTile tc_pick_tile(int ny, int nx, bool thin = false) {
   constexpr int NF = (PASSES == 3 && COUT <= 32) ? 2 * COUT : COUT;
   static int force_nh = -1;
   if (force_nh < 0) { const char* e = getenv("QGB_TC_NH"); force_nh = e ? atoi(e) : 0; }
   if (force_nh != 1) {
+    // 32 -> 32 layers: 32 x 8 tiles leave room for a 4-deep accumulator ring (measured 228 -> 208 us per 1024 images at 64^2)
+    if (ny % 32 == 0 && PASSES == 3 && COUT == 32 && thin) return {2, 1};
     if (ny % 32 == 0 && nx % 16 == 0 && 2 * 2 * 2 * NF <= 512) return {2, 2};
     if (NF == 64 && PASSES != 3 && ny % 48 == 0) return {3, 1};
   }
   return {1, nx % 32 == 0 ? 4 : (nx % 24 == 0 ? 3 : 2)};
 }
 template <int CIN, int COUT, int KS, int PASSES, int OUTMODE>
-inline cudaError_t tc_launch_T(TcTile tl, const TcConvParams& P, int nimg, int nsm, cudaStream_t st) {
-  if (tl.nh == 2) return tc_launch<CIN, COUT, KS, PASSES, 2, OUTMODE, 0, 2>(P, nimg, nsm, st);
-  if constexpr (COUT == 64 && PASSES != 3) {
-    if (tl.nh == 3) return tc_launch<CIN, COUT, KS, PASSES, 1, OUTMODE, 0, 3>(P, nimg, nsm, st);
+inline cudaError_t tc_launch_T(TcTile tl, const TcConvParams& P, const TcEpi& E, int nimg, int nsm, cudaStream_t st) {
+  if constexpr (PASSES == 3) {
+    if (tl.nh == 2 && tl.t == 1) return tc_launch<CIN, COUT, KS, PASSES, 1, OUTMODE, 0, 2>(P, E, nimg, nsm, st);
   }
-  if (tl.t == 4) return tc_launch<CIN, COUT, KS, PASSES, 4, OUTMODE>(P, nimg, nsm, st);
-  if (tl.t == 3) return tc_launch<CIN, COUT, KS, PASSES, 3, OUTMODE>(P, nimg, nsm, st);
-  return tc_launch<CIN, COUT, KS, PASSES, 2, OUTMODE>(P, nimg, nsm, st);
+  if (tl.nh == 2) return tc_launch<CIN, COUT, KS, PASSES, 2, OUTMODE, 0, 2>(P, E, nimg, nsm, st);
+  if constexpr (COUT == 64 && PASSES != 3) {
+    if (tl.nh == 3) return tc_launch<CIN, COUT, KS, PASSES, 1, OUTMODE, 0, 3>(P, E, nimg, nsm, st);
+  }
+  if (tl.t == 4) return tc_launch<CIN, COUT, KS, PASSES, 4, OUTMODE>(P, E, nimg, nsm, st);
+  if (tl.t == 3) return tc_launch<CIN, COUT, KS, PASSES, 3, OUTMODE>(P, E, nimg, nsm, st);
+  return tc_launch<CIN, COUT, KS, PASSES, 2, OUTMODE>(P, E, nimg, nsm, st);
 }
 
 inline int tc_forward(const TcNet& net, TcWorkspace& ws, const float* x, long long x_bs, float* y, long long y_bs,
@@ -852,14 +916,14 @@ inline int tc_forward(const TcNet& net, TcWorkspace& ws, const float* x, long lo
     for (int li = 0; li < 8; ++li) {
       const TcLayer& L = (li == 1 && fast_l2) ? net.l2_fast : net.layers[li];
       TcConvParams P;
-      P.w = L.w; P.bias = L.bias; P.bn_s = L.bn_s; P.bn_t = L.bn_t; P.inv_wscale = L.inv_wscale; P.relu_bn = L.relu_bn;
+      P.w = L.w; P.inv_wscale = L.inv_wscale; P.relu = L.relu;
       P.ny = ny; P.nx = nx;
       P.out_f32 = nullptr; P.out_bs = 0; P.out_c = 0; P.softplus = 0; P.accumulate = 0;
       P.x_f32 = x + (long long)b0 * x_bs; P.x_bs = x_bs;
       P.out_hi = P.out_lo = nullptr; P.out_pad = 0; P.out_nch = 0;
       TcTile tl = {1, 2};                                        // layer 1 (fused im2col): 16 x 16 tiles
       if (li == 1) tl = fast_l2 ? tc_pick_tile<64, 1>(ny, nx) : tc_pick_tile<64, 2>(ny, nx);
-      else if (li >= 2 && li < 7) tl = tc_pick_tile<32, 3>(ny, nx);
+      else if (li >= 2 && li < 7) tl = tc_pick_tile<32, 3>(ny, nx, L.cin == 32);
       else if (li == 7) tl = tc_pick_tile<16, 3>(ny, nx);
       P.tiles_y = ny / (16 * tl.nh);
       P.tiles_x = nx / (8 * tl.t);
@@ -882,12 +946,12 @@ inline int tc_forward(const TcNet& net, TcWorkspace& ws, const float* x, long lo
       if (prof) { cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventRecord(ev0, st); }
       cudaError_t e;
       if (li == 0) {
-        if (fast_l2) e = net.kp == 128 ? tc_launch<128, 128, 1, 3, 2, TC_OUT_HI, 4>(P, nb, nsm, st) : tc_launch<64, 128, 1, 3, 2, TC_OUT_HI, 2>(P, nb, nsm, st);
-        else e = net.kp == 128 ? tc_launch<128, 128, 1, 3, 2, TC_OUT_HILO, 4>(P, nb, nsm, st) : tc_launch<64, 128, 1, 3, 2, TC_OUT_HILO, 2>(P, nb, nsm, st);
-      } else if (li == 1) e = fast_l2 ? tc_launch_T<128, 64, 5, 1, TC_OUT_HILO>(tl, P, nb, nsm, st) : tc_launch_T<128, 64, 5, 2, TC_OUT_HILO>(tl, P, nb, nsm, st);
-      else if (li == 2) e = tc_launch_T<64, 32, 3, 3, TC_OUT_HILO>(tl, P, nb, nsm, st);
-      else if (li < 7) e = tc_launch_T<32, 32, 3, 3, TC_OUT_HILO>(tl, P, nb, nsm, st);
-      else e = tc_launch_T<32, 16, 3, 3, TC_OUT_FINAL>(tl, P, nb, nsm, st);
+        if (fast_l2) e = net.kp == 128 ? tc_launch<128, 128, 1, 3, 2, TC_OUT_HI, 4>(P, L.epi, nb, nsm, st) : tc_launch<64, 128, 1, 3, 2, TC_OUT_HI, 2>(P, L.epi, nb, nsm, st);
+        else e = net.kp == 128 ? tc_launch<128, 128, 1, 3, 2, TC_OUT_HILO, 4>(P, L.epi, nb, nsm, st) : tc_launch<64, 128, 1, 3, 2, TC_OUT_HILO, 2>(P, L.epi, nb, nsm, st);
+      } else if (li == 1) e = fast_l2 ? tc_launch_T<128, 64, 5, 1, TC_OUT_HILO>(tl, P, L.epi, nb, nsm, st) : tc_launch_T<128, 64, 5, 2, TC_OUT_HILO>(tl, P, L.epi, nb, nsm, st);
+      else if (li == 2) e = tc_launch_T<64, 32, 3, 3, TC_OUT_HILO>(tl, P, L.epi, nb, nsm, st);
+      else if (li < 7) e = tc_launch_T<32, 32, 3, 3, TC_OUT_HILO>(tl, P, L.epi, nb, nsm, st);
+      else e = tc_launch_T<32, 16, 3, 3, TC_OUT_FINAL>(tl, P, L.epi, nb, nsm, st);
       if (prof) { cudaEventRecord(ev1, st); ws.prof_events->emplace_back(ev0, ev1); *ws.prof_images += nb; }
       ws.last_launches += 1;
       if (e != cudaSuccess) { *err = std::string("tcgen05 conv launch failed: ") + cudaGetErrorString(e); return QGB_ECUDA; }
