@@ -865,6 +865,8 @@ inline TcTile tc_pick_tile(int ny, int nx, bool thin = false) {
   static int force_nh = -1;
   if (force_nh < 0) { const char* e = getenv("QGB_TC_NH"); force_nh = e ? atoi(e) : 0; }
   if (force_nh != 1) {
+    // layer 2: four stacked rows (N up to 256, 64 x 8 tiles) where the image height allows
+    if (NF == 64 && PASSES != 3 && ny % 64 == 0 && force_nh != 2) return {4, 1};
     // 32 -> 32 layers: 32 x 8 tiles leave room for a 4-deep accumulator ring (measured 228 -> 208 us per 1024 images at 64^2)
     if (ny % 32 == 0 && PASSES == 3 && COUT == 32 && thin) return {2, 1};
     if (ny % 32 == 0 && nx % 16 == 0 && 2 * 2 * 2 * NF <= 512) return {2, 2};
@@ -879,6 +881,7 @@ inline cudaError_t tc_launch_T(TcTile tl, const TcConvParams& P, const TcEpi& E,
   }
   if (tl.nh == 2) return tc_launch<CIN, COUT, KS, PASSES, 2, OUTMODE, 0, 2>(P, E, nimg, nsm, st);
   if constexpr (COUT == 64 && PASSES != 3) {
+    if (tl.nh == 4) return tc_launch<CIN, COUT, KS, PASSES, 1, OUTMODE, 0, 4>(P, E, nimg, nsm, st);
     if (tl.nh == 3) return tc_launch<CIN, COUT, KS, PASSES, 1, OUTMODE, 0, 3>(P, E, nimg, nsm, st);
   }
   if (tl.t == 4) return tc_launch<CIN, COUT, KS, PASSES, 4, OUTMODE>(P, E, nimg, nsm, st);
