@@ -149,6 +149,20 @@ int qgb_diag(qgb_handle* h, double* ke, double* cfl, int32_t* flags, int on_devi
 /* pyqg diagnostics KEspec = wv2*|ph|^2/M^2 and Ensspec = |qh|^2/M^2 summed over local members:
  * double (2, N, N/2+1) each (the accumulators that are all-reduced over NCCL by the Python layer). */
 int qgb_diag_spectra(qgb_handle* h, double* kespec_sum, double* ensspec_sum, int on_device, void* stream);
+/* Spectral energy budget of the current state, summed over the local members (pyqg 0.7.2
+ * QGModel._initialize_model_diagnostics / Model._initialize_diagnostics lambdas, consumed by
+ * tools/comparison_tools.py:91,164-189,222-263).  out: double (QGB_BUDGET_TERMS, N, N/2+1), every term / M^2:
+ * KEflux, APEflux, APEgenspec, KEfrictionspec, entspec, paramspec_KEflux, paramspec_APEflux (their sum is pyqg's
+ * paramspec; zero without a closure or before its first evaluation). */
+#define QGB_BUDGET_TERMS 7
+int qgb_diag_budget(qgb_handle* h, double* out, int on_device, void* stream);
+/* pyqg's time-averaged diagnostics (Model tavestart / taveint, _increment_diagnostics): once configured, qgb_step samples
+ * KEspec (2), Ensspec (2) and the 7 budget terms before every step with t >= dt, t >= tavestart and
+ * tc % ceil(taveint/dt) == 0 and adds them (summed over the local members) to device accumulators.
+ * qgb_diag_averages returns the accumulators, double (4 + QGB_BUDGET_TERMS, N, N/2+1), and the number of samples;
+ * mean = sum / (nsamples * total members) after the cross-rank all-reduce.  reset != 0 clears them afterwards. */
+int qgb_diag_config(qgb_handle* h, double tavestart, double taveint);
+int qgb_diag_averages(qgb_handle* h, double* out, int64_t* nsamples, int reset, int on_device, void* stream);
 
 /* ---- coarse-graining operators (stateless; tools/operators.py) -------------------------------------------
  * op: 1 = Operator1 (cut_off + model filter, :204-205), 2 = Operator2 (cut_off + gaussian, :207-208),

@@ -341,26 +341,60 @@ class QGModel(object):
             self.log.append((self.tc, self.t, self.ke, self.cfl))
             assert self.cfl < 1., "CFL condition violated"
 
-    # ---- model.py : diagnostics (subset on the online-metric path: KEspec, Ensspec, EKE) -----
+    # ---- model.py / qg_model.py : diagnostics -------------------------------------------------
+    # Restated from pyqg 0.7.2 (``Model._initialize_diagnostics`` and ``QGModel._initialize_model_diagnostics``: the
+    # ``add_diagnostic`` lambdas; ``Model._increment_diagnostics`` running mean).  pyqg is not installable here, so these
+    # formulas are PARITY UNPINNED against pyqg itself; tests/test_oracle_pins.py pins them through identities that must
+    # hold for the true definitions (energy conservation of the Jacobian terms, paramspec = KE part + APE part, and the
+    # spectral energy budget d/dt E(k) = sum of the terms measured by stepping the model).
+    # Consumers in the reference: tools/comparison_tools.py:91,164-189,222-263, tools/spectral_tools.py:103-180.
     def _initialize_diagnostics(self):
         self.diag_count = 0
         self.diag = {}
 
+    def diagnostic_fields(self):
+        """Instantaneous values of the time-averaged diagnostics for the current (inverted) state."""
+        M2 = self.M ** 2
+        self._calc_derived_fields()
+        ph, qh = self.ph, self.qh
+        d = {
+            'KEspec': self.wv2 * np.abs(ph) ** 2 / M2,
+            'Ensspec': np.abs(qh) ** 2 / M2,
+            'entspec': np.abs(self.del1 * qh[0] + self.del2 * qh[1]) ** 2 / M2,
+            'KEflux': (np.real(self.del1 * ph[0] * np.conj(self.Jpxi[0])) + np.real(self.del2 * ph[1] * np.conj(self.Jpxi[1]))) / M2,
+            'APEflux': self.rd ** -2 * self.del1 * self.del2 * np.real((ph[0] - ph[1]) * np.conj(self.Jptpc)) / M2,
+            'APEgenspec': self.U * self.rd ** -2 * self.del1 * self.del2 * np.real(
+                1j * self.k * (self.del1 * ph[0] + self.del2 * ph[1]) * np.conj(ph[0] - ph[1])) / M2,
+            'KEfrictionspec': -self.rek * self.del2 * self.wv2 * np.abs(ph[1]) ** 2 / M2,
+            'EKE': 0.5 * (self.u ** 2 + self.v ** 2).mean(axis=(-1, -2)),
+        }
+        if self.q_parameterization is not None and getattr(self, 'dqh', None) is not None:
+            dqh = self.dqh
+            hr = (self.Hi / self.H)[:, np.newaxis, np.newaxis]
+            d['paramspec'] = -np.real((hr * np.conj(ph) * dqh).sum(axis=0)) / M2
+            dph = np.einsum('ij...,j...->i...', self.a, dqh)          # streamfunction tendency of the parameterization
+            d['paramspec_KEflux'] = self.wv2 * (self.del1 * np.real(np.conj(ph[0]) * dph[0])
+                                               + self.del2 * np.real(np.conj(ph[1]) * dph[1])) / M2
+            d['paramspec_APEflux'] = self.rd ** -2 * self.del1 * self.del2 * np.real(
+                np.conj(ph[0] - ph[1]) * (dph[0] - dph[1])) / M2
+        return d
+
     def _calc_diagnostics(self):
-        if self.t >= self.dt and self.t >= self.tavestart and (self.tc % int(self.taveint / self.dt)) == 0:
-            vals = {
-                'KEspec': self.wv2 * np.abs(self.ph) ** 2 / self.M ** 2,
-                'Ensspec': np.abs(self.qh) ** 2 / self.M ** 2,
-            }
+        taveints = np.ceil(self.taveint / self.dt)
+        if self.t >= self.dt and self.t >= self.tavestart and (self.tc % taveints) == 0:
+            vals = self.diagnostic_fields()
             n = self.diag_count
             for k, v in vals.items():
-                self.diag[k] = v.copy() if n == 0 else (self.diag[k] * n + v) / (n + 1)
+                self.diag[k] = np.array(v, copy=True) if n == 0 else (self.diag[k] * n + v) / (n + 1)
             self.diag_count = n + 1
 
-    # ---- qg_model.py : _calc_derived_fields (only p is consumed on the in-scope paths) -------
+    # ---- qg_model.py : _calc_derived_fields ---------------------------------------------------
     def _calc_derived_fields(self):
         self.p = self.ifft(self.ph)
         self.xi = self.ifft(-self.wv2 * self.ph)
+        self.Jptpc = -self._advect(self.p[0] - self.p[1], self.del1 * self.u[0] + self.del2 * self.u[1],
+                                   self.del1 * self.v[0] + self.del2 * self.v[1])
+        self.Jpxi = self._advect(self.xi, self.u, self.v)
 
     def _advect(self, q, u=None, v=None):
         if u is None:

@@ -54,6 +54,9 @@ SYMBOLS = {
     'qgb_step_host_async': (_i, [_vp, _vp, _vp, _i, _vp]),
     'qgb_diag': (_i, [_vp, _vp, _vp, _vp, _i, _vp]),
     'qgb_diag_spectra': (_i, [_vp, _vp, _vp, _i, _vp]),
+    'qgb_diag_budget': (_i, [_vp, _vp, _i, _vp]),
+    'qgb_diag_config': (_i, [_vp, _d, _d]),
+    'qgb_diag_averages': (_i, [_vp, _vp, ctypes.POINTER(ctypes.c_int64), _i, _i, _vp]),
     'qgb_operator': (_i, [_i, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
     'qgb_subgrid_forcing': (_i, [ctypes.POINTER(QgbConfig), _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     'qgb_fft_interpolate': (_i, [_i, _i, _i, _i, _vp, _vp, _i, _vp]),

@@ -49,6 +49,10 @@ struct qgb_handle {
   cplx* ph = nullptr; double *u = nullptr, *v = nullptr, *p = nullptr, *red = nullptr;
   double *d_ke = nullptr, *d_cfl = nullptr; int* d_flags = nullptr;
   double *d_kespec = nullptr, *d_ensspec = nullptr;
+  // spectral energy budget (PROG_BUDGET) and pyqg-style time averages of the spectral diagnostics
+  double *bud = nullptr, *bud_scr = nullptr, *bud_sum = nullptr;     // per member / scratch / summed over members
+  const double* last_dq = nullptr;   // forcing used by the latest step (closure output or external), for the budget terms
+  double* avg = nullptr; long long avg_n = 0; bool avg_on = false; double tavestart = 0.0, taveint = 86400.0;
   long long tc = 0; double t = 0.0; int ablevel = 0;
   int nthreads = 256; size_t smem = 0; int grid = 0;
   bool fixed = false;   // compile-time specialised step kernel available for this nx
@@ -116,6 +120,8 @@ StepIO base_io(qgb_handle* h) {
   io.qh = h->qh; io.q = h->q;
   io.Hi_over_H[0] = h->ht.Hi_over_H[0]; io.Hi_over_H[1] = h->ht.Hi_over_H[1];
   io.x_std[0] = h->x_std[0]; io.x_std[1] = h->x_std[1];
+  io.bud_F = h->ht.Hi_over_H[0] * h->ht.Hi_over_H[1] / (h->cfg.rd * h->cfg.rd);
+  io.bud_U = h->cfg.U1 - h->cfg.U2;
   return io;
 }
 
@@ -503,6 +509,7 @@ void qgb_destroy(qgb_handle* h) {
   for (int i = 0; i < 3; ++i) cudaFree(h->hist[i]);
   cudaFree(h->ph); cudaFree(h->u); cudaFree(h->v); cudaFree(h->p); cudaFree(h->red);
   cudaFree(h->d_ke); cudaFree(h->d_cfl); cudaFree(h->d_flags); cudaFree(h->d_kespec); cudaFree(h->d_ensspec);
+  cudaFree(h->bud); cudaFree(h->bud_scr); cudaFree(h->bud_sum); cudaFree(h->avg);
   cudaFree(h->xin); cudaFree(h->z64); cudaFree(h->xi_inj); cudaFree(h->ynet[0]); cudaFree(h->ynet[1]);
   cudaFree(h->yacc); cudaFree(h->dq_ext); cudaFree(h->dq); cudaFree(h->dq_dm); cudaFree(h->act[0]); cudaFree(h->act[1]);
   free_net(h->nets[0]); free_net(h->nets[1]);
@@ -553,6 +560,101 @@ int qgb_invert(qgb_handle* h, void* stream) {
   return launch_program(h, io, PROG_INVERT, S(stream));
 }
 
+namespace {
+// out[i] (+)= sum over members of per_member[m][i], in member order (deterministic, independent of the sharding)
+__global__ void reduce_members_kernel(const double* __restrict__ per_member, int members, long long n, double* __restrict__ out,
+                                      int accumulate) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double acc = 0.0;
+  for (int m = 0; m < members; ++m) acc += per_member[(long long)m * n + i];
+  out[i] = accumulate ? out[i] + acc : acc;
+}
+__global__ void add_kernel(const double* __restrict__ a, long long n, double* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] += a[i];
+}
+
+// budget terms of the current state summed over the local members -> ``out`` (kBudgetTerms, N, NK), device pointer
+int budget_sums(qgb_handle* h, const double* dq, double* out, int accumulate, cudaStream_t st) {
+  const long long NN = (long long)h->ht.N * h->ht.NK, B = h->cfg.members;
+  if (!h->bud) {
+    CUDA_TRY(h, dalloc(&h->bud, (size_t)(B * kBudgetTerms * NN)));
+    CUDA_TRY(h, dalloc(&h->bud_scr, (size_t)(B * 3 * h->ht.N * h->ht.N)));
+  }
+  StepIO io = base_io(h);
+  io.bud_out = h->bud; io.bud_scr = h->bud_scr;
+  io.dq = dq;
+  int rc = launch_program(h, io, PROG_BUDGET, st);
+  if (rc) return rc;
+  const long long n = kBudgetTerms * NN;
+  reduce_members_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(h->bud, (int)B, n, out, accumulate);
+  QGB_COUNT_LAUNCH();
+  CUDA_TRY(h, cudaGetLastError());
+  return QGB_OK;
+}
+
+// pyqg Model._increment_diagnostics: called before the time step when t >= dt, t >= tavestart and tc % ceil(taveint/dt) == 0
+int sample_averages(qgb_handle* h, const double* dq, cudaStream_t st) {
+  const long long NN = (long long)h->ht.N * h->ht.NK, nspec = 4 * NN;
+  if (!h->avg) {
+    CUDA_TRY(h, dalloc(&h->avg, (size_t)((4 + kBudgetTerms) * NN)));
+    CUDA_TRY(h, cudaMemsetAsync(h->avg, 0, (size_t)((4 + kBudgetTerms) * NN) * sizeof(double), st));
+    h->avg_n = 0;
+  }
+  if (!h->d_kespec) { CUDA_TRY(h, dalloc(&h->d_kespec, (size_t)(2 * NN))); CUDA_TRY(h, dalloc(&h->d_ensspec, (size_t)(2 * NN))); }
+  spectra_kernel<<<(unsigned)((2 * NN + 127) / 128), 128, 0, st>>>(h->T, h->qh, h->cfg.members, h->d_kespec, h->d_ensspec);
+  QGB_COUNT_LAUNCH();
+  add_kernel<<<(unsigned)((2 * NN + 127) / 128), 128, 0, st>>>(h->d_kespec, 2 * NN, h->avg);
+  add_kernel<<<(unsigned)((2 * NN + 127) / 128), 128, 0, st>>>(h->d_ensspec, 2 * NN, h->avg + 2 * NN);
+  QGB_COUNT_LAUNCH(); QGB_COUNT_LAUNCH();
+  int rc = budget_sums(h, dq, h->avg + nspec, 1, st);
+  if (rc) return rc;
+  h->avg_n += 1;
+  return QGB_OK;
+}
+}  // namespace
+
+int qgb_diag_budget(qgb_handle* h, double* out, int on_device, void* stream) {
+  if (!h || !out) return fail(h, QGB_EINVAL, "null argument");
+  cudaStream_t st = S(stream);
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  const size_t n = (size_t)kBudgetTerms * h->ht.N * h->ht.NK;
+  if (on_device) return budget_sums(h, h->last_dq, out, 0, st);
+  if (!h->bud_sum) CUDA_TRY(h, dalloc(&h->bud_sum, n));
+  int rc = budget_sums(h, h->last_dq, h->bud_sum, 0, st);
+  if (rc) return rc;
+  CUDA_TRY(h, cudaMemcpyAsync(out, h->bud_sum, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(h, cudaStreamSynchronize(st));
+  return QGB_OK;
+}
+
+int qgb_diag_config(qgb_handle* h, double tavestart, double taveint) {
+  if (!h) return QGB_EINVAL;
+  if (!(taveint > 0.0)) return fail(h, QGB_EINVAL, "taveint must be positive");
+  h->tavestart = tavestart; h->taveint = taveint; h->avg_on = true;
+  return QGB_OK;
+}
+
+int qgb_diag_averages(qgb_handle* h, double* out, int64_t* nsamples, int reset, int on_device, void* stream) {
+  if (!h) return QGB_EINVAL;
+  cudaStream_t st = S(stream);
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  const size_t n = (size_t)(4 + kBudgetTerms) * h->ht.N * h->ht.NK;
+  if (nsamples) *nsamples = h->avg_n;
+  if (out) {
+    if (h->avg && h->avg_n > 0) CUDA_TRY(h, cudaMemcpyAsync(out, h->avg, n * sizeof(double), on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+    else if (on_device) CUDA_TRY(h, cudaMemsetAsync(out, 0, n * sizeof(double), st));
+    else std::memset(out, 0, n * sizeof(double));
+    if (!on_device) CUDA_TRY(h, cudaStreamSynchronize(st));
+  }
+  if (reset) {
+    if (h->avg) CUDA_TRY(h, cudaMemsetAsync(h->avg, 0, n * sizeof(double), st));
+    h->avg_n = 0;
+  }
+  return QGB_OK;
+}
+
 int qgb_step(qgb_handle* h, int nsteps, void* stream) {
   if (!h || nsteps < 0) return fail(h, QGB_EINVAL, "bad argument");
   cudaStream_t st = S(stream);
@@ -571,11 +673,17 @@ int qgb_step(qgb_handle* h, int nsteps, void* stream) {
       io.dq = h->dq;
       prog = PROG_STEP_DQ;
     }
+    if (h->avg_on && h->t >= h->cfg.dt && h->t >= h->tavestart &&
+        h->tc % (long long)std::ceil(h->taveint / h->cfg.dt) == 0) {
+      int rc = sample_averages(h, io.dq, st);
+      if (rc) return rc;
+    }
     const int cur = (int)(h->tc % 3), prev = (int)((h->tc + 2) % 3), pprev = (int)((h->tc + 1) % 3);
     io.d_cur = h->hist[cur]; io.d_p = h->hist[prev]; io.d_pp = h->hist[pprev];
     ab_coefficients(h->ablevel, h->cfg.dt, io.dt1, io.dt2, io.dt3);
     int rc = launch_program(h, io, prog, st);
     if (rc) return rc;
+    h->last_dq = io.dq;
     if (h->ablevel < 2) h->ablevel++;
     h->tc += 1;
     h->t += h->cfg.dt;

@@ -80,7 +80,17 @@ struct StepIO {
   double* p_out;
   double* red_out;      // (B,4): ke, max|u+U|, max|v|, nonfinite count
   double Hi_over_H[2];
+  // spectral energy budget (PROG_BUDGET): per-member terms (B, kBudgetTerms, N, NK) and real scratch (B, 3, N, N)
+  double* bud_out;
+  double* bud_scr;
+  double bud_F;         // rd^-2 del1 del2
+  double bud_U;         // U1 - U2
 };
+
+// PROG_BUDGET terms (pyqg QGModel._initialize_model_diagnostics / Model._initialize_diagnostics; all / M^2)
+enum BudgetTerm { BUD_KEFLUX = 0, BUD_APEFLUX = 1, BUD_APEGEN = 2, BUD_KEFRIC = 3, BUD_ENTSPEC = 4, BUD_PARAM_KE = 5,
+                  BUD_PARAM_APE = 6 };
+constexpr int kBudgetTerms = 7;
 
 // Per-CTA context: shared-memory views + which member this CTA owns.  CN > 0 fixes the grid size at compile time
 // (the specialised step kernels of spectral.cuh: all index divisions become shifts / multiplies); CN = 0 reads it from T.
@@ -454,6 +464,138 @@ QGB_HD void ph_store_p(const C& c, int tid, int nt) {
   }
 }
 
+// ---- spectral energy budget (pyqg _calc_derived_fields + the add_diagnostic lambdas of qg_model.py) -------------------
+template <class C>
+struct GetXi {   // xi_h = -wv2 ph  (relative vorticity), both layers as one packed pair
+  const C& c; const cplx* qh;
+  QGB_HD void operator()(int l, int k, cplx& A, cplx& B) const {
+    const int idx = l * c.NK() + k;
+    const double w = -(c.T.kv[k] * c.T.kv[k] + c.T.lv[l] * c.T.lv[l]);
+    A = cscale(half_ph(c, qh, 0, idx), w);
+    B = cscale(half_ph(c, qh, 1, idx), w);
+  }
+};
+template <class C>
+struct GetTau {  // tau_h = ph0 - ph1 (paired with zero)
+  const C& c; const cplx* qh;
+  QGB_HD void operator()(int l, int k, cplx& A, cplx& B) const {
+    const int idx = l * c.NK() + k;
+    A = csub(half_ph(c, qh, 0, idx), half_ph(c, qh, 1, idx));
+    B = cmake(0.0, 0.0);
+  }
+};
+template <class C>
+struct GetUVbt {  // barotropic velocities del1 u0 + del2 u1, del1 v0 + del2 v1
+  const C& c; const cplx* qh;
+  QGB_HD void operator()(int l, int k, cplx& A, cplx& B) const {
+    cplx u0, v0, u1, v1;
+    half_uv(c, qh, 0, l, k, u0, v0);
+    half_uv(c, qh, 1, l, k, u1, v1);
+    const double d1 = c.io.Hi_over_H[0], d2 = c.io.Hi_over_H[1];
+    A = cmake(d1 * u0.x + d2 * u1.x, d1 * u0.y + d2 * u1.y);
+    B = cmake(d1 * v0.x + d2 * v1.x, d1 * v0.y + d2 * v1.y);
+  }
+};
+template <class C>
+QGB_HD void ph_build_xi(const C& c, int tid, int nt) { GetXi<C> g{c, member_qh(c)}; build_packed(c, g, tid, nt); }
+template <class C>
+QGB_HD void ph_build_tau(const C& c, int tid, int nt) { GetTau<C> g{c, member_qh(c)}; build_packed(c, g, tid, nt); }
+template <class C>
+QGB_HD void ph_build_uvbt(const C& c, int tid, int nt) { GetUVbt<C> g{c, member_qh(c)}; build_packed(c, g, tid, nt); }
+
+// scratch fields slot, slot+1 = real / imaginary part of the packed inverse transform
+template <class C>
+QGB_HD void ph_store_scr(const C& c, int slot, int nfields, int tid, int nt) {
+  const int N = c.N(), P = c.P();
+  double* f = c.io.bud_scr + ((long long)c.member * 3 + slot) * N * N;
+  const double s = c.T.inv_M;
+  for (int i = tid; i < N * N; i += nt) {
+    const int y = i / N, x = i - y * N;
+    const cplx w = c.buf[y * P + x];
+    f[i] = w.x * s;
+    if (nfields == 2) f[N * N + i] = w.y * s;
+  }
+}
+// buf = u f + i v f  with (u, v) the packed inverse transform in the buffer and f a scratch field
+template <class C>
+QGB_HD void ph_products_scr(const C& c, int slot, int tid, int nt) {
+  const int N = c.N(), P = c.P();
+  const double* f = c.io.bud_scr + ((long long)c.member * 3 + slot) * N * N;
+  const double s = c.T.inv_M;
+  for (int i = tid; i < N * N; i += nt) {
+    const int y = i / N, x = i - y * N;
+    const cplx w = c.buf[y * P + x];
+    const double ff = f[i] * s;
+    c.buf[y * P + x] = cmake(w.x * ff, w.y * ff);
+  }
+}
+// KEflux (+)= del_z Re(ph_z conj(Jpxi_z)) / M^2,  Jpxi_z = ik F(u xi) + il F(v xi)
+template <class C>
+QGB_HD void ph_bud_keflux(const C& c, int z, int tid, int nt) {
+  const int N = c.N(), NK = c.NK(), NN = N * NK;
+  const cplx* qh = member_qh(c);
+  double* out = c.io.bud_out + ((long long)c.member * kBudgetTerms + BUD_KEFLUX) * NN;
+  const double s = c.T.inv_M * c.T.inv_M * c.io.Hi_over_H[z];
+  for (int i = tid; i < NN; i += nt) {
+    const int l = i / NK, k = i - l * NK;
+    cplx a, b;
+    unpack_pair(c, l, k, a, b);
+    const cplx J = cadd(cmuli(a, c.T.kv[k]), cmuli(b, c.T.lv[l]));
+    const cplx ph = half_ph(c, qh, z, i);
+    const double v = s * (ph.x * J.x + ph.y * J.y);
+    out[i] = z == 0 ? v : out[i] + v;
+  }
+}
+// APEflux = F Re((ph0 - ph1) conj(Jptpc)) / M^2 with Jptpc = -(ik F(ubt tau) + il F(vbt tau)); plus the pointwise terms
+template <class C>
+QGB_HD void ph_bud_apeflux(const C& c, int tid, int nt) {
+  const int N = c.N(), NK = c.NK(), NN = N * NK;
+  const cplx* qh = member_qh(c);
+  double* out = c.io.bud_out + (long long)c.member * kBudgetTerms * NN;
+  const double m2 = c.T.inv_M * c.T.inv_M, d1 = c.io.Hi_over_H[0], d2 = c.io.Hi_over_H[1], F = c.io.bud_F;
+  for (int i = tid; i < NN; i += nt) {
+    const int l = i / NK, k = i - l * NK;
+    cplx a, b;
+    unpack_pair(c, l, k, a, b);
+    const cplx J = cadd(cmuli(a, c.T.kv[k]), cmuli(b, c.T.lv[l]));      // = -Jptpc
+    const cplx p0 = half_ph(c, qh, 0, i), p1 = half_ph(c, qh, 1, i);
+    const cplx t = csub(p0, p1);
+    out[BUD_APEFLUX * NN + i] = -F * m2 * (t.x * J.x + t.y * J.y);
+    // APEgenspec = U F Re(ik (del1 ph0 + del2 ph1) conj(ph0 - ph1)) / M^2
+    const cplx bt = cmake(d1 * p0.x + d2 * p1.x, d1 * p0.y + d2 * p1.y);
+    const cplx ikbt = cmuli(bt, c.T.kv[k]);
+    out[BUD_APEGEN * NN + i] = c.io.bud_U * F * m2 * (ikbt.x * t.x + ikbt.y * t.y);
+    const double wv2 = c.T.kv[k] * c.T.kv[k] + c.T.lv[l] * c.T.lv[l];
+    out[BUD_KEFRIC * NN + i] = -c.T.rek * d2 * wv2 * m2 * (p1.x * p1.x + p1.y * p1.y);
+    const cplx q0 = qh[i], q1 = qh[NN + i];
+    const cplx e = cmake(d1 * q0.x + d2 * q1.x, d1 * q0.y + d2 * q1.y);
+    out[BUD_ENTSPEC * NN + i] = m2 * (e.x * e.x + e.y * e.y);
+    out[BUD_PARAM_KE * NN + i] = 0.0;
+    out[BUD_PARAM_APE * NN + i] = 0.0;
+  }
+}
+// parameterization terms from dqh = rfft2(dq) (the buffer holds the packed forward transform of the forcing pair)
+template <class C>
+QGB_HD void ph_bud_param(const C& c, int tid, int nt) {
+  const int N = c.N(), NK = c.NK(), NN = N * NK;
+  const cplx* qh = member_qh(c);
+  double* out = c.io.bud_out + (long long)c.member * kBudgetTerms * NN;
+  const double m2 = c.T.inv_M * c.T.inv_M, d1 = c.io.Hi_over_H[0], d2 = c.io.Hi_over_H[1], F = c.io.bud_F;
+  for (int i = tid; i < NN; i += nt) {
+    const int l = i / NK, k = i - l * NK;
+    cplx f0, f1;
+    unpack_pair(c, l, k, f0, f1);
+    const double a00 = c.T.a[i], a01 = c.T.a[NN + i], a10 = c.T.a[2 * NN + i], a11 = c.T.a[3 * NN + i];
+    const cplx dp0 = cmake(a00 * f0.x + a01 * f1.x, a00 * f0.y + a01 * f1.y);
+    const cplx dp1 = cmake(a10 * f0.x + a11 * f1.x, a10 * f0.y + a11 * f1.y);
+    const cplx p0 = half_ph(c, qh, 0, i), p1 = half_ph(c, qh, 1, i);
+    const double wv2 = c.T.kv[k] * c.T.kv[k] + c.T.lv[l] * c.T.lv[l];
+    out[BUD_PARAM_KE * NN + i] = wv2 * m2 * (d1 * (p0.x * dp0.x + p0.y * dp0.y) + d2 * (p1.x * dp1.x + p1.y * dp1.y));
+    const cplx t = csub(p0, p1), dt = csub(dp0, dp1);
+    out[BUD_PARAM_APE * NN + i] = F * m2 * (t.x * dt.x + t.y * dt.y);
+  }
+}
+
 // diagnostics partials: red[0*nt+tid] ke, [1] max|u+U|, [2] max|v|, [3] non-finite count
 template <class C>
 QGB_HD void ph_red_clear(const C& c, int tid, int nt) {
@@ -512,8 +654,9 @@ QGB_HD void ph_red_final(const C& c, int tid, int nt) {
 // PROG_STEP_DQ removes the mean of dq (closure output, models/parameterization.py:25); PROG_STEP_DQ_RAW adds dq as given
 // PROG_ADVECT: d_cur = -(ik uqh + il vqh + ikQy ph) [+ friction] without time stepping (tools/operators.py:249-252 ``advect`` when
 // the tables carry Ubg = Qy = rek = 0);  PROG_C2R: q = irfft2(qh) for arbitrary half-plane spectra (tools/operators.py:132)
+// PROG_BUDGET: spectral energy budget terms of the current state (and of the closure forcing io.dq when given) -> bud_out
 enum Program { PROG_STEP = 0, PROG_STEP_DQ = 1, PROG_SET_Q = 2, PROG_INVERT = 3, PROG_DIAG = 4, PROG_EMIT_X = 5, PROG_STEP_DQ_RAW = 6,
-               PROG_ADVECT = 7, PROG_C2R = 8 };
+               PROG_ADVECT = 7, PROG_C2R = 8, PROG_BUDGET = 9 };
 
 #define QGB_RUN(stmt)        \
   do {                       \
@@ -587,6 +730,30 @@ QGB_HD int run_program(const C& c, int prog, int phase, int tid, int nt) {
     QGB_RUN(ph_red_final(c, tid, nt));
   } else if (prog == PROG_EMIT_X) {
     QGB_RUN(ph_emit_x_only(c, tid, nt));
+  } else if (prog == PROG_BUDGET) {
+    QGB_RUN(ph_build_xi(c, tid, nt));
+    QGB_FFT(true);
+    QGB_RUN(ph_store_scr(c, 0, 2, tid, nt));
+    for (int z = 0; z < 2; ++z) {
+      QGB_RUN(ph_build_uv(c, z, tid, nt));
+      QGB_FFT(true);
+      QGB_RUN(ph_products_scr(c, z, tid, nt));
+      QGB_FFT(false);
+      QGB_RUN(ph_bud_keflux(c, z, tid, nt));
+    }
+    QGB_RUN(ph_build_tau(c, tid, nt));
+    QGB_FFT(true);
+    QGB_RUN(ph_store_scr(c, 2, 1, tid, nt));
+    QGB_RUN(ph_build_uvbt(c, tid, nt));
+    QGB_FFT(true);
+    QGB_RUN(ph_products_scr(c, 2, tid, nt));
+    QGB_FFT(false);
+    QGB_RUN(ph_bud_apeflux(c, tid, nt));
+    if (c.io.dq) {
+      QGB_RUN(ph_load_pair(c, c.io.dq, tid, nt));
+      QGB_FFT(false);
+      QGB_RUN(ph_bud_param(c, tid, nt));
+    }
   }
   return _n;
 }

@@ -74,6 +74,25 @@ def ensemble_spectra(spec_sums):
     return ke / n, en / n, int(cnt[0])
 
 
+def ensemble_diagnostics(diag_sums):
+    """Ensemble- and time-mean pyqg diagnostics over ALL ranks (one all-reduce of the concatenated accumulators).
+    ``diag_sums`` = (dict name -> sum, count) as returned by ``EnsembleQGModel.diagnostic_sums()``; returns
+    (dict name -> mean incl. ``paramspec``, total count)."""
+    d, count = diag_sums
+    names = sorted(d)
+    flat = np.concatenate([np.asarray(d[k], dtype=np.float64).ravel() for k in names] + [np.array([float(count)])])
+    red = allreduce_sum([flat])[0]
+    n = max(red[-1], 1.0)
+    out, o = {}, 0
+    for k in names:
+        sz = int(np.prod(np.shape(d[k])))
+        out[k] = (red[o:o + sz] / n).reshape(np.shape(d[k]))
+        o += sz
+    if 'paramspec_KEflux' in out:
+        out['paramspec'] = out['paramspec_KEflux'] + out['paramspec_APEflux']
+    return out, int(red[-1])
+
+
 def ensemble_ke(ke_members):
     """Ensemble-mean kinetic energy over all ranks from the per-member values of the local shard."""
     s, c = allreduce_sum([np.array([np.nansum(ke_members)]), np.array([float(np.isfinite(ke_members).sum())])])

@@ -40,6 +40,10 @@ def snapshot(m):
                 psi=np.asarray(m.p, 'float32'), time=np.float64(m.t / 86400.))
 
 
+SPECTRAL_VARS = ('KEspec', 'Ensspec', 'KEflux', 'APEflux', 'APEgenspec', 'KEfrictionspec', 'entspec', 'paramspec',
+                 'paramspec_KEflux', 'paramspec_APEflux')
+
+
 def concat_in_time(snaps):
     out = {k: np.stack([s[k] for s in snaps], axis=1 if np.ndim(snaps[0][k]) else 0) for k in ('q', 'u', 'v', 'psi')}
     out['time'] = np.array([s['time'] for s in snaps])
@@ -54,9 +58,9 @@ def to_xarray(d, attrs=None):
         return d
     ds = xr.Dataset({k: xr.DataArray(d[k], dims=['run', 'time', 'lev', 'y', 'x']) for k in ('q', 'u', 'v', 'psi')})
     ds['time'] = xr.DataArray(d['time'], dims=['time'], attrs={'units': 'days'})
-    for k in ('KEspec', 'Ensspec'):
+    for k in SPECTRAL_VARS:
         if k in d:
-            ds[k] = xr.DataArray(d[k], dims=['lev', 'l', 'k'])
+            ds[k] = xr.DataArray(d[k], dims=['lev', 'l', 'k'] if np.ndim(d[k]) == 3 else ['l', 'k'])
     ds.attrs.update(attrs or {})
     return ds
 
@@ -81,9 +85,7 @@ def run_simulation(pyqg_params, parameterization=None, q_init=None, sampling_fre
     for t in m.run_with_snapshots(tsnapint=sampling_freq):
         snaps.append(snapshot(m))
     ds = concat_in_time(snaps)
-    ke, en, count = m.spectra_sums()
-    if count:
-        ds['KEspec'], ds['Ensspec'] = ke / count, en / count
+    ds.update(m.averaged_diagnostics())      # KEspec, Ensspec, KEflux, APEflux, APEgenspec, KEfrictionspec, paramspec*, entspec
     ds['attrs'] = {'pyqg_params': str(pyqg_params)}
     ds['model'] = m
     return ds

@@ -126,6 +126,7 @@ class EnsembleQGModel(object):
         self._cfg = cfg
         self._h = ctypes.c_void_p()
         _lib.check(self._lib.qgb_create(ctypes.byref(cfg), ctypes.byref(self._h)))
+        _lib.check(self._lib.qgb_diag_config(self._h, self.tavestart, self.taveint), self._h)
 
         self.t, self.tc = 0.0, 0
         self.sampling_type = sampling_type
@@ -136,7 +137,6 @@ class EnsembleQGModel(object):
         self._pv_host = None
         self.q_parameterization = None
         self.diag_count = 0
-        self._kespec = self._ensspec = None
         if sampling_type not in _SAMPLERS:
             raise ValueError('Unknown sampling type')
         self._nsteps = nsteps
@@ -374,18 +374,9 @@ class EnsembleQGModel(object):
         if self.log_level and self.twrite:
             tw = int(self.twrite)
             nxt = min(nxt, (self.tc // tw + 1) * tw)
-        tav = int(np.ceil(self.taveint / self.dt))
-        s = (self.tc // tav + 1) * tav
-        s0 = int(np.ceil(self.tavestart / self.dt))      # first step count with t >= tavestart
-        if s < s0:
-            s = ((s0 + tav - 1) // tav) * tav
-        nxt = min(nxt, s)
-        return max(1, nxt - self.tc)
+        return max(1, nxt - self.tc)      # (time-averaged diagnostics are sampled on the device inside qgb_step)
 
     def _after_step(self):
-        tav = int(np.ceil(self.taveint / self.dt))
-        if self.t >= self.tavestart and self.tc % tav == 0:
-            self._accumulate_spectra()
         if self.log_level and self.twrite and self.tc % int(self.twrite) == 0:
             self._print_status()
 
@@ -414,24 +405,49 @@ class EnsembleQGModel(object):
         if self.squeeze:
             assert cfl[0] < 1., 'CFL condition violated'
 
-    def _accumulate_spectra(self):
-        n = 2 * self.nl * self.nk
-        ke = np.empty(n)
-        en = np.empty(n)
-        _lib.check(self._lib.qgb_diag_spectra(self._h, ke.ctypes.data, en.ctypes.data, 0, self._stream()), self._h)
-        if self._kespec is None:
-            self._kespec, self._ensspec = np.zeros(n), np.zeros(n)
-        self._kespec += ke
-        self._ensspec += en
-        self.diag_count += 1
+    # ---- pyqg time-averaged diagnostics (Model tavestart / taveint; sampled on the device before each eligible step) ----
+    DIAG_LAYERED = ('KEspec', 'Ensspec')
+    DIAG_BUDGET = ('KEflux', 'APEflux', 'APEgenspec', 'KEfrictionspec', 'entspec', 'paramspec_KEflux', 'paramspec_APEflux')
+
+    def _split_terms(self, a, first):
+        a = a.reshape((-1, self.nl, self.nk))
+        return {name: a[first + i] for i, name in enumerate(self.DIAG_BUDGET)}
+
+    def budget_sums(self):
+        """Spectral energy budget of the CURRENT state summed over the local members: dict name -> (nl, nk)
+        (pyqg diagnostics KEflux, APEflux, APEgenspec, KEfrictionspec, entspec, paramspec_KEflux, paramspec_APEflux;
+        consumers: tools/comparison_tools.py:91,164-189,222-263)."""
+        out = np.empty(len(self.DIAG_BUDGET) * self.nl * self.nk)
+        _lib.check(self._lib.qgb_diag_budget(self._h, out.ctypes.data, 0, self._stream()), self._h)
+        return self._split_terms(out, 0)
+
+    def diagnostic_sums(self):
+        """(dict name -> sum over local members and averaging times, count = members * samples): the accumulators that
+        ``parallel.ensemble_diagnostics`` all-reduces.  KEspec / Ensspec are (2, nl, nk), the budget terms (nl, nk)."""
+        n = (4 + len(self.DIAG_BUDGET)) * self.nl * self.nk
+        out = np.empty(n)
+        ns = ctypes.c_int64(0)
+        _lib.check(self._lib.qgb_diag_averages(self._h, out.ctypes.data, ctypes.byref(ns), 0, 0, self._stream()), self._h)
+        a = out.reshape((-1, self.nl, self.nk))
+        d = {'KEspec': a[0:2].copy(), 'Ensspec': a[2:4].copy()}
+        d.update({k: v.copy() for k, v in self._split_terms(out, 4).items()})
+        self.diag_count = int(ns.value)
+        return d, int(ns.value) * self.members
+
+    def averaged_diagnostics(self):
+        """Ensemble- (local members) and time-mean diagnostics like pyqg's ``m.get_diagnostic``; adds ``paramspec``."""
+        d, count = self.diagnostic_sums()
+        if not count:
+            return {}
+        out = {k: v / count for k, v in d.items()}
+        out['paramspec'] = out['paramspec_KEflux'] + out['paramspec_APEflux']
+        return out
 
     def spectra_sums(self):
         """(KEspec_sum, Ensspec_sum, count): sums over local members and averaging times, shape (2,nl,nk);
         ``count`` = members * samples.  These are the accumulators all-reduced over NCCL (parallel.py)."""
-        shp = (2, self.nl, self.nk)
-        if self._kespec is None:
-            return np.zeros(shp), np.zeros(shp), 0
-        return self._kespec.reshape(shp), self._ensspec.reshape(shp), self.diag_count * self.members
+        d, count = self.diagnostic_sums()
+        return d['KEspec'], d['Ensspec'], count
 
     def run_with_snapshots(self, tsnapstart=0., tsnapint=432000.):
         tsnapints = int(np.ceil(tsnapint / self.dt))

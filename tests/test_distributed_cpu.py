@@ -28,6 +28,11 @@ def _worker(rank, world, port, total, out):
     kem, enm, n = parallel.ensemble_spectra((ke, en, count))
     kbar = parallel.ensemble_ke(np.array([float(m) for m in members]))
     tmax = parallel.allreduce_max(10.0 + r)
+    # the full pyqg diagnostic set travels as ONE bucket: dict of sums + count -> dict of ensemble means (+ paramspec)
+    sums = {'KEspec': ke, 'KEflux': ke[0] * 2, 'paramspec_KEflux': ke[0], 'paramspec_APEflux': -0.25 * ke[0]}
+    dmean, dn = parallel.ensemble_diagnostics((sums, count))
+    assert dn == n and abs(dmean['KEflux'][0, 0] - 2 * kem[0, 0, 0]) < 1e-12
+    assert abs(dmean['paramspec'][0, 0] - 0.75 * kem[0, 0, 0]) < 1e-12 and dmean['KEspec'].shape == (2, 8, 5)
     out[rank] = (kem[0, 0, 0], enm[0, 0, 0], n, kbar, tmax, count, offset)
     dist.barrier()
     dist.destroy_process_group()

@@ -20,11 +20,11 @@ def _p(a):
 
 
 def run(lib, cfg, prog, qh, q, dcur=None, dp=None, dpp=None, dq=None, x=None, ab=2, ph=None, u=None, v=None, p=None,
-        red=None, nt=96):
+        red=None, nt=96, bud=None, scr=None):
     lib.qgbemu_run.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 7 + \
-        [ctypes.c_float, ctypes.c_float, ctypes.c_int] + [ctypes.c_void_p] * 5
+        [ctypes.c_float, ctypes.c_float, ctypes.c_int] + [ctypes.c_void_p] * 7
     assert lib.qgbemu_run(ctypes.byref(cfg), prog, nt, _p(qh), _p(q), _p(dcur), _p(dp), _p(dpp), _p(dq), _p(x),
-                          7.78e-6, 1.05e-6, ab, _p(ph), _p(u), _p(v), _p(p), _p(red)) == 0
+                          7.78e-6, 1.05e-6, ab, _p(ph), _p(u), _p(v), _p(p), _p(red), _p(bud), _p(scr)) == 0
 
 
 def rel(a, b):
@@ -97,3 +97,36 @@ def test_raw_forcing_program_keeps_the_mean(emu_lib):
     m._step_forward()
     assert rel(qh[0], m.qh) < 1e-13
     assert abs(q[0, 0].mean() - m.q[0].mean()) < 1e-20
+
+
+BUDGET_TERMS = ['KEflux', 'APEflux', 'APEgenspec', 'KEfrictionspec', 'entspec', 'paramspec_KEflux', 'paramspec_APEflux']
+
+
+@pytest.mark.parametrize('N,jet', [(64, False), (48, True), (32, False)])
+def test_budget_program_matches_oracle(emu_lib, N, jet):
+    """PROG_BUDGET (spectral energy budget terms) against the oracle's restatement of the pyqg diagnostics."""
+    rng = np.random.RandomState(7 + N)
+    dt = 7200.
+    phys = dict(rek=7e-8, delta=0.1, beta=1e-11) if jet else dict(rek=5.787e-7, delta=0.25, beta=1.5e-11)
+    B = 2
+    dq = rng.randn(B, 2, N, N) * np.array([7e-12, 2e-13])[None, :, None, None]
+
+    class Par(pyqg_shim.QParameterization):
+        def __call__(self, mm):
+            return dq[1] - dq[1].mean(axis=(1, 2), keepdims=True)
+    m = pyqg_shim.QGModel(nx=N, dt=dt, log_level=0, q_parameterization=Par(), **phys)
+    cfg = Cfg(N, B, 0, 0, 1e6, dt, phys['rek'], 23.6, phys['beta'], 15000., phys['delta'], 500., 0.025, 0.)
+    q0 = rng.randn(B, 2, N, N) * np.array([7e-6, 1e-6])[None, :, None, None]
+    qh = np.zeros((B, 2, N, N // 2 + 1), complex)
+    q = q0.copy()
+    run(emu_lib, cfg, 2, qh, q)
+    bud = np.zeros((B, len(BUDGET_TERMS), N, N // 2 + 1))
+    scr = np.zeros((B, 3, N, N))
+    run(emu_lib, cfg, 9, qh, q, dq=dq.copy(), bud=bud, scr=scr)               # PROG_BUDGET
+    m.q = q0[1]
+    m._invert()
+    m._do_q_subgrid_parameterization()
+    d = m.diagnostic_fields()
+    for i, name in enumerate(BUDGET_TERMS):
+        assert rel(bud[1, i], d[name]) < 1e-12, name
+    assert rel(bud[1, 5] + bud[1, 6], d['paramspec']) < 1e-12

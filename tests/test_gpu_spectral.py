@@ -115,7 +115,8 @@ def test_run_with_snapshots_cadence_and_log():
     assert np.allclose(times, [8 * dt * i for i in range(1, 6)])
     assert [s for s, _, _, _ in m.log] == [10, 20, 30, 40]
     ke, en, count = m.spectra_sums()
-    assert count == 2 * 5 and ke.shape == (2, N, N // 2 + 1) and (ke >= 0).all()
+    # pyqg samples BEFORE the step when t >= tavestart and tc % taveints == 0: tc = 20, 25, 30, 35 (no step starts at 40)
+    assert count == 2 * 4 and ke.shape == (2, N, N // 2 + 1) and (ke >= 0).all()
     kespec = 0
     for b in range(2):
         o = pyqg_shim.QGModel(nx=N, dt=dt, log_level=0)
@@ -183,3 +184,59 @@ def test_host_buffer_stepping_sync_and_pipelined():
         st.synchronize()
     got = np.concatenate([g[2].numpy() for g in groups])
     assert np.array_equal(got, ref.q)
+
+
+BUDGET = ('KEflux', 'APEflux', 'APEgenspec', 'KEfrictionspec', 'entspec', 'paramspec_KEflux', 'paramspec_APEflux')
+
+
+@pytest.mark.parametrize('N,dt,phys', [(64, 14400., {}), (48, 7200., dict(rek=7e-8, delta=0.1, beta=1e-11)), (128, 7200., {})])
+def test_spectral_energy_budget_matches_oracle(N, dt, phys):
+    """qgb_diag_budget (PROG_BUDGET) against the oracle's restatement of the pyqg diagnostics, with an
+    external forcing standing in for the closure output (paramspec terms).  Sum over members, tolerance 1e-10."""
+    rng = np.random.RandomState(N + 1)
+    B = 3
+    m = make(N, B, dt=dt, **phys)
+    q0 = rng.randn(B, 2, N, N) * np.array([7e-6, 1e-6])[None, :, None, None]
+    dq = rng.randn(2, N, N) * np.array([7e-12, 2e-13])[:, None, None]
+    dq -= dq.mean(axis=(1, 2), keepdims=True)
+    m.q = q0
+    m.set_parameterization(_OracleConst(dq), 'AR1', 1)      # host callback -> qgb_set_forcing -> PROG_STEP_DQ_RAW
+    m._step_forward()
+    terms = m.budget_sums()
+    q1 = m.q
+    ref = {k: 0 for k in BUDGET + ('paramspec',)}
+    for b in range(B):
+        o = pyqg_shim.QGModel(nx=N, dt=dt, log_level=0, q_parameterization=_OracleConst(dq), **phys)
+        o.q = q1[b]
+        o._invert()
+        o._do_q_subgrid_parameterization()
+        d = o.diagnostic_fields()
+        for k in ref:
+            ref[k] = ref[k] + d[k]
+    for k in BUDGET:
+        assert rel(terms[k], ref[k]) < TOL, k
+    assert rel(terms['paramspec_KEflux'] + terms['paramspec_APEflux'], ref['paramspec']) < TOL
+
+
+def test_time_averaged_diagnostics_follow_pyqg_sampling():
+    """Device-side running sums (qgb_diag_config / qgb_diag_averages) against the oracle's _calc_diagnostics running mean."""
+    N, dt, B = 32, 14400., 2
+    rng = np.random.RandomState(5)
+    kw = dict(dt=dt, tavestart=2 * dt, taveint=2 * dt, tmax=1e12)
+    m = make(N, B, **kw)
+    q0 = rng.randn(B, 2, N, N) * np.array([7e-6, 1e-6])[None, :, None, None]
+    m.q = q0
+    m._step_forward(9)
+    avg = m.averaged_diagnostics()
+    refs = []
+    for b in range(B):
+        o = pyqg_shim.QGModel(nx=N, log_level=0, **kw)
+        o.q = q0[b]
+        for _ in range(9):
+            o._step_forward()
+        refs.append(o)
+    assert m.diag_count == refs[0].diag_count == 4           # sampled before the steps starting at tc = 2, 4, 6, 8
+    for k in ('KEspec', 'Ensspec', 'KEflux', 'APEflux', 'APEgenspec', 'KEfrictionspec', 'entspec'):
+        ref = sum(o.diag[k] for o in refs) / B
+        assert rel(avg[k], ref) < 1e-9, k
+    assert np.abs(avg['paramspec']).max() == 0.0
