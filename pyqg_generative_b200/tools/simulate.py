@@ -3,15 +3,16 @@
 ``run_simulation(pyqg_params, parameterization, q_init, sampling_freq)`` (:108-145) and
 ``set_initial_condition(m)`` (:147-168) keep the reference signatures; ``pyqg_params`` may additionally carry
 ``members`` (ensemble size on this GPU), ``member_offset``, ``device``, ``precision`` and ``seed``.
-xarray / NetCDF export (to_dataset, drop_vars, concat_in_time :16-60) is a "next" row: snapshots
-are returned as a dict of numpy arrays with the same variable names and a leading ``run`` axis, float32 like
-``drop_vars`` produces, and become an xarray.Dataset when xarray is importable.
+Snapshots are returned as a dict of numpy arrays with the variable names ``drop_vars(m.to_dataset())`` keeps (:16-60), a
+leading ``run`` axis and float32 precision; ``tools/dataset.py`` writes them as NetCDF files in the reference's layout
+(one ``<n>.nc`` per run) and ``to_xarray`` wraps them when xarray is importable.
 """
 import json
 import os
 
 import numpy as np
 
+from .dataset import model_coords, write_runs
 from .parameters import ANDREW_1000_STEPS, DAY
 from .stochastic_pyqg import EnsembleQGModel, stochastic_QGModel
 
@@ -86,7 +87,9 @@ def run_simulation(pyqg_params, parameterization=None, q_init=None, sampling_fre
         snaps.append(snapshot(m))
     ds = concat_in_time(snaps)
     ds.update(m.averaged_diagnostics())      # KEspec, Ensspec, KEflux, APEflux, APEgenspec, KEfrictionspec, paramspec*, entspec
-    ds['attrs'] = {'pyqg_params': str(pyqg_params)}
+    coords, attrs = model_coords(m)
+    ds['coords'] = coords
+    ds['attrs'] = dict(attrs, pyqg_params=str(pyqg_params))
     ds['model'] = m
     return ds
 
@@ -168,20 +171,21 @@ def main(argv=None):
         ds = {k: v for k, v in ds.items() if isinstance(v, np.ndarray)}
         np.savez_compressed(path, **ds)
 
+    def save_runs(ds, folder):          # <ensemble_member + i>.nc like the reference (:249-263)
+        write_runs(ds, folder or '.', first=args.ensemble_member)
+
     if args.forcing == 'yes':
         out = generate_subgrid_forcing([32, 48, 64, 96, 128], params, args.sampling_freq)
         for key, ds in out.items():
             os.makedirs(key, exist_ok=True)
             save(ds, os.path.join(key, '%d.npz' % args.ensemble_member))
     if args.reference == 'yes':
-        save(run_simulation(params, sampling_freq=args.sampling_freq),
-             os.path.join(args.subfolder, '%d.npz' % args.ensemble_member))
+        save_runs(run_simulation(params, sampling_freq=args.sampling_freq), args.subfolder)
     if args.parameterization == 'yes':
         params['precision'] = args.precision
         model = args.model_weight * _load_model(args.model_folder)
         par = dict(self=model, sampling=args.sampling, nsteps=args.nsteps)
-        save(run_simulation(params, par, sampling_freq=args.sampling_freq),
-             os.path.join(args.subfolder, '%d.npz' % args.ensemble_member))
+        save_runs(run_simulation(params, par, sampling_freq=args.sampling_freq), args.subfolder)
 
 
 if __name__ == '__main__':

@@ -1,4 +1,5 @@
 """Host-side logic that needs no GPU: configuration tables, samplers, weight packing (BatchNorm folding), sharding."""
+import os
 import numpy as np
 import pytest
 import torch
@@ -114,3 +115,34 @@ def test_isotropic_spectrum_integrates_to_total():
     kr, s = calc_ispec(m.k, m.l, spec, averaging=False)
     inside = m.wv < kr[-1] + (kr[1] - kr[0]) / 2
     assert abs(s.sum() * (kr[1] - kr[0]) - spec[inside & (m.wv >= (kr[0] - (kr[1] - kr[0]) / 2))].sum()) < 1e-9 * spec.sum()
+
+
+def test_netcdf_writer_layout_matches_reference_files(tmp_path):
+    """tools/dataset.py: one <n>.nc per run with the variables / dims / dtypes / units that
+    drop_vars + concat_in_time produce (pyqg_generative/tools/simulate.py:16-60,138-145)."""
+    from pyqg_generative_b200.tools import dataset
+    rng = np.random.RandomState(0)
+    R, T, N = 3, 4, 16
+    ds = {k: rng.randn(R, T, 2, N, N).astype('float32') for k in dataset.PHYSICAL}
+    ds['time'] = np.arange(1, T + 1) * 41.6666666667
+    ds['KEspec'] = rng.rand(2, N, N // 2 + 1)
+    ds['KEflux'] = rng.randn(N, N // 2 + 1)
+    ds['paramspec'] = rng.randn(N, N // 2 + 1)
+    ds['coords'] = dict(x=(np.arange(N) + .5) * 1e6 / N, y=(np.arange(N) + .5) * 1e6 / N, lev=np.array([1, 2]),
+                        l=np.fft.fftfreq(N, 1. / N) * 2 * np.pi / 1e6, k=np.arange(N // 2 + 1) * 2 * np.pi / 1e6,
+                        Ubg=np.array([0.025, 0.]), Qy=np.array([1e-10, 2e-11]))
+    ds['attrs'] = {'pyqg_params': str(dict(nx=N, dt=3600.)), 'pyqg:beta': 1.5e-11}
+    paths = dataset.write_runs(ds, str(tmp_path / 'runs'), first=5)
+    assert [os.path.basename(p) for p in paths] == ['5.nc', '6.nc', '7.nc']
+    d = dataset.read_netcdf(paths[1])
+    assert d['dims'] == {'time': T, 'lev': 2, 'y': N, 'x': N, 'l': N, 'k': N // 2 + 1}
+    for k in dataset.PHYSICAL:
+        assert d[k].dtype == np.float32 and d['var_dims'][k] == ('time', 'lev', 'y', 'x')
+        assert np.array_equal(d[k], ds[k][1])
+    assert d['var_attrs']['time']['units'] == b'days' and np.allclose(d['time'], ds['time'])
+    assert d['var_dims']['KEspec'] == ('lev', 'l', 'k') and d['var_dims']['KEflux'] == ('l', 'k')
+    assert np.allclose(d['KEspec'], ds['KEspec'].astype('float32')) and d['KEspec'].dtype == np.float32
+    assert d['attrs']['pyqg_params'] == str(dict(nx=N, dt=3600.)) and abs(d['attrs']['pyqg:beta'] - 1.5e-11) < 1e-25
+    assert np.allclose(d['Ubg'], [0.025, 0.]) and np.allclose(d['x'], ds['coords']['x'])
+    one = dataset.read_netcdf(dataset.write_netcdf(ds, str(tmp_path / 'all.nc')))
+    assert one['var_dims']['q'] == ('run', 'time', 'lev', 'y', 'x') and np.array_equal(one['q'], ds['q'])
