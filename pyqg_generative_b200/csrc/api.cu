@@ -58,6 +58,7 @@ struct qgb_handle {
   bool fixed = false;   // compile-time specialised step kernel available for this nx
   int nt64 = 384;
   bool large = false; cplx* scratch = nullptr; double* red_scratch = nullptr;   // cluster path for nx > 96
+  int large_lines = 0; size_t large_smem = 0;   // lines of a 1-D FFT pass staged per CTA in shared memory
   // closure
   int kind = QGB_CLOSURE_NONE; int precision = QGB_PREC_FP32;
   DevNet nets[2];
@@ -131,7 +132,7 @@ int launch_program(qgb_handle* h, const StepIO& io, int prog, cudaStream_t st, c
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(h->grid);
     cfg.blockDim = dim3(h->nthreads);
-    cfg.dynamicSmemBytes = 0;
+    cfg.dynamicSmemBytes = h->large_smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -140,7 +141,8 @@ int launch_program(qgb_handle* h, const StepIO& io, int prog, cudaStream_t st, c
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    CUDA_TRY(h, cudaLaunchKernelEx(&cfg, qg_program_cluster_kernel, TT, io, prog, h->cfg.members, h->scratch, h->red_scratch));
+    CUDA_TRY(h, cudaLaunchKernelEx(&cfg, qg_program_cluster_kernel, TT, io, prog, h->cfg.members, h->scratch, h->red_scratch,
+                                   h->large_lines));
     QGB_COUNT_LAUNCH();
     return QGB_OK;
   }
@@ -476,6 +478,22 @@ int qgb_create(const qgb_config* cfg, qgb_handle** out) {
   if (h->large) {
     // one cluster of kClusterSize CTAs per member, persistent over members when the ensemble exceeds the machine
     h->nthreads = 512;
+    // lines of a 1-D transform pass that a CTA stages in shared memory at a time: all it owns (N / cluster size) when that
+    // leaves room for two CTAs per SM (<= 110 KB), else the largest power-of-two fraction that does
+    const int per_cta = h->ht.N / kClusterSize;
+    const size_t line_bytes = (size_t)(h->ht.N + 1) * sizeof(cplx);
+    int lines = per_cta;
+    while (lines > 1 && lines * line_bytes > 110 * 1024) lines /= 2;
+    if (const char* e = getenv("QGB_LARGE_LINES")) { int v = atoi(e); if (v >= 1 && v <= per_cta && v * line_bytes <= 200 * 1024) lines = v; }
+    h->large_lines = lines;
+    h->large_smem = lines * line_bytes;
+    {
+      static size_t cluster_smem_limit = 0;
+      if (h->large_smem > cluster_smem_limit) {
+        CR(cudaFuncSetAttribute(qg_program_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->large_smem));
+        cluster_smem_limit = h->large_smem;
+      }
+    }
     int clusters = (2 * h->nsm) / kClusterSize;
     if (clusters > cfg->members) clusters = cfg->members;
     if (clusters < 1) clusters = 1;

@@ -103,6 +103,10 @@ struct CtxT {
   short* pos;     // [N]   shared copy of the position map
   double* red;    // [4*nthreads] reduction scratch (diagnostic program only)
   int member;
+  // thread-block-cluster path (N >= 128): the field lives in global memory; a 1-D pass of the 2-D transform stages the
+  // lines owned by this CTA through ``tile`` (shared memory, tile_lines x (N+1)) and runs all its stages locally
+  cplx* tile = nullptr;
+  int tile_lines = 0, ncta = 1;
   QGB_HD int N() const { return CN ? CN : T.N; }
   QGB_HD int NK() const { return CN ? CN / 2 + 1 : T.NK; }
   QGB_HD int P() const { return CN ? CN + 1 : T.P; }
@@ -181,10 +185,53 @@ QGB_HD void fft_stage(cplx* buf, const cplx* tw, int N, int es, int ls, int nlin
 // number of barrier-separated phases of one 2-D transform
 QGB_HD int fft2d_phases(const Tables& T) { return 2 * T.nstages; }
 
+#ifdef __CUDACC__
+// One whole 1-D pass (all radix stages) of the 2-D transform for a field in global memory, cluster path.  The lines of
+// the pass are dealt to the CTAs of the cluster (rows for the x pass, columns for the y pass); each CTA copies its lines
+// into shared memory (coalesced: contiguous rows, or 16-byte elements of adjacent columns), runs the stages with block
+// barriers only and writes the lines back.  A 2-D transform is 2 cluster phases instead of 2 * nstages, and the stages
+// run at shared-memory speed instead of one L2 round trip per butterfly.
+template <class C>
+__device__ void fft2d_pass_tiled(const C& c, int pass, bool inverse, int tid, int nt) {
+  const Tables& T = c.T;
+  const int N = c.N(), P = c.P(), TP = N + 1;
+  const int ntc = nt / c.ncta, rank = tid / ntc, lt = tid - rank * ntc;
+  const int per_cta = N / c.ncta;                 // lines owned by this CTA
+  cplx* tile = c.tile;
+  for (int l0 = 0; l0 < per_cta; l0 += c.tile_lines) {
+    const int L = per_cta - l0 < c.tile_lines ? per_cta - l0 : c.tile_lines;
+    const int first = rank * per_cta + l0;
+    for (int i = lt; i < L * N; i += ntc) {
+      int line, e;
+      if (pass == 0) { line = i / N; e = i - line * N; } else { e = i / L; line = i - e * L; }
+      tile[line * TP + e] = pass == 0 ? c.buf[(first + line) * P + e] : c.buf[e * P + first + line];
+    }
+    __syncthreads();
+    for (int si = 0; si < T.nstages; ++si) {
+      const int s = inverse ? T.nstages - 1 - si : si;
+      int n = N;
+      for (int j = 0; j < s; ++j) n /= T.radix[j];
+      fft_stage(tile, c.tw, N, 1, TP, L, T.radix[s], n, inverse, lt, ntc);
+      __syncthreads();
+    }
+    for (int i = lt; i < L * N; i += ntc) {
+      int line, e;
+      if (pass == 0) { line = i / N; e = i - line * N; } else { e = i / L; line = i - e * L; }
+      if (pass == 0) c.buf[(first + line) * P + e] = tile[line * TP + e];
+      else c.buf[e * P + first + line] = tile[line * TP + e];
+    }
+    __syncthreads();
+  }
+}
+#endif
+
 // phase ``ph`` (0 .. 2*nstages-1) of the 2-D transform of the whole N x N buffer
 template <class C>
 QGB_HD void fft2d_phase(const C& c, int ph, bool inverse, int tid, int nt) {
   const Tables& T = c.T;
+#ifdef __CUDA_ARCH__
+  if (c.tile) { fft2d_pass_tiled(c, ph, inverse, tid, nt); return; }
+#endif
   const int S = T.nstages;
   const int pass = ph / S;  // 0: along x (rows), 1: along y (columns)
   int s = ph - pass * S;
@@ -671,7 +718,7 @@ enum Program { PROG_STEP = 0, PROG_STEP_DQ = 1, PROG_SET_Q = 2, PROG_INVERT = 3,
 template <class C>
 QGB_HD int run_program(const C& c, int prog, int phase, int tid, int nt) {
   int _n = 0;
-  const int F = fft2d_phases(c.T);
+  const int F = c.tile ? 2 : fft2d_phases(c.T);
   QGB_RUN(ph_init(c, tid, nt));
   const bool with_dq = prog == PROG_STEP_DQ || prog == PROG_STEP_DQ_RAW;
   if (prog == PROG_STEP || with_dq) {

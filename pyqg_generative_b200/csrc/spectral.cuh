@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(NT) qg_step_fixed_kernel(const __grid_constant
 // programs run with the working field in a per-member global-memory scratch (L2 resident: 64 members x 1 MB at 256^2)
 // and a thread-block CLUSTER of kClusterSize CTAs per member.  Threads are numbered across the cluster, phases are separated
 // by the hardware cluster barrier (release/acquire at cluster scope, which also invalidates L1), tables are read in place.
+// The 1-D passes of the transforms run per CTA in shared memory (fft2d_pass_tiled): 2 cluster phases per 2-D transform.
 constexpr int kClusterSize = 8;
 
 __device__ __forceinline__ void cluster_barrier() {
@@ -131,13 +132,14 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 
 __global__ void __launch_bounds__(512) qg_program_cluster_kernel(const __grid_constant__ Tables T,
                                                                  const __grid_constant__ StepIO io, int prog, int members,
-                                                                 cplx* scratch, double* red_scratch) {
+                                                                 cplx* scratch, double* red_scratch, int tile_lines) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   const int rank = (int)cluster_ctarank();
   const int ncl = gridDim.x / kClusterSize, cl = blockIdx.x / kClusterSize;
   const int tid = rank * blockDim.x + threadIdx.x, nt = kClusterSize * blockDim.x;
   for (int m = cl; m < members; m += ncl) {
     Ctx c{T, io, scratch + (size_t)m * T.N * T.P, const_cast<cplx*>(T.tw), const_cast<short*>(T.pos),
-          red_scratch + (size_t)m * 4 * nt, m};
+          red_scratch + (size_t)m * 4 * nt, m, reinterpret_cast<cplx*>(smem_raw), tile_lines, kClusterSize};
     const int nph = run_program(c, prog, -1, tid, nt);
     for (int ph = 0; ph < nph; ++ph) {
       run_program(c, prog, ph, tid, nt);
