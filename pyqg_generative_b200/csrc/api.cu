@@ -43,7 +43,7 @@ struct qgb_handle {
   Tables T;
   std::string err;
   // device tables
-  cplx* d_tw = nullptr; short* d_pos = nullptr; double *d_kv = nullptr, *d_lv = nullptr, *d_a = nullptr, *d_filtr = nullptr;
+  cplx* d_tw = nullptr; short* d_pos = nullptr; short* d_pos_id = nullptr; double *d_kv = nullptr, *d_lv = nullptr, *d_a = nullptr, *d_filtr = nullptr;
   // state
   cplx* qh = nullptr; double* q = nullptr; cplx* hist[3] = {nullptr, nullptr, nullptr};
   cplx* ph = nullptr; double *u = nullptr, *v = nullptr, *p = nullptr, *red = nullptr;
@@ -141,8 +141,12 @@ int launch_program(qgb_handle* h, const StepIO& io, int prog, cudaStream_t st, c
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    CUDA_TRY(h, cudaLaunchKernelEx(&cfg, qg_program_cluster_kernel, TT, io, prog, h->cfg.members, h->scratch, h->red_scratch,
-                                   h->large_lines));
+    // compile-time grid size for the power-of-two production sizes (index arithmetic folds to shifts), generic otherwise
+    auto kern = h->ht.N == 128 ? qg_program_cluster_kernel<128> : h->ht.N == 256 ? qg_program_cluster_kernel<256>
+              : h->ht.N == 512 ? qg_program_cluster_kernel<512> : h->ht.N == 1024 ? qg_program_cluster_kernel<1024>
+                                                                                  : qg_program_cluster_kernel<0>;
+    CUDA_TRY(h, cudaLaunchKernelEx(&cfg, kern, TT, io, prog, h->cfg.members, h->scratch, h->red_scratch, h->large_lines,
+                                   (const short*)h->d_pos));
     QGB_COUNT_LAUNCH();
     return QGB_OK;
   }
@@ -486,11 +490,15 @@ int qgb_create(const qgb_config* cfg, qgb_handle** out) {
     while (lines > 1 && lines * line_bytes > 110 * 1024) lines /= 2;
     if (const char* e = getenv("QGB_LARGE_LINES")) { int v = atoi(e); if (v >= 1 && v <= per_cta && v * line_bytes <= 200 * 1024) lines = v; }
     h->large_lines = lines;
-    h->large_smem = lines * line_bytes;
+    h->large_smem = lines * line_bytes + (size_t)h->ht.N * sizeof(short) + 16;
     {
       static size_t cluster_smem_limit = 0;
       if (h->large_smem > cluster_smem_limit) {
-        CR(cudaFuncSetAttribute(qg_program_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->large_smem));
+        CR(cudaFuncSetAttribute(qg_program_cluster_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->large_smem));
+        CR(cudaFuncSetAttribute(qg_program_cluster_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->large_smem));
+        CR(cudaFuncSetAttribute(qg_program_cluster_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->large_smem));
+        CR(cudaFuncSetAttribute(qg_program_cluster_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->large_smem));
+        CR(cudaFuncSetAttribute(qg_program_cluster_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->large_smem));
         cluster_smem_limit = h->large_smem;
       }
     }
@@ -507,7 +515,12 @@ int qgb_create(const qgb_config* cfg, qgb_handle** out) {
   CR(upload(&h->d_lv, h->ht.lv));
   CR(upload(&h->d_a, h->ht.a));
   CR(upload(&h->d_filtr, h->ht.filtr));
-  fill_tables(h->ht, h->T, h->d_tw, h->d_pos, h->d_kv, h->d_lv, h->d_a, h->d_filtr);
+  if (h->large) {   // cluster path: the global field is kept in natural order, the stages' digit reversal stays inside the tiles
+    std::vector<short> ident(h->ht.N);
+    for (int i = 0; i < h->ht.N; ++i) ident[i] = (short)i;
+    CR(upload(&h->d_pos_id, ident));
+  }
+  fill_tables(h->ht, h->T, h->d_tw, h->large ? h->d_pos_id : h->d_pos, h->d_kv, h->d_lv, h->d_a, h->d_filtr);
   const size_t nr = nreal(h), nc = ncplx(h), B = cfg->members;
   CR(dalloc(&h->qh, nc)); CR(cudaMemset(h->qh, 0, nc * sizeof(cplx)));
   CR(dalloc(&h->q, nr)); CR(cudaMemset(h->q, 0, nr * sizeof(double)));
@@ -522,7 +535,7 @@ int qgb_create(const qgb_config* cfg, qgb_handle** out) {
 void qgb_destroy(qgb_handle* h) {
   if (!h) return;
   cudaSetDevice(h->cfg.device);
-  cudaFree(h->d_tw); cudaFree(h->d_pos); cudaFree(h->d_kv); cudaFree(h->d_lv); cudaFree(h->d_a); cudaFree(h->d_filtr);
+  cudaFree(h->d_tw); cudaFree(h->d_pos); cudaFree(h->d_pos_id); cudaFree(h->d_kv); cudaFree(h->d_lv); cudaFree(h->d_a); cudaFree(h->d_filtr);
   cudaFree(h->qh); cudaFree(h->q); cudaFree(h->scratch); cudaFree(h->red_scratch);
   for (int i = 0; i < 3; ++i) cudaFree(h->hist[i]);
   cudaFree(h->ph); cudaFree(h->u); cudaFree(h->v); cudaFree(h->p); cudaFree(h->red);

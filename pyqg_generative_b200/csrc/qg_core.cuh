@@ -24,6 +24,9 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#if defined(__CUDACC__)
+#include <type_traits>
+#endif
 
 #if defined(__CUDACC__)
 #define QGB_HD __host__ __device__ __forceinline__
@@ -96,6 +99,7 @@ constexpr int kBudgetTerms = 7;
 // (the specialised step kernels of spectral.cuh: all index divisions become shifts / multiplies); CN = 0 reads it from T.
 template <int CN>
 struct CtxT {
+  static constexpr int kN = CN;
   const Tables& T;   // lives in kernel parameter (constant) space on the device
   const StepIO& io;
   cplx* buf;      // [N*P]
@@ -107,6 +111,7 @@ struct CtxT {
   // lines owned by this CTA through ``tile`` (shared memory, tile_lines x (N+1)) and runs all its stages locally
   cplx* tile = nullptr;
   int tile_lines = 0, ncta = 1;
+  const short* tpos = nullptr;   // digit-reversal map of the transform stages (the global field is kept in NATURAL order: ``pos`` = identity)
   QGB_HD int N() const { return CN ? CN : T.N; }
   QGB_HD int NK() const { return CN ? CN / 2 + 1 : T.NK; }
   QGB_HD int P() const { return CN ? CN + 1 : T.P; }
@@ -189,10 +194,30 @@ QGB_HD int fft2d_phases(const Tables& T) { return 2 * T.nstages; }
 // One whole 1-D pass (all radix stages) of the 2-D transform for a field in global memory, cluster path.  The lines of
 // the pass are dealt to the CTAs of the cluster (rows for the x pass, columns for the y pass); each CTA copies its lines
 // into shared memory (coalesced: contiguous rows, or 16-byte elements of adjacent columns), runs the stages with block
-// barriers only and writes the lines back.  A 2-D transform is 2 cluster phases instead of 2 * nstages, and the stages
+// barriers only and writes the lines back.  The digit reversal of the in-place stages is undone while the lines move
+// between global and shared memory, so the global field is in natural order (``pos`` = identity) and the pointwise phases
+// read and write it coalesced.  A 2-D transform is 2 cluster phases instead of 2 * nstages, and the stages
 // run at shared-memory speed instead of one L2 round trip per butterfly.
-template <class C>
-__device__ void fft2d_pass_tiled(const C& c, int pass, bool inverse, int tid, int nt) {
+// ``load(row, col)`` / ``store(row, col, v)`` replace the buffer read / write (fusing the pointwise phase before / after
+// the pass); mode 0 = forward stages, 1 = inverse stages, 2 = inverse stages, ``mid(row, col, v)`` on every element,
+// forward stages (a physical-space product between two transforms along the same direction).  TileNone = use the buffer.
+struct TileNone {};
+// compile-time radix plan of a power-of-two size (the order make_radix_plan produces: 4s first, then one 2)
+__host__ __device__ constexpr int pow2_stages(int n) { int s = 0; while (n % 4 == 0 && n > 1) { n /= 4; ++s; } while (n % 2 == 0 && n > 1) { n /= 2; ++s; } return s; }
+__host__ __device__ constexpr int pow2_radix(int n, int s) { for (int i = 0; i < s; ++i) n /= (n % 4 == 0 ? 4 : 2); return n % 4 == 0 ? 4 : 2; }
+__host__ __device__ constexpr int pow2_len(int n, int s) { for (int i = 0; i < s; ++i) n /= (n % 4 == 0 ? 4 : 2); return n; }
+template <int CN, int S, bool INV>
+__device__ __forceinline__ void tile_stages_fixed(cplx* tile, const cplx* tw, int L, int lt, int ntc) {
+  constexpr int NS = pow2_stages(CN);
+  if constexpr (S < NS) {
+    constexpr int s = INV ? NS - 1 - S : S;
+    fft_stage_r<pow2_radix(CN, s)>(tile, tw, CN, 1, CN + 1, L, pow2_len(CN, s), INV, lt, ntc);
+    __syncthreads();
+    tile_stages_fixed<CN, S + 1, INV>(tile, tw, L, lt, ntc);
+  }
+}
+template <class C, class Load, class Mid, class Store>
+__device__ void tiled_pass(const C& c, int pass, int mode, const Load& load, const Mid& mid, const Store& store, int tid, int nt) {
   const Tables& T = c.T;
   const int N = c.N(), P = c.P(), TP = N + 1;
   const int ntc = nt / c.ncta, rank = tid / ntc, lt = tid - rank * ntc;
@@ -204,24 +229,52 @@ __device__ void fft2d_pass_tiled(const C& c, int pass, bool inverse, int tid, in
     for (int i = lt; i < L * N; i += ntc) {
       int line, e;
       if (pass == 0) { line = i / N; e = i - line * N; } else { e = i / L; line = i - e * L; }
-      tile[line * TP + e] = pass == 0 ? c.buf[(first + line) * P + e] : c.buf[e * P + first + line];
+      const int row = pass == 0 ? first + line : e, col = pass == 0 ? e : first + line;
+      const int te = mode != 0 ? c.tpos[e] : e;          // spectral input: frequency e sits at its digit-reversed slot
+      if constexpr (std::is_same<Load, TileNone>::value) tile[line * TP + te] = c.buf[row * P + col];
+      else tile[line * TP + te] = load(row, col);
     }
     __syncthreads();
-    for (int si = 0; si < T.nstages; ++si) {
-      const int s = inverse ? T.nstages - 1 - si : si;
-      int n = N;
-      for (int j = 0; j < s; ++j) n /= T.radix[j];
-      fft_stage(tile, c.tw, N, 1, TP, L, T.radix[s], n, inverse, lt, ntc);
-      __syncthreads();
+    for (int part = 0; part < (mode == 2 ? 2 : 1); ++part) {
+      const bool inverse = mode == 1 || (mode == 2 && part == 0);
+      if (part == 1) {
+        if constexpr (!std::is_same<Mid, TileNone>::value) {
+          for (int i = lt; i < L * N; i += ntc) {
+            int line, e;
+            if (pass == 0) { line = i / N; e = i - line * N; } else { e = i / L; line = i - e * L; }
+            const int row = pass == 0 ? first + line : e, col = pass == 0 ? e : first + line;
+            tile[line * TP + e] = mid(row, col, tile[line * TP + e]);
+          }
+          __syncthreads();
+        }
+      }
+      if constexpr (C::kN > 0) {      // compile-time size: the stage sequence is unrolled, index arithmetic folds to shifts
+        if (inverse) tile_stages_fixed<C::kN, 0, true>(tile, c.tw, L, lt, ntc);
+        else tile_stages_fixed<C::kN, 0, false>(tile, c.tw, L, lt, ntc);
+      } else {
+        for (int si = 0; si < T.nstages; ++si) {
+          const int s = inverse ? T.nstages - 1 - si : si;
+          int n = N;
+          for (int j = 0; j < s; ++j) n /= T.radix[j];
+          fft_stage(tile, c.tw, N, 1, TP, L, T.radix[s], n, inverse, lt, ntc);
+          __syncthreads();
+        }
+      }
     }
     for (int i = lt; i < L * N; i += ntc) {
       int line, e;
       if (pass == 0) { line = i / N; e = i - line * N; } else { e = i / L; line = i - e * L; }
-      if (pass == 0) c.buf[(first + line) * P + e] = tile[line * TP + e];
-      else c.buf[e * P + first + line] = tile[line * TP + e];
+      const int row = pass == 0 ? first + line : e, col = pass == 0 ? e : first + line;
+      const int te = mode != 1 ? c.tpos[e] : e;          // spectral output leaves in natural frequency order
+      if constexpr (std::is_same<Store, TileNone>::value) c.buf[row * P + col] = tile[line * TP + te];
+      else store(row, col, tile[line * TP + te]);
     }
     __syncthreads();
   }
+}
+template <class C>
+__device__ void fft2d_pass_tiled(const C& c, int pass, bool inverse, int tid, int nt) {
+  tiled_pass(c, pass, inverse ? 1 : 0, TileNone(), TileNone(), TileNone(), tid, nt);
 }
 #endif
 
@@ -277,26 +330,31 @@ QGB_HD void half_uv(const C& c, const cplx* qh, int z, int l, int k, cplx& uh, c
 // ' symmetrises the self-conjugate columns k=0,N/2 (what a c2r transform does implicitly by dropping the
 // imaginary part there) and E is the Hermitian extension to the full plane.
 template <class C, class Get>
+QGB_HD cplx packed_value(const C& c, const Get& get, int l, int k) {
+  const int N = c.N(), H = N / 2;
+  const int lm = l == 0 ? 0 : N - l;
+  cplx A, B;
+  if (k <= H) {
+    get(l, k, A, B);
+    if (k == 0 || k == H) {
+      cplx A2, B2;
+      get(lm, k, A2, B2);
+      A = cmake(0.5 * (A.x + A2.x), 0.5 * (A.y - A2.y));
+      B = cmake(0.5 * (B.x + B2.x), 0.5 * (B.y - B2.y));
+    }
+  } else {
+    get(lm, N - k, A, B);
+    A = cconj(A);
+    B = cconj(B);
+  }
+  return cmake(A.x - B.y, A.y + B.x);
+}
+template <class C, class Get>
 QGB_HD void build_packed(const C& c, Get get, int tid, int nt) {
-  const int N = c.N(), P = c.P(), H = N / 2;
+  const int N = c.N(), P = c.P();
   for (int i = tid; i < N * N; i += nt) {
     const int l = i / N, k = i - l * N;
-    const int lm = l == 0 ? 0 : N - l;
-    cplx A, B;
-    if (k <= H) {
-      get(l, k, A, B);
-      if (k == 0 || k == H) {
-        cplx A2, B2;
-        get(lm, k, A2, B2);
-        A = cmake(0.5 * (A.x + A2.x), 0.5 * (A.y - A2.y));
-        B = cmake(0.5 * (B.x + B2.x), 0.5 * (B.y - B2.y));
-      }
-    } else {
-      get(lm, N - k, A, B);
-      A = cconj(A);
-      B = cconj(B);
-    }
-    c.buf[c.pos[l] * P + c.pos[k]] = cmake(A.x - B.y, A.y + B.x);
+    c.buf[c.pos[l] * P + c.pos[k]] = packed_value(c, get, l, k);
   }
 }
 
@@ -705,6 +763,70 @@ QGB_HD void ph_red_final(const C& c, int tid, int nt) {
 enum Program { PROG_STEP = 0, PROG_STEP_DQ = 1, PROG_SET_Q = 2, PROG_INVERT = 3, PROG_DIAG = 4, PROG_EMIT_X = 5, PROG_STEP_DQ_RAW = 6,
                PROG_ADVECT = 7, PROG_C2R = 8, PROG_BUDGET = 9 };
 
+#ifdef __CUDACC__
+// ---- cluster path: the time step with the pointwise phases fused into the tiled transform passes ---------------------
+// Per layer z: build (u,v) spectra | inverse x pass | [inverse y pass -> (u+U) q, v q -> forward y pass] | forward x pass |
+// tendency;  then [dq -> forward y pass] | forward x pass | AB3 update | build q spectra | inverse x pass |
+// [inverse y pass -> q, closure input].  14 (16 with a forcing) cluster phases instead of 23 (26).  The forward transform
+// runs its y pass first here (the two 1-D transforms commute and the digit-reversed layout is per dimension).
+template <class C>
+struct TileProducts {   // ph_products on one element: the tile holds the unnormalised (u, v) at physical (y, x)
+  const C& c; const double* q; double s, U;
+  __device__ cplx operator()(int y, int x, cplx w) const {
+    const double qq = q[y * c.N() + x];
+    return cmake((w.x * s + U) * qq, (w.y * s) * qq);
+  }
+};
+template <class C>
+struct TileLoadPair {   // ph_load_pair
+  const C& c; const double* f0; const double* f1;
+  __device__ cplx operator()(int y, int x) const { return cmake(f0[y * c.N() + x], f1[y * c.N() + x]); }
+};
+template <class C>
+struct TileEmitQ {      // ph_emit_q
+  const C& c; double* q; float* x; double s;
+  __device__ void operator()(int y, int xx, cplx w) const {
+    const int N = c.N(), i = y * N + xx;
+    const double q0 = w.x * s, q1 = w.y * s;
+    q[i] = q0;
+    q[N * N + i] = q1;
+    if (x) {
+      x[i] = (float)q0 / c.io.x_std[0];
+      x[N * N + i] = (float)q1 / c.io.x_std[1];
+    }
+  }
+};
+
+template <class C>
+__device__ int run_step_tiled(const C& c, int prog, int phase, int tid, int nt) {
+  int _n = 0;
+  const int N = c.N();
+  const bool with_dq = prog == PROG_STEP_DQ || prog == PROG_STEP_DQ_RAW;
+#define QGB_TRUN(stmt) do { if (_n == phase) { stmt; } ++_n; } while (0)
+  for (int z = 0; z < 2; ++z) {
+    QGB_TRUN(ph_build_uv(c, z, tid, nt));     // (building inside the pass load would turn the scatter into uncoalesced reads: slower)
+    QGB_TRUN((tiled_pass(c, 0, 1, TileNone(), TileNone(), TileNone(), tid, nt)));
+    QGB_TRUN((tiled_pass(c, 1, 2, TileNone(),
+                         TileProducts<C>{c, c.io.q + ((long long)c.member * 2 + z) * N * N, c.T.inv_M, c.T.Ubg[z]}, TileNone(), tid, nt)));
+    QGB_TRUN((tiled_pass(c, 0, 0, TileNone(), TileNone(), TileNone(), tid, nt)));
+    QGB_TRUN(ph_tendency(c, z, tid, nt));
+  }
+  if (with_dq) {
+    const double* f0 = c.io.dq + (long long)c.member * 2 * N * N;
+    QGB_TRUN((tiled_pass(c, 1, 0, TileLoadPair<C>{c, f0, f0 + N * N}, TileNone(), TileNone(), tid, nt)));
+    QGB_TRUN((tiled_pass(c, 0, 0, TileNone(), TileNone(), TileNone(), tid, nt)));
+  }
+  QGB_TRUN(ph_update(c, with_dq, prog == PROG_STEP_DQ, tid, nt));
+  QGB_TRUN(ph_build_q(c, tid, nt));
+  QGB_TRUN((tiled_pass(c, 0, 1, TileNone(), TileNone(), TileNone(), tid, nt)));
+  QGB_TRUN((tiled_pass(c, 1, 1, TileNone(), TileNone(),
+                       TileEmitQ<C>{c, c.io.q + (long long)c.member * 2 * N * N,
+                                    c.io.cnn_x ? c.io.cnn_x + (long long)c.member * c.io.cnn_mstride : nullptr, c.T.inv_M}, tid, nt)));
+#undef QGB_TRUN
+  return _n;
+}
+#endif
+
 #define QGB_RUN(stmt)        \
   do {                       \
     if (_n == phase) { stmt; } \
@@ -717,6 +839,10 @@ enum Program { PROG_STEP = 0, PROG_STEP_DQ = 1, PROG_SET_Q = 2, PROG_INVERT = 3,
 
 template <class C>
 QGB_HD int run_program(const C& c, int prog, int phase, int tid, int nt) {
+#ifdef __CUDA_ARCH__
+  if (c.tile && (prog == PROG_STEP || prog == PROG_STEP_DQ || prog == PROG_STEP_DQ_RAW))
+    return run_step_tiled(c, prog, phase, tid, nt);
+#endif
   int _n = 0;
   const int F = c.tile ? 2 : fft2d_phases(c.T);
   QGB_RUN(ph_init(c, tid, nt));

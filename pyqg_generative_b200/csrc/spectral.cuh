@@ -130,16 +130,21 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
   return r;
 }
 
-__global__ void __launch_bounds__(512) qg_program_cluster_kernel(const __grid_constant__ Tables T,
+template <int CN>
+__global__ void __launch_bounds__(512, 2) qg_program_cluster_kernel(const __grid_constant__ Tables T,
                                                                  const __grid_constant__ StepIO io, int prog, int members,
-                                                                 cplx* scratch, double* red_scratch, int tile_lines) {
+                                                                 cplx* scratch, double* red_scratch, int tile_lines, const short* true_pos) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int rank = (int)cluster_ctarank();
   const int ncl = gridDim.x / kClusterSize, cl = blockIdx.x / kClusterSize;
   const int tid = rank * blockDim.x + threadIdx.x, nt = kClusterSize * blockDim.x;
+  // digit-reversal map of the stages, behind the tile in shared memory (T.pos is the identity on this path)
+  short* tpos = reinterpret_cast<short*>(smem_raw + (size_t)tile_lines * (T.N + 1) * sizeof(cplx));
+  for (int i = threadIdx.x; i < T.N; i += blockDim.x) tpos[i] = true_pos[i];
+  __syncthreads();
   for (int m = cl; m < members; m += ncl) {
-    Ctx c{T, io, scratch + (size_t)m * T.N * T.P, const_cast<cplx*>(T.tw), const_cast<short*>(T.pos),
-          red_scratch + (size_t)m * 4 * nt, m, reinterpret_cast<cplx*>(smem_raw), tile_lines, kClusterSize};
+    CtxT<CN> c{T, io, scratch + (size_t)m * T.N * T.P, const_cast<cplx*>(T.tw), const_cast<short*>(T.pos),
+          red_scratch + (size_t)m * 4 * nt, m, reinterpret_cast<cplx*>(smem_raw), tile_lines, kClusterSize, tpos};
     const int nph = run_program(c, prog, -1, tid, nt);
     for (int ph = 0; ph < nph; ++ph) {
       run_program(c, prog, ph, tid, nt);
