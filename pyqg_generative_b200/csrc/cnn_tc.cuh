@@ -152,6 +152,9 @@ __device__ __forceinline__ void st_global_v8(void* p, const uint32_t* r) {
                "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
 }
+// programmatic dependent launch: let the next kernel of the stream be scheduled early / wait for the previous one to finish
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 }  // namespace ptx
 
@@ -297,9 +300,15 @@ __global__ void __launch_bounds__(FUSE ? 640 : 384, 1) conv_tc_kernel(const __gr
     ptx::prefetch_tmap(&M.hi);
     if (C::PLANES == 2) ptx::prefetch_tmap(&M.lo);
   }
+  // Programmatic dependent launch: the layers of one forward pass are launched back to back with the stream-serialization
+  // attribute; this CTA may have been scheduled while the previous layer's last CTAs are still running (its own set-up
+  // above -- barriers, TMEM allocation, descriptor prefetch -- overlaps their tail) and must not touch activations before
+  // the previous grid has completed and flushed.
+  ptx::pdl_launch_dependents();
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
+  ptx::pdl_wait();
   const uint32_t tmem_base = *tmem_slot;
   const int tiles_per_img = P.tiles_y * P.tiles_x;
 
@@ -853,8 +862,17 @@ inline cudaError_t tc_launch(const TcConvParams& P, const TcEpi& E, int nimg, in
     configured = true;
   }
   const int grid = P.num_tiles < nsm ? P.num_tiles : nsm;
-  kern<<<grid, FUSE ? 640 : 384, C::SMEM + (FUSE ? 6400 : 0), st>>>(P, M, E);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(FUSE ? 640 : 384);
+  cfg.dynamicSmemBytes = C::SMEM + (FUSE ? 6400 : 0);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, P, M, E);
 }
 
 // Tile shape of a layer: NH stacked rows (tile height 16*NH) x T M-tiles of 8 columns.  TMEM holds 2 x T x NH x NF columns.
