@@ -186,7 +186,8 @@ def rel_l2(a, b):
 
 
 @pytest.mark.parametrize('shape,cin', [((2, 64, 64), 4), ((3, 48, 48), 4), ((1, 96, 96), 2), ((5, 16, 16), 4), ((2, 32, 48), 2),
-                                       ((200, 64, 64), 4)])   # 200 images: several tiles per persistent CTA
+                                       ((200, 64, 64), 4),    # 200 images: several tiles per persistent CTA
+                                       ((1, 128, 128), 4), ((2, 80, 80), 2), ((1, 64, 48), 4), ((1, 112, 16), 4)])  # tile-shape variants
 def test_tensor_core_network_matches_fp32_oracle(shape, cin):
     from pyqg_generative_b200.tools.cnn_tools import AndrewCNN
     B, ny, nx = shape
@@ -201,6 +202,29 @@ def test_tensor_core_network_matches_fp32_oracle(shape, cin):
     assert rel(y, ref) < 2 * TC_TOL, rel(y, ref)
     y_sp = net.forward(x.cuda(), softplus=True).cpu().numpy()
     assert rel_l2(y_sp, cnn_ref.andrew_cnn_forward(sd, x, final_softplus=True).numpy()) < TC_TOL
+
+
+def test_tensor_core_network_with_negative_and_tiny_batchnorm_scales():
+    """The thin layers fold |BN scale| into their weights and the sign into the next layer (csrc/cnn_tc.cuh): exercise negative,
+    zero and widely spread scales, which random-init and the shipped networks do not contain."""
+    from pyqg_generative_b200.tools.cnn_tools import AndrewCNN
+    sd = cnn_ref.random_state_dict(4, 2, seed=11)
+    g = torch.Generator().manual_seed(5)
+    for i in range(7):
+        w = sd['conv.%d.weight' % (3 * i + 2)]
+        sign = torch.where(torch.rand(w.shape, generator=g) < 0.4, -1.0, 1.0)
+        scale = torch.exp(torch.randn(w.shape, generator=g) * 0.7)
+        w.mul_(sign * scale)
+        w[0] = 0.0                                            # a pruned channel
+        sd['conv.%d.bias' % (3 * i + 2)].add_(torch.randn(w.shape, generator=g) * 0.5)
+        sd['conv.%d.running_mean' % (3 * i + 2)].add_(torch.rand(w.shape, generator=g) * 0.3)
+    x = torch.randn(3, 4, 64, 64, generator=torch.Generator().manual_seed(3))
+    ref = cnn_ref.andrew_cnn_forward(sd, x, dtype=torch.float64).numpy()
+    for prec, tol in (('tc', TC_TOL), ('fp32', FP32_TOL)):
+        net = AndrewCNN(4, 2, precision=prec)
+        net.load_state_dict(sd)
+        y = net(x.cuda()).cpu().numpy()
+        assert rel_l2(y, ref) < tol, (prec, rel_l2(y, ref))
 
 
 def test_tensor_core_path_with_shipped_weights_and_coupled_step(tmp_path):
