@@ -1,30 +1,32 @@
 // cnn_tc.cuh -- AndrewCNN forward on the 5th-generation tensor cores (sm_100a): implicit-GEMM circular convolutions
-// issued as tcgen05.mma (cta_group::1, kind::f16, M=128) with fp32 accumulators in TMEM, operands staged in shared
-// memory by the TMA engine (cp.async.bulk + mbarrier complete_tx), warp-specialised persistent CTAs (one per SM).
+// issued as tcgen05.mma (cta_group::1, kind::f16 and kind::f8f6f4, M=128) with fp32 accumulators in TMEM, operands staged
+// in shared memory by the TMA engine (cp.async.bulk[.tensor] + mbarrier complete_tx), warp-specialised persistent CTAs
+// (one per SM).
 //
 // Reference semantics: pyqg_generative/tools/cnn_tools.py:79-98 (make_block: Conv2d circular 'same' -> ReLU ->
 // BatchNorm2d), :125-176 (AndrewCNN), models/mean_var_model.py:14-17 (softplus head).
 //
 // Precision plan ("plain TF32 fails the 1e-3 bound"): operands are fp16 (11-bit significand, same as
 // TF32, at twice the tensor rate).  Every layer but the second runs the 3-pass split  a*w ~= a_hi*w_hi + a_lo*w_hi + a_hi*w_lo
-// (a = a_hi + a_lo, both fp16; error ~2^-22), fp32 accumulation throughout.  Layer 2 (128->64, 5x5, 75 % of the FLOPs) runs
-// TWO passes, (a_hi + a_lo)*w_hi: with the shipped networks the rounding of its ACTIVATIONS to 11 bits alone costs up to
-// 1.8e-3 relative (VAE decoder, GZ mean net; measured, profiles/r1_tc_precision.md) while rounding its weights costs
-// 2-5e-4.  A single-pass variant (QGB_PREC_TC_FAST) is kept for networks where that is acceptable.  Weights are pre-scaled per layer by a power of two so they sit
-// in the fp16 normal range; the epilogue undoes the scale exactly.
+// (a = a_hi + a_lo; error ~2^-22), fp32 accumulation throughout.  Layer 2 (128->64, 5x5, 75 % of the FLOPs) runs TWO passes,
+// (a_hi + a_lo)*w_hi: with the shipped networks the rounding of its ACTIVATIONS to 11 bits alone costs up to 1.8e-3 relative
+// (VAE decoder, GZ mean net; measured, profiles/r1_tc_precision.md) while rounding its weights costs 2-5e-4.  A single-pass
+// variant (QGB_PREC_TC_FAST) is kept for networks where that is acceptable.  In the TMA-fed layers the low half a_lo travels
+// as e4m3 (x 2^11) and multiplies an e4m3 copy of the weights (x 2^-11) in one kind::f8f6f4 MMA per 32 channels (see TcCfg).
+// Weights are pre-scaled per layer by a power of two so they sit in the fp16 normal range; the epilogue undoes the scale.
 //
-// Data layout.  Activations live in HBM as  [image][C/32][ny+2p][nx+2p][32] fp16  (hi plane, optional lo plane): the
-// innermost 64 B are 32 consecutive channels of one pixel, the circular halo (p = padding of the CONSUMING layer) is
+// Data layout.  Activations live in HBM as  [image][C/32][ny+2p][nx+2p][32]  (fp16 hi plane, e4m3 lo plane): the innermost
+// 64 B (32 B) are 32 consecutive channels of one pixel, the circular halo (p = padding of the CONSUMING layer) is
 // materialised by the producing epilogue, so every tap of the consumer is a plain in-bounds box.  A CTA tile is
-// 16 rows x 8T columns (T accumulators of 128 pixels).  The tile + halo of one 32-channel chunk is loaded ONCE by a
-// 4-D TMA box with the 64-byte swizzle and serves all KSxKS taps: tap (dy,dx), K-step ks and M-tile t are just a
-// different start address of the SAME K-major SWIZZLE_64B canonical UMMA layout (8 pixel rows of 64 B per atom, next
-// image row at the stride byte offset).  Because a pixel row is 64 B, every tap shift keeps the 8x16 B core matrices
-// bank-conflict free (the first version used 16 B pixel rows: shifted core matrices straddled two 128 B lines and the
-// tensor pipe sat at 41 %, profiles/r1_conv_l2_noswizzle.md).
+// 16*NH rows x 8T columns (T M-tiles of 128 accumulator rows, NH stacked output rows per accumulator row, see TcCfg).  The
+// tile + halo of one 32-channel chunk is loaded ONCE by a 4-D TMA box with the 64-byte swizzle and serves all taps: a tap
+// (vertical shift, column), K-step and M-tile are just a different start address of the SAME K-major SWIZZLE_64B canonical
+// UMMA layout (8 pixel rows of 64 B per atom, the next row group at the stride byte offset).  Because a pixel row is 64 B,
+// every tap shift keeps the 8x16 B core matrices bank-conflict free (the first version used 16 B pixel rows: shifted core
+// matrices straddled two 128 B lines and the tensor pipe sat at 41 %, profiles/r1_history.md).
 //
 // Layer 1 (Cin = 4 or 2) is too thin for a K=16 MMA: it runs as a 1x1 convolution over its 5x5 im2col (K = 100 -> 128),
-// which four extra "builder" warps write straight into the shared-memory operand stages from the raw fp32 input
+// which eight extra "builder" warps write straight into the shared-memory operand stages from the raw fp32 input
 // (template parameter FUSE), so the im2col tensor never exists in HBM.
 #pragma once
 #include <cuda.h>
