@@ -95,6 +95,24 @@ def write_runs(ds, folder, first=0):
     return paths
 
 
+def write_forecast(fc, path):
+    """Ensemble forecast file of the reference's ``--forecast`` mode (tools/simulate.py:254-292): q, u, v, psi of run 0 and
+    their ensemble means ``*_mean``, dims (time, lev, y, x), float32."""
+    from scipy.io import netcdf_file
+    ntime, nlev, ny, nx = np.asarray(fc['q']).shape
+    with netcdf_file(path, 'w', version=2) as f:
+        for name, n in (('time', ntime), ('lev', nlev), ('y', ny), ('x', nx)):
+            f.createDimension(name, n)
+        _nc_var(f, 'time', np.asarray(fc['time'], dtype=np.float64), ('time',), {'units': 'days', 'long_name': 'time'})
+        _nc_var(f, 'lev', np.arange(1, nlev + 1, dtype=np.int32), ('lev',))
+        for name in PHYSICAL:
+            _nc_var(f, name, np.asarray(fc[name], dtype=np.float32), ('time', 'lev', 'y', 'x'))
+            _nc_var(f, name + '_mean', np.asarray(fc[name + '_mean'], dtype=np.float32), ('time', 'lev', 'y', 'x'))
+        for k, v in fc.get('attrs', {}).items():
+            setattr(f, k, v if isinstance(v, (int, float)) else str(v))
+    return path
+
+
 def read_netcdf(path):
     """File -> dict of numpy arrays (+ 'attrs', 'dims'); for users without xarray and for the tests."""
     from scipy.io import netcdf_file

@@ -12,7 +12,7 @@ import os
 
 import numpy as np
 
-from .dataset import model_coords, write_runs
+from .dataset import model_coords, read_netcdf, write_forecast, write_runs
 from .parameters import ANDREW_1000_STEPS, DAY
 from .stochastic_pyqg import EnsembleQGModel, stochastic_QGModel
 
@@ -94,6 +94,21 @@ def run_simulation(pyqg_params, parameterization=None, q_init=None, sampling_fre
     return ds
 
 
+def run_forecast(pyqg_params, parameterization, q_init, n_ens, sampling_freq=DAY, rng=None):
+    """Ensemble forecast of the reference's ``--forecast`` mode (:254-292): ``n_ens`` runs from the SAME initial condition
+    ``q_init`` (2, ny, nx), differing only in the stochastic closure, sampled every ``sampling_freq`` (1 day).  The reference
+    calls ``run_simulation`` n_ens times; here the runs are the members of one batched integration.  Returns the fields of
+    run 0 and the ensemble means, like the file the reference writes: {q, u, v, psi, q_mean, ..., time}."""
+    params = dict(pyqg_params, members=int(n_ens))
+    q0 = np.broadcast_to(np.asarray(q_init, dtype='float64'), (int(n_ens), 2) + np.shape(q_init)[-2:])
+    ds = run_simulation(params, parameterization, q0, sampling_freq, rng)
+    out = {'time': ds['time'], 'attrs': ds['attrs'], 'coords': ds['coords']}
+    for var in ('q', 'u', 'v', 'psi'):
+        out[var] = ds[var][0]
+        out[var + '_mean'] = ds[var].astype('float64').mean(axis=0).astype('float32')
+    return out
+
+
 def generate_subgrid_forcing(Nc, pyqg_params, sampling_freq=ANDREW_1000_STEPS, operators=None, dealias='3/2-rule', rng=None):
     """Reference :62-106: run a hi-res ensemble and coarse-grain every ``sampling_freq`` seconds.  Defaults follow the
     reference ([Operator2, Operator5], '3/2-rule', keys '<Operator>-<nc>-dealias'); the published datasets used
@@ -160,6 +175,9 @@ def main(argv=None):
     p.add_argument('--model_weight', type=float, default=1.0)
     p.add_argument('--model_folder', type=str, default='model')
     p.add_argument('--precision', type=str, default='fp32')
+    p.add_argument('--forecast', type=str, default='no')
+    p.add_argument('--initial_condition', type=str, default='no',
+                   help="dict(path=, selector=dict(run=, time=), operator='Operator1'|..., n_ens=, number=) like the reference")
     args = p.parse_args(argv)
     params = dict(ast.literal_eval(args.pyqg_params))
     params.setdefault('members', args.members)
@@ -186,6 +204,22 @@ def main(argv=None):
         model = args.model_weight * _load_model(args.model_folder)
         par = dict(self=model, sampling=args.sampling, nsteps=args.nsteps)
         save_runs(run_simulation(params, par, sampling_freq=args.sampling_freq), args.subfolder)
+
+
+    if args.forecast == 'yes':
+        from . import operators as ops
+        ic = dict(ast.literal_eval(args.initial_condition))
+        src = read_netcdf(ic['path'] + str(ic['selector']['run']) + '.nc')
+        q_init = np.asarray(src['q'][ic['selector']['time']], dtype='float64')
+        if ic.get('operator') in ('Operator1', 'Operator2', 'Operator5') and q_init.shape[-1] != params['nx']:
+            q_init = getattr(ops, ic['operator'])(q_init, params['nx'])          # coarse-grain the hi-res snapshot (:274-278)
+        par = None
+        if os.path.exists(os.path.join(args.model_folder, 'model_args.json')):
+            params['precision'] = args.precision
+            par = dict(self=args.model_weight * _load_model(args.model_folder), sampling=args.sampling, nsteps=args.nsteps)
+        params.pop('members', None)
+        fc = run_forecast(params, par, q_init, ic['n_ens'], 1 * DAY)
+        write_forecast(fc, os.path.join(args.subfolder or '.', '%s.nc' % ic['number']))
 
 
 if __name__ == '__main__':

@@ -41,3 +41,26 @@ def test_cli_writes_one_file_per_member(tmp_path):
     assert sorted(os.listdir(sub)) == ['4.nc', '5.nc']
     d = dataset.read_netcdf(os.path.join(sub, '5.nc'))
     assert d['q'].shape == (2, 2, 32, 32) and np.isfinite(d['q']).all()
+
+
+def test_forecast_mode_runs_the_ensemble_in_one_batch(tmp_path):
+    """tools/simulate.py --forecast (reference :254-292): members share the initial condition read from a run file."""
+    import os
+    from pyqg_generative_b200.tools import dataset, simulate
+    N, dt = 32, 14400.
+    ref = simulate.run_simulation(dict(nx=N, dt=dt, tmax=12 * dt, members=2, log_level=0), sampling_freq=6 * dt,
+                                  rng=np.random.RandomState(2))
+    dataset.write_runs(ref, str(tmp_path / 'ref'), first=0)
+    ic = dict(path=str(tmp_path / 'ref') + '/', selector=dict(run=1, time=-1), operator='Operator1', n_ens=3, number=7)
+    simulate.main(['--forecast=yes', '--subfolder=' + str(tmp_path / 'fc'), '--model_folder=' + str(tmp_path / 'nomodel'),
+                   '--initial_condition=' + str(ic), "--pyqg_params={'nx': 32, 'dt': 14400.0, 'tmax': 172800.0, 'log_level': 0}"])
+    d = dataset.read_netcdf(os.path.join(str(tmp_path / 'fc'), '7.nc'))
+    assert d['q'].shape == (3, 2, N, N) and np.allclose(d['time'], [0., 1., 2.])            # IC + 2 daily snapshots
+    assert np.array_equal(d['q'][0], ref['q'][1, -1])                                        # starts from the selected snapshot
+    # without a stochastic closure every member follows the same trajectory: run 0 equals the ensemble mean
+    assert np.abs(d['q'] - d['q_mean']).max() <= 1e-6 * np.abs(d['q']).max()
+    o = pyqg_shim.QGModel(nx=N, dt=dt, log_level=0)
+    o.q = ref['q'][1, -1].astype('float64')
+    for _ in range(6):
+        o._step_forward()
+    assert np.abs(d['q'][1] - o.q).max() < 1e-6 * np.abs(o.q).max()
