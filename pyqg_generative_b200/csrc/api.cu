@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -985,9 +986,53 @@ int qgb_diag_spectra(qgb_handle* h, double* kespec, double* ensspec, int on_devi
 
 // ---- coarse-graining (operators.cuh + the phase programs) --------------------------------------------------------
 namespace {
+// Work handles of the stateless coarse-graining entry points.  Creating a handle costs milliseconds (tables built on the
+// host and uploaded, ~15 allocations, function attributes) against microseconds of kernel time per snapshot, and forcing
+// datasets call these entries per snapshot, operator and resolution, so handles are kept in a small process-wide cache
+// keyed by the full configuration and handed out exclusively (busy flag) -- every entry point synchronises its stream
+// before it returns, so a released handle has no work in flight.
+struct HandleCache {
+  struct Entry { qgb_handle* h; bool busy; unsigned long long stamp; };
+  std::mutex mu;
+  std::vector<Entry> entries;
+  unsigned long long clock = 0;
+  static bool same(const qgb_config& a, const qgb_config& b) {
+    return a.nx == b.nx && a.members == b.members && a.member_offset == b.member_offset && a.device == b.device && a.L == b.L &&
+           a.dt == b.dt && a.rek == b.rek && a.filterfac == b.filterfac && a.beta == b.beta && a.rd == b.rd && a.delta == b.delta &&
+           a.H1 == b.H1 && a.U1 == b.U1 && a.U2 == b.U2;
+  }
+  int acquire(const qgb_config& c, qgb_handle** out) {
+    if (cudaSetDevice(c.device) != cudaSuccess) return fail(nullptr, QGB_ECUDA, "cudaSetDevice(%d) failed", c.device);
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      for (auto& e : entries)
+        if (!e.busy && same(e.h->cfg, c)) { e.busy = true; e.stamp = ++clock; *out = e.h; return QGB_OK; }
+    }
+    qgb_handle* h = nullptr;
+    int rc = qgb_create(&c, &h);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(mu);
+    if (entries.size() >= 32) {      // evict the least recently used idle handle
+      int victim = -1;
+      for (int i = 0; i < (int)entries.size(); ++i)
+        if (!entries[i].busy && (victim < 0 || entries[i].stamp < entries[victim].stamp)) victim = i;
+      if (victim >= 0) { qgb_destroy(entries[victim].h); entries.erase(entries.begin() + victim); }
+    }
+    entries.push_back({h, true, ++clock});
+    *out = h;
+    return QGB_OK;
+  }
+  void release(qgb_handle* h) {
+    std::lock_guard<std::mutex> lk(mu);
+    for (auto& e : entries)
+      if (e.h == h) { e.busy = false; return; }
+  }
+};
+HandleCache& handle_cache() { static HandleCache c; return c; }
 struct HandleGuard {
   qgb_handle* h = nullptr;
-  ~HandleGuard() { if (h) qgb_destroy(h); }
+  int create(const qgb_config& c) { return handle_cache().acquire(c, &h); }
+  ~HandleGuard() { if (h) handle_cache().release(h); }
 };
 int grid_for(long long n) { long long b = (n + 255) / 256; return (int)(b > 148 * 16 ? 148 * 16 : (b < 1 ? 1 : b)); }
 Tables no_background(const Tables& T) {   // advect(var, u, v) uses anomaly velocities and no beta / drag terms
@@ -1009,9 +1054,9 @@ int advect_dealiased(const qgb_config& base, int n, int B, const double* q, cons
   c2N.nx = N; c2N.members = 2 * B;
   HandleGuard g3n, g3N, g2N;
   int rc;
-  if ((rc = qgb_create(&c3n, &g3n.h))) return rc;
-  if ((rc = qgb_create(&c3N, &g3N.h))) return rc;
-  if ((rc = qgb_create(&c2N, &g2N.h))) return rc;
+  if ((rc = g3n.create(c3n))) return rc;
+  if ((rc = g3N.create(c3N))) return rc;
+  if ((rc = g2N.create(c2N))) return rc;
   qgb_handle *h3n = g3n.h, *h3N = g3N.h, *h2N = g2N.h;
   const size_t fn = (size_t)B * 2 * n * n, fN = (size_t)B * 2 * N * N;
   CUDA_TRY(nullptr, cudaMemcpyAsync(h3n->q, q, fn * sizeof(double), cudaMemcpyDeviceToDevice, st));
@@ -1049,8 +1094,8 @@ int qgb_fft_interpolate(int device, int n, int N, int batch, const double* in, d
   cb = ca; cb.nx = N;
   HandleGuard ga, gb;
   int rc;
-  if ((rc = qgb_create(&ca, &ga.h))) return rc;
-  if ((rc = qgb_create(&cb, &gb.h))) return rc;
+  if ((rc = ga.create(ca))) return rc;
+  if ((rc = gb.create(cb))) return rc;
   const cudaMemcpyKind kin = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
   const cudaMemcpyKind kout = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
   CUDA_TRY(nullptr, cudaMemsetAsync(ga.h->q, 0, nreal(ga.h) * sizeof(double), st));
@@ -1081,9 +1126,9 @@ int qgb_operator(int device, int op, int n, int nc, int batch, const double* in,
   cf.device = device; cf.members = pairs; cf.nx = n;
   cc = cf; cc.nx = nc;
   HandleGuard gf, gc;
-  int rc = qgb_create(&cf, &gf.h);
+  int rc = gf.create(cf);
   if (rc) return rc;
-  rc = qgb_create(&cc, &gc.h);
+  rc = gc.create(cc);
   if (rc) return rc;
   qgb_handle *hf = gf.h, *hc = gc.h;
   const cudaMemcpyKind kin = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
@@ -1117,9 +1162,9 @@ int qgb_subgrid_forcing(const qgb_config* cfg, int op, int nc, int dealias, int 
   qgb_config cf = *cfg, cc = *cfg;
   cf.members = batch; cc.members = batch; cc.nx = nc;
   HandleGuard gf, gc;
-  int rc = qgb_create(&cf, &gf.h);
+  int rc = gf.create(cf);
   if (rc) return rc;
-  rc = qgb_create(&cc, &gc.h);
+  rc = gc.create(cc);
   if (rc) return rc;
   qgb_handle *hf = gf.h, *hc = gc.h;
   const cudaMemcpyKind kin = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
