@@ -69,7 +69,13 @@ class Parameterization(QParameterization):
         if m.sampling_type == 'deterministic':
             m.PV_forcing = demean(self.predict_mean_snapshot(m))
         else:
-            latent_noise = lambda: self.generate_latent_noise(m.ny, m.nx)
+            nb = np.shape(m.q)[0] if np.ndim(m.q) == 4 else 0     # batched host model: independent noise per member
+
+            def latent_noise():
+                if not nb:
+                    return self.generate_latent_noise(m.ny, m.nx)
+                return np.concatenate([np.asarray(self.generate_latent_noise(m.ny, m.nx)).reshape((1, -1, m.ny, m.nx))
+                                       for _ in range(nb)])
             if m.noise_sampler.update(latent_noise):
                 m.PV_forcing = demean(self.predict_snapshot(m, m.noise_sampler.noise))
         return m.PV_forcing

@@ -294,3 +294,29 @@ def test_ols_closure_and_driver_entry_points(tmp_path):
     d = out['Operator2-48']
     assert d['q_forcing_advection'].shape == (2, 2, 2, 48, 48) and d['q'].dtype == np.float32
     assert np.isfinite(d['q_forcing_advection']).all() and np.abs(d['q_forcing_advection']).max() > 0
+
+
+def test_closure_callable_accepts_a_batched_host_model(tmp_path):
+    """Drop-in boundary: ``parameterization(m)`` with m.q of shape (B,2,ny,nx) on the host draws independent
+    latent noise per member and equals the per-member calls with the same noise."""
+    from pyqg_generative_b200.models.cgan_regression import CGANRegression
+    from pyqg_generative_b200.tools.stochastic_pyqg import AR1_sampler
+    model = CGANRegression(folder=write_model_folder(tmp_path, 'gan'), nx=48)
+
+    class M:
+        pass
+    m = M()
+    m.ny = m.nx = 48
+    m.q = np.random.RandomState(0).randn(3, 2, 48, 48) * np.array([7e-6, 1e-6])[None, :, None, None]
+    m.sampling_type, m.noise_sampler = 'AR1', AR1_sampler(1)
+    y = model(m)
+    assert y.shape == (3, 2, 48, 48) and np.abs(y.mean(axis=(-2, -1))).max() < 1e-6 * np.abs(y).max()
+    z = m.noise_sampler.noise
+    assert z.shape == (3, 2, 48, 48) and not np.allclose(z[0], z[1])
+    for b in range(3):
+        mb = M()
+        mb.ny = mb.nx = 48
+        mb.q = m.q[b]
+        yb = model.predict_snapshot(mb, z[b:b + 1])
+        yb = yb - yb.mean(axis=(-2, -1), keepdims=True)
+        assert rel(y[b], yb) < FP32_TOL
