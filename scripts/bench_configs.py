@@ -48,7 +48,28 @@ def run(name, nx, members, closure, base, steps=20, precision='tc'):
                       'healthy': bool(np.isfinite(ke).all() and not flags.any())}))
 
 
+def run_forcing(members=64, steps=2000, every=1000):
+    """configs[4]: hi-res 256^2 ensemble coarse-grained to 64^2 by Operator1/Operator2 with the subgrid forcing S every
+    ``every`` steps (tools/simulate.py generate_subgrid_forcing, run_forcing_datasets.py); wall clock incl. host copies."""
+    from pyqg_generative_b200.tools import operators as ops
+    from pyqg_generative_b200.tools.simulate import generate_subgrid_forcing
+    p = dict(EDDY_PARAMS.nx(256))
+    p.update(dict(log_level=0, tmax=steps * p['dt'], tavestart=1e12, members=members))
+    generate_subgrid_forcing([64], dict(p, tmax=2 * every * p['dt'] if False else every * p['dt']), every * p['dt'],
+                             [ops.Operator1, ops.Operator2], 'none', np.random.RandomState(0))      # warm-up (handles, tables)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out = generate_subgrid_forcing([64], p, every * p['dt'], [ops.Operator1, ops.Operator2], 'none', np.random.RandomState(0))
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    key = sorted(out)[0]
+    print(json.dumps({'config': 'configs[4] forcing datasets 256->64, Operator1+Operator2, S every %d steps' % every, 'nx': 256,
+                      'members': members, 'steps': steps, 'snapshots': int(out[key]['q'].shape[1]), 'wall_s': round(dt, 3),
+                      'member_steps_per_s': round(members * steps / dt, 1), 'keys': sorted(out)}))
+
+
 if __name__ == '__main__':
+    run_forcing()
     run('configs[1] hi-res reference ensemble', 256, 64, None, EDDY_PARAMS)
     run('hi-res 128', 128, 64, None, EDDY_PARAMS)
     run('configs[0]-like, no closure', 64, 1024, None, EDDY_PARAMS)
