@@ -59,7 +59,7 @@ struct qgb_handle {
   bool fixed = false;   // compile-time specialised step kernel available for this nx
   int nt64 = 384;
   bool large = false; cplx* scratch = nullptr; double* red_scratch = nullptr;   // cluster path for nx > 96
-  int large_lines = 0; size_t large_smem = 0;   // lines of a 1-D FFT pass staged per CTA in shared memory
+  int cluster = 8; int large_lines = 0; size_t large_smem = 0;   // lines of a 1-D FFT pass staged per CTA in shared memory
   // closure
   int kind = QGB_CLOSURE_NONE; int precision = QGB_PREC_FP32;
   DevNet nets[2];
@@ -137,7 +137,7 @@ int launch_program(qgb_handle* h, const StepIO& io, int prog, cudaStream_t st, c
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = kClusterSize;
+    attr[0].val.clusterDim.x = h->cluster;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
@@ -481,11 +481,17 @@ int qgb_create(const qgb_config* cfg, qgb_handle** out) {
   }
   h->grid = cfg->members;
   if (h->large) {
-    // one cluster of kClusterSize CTAs per member, persistent over members when the ensemble exceeds the machine
+    // one cluster of CTAs per member, persistent over members when the ensemble exceeds the machine.  Cluster size: small
+    // grids are barrier-bound, so fewer CTAs per member and more members in flight win (measured 128^2 x 64: 0.286 ms with
+    // 8, 0.228 ms with 4); from 256^2 on the per-member work fills 8 CTAs (256^2: 0.873 vs 0.918 ms, 512^2: 1.76 vs 2.78 ms).
+    // With more members than 4-CTA clusters fit (2 CTAs per SM), 128^2 runs best with 2 CTAs per member (256 members:
+    // 1.21 ms with 4, 0.86 ms with 2).
+    h->cluster = h->ht.N <= 128 ? (4 * cfg->members <= 2 * h->nsm ? 4 : 2) : kMaxClusterSize;
+    if (const char* e = getenv("QGB_CLUSTER")) { int v = atoi(e); if (v == 2 || v == 4 || v == 8) h->cluster = v; }
     h->nthreads = 512;
     // lines of a 1-D transform pass that a CTA stages in shared memory at a time: all it owns (N / cluster size) when that
     // leaves room for two CTAs per SM (<= 110 KB), else the largest power-of-two fraction that does
-    const int per_cta = h->ht.N / kClusterSize;
+    const int per_cta = h->ht.N / h->cluster;
     const size_t line_bytes = (size_t)(h->ht.N + 1) * sizeof(cplx);
     int lines = per_cta;
     while (lines > 1 && lines * line_bytes > 110 * 1024) lines /= 2;
@@ -503,12 +509,12 @@ int qgb_create(const qgb_config* cfg, qgb_handle** out) {
         cluster_smem_limit = h->large_smem;
       }
     }
-    int clusters = (2 * h->nsm) / kClusterSize;
+    int clusters = (2 * h->nsm) / h->cluster;
     if (clusters > cfg->members) clusters = cfg->members;
     if (clusters < 1) clusters = 1;
-    h->grid = clusters * kClusterSize;
+    h->grid = clusters * h->cluster;
     CR(dalloc(&h->scratch, (size_t)cfg->members * h->ht.N * h->ht.P));
-    CR(dalloc(&h->red_scratch, (size_t)cfg->members * 4 * kClusterSize * h->nthreads));
+    CR(dalloc(&h->red_scratch, (size_t)cfg->members * 4 * h->cluster * h->nthreads));
   }
   CR(upload(&h->d_tw, h->ht.tw));
   CR(upload(&h->d_pos, h->ht.pos));

@@ -116,10 +116,10 @@ __global__ void __launch_bounds__(NT) qg_step_fixed_kernel(const __grid_constant
 
 // Large grids (N = 128, 256: the packed field is 0.26 / 1.0 MB and no longer fits one CTA's shared memory): the SAME phase
 // programs run with the working field in a per-member global-memory scratch (L2 resident: 64 members x 1 MB at 256^2)
-// and a thread-block CLUSTER of kClusterSize CTAs per member.  Threads are numbered across the cluster, phases are separated
+// and a thread-block CLUSTER of 4 or 8 CTAs per member.  Threads are numbered across the cluster, phases are separated
 // by the hardware cluster barrier (release/acquire at cluster scope, which also invalidates L1), tables are read in place.
 // The 1-D passes of the transforms run per CTA in shared memory (fft2d_pass_tiled): 2 cluster phases per 2-D transform.
-constexpr int kClusterSize = 8;
+constexpr int kMaxClusterSize = 8;   // portable limit; the size is chosen per handle (4 for N <= 128, 8 above)
 
 __device__ __forceinline__ void cluster_barrier() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -136,15 +136,17 @@ __global__ void __launch_bounds__(512, 2) qg_program_cluster_kernel(const __grid
                                                                  cplx* scratch, double* red_scratch, int tile_lines, const short* true_pos) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int rank = (int)cluster_ctarank();
-  const int ncl = gridDim.x / kClusterSize, cl = blockIdx.x / kClusterSize;
-  const int tid = rank * blockDim.x + threadIdx.x, nt = kClusterSize * blockDim.x;
+  uint32_t csz;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(csz));
+  const int ncl = gridDim.x / (int)csz, cl = blockIdx.x / (int)csz;
+  const int tid = rank * blockDim.x + threadIdx.x, nt = (int)csz * blockDim.x;
   // digit-reversal map of the stages, behind the tile in shared memory (T.pos is the identity on this path)
   short* tpos = reinterpret_cast<short*>(smem_raw + (size_t)tile_lines * (T.N + 1) * sizeof(cplx));
   for (int i = threadIdx.x; i < T.N; i += blockDim.x) tpos[i] = true_pos[i];
   __syncthreads();
   for (int m = cl; m < members; m += ncl) {
     CtxT<CN> c{T, io, scratch + (size_t)m * T.N * T.P, const_cast<cplx*>(T.tw), const_cast<short*>(T.pos),
-          red_scratch + (size_t)m * 4 * nt, m, reinterpret_cast<cplx*>(smem_raw), tile_lines, kClusterSize, tpos};
+          red_scratch + (size_t)m * 4 * nt, m, reinterpret_cast<cplx*>(smem_raw), tile_lines, (int)csz, tpos};
     const int nph = run_program(c, prog, -1, tid, nt);
     for (int ph = 0; ph < nph; ++ph) {
       run_program(c, prog, ph, tid, nt);
