@@ -45,3 +45,30 @@ class CNNClosure(DeviceClosure):
     def _shape_of(self, ds):
         q = ds['q']
         return tuple(getattr(q, 'shape'))
+
+
+def batched_mean_var(generate, x, M, images_per_forward=1024):
+    """``(y_first, mean, var)`` of M generator samples per input, like the reference's
+    ``y = torch.stack([generate(x) for _ in range(M)]); y[0], y.mean(0), y.var(0)`` (models/cgan_regression.py:164-166,
+    cvae_regression.py:138-140), but with the M noise realisations folded into the batch axis (up to ``images_per_forward``
+    images per forward pass, running sums in float64) so that the tensor-core kernels see full persistent grids instead of
+    1000 launches of 64 images, and no (M, B, 2, ny, nx) tensor is materialised."""
+    import torch
+    B = x.shape[0]
+    rep = max(1, min(int(M), images_per_forward // max(B, 1)))
+    first = None
+    s = torch.zeros(x.shape[0:1] + (2,) + x.shape[2:], dtype=torch.float64, device=x.device)
+    s2 = torch.zeros_like(s)
+    done = 0
+    while done < M:
+        r = min(rep, M - done)
+        y = generate(x.repeat((r, 1, 1, 1))).reshape((r, B) + tuple(s.shape[1:]))
+        if first is None:
+            first = y[0].clone()
+        yd = y.double()
+        s += yd.sum(dim=0)
+        s2 += (yd * yd).sum(dim=0)
+        done += r
+    mean = s / M
+    var = (s2 - M * mean * mean) / max(M - 1, 1)           # unbiased, like torch.var
+    return first, mean.float(), var.clamp_min(0).float()

@@ -11,7 +11,7 @@ import torch
 
 from .. import _lib
 from ..tools.cnn_tools import AndrewCNN, apply_function, extract
-from ._cnn_closure import CNNClosure, make_dataset
+from ._cnn_closure import CNNClosure, batched_mean_var, make_dataset
 
 
 class CVAERegression(CNNClosure):
@@ -44,8 +44,7 @@ class CVAERegression(CNNClosure):
         return self.decoder(torch.cat([x, z], dim=1))
 
     def generate_mean_var(self, x, M):
-        y = torch.stack([self.generate(x) for _ in range(M)], dim=0)
-        return y[0], y.mean(dim=0), y.var(dim=0)
+        return batched_mean_var(self.generate, x, M)
 
     def generate_latent_noise(self, ny, nx):
         return np.random.randn(1, self.n_latent, ny, nx).astype('float32')

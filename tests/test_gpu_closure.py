@@ -320,3 +320,35 @@ def test_closure_callable_accepts_a_batched_host_model(tmp_path):
         yb = model.predict_snapshot(mb, z[b:b + 1])
         yb = yb - yb.mean(axis=(-2, -1), keepdims=True)
         assert rel(y[b], yb) < FP32_TOL
+
+
+def test_offline_predict_statistics_with_batched_noise(tmp_path):
+    """``predict(ds, M)`` (models/cgan_regression.py:173-183): mean / variance of M generator samples per snapshot.  The M
+    noise realisations are folded into the batch axis; the statistics must agree with the reference's stack-and-reduce
+    within Monte-Carlo error, and a deterministic 'generator' must reproduce mean and variance exactly."""
+    from pyqg_generative_b200.models._cnn_closure import batched_mean_var
+    from pyqg_generative_b200.models.cgan_regression import CGANRegression
+    g = torch.Generator(device='cuda').manual_seed(1)
+    x = torch.randn(5, 2, 16, 16, device='cuda', generator=g)
+
+    def fake(xx):            # sample k of input b = x_b * (1 + k/10): known mean and variance
+        r = xx.shape[0] // 5
+        k = torch.arange(fake.k, fake.k + r, device='cuda', dtype=torch.float32).repeat_interleave(5).reshape(-1, 1, 1, 1)
+        fake.k += r
+        return xx * (1 + k / 10)
+    fake.k = 0
+    first, mean, var = batched_mean_var(fake, x, 37, images_per_forward=40)
+    ks = 1 + torch.arange(37, device='cuda') / 10
+    assert torch.allclose(first, x) and torch.allclose(mean, x * ks.mean(), rtol=1e-5, atol=1e-6)
+    assert torch.allclose(var, x * x * ks.var(), rtol=1e-4, atol=1e-7)
+    model = CGANRegression(folder=write_model_folder(tmp_path, 'gan'), nx=48, precision='tc')
+    c = golden('closure_48.npz')
+    ds = {'q': np.repeat(c['q'][None, None], 3, axis=1).astype('float32')}            # (run=1, time=3, lev, y, x)
+    out = model.predict(ds, M=256)
+    y, mean, var = out['q_forcing_advection'], out['q_forcing_advection_mean'], out['q_forcing_advection_var']
+    assert y.shape == mean.shape == var.shape == (1, 3, 2, 48, 48) and (var >= 0).all()
+    # identical inputs at the three times: independent Monte-Carlo estimates of the same mean field
+    sem = np.sqrt((var[0, 0] + var[0, 1]) / 256)                                        # per-pixel standard error of the difference
+    assert (np.abs(mean[0, 0] - mean[0, 1]) < 7 * sem + 1e-3 * np.abs(mean).max()).all()
+    assert (np.abs(y[0, 0] - mean[0, 0]) < 7 * np.sqrt(var[0, 0]) + 1e-3 * np.abs(mean).max()).all()
+    assert np.abs(mean[0, 0] - mean[0, 1]).max() > 0                                    # the three estimates are independent
