@@ -35,12 +35,18 @@ def run(count, offset):
 count, offset = parallel.shard_members(TOTAL, rank, world)
 m = run(count, offset)
 ke, en, n = parallel.ensemble_spectra(m.spectra_sums())
+diag, nd = parallel.ensemble_diagnostics(m.diagnostic_sums())       # all time-averaged pyqg diagnostics in one all-reduce
 kebar = parallel.ensemble_ke(m.diagnostics()[0])
 if rank == 0:
     ref = run(TOTAL, 0)
     ke0, en0, n0 = ref.spectra_sums()
-    assert n == n0 == TOTAL * 5, (n, n0)
+    assert n == n0 == nd == TOTAL * 4, (n, n0, nd)      # sampled before the steps starting at tc = 4, 6, 8, 10
     err = np.abs(ke - ke0 / n0).max() / np.abs(ke0 / n0).max()
+    d0 = ref.averaged_diagnostics()
+    for k in ('KEflux', 'APEflux', 'APEgenspec', 'KEfrictionspec', 'paramspec'):
+        e = np.abs(diag[k] - d0[k]).max() / np.abs(d0[k]).max()
+        assert e < 1e-11, (k, e)
+    print('world %d: budget terms of the sharded ensemble equal the single-GPU ensemble to 1e-11' % world)
     errq = np.abs(ref.q[offset:offset + count] - m.q).max()
     print('world %d: ensemble KEspec rel diff vs single GPU %.2e, ensemble KE %.6e vs %.6e, shard state diff %.1e'
           % (world, err, kebar, ref.diagnostics()[0].mean(), errq))
