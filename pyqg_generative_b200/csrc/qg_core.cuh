@@ -140,6 +140,12 @@ QGB_HD void fft_stage_r(cplx* buf, const cplx* tw, int N, int es, int ls, int nl
     cplx* p = buf + line * ls + (blk * n + j2) * es;
     if (r == 4) {
       cplx x0 = p[0], x1 = p[step], x2 = p[2 * step], x3 = p[3 * step];
+      if (m == 1) {                 // last forward / first inverse stage: all twiddles are 1 (folds away when n is constant)
+        cplx t0 = cadd(x0, x2), t1 = csub(x0, x2), t2 = cadd(x1, x3), d = csub(x1, x3);
+        cplx t3 = cmake(-sgn * d.y, sgn * d.x);
+        p[0] = cadd(t0, t2); p[step] = cadd(t1, t3); p[2 * step] = csub(t0, t2); p[3 * step] = csub(t1, t3);
+        continue;
+      }
       if (inverse) {
         x1 = cmulc(x1, tw[j2 * tws]);
         x2 = cmulc(x2, tw[2 * j2 * tws]);
