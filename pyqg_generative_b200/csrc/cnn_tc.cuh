@@ -441,21 +441,34 @@ __global__ void __launch_bounds__(FUSE ? 640 : 384, 1) conv_tc_kernel(const __gr
     uint32_t ia = 0, iw = 0, it = 0;
     // The elected lane runs the WHOLE persistent loop (barrier waits included): no per-row elect / reconvergence, so the
     // tensor-pipe queue does not drain between tap columns.
+    // Every mbarrier wait costs the issuing thread ~85 clk even when the barrier has completed, and the tensor-pipe queue
+    // holds only a few hundred clocks of work: a per-tile timeline of the thin layers (2.6 k clk per tile) showed a ~650 clk
+    // bubble between the last MMA of one tile and the first of the next.  So the waits for the NEXT tile's accumulator
+    // and first activation stage are taken while the last tap column of the current tile is still queued, and resident
+    // weight stages are only waited for on the first tile.
+    bool ahead = false;     // acc_empty / a_full of the coming tile were already waited for
     if (ptx::elect_one_sync()) {
     for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x, ++it) {
       const uint32_t as = it % C::NACC;
-      ptx::mbar_wait(&acc_empty[as], ((it / C::NACC) & 1) ^ 1);
-      ptx::tc_fence_after();
+      if (!ahead) {
+        ptx::mbar_wait(&acc_empty[as], ((it / C::NACC) & 1) ^ 1);
+        ptx::tc_fence_after();
+      }
       const uint32_t dbase = tmem_base + as * (T * C::DCOLS);
       for (int c = 0; c < C::NCHUNK; ++c, ++ia) {
         const uint32_t sa = ia % C::NA;
-        ptx::mbar_wait(&a_full[sa], (ia / C::NA) & 1);
-        ptx::tc_fence_after();
+        if (!(ahead && c == 0)) {
+          ptx::mbar_wait(&a_full[sa], (ia / C::NA) & 1);
+          ptx::tc_fence_after();
+        }
+        if (c == 0) ahead = false;
 #pragma unroll
         for (int dx = 0; dx < KS; ++dx, ++iw) {
           const uint32_t sw = C::W_RESIDENT ? (uint32_t)(c * KS + dx) : iw % C::NW;
-          ptx::mbar_wait(&w_full[sw], C::W_RESIDENT ? 0u : (iw / C::NW) & 1);
-          ptx::tc_fence_after();
+          if (!C::W_RESIDENT || it == 0) {
+            ptx::mbar_wait(&w_full[sw], C::W_RESIDENT ? 0u : (iw / C::NW) & 1);
+            ptx::tc_fence_after();
+          }
           // The 64 B swizzle is a pure function of the shared-memory ADDRESS bits (verified on B200: a non-zero 'matrix
           // base offset' gives wrong results), so shifted tap windows need no descriptor fix-up.
           const uint32_t a_col = sA_u + sa * (C::A_STAGE >> 4) + dx * 4;
@@ -512,6 +525,14 @@ __global__ void __launch_bounds__(FUSE ? 640 : 384, 1) conv_tc_kernel(const __gr
                 ptx::mma_f8(dcol + t * C::DCOLS, adesc8, bdesc8, make_idesc_f16(128, n8), 1u);
               }
             }
+          }
+          if (dx == KS - 1 && c == C::NCHUNK - 1 && tile + (int)gridDim.x < P.num_tiles) {
+            // look ahead while the MMAs just issued execute (no dependence on this tile's commits: other ring slots)
+            const uint32_t nas = (it + 1) % C::NACC, nsa = (ia + 1) % C::NA;
+            ptx::mbar_wait(&acc_empty[nas], (((it + 1) / C::NACC) & 1) ^ 1);
+            ptx::mbar_wait(&a_full[nsa], ((ia + 1) / C::NA) & 1);
+            ptx::tc_fence_after();
+            ahead = true;
           }
           if (!C::W_RESIDENT) ptx::tc_commit(&w_empty[sw]);               // weight column free once these MMAs have read it
           if (dx == KS - 1) {
