@@ -90,7 +90,9 @@ enum { QGB_CLOSURE_NONE = 0, QGB_CLOSURE_GAN = 1, QGB_CLOSURE_VAE = 2, QGB_CLOSU
 enum { QGB_SAMPLER_AR1 = 0, QGB_SAMPLER_CONSTANT = 1, QGB_SAMPLER_DETERMINISTIC = 2 };
 enum { QGB_PREC_FP32 = 0,  /* fp32 FFMA direct convolution (bit-for-bit deterministic, parity reference) */
        QGB_PREC_TC = 1,    /* tcgen05 implicit GEMM, fp16 split precision (<=1e-3 rel. of the fp32 reference) */
-       QGB_PREC_TC_FAST = 2 /* same with a single-pass layer 2: ~30 % faster, error up to ~2e-3 with the shipped VAE/GZ nets */ };
+       QGB_PREC_TC_FAST = 2, /* same with a single-pass layer 2: ~18 % faster, error up to ~2e-3 with the shipped VAE/GZ nets */
+       QGB_PREC_AUTO = 3   /* chosen per loaded network at its first evaluation: tc_fast if its measured relative L2 error
+                              against the fp32 path is <= 7e-4 on the actual closure input, else tc if <= 1e-3, else fp32 */ };
 
 /* One AndrewCNN (tools/cnn_tools.py:125-182) in eval mode with BatchNorm folded to a per-channel affine
  * (scale = gamma/sqrt(running_var+eps), shift = beta - running_mean*scale), laid out as torch stores it. */
@@ -111,6 +113,11 @@ int qgb_cnn_load(qgb_handle* h, int kind, int net, int nlayers, const qgb_cnn_la
 /* ChannelwiseScaler stds (tools/cnn_tools.py:524-528 normalize/denormalize), model_weight
  * (WeightedParameterization, tools/simulate.py:242) */
 int qgb_closure_config(qgb_handle* h, const float x_std[2], const float y_std[2], double weight, int precision);
+/* The precision in effect (QGB_PREC_AUTO until the first evaluation has calibrated it) and, after an AUTO calibration, the
+ * measured errors against the fp32 path: err = {tc rel-L2, tc max-norm, tc_fast rel-L2, tc_fast max-norm} (-1: not measured).
+ * The tolerance they are held to is north_star's "parameterization output <= 1e-3 relative" (apply_function output,
+ * tools/cnn_tools.py:702-735, in the relative L2 norm). */
+int qgb_closure_precision(qgb_handle* h, int* precision, double err[4]);
 /* stochastic_QGModel(sampling_type, nsteps) (tools/stochastic_pyqg.py:78-88); n_mean = M of predict_mean_snapshot
  * for the 'deterministic' sampler (models/cgan_regression.py:164-171, default 100). */
 int qgb_set_sampler(qgb_handle* h, int kind, int nsteps, int n_mean);

@@ -13,8 +13,9 @@ QGB_OK, QGB_EINVAL, QGB_ECUDA, QGB_ESTATE, QGB_EUNSUPPORTED = 0, -1, -2, -3, -4
 (F_Q, F_QH, F_PH, F_U, F_V, F_DQHDT, F_FORCING, F_NOISE, F_P) = range(9)
 CLOSURE_NONE, CLOSURE_GAN, CLOSURE_VAE, CLOSURE_GZ, CLOSURE_OLS, CLOSURE_RAW = range(6)
 SAMPLER_AR1, SAMPLER_CONSTANT, SAMPLER_DETERMINISTIC = range(3)
-PREC_FP32, PREC_TC, PREC_TC_FAST = 0, 1, 2
-PRECISIONS = {'fp32': PREC_FP32, 'tc': PREC_TC, 'tc_fast': PREC_TC_FAST}
+PREC_FP32, PREC_TC, PREC_TC_FAST, PREC_AUTO = 0, 1, 2, 3
+PRECISIONS = {'fp32': PREC_FP32, 'tc': PREC_TC, 'tc_fast': PREC_TC_FAST, 'auto': PREC_AUTO}
+PRECISION_NAMES = {v: k for k, v in PRECISIONS.items()}
 
 
 class QgbConfig(ctypes.Structure):
@@ -44,6 +45,7 @@ SYMBOLS = {
     'qgb_get_time': (_i, [_vp, ctypes.POINTER(_d), ctypes.POINTER(ctypes.c_int64)]),
     'qgb_cnn_load': (_i, [_vp, _i, _i, _i, ctypes.POINTER(QgbCnnLayer)]),
     'qgb_closure_config': (_i, [_vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), _d, _i]),
+    'qgb_closure_precision': (_i, [_vp, ctypes.POINTER(_i), ctypes.POINTER(_d)]),
     'qgb_set_sampler': (_i, [_vp, _i, _i, _i]),
     'qgb_seed': (_i, [_vp, ctypes.c_uint64]),
     'qgb_set_latent': (_i, [_vp, _vp, _i, _i, _vp]),

@@ -13,10 +13,10 @@
 
 #include "../../include/qgb200.h"
 #include "closure.cuh"
-#include "cnn_tc.cuh"
+#include "cnn_tc_host.hpp"
 #include "operators.cuh"
 #include "qg_host.hpp"
-#include "spectral.cuh"
+#include "spectral_host.hpp"
 
 using namespace qgb;
 
@@ -63,6 +63,7 @@ struct qgb_handle {
   // closure
   int kind = QGB_CLOSURE_NONE; int precision = QGB_PREC_FP32;
   DevNet nets[2];
+  bool calibrated = false; int auto_precision = QGB_PREC_TC;   // per-network precision choice (QGB_PREC_AUTO)
   float x_std[2] = {1.f, 1.f}, y_std[2] = {1.f, 1.f}; double weight = 1.0;
   int sampler = QGB_SAMPLER_AR1, sampler_nsteps = 1, n_mean = 100;
   bool noise_init = false; long long const_counter = 0; uint32_t draw = 0; uint64_t seed = 0x5eed5eedULL;
@@ -75,6 +76,7 @@ struct qgb_handle {
   double* dq = nullptr;     // closure forcing (B,2,N,N), not demeaned
   double* dq_dm = nullptr;  // demeaned copy served to qgb_get
   bool dq_valid = false;
+  double calib_err[4] = {-1.0, -1.0, -1.0, -1.0};   // measured rel-L2 / max-norm error of tc, tc_fast against fp32
   double* dq_ext = nullptr; bool ext_set = false;  // externally supplied forcing (qgb_set_forcing)
   float* act[2] = {nullptr, nullptr}; size_t act_floats = 0; int act_chunk = 0;  // fp32 path ping-pong activations
   TcWorkspace tcw;
@@ -127,49 +129,17 @@ StepIO base_io(qgb_handle* h) {
   return io;
 }
 
+SpectralPlan make_plan(const qgb_handle* h) {
+  SpectralPlan p;
+  p.N = h->ht.N; p.members = h->cfg.members; p.grid = h->grid; p.nthreads = h->nthreads; p.smem = h->smem;
+  p.fixed = h->fixed; p.nt64 = h->nt64; p.large = h->large; p.cluster = h->cluster; p.large_lines = h->large_lines;
+  p.large_smem = h->large_smem; p.scratch = h->scratch; p.red_scratch = h->red_scratch; p.true_pos = h->d_pos;
+  return p;
+}
+
 int launch_program(qgb_handle* h, const StepIO& io, int prog, cudaStream_t st, const Tables* Tov = nullptr) {
-  const Tables& TT = Tov ? *Tov : h->T;
-  if (h->large) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(h->grid);
-    cfg.blockDim = dim3(h->nthreads);
-    cfg.dynamicSmemBytes = h->large_smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = h->cluster;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    // compile-time grid size for the power-of-two production sizes (index arithmetic folds to shifts), generic otherwise
-    auto kern = h->ht.N == 128 ? qg_program_cluster_kernel<128> : h->ht.N == 256 ? qg_program_cluster_kernel<256>
-              : h->ht.N == 512 ? qg_program_cluster_kernel<512> : h->ht.N == 1024 ? qg_program_cluster_kernel<1024>
-                                                                                  : qg_program_cluster_kernel<0>;
-    CUDA_TRY(h, cudaLaunchKernelEx(&cfg, kern, TT, io, prog, h->cfg.members, h->scratch, h->red_scratch, h->large_lines,
-                                   (const short*)h->d_pos));
-    QGB_COUNT_LAUNCH();
-    return QGB_OK;
-  }
-  const bool is_step = prog == PROG_STEP || prog == PROG_STEP_DQ || prog == PROG_STEP_DQ_RAW;
-  if (is_step && h->fixed) {
-    switch (h->ht.N) {
-      case 32: qg_step_fixed_kernel<32, 256><<<h->grid, 256, h->smem, st>>>(TT, io, prog, h->cfg.members); break;
-      case 48: qg_step_fixed_kernel<48, 256><<<h->grid, 256, h->smem, st>>>(TT, io, prog, h->cfg.members); break;
-      case 64:
-        if (h->nt64 == 512) qg_step_fixed_kernel<64, 512><<<h->grid, 512, h->smem, st>>>(TT, io, prog, h->cfg.members);
-        else if (h->nt64 == 384) qg_step_fixed_kernel<64, 384><<<h->grid, 384, h->smem, st>>>(TT, io, prog, h->cfg.members);
-        else qg_step_fixed_kernel<64, 256><<<h->grid, 256, h->smem, st>>>(TT, io, prog, h->cfg.members);
-        break;
-      default: qg_step_fixed_kernel<96, 512><<<h->grid, 512, h->smem, st>>>(TT, io, prog, h->cfg.members); break;
-    }
-    QGB_COUNT_LAUNCH();
-    CUDA_TRY(h, cudaGetLastError());
-    return QGB_OK;
-  }
-  qg_program_kernel<<<h->grid, h->nthreads, h->smem, st>>>(TT, io, prog, h->cfg.members);
+  CUDA_TRY(h, spectral_launch(make_plan(h), Tov ? *Tov : h->T, io, prog, st));
   QGB_COUNT_LAUNCH();
-  CUDA_TRY(h, cudaGetLastError());
   return QGB_OK;
 }
 
@@ -278,6 +248,84 @@ int draw_latent(qgb_handle* h, double a, double b, int replace, cudaStream_t st)
   return QGB_OK;  // ols: generate_latent_noise returns 0 (models/ols_model.py:68-69)
 }
 
+// ---- per-network precision calibration (QGB_PREC_AUTO) ---------------------------------------------------------------
+// partial sums of one comparison: out[4*block + {0,1,2,3}] = sum (y-ref)^2, sum ref^2, max |y-ref|, max |ref|
+__global__ void err_partial_kernel(const float* __restrict__ y, const float* __restrict__ ref, long long n, double* __restrict__ out) {
+  __shared__ double sh[4][256];
+  double d2 = 0.0, r2 = 0.0, dm = 0.0, rm = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double r = ref[i], d = (double)y[i] - r;
+    d2 += d * d; r2 += r * r; dm = fmax(dm, fabs(d)); rm = fmax(rm, fabs(r));
+  }
+  sh[0][threadIdx.x] = d2; sh[1][threadIdx.x] = r2; sh[2][threadIdx.x] = dm; sh[3][threadIdx.x] = rm;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      sh[0][threadIdx.x] += sh[0][threadIdx.x + o]; sh[1][threadIdx.x] += sh[1][threadIdx.x + o];
+      sh[2][threadIdx.x] = fmax(sh[2][threadIdx.x], sh[2][threadIdx.x + o]); sh[3][threadIdx.x] = fmax(sh[3][threadIdx.x], sh[3][threadIdx.x + o]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) for (int j = 0; j < 4; ++j) out[4 * blockIdx.x + j] = sh[j][0];
+}
+
+// The split-precision tensor-core plan has two variants of layer 2 (75 % of the flops): two passes (a_hi + a_lo) w_hi ("tc") or one
+// pass a_hi w_hi ("tc_fast", ~18 % faster end to end).  Which one keeps the closure output within the 1e-3 relative (L2)
+// tolerance depends on the NETWORK (shipped GAN: 4.4e-4 single-pass; shipped VAE decoder / GZ mean net: 1.3-1.8e-3), so with
+// precision 'auto' the choice is measured once per loaded network set, at its first evaluation, on up to 16 members of the
+// actual closure input: fp32 FFMA forward (the parity reference) against both variants; tc_fast is taken when every network's
+// relative L2 error stays below kAutoFastTol (30 % margin), tc when that holds for tc, fp32 otherwise.  One-time cost: three
+// small forwards and a stream synchronisation.
+constexpr double kAutoFastTol = 7e-4, kAutoTcTol = 1e-3;
+int calibrate_precision(qgb_handle* h, cudaStream_t st) {
+  const int N = h->ht.N, B = h->cfg.members;
+  const long long npix = (long long)N * N, x_bs = (long long)h->xin_c * npix;
+  h->calibrated = true;
+  h->auto_precision = QGB_PREC_FP32;
+  for (int i = 0; i < 4; ++i) h->calib_err[i] = -1.0;
+  const int nnets = h->kind == QGB_CLOSURE_GZ ? 2 : 1;
+  for (int k = 0; k < nnets; ++k) if (!h->nets[k].tc.ready) return QGB_OK;
+  if (N % 16) return QGB_OK;
+  const int nb = B < 16 ? B : 16;
+  const size_t n = (size_t)nb * 2 * npix;
+  float* yb = nullptr; double* part = nullptr;
+  constexpr int NBLK = 64;
+  CUDA_TRY(h, dalloc(&yb, 3 * n));
+  if (cudaError_t ce = dalloc(&part, (size_t)2 * NBLK * 4); ce != cudaSuccess) { cudaFree(yb); return fail(h, QGB_ECUDA, "cudaMalloc failed"); }
+  double worst[2][2] = {{0, 0}, {0, 0}};      // [variant tc / tc_fast][rel-L2, max-norm]
+  int rc = QGB_OK;
+  for (int k = 0; k < nnets && rc == QGB_OK; ++k) {
+    const int sp = k == 1 ? 1 : 0;
+    rc = net_forward(h, k, h->xin, x_bs, yb, 2 * npix, nb, N, N, sp, 0, QGB_PREC_FP32, st);
+    if (rc == QGB_OK) rc = net_forward(h, k, h->xin, x_bs, yb + n, 2 * npix, nb, N, N, sp, 0, QGB_PREC_TC, st);
+    if (rc == QGB_OK) rc = net_forward(h, k, h->xin, x_bs, yb + 2 * n, 2 * npix, nb, N, N, sp, 0, QGB_PREC_TC_FAST, st);
+    if (rc != QGB_OK) break;
+    err_partial_kernel<<<NBLK, 256, 0, st>>>(yb + n, yb, (long long)n, part);
+    err_partial_kernel<<<NBLK, 256, 0, st>>>(yb + 2 * n, yb, (long long)n, part + NBLK * 4);
+    g_launches.fetch_add(2, std::memory_order_relaxed);
+    std::vector<double> hp((size_t)2 * NBLK * 4);
+    cudaError_t ce = cudaMemcpyAsync(hp.data(), part, hp.size() * sizeof(double), cudaMemcpyDeviceToHost, st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+    if (ce != cudaSuccess) { rc = fail(h, QGB_ECUDA, "precision calibration failed: %s", cudaGetErrorString(ce)); break; }
+    for (int v = 0; v < 2; ++v) {
+      double d2 = 0, r2 = 0, dm = 0, rm = 0;
+      for (int b = 0; b < NBLK; ++b) {
+        const double* q = hp.data() + ((size_t)v * NBLK + b) * 4;
+        d2 += q[0]; r2 += q[1]; dm = std::fmax(dm, q[2]); rm = std::fmax(rm, q[3]);
+      }
+      const double l2 = r2 > 0 ? std::sqrt(d2 / r2) : (d2 > 0 ? 1.0 : 0.0), mx = rm > 0 ? dm / rm : (dm > 0 ? 1.0 : 0.0);
+      worst[v][0] = std::fmax(worst[v][0], l2);
+      worst[v][1] = std::fmax(worst[v][1], mx);
+    }
+  }
+  cudaFree(yb); cudaFree(part);
+  if (rc != QGB_OK) return rc;
+  h->calib_err[0] = worst[0][0]; h->calib_err[1] = worst[0][1]; h->calib_err[2] = worst[1][0]; h->calib_err[3] = worst[1][1];
+  if (worst[1][0] <= kAutoFastTol) h->auto_precision = QGB_PREC_TC_FAST;
+  else if (worst[0][0] <= kAutoTcTol) h->auto_precision = QGB_PREC_TC;
+  return QGB_OK;
+}
+
 // Parameterization.__call__ body.  Returns via *computed whether a new forcing was produced.
 int closure_update(qgb_handle* h, cudaStream_t st) {
   if (h->kind == QGB_CLOSURE_NONE) return fail(h, QGB_ESTATE, "no closure loaded");
@@ -296,27 +344,36 @@ int closure_update(qgb_handle* h, cudaStream_t st) {
   if (blocks > 148 * 16) blocks = 148 * 16;
   const long long x_bs = (long long)h->xin_c * npix;
   bool compute = true;
+  int prec = h->precision;       // resolved after the noise update (the calibration evaluates the nets on the current input)
+  auto resolve = [&]() -> int {
+    if (h->precision != QGB_PREC_AUTO) return QGB_OK;
+    if (!h->calibrated) { int rc = calibrate_precision(h, st); if (rc) return rc; }
+    prec = h->auto_precision;
+    return QGB_OK;
+  };
   if (h->sampler == QGB_SAMPLER_DETERMINISTIC) {
+    if (h->precision == QGB_PREC_AUTO && !h->calibrated) { int rc0 = draw_latent(h, 0.0, 1.0, 1, st); if (rc0) return rc0; }
+    if (int rc0 = resolve()) return rc0;
     // predict_mean_snapshot: mean of M generator samples (gan/vae); the mean net (gz); the net itself (ols)
     if (h->kind == QGB_CLOSURE_GAN || h->kind == QGB_CLOSURE_VAE) {
       if (!h->yacc) CUDA_TRY(h, dalloc(&h->yacc, (size_t)total));
       for (int m = 0; m < h->n_mean; ++m) {
         int rc = draw_latent(h, 0.0, 1.0, 1, st);
         if (rc) return rc;
-        rc = net_forward(h, 0, h->xin, x_bs, h->yacc, 2 * npix, B, N, N, 0, m > 0, h->precision, st);
+        rc = net_forward(h, 0, h->xin, x_bs, h->yacc, 2 * npix, B, N, N, 0, m > 0, prec, st);
         if (rc) return rc;
       }
       finish_plain_kernel<<<blocks, 256, 0, st>>>(h->yacc, h->dq, (int)npix, total, h->y_std[0], h->y_std[1],
                                                    h->weight, 1.0f / (float)h->n_mean);
       QGB_COUNT_LAUNCH();
     } else if (h->kind == QGB_CLOSURE_GZ) {
-      int rc = net_forward(h, 0, h->xin, x_bs, h->ynet[0], 2 * npix, B, N, N, 0, 0, h->precision, st);
+      int rc = net_forward(h, 0, h->xin, x_bs, h->ynet[0], 2 * npix, B, N, N, 0, 0, prec, st);
       if (rc) return rc;
       finish_gz_kernel<<<blocks, 256, 0, st>>>(h->ynet[0], nullptr, nullptr, h->dq, (int)npix, total, h->y_std[0],
                                                 h->y_std[1], h->weight, 0);
       QGB_COUNT_LAUNCH();
     } else {
-      int rc = net_forward(h, 0, h->xin, x_bs, h->ynet[0], 2 * npix, B, N, N, 0, 0, h->precision, st);
+      int rc = net_forward(h, 0, h->xin, x_bs, h->ynet[0], 2 * npix, B, N, N, 0, 0, prec, st);
       if (rc) return rc;
       finish_plain_kernel<<<blocks, 256, 0, st>>>(h->ynet[0], h->dq, (int)npix, total, h->y_std[0], h->y_std[1],
                                                    h->weight, 1.0f);
@@ -361,15 +418,16 @@ int closure_update(qgb_handle* h, cudaStream_t st) {
   h->xi_set = false;  // an injected xi is consumed by one sampler update
   if (!compute && h->dq_valid) return QGB_OK;
   // ---- predict_snapshot ----
+  if (int rc0 = resolve()) return rc0;
   if (h->kind == QGB_CLOSURE_GZ) {
-    int rc = net_forward(h, 0, h->xin, x_bs, h->ynet[0], 2 * npix, B, N, N, 0, 0, h->precision, st);
+    int rc = net_forward(h, 0, h->xin, x_bs, h->ynet[0], 2 * npix, B, N, N, 0, 0, prec, st);
     if (rc) return rc;
-    rc = net_forward(h, 1, h->xin, x_bs, h->ynet[1], 2 * npix, B, N, N, 1, 0, h->precision, st);
+    rc = net_forward(h, 1, h->xin, x_bs, h->ynet[1], 2 * npix, B, N, N, 1, 0, prec, st);
     if (rc) return rc;
     finish_gz_kernel<<<blocks, 256, 0, st>>>(h->ynet[0], h->ynet[1], h->z64, h->dq, (int)npix, total, h->y_std[0],
                                               h->y_std[1], h->weight, 1);
   } else {
-    int rc = net_forward(h, 0, h->xin, x_bs, h->ynet[0], 2 * npix, B, N, N, 0, 0, h->precision, st);
+    int rc = net_forward(h, 0, h->xin, x_bs, h->ynet[0], 2 * npix, B, N, N, 0, 0, prec, st);
     if (rc) return rc;
     finish_plain_kernel<<<blocks, 256, 0, st>>>(h->ynet[0], h->dq, (int)npix, total, h->y_std[0], h->y_std[1],
                                                  h->weight, 1.0f);
@@ -458,26 +516,10 @@ int qgb_create(const qgb_config* cfg, qgb_handle** out) {
     qgb_destroy(h);
     return QGB_EUNSUPPORTED;
   }
-  if (!h->large) {
-    // the opt-in limit is a per-function, process-wide attribute: only ever raise it (handles of several grid sizes coexist)
-    static size_t generic_smem_limit = 0;
-    if (h->smem > generic_smem_limit) {
-      CR(cudaFuncSetAttribute(qg_program_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
-      generic_smem_limit = h->smem;
-    }
-  }
   h->fixed = !h->large && (cfg->nx == 32 || cfg->nx == 48 || cfg->nx == 64 || cfg->nx == 96) && !getenv("QGB_GENERIC_STEP");
-  if (h->fixed) {
-    if (cfg->nx == 32) CR(cudaFuncSetAttribute(qg_step_fixed_kernel<32, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
-    if (cfg->nx == 48) CR(cudaFuncSetAttribute(qg_step_fixed_kernel<48, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
-    if (cfg->nx == 64) {
-      const char* e = getenv("QGB_STEP_NT");
-      h->nt64 = e ? atoi(e) : 384;   // measured on B200: 256 -> 0.370 ms, 384 -> 0.299 ms, 512 -> 0.301 ms per 1024 members
-      CR(cudaFuncSetAttribute(qg_step_fixed_kernel<64, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
-      CR(cudaFuncSetAttribute(qg_step_fixed_kernel<64, 384>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
-      CR(cudaFuncSetAttribute(qg_step_fixed_kernel<64, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
-    }
-    if (cfg->nx == 96) CR(cudaFuncSetAttribute(qg_step_fixed_kernel<96, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+  if (h->fixed && cfg->nx == 64) {
+    const char* e = getenv("QGB_STEP_NT");
+    h->nt64 = e ? atoi(e) : 384;   // measured on B200: 256 -> 0.370 ms, 384 -> 0.299 ms, 512 -> 0.301 ms per 1024 members
   }
   h->grid = cfg->members;
   if (h->large) {
@@ -488,6 +530,14 @@ int qgb_create(const qgb_config* cfg, qgb_handle** out) {
     // 1.21 ms with 4, 0.86 ms with 2).
     h->cluster = h->ht.N <= 128 ? (4 * cfg->members <= 2 * h->nsm ? 4 : 2) : kMaxClusterSize;
     if (const char* e = getenv("QGB_CLUSTER")) { int v = atoi(e); if (v == 2 || v == 4 || v == 8) h->cluster = v; }
+    // the lines of a 1-D pass are dealt evenly to the CTAs of the cluster: the size must divide nx (nx = 162, 324, ... = 2 * 3^k
+    // only admit 2)
+    while (h->cluster > 1 && h->ht.N % h->cluster != 0) h->cluster /= 2;
+    if (h->cluster < 2) {
+      fail(nullptr, QGB_EUNSUPPORTED, "nx=%d unsupported on the cluster path (needs an even nx)", cfg->nx);
+      qgb_destroy(h);
+      return QGB_EUNSUPPORTED;
+    }
     h->nthreads = 512;
     // lines of a 1-D transform pass that a CTA stages in shared memory at a time: all it owns (N / cluster size) when that
     // leaves room for two CTAs per SM (<= 110 KB), else the largest power-of-two fraction that does
@@ -498,17 +548,6 @@ int qgb_create(const qgb_config* cfg, qgb_handle** out) {
     if (const char* e = getenv("QGB_LARGE_LINES")) { int v = atoi(e); if (v >= 1 && v <= per_cta && v * line_bytes <= 200 * 1024) lines = v; }
     h->large_lines = lines;
     h->large_smem = lines * line_bytes + (size_t)h->ht.N * sizeof(short) + 16;
-    {
-      static size_t cluster_smem_limit = 0;
-      if (h->large_smem > cluster_smem_limit) {
-        CR(cudaFuncSetAttribute(qg_program_cluster_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->large_smem));
-        CR(cudaFuncSetAttribute(qg_program_cluster_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->large_smem));
-        CR(cudaFuncSetAttribute(qg_program_cluster_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->large_smem));
-        CR(cudaFuncSetAttribute(qg_program_cluster_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->large_smem));
-        CR(cudaFuncSetAttribute(qg_program_cluster_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->large_smem));
-        cluster_smem_limit = h->large_smem;
-      }
-    }
     int clusters = (2 * h->nsm) / h->cluster;
     if (clusters > cfg->members) clusters = cfg->members;
     if (clusters < 1) clusters = 1;
@@ -516,6 +555,7 @@ int qgb_create(const qgb_config* cfg, qgb_handle** out) {
     CR(dalloc(&h->scratch, (size_t)cfg->members * h->ht.N * h->ht.P));
     CR(dalloc(&h->red_scratch, (size_t)cfg->members * 4 * h->cluster * h->nthreads));
   }
+  CR(spectral_configure(make_plan(h)));
   CR(upload(&h->d_tw, h->ht.tw));
   CR(upload(&h->d_pos, h->ht.pos));
   CR(upload(&h->d_kv, h->ht.kv));
@@ -641,7 +681,7 @@ int sample_averages(qgb_handle* h, const double* dq, cudaStream_t st) {
     h->avg_n = 0;
   }
   if (!h->d_kespec) { CUDA_TRY(h, dalloc(&h->d_kespec, (size_t)(2 * NN))); CUDA_TRY(h, dalloc(&h->d_ensspec, (size_t)(2 * NN))); }
-  spectra_kernel<<<(unsigned)((2 * NN + 127) / 128), 128, 0, st>>>(h->T, h->qh, h->cfg.members, h->d_kespec, h->d_ensspec);
+  CUDA_TRY(h, launch_spectra(h->T, h->qh, h->cfg.members, h->d_kespec, h->d_ensspec, st));
   QGB_COUNT_LAUNCH();
   add_kernel<<<(unsigned)((2 * NN + 127) / 128), 128, 0, st>>>(h->d_kespec, 2 * NN, h->avg);
   add_kernel<<<(unsigned)((2 * NN + 127) / 128), 128, 0, st>>>(h->d_ensspec, 2 * NN, h->avg + 2 * NN);
@@ -810,19 +850,22 @@ int qgb_cnn_load(qgb_handle* h, int kind, int net, int nlayers, const qgb_cnn_la
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
   for (int i = 1; i < nlayers; ++i)
     if (layers[i].cin != layers[i - 1].cout) return fail(h, QGB_EINVAL, "layer %d: cin does not match previous cout", i);
+  // validate everything before anything is freed or replaced: a failed load leaves the handle as it was
+  for (int i = 0; i < nlayers; ++i) {
+    const qgb_cnn_layer& L = layers[i];
+    if (L.cin < 1 || L.cout < 1) return fail(h, QGB_EINVAL, "layer %d: bad channel counts", i);
+    if (L.ksize != 1 && L.ksize != 3 && L.ksize != 5) return fail(h, QGB_EUNSUPPORTED, "layer %d: kernel size %d not supported (1, 3, 5)", i, L.ksize);
+    if (!L.weight || !L.bias) return fail(h, QGB_EINVAL, "layer %d: null weight/bias", i);
+    if (L.relu_bn && (!L.bn_scale || !L.bn_shift)) return fail(h, QGB_EINVAL, "layer %d: null batch-norm affine", i);
+  }
   if (kind != QGB_CLOSURE_RAW) {
     const int cin0 = (kind == QGB_CLOSURE_GAN || kind == QGB_CLOSURE_VAE) ? 4 : 2;
     if (layers[0].cin != cin0) return fail(h, QGB_EINVAL, "first layer must have %d input channels, got %d", cin0, layers[0].cin);
     if (layers[nlayers - 1].cout != 2) return fail(h, QGB_EINVAL, "last layer must have 2 output channels");
-    if (h->kind != kind) { free_net(h->nets[0]); free_net(h->nets[1]); h->dq_valid = false; h->noise_init = false; }
-    h->kind = kind;
   }
-  DevNet& N = h->nets[net];
-  free_net(N);
+  DevNet fresh;      // built aside, swapped in on success
   for (int i = 0; i < nlayers; ++i) {
     const qgb_cnn_layer& L = layers[i];
-    if (!L.weight || !L.bias) return fail(h, QGB_EINVAL, "layer %d: null weight/bias", i);
-    if (L.relu_bn && (!L.bn_scale || !L.bn_shift)) return fail(h, QGB_EINVAL, "layer %d: null batch-norm affine", i);
     DevNetLayer D;
     D.cin = L.cin; D.cout = L.cout; D.ks = L.ksize; D.relu_bn = L.relu_bn;
     const int co_t = L.cout <= 4 ? 2 : 32;
@@ -834,25 +877,47 @@ int qgb_cnn_load(qgb_handle* h, int kind, int net, int nlayers, const qgb_cnn_la
         for (int t = 0; t < kk; ++t) wp[((size_t)ci * kk + t) * D.cout_pad + co] = L.weight[((size_t)co * L.cin + ci) * kk + t];
     std::vector<float> bias(L.bias, L.bias + L.cout), s(L.cout, 1.f), tt(L.cout, 0.f);
     if (L.relu_bn) { s.assign(L.bn_scale, L.bn_scale + L.cout); tt.assign(L.bn_shift, L.bn_shift + L.cout); }
-    CUDA_TRY(h, upload(&D.wp, wp));
-    CUDA_TRY(h, upload(&D.bias, bias));
-    CUDA_TRY(h, upload(&D.bn_s, s));
-    CUDA_TRY(h, upload(&D.bn_t, tt));
-    N.layers.push_back(D);
+    cudaError_t ce = upload(&D.wp, wp);
+    if (ce == cudaSuccess) ce = upload(&D.bias, bias);
+    if (ce == cudaSuccess) ce = upload(&D.bn_s, s);
+    if (ce == cudaSuccess) ce = upload(&D.bn_t, tt);
+    fresh.layers.push_back(D);        // (pushed first so that free_net releases a partial upload too)
+    if (ce != cudaSuccess) {
+      free_net(fresh);
+      return fail(h, QGB_ECUDA, "qgb_cnn_load: upload of layer %d failed: %s", i, cudaGetErrorString(ce));
+    }
   }
   std::string e;
-  tc_pack_net(N.tc, nlayers, layers, &e);  // leaves N.tc.ready == false if the architecture is not the AndrewCNN default
+  if (tc_pack_net(fresh.tc, nlayers, layers, &e) == QGB_ECUDA) {   // (other failures just leave fresh.tc.ready == false: fp32 only)
+    free_net(fresh);
+    return fail(h, QGB_ECUDA, "qgb_cnn_load: packing the tensor-core weights failed");
+  }
+  if (kind != QGB_CLOSURE_RAW) {
+    if (h->kind != kind) { free_net(h->nets[0]); free_net(h->nets[1]); h->dq_valid = false; h->noise_init = false; }
+    h->kind = kind;
+  }
+  free_net(h->nets[net]);
+  h->nets[net] = std::move(fresh);
+  h->calibrated = false;
   return kind == QGB_CLOSURE_RAW ? QGB_OK : ensure_closure_buffers(h);
 }
 
 int qgb_closure_config(qgb_handle* h, const float x_std[2], const float y_std[2], double weight, int precision) {
   if (!h || !x_std || !y_std) return fail(h, QGB_EINVAL, "null argument");
-  if (precision < QGB_PREC_FP32 || precision > QGB_PREC_TC_FAST) return fail(h, QGB_EINVAL, "unknown precision %d", precision);
+  if (precision < QGB_PREC_FP32 || precision > QGB_PREC_AUTO) return fail(h, QGB_EINVAL, "unknown precision %d", precision);
   h->x_std[0] = x_std[0]; h->x_std[1] = x_std[1];
   h->y_std[0] = y_std[0]; h->y_std[1] = y_std[1];
   h->weight = weight;
+  if (precision != h->precision) h->calibrated = false;
   h->precision = precision;
   h->x_valid = false;
+  return QGB_OK;
+}
+
+int qgb_closure_precision(qgb_handle* h, int* precision, double err[4]) {
+  if (!h) return QGB_EINVAL;
+  if (precision) *precision = h->precision == QGB_PREC_AUTO ? (h->calibrated ? h->auto_precision : QGB_PREC_AUTO) : h->precision;
+  if (err) for (int i = 0; i < 4; ++i) err[i] = h->calib_err[i];
   return QGB_OK;
 }
 
@@ -860,7 +925,6 @@ int qgb_set_sampler(qgb_handle* h, int kind, int nsteps, int n_mean) {
   if (!h) return QGB_EINVAL;
   if (kind < QGB_SAMPLER_AR1 || kind > QGB_SAMPLER_DETERMINISTIC) return fail(h, QGB_EINVAL, "Unknown sampling type");
   if (kind == QGB_SAMPLER_CONSTANT && nsteps < 1) return fail(h, QGB_EINVAL, "constant sampler needs nsteps >= 1");
-  if (nsteps == 0) return fail(h, QGB_EINVAL, "nsteps must be non-zero");
   h->sampler = kind; h->sampler_nsteps = nsteps; h->n_mean = n_mean > 0 ? n_mean : 100;
   h->noise_init = false; h->const_counter = 0;
   return QGB_OK;
@@ -937,6 +1001,8 @@ int qgb_cnn_forward(qgb_handle* h, int net, const float* x, float* y, int batch,
   cudaStream_t st = S(stream);
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
   const int cin = h->nets[net].layers.front().cin, cout = h->nets[net].layers.back().cout;
+  if (precision == QGB_PREC_AUTO)     // the calibrated choice of the coupled closure if there is one, else the safe tensor-core plan
+    precision = h->calibrated ? h->auto_precision : ((h->nets[net].tc.ready && ny % 16 == 0 && nx % 16 == 0) ? QGB_PREC_TC : QGB_PREC_FP32);
   const long long x_bs = (long long)cin * ny * nx, y_bs = (long long)cout * ny * nx;
   if (on_device) return net_forward(h, net, x, x_bs, y, y_bs, batch, ny, nx, softplus, 0, precision, st);
   float *dx = nullptr, *dy = nullptr;
@@ -963,7 +1029,7 @@ int qgb_diag(qgb_handle* h, double* ke, double* cfl, int32_t* flags, int on_devi
   int rc = launch_program(h, io, PROG_DIAG, st);
   if (rc) return rc;
   const int B = h->cfg.members;
-  diag_finish_kernel<<<(B + 127) / 128, 128, 0, st>>>(h->red, B, h->cfg.dt / h->ht.dx, h->d_ke, h->d_cfl, h->d_flags);
+  CUDA_TRY(h, launch_diag_finish(h->red, B, h->cfg.dt / h->ht.dx, h->d_ke, h->d_cfl, h->d_flags, st));
   QGB_COUNT_LAUNCH();
   CUDA_TRY(h, cudaGetLastError());
   const cudaMemcpyKind kd = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
@@ -980,7 +1046,7 @@ int qgb_diag_spectra(qgb_handle* h, double* kespec, double* ensspec, int on_devi
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
   const int n = 2 * h->ht.N * h->ht.NK;
   if (!h->d_kespec) { CUDA_TRY(h, dalloc(&h->d_kespec, (size_t)n)); CUDA_TRY(h, dalloc(&h->d_ensspec, (size_t)n)); }
-  spectra_kernel<<<(n + 127) / 128, 128, 0, st>>>(h->T, h->qh, h->cfg.members, h->d_kespec, h->d_ensspec);
+  CUDA_TRY(h, launch_spectra(h->T, h->qh, h->cfg.members, h->d_kespec, h->d_ensspec, st));
   QGB_COUNT_LAUNCH();
   CUDA_TRY(h, cudaGetLastError());
   const cudaMemcpyKind kd = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;

@@ -42,6 +42,7 @@
 #include <vector>
 
 #include "../../include/qgb200.h"
+#include "cnn_tc_host.hpp"
 
 #ifndef QGB_TC_NW_OVERRIDE
 #define QGB_TC_NW_OVERRIDE 0
@@ -249,18 +250,6 @@ __device__ __forceinline__ float softplus_f(float v) { return v > 20.f ? v : log
 // [HY][HX][64 B] with 16-byte chunks XOR-swizzled by address bits 7-8 -- the K-major SWIZZLE_64B UMMA layout.
 struct TcMaps {
   CUtensorMap hi, lo;
-};
-// Epilogue: y = relu(acc / wscale + b) * s + t  (eval-mode BatchNorm after the ReLU).  The constants travel as a kernel
-// parameter.  Layers with COUT <= 32 keep them in REGISTERS for the whole persistent loop, with the BN scale folded on the
-// host into the layer's own weights and bias (relu(z) s = sign(s) relu(|s| z); the sign goes into the next layer's weights)
-// so that two constants per channel remain.  A first version read bias / scale / shift from shared memory everywhere: 24
-// LDS.128 per 32 channels took 25 % of the shared-memory data pipe that the MMAs' operand reads saturate in the thin
-// layers (ncu l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld, profiles/r1_history.md).  The wide layers (1 and 2) spend
-// 10-40x more MMA time per epilogue item and keep the three constants in shared memory, unfolded.  The SHIFT is never
-// folded forward: storing relu(|s| z) without it costs up to 16x in absolute precision where the ReLU output has a large
-// mean (measured 1.2e-3 on the shipped VAE decoder instead of 4e-4).
-struct TcEpi {
-  float b[128], s[128], t[128];
 };
 
 // FUSE = 0: activations arrive by TMA.  FUSE = cin0 (4 or 2): layer 1 -- four extra warps BUILD the 5x5 im2col operand
@@ -676,41 +665,17 @@ __global__ void __launch_bounds__(FUSE ? 640 : 384, 1) conv_tc_kernel(const __gr
 }
 
 // ------------------------------------------------------------------------------------------------ host side ----
-struct TcLayer {
-  int cin = 0, cout = 0, ks = 0, relu = 0;      // MMA-level shapes (padded): cin multiple of 32, cout = MMA N
-  int real_cout = 0, passes = 3;
-  __half* w = nullptr;
-  TcEpi epi;
-  float inv_wscale = 1.f;
-};
-struct TcNet {
-  bool ready = false;
-  int cin0 = 0;          // real input channels of the network (4 or 2)
-  int kp = 0;            // padded im2col K of layer 1 (128 or 64)
-  std::vector<TcLayer> layers;
-  TcLayer l2_fast;       // layer 2 packed for the single-pass variant (QGB_PREC_TC_FAST)
-};
-struct TcWorkspace {
-  __half* buf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // a0_hi, a0_lo, ping hi/lo, pong hi/lo
-  size_t halves[6] = {0, 0, 0, 0, 0, 0};
-  // per-layer timing hook (qgb_profile_begin/end): layer index to bracket with events, filled by api.cu
-  int prof_layer = -1;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>>* prof_events = nullptr;
-  long long* prof_images = nullptr;
-  long long last_launches = 0;   // kernels launched by the latest tc_forward
-};
-
-inline void tc_free_net(TcNet& n) {
+// (TcLayer / TcNet / TcWorkspace live in cnn_tc_host.hpp)
+void tc_free_net(TcNet& n) {
   for (auto& L : n.layers) cudaFree(L.w);
   cudaFree(n.l2_fast.w);
   n.l2_fast = TcLayer();
   n.layers.clear();
   n.ready = false;
 }
-inline void tc_free_workspace(TcWorkspace& w) {
+void tc_free_workspace(TcWorkspace& w) {
   for (int i = 0; i < 6; ++i) { cudaFree(w.buf[i]); w.buf[i] = nullptr; w.halves[i] = 0; }
 }
-inline int tc_launches_per_forward(const TcNet& n) { return n.ready ? (int)n.layers.size() : 0; }
 
 // Pack one layer.  Weight stage = one (32-channel chunk, tap COLUMN kx): fp16 [4 j][ky descending][WROWS][8] (values scaled
 // by 2^k; WROWS = [w_hi | w_lo] x cout_p for the N-concatenated layers, [plane][cout_p] otherwise) followed (lo8) by
@@ -767,7 +732,7 @@ inline bool tc_pack_layer(TcLayer& L, int cin_p, int cout_p, int ks, int passes,
 }
 
 // Accepts exactly the default AndrewCNN architecture: (4|2)->128 (5x5) ->64 (5x5) ->32 (3x3) -> 4 x [32->32 (3x3)] -> 2 (3x3)
-inline int tc_pack_net(TcNet& n, int nlayers, const qgb_cnn_layer* L, std::string* err) {
+int tc_pack_net(TcNet& n, int nlayers, const qgb_cnn_layer* L, std::string* err) {
   tc_free_net(n);
   static const int cin[8] = {0, 128, 64, 32, 32, 32, 32, 32}, cout[8] = {128, 64, 32, 32, 32, 32, 32, 2};
   static const int ks[8] = {5, 5, 3, 3, 3, 3, 3, 3};
@@ -878,11 +843,14 @@ inline cudaError_t tc_launch(const TcConvParams& P, const TcEpi& E, int nimg, in
     M.lo = M.hi;
   }
   auto kern = conv_tc_kernel<CIN, COUT, KS, PASSES, T, OUTMODE, FUSE, NH>;
-  static bool configured = false;
-  if (!configured) {
+  // the opt-in shared-memory limit is a per-device (per-context) function attribute: track it per device ordinal
+  static bool configured[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM + (FUSE ? 6400 : 0));
     if (e != cudaSuccess) return e;
-    configured = true;
+    if (dev >= 0 && dev < 64) configured[dev] = true;
   }
   const int grid = P.num_tiles < nsm ? P.num_tiles : nsm;
   cudaLaunchConfig_t cfg = {};
@@ -930,9 +898,9 @@ inline cudaError_t tc_launch_T(TcTile tl, const TcConvParams& P, const TcEpi& E,
   return tc_launch<CIN, COUT, KS, PASSES, 2, OUTMODE>(P, E, nimg, nsm, st);
 }
 
-inline int tc_forward(const TcNet& net, TcWorkspace& ws, const float* x, long long x_bs, float* y, long long y_bs,
+int tc_forward(const TcNet& net, TcWorkspace& ws, const float* x, long long x_bs, float* y, long long y_bs,
                       int batch, int ny, int nx, int softplus, int accumulate, int nsm, cudaStream_t st, std::string* err,
-                      bool fast_l2 = false) {
+                      bool fast_l2) {
   if (!net.ready) { *err = "tcgen05 path: network not packed"; return QGB_EUNSUPPORTED; }
   if (ny % 16 || nx % 16) { *err = "tcgen05 path needs ny and nx to be multiples of 16 (use precision='fp32')"; return QGB_EUNSUPPORTED; }
   // Images per launch: large launches amortise the persistent-CTA ramp/tail (measured on B200, 64^2: 128 -> 150 k,

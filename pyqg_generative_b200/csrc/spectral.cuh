@@ -5,16 +5,9 @@
 #include <cuda_runtime.h>
 
 #include "qg_core.cuh"
+#include "spectral_host.hpp"
 
 namespace qgb {
-
-inline size_t program_smem_bytes(int N, int P, int nthreads) {
-  size_t b = (size_t)N * P * sizeof(cplx);  // buf
-  b += (size_t)N * sizeof(cplx);            // twiddles
-  b += ((size_t)N * sizeof(short) + 15) / 16 * 16;
-  b += 4 * (size_t)nthreads * sizeof(double);  // reduction scratch
-  return b;
-}
 
 __global__ void __launch_bounds__(512) qg_program_kernel(const __grid_constant__ Tables T,
                                                          const __grid_constant__ StepIO io, int prog, int members) {
@@ -119,7 +112,6 @@ __global__ void __launch_bounds__(NT) qg_step_fixed_kernel(const __grid_constant
 // and a thread-block CLUSTER of 4 or 8 CTAs per member.  Threads are numbered across the cluster, phases are separated
 // by the hardware cluster barrier (release/acquire at cluster scope, which also invalidates L1), tables are read in place.
 // The 1-D passes of the transforms run per CTA in shared memory (fft2d_pass_tiled): 2 cluster phases per 2-D transform.
-constexpr int kMaxClusterSize = 8;   // portable limit; the size is chosen per handle (4 for N <= 128, 8 above)
 
 __device__ __forceinline__ void cluster_barrier() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");

@@ -43,6 +43,12 @@ class WeightedParameterization(QParameterization):
         self.weight = weight
 
     def __call__(self, m):
+        inner = self.param
+        while isinstance(inner, WeightedParameterization):
+            inner = inner.param
+        if getattr(m, '_closure', None) is inner and inner is not None:
+            # attached device closure: the engine already applies the (product of the) weights folded in at attach time
+            return inner(m)
         return np.array(self.param(m)) * self.weight
 
 

@@ -91,6 +91,8 @@ class EnsembleQGModel(object):
                  parameterization=None, diagnostics_list='all', ntd=1, log_level=1, logfile=None,
                  beta=1.5e-11, rd=15000.0, delta=0.25, H1=500, U1=0.025, U2=0.0,
                  sampling_type='AR1', nsteps=1, precision='fp32', seed=None, squeeze=False, **kwargs):
+        if kwargs:      # pyqg.Model.__init__ takes no **kwargs: unknown keywords are a TypeError there too
+            raise TypeError("__init__() got an unexpected keyword argument '%s'" % sorted(kwargs)[0])
         if nz != 2:
             raise ValueError('QGModel is a two-layer model')
         if (ny is not None and ny != nx) or (W is not None and W != L):
@@ -333,6 +335,15 @@ class EnsembleQGModel(object):
             raise ValueError('latent noise must be float32 or float64')
         xi = xi.reshape(self.members, 2, self.ny, self.nx)
         _lib.check(self._lib.qgb_set_latent(self._h, xi.ctypes.data, dtype, 0, self._stream()), self._h)
+
+    def closure_precision(self):
+        """(name, errors): the CNN precision in effect ('auto' until the first closure evaluation has calibrated it) and, for
+        precision='auto', the measured errors against the fp32 path: dict(tc_l2, tc_max, tc_fast_l2, tc_fast_max)."""
+        pr = ctypes.c_int(0)
+        err = (ctypes.c_double * 4)()
+        _lib.check(self._lib.qgb_closure_precision(self._h, ctypes.byref(pr), err), self._h)
+        names = ('tc_l2', 'tc_max', 'tc_fast_l2', 'tc_fast_max')
+        return _lib.PRECISION_NAMES[pr.value], {k: (v if v >= 0 else None) for k, v in zip(names, err)}
 
     def seed(self, seed):
         _lib.check(self._lib.qgb_seed(self._h, int(seed)), self._h)
