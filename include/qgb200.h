@@ -192,6 +192,13 @@ int qgb_fft_interpolate(int device, int n, int N, int batch, const double* in, d
  * the images processed by them, and stops profiling. */
 int qgb_profile_begin(qgb_handle* h, int net, int layer);
 int qgb_profile_end(qgb_handle* h, double* total_ms, int64_t* launches, int64_t* images);
+/* Same for EVERY kernel of the step (bench.py's per-kernel table; the event pairs between the back-to-back conv launches
+ * cost a little overlap, so this is run outside the headline timed region).  Slots: 0-7 conv layers of network 0, 8-15 of
+ * network 1, 16 spectral step kernel, 17 latent-noise kernel, 18 closure epilogue, 19 time-averaged diagnostics sampling.
+ * ms / launches / units (images or members processed) are arrays of QGB_PROF_SLOTS entries, any may be NULL. */
+#define QGB_PROF_SLOTS 20
+int qgb_profile_all_begin(qgb_handle* h);
+int qgb_profile_all_end(qgb_handle* h, double* ms, int64_t* launches, int64_t* units);
 
 /* number of kernels launched by this library in this process (bench.py's gpu_launches) */
 int64_t qgb_launch_count(void);

@@ -13,6 +13,9 @@ QGB_OK, QGB_EINVAL, QGB_ECUDA, QGB_ESTATE, QGB_EUNSUPPORTED = 0, -1, -2, -3, -4
 (F_Q, F_QH, F_PH, F_U, F_V, F_DQHDT, F_FORCING, F_NOISE, F_P) = range(9)
 CLOSURE_NONE, CLOSURE_GAN, CLOSURE_VAE, CLOSURE_GZ, CLOSURE_OLS, CLOSURE_RAW = range(6)
 SAMPLER_AR1, SAMPLER_CONSTANT, SAMPLER_DETERMINISTIC = range(3)
+PROF_SLOTS = 20
+PROF_SLOT_NAMES = ['net0.L%d' % (i + 1) for i in range(8)] + ['net1.L%d' % (i + 1) for i in range(8)] + \
+    ['spectral_step', 'latent_noise', 'closure_epilogue', 'diagnostics']
 PREC_FP32, PREC_TC, PREC_TC_FAST, PREC_AUTO = 0, 1, 2, 3
 PRECISIONS = {'fp32': PREC_FP32, 'tc': PREC_TC, 'tc_fast': PREC_TC_FAST, 'auto': PREC_AUTO}
 PRECISION_NAMES = {v: k for k, v in PRECISIONS.items()}
@@ -64,6 +67,8 @@ SYMBOLS = {
     'qgb_fft_interpolate': (_i, [_i, _i, _i, _i, _vp, _vp, _i, _vp]),
     'qgb_profile_begin': (_i, [_vp, _i, _i]),
     'qgb_profile_end': (_i, [_vp, ctypes.POINTER(_d), ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]),
+    'qgb_profile_all_begin': (_i, [_vp]),
+    'qgb_profile_all_end': (_i, [_vp, ctypes.POINTER(_d), ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]),
     'qgb_launch_count': (ctypes.c_int64, []),
     'qgb_version': (ctypes.c_char_p, []),
 }

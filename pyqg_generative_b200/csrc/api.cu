@@ -15,6 +15,7 @@
 #include "closure.cuh"
 #include "cnn_tc_host.hpp"
 #include "operators.cuh"
+#include "prof.hpp"
 #include "qg_host.hpp"
 #include "spectral_host.hpp"
 
@@ -82,8 +83,7 @@ struct qgb_handle {
   TcWorkspace tcw;
   int nsm = 148;
   // per-layer profiling (qgb_profile_begin/end)
-  int prof_net = -1, prof_layer = -1; long long prof_images = 0;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+  Profiler prof;
 };
 
 namespace {
@@ -178,9 +178,7 @@ int net_forward_fp32(qgb_handle* h, const DevNet& net, const float* x, long long
       const bool small = L.cout <= 4;
       const int co_t = small ? 2 : 32;
       dim3 grid(tiles_x * tiles_y, (L.cout + co_t - 1) / co_t, nb);
-      const bool prof = h->prof_layer == (int)li && h->prof_net == (int)(&net - h->nets);
-      cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-      if (prof) { cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventRecord(ev0, st); }
+      const int pi = h->prof.start(8 * (int)(&net - h->nets) + (int)li, st);
 #define QGB_CONV(KS, CT)                                                                                         \
   conv_ffma_kernel<KS, CT><<<grid, 256, 0, st>>>(in, in_bs, out, out_bs, L.wp, L.bias, L.bn_s, L.bn_t, L.cin, L.cout, \
                                                  L.cout_pad, ny, nx, tiles_x, L.relu_bn, sp, acc)
@@ -194,7 +192,7 @@ int net_forward_fp32(qgb_handle* h, const DevNet& net, const float* x, long long
 #undef QGB_CONV
       QGB_COUNT_LAUNCH();
       CUDA_TRY(h, cudaGetLastError());
-      if (prof) { cudaEventRecord(ev1, st); h->prof_events.emplace_back(ev0, ev1); h->prof_images += nb; }
+      h->prof.stop(pi, st, nb);
       in = out;
       in_bs = out_bs;
     }
@@ -207,9 +205,8 @@ int net_forward(qgb_handle* h, int net, const float* x, long long x_bs, float* y
   if (precision == QGB_PREC_TC || precision == QGB_PREC_TC_FAST) {
     if (!h->nets[net].tc.ready) return fail(h, QGB_EUNSUPPORTED, "tcgen05 path: network architecture not supported");
     std::string e;
-    h->tcw.prof_layer = (h->prof_net == net) ? h->prof_layer : -1;
-    h->tcw.prof_events = &h->prof_events;
-    h->tcw.prof_images = &h->prof_images;
+    h->tcw.prof = &h->prof;
+    h->tcw.prof_net = net;
     int rc = tc_forward(h->nets[net].tc, h->tcw, x, x_bs, y, y_bs, batch, ny, nx, softplus, accumulate, h->nsm, st, &e,
                         precision == QGB_PREC_TC_FAST);
     if (rc != 0) return fail(h, rc, "%s", e.c_str());
@@ -226,8 +223,10 @@ int launch_latent(qgb_handle* h, T* z, long long mstride, double a, double b, in
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   const T* inj = h->xi_set ? (const T*)h->xi_inj : nullptr;
+  const int pi = h->prof.start(PROF_LATENT, st);
   latent_update_kernel<T><<<blocks, 256, 0, st>>>(z, mstride, npix, h->cfg.members, h->cfg.member_offset, h->seed,
                                                    h->draw, (T)a, (T)b, replace, inj);
+  h->prof.stop(pi, st, h->cfg.members);
   QGB_COUNT_LAUNCH();
   CUDA_TRY(h, cudaGetLastError());
   h->draw++;
@@ -419,19 +418,23 @@ int closure_update(qgb_handle* h, cudaStream_t st) {
   if (!compute && h->dq_valid) return QGB_OK;
   // ---- predict_snapshot ----
   if (int rc0 = resolve()) return rc0;
+  int pf = -1;
   if (h->kind == QGB_CLOSURE_GZ) {
     int rc = net_forward(h, 0, h->xin, x_bs, h->ynet[0], 2 * npix, B, N, N, 0, 0, prec, st);
     if (rc) return rc;
     rc = net_forward(h, 1, h->xin, x_bs, h->ynet[1], 2 * npix, B, N, N, 1, 0, prec, st);
     if (rc) return rc;
+    pf = h->prof.start(PROF_FINISH, st);
     finish_gz_kernel<<<blocks, 256, 0, st>>>(h->ynet[0], h->ynet[1], h->z64, h->dq, (int)npix, total, h->y_std[0],
                                               h->y_std[1], h->weight, 1);
   } else {
     int rc = net_forward(h, 0, h->xin, x_bs, h->ynet[0], 2 * npix, B, N, N, 0, 0, prec, st);
     if (rc) return rc;
+    pf = h->prof.start(PROF_FINISH, st);
     finish_plain_kernel<<<blocks, 256, 0, st>>>(h->ynet[0], h->dq, (int)npix, total, h->y_std[0], h->y_std[1],
                                                  h->weight, 1.0f);
   }
+  h->prof.stop(pf, st, B);
   QGB_COUNT_LAUNCH();
   CUDA_TRY(h, cudaGetLastError());
   h->dq_valid = true;
@@ -592,6 +595,7 @@ void qgb_destroy(qgb_handle* h) {
   cudaFree(h->yacc); cudaFree(h->dq_ext); cudaFree(h->dq); cudaFree(h->dq_dm); cudaFree(h->act[0]); cudaFree(h->act[1]);
   free_net(h->nets[0]); free_net(h->nets[1]);
   tc_free_workspace(h->tcw);
+  h->prof.destroy();
   delete h;
 }
 
@@ -753,14 +757,18 @@ int qgb_step(qgb_handle* h, int nsteps, void* stream) {
     }
     if (h->avg_on && h->t >= h->cfg.dt && h->t >= h->tavestart &&
         h->tc % (long long)std::ceil(h->taveint / h->cfg.dt) == 0) {
+      const int pd = h->prof.start(PROF_DIAG, st);
       int rc = sample_averages(h, io.dq, st);
       if (rc) return rc;
+      h->prof.stop(pd, st, h->cfg.members);
     }
     const int cur = (int)(h->tc % 3), prev = (int)((h->tc + 2) % 3), pprev = (int)((h->tc + 1) % 3);
     io.d_cur = h->hist[cur]; io.d_p = h->hist[prev]; io.d_pp = h->hist[pprev];
     ab_coefficients(h->ablevel, h->cfg.dt, io.dt1, io.dt2, io.dt3);
+    const int pi = h->prof.start(PROF_SPECTRAL, st);
     int rc = launch_program(h, io, prog, st);
     if (rc) return rc;
+    h->prof.stop(pi, st, h->cfg.members);
     h->last_dq = io.dq;
     if (h->ablevel < 2) h->ablevel++;
     h->tc += 1;
@@ -962,10 +970,9 @@ int qgb_set_forcing(qgb_handle* h, const double* dq, int on_device, void* stream
 }
 
 int qgb_profile_begin(qgb_handle* h, int net, int layer) {
-  if (!h || net < 0 || net > 1 || layer < 0) return fail(h, QGB_EINVAL, "bad argument");
-  for (auto& e : h->prof_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
-  h->prof_events.clear();
-  h->prof_net = net; h->prof_layer = layer; h->prof_images = 0;
+  if (!h || net < 0 || net > 1 || layer < 0 || layer > 7) return fail(h, QGB_EINVAL, "bad argument");
+  h->prof.reset();
+  h->prof.net = net; h->prof.layer = layer;
   return QGB_OK;
 }
 
@@ -973,18 +980,42 @@ int qgb_profile_end(qgb_handle* h, double* total_ms, int64_t* launches, int64_t*
   if (!h) return QGB_EINVAL;
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
   double tot = 0.0;
-  for (auto& e : h->prof_events) {
-    CUDA_TRY(h, cudaEventSynchronize(e.second));
+  long long units = 0;
+  for (auto& r : h->prof.recs) {
+    CUDA_TRY(h, cudaEventSynchronize(r.b));
     float ms = 0.f;
-    CUDA_TRY(h, cudaEventElapsedTime(&ms, e.first, e.second));
+    CUDA_TRY(h, cudaEventElapsedTime(&ms, r.a, r.b));
     tot += ms;
-    cudaEventDestroy(e.first); cudaEventDestroy(e.second);
+    units += r.units;
   }
   if (total_ms) *total_ms = tot;
-  if (launches) *launches = (int64_t)h->prof_events.size();
-  if (images) *images = (int64_t)h->prof_images;
-  h->prof_events.clear();
-  h->prof_net = -1; h->prof_layer = -1; h->prof_images = 0;
+  if (launches) *launches = (int64_t)h->prof.recs.size();
+  if (images) *images = (int64_t)units;
+  h->prof.reset();
+  return QGB_OK;
+}
+
+int qgb_profile_all_begin(qgb_handle* h) {
+  if (!h) return QGB_EINVAL;
+  h->prof.reset();
+  h->prof.layer = -2;
+  return QGB_OK;
+}
+
+int qgb_profile_all_end(qgb_handle* h, double ms[QGB_PROF_SLOTS], int64_t launches[QGB_PROF_SLOTS], int64_t units[QGB_PROF_SLOTS]) {
+  if (!h) return QGB_EINVAL;
+  static_assert(QGB_PROF_SLOTS == PROF_SLOTS, "header / prof.hpp slot counts differ");
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  for (int i = 0; i < QGB_PROF_SLOTS; ++i) { if (ms) ms[i] = 0.0; if (launches) launches[i] = 0; if (units) units[i] = 0; }
+  for (auto& r : h->prof.recs) {
+    CUDA_TRY(h, cudaEventSynchronize(r.b));
+    float t = 0.f;
+    CUDA_TRY(h, cudaEventElapsedTime(&t, r.a, r.b));
+    if (ms) ms[r.slot] += t;
+    if (launches) launches[r.slot] += 1;
+    if (units) units[r.slot] += r.units;
+  }
+  h->prof.reset();
   return QGB_OK;
 }
 

@@ -953,9 +953,7 @@ int tc_forward(const TcNet& net, TcWorkspace& ws, const float* x, long long x_bs
       } else {
         P.out_f32 = y + (long long)b0 * y_bs; P.out_bs = y_bs; P.out_c = L.real_cout; P.softplus = softplus; P.accumulate = accumulate;
       }
-      const bool prof = ws.prof_events && ws.prof_layer == li;
-      cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-      if (prof) { cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventRecord(ev0, st); }
+      const int pi = ws.prof ? ws.prof->start(8 * ws.prof_net + li, st) : -1;
       cudaError_t e;
       if (li == 0) {
         if (fast_l2) e = net.kp == 128 ? tc_launch<128, 128, 1, 3, 2, TC_OUT_HI, 4>(P, L.epi, nb, nsm, st) : tc_launch<64, 128, 1, 3, 2, TC_OUT_HI, 2>(P, L.epi, nb, nsm, st);
@@ -964,7 +962,7 @@ int tc_forward(const TcNet& net, TcWorkspace& ws, const float* x, long long x_bs
       else if (li == 2) e = tc_launch_T<64, 32, 3, 3, TC_OUT_HILO>(tl, P, L.epi, nb, nsm, st);
       else if (li < 7) e = tc_launch_T<32, 32, 3, 3, TC_OUT_HILO>(tl, P, L.epi, nb, nsm, st);
       else e = tc_launch_T<32, 16, 3, 3, TC_OUT_FINAL>(tl, P, L.epi, nb, nsm, st);
-      if (prof) { cudaEventRecord(ev1, st); ws.prof_events->emplace_back(ev0, ev1); *ws.prof_images += nb; }
+      if (ws.prof) ws.prof->stop(pi, st, nb);
       ws.last_launches += 1;
       if (e != cudaSuccess) { *err = std::string("tcgen05 conv launch failed: ") + cudaGetErrorString(e); return QGB_ECUDA; }
     }

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../include/qgb200.h"
+#include "prof.hpp"
 
 namespace qgb {
 
@@ -42,10 +43,9 @@ struct TcNet {
 struct TcWorkspace {
   __half* buf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // a0_hi, a0_lo, ping hi/lo, pong hi/lo
   size_t halves[6] = {0, 0, 0, 0, 0, 0};
-  // per-layer timing hook (qgb_profile_begin/end): layer index to bracket with events, filled by api.cu
-  int prof_layer = -1;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>>* prof_events = nullptr;
-  long long* prof_images = nullptr;
+  // per-layer timing hook (qgb_profile_*, prof.hpp): set by api.cu around a forward pass; slot = 8 * prof_net + layer
+  Profiler* prof = nullptr;
+  int prof_net = 0;
   long long last_launches = 0;   // kernels launched by the latest tc_forward
 };
 

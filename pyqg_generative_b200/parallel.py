@@ -93,6 +93,37 @@ def ensemble_diagnostics(diag_sums):
     return out, int(red[-1])
 
 
+def ensemble_diagnostics_device(model, reset=False):
+    """Same result as ``ensemble_diagnostics(model.diagnostic_sums())`` without the host bounce: the engine hands out its
+    device accumulators (``qgb_diag_averages(on_device=1)``), ONE ``all_reduce`` (NCCL over NVLink) sums them together with
+    the sample count, and only the reduced means travel to the host.  Returns (dict name -> mean, total count)."""
+    import ctypes
+    from . import _lib
+    nl, nk = model.nl, model.nk
+    nterms = 4 + len(model.DIAG_BUDGET)
+    dev = torch.device('cuda', model.device_index)
+    buf = torch.zeros(nterms * nl * nk + 1, dtype=torch.float64, device=dev)
+    ns = ctypes.c_int64(0)
+    _lib.check(model._lib.qgb_diag_averages(model._h, buf.data_ptr(), ctypes.byref(ns), 1 if reset else 0, 1, model._stream()),
+               model._h)
+    buf[-1] = float(ns.value) * model.members
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        if dist.get_backend() == 'nccl':
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+        else:                                   # gloo (CPU tests of the orchestration): reduce on the host
+            hb = buf.cpu()
+            dist.all_reduce(hb, op=dist.ReduceOp.SUM)
+            buf = hb
+    red = buf.cpu().numpy()
+    n = max(red[-1], 1.0)
+    a = (red[:-1] / n).reshape((nterms, nl, nk))
+    out = {'KEspec': a[0:2].copy(), 'Ensspec': a[2:4].copy()}
+    for i, name in enumerate(model.DIAG_BUDGET):
+        out[name] = a[4 + i].copy()
+    out['paramspec'] = out['paramspec_KEflux'] + out['paramspec_APEflux']
+    return out, int(red[-1])
+
+
 def ensemble_ke(ke_members):
     """Ensemble-mean kinetic energy over all ranks from the per-member values of the local shard."""
     s, c = allreduce_sum([np.array([np.nansum(ke_members)]), np.array([float(np.isfinite(ke_members).sum())])])
@@ -100,27 +131,9 @@ def ensemble_ke(ke_members):
 
 
 def calc_ispec(k, l, spec2d, averaging=True, truncate=True, nd_wavenumber=False, nfactor=1):
-    """Isotropic spectrum of a (nl, nk) half-plane density -- pyqg_generative/tools/spectral_tools.py:103-180
-    (``calc_ispec``), used to turn the reduced KEspec into KE(kappa).  Returns (kr, spectrum)."""
-    kk, ll = k[0], l[:, 0]
-    dk, dl = kk[1] - kk[0], ll[1] - ll[0]
-    dkr = nfactor * np.sqrt(dk ** 2 + dl ** 2)
-    kmax = min(np.abs(ll).max(), np.abs(kk).max()) if truncate else np.sqrt(np.abs(ll).max() ** 2 + np.abs(kk).max() ** 2)
-    kr = np.arange(dkr / 2., kmax + dkr, dkr)
-    wv = np.sqrt(k ** 2 + l ** 2)
-    spec = np.array(spec2d, dtype=np.float64).copy()
-    out = np.zeros(kr.size - 1)
-    keep = np.ones(kr.size - 1, dtype=bool)
-    for i in range(kr.size - 1):
-        mask = (wv >= kr[i]) & (wv < kr[i + 1])
-        n = mask.sum()
-        if n == 0:
-            keep[i] = False
-            continue
-        if averaging:
-            # density in |kappa|: mean over the shell times the shell circumference (half-plane -> factor pi)
-            out[i] = spec[mask].mean() * (kr[i] + kr[i + 1]) / 2 * np.pi / (dk * dl)
-        else:
-            out[i] = spec[mask].sum() / dkr
-    krm = (kr[:-1] + kr[1:]) / 2
-    return krm[keep], out[keep]
+    """Isotropic spectrum of a (nl, nk) half-plane density given the wavenumber arrays instead of a model:
+    ``tools.spectral_tools.calc_ispec`` (= pyqg_generative/tools/spectral_tools.py:103-180, bit-for-bit) on a ``GridView``.
+    Used to turn the all-reduced KEspec into KE(kappa).  Returns (kr, spectrum)."""
+    from .tools.spectral_tools import GridView, calc_ispec as _calc_ispec
+    return _calc_ispec(GridView(k, l), spec2d, averaging=averaging, truncate=truncate, nd_wavenumber=nd_wavenumber,
+                       nfactor=nfactor)

@@ -8,7 +8,7 @@ NetCDF-3 (64-bit offset) with ``scipy.io.netcdf_file``, which xarray opens nativ
 Layout of one file (= one run, like the reference) :
   dims       time, lev (2), y, x, l (= ny), k (= nx/2+1)
   coords     time [days, attrs units='days'], lev [1, 2], x, y [m], l, k [rad/m]
-  float32    q, u, v, psi (time, lev, y, x);  Ubg, Qy (lev)
+  float32    q, u, v, psi (time, lev, y, x) [+ q_forcing_advection in forcing datasets];  Ubg, Qy (lev)
   float32    time-averaged spectral diagnostics of the LAST snapshot: KEspec, Ensspec (lev, l, k); KEflux, APEflux,
              APEgenspec, KEfrictionspec, entspec, paramspec, paramspec_KEflux, paramspec_APEflux (l, k)
   attrs      pyqg_params (str of the dict, :144), pyqg:<name> physical parameters like pyqg's to_dataset
@@ -19,6 +19,7 @@ import os
 import numpy as np
 
 PHYSICAL = ('q', 'u', 'v', 'psi')
+FORCING = ('q_forcing_advection',)      # forcing datasets (generate_subgrid_forcing, tools/simulate.py:62-106) carry S next to q, u, v, psi
 LAYERED_SPECTRA = ('KEspec', 'Ensspec')
 PLANE_SPECTRA = ('KEflux', 'APEflux', 'APEgenspec', 'KEfrictionspec', 'entspec', 'paramspec', 'paramspec_KEflux',
                  'paramspec_APEflux')
@@ -65,7 +66,11 @@ def _write(path, ds, run_index=None):
         for name in ('Ubg', 'Qy'):
             if name in c:
                 _nc_var(f, name, np.asarray(c[name], dtype=np.float32), ('lev',))
-        for name in PHYSICAL:
+        for name in PHYSICAL + FORCING:
+            if name not in ds:
+                if name in PHYSICAL:
+                    raise KeyError(name)
+                continue
             a = np.asarray(ds[name], dtype=np.float32)
             _nc_var(f, name, a if run_index is None else a[run_index], lead + ('time', 'lev', 'y', 'x'))
         for name in LAYERED_SPECTRA:

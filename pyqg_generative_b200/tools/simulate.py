@@ -17,19 +17,30 @@ from .parameters import ANDREW_1000_STEPS, DAY
 from .stochastic_pyqg import EnsembleQGModel, stochastic_QGModel
 
 
-def set_initial_condition(m, rng=None):
-    """JAMES-paper initial condition (:147-168), drawn independently for every member."""
+def initial_condition_fields(nx, L=1e6, members=1, rng=None):
+    """Upper-layer PV of the JAMES-paper initial condition (:147-166) for ``members`` members, (members, nx, nx) float64.
+    Members are drawn one after the other in the reference's order (rand(ny, nx), then rand(1, nx)), so a seeded ``rng``
+    gives exactly what ``members`` successive reference calls would."""
     rng = np.random if rng is None else rng
-    B = m.members
-    q2d = 1e-7 * rng.rand(B, m.ny, m.nx)
-    q2d -= q2d.mean(axis=(-2, -1), keepdims=True)
-    q2d *= np.sqrt(m.nx * m.ny / 64 ** 2)
-    q1d = 1e-6 * (np.ones((1, m.ny, 1)) * rng.rand(B, 1, m.nx))
-    q1d -= q1d.mean(axis=(-2, -1), keepdims=True)
-    q1d *= np.sqrt(m.nx / 64)
-    noise = q1d + q2d
-    Xf = np.fft.rfftn(noise, axes=(-2, -1))
-    noise = np.fft.irfftn(Xf * (m.wv < np.pi / (m.L / 32)), axes=(-2, -1))
+    N = int(nx)
+    dk = 2. * np.pi / L
+    k, l = np.meshgrid(dk * np.arange(0., N // 2 + 1), dk * np.append(np.arange(0., N / 2), np.arange(-N / 2, 0.)))
+    keep = np.sqrt(k ** 2 + l ** 2) < np.pi / (L / 32)
+    out = np.empty((int(members), N, N))
+    for b in range(int(members)):
+        q2d = 1e-7 * rng.rand(N, N)
+        q2d -= q2d.mean(axis=(-2, -1), keepdims=True)
+        q2d *= np.sqrt(N * N / 64 ** 2)
+        q1d = 1e-6 * (np.ones((N, 1)) * rng.rand(1, N))
+        q1d -= q1d.mean(axis=(-2, -1), keepdims=True)
+        q1d *= np.sqrt(N / 64)
+        out[b] = np.fft.irfftn(np.fft.rfftn(q1d + q2d) * keep)
+    return out
+
+
+def set_initial_condition(m, rng=None):
+    """JAMES-paper initial condition (:147-168), drawn independently for every member; lower layer at rest."""
+    noise = initial_condition_fields(m.nx, m.L, m.members, rng)
     m.set_q(np.stack([noise, np.zeros_like(noise)], axis=1))
     m._invert()
 
@@ -136,6 +147,8 @@ def generate_subgrid_forcing(Nc, pyqg_params, sampling_freq=ANDREW_1000_STEPS, o
     for key, recs in out.items():
         d = {k: np.stack([r[k] for r in recs], axis=1) for k in ('q_forcing_advection', 'q', 'u', 'v', 'psi')}
         d['time'] = np.array([r['time'] for r in recs])
+        nc = d['q'].shape[-1]
+        d['coords'] = dict(x=(np.arange(nc) + 0.5) * m.L / nc, y=(np.arange(nc) + 0.5) * m.L / nc, lev=np.array([1, 2], dtype=np.int32))
         d['attrs'] = {'pyqg_params': str(pyqg_params)}
         out[key] = d
     return out
@@ -185,18 +198,13 @@ def main(argv=None):
     if args.subfolder:
         os.makedirs(args.subfolder, exist_ok=True)
 
-    def save(ds, path):
-        ds = {k: v for k, v in ds.items() if isinstance(v, np.ndarray)}
-        np.savez_compressed(path, **ds)
-
     def save_runs(ds, folder):          # <ensemble_member + i>.nc like the reference (:249-263)
         write_runs(ds, folder or '.', first=args.ensemble_member)
 
     if args.forcing == 'yes':
         out = generate_subgrid_forcing([32, 48, 64, 96, 128], params, args.sampling_freq)
-        for key, ds in out.items():
-            os.makedirs(key, exist_ok=True)
-            save(ds, os.path.join(key, '%d.npz' % args.ensemble_member))
+        for key, ds in out.items():         # <Operator>-<nc>[-dealias]/<member>.nc, what xr.open_mfdataset('<key>/*.nc') reads (:192-199)
+            write_runs(ds, os.path.join(args.subfolder, key) if args.subfolder else key, first=args.ensemble_member)
     if args.reference == 'yes':
         save_runs(run_simulation(params, sampling_freq=args.sampling_freq), args.subfolder)
     if args.parameterization == 'yes':

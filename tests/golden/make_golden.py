@@ -17,6 +17,9 @@ coupled_48.npz     3 steps of reference ``stochastic_QGModel`` + ``CVAERegressio
                    constant nsteps=2) with recorded noise and states
 operators_128.npz  Operator1/2/5, cut_off, fft_interpolate, PV_subgrid_forcing(none, 3/2-rule) on a 128^2 field
 samplers.npz       AR1 / constant sampler sequences
+ispec.npz          calc_ispec (tools/spectral_tools.py:103-180) of seeded spectra at nx = 48, 64 for every option combination
+initial_condition.npz  set_initial_condition (tools/simulate.py:147-168) under np.random.seed for nx = 48, 64, 96 (two
+                   successive members each)
 """
 import os
 import shutil
@@ -196,12 +199,50 @@ def samplers_fixture():
     np.savez_compressed(os.path.join(HERE, 'samplers.npz'), **out)
 
 
+def ispec_fixture():
+    from pyqg_generative.tools.spectral_tools import calc_ispec
+    out = {}
+    for n in (48, 64):
+        m = pyqg.QGModel(nx=n, log_level=0)
+        rng = np.random.RandomState(100 + n)
+        spec = rng.rand(n, n // 2 + 1) * np.exp(-(m.wv / (10 * m.dk)) ** 1.5)
+        out['spec_%d' % n] = spec
+        for avg in (True, False):
+            for trunc in (True, False):
+                for nd in (False, True):
+                    for nf in (1, 2):
+                        kr, ph = calc_ispec(m, spec, averaging=avg, truncate=trunc, nd_wavenumber=nd, nfactor=nf)
+                        tag = '%d_%d%d%d%d' % (n, avg, trunc, nd, nf)
+                        out['kr_' + tag], out['ph_' + tag] = kr, ph
+    np.savez_compressed(os.path.join(HERE, 'ispec.npz'), **out)
+
+
+def initial_condition_fixture():
+    from pyqg_generative.tools.simulate import set_initial_condition
+    out = {}
+    for n in (48, 64, 96):
+        models = [pyqg.QGModel(nx=n, log_level=0) for _ in range(2)]   # (the pyqg constructor draws its own default IC)
+        np.random.seed(1000 + n)
+        qs = []
+        for m in models:
+            set_initial_condition(m)
+            qs.append(m.q.copy())
+        out['q_%d' % n] = np.stack(qs)
+    np.savez_compressed(os.path.join(HERE, 'initial_condition.npz'), **out)
+
+
 if __name__ == '__main__':
+    if '--only-new' in sys.argv:       # fixtures added in round 2 (the others are unchanged)
+        ispec_fixture()
+        initial_condition_fixture()
+        sys.exit(0)
     save_weights()
     gan, vae, gz = load_reference_models()
     closure_fixture(gan, vae, gz)
     coupled_fixture(vae)
     operators_fixture()
     samplers_fixture()
+    ispec_fixture()
+    initial_condition_fixture()
     for f in sorted(os.listdir(HERE)):
         print('%10d  %s' % (os.path.getsize(os.path.join(HERE, f)), f))

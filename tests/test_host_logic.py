@@ -107,14 +107,48 @@ def test_member_sharding_is_a_partition():
             assert max(c for c, _ in blocks) - min(c for c, _ in blocks) <= 1
 
 
-def test_isotropic_spectrum_integrates_to_total():
-    from pyqg_generative_b200.parallel import calc_ispec
+def test_calc_ispec_matches_reference_golden():
+    """tools/spectral_tools.calc_ispec (and the array-argument adapter parallel.calc_ispec) against the outputs of the
+    unmodified reference function (pyqg_generative/tools/spectral_tools.py:103-180; tests/golden/make_golden.py
+    ispec_fixture) for every option combination: bit-for-bit."""
+    from pyqg_generative_b200 import parallel
+    from pyqg_generative_b200.tools.spectral_tools import calc_ispec
     from oracle import pyqg_shim
+    g = golden('ispec.npz')
+    for n in (48, 64):
+        m = pyqg_shim.QGModel(nx=n, log_level=0)
+        spec = g['spec_%d' % n]
+        for avg in (True, False):
+            for trunc in (True, False):
+                for nd in (False, True):
+                    for nf in (1, 2):
+                        tag = '%d_%d%d%d%d' % (n, avg, trunc, nd, nf)
+                        kr, ph = calc_ispec(m, spec, averaging=avg, truncate=trunc, nd_wavenumber=nd, nfactor=nf)
+                        assert np.array_equal(kr, g['kr_' + tag]) and np.array_equal(ph, g['ph_' + tag]), tag
+                        kr2, ph2 = parallel.calc_ispec(m.k, m.l, spec, averaging=avg, truncate=trunc, nd_wavenumber=nd, nfactor=nf)
+                        assert np.array_equal(kr2, kr) and np.array_equal(ph2, ph), tag
+    # Parseval in summation mode (the normalisation the reference documents): signal.var() == phr.sum() * dkr
     m = pyqg_shim.QGModel(nx=64, log_level=0)
-    spec = np.exp(-(m.wv / (8 * m.dk)) ** 2)
-    kr, s = calc_ispec(m.k, m.l, spec, averaging=False)
-    inside = m.wv < kr[-1] + (kr[1] - kr[0]) / 2
-    assert abs(s.sum() * (kr[1] - kr[0]) - spec[inside & (m.wv >= (kr[0] - (kr[1] - kr[0]) / 2))].sum()) < 1e-9 * spec.sum()
+    x = np.random.RandomState(3).randn(64, 64)
+    xh = np.fft.rfftn(x) * (m.wv < 30 * m.dk) * (m.wv >= m.dk)     # inside the truncation circle, no mean
+    x = np.fft.irfftn(xh)
+    kr, ph = calc_ispec(m, np.abs(xh) ** 2 / m.M ** 2, averaging=False, truncate=True)
+    assert abs(ph.sum() * (kr[1] - kr[0]) - x.var()) < 1e-12 * x.var()
+
+
+def test_initial_condition_matches_reference_golden():
+    """tools/simulate.initial_condition_fields against the unmodified reference set_initial_condition
+    (pyqg_generative/tools/simulate.py:147-168) under the same seeded host RNG: two successive members per grid size."""
+    from pyqg_generative_b200.tools.simulate import initial_condition_fields
+    g = golden('initial_condition.npz')
+    for n in (48, 64, 96):
+        np.random.seed(1000 + n)
+        q1 = initial_condition_fields(n, 1e6, members=2)
+        ref = g['q_%d' % n]                     # (member, lev, y, x)
+        assert np.array_equal(ref[:, 1], np.zeros_like(ref[:, 1]))
+        assert np.abs(q1 - ref[:, 0]).max() <= 1e-15 * np.abs(ref[:, 0]).max(), n
+        rs = np.random.RandomState(1000 + n)     # an explicit generator gives the same stream
+        assert np.array_equal(initial_condition_fields(n, 1e6, members=2, rng=rs), q1)
 
 
 def test_netcdf_writer_layout_matches_reference_files(tmp_path):
