@@ -48,8 +48,9 @@ def test_eddy64_10k_steps_match_oracle_series_and_recorded_log():
     rel = np.abs(ke[:, :n_ora].T / g['ke'] - 1)                     # (member, time)
     print('KE(t) member-wise rel. error: max over steps<=3000 %.2e, at step 4000 %.2e, 5000 %.2e; q at step 2500 %.2e'
           % (rel[:, :30].max(), rel[:, 39].max(), rel[:, 49].max(), err_q))
-    assert rel[:, :30].max() < 1e-8 and err_q < 1e-8
-    assert rel[:, :40].max() < 1e-5
+    # measured on B200: 8.7e-15 through step 3000, 9.1e-15 at step 5000, q at step 2500 4.2e-15
+    assert rel[:, :30].max() < 1e-12 and err_q < 1e-12
+    assert rel[:, :50].max() < 1e-9
     # (ii) statistics after saturation: ensemble-mean KE against the oracle ensemble and the reference's recorded log
     se_ora = g['ke'][:, -1].std(ddof=1) / np.sqrt(n_ora)
     print('KE at 10k: gpu %.3e +- %.1e (256 members), oracle %.3e +- %.1e (8 members), notebook %.2e'
@@ -73,7 +74,8 @@ def test_eddy64_10k_steps_match_oracle_series_and_recorded_log():
         assert abs(s_gpu.sum() / s_ora.sum() - 1) < 0.08
 
 
-@pytest.mark.parametrize('prec,tol', [('fp32', 2e-5), ('tc', 2e-4)])
+# measured 2.7e-7 (fp32) / 4.2e-5 (tc) through step 3000
+@pytest.mark.parametrize('prec,tol', [('fp32', 2e-6), ('tc', 2e-4)])
 def test_cgan48_replay_of_oracle_members_with_shared_noise(tmp_path, prec, tol):
     from pyqg_generative_b200.models.cgan_regression import CGANRegression
     from pyqg_generative_b200.tools.simulate import initial_condition_fields
