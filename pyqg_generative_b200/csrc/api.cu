@@ -58,6 +58,7 @@ struct qgb_handle {
   long long tc = 0; double t = 0.0; int ablevel = 0;
   int nthreads = 256; size_t smem = 0; int grid = 0;
   bool fixed = false;   // compile-time specialised step kernel available for this nx
+  bool reg64 = false;   // register-resident kernel (spectral64.cuh) for nx = 64
   int nt64 = 384;
   bool large = false; cplx* scratch = nullptr; double* red_scratch = nullptr;   // cluster path for nx > 96
   int cluster = 8; int large_lines = 0; size_t large_smem = 0;   // lines of a 1-D FFT pass staged per CTA in shared memory
@@ -132,7 +133,7 @@ StepIO base_io(qgb_handle* h) {
 SpectralPlan make_plan(const qgb_handle* h) {
   SpectralPlan p;
   p.N = h->ht.N; p.members = h->cfg.members; p.grid = h->grid; p.nthreads = h->nthreads; p.smem = h->smem;
-  p.fixed = h->fixed; p.nt64 = h->nt64; p.large = h->large; p.cluster = h->cluster; p.large_lines = h->large_lines;
+  p.fixed = h->fixed; p.nt64 = h->nt64; p.reg64 = h->reg64; p.large = h->large; p.cluster = h->cluster; p.large_lines = h->large_lines;
   p.large_smem = h->large_smem; p.scratch = h->scratch; p.red_scratch = h->red_scratch; p.true_pos = h->d_pos;
   return p;
 }
@@ -524,6 +525,7 @@ int qgb_create(const qgb_config* cfg, qgb_handle** out) {
     const char* e = getenv("QGB_STEP_NT");
     h->nt64 = e ? atoi(e) : 384;   // measured on B200: 256 -> 0.370 ms, 384 -> 0.299 ms, 512 -> 0.301 ms per 1024 members
   }
+  h->reg64 = !h->large && cfg->nx == 64 && !getenv("QGB_S64_OFF");
   h->grid = cfg->members;
   if (h->large) {
     // one cluster of CTAs per member, persistent over members when the ensemble exceeds the machine.  Cluster size: small

@@ -28,6 +28,10 @@ cudaError_t spectral_configure(const SpectralPlan& p) {
     QGB_ATTR(qg_program_kernel, p.smem);
     if (dev >= 0 && dev < 64) generic_limit[dev] = p.smem;
   }
+  if (p.reg64) {
+    e = spectral64_configure();
+    if (e != cudaSuccess) return e;
+  }
   if (p.fixed) {
     if (p.N == 32) QGB_ATTR((qg_step_fixed_kernel<32, 256>), p.smem);
     if (p.N == 48) QGB_ATTR((qg_step_fixed_kernel<48, 256>), p.smem);
@@ -62,6 +66,7 @@ cudaError_t spectral_launch(const SpectralPlan& p, const Tables& TT, const StepI
                                                                             : qg_program_cluster_kernel<0>;
     return cudaLaunchKernelEx(&cfg, kern, TT, io, prog, p.members, p.scratch, p.red_scratch, p.large_lines, p.true_pos);
   }
+  if (p.reg64 && spectral64_handles(prog)) return spectral64_launch(TT, io, prog, p.members, st);
   const bool is_step = prog == PROG_STEP || prog == PROG_STEP_DQ || prog == PROG_STEP_DQ_RAW;
   if (is_step && p.fixed) {
     switch (p.N) {
