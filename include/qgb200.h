@@ -83,6 +83,11 @@ int qgb_invert(qgb_handle* h, void* stream);
  * ``for t in m.run_with_snapshots(...)`` at tools/simulate.py:137. */
 int qgb_step(qgb_handle* h, int nsteps, void* stream);
 int qgb_get_time(qgb_handle* h, double* t, int64_t* tc);
+/* In the steady state (Adams-Bashforth level 3 reached, sampler drawing every step, nothing injected, no kernel timing, no
+ * diagnostics sample due) qgb_step replays a captured CUDA graph of the step instead of launching its 3-12 kernels one by one:
+ * the launch-bound regime of small ensembles.  Number of steps replayed so far by this handle;
+ * the environment variable QGB_NO_GRAPH disables the replay. */
+int64_t qgb_graph_replays(const qgb_handle* h);
 
 /* ---- closure (CNN subgrid parameterization) ------------------------------------------------------------ */
 enum { QGB_CLOSURE_NONE = 0, QGB_CLOSURE_GAN = 1, QGB_CLOSURE_VAE = 2, QGB_CLOSURE_GZ = 3, QGB_CLOSURE_OLS = 4,

@@ -45,6 +45,7 @@ SYMBOLS = {
     'qgb_get': (_i, [_vp, _i, _vp, _i, _vp]),
     'qgb_invert': (_i, [_vp, _vp]),
     'qgb_step': (_i, [_vp, _i, _vp]),
+    'qgb_graph_replays': (ctypes.c_int64, [_vp]),
     'qgb_get_time': (_i, [_vp, ctypes.POINTER(_d), ctypes.POINTER(ctypes.c_int64)]),
     'qgb_cnn_load': (_i, [_vp, _i, _i, _i, ctypes.POINTER(QgbCnnLayer)]),
     'qgb_closure_config': (_i, [_vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), _d, _i]),

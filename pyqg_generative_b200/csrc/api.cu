@@ -68,7 +68,12 @@ struct qgb_handle {
   bool calibrated = false; int auto_precision = QGB_PREC_TC;   // per-network precision choice (QGB_PREC_AUTO)
   float x_std[2] = {1.f, 1.f}, y_std[2] = {1.f, 1.f}; double weight = 1.0;
   int sampler = QGB_SAMPLER_AR1, sampler_nsteps = 1, n_mean = 100;
-  bool noise_init = false; long long const_counter = 0; uint32_t draw = 0; uint64_t seed = 0x5eed5eedULL;
+  bool noise_init = false; long long const_counter = 0; uint64_t seed = 0x5eed5eedULL;
+  uint32_t* d_draw = nullptr;   // Philox draw counter, device resident (read by the latent kernel, bumped after it)
+  // CUDA-graph replay of the steady-state step (one graph per position of the tendency-history ring)
+  cudaGraphExec_t step_graph[3] = {nullptr, nullptr, nullptr}; unsigned long long graph_key = 0; bool graph_failed = false;
+  long long graph_replays = 0, graph_launches[3] = {0, 0, 0};
+  cudaStream_t cap_stream = nullptr;   // capture happens on a private stream (the caller's may be the legacy default stream, which cannot capture)
   float* xin = nullptr;     // (B, cin0, N, N) closure input: normalised q [+ latent z for gan/vae]
   int xin_c = 0; bool x_valid = false;
   double* z64 = nullptr;    // gz latent (B,2,N,N)
@@ -226,11 +231,12 @@ int launch_latent(qgb_handle* h, T* z, long long mstride, double a, double b, in
   const T* inj = h->xi_set ? (const T*)h->xi_inj : nullptr;
   const int pi = h->prof.start(PROF_LATENT, st);
   latent_update_kernel<T><<<blocks, 256, 0, st>>>(z, mstride, npix, h->cfg.members, h->cfg.member_offset, h->seed,
-                                                   h->draw, (T)a, (T)b, replace, inj);
+                                                   h->d_draw, (T)a, (T)b, replace, inj);
+  bump_counter_kernel<<<1, 1, 0, st>>>(h->d_draw);
+  QGB_COUNT_LAUNCH();
   h->prof.stop(pi, st, h->cfg.members);
   QGB_COUNT_LAUNCH();
   CUDA_TRY(h, cudaGetLastError());
-  h->draw++;
   return QGB_OK;
 }
 
@@ -462,6 +468,11 @@ int ensure_closure_buffers(qgb_handle* h) {
   return QGB_OK;
 }
 
+void invalidate_graphs(qgb_handle* h) {
+  for (int i = 0; i < 3; ++i)
+    if (h->step_graph[i]) { cudaGraphExecDestroy(h->step_graph[i]); h->step_graph[i] = nullptr; }
+}
+
 void free_net(DevNet& n) {
   for (auto& L : n.layers) { cudaFree(L.wp); cudaFree(L.bias); cudaFree(L.bn_s); cudaFree(L.bn_t); }
   n.layers.clear();
@@ -579,6 +590,7 @@ int qgb_create(const qgb_config* cfg, qgb_handle** out) {
   for (int i = 0; i < 3; ++i) { CR(dalloc(&h->hist[i], nc)); CR(cudaMemset(h->hist[i], 0, nc * sizeof(cplx))); }
   CR(dalloc(&h->red, B * 4));
   CR(dalloc(&h->d_ke, B)); CR(dalloc(&h->d_cfl, B)); CR(dalloc(&h->d_flags, B));
+  CR(dalloc(&h->d_draw, 1)); CR(cudaMemset(h->d_draw, 0, sizeof(uint32_t)));
 #undef CR
   *out = h;
   return QGB_OK;
@@ -591,6 +603,9 @@ void qgb_destroy(qgb_handle* h) {
   cudaFree(h->qh); cudaFree(h->q); cudaFree(h->scratch); cudaFree(h->red_scratch);
   for (int i = 0; i < 3; ++i) cudaFree(h->hist[i]);
   cudaFree(h->ph); cudaFree(h->u); cudaFree(h->v); cudaFree(h->p); cudaFree(h->red);
+  invalidate_graphs(h);
+  if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
+  cudaFree(h->d_draw);
   cudaFree(h->d_ke); cudaFree(h->d_cfl); cudaFree(h->d_flags); cudaFree(h->d_kespec); cudaFree(h->d_ensspec);
   cudaFree(h->bud); cudaFree(h->bud_scr); cudaFree(h->bud_sum); cudaFree(h->avg);
   cudaFree(h->xin); cudaFree(h->z64); cudaFree(h->xi_inj); cudaFree(h->ynet[0]); cudaFree(h->ynet[1]);
@@ -739,46 +754,139 @@ int qgb_diag_averages(qgb_handle* h, double* out, int64_t* nsamples, int reset, 
   return QGB_OK;
 }
 
+namespace {
+// one time step enqueued on ``st`` (the body of pyqg Model._step_forward)
+int step_once(qgb_handle* h, cudaStream_t st) {
+  StepIO io = base_io(h);
+  set_cnn_io(h, io);
+  int prog = PROG_STEP;
+  if (h->ext_set) {
+    io.dq = h->dq_ext;
+    prog = PROG_STEP_DQ_RAW;
+    h->ext_set = false;
+  } else if (h->kind != QGB_CLOSURE_NONE) {
+    int rc = closure_update(h, st);
+    if (rc) return rc;
+    io.dq = h->dq;
+    prog = PROG_STEP_DQ;
+  }
+  if (h->avg_on && h->t >= h->cfg.dt && h->t >= h->tavestart &&
+      h->tc % (long long)std::ceil(h->taveint / h->cfg.dt) == 0) {
+    const int pd = h->prof.start(PROF_DIAG, st);
+    int rc = sample_averages(h, io.dq, st);
+    if (rc) return rc;
+    h->prof.stop(pd, st, h->cfg.members);
+  }
+  const int cur = (int)(h->tc % 3), prev = (int)((h->tc + 2) % 3), pprev = (int)((h->tc + 1) % 3);
+  io.d_cur = h->hist[cur]; io.d_p = h->hist[prev]; io.d_pp = h->hist[pprev];
+  ab_coefficients(h->ablevel, h->cfg.dt, io.dt1, io.dt2, io.dt3);
+  const int pi = h->prof.start(PROF_SPECTRAL, st);
+  int rc = launch_program(h, io, prog, st);
+  if (rc) return rc;
+  h->prof.stop(pi, st, h->cfg.members);
+  h->last_dq = io.dq;
+  if (h->ablevel < 2) h->ablevel++;
+  h->tc += 1;
+  h->t += h->cfg.dt;
+  h->x_valid = io.cnn_x != nullptr;
+  return QGB_OK;
+}
+
+// A step is the SAME sequence of launches with the same arguments whenever: AB3 has started (ablevel 2), the sampler draws every
+// step (AR1, or constant with nsteps = 1) or there is no closure, nothing was injected for this step, nobody is timing kernels,
+// the precision calibration is done and no diagnostics sample is due.  Only the position of the tendency-history ring (tc % 3)
+// changes, so three captured graphs cover the steady state; the Philox draw counter lives in device memory.
+bool graph_eligible(const qgb_handle* h) {
+  if (h->graph_failed || h->ablevel < 2 || h->ext_set || h->xi_set || h->prof.layer != -1) return false;
+  if (h->kind != QGB_CLOSURE_NONE) {
+    if (!h->noise_init || !h->dq_valid) return false;
+    if (h->sampler == QGB_SAMPLER_DETERMINISTIC) return false;
+    if (h->sampler == QGB_SAMPLER_CONSTANT && h->sampler_nsteps != 1) return false;
+    if (h->precision == QGB_PREC_AUTO && !h->calibrated) return false;
+  }
+  return true;
+}
+bool diag_sample_due(const qgb_handle* h) {
+  return h->avg_on && h->t >= h->cfg.dt && h->t >= h->tavestart && h->tc % (long long)std::ceil(h->taveint / h->cfg.dt) == 0;
+}
+// everything a captured step depends on besides tc % 3
+unsigned long long graph_state_key(const qgb_handle* h) {
+  unsigned long long k = 1469598103934665603ull;
+  auto mix = [&](unsigned long long v) { k = (k ^ v) * 1099511628211ull; };
+  mix((unsigned long long)h->kind); mix((unsigned long long)h->precision); mix((unsigned long long)h->auto_precision);
+  mix((unsigned long long)h->sampler); mix((unsigned long long)h->sampler_nsteps);
+  mix((unsigned long long)(h->sampler == QGB_SAMPLER_CONSTANT ? h->const_counter : 0));
+  unsigned long long w; std::memcpy(&w, &h->weight, 8); mix(w);
+  unsigned int f; std::memcpy(&f, &h->x_std[0], 4); mix(f); std::memcpy(&f, &h->x_std[1], 4); mix(f);
+  std::memcpy(&f, &h->y_std[0], 4); mix(f); std::memcpy(&f, &h->y_std[1], 4); mix(f);
+  mix((unsigned long long)(uintptr_t)h->xin); mix((unsigned long long)(uintptr_t)h->dq); mix((unsigned long long)h->seed);
+  mix((unsigned long long)(uintptr_t)h->tcw.buf[2]); mix((unsigned long long)(uintptr_t)h->nets[0].tc.layers.data());
+  return k;
+}
+}  // namespace
+
 int qgb_step(qgb_handle* h, int nsteps, void* stream) {
   if (!h || nsteps < 0) return fail(h, QGB_EINVAL, "bad argument");
   cudaStream_t st = S(stream);
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  static const bool graphs_off = getenv("QGB_NO_GRAPH") != nullptr;
   for (int s = 0; s < nsteps; ++s) {
-    StepIO io = base_io(h);
-    set_cnn_io(h, io);
-    int prog = PROG_STEP;
-    if (h->ext_set) {
-      io.dq = h->dq_ext;
-      prog = PROG_STEP_DQ_RAW;
-      h->ext_set = false;
-    } else if (h->kind != QGB_CLOSURE_NONE) {
-      int rc = closure_update(h, st);
+    if (graphs_off || !graph_eligible(h) || diag_sample_due(h)) {
+      int rc = step_once(h, st);
       if (rc) return rc;
-      io.dq = h->dq;
-      prog = PROG_STEP_DQ;
+      continue;
     }
-    if (h->avg_on && h->t >= h->cfg.dt && h->t >= h->tavestart &&
-        h->tc % (long long)std::ceil(h->taveint / h->cfg.dt) == 0) {
-      const int pd = h->prof.start(PROF_DIAG, st);
-      int rc = sample_averages(h, io.dq, st);
-      if (rc) return rc;
-      h->prof.stop(pd, st, h->cfg.members);
+    const unsigned long long key = graph_state_key(h);
+    if (key != h->graph_key) { invalidate_graphs(h); h->graph_key = key; }
+    const int slot = (int)(h->tc % 3);
+    if (!h->step_graph[slot]) {
+      // capture this step (the launches are recorded, not executed), instantiate, then replay it below
+      const long long tc0 = h->tc; const double t0 = h->t; const long long cc0 = h->const_counter; const bool xv0 = h->x_valid;
+      const long long l0 = g_launches.load();
+      cudaGraph_t graph = nullptr;
+      cudaError_t ce = cudaSuccess;
+      if (!h->cap_stream) ce = cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking);
+      if (ce == cudaSuccess) ce = cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal);
+      int rc = QGB_OK;
+      if (ce == cudaSuccess) {
+        rc = step_once(h, h->cap_stream);
+        ce = cudaStreamEndCapture(h->cap_stream, &graph);
+      }
+      h->tc = tc0; h->t = t0; h->const_counter = cc0; h->x_valid = xv0;   // host-side bookkeeping is redone by the replay
+      const long long captured = g_launches.load() - l0;                   // kernels recorded in the graph (not run yet)
+      g_launches.store(l0);
+      if (ce == cudaSuccess && rc == QGB_OK && graph) ce = cudaGraphInstantiate(&h->step_graph[slot], graph, 0);
+      if (graph) cudaGraphDestroy(graph);
+      if (ce != cudaSuccess || rc != QGB_OK || !h->step_graph[slot]) {
+        // capture is an optimisation: fall back to plain launches for the rest of this handle's life
+        cudaGetLastError();
+        h->step_graph[slot] = nullptr;
+        h->graph_failed = true;
+        h->err.clear();
+        rc = step_once(h, st);
+        if (rc) return rc;
+        continue;
+      }
+      h->graph_launches[slot] = captured;
     }
-    const int cur = (int)(h->tc % 3), prev = (int)((h->tc + 2) % 3), pprev = (int)((h->tc + 1) % 3);
-    io.d_cur = h->hist[cur]; io.d_p = h->hist[prev]; io.d_pp = h->hist[pprev];
-    ab_coefficients(h->ablevel, h->cfg.dt, io.dt1, io.dt2, io.dt3);
-    const int pi = h->prof.start(PROF_SPECTRAL, st);
-    int rc = launch_program(h, io, prog, st);
-    if (rc) return rc;
-    h->prof.stop(pi, st, h->cfg.members);
-    h->last_dq = io.dq;
-    if (h->ablevel < 2) h->ablevel++;
+    CUDA_TRY(h, cudaGraphLaunch(h->step_graph[slot], st));
+    g_launches.fetch_add(h->graph_launches[slot], std::memory_order_relaxed);
+    h->graph_replays += 1;
+    // host-side bookkeeping of step_once
+    if (h->kind != QGB_CLOSURE_NONE) {
+      if (h->sampler == QGB_SAMPLER_CONSTANT) h->const_counter = 1;
+      h->last_dq = h->dq;
+    } else {
+      h->last_dq = nullptr;
+    }
     h->tc += 1;
     h->t += h->cfg.dt;
-    h->x_valid = io.cnn_x != nullptr;
+    h->x_valid = h->kind != QGB_CLOSURE_NONE && h->xin != nullptr;
   }
   return QGB_OK;
 }
+
+int64_t qgb_graph_replays(const qgb_handle* h) { return h ? (int64_t)h->graph_replays : 0; }
 
 int qgb_step_host(qgb_handle* h, const double* q_in, double* q_out, int nsteps, void* stream) {
   if (!h) return QGB_EINVAL;
@@ -906,6 +1014,7 @@ int qgb_cnn_load(qgb_handle* h, int kind, int net, int nlayers, const qgb_cnn_la
     if (h->kind != kind) { free_net(h->nets[0]); free_net(h->nets[1]); h->dq_valid = false; h->noise_init = false; }
     h->kind = kind;
   }
+  invalidate_graphs(h);
   free_net(h->nets[net]);
   h->nets[net] = std::move(fresh);
   h->calibrated = false;
@@ -918,6 +1027,7 @@ int qgb_closure_config(qgb_handle* h, const float x_std[2], const float y_std[2]
   h->x_std[0] = x_std[0]; h->x_std[1] = x_std[1];
   h->y_std[0] = y_std[0]; h->y_std[1] = y_std[1];
   h->weight = weight;
+  invalidate_graphs(h);
   if (precision != h->precision) h->calibrated = false;
   h->precision = precision;
   h->x_valid = false;
@@ -935,6 +1045,7 @@ int qgb_set_sampler(qgb_handle* h, int kind, int nsteps, int n_mean) {
   if (!h) return QGB_EINVAL;
   if (kind < QGB_SAMPLER_AR1 || kind > QGB_SAMPLER_DETERMINISTIC) return fail(h, QGB_EINVAL, "Unknown sampling type");
   if (kind == QGB_SAMPLER_CONSTANT && nsteps < 1) return fail(h, QGB_EINVAL, "constant sampler needs nsteps >= 1");
+  invalidate_graphs(h);
   h->sampler = kind; h->sampler_nsteps = nsteps; h->n_mean = n_mean > 0 ? n_mean : 100;
   h->noise_init = false; h->const_counter = 0;
   return QGB_OK;
@@ -942,7 +1053,10 @@ int qgb_set_sampler(qgb_handle* h, int kind, int nsteps, int n_mean) {
 
 int qgb_seed(qgb_handle* h, uint64_t seed) {
   if (!h) return QGB_EINVAL;
-  h->seed = seed; h->draw = 0;
+  h->seed = seed;
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  CUDA_TRY(h, cudaMemset(h->d_draw, 0, sizeof(uint32_t)));
+  invalidate_graphs(h);
   return QGB_OK;
 }
 

@@ -57,7 +57,8 @@ __device__ inline void philox_normal4(uint64_t seed, uint32_t member, uint32_t d
 // xi_inj (optional) replaces Philox (parity injection).  One thread per 4 consecutive pixels.
 template <typename T>
 __global__ void latent_update_kernel(T* z, long long mstride, int npix, int members, int member_offset,
-                                     uint64_t seed, uint32_t draw, T a, T b, int replace, const T* xi_inj) {
+                                     uint64_t seed, const uint32_t* __restrict__ draw_counter, T a, T b, int replace, const T* xi_inj) {
+  const uint32_t draw = *draw_counter;      // device-resident draw counter: the launch is identical every step (CUDA-graph replay)
   const int quads = (npix + 3) / 4;
   const long long total = (long long)members * 2 * quads;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -81,6 +82,9 @@ __global__ void latent_update_kernel(T* z, long long mstride, int npix, int memb
     }
   }
 }
+
+// one thread: advances the draw counter after the latent kernel of a step has read it
+__global__ void bump_counter_kernel(uint32_t* c) { *c += 1u; }
 
 // ---------------------------------------------------------------- fp32 direct convolution -------------
 // in  : (batch, Cin, ny, nx) with batch stride in_bs;  out: (batch, Cout, ny, nx) with batch stride out_bs

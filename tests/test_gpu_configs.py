@@ -160,3 +160,32 @@ def test_two_devices_in_one_process_and_odd_cluster_sizes():
         m._step_forward()
         o._step_forward()
     assert np.abs(m.q[0] - o.q).max() / np.abs(o.q).max() < 1e-10
+
+
+def test_cuda_graph_replay_is_bit_identical_to_plain_launches(tmp_path):
+    """qgb_step replays a captured graph of the step in the steady state; a handle with kernel timing switched on launches
+    the same kernels one by one.  Same seed -> bit-identical states, with and without a closure."""
+    import ctypes
+    from pyqg_generative_b200 import _lib
+    from pyqg_generative_b200.models.cgan_regression import CGANRegression
+    from pyqg_generative_b200.tools.stochastic_pyqg import EnsembleQGModel, stochastic_QGModel
+    c = golden('closure_48.npz')
+    q0 = np.stack([c['q'].astype('float64')] * 4) * np.array([1.0, 0.9, 1.1, 0.8]).reshape(4, 1, 1, 1)
+
+    def run(plain, closure):
+        if closure:
+            model = CGANRegression(folder=write_model_folder(tmp_path, 'gan'), nx=48, precision='tc')
+            m = stochastic_QGModel(dict(nx=48, dt=7200.0, log_level=0, tmax=1e12, tavestart=1e12, members=4, parameterization=model,
+                                        precision='tc', seed=5), 'AR1', 1)
+        else:
+            m = EnsembleQGModel(nx=48, dt=7200.0, log_level=0, tmax=1e12, tavestart=1e12, members=4)
+        m.set_q(q0)
+        if plain:
+            _lib.check(m._lib.qgb_profile_all_begin(m._h), m._h)
+        m._step_forward(25)
+        return m.q, int(m._lib.qgb_graph_replays(m._h))
+    for closure in (False, True):
+        qa, ra = run(False, closure)
+        qb, rb = run(True, closure)
+        assert ra >= 20 and rb == 0, (closure, ra, rb)
+        assert np.array_equal(qa, qb), closure
