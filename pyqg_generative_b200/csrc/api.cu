@@ -59,6 +59,7 @@ struct qgb_handle {
   int nthreads = 256; size_t smem = 0; int grid = 0;
   bool fixed = false;   // compile-time specialised step kernel available for this nx
   bool reg64 = false;   // register-resident kernel (spectral64.cuh) for nx = 64
+  bool regcl = false;   // cluster register-FFT kernel (spectral_cl.cuh) for nx = 128, 256
   int nt64 = 384;
   bool large = false; cplx* scratch = nullptr; double* red_scratch = nullptr;   // cluster path for nx > 96
   int cluster = 8; int large_lines = 0; size_t large_smem = 0;   // lines of a 1-D FFT pass staged per CTA in shared memory
@@ -138,7 +139,7 @@ StepIO base_io(qgb_handle* h) {
 SpectralPlan make_plan(const qgb_handle* h) {
   SpectralPlan p;
   p.N = h->ht.N; p.members = h->cfg.members; p.grid = h->grid; p.nthreads = h->nthreads; p.smem = h->smem;
-  p.fixed = h->fixed; p.nt64 = h->nt64; p.reg64 = h->reg64; p.large = h->large; p.cluster = h->cluster; p.large_lines = h->large_lines;
+  p.fixed = h->fixed; p.nt64 = h->nt64; p.reg64 = h->reg64; p.regcl = h->regcl; p.large = h->large; p.cluster = h->cluster; p.large_lines = h->large_lines;
   p.large_smem = h->large_smem; p.scratch = h->scratch; p.red_scratch = h->red_scratch; p.true_pos = h->d_pos;
   return p;
 }
@@ -537,6 +538,7 @@ int qgb_create(const qgb_config* cfg, qgb_handle** out) {
     h->nt64 = e ? atoi(e) : 384;   // measured on B200: 256 -> 0.370 ms, 384 -> 0.299 ms, 512 -> 0.301 ms per 1024 members
   }
   h->reg64 = !h->large && cfg->nx == 64 && !getenv("QGB_S64_OFF");
+  h->regcl = h->large && (cfg->nx == 128 || cfg->nx == 256) && !getenv("QGB_SCL_OFF");
   h->grid = cfg->members;
   if (h->large) {
     // one cluster of CTAs per member, persistent over members when the ensemble exceeds the machine.  Cluster size: small

@@ -26,6 +26,12 @@
 #include "qg_core.cuh"
 
 namespace qgb {
+
+// pointwise spectral work, one bit per stage; a phase runs the selected stages on every half-plane point in array order
+enum { PW_TEND0 = 1, PW_TEND1 = 2, PW_UPDATE = 4, PW_UV0 = 8, PW_UV1 = 16, PW_STORE_QH = 32, PW_LOAD_QH = 64, PW_FORCING = 128 };
+// physical-space stage between the inverse and the forward x pass of a round
+enum { PH_PRODUCTS0 = 0, PH_PRODUCTS1 = 1, PH_LOAD_DQ = 2, PH_LOAD_Q = 3, PH_EMIT = 4 };
+
 namespace s64 {
 
 constexpr int N = 64, NK = 33, NN = N * NK, NPIX = N * N;
@@ -243,10 +249,6 @@ struct MemberPtrs {
   }
 };
 
-// pointwise spectral work, one bit per stage; a phase runs the selected stages on every half-plane point in array order
-enum { PW_TEND0 = 1, PW_TEND1 = 2, PW_UPDATE = 4, PW_UV0 = 8, PW_UV1 = 16, PW_STORE_QH = 32, PW_LOAD_QH = 64, PW_FORCING = 128 };
-// physical-space stage between the inverse and the forward x pass of a round
-enum { PH_PRODUCTS0 = 0, PH_PRODUCTS1 = 1, PH_LOAD_DQ = 2, PH_LOAD_Q = 3, PH_EMIT = 4 };
 
 // ST = the stages (compile time: straight-line code), NB = points in flight per thread: all global / shared loads of a batch
 // are issued before the first dependent instruction (the first version, one point at a time behind run-time stage tests, spent
@@ -286,11 +288,11 @@ S64_PHASE void pointwise_phase(const Tables& T, const StepIO& io, int member, cp
         dpp0[u] = P.d_pp[idx[u]]; dpp1[u] = P.d_pp[NN + idx[u]];
       }
       if (kQh) { kv[u] = dkw * (double)k[u]; lv[u] = dkw * (double)(l[u] < N / 2 ? l[u] : l[u] - N); }
-      if (kRead) spec_read(S, l[u], k[u], A[u], B[u]);
     }
     // ---- arithmetic and stores ----
 #pragma unroll
     for (int u = 0; u < NB; ++u) {
+      if (kRead) spec_read(S, l[u], k[u], A[u], B[u]);      // (shared memory: short latency, read where it is used)
       if (ST & PW_STORE_QH) {
         if (ok[u]) { P.qh[idx[u]] = A[u]; P.qh[NN + idx[u]] = B[u]; }
         continue;
@@ -437,6 +439,7 @@ S64_PHASE void round(bool has_inv, int phys, bool has_fwd, const Tables& T, cons
 }
 
 
+#ifndef S64_HELPERS_ONLY      // (spectral_cl.cuh reuses the building blocks above)
 // prog: PROG_STEP, PROG_STEP_DQ, PROG_STEP_DQ_RAW, PROG_SET_Q, PROG_C2R
 __global__ void __launch_bounds__(kThreads, 2) qg_step64_kernel(const __grid_constant__ Tables T, const __grid_constant__ StepIO io,
                                                                 int prog, int members) {
@@ -494,6 +497,8 @@ __global__ void __launch_bounds__(kThreads, 2) qg_step64_kernel(const __grid_con
     }
   }
 }
+
+#endif
 
 }  // namespace s64
 }  // namespace qgb

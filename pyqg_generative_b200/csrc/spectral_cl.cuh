@@ -1,0 +1,458 @@
+// spectral_cl.cuh -- register-FFT fused spectral time step for nx = 128 and 256 on a thread-block CLUSTER, sm_100a.
+//
+// Same step as spectral64.cuh (pyqg Model._step_forward, see qg_core.cuh), same building blocks (line transforms in registers,
+// 16 complex numbers per thread, the lanes of a line exchanging data with warp shuffles; two real fields per complex transform,
+// split into half-plane spectra between the passes; pointwise phases over half-plane points), scaled out:
+//
+//   nx = 128: a line is transformed by G = 8 lanes (16-point FFT, 3 xor rounds, two radix-8 butterflies), CL = 2 CTAs per member
+//   nx = 256: G = 16 lanes (16-point FFT, 4 xor rounds, 16-point FFT),                                   CL = 8 CTAs per member
+//
+// Every CTA has (nx / CL) * G = 512 threads.  In the x pass it owns nx / CL rows; in the y pass nx / (2 CL) columns of each of the
+// two half-plane spectra; in the pointwise phases the wavenumbers k of those columns (CTA 0 also k = nx / 2).  The transposition
+// between the passes goes through DISTRIBUTED SHARED MEMORY: the x-pass lanes store W_y(kx) with st.shared::cluster straight into
+// the buffer of the CTA that owns column kx (and back for the inverse transform), separated by cluster barriers -- the first-
+// generation cluster kernel (qg_core.cuh tiled_pass) bounced the whole field through an L2 scratch four times per transform and
+// ran every radix stage as a shared-memory pass (0.07 of the HBM roofline at 256^2, 2.5x the algorithmic DRAM traffic).
+// The half-plane spectra never leave the CTA: no Hermitian extension is built and the pointwise phases read and write global
+// memory in runs of nx / (2 CL) consecutive wavenumbers.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "spectral64.cuh"
+
+namespace qgb {
+namespace scl {
+
+using s64::conj16;
+using s64::dft4;
+using s64::exchange_pair;
+using s64::fft16;
+using s64::mulw16;
+using s64::sel;
+
+template <int N_, int G_, int CL_>
+struct Cfg {
+  static constexpr int N = N_, G = G_, CL = CL_;
+  static constexpr int NK = N / 2 + 1, NN = N * NK, NPIX = N * N, H = N / 2;
+  static constexpr int RPC = N / CL;            // rows of the x pass per CTA
+  static constexpr int SPC = N / (2 * CL);      // columns (wavenumbers k) of each spectrum per CTA
+  static constexpr int LPW = 32 / G;            // lines per warp
+  static constexpr int I = 16 / G;              // k1 values per lane after the exchange
+  static constexpr int kThreads = RPC * G;
+  static constexpr int PS = 2 * SPC + 5;        // row pitch of T / S: plus | minus (A | B) columns + 4 pad columns; odd
+  static constexpr int PT = N + 1;              // row pitch of T' (RPC rows): A columns 0..N/2-1, B columns N/2..N-1; odd
+  static constexpr int kBuf = (N * PS > RPC * PT) ? N * PS : RPC * PT;
+  static constexpr size_t kSmemBytes = (size_t)(kBuf + N) * sizeof(cplx);
+  static_assert(kThreads == 512 && (G == 8 || G == 16) && 16 * G == N, "unsupported geometry");
+};
+
+#define SCL_INL __device__ __forceinline__
+// half-plane points whose global loads are in flight together, per thread and pointwise phase (DRAM latency is the limiter of
+// these kernels: one CTA per SM, 16 warps)
+#ifndef SCL_PREFETCH
+#define SCL_PREFETCH 0
+#endif
+#ifndef SCL_NB_UV
+#define SCL_NB_UV 2
+#endif
+#ifndef SCL_NB_TEND
+#define SCL_NB_TEND 2
+#endif
+#ifndef SCL_NB_UPD
+#define SCL_NB_UPD 1
+#endif
+
+SCL_INL uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+SCL_INL void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// store a complex number into the shared memory of CTA ``rank`` of this cluster at the same offset as the local address
+SCL_INL void st_cluster(const cplx* local, uint32_t rank, cplx v) {
+  const uint32_t la = (uint32_t)__cvta_generic_to_shared(local);
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rank));
+  asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};" ::"r"(ra), "d"(v.x), "d"(v.y) : "memory");
+}
+
+// 8-point DFT, natural order in and out (forward kernel)
+SCL_INL void dft8(cplx& x0, cplx& x1, cplx& x2, cplx& x3, cplx& x4, cplx& x5, cplx& x6, cplx& x7) {
+  cplx e0 = x0, e1 = x2, e2 = x4, e3 = x6, o0 = x1, o1 = x3, o2 = x5, o3 = x7;
+  dft4<false>(e0, e1, e2, e3);
+  dft4<false>(o0, o1, o2, o3);
+  o1 = mulw16<2, false>(o1);
+  o2 = mulw16<4, false>(o2);
+  o3 = mulw16<6, false>(o3);
+  x0 = cadd(e0, o0); x4 = csub(e0, o0);
+  x1 = cadd(e1, o1); x5 = csub(e1, o1);
+  x2 = cadd(e2, o2); x6 = csub(e2, o2);
+  x3 = cadd(e3, o3); x7 = csub(e3, o3);
+}
+
+// N = 16 G point DFT of a line distributed over G lanes t = 0..G-1 (lanes lane0 + t of a warp), forward kernel:
+//   in  v[j] = x[G j + t]            out v[G i + k2] = X[t + G i + 16 k2]   (i < 16 / G, k2 < G)
+template <class C>
+SCL_INL void fftN(cplx (&v)[16], int t, const cplx* tw) {
+  constexpr int G = C::G, I = C::I, N = C::N;
+  fft16<false>(v);                        // v[k1] = sum_j x[G j + t] w16^{j k1};  k1 = dest + G i sits at index G i + dest
+  // G x G block transpose across the lanes of the line: one xor round per bit of the lane index
+#pragma unroll
+  for (int p = (G == 16 ? 3 : 2); p >= 0; --p) {
+    const bool bit = (t >> p) & 1;
+#pragma unroll
+    for (int i = 0; i < I; ++i)
+#pragma unroll
+      for (int q = 0; q < G; ++q)
+        if (!(q & (1 << p))) exchange_pair(v[G * i + q], v[G * i + (q | (1 << p))], bit, 1 << p);
+  }
+  // afterwards v[G i + n2] = Z_{n2}[t + G i];  twiddle w_N^{n2 (t + G i)}
+#pragma unroll
+  for (int i = 0; i < I; ++i)
+#pragma unroll
+    for (int n2 = 1; n2 < G; ++n2) v[G * i + n2] = cmul(v[G * i + n2], tw[(n2 * (t + G * i)) & (N - 1)]);
+  if (G == 16) fft16<false>(v);
+  else {
+#pragma unroll
+    for (int i = 0; i < I; ++i) dft8(v[8 * i], v[8 * i + 1], v[8 * i + 2], v[8 * i + 3], v[8 * i + 4], v[8 * i + 5], v[8 * i + 6], v[8 * i + 7]);
+  }
+}
+// rename the output naming v[G i + k2] (index t + G i + 16 k2 = G (i + I k2) + t) to the input naming v[j], j = i + I k2
+template <class C>
+SCL_INL void out_to_in_naming(cplx (&v)[16]) {
+  if (C::I == 1) return;
+  cplx tmp[16];
+#pragma unroll
+  for (int i = 0; i < C::I; ++i)
+#pragma unroll
+    for (int k2 = 0; k2 < C::G; ++k2) tmp[i + C::I * k2] = v[C::G * i + k2];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = tmp[j];
+}
+// index carried by register m of the output naming, for lane t
+template <class C>
+SCL_INL int out_index(int m, int t) { return t + C::G * (m / C::G) + 16 * (m % C::G); }
+
+// ---- geometry -----------------------------------------------------------------------------------------------------------
+// lane = G * (line within the warp) + t.  x pass: row y = rank * RPC + line.  y pass: line = isB * SPC + sl, column slot
+// rank * SPC + sl of spectrum A (isB = 0) or B; slot 0 (CTA 0) = the packed columns k = 0 and k = N / 2.
+// Shared buffer, used in turn as
+//   T   [N rows y][PS]      W_y(c) at column sl, W_y(-c) at column SPC + sl for the CTA's slots c        (physical -> spectral)
+//   S   [N rows l][PS]      Ahat(l, c) at sl, Bhat(l, c) at SPC + sl; pad columns 2 SPC .. 2 SPC + 3 = raw A / B at k = N/2, A / B at k = 0
+//   T'  [RPC rows y][PT]    A_y(c) at column c, B_y(c) at N / 2 + c for ALL slots c                      (spectral -> physical)
+template <class C>
+struct Geo {
+  int t, line, rank, y, sl, isB, slot, colS;
+  bool packed;
+  __device__ Geo() {
+    const int lane = threadIdx.x & 31;
+    t = lane % C::G;
+    line = (threadIdx.x >> 5) * C::LPW + lane / C::G;
+    rank = (int)cluster_rank();
+    y = rank * C::RPC + line;
+    sl = line % C::SPC;
+    isB = line / C::SPC;
+    slot = rank * C::SPC + sl;
+    packed = slot == 0;
+    colS = sl + (isB ? C::SPC : 0);
+  }
+};
+
+template <class C>
+struct MemberPtrs {
+  cplx* qh; double* q; cplx* d_cur; const cplx* d_p; const cplx* d_pp; const double* dq; float* cnn_x;
+  __device__ MemberPtrs(const StepIO& io, int m) {
+    qh = io.qh + (long long)m * 2 * C::NN;
+    q = io.q + (long long)m * 2 * C::NPIX;
+    d_cur = io.d_cur ? io.d_cur + (long long)m * 2 * C::NN : nullptr;
+    d_p = io.d_p ? io.d_p + (long long)m * 2 * C::NN : nullptr;
+    d_pp = io.d_pp ? io.d_pp + (long long)m * 2 * C::NN : nullptr;
+    dq = io.dq ? io.dq + (long long)m * 2 * C::NPIX : nullptr;
+    cnn_x = io.cnn_x ? io.cnn_x + (long long)m * io.cnn_mstride : nullptr;
+  }
+};
+
+// half-plane spectra of this CTA's wavenumbers in S (kk = k - rank * SPC; k = N / 2 belongs to CTA 0)
+template <class C>
+SCL_INL void spec_read(const cplx* S, int l, int k, int kk, cplx& A, cplx& B) {
+  if (k != 0 && k != C::H) { A = S[l * C::PS + kk]; B = S[l * C::PS + C::SPC + kk]; return; }
+  const int ln = (C::N - l) & (C::N - 1);
+  const cplx c0 = S[l * C::PS], n0 = S[ln * C::PS], c1 = S[l * C::PS + C::SPC], n1 = S[ln * C::PS + C::SPC];
+  if (k == 0) {
+    A = cmake(0.5 * (c0.x + n0.x), 0.5 * (c0.y - n0.y));
+    B = cmake(0.5 * (c1.x + n1.x), 0.5 * (c1.y - n1.y));
+  } else {
+    A = cmake(0.5 * (c0.y + n0.y), 0.5 * (n0.x - c0.x));
+    B = cmake(0.5 * (c1.y + n1.y), 0.5 * (n1.x - c1.x));
+  }
+}
+template <class C>
+SCL_INL void spec_write(cplx* S, int l, int k, int kk, cplx A, cplx B) {
+  const int ca = k == C::H ? 2 * C::SPC : (k == 0 ? 2 * C::SPC + 2 : kk);
+  const int cb = k == C::H ? 2 * C::SPC + 1 : (k == 0 ? 2 * C::SPC + 3 : C::SPC + kk);
+  S[l * C::PS + ca] = A;
+  S[l * C::PS + cb] = B;
+}
+
+// pointwise stages on the CTA's half-plane points (see spectral64.cuh pointwise_phase); ST compile time, NB points in flight
+template <class C, int ST, int NB>
+SCL_INL void pointwise_phase(const Tables& T, const StepIO& io, int member, int rank, cplx* S, bool demean) {
+  constexpr bool kRead = (ST & (PW_TEND0 | PW_TEND1 | PW_FORCING | PW_STORE_QH)) != 0;
+  constexpr bool kQh = (ST & PW_STORE_QH) == 0;
+  constexpr bool kTend = (ST & (PW_TEND0 | PW_TEND1)) != 0, kUv = (ST & (PW_UV0 | PW_UV1)) != 0, kUpd = (ST & PW_UPDATE) != 0;
+  constexpr int zT = (ST & PW_TEND1) ? 1 : 0, zU = (ST & PW_UV1) ? 1 : 0;
+  constexpr int NN = C::NN, NK = C::NK;
+  constexpr int NMAIN = C::SPC * C::N / C::kThreads;         // 8 points per thread; CTA 0 adds the column k = N / 2
+  constexpr int NIT = (NMAIN + 1 + NB - 1) / NB;
+  const MemberPtrs<C> P(io, member);
+  const double dkw = T.kv[1];
+  const double dt1 = io.dt1, dt2 = io.dt2, dt3 = io.dt3;
+#pragma unroll 1
+  for (int b = 0; b < NIT; ++b) {
+    int idx[NB], l[NB], k[NB], kk[NB];
+    bool ok[NB];
+    cplx A[NB], B[NB], q0[NB], q1[NB], dc0[NB], dc1[NB], dp0[NB], dp1[NB], dpp0[NB], dpp1[NB];
+    double aT0[NB], aT1[NB], aU0[NB], aU1[NB], fl[NB], kv[NB], lv[NB];
+#pragma unroll
+    for (int u = 0; u < NB; ++u) {
+      const int n = b * NB + u;
+      if (n < NMAIN) {
+        const int i = threadIdx.x + C::kThreads * n;
+        ok[u] = true;
+        kk[u] = i % C::SPC;
+        l[u] = i / C::SPC;
+        k[u] = rank * C::SPC + kk[u];
+      } else {                                    // the Nyquist column k = N / 2 (CTA 0, one point for the first N threads)
+        ok[u] = n == NMAIN && rank == 0 && (int)threadIdx.x < C::N;
+        l[u] = ok[u] ? (int)threadIdx.x : 0;
+        k[u] = ok[u] ? C::H : rank * C::SPC + 1;
+        kk[u] = ok[u] ? 0 : 1;
+      }
+      idx[u] = l[u] * NK + k[u];
+      if (kQh) { q0[u] = P.qh[idx[u]]; q1[u] = P.qh[NN + idx[u]]; }
+      if (kTend) { aT0[u] = T.a[(2 * zT) * NN + idx[u]]; aT1[u] = T.a[(2 * zT + 1) * NN + idx[u]]; }
+      if (kUv) { aU0[u] = T.a[(2 * zU) * NN + idx[u]]; aU1[u] = T.a[(2 * zU + 1) * NN + idx[u]]; }
+      if (kUpd) {
+        fl[u] = T.filtr[idx[u]];
+        dc0[u] = P.d_cur[idx[u]];
+        if (!(ST & PW_TEND1)) dc1[u] = P.d_cur[NN + idx[u]];
+        dp0[u] = P.d_p[idx[u]]; dp1[u] = P.d_p[NN + idx[u]];
+        dpp0[u] = P.d_pp[idx[u]]; dpp1[u] = P.d_pp[NN + idx[u]];
+      }
+      if (kQh) { kv[u] = dkw * (double)k[u]; lv[u] = dkw * (double)(l[u] < C::H ? l[u] : l[u] - C::N); }
+    }
+#pragma unroll
+    for (int u = 0; u < NB; ++u) {
+      if (kRead) spec_read<C>(S, l[u], k[u], kk[u], A[u], B[u]);      // (shared memory: short latency, read where it is used)
+      if (ST & PW_STORE_QH) {
+        if (ok[u]) { P.qh[idx[u]] = A[u]; P.qh[NN + idx[u]] = B[u]; }
+        continue;
+      }
+      cplx r = cmake(0.0, 0.0);
+      if (kTend) {
+        const cplx ph = cmake(aT0[u] * q0[u].x + aT1[u] * q1[u].x, aT0[u] * q0[u].y + aT1[u] * q1[u].y);
+        const cplx t1 = cmuli(A[u], kv[u]), t2 = cmuli(B[u], lv[u]), t3 = cmuli(ph, kv[u] * T.Qy[zT]);
+        r = cmake(-(t1.x + t2.x + t3.x), -(t1.y + t2.y + t3.y));
+        if (zT == 1 && T.rek != 0.0) {
+          const double f = T.rek * (kv[u] * kv[u] + lv[u] * lv[u]);
+          r.x += f * ph.x;
+          r.y += f * ph.y;
+        }
+        if (!kUpd && ok[u]) P.d_cur[zT * NN + idx[u]] = r;
+      }
+      if (kUpd) {
+        cplx f0 = cmake(0.0, 0.0), f1 = cmake(0.0, 0.0);
+        if ((ST & PW_FORCING) && !(demean && idx[u] == 0)) { f0 = A[u]; f1 = B[u]; }
+        const cplx dd0 = cadd(dc0[u], f0), dd1 = cadd((ST & PW_TEND1) ? r : dc1[u], f1);
+        const cplx n0 = cmake(fl[u] * (q0[u].x + dt1 * dd0.x + dt2 * dp0[u].x + dt3 * dpp0[u].x),
+                              fl[u] * (q0[u].y + dt1 * dd0.y + dt2 * dp0[u].y + dt3 * dpp0[u].y));
+        const cplx n1 = cmake(fl[u] * (q1[u].x + dt1 * dd1.x + dt2 * dp1[u].x + dt3 * dpp1[u].x),
+                              fl[u] * (q1[u].y + dt1 * dd1.y + dt2 * dp1[u].y + dt3 * dpp1[u].y));
+        if (ok[u]) {
+          P.d_cur[idx[u]] = dd0; P.d_cur[NN + idx[u]] = dd1;
+          P.qh[idx[u]] = n0; P.qh[NN + idx[u]] = n1;
+          spec_write<C>(S, l[u], k[u], kk[u], n0, n1);
+        }
+      }
+      if (kUv && ok[u]) {
+        const cplx ph = cmake(aU0[u] * q0[u].x + aU1[u] * q1[u].x, aU0[u] * q0[u].y + aU1[u] * q1[u].y);
+        spec_write<C>(S, l[u], k[u], kk[u], cmake(lv[u] * ph.y, -lv[u] * ph.x), cmake(-kv[u] * ph.y, kv[u] * ph.x));
+      }
+      if ((ST & PW_LOAD_QH) && ok[u]) spec_write<C>(S, l[u], k[u], kk[u], q0[u], q1[u]);
+    }
+  }
+}
+
+// One round: [inverse 2-D transform of the spectra in S] -> physical stage in registers -> [forward 2-D transform into S]
+template <class C>
+SCL_INL void round(bool has_inv, int phys, bool has_fwd, const Tables& T, const StepIO& io, int member, cplx* buf, const cplx* tw) {
+  constexpr int N = C::N, G = C::G, H = C::H, SPC = C::SPC, PS = C::PS, PT = C::PT, RPC = C::RPC, NPIX = C::NPIX;
+  const Geo<C> g;
+  const MemberPtrs<C> P(io, member);
+  cplx v[16];
+  const double s = T.inv_M;
+#pragma unroll 1
+  for (int hp = has_inv ? 0 : 2; hp < (has_fwd ? 4 : 2); ++hp) {
+    // ---- stage in ----
+    if (hp == 0) {                                     // columns of S, l = G j + t  (packed lanes: C with the c2r convention)
+      if (!g.packed) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = buf[(G * j + g.t) * PS + g.colS];
+      } else {
+        const int c0 = 2 * SPC + (g.isB ? 3 : 2), c1 = 2 * SPC + (g.isB ? 1 : 0);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int l = G * j + g.t, ln = (N - l) & (N - 1);
+          const cplx x0 = buf[l * PS + c0], n0 = buf[ln * PS + c0], x1 = buf[l * PS + c1], n1 = buf[ln * PS + c1];
+          v[j] = cmake(0.5 * (x0.x + n0.x - x1.y + n1.y), 0.5 * (x0.y - n0.y + x1.x + n1.x));
+        }
+      }
+      conj16(v);
+    } else if (hp == 1) {                              // row of T': W_y(kx) from A_y, B_y; kx = G j + t (j < 8 <=> kx < N / 2)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int kx = G * j + g.t;
+        const bool dc = j == 0 && g.t == 0, nyq = j == 8 && g.t == 0;
+        const int c = nyq ? 0 : (j < 8 ? kx : N - kx);
+        const cplx A = buf[g.line * PT + c], B = buf[g.line * PT + H + c];
+        cplx w = j < 8 ? cmake(A.x - B.y, A.y + B.x) : cmake(A.x + B.y, B.x - A.y);
+        if (j == 0) w = sel(dc, cmake(A.x, B.x), w);
+        if (j == 8) w = sel(nyq, cmake(A.y, B.y), w);
+        v[j] = cmake(w.x, -w.y);
+      }
+    } else if (hp == 3) {                              // columns of T: split W_y into A_y / B_y (packed: C0 / C1), y = G j + t
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int yy = G * j + g.t;
+        const cplx Pw = buf[yy * PS + g.sl], Q = buf[yy * PS + SPC + g.sl];     // W(c), W(-c)   (slot 0: W(0), W(N/2))
+        const cplx nA = cmake(0.5 * (Pw.x + Q.x), 0.5 * (Pw.y - Q.y)), nB = cmake(0.5 * (Pw.y + Q.y), 0.5 * (Q.x - Pw.x));
+        const cplx pA = cmake(Pw.x, Q.x), pB = cmake(Pw.y, Q.y);
+        v[j] = g.packed ? (g.isB ? pB : pA) : (g.isB ? nB : nA);
+      }
+    } else if (!has_inv) {                             // hp == 2 of a forward-only round: load the real pair, x = G j + t
+      const double* f0 = phys == PH_LOAD_DQ ? P.dq : P.q;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int i = g.y * N + G * j + g.t;
+        v[j] = cmake(f0[i], f0[NPIX + i]);
+        if (phys == PH_LOAD_Q && P.cnn_x) { P.cnn_x[i] = (float)v[j].x / io.x_std[0]; P.cnn_x[NPIX + i] = (float)v[j].y / io.x_std[1]; }
+      }
+    }
+    // ---- the line transform ----
+    fftN<C>(v, g.t, tw);
+    // ---- stage out ----
+    if (hp == 0) {                                     // A_y / B_y at y = out_index -> T' of the CTA that owns row y
+      cluster_sync();                                  // every CTA has read its S columns (and finished with its old T')
+      const int col = g.slot + (g.isB ? H : 0);
+#pragma unroll
+      for (int m = 0; m < 16; ++m) {
+        const int yy = out_index<C>(m, g.t);
+        st_cluster(buf + (yy % RPC) * PT + col, (uint32_t)(yy / RPC), cmake(v[m].x, -v[m].y));
+      }
+      cluster_sync();
+    } else if (hp == 1) {                              // physical row y, x = out_index (conjugate back, scale)
+      conj16(v);
+      if (phys == PH_EMIT) {
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+          const int i = g.y * N + out_index<C>(m, g.t);
+          const double q0 = v[m].x * s, q1 = v[m].y * s;
+          P.q[i] = q0;
+          P.q[NPIX + i] = q1;
+          if (P.cnn_x) { P.cnn_x[i] = (float)q0 / io.x_std[0]; P.cnn_x[NPIX + i] = (float)q1 / io.x_std[1]; }
+        }
+      } else {
+        const int z = phys == PH_PRODUCTS1 ? 1 : 0;
+        const double* qz = P.q + z * NPIX + g.y * N;
+        const double U = T.Ubg[z];
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+          const double qq = qz[out_index<C>(m, g.t)];
+          v[m] = cmake((v[m].x * s + U) * qq, (v[m].y * s) * qq);
+        }
+        out_to_in_naming<C>(v);
+      }
+    } else if (hp == 2) {                              // W_y(kx), kx = out_index -> T of the CTA that owns column slot(kx)
+      cluster_sync();                                  // every CTA has read its T' rows
+#pragma unroll
+      for (int m = 0; m < 16; ++m) {
+        const int kx = out_index<C>(m, g.t);
+        const bool minus = kx >= H;                    // kx = N / 2 is the "minus" partner of slot 0 (packed columns)
+        const int sg = kx < H ? kx : (N - kx) & (N - 1) & (H - 1);
+        st_cluster(buf + g.y * PS + (sg % SPC) + (minus ? SPC : 0), (uint32_t)(sg / SPC), v[m]);
+      }
+      cluster_sync();
+    } else {                                           // hp == 3: Ahat / Bhat / packed C at l = out_index -> S (local)
+      __syncthreads();                                 // the CTA's T columns have been read
+#pragma unroll
+      for (int m = 0; m < 16; ++m) buf[out_index<C>(m, g.t) * PS + g.colS] = v[m];
+      __syncthreads();
+    }
+  }
+}
+
+// prog: PROG_STEP, PROG_STEP_DQ, PROG_STEP_DQ_RAW, PROG_SET_Q, PROG_C2R.  One cluster of CL CTAs per member.
+template <int N_, int G_, int CL_>
+__global__ void __launch_bounds__(512, 1) qg_step_cl_kernel(const __grid_constant__ Tables T, const __grid_constant__ StepIO io,
+                                                            int prog, int members) {
+  using C = Cfg<N_, G_, CL_>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx* buf = reinterpret_cast<cplx*>(smem_raw);
+  cplx* tw = buf + C::kBuf;
+  for (int i = threadIdx.x; i < C::N; i += C::kThreads) tw[i] = T.tw[i];
+  const int rank = (int)cluster_rank();
+  const int ncl = gridDim.x / C::CL, cl = blockIdx.x / C::CL;
+  const bool with_dq = prog == PROG_STEP_DQ || prog == PROG_STEP_DQ_RAW;
+  const bool demean = prog == PROG_STEP_DQ;
+  const int nrounds = prog == PROG_C2R ? 1 : prog == PROG_SET_Q ? 2 : (with_dq ? 4 : 3);
+  cluster_sync();                                      // all CTAs of the cluster are resident before any remote store
+  for (int m = cl; m < members; m += ncl) {
+#if SCL_PREFETCH
+    {   // pull this member's arrays into L2 while the first transform runs: the pointwise phases then see L2 latency, not DRAM's
+      const MemberPtrs<C> P(io, m);
+      const int nspec = 2 * C::NN * (int)sizeof(cplx) / 128, nphys = 2 * C::NPIX * (int)sizeof(double) / 128;
+      for (int i = rank * C::kThreads + threadIdx.x; i < nspec; i += C::CL * C::kThreads) {
+        s64::prefetch_l2(reinterpret_cast<const char*>(P.qh) + 128 * i);
+        if (prog != PROG_SET_Q && prog != PROG_C2R) {
+          s64::prefetch_l2(reinterpret_cast<const char*>(P.d_p) + 128 * i);
+          s64::prefetch_l2(reinterpret_cast<const char*>(P.d_pp) + 128 * i);
+        }
+      }
+      if (prog != PROG_C2R)
+        for (int i = rank * C::kThreads + threadIdx.x; i < nphys; i += C::CL * C::kThreads) {
+          s64::prefetch_l2(reinterpret_cast<const char*>(P.q) + 128 * i);
+          if (P.dq) s64::prefetch_l2(reinterpret_cast<const char*>(P.dq) + 128 * i);
+        }
+    }
+#endif
+    __syncthreads();
+#pragma unroll 1
+    for (int r = 0; r < nrounds; ++r) {
+      int pw = 0, phys = PH_EMIT;
+      bool inv = true, fwd = true, rnd = true;
+      if (prog == PROG_C2R) { pw = PW_LOAD_QH; fwd = false; }
+      else if (prog == PROG_SET_Q) {
+        if (r == 0) { inv = false; phys = PH_LOAD_Q; } else { pw = PW_STORE_QH; rnd = false; }
+      } else if (r == 0) { pw = PW_UV0; phys = PH_PRODUCTS0; }
+      else if (r == 1) { pw = PW_TEND0 | PW_UV1; phys = PH_PRODUCTS1; }
+      else if (r == 2 && with_dq) { pw = PW_TEND1; inv = false; phys = PH_LOAD_DQ; }
+      else if (r == 2) { pw = PW_TEND1 | PW_UPDATE; fwd = false; }
+      else { pw = PW_FORCING | PW_UPDATE; fwd = false; }
+      if (pw) {
+        switch (pw) {
+          case PW_UV0: pointwise_phase<C, PW_UV0, SCL_NB_UV>(T, io, m, rank, buf, demean); break;
+          case PW_TEND0 | PW_UV1: pointwise_phase<C, PW_TEND0 | PW_UV1, SCL_NB_TEND>(T, io, m, rank, buf, demean); break;
+          case PW_TEND1: pointwise_phase<C, PW_TEND1, SCL_NB_TEND>(T, io, m, rank, buf, demean); break;
+          case PW_TEND1 | PW_UPDATE: pointwise_phase<C, PW_TEND1 | PW_UPDATE, SCL_NB_UPD>(T, io, m, rank, buf, demean); break;
+          case PW_FORCING | PW_UPDATE: pointwise_phase<C, PW_FORCING | PW_UPDATE, SCL_NB_UPD>(T, io, m, rank, buf, demean); break;
+          case PW_STORE_QH: pointwise_phase<C, PW_STORE_QH, SCL_NB_UV>(T, io, m, rank, buf, demean); break;
+          default: pointwise_phase<C, PW_LOAD_QH, SCL_NB_UV>(T, io, m, rank, buf, demean); break;
+        }
+        __syncthreads();
+      }
+      if (rnd) round<C>(inv, phys, fwd, T, io, m, buf, tw);
+    }
+  }
+  cluster_sync();                                      // no CTA exits while a peer may still store into its shared memory
+}
+
+}  // namespace scl
+}  // namespace qgb

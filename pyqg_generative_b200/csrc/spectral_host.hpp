@@ -22,6 +22,7 @@ struct SpectralPlan {
   size_t smem = 0;
   bool fixed = false;       // compile-time specialised step kernel available for this nx
   int nt64 = 384;
+  bool regcl = false;       // nx = 128, 256: cluster register-FFT kernel (spectral_cl.cuh) for the same programs
   bool reg64 = false;       // nx = 64: register-resident kernel (spectral64.cuh) for the step, the q setter and irfft2
   bool large = false;       // thread-block-cluster path (the packed field does not fit one CTA)
   int cluster = 8, large_lines = 0;
@@ -39,6 +40,9 @@ cudaError_t spectral_launch(const SpectralPlan& p, const Tables& T, const StepIO
 cudaError_t spectral64_configure();
 bool spectral64_handles(int prog);
 cudaError_t spectral64_launch(const Tables& T, const StepIO& io, int prog, int members, cudaStream_t st);
+// cluster (DSMEM) register-FFT kernel for nx = 128, 256 (tu_spectral_cl.cu)
+bool spectralcl_handles(int N, int prog);
+cudaError_t spectralcl_launch(const Tables& T, const StepIO& io, int prog, int members, cudaStream_t st);
 cudaError_t launch_diag_finish(const double* red, int members, double dt_over_dx, double* ke, double* cfl, int* flags, cudaStream_t st);
 cudaError_t launch_spectra(const Tables& T, const cplx* qh, int members, double* kespec, double* ensspec, cudaStream_t st);
 

@@ -47,6 +47,7 @@ cudaError_t spectral_configure(const SpectralPlan& p) {
 }
 
 cudaError_t spectral_launch(const SpectralPlan& p, const Tables& TT, const StepIO& io, int prog, cudaStream_t st) {
+  if (p.regcl && spectralcl_handles(p.N, prog)) return spectralcl_launch(TT, io, prog, p.members, st);
   if (p.large) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(p.grid);
