@@ -131,6 +131,7 @@ StepIO base_io(qgb_handle* h) {
   io.qh = h->qh; io.q = h->q;
   io.Hi_over_H[0] = h->ht.Hi_over_H[0]; io.Hi_over_H[1] = h->ht.Hi_over_H[1];
   io.x_std[0] = h->x_std[0]; io.x_std[1] = h->x_std[1];
+  io.x_inv[0] = 1.0f / h->x_std[0]; io.x_inv[1] = 1.0f / h->x_std[1];
   io.bud_F = h->ht.Hi_over_H[0] * h->ht.Hi_over_H[1] / (h->cfg.rd * h->cfg.rd);
   io.bud_U = h->cfg.U1 - h->cfg.U2;
   return io;

@@ -75,6 +75,7 @@ struct StepIO {
   float* cnn_x;         // closure input: member stride cnn_mstride floats, channel stride N*N; or nullptr
   long long cnn_mstride;
   float x_std[2];
+  float x_inv[2];       // 1 / x_std (rounded): the register-FFT kernels divide with one reciprocal multiply + one residual correction
   double dt1, dt2, dt3;
   // invert / diagnostics outputs (may be null)
   cplx* ph_out;

@@ -116,6 +116,12 @@ S64_INL cplx shfl_xor_c(cplx a, int mask, unsigned lanes = 0xffffffffu) {
 S64_INL cplx shfl_c(cplx a, int src, unsigned lanes) {
   return cmake(__shfl_sync(lanes, a.x, src), __shfl_sync(lanes, a.y, src));
 }
+// a / b in fp32 with b's rounded reciprocal at hand: quotient estimate + one residual correction (the sequence the compiler's
+// IEEE division runs, without its range checks: |a / b| is O(1) here) -- x_scale.normalize(q.astype('float32')), cnn_tools.py:524-528
+S64_INL float div_by(float a, float b, float inv) {
+  const float q = a * inv;
+  return fmaf(fmaf(-q, b, a), inv, q);
+}
 S64_INL void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 S64_INL cplx sel(bool p, cplx a, cplx b) { return cmake(p ? a.x : b.x, p ? a.y : b.y); }
 
@@ -389,7 +395,7 @@ S64_PHASE void round(bool has_inv, int phys, bool has_fwd, const Tables& T, cons
       for (int j = 0; j < 16; ++j) {
         const int i = g.y * N + 4 * j + g.xt;
         v[j] = cmake(f0[i], f0[NPIX + i]);
-        if (phys == PH_LOAD_Q && P.cnn_x) { P.cnn_x[i] = (float)v[j].x / io.x_std[0]; P.cnn_x[NPIX + i] = (float)v[j].y / io.x_std[1]; }
+        if (phys == PH_LOAD_Q && P.cnn_x) { P.cnn_x[i] = div_by((float)v[j].x, io.x_std[0], io.x_inv[0]); P.cnn_x[NPIX + i] = div_by((float)v[j].y, io.x_std[1], io.x_inv[1]); }
       }
     }                                                  // (else hp == 2: v comes from the physical stage of hp == 1)
     // ---- the line transform ----
@@ -410,7 +416,7 @@ S64_PHASE void round(bool has_inv, int phys, bool has_fwd, const Tables& T, cons
           const double q0 = v[m].x * s, q1 = v[m].y * s;
           P.q[i] = q0;
           P.q[NPIX + i] = q1;
-          if (P.cnn_x) { P.cnn_x[i] = (float)q0 / io.x_std[0]; P.cnn_x[NPIX + i] = (float)q1 / io.x_std[1]; }
+          if (P.cnn_x) { P.cnn_x[i] = div_by((float)q0, io.x_std[0], io.x_inv[0]); P.cnn_x[NPIX + i] = div_by((float)q1, io.x_std[1], io.x_inv[1]); }
         }
       } else {
         // (u + Ubg) q + i v q                                            (pyqg _do_advection, physical-space products)

@@ -333,7 +333,7 @@ SCL_INL void round(bool has_inv, int phys, bool has_fwd, const Tables& T, const 
       for (int j = 0; j < 16; ++j) {
         const int i = g.y * N + G * j + g.t;
         v[j] = cmake(f0[i], f0[NPIX + i]);
-        if (phys == PH_LOAD_Q && P.cnn_x) { P.cnn_x[i] = (float)v[j].x / io.x_std[0]; P.cnn_x[NPIX + i] = (float)v[j].y / io.x_std[1]; }
+        if (phys == PH_LOAD_Q && P.cnn_x) { P.cnn_x[i] = s64::div_by((float)v[j].x, io.x_std[0], io.x_inv[0]); P.cnn_x[NPIX + i] = s64::div_by((float)v[j].y, io.x_std[1], io.x_inv[1]); }
       }
     }
     // ---- the line transform ----
@@ -357,7 +357,7 @@ SCL_INL void round(bool has_inv, int phys, bool has_fwd, const Tables& T, const 
           const double q0 = v[m].x * s, q1 = v[m].y * s;
           P.q[i] = q0;
           P.q[NPIX + i] = q1;
-          if (P.cnn_x) { P.cnn_x[i] = (float)q0 / io.x_std[0]; P.cnn_x[NPIX + i] = (float)q1 / io.x_std[1]; }
+          if (P.cnn_x) { P.cnn_x[i] = s64::div_by((float)q0, io.x_std[0], io.x_inv[0]); P.cnn_x[NPIX + i] = s64::div_by((float)q1, io.x_std[1], io.x_inv[1]); }
         }
       } else {
         const int z = phys == PH_PRODUCTS1 ? 1 : 0;
