@@ -664,12 +664,234 @@ __global__ void __launch_bounds__(FUSE ? 640 : 384, 1) conv_tc_kernel(const __gr
   if (warp == 1) ptx::tmem_dealloc(tmem_base, C::NCOLS);
 }
 
+// ---------------------------------------------------------------------------------------- direct layer 1 ----
+// Layer 1 (4 or 2 -> 128, 5x5) without an im2col operand.  The im2col variant above writes 512 B of shared memory per pixel
+// (K = 100 padded to 128, hi and lo planes) and is bound by the LSU pipe (82 % busy, tensor pipe 36 %).  Here a pixel of the
+// input window is ONE 32-byte row of 16 fp16 "channels"
+//        [ a_hi (F) | a_lo (F) | a_hi (F) | 0 ... ]        F = real input channels, a = a_hi + a_lo
+// and the weights of a tap are a 16 x 128 matrix with rows   [ w_hi (F) | w_hi (F) | w_lo (F) | 0 ... ],
+// so ONE K = 16 tcgen05.mma per tap and M-tile accumulates the whole split-precision product a_hi w_hi + a_lo w_hi + a_hi w_lo,
+// the tap being just a different start address of the same window (like every other layer).  25 MMAs of N = 128 per M-tile
+// instead of 24 (same tensor time), 13 KB instead of 228 KB of builder traffic per 16 x 16 tile.
+// Shared memory: window stages [20][20] x 32 B (SWIZZLE_32B rows), all 25 tap matrices resident (100 KB).
+constexpr int kL1Win = 20, kL1AStage = 13312 /* 20*20*32 = 12800 -> 1024-aligned */, kL1NA = 4, kL1WBytes = 25 * 4096;
+constexpr int kL1Smem = kL1NA * kL1AStage + kL1WBytes + 1536 + 256 + 1024;
+
+template <int F, int OUTMODE>
+__global__ void __launch_bounds__(512, 1) conv_l1_direct_kernel(const __grid_constant__ TcConvParams P, const __grid_constant__ TcEpi E) {
+  constexpr int T = 2, COUT = 128, NACC = 2, DCOLS = 128, NCOLS = 512, HX = kL1Win;
+  extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
+  unsigned char* smem = tc_smem_raw + ((1024u - (ptx::smem_u32(tc_smem_raw) & 1023u)) & 1023u);
+  unsigned char* sA = smem;
+  unsigned char* sW = smem + kL1NA * kL1AStage;
+  float* sEpi = reinterpret_cast<float*>(sW + kL1WBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(sEpi) + 1536);
+  uint64_t* a_full = bars;                 // [NA]  128 builder arrivals
+  uint64_t* a_empty = bars + kL1NA;        // [NA]
+  uint64_t* w_full = bars + 2 * kL1NA;     // [1]
+  uint64_t* acc_full = w_full + 1;         // [NACC]
+  uint64_t* acc_empty = acc_full + NACC;   // [NACC] 256 epilogue arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + NACC);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < COUT; i += blockDim.x) { sEpi[i] = E.b[i]; sEpi[COUT + i] = E.s[i]; sEpi[2 * COUT + i] = E.t[i]; }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kL1NA; ++i) { ptx::mbar_init(&a_full[i], 128); ptx::mbar_init(&a_empty[i], 1); }
+    ptx::mbar_init(w_full, 1);
+    for (int i = 0; i < NACC; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], 256); }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc(tmem_slot, NCOLS);
+  ptx::pdl_launch_dependents();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  ptx::pdl_wait();
+  const uint32_t tmem_base = *tmem_slot;
+  const int tiles_per_img = P.tiles_y * P.tiles_x;
+
+  if (warp >= 12) {
+    // ===================== window builders: 4 warps, fp32 -> [a_hi | a_lo | a_hi | 0] rows, 32-byte swizzle ==============
+    const int bt = threadIdx.x - 384;                      // 0..127
+    uint32_t ia = 0;
+    const long long cs = (long long)P.ny * P.nx;
+    auto fetch = [&](int tile, int i, float (&f)[4]) {
+      f[0] = f[1] = f[2] = f[3] = 0.f;
+      if (tile < P.num_tiles && i < HX * HX) {
+        const int img = tile / tiles_per_img, r = tile - img * tiles_per_img;
+        const int y0 = (r / P.tiles_x) * 16, x0 = (r % P.tiles_x) * 16;
+        int sy = y0 + i / HX - 2, sx = x0 + i % HX - 2;
+        sy = sy < 0 ? sy + P.ny : (sy >= P.ny ? sy - P.ny : sy);
+        sx = sx < 0 ? sx + P.nx : (sx >= P.nx ? sx - P.nx : sx);
+        const float* src = P.x_f32 + (long long)img * P.x_bs + (long long)sy * P.nx + sx;
+#pragma unroll
+        for (int c = 0; c < F; ++c) f[c] = src[c * cs];
+      }
+    };
+    // window entries of this thread: bt, bt + 128, bt + 256, bt + 384 (< 400); the next tile's are fetched before this one is built
+    float nx_[4][4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) fetch(blockIdx.x, bt + 128 * e, nx_[e]);
+    for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x, ++ia) {
+      float cur[4][4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) cur[e][c] = nx_[e][c];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) fetch(tile + gridDim.x, bt + 128 * e, nx_[e]);
+      const uint32_t s = ia % kL1NA, par = (ia / kL1NA) & 1;
+      ptx::mbar_wait(&a_empty[s], par ^ 1);
+      unsigned char* stage = sA + s * kL1AStage;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int p = bt + 128 * e;
+        if (p < HX * HX) {
+          __half hi[4], lo[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            hi[c] = __float2half_rn(cur[e][c]);
+            lo[c] = __float2half_rn(cur[e][c] - __half2float(hi[c]));
+          }
+          __half row[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) row[k] = __float2half_rn(0.f);
+#pragma unroll
+          for (int c = 0; c < F; ++c) { row[c] = hi[c]; row[F + c] = lo[c]; row[2 * F + c] = hi[c]; }
+          const uint4* r4 = reinterpret_cast<const uint4*>(row);
+          unsigned char* dst = stage + p * 32;
+          const int sw = (p >> 2) & 1;                      // 32-byte swizzle: 16-byte chunk ^= address bit 7
+          *reinterpret_cast<uint4*>(dst + ((0 ^ sw) << 4)) = r4[0];
+          *reinterpret_cast<uint4*>(dst + ((1 ^ sw) << 4)) = r4[1];
+        }
+      }
+      ptx::fence_proxy_async_smem();
+      ptx::mbar_arrive(&a_full[s]);
+    }
+  } else if (warp == 0) {
+    // ===================== weights: all 25 tap matrices, once =========================================================
+    if (lane == 0) {
+      ptx::mbar_arrive_expect_tx(w_full, kL1WBytes);
+      for (int c = 0; c < 4; ++c)
+        ptx::bulk_g2s(sW + c * (kL1WBytes / 4), reinterpret_cast<const unsigned char*>(P.w) + c * (kL1WBytes / 4), kL1WBytes / 4, w_full);
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer ===================================================================================
+    // A: K-major SWIZZLE_32B, pixel rows of 32 B, 8-row groups one image row (HX pixels) apart; B: K-major no swizzle,
+    // tap matrix [2 k-chunks][128 n][8 halves]: core matrices 8 rows x 16 B, next k-chunk 2048 B further
+    constexpr uint32_t a_hi32 = (uint32_t)(HX * 2) | (1u << 14) | (6u << 29);
+    constexpr uint32_t b_hi32 = 8u | (1u << 14);
+    constexpr uint32_t idesc = make_idesc_f16(128, 128);
+    const uint32_t sA_u = ptx::smem_u32(sA) >> 4, sW_u = ptx::smem_u32(sW) >> 4;
+    uint32_t ia = 0, it = 0;
+    if (ptx::elect_one_sync()) {
+      ptx::mbar_wait(w_full, 0);
+      ptx::tc_fence_after();
+      for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x, ++it, ++ia) {
+        const uint32_t as = it % NACC, sa = ia % kL1NA;
+        ptx::mbar_wait(&acc_empty[as], ((it / NACC) & 1) ^ 1);
+        ptx::mbar_wait(&a_full[sa], (ia / kL1NA) & 1);
+        ptx::tc_fence_after();
+        const uint32_t dbase = tmem_base + as * (T * DCOLS);
+        const uint32_t a_stage = sA_u + sa * (kL1AStage >> 4);
+#pragma unroll 1
+        for (int dy = 0; dy < 5; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 5; ++dx) {
+            const uint32_t a0 = a_stage + (dy * HX + dx) * 2;
+            const uint64_t bdesc = ((uint64_t)b_hi32 << 32) | (sW_u + (dy * 5 + dx) * 256) | (128u << 16);
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+              const uint64_t adesc = ((uint64_t)a_hi32 << 32) | ((a0 + 16 * t) & 0x3FFFu) | (1u << 16);
+              ptx::mma_f16(dbase + t * DCOLS, adesc, bdesc, idesc, (dy | dx) ? 1u : 0u);
+            }
+          }
+        ptx::tc_commit(&a_empty[sa]);
+        ptx::tc_commit(&acc_full[as]);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4 && warp < 12) {
+    // ===================== epilogue: TMEM -> bias / ReLU / BN -> fp16 hi (+ e4m3 lo) with the circular halo -> HBM =========
+    const int q = warp & 3, half = (warp - 4) >> 2;
+    const int m = q * 32 + lane, prow = m >> 3, pcol = m & 7;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x, ++it) {
+      const int img = tile / tiles_per_img, r = tile - img * tiles_per_img;
+      const int y0 = (r / P.tiles_x) * 16, x0 = (r % P.tiles_x) * 16;
+      const uint32_t as = it % NACC;
+      ptx::mbar_wait(&acc_full[as], (it / NACC) & 1);
+      ptx::tc_fence_after();
+      constexpr int CW = 32, NBW = COUT / CW;
+      const int t = half;                                  // the two warps of a lane quarter take one M-tile each
+#pragma unroll
+      for (int nb = 0; nb < NBW; ++nb) {
+        const int n0 = nb * CW;
+        const int x = x0 + 8 * t + pcol, y = y0 + prow;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * (T * DCOLS) + t * DCOLS;
+        uint32_t rr[CW];
+        ptx::tmem_ld16(taddr + n0, reinterpret_cast<uint32_t(&)[16]>(rr[0]));
+        ptx::tmem_ld16(taddr + n0 + 16, reinterpret_cast<uint32_t(&)[16]>(rr[16]));
+        ptx::tmem_ld_wait();
+        if (nb == NBW - 1) {
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(&acc_empty[as]);
+        }
+        float v[CW];
+        const float4* eb = reinterpret_cast<const float4*>(sEpi + n0);
+        const float4* es = reinterpret_cast<const float4*>(sEpi + COUT + n0);
+        const float4* et = reinterpret_cast<const float4*>(sEpi + 2 * COUT + n0);
+#pragma unroll
+        for (int i4 = 0; i4 < CW / 4; ++i4) {
+          const float4 b = eb[i4], sc = es[i4], sh = et[i4];
+          const float a0 = __uint_as_float(rr[4 * i4 + 0]) * P.inv_wscale + b.x, a1 = __uint_as_float(rr[4 * i4 + 1]) * P.inv_wscale + b.y;
+          const float a2 = __uint_as_float(rr[4 * i4 + 2]) * P.inv_wscale + b.z, a3 = __uint_as_float(rr[4 * i4 + 3]) * P.inv_wscale + b.w;
+          v[4 * i4 + 0] = fmaxf(a0, 0.f) * sc.x + sh.x;
+          v[4 * i4 + 1] = fmaxf(a1, 0.f) * sc.y + sh.y;
+          v[4 * i4 + 2] = fmaxf(a2, 0.f) * sc.z + sh.z;
+          v[4 * i4 + 3] = fmaxf(a3, 0.f) * sc.w + sh.w;
+        }
+        const int op = P.out_pad, HPo = P.ny + 2 * op, WPo = P.nx + 2 * op;
+        int ys[2], xs[2], nys = 1, nxs = 1;
+        ys[0] = y + op; xs[0] = x + op;
+        if (y < op) ys[nys++] = y + op + P.ny; else if (y >= P.ny - op) ys[nys++] = y + op - P.ny;
+        if (x < op) xs[nxs++] = x + op + P.nx; else if (x >= P.nx - op) xs[nxs++] = x + op - P.nx;
+        uint32_t hi[CW / 2], lo8[CW / 4];
+#pragma unroll
+        for (int e = 0; e < CW / 2; ++e) {
+          const float f0 = v[2 * e], f1 = v[2 * e + 1];
+          const __half2 h2 = __floats2half2_rn(f0, f1);
+          hi[e] = *reinterpret_cast<const uint32_t*>(&h2);
+          if (OUTMODE == TC_OUT_HILO) {
+            const float2 back = __half22float2(h2);
+            const unsigned short p8 = __nv_cvt_float2_to_fp8x2(make_float2((f0 - back.x) * 2048.f, (f1 - back.y) * 2048.f), __NV_SATFINITE, __NV_E4M3);
+            if (e & 1) lo8[e >> 1] |= (uint32_t)p8 << 16; else lo8[e >> 1] = p8;
+          }
+        }
+        const int chunk = n0 >> 5;
+        for (int a = 0; a < nys; ++a)
+          for (int b2 = 0; b2 < nxs; ++b2) {
+            const long long pix = (((long long)img * P.out_nch + chunk) * HPo + ys[a]) * WPo + xs[b2];
+            __half* dh = P.out_hi + pix * 32;
+            ptx::st_global_v8(dh, &hi[0]);
+            ptx::st_global_v8(dh + 16, &hi[8]);
+            if (OUTMODE == TC_OUT_HILO) ptx::st_global_v8(reinterpret_cast<unsigned char*>(P.out_lo) + pix * 32, lo8);
+          }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, NCOLS);
+}
+
 // ------------------------------------------------------------------------------------------------ host side ----
 // (TcLayer / TcNet / TcWorkspace live in cnn_tc_host.hpp)
 void tc_free_net(TcNet& n) {
   for (auto& L : n.layers) cudaFree(L.w);
   cudaFree(n.l2_fast.w);
   n.l2_fast = TcLayer();
+  cudaFree(n.l1_direct.w);
+  n.l1_direct = TcLayer();
   n.layers.clear();
   n.ready = false;
 }
@@ -731,6 +953,55 @@ inline bool tc_pack_layer(TcLayer& L, int cin_p, int cout_p, int ks, int passes,
   return true;
 }
 
+// Direct layer 1 (conv_l1_direct_kernel): tap matrix [2 k-chunks][128 n][8 halves] with K rows [w_hi (F) | w_hi (F) | w_lo (F) | 0]
+inline bool tc_pack_l1_direct(TcLayer& L, int F, const float* w /* (128, F, 5, 5) */, const float* bias, const float* bnscale,
+                              const float* shift) {
+  L.cin = 16; L.cout = 128; L.ks = 5; L.relu = 1; L.real_cout = 128; L.passes = 3;
+  float maxabs = 0.f;
+  for (int i = 0; i < 128 * F * 25; ++i) maxabs = std::fmax(maxabs, std::fabs(w[i]));
+  int k = 0;
+  if (maxabs > 0.f) { k = (int)std::floor(std::log2(16384.0 / (double)maxabs)); if (k < 0) k = 0; if (k > 24) k = 24; }
+  const float scale = std::ldexp(1.0f, k);
+  L.inv_wscale = std::ldexp(1.0f, -k);
+  std::vector<__half> pk((size_t)25 * 2 * 128 * 8, __float2half_rn(0.f));
+  for (int tap = 0; tap < 25; ++tap)
+    for (int n = 0; n < 128; ++n)
+      for (int c = 0; c < F; ++c) {
+        const float v = w[((size_t)n * F + c) * 25 + tap] * scale;
+        const __half h = __float2half_rn(v), l = __float2half_rn(v - __half2float(h));
+        const int rows[3] = {c, F + c, 2 * F + c};
+        const __half vals[3] = {h, h, l};
+        for (int j = 0; j < 3; ++j) pk[(((size_t)tap * 2 + rows[j] / 8) * 128 + n) * 8 + rows[j] % 8] = vals[j];
+      }
+  for (int i = 0; i < 128; ++i) { L.epi.b[i] = bias[i]; L.epi.s[i] = bnscale[i]; L.epi.t[i] = shift[i]; }
+  if (cudaMalloc(&L.w, pk.size() * sizeof(__half)) != cudaSuccess) return false;
+  return cudaMemcpy(L.w, pk.data(), pk.size() * sizeof(__half), cudaMemcpyHostToDevice) == cudaSuccess;
+}
+
+template <int F, int OUTMODE>
+inline cudaError_t tc_launch_l1_direct(const TcConvParams& P, const TcEpi& E, int nsm, cudaStream_t st) {
+  auto kern = conv_l1_direct_kernel<F, OUTMODE>;
+  static bool configured[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kL1Smem);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64) configured[dev] = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(P.num_tiles < nsm ? P.num_tiles : nsm);
+  cfg.blockDim = dim3(512);
+  cfg.dynamicSmemBytes = kL1Smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, P, E);
+}
+
 // Accepts exactly the default AndrewCNN architecture: (4|2)->128 (5x5) ->64 (5x5) ->32 (3x3) -> 4 x [32->32 (3x3)] -> 2 (3x3)
 int tc_pack_net(TcNet& n, int nlayers, const qgb_cnn_layer* L, std::string* err) {
   tc_free_net(n);
@@ -770,6 +1041,7 @@ int tc_pack_net(TcNet& n, int nlayers, const qgb_cnn_layer* L, std::string* err)
       for (int ch = 0; ch < n.cin0; ++ch)
         for (int tap = 0; tap < 25; ++tap) wd[(size_t)co * K + tap * n.cin0 + ch] = L[0].weight[((size_t)co * n.cin0 + ch) * 25 + tap];
     if (!tc_pack_layer(n.layers[0], n.kp, 128, 1, 3, false, K, 128, wd, L[0].bias, sf.data(), tf.data(), 1)) { *err = "cuda"; return QGB_ECUDA; }
+    if (!tc_pack_l1_direct(n.l1_direct, n.cin0, L[0].weight, L[0].bias, sf.data(), tf.data())) { *err = "cuda"; return QGB_ECUDA; }
   }
   for (int i = 1; i < 8; ++i) {
     const int taps = ks[i] * ks[i];
@@ -955,7 +1227,14 @@ int tc_forward(const TcNet& net, TcWorkspace& ws, const float* x, long long x_bs
       }
       const int pi = ws.prof ? ws.prof->start(8 * ws.prof_net + li, st) : -1;
       cudaError_t e;
-      if (li == 0) {
+      static int l1_mode = -1;     // QGB_TC_L1 = im2col selects the first-generation layer-1 kernel
+      if (l1_mode < 0) { const char* e1 = getenv("QGB_TC_L1"); l1_mode = (e1 && std::strcmp(e1, "im2col") == 0) ? 0 : 1; }
+      if (li == 0 && l1_mode == 1) {
+        P.w = net.l1_direct.w; P.inv_wscale = net.l1_direct.inv_wscale;
+        P.tiles_y = ny / 16; P.tiles_x = nx / 16; P.num_tiles = nb * P.tiles_y * P.tiles_x;
+        if (fast_l2) e = net.cin0 == 4 ? tc_launch_l1_direct<4, TC_OUT_HI>(P, net.l1_direct.epi, nsm, st) : tc_launch_l1_direct<2, TC_OUT_HI>(P, net.l1_direct.epi, nsm, st);
+        else e = net.cin0 == 4 ? tc_launch_l1_direct<4, TC_OUT_HILO>(P, net.l1_direct.epi, nsm, st) : tc_launch_l1_direct<2, TC_OUT_HILO>(P, net.l1_direct.epi, nsm, st);
+      } else if (li == 0) {
         if (fast_l2) e = net.kp == 128 ? tc_launch<128, 128, 1, 3, 2, TC_OUT_HI, 4>(P, L.epi, nb, nsm, st) : tc_launch<64, 128, 1, 3, 2, TC_OUT_HI, 2>(P, L.epi, nb, nsm, st);
         else e = net.kp == 128 ? tc_launch<128, 128, 1, 3, 2, TC_OUT_HILO, 4>(P, L.epi, nb, nsm, st) : tc_launch<64, 128, 1, 3, 2, TC_OUT_HILO, 2>(P, L.epi, nb, nsm, st);
       } else if (li == 1) e = fast_l2 ? tc_launch_T<128, 64, 5, 1, TC_OUT_HILO>(tl, P, L.epi, nb, nsm, st) : tc_launch_T<128, 64, 5, 2, TC_OUT_HILO>(tl, P, L.epi, nb, nsm, st);

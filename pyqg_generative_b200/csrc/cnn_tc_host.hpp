@@ -39,6 +39,7 @@ struct TcNet {
   int kp = 0;            // padded im2col K of layer 1 (128 or 64)
   std::vector<TcLayer> layers;
   TcLayer l2_fast;       // layer 2 packed for the single-pass variant (QGB_PREC_TC_FAST)
+  TcLayer l1_direct;     // layer 1 packed for the im2col-free kernel (conv_l1_direct_kernel)
 };
 struct TcWorkspace {
   __half* buf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // a0_hi, a0_lo, ping hi/lo, pong hi/lo
