@@ -70,10 +70,13 @@ struct qgb_handle {
   float x_std[2] = {1.f, 1.f}, y_std[2] = {1.f, 1.f}; double weight = 1.0;
   int sampler = QGB_SAMPLER_AR1, sampler_nsteps = 1, n_mean = 100;
   bool noise_init = false; long long const_counter = 0; uint64_t seed = 0x5eed5eedULL;
+  bool noise_pending = false;   // this evaluation's white noise is generated inside layer 1 (no latent kernel ran)
+  bool noise_regen = false;     // ... so xin channels 2, 3 must be regenerated before the noise is read back
   uint32_t* d_draw = nullptr;   // Philox draw counter, device resident (read by the latent kernel, bumped after it)
   // CUDA-graph replay of the steady-state step (one graph per position of the tendency-history ring)
   cudaGraphExec_t step_graph[3] = {nullptr, nullptr, nullptr}; unsigned long long graph_key = 0; bool graph_failed = false;
   long long graph_replays = 0, graph_launches[3] = {0, 0, 0};
+  bool graph_noise_regen[3] = {false, false, false};
   cudaStream_t cap_stream = nullptr;   // capture happens on a private stream (the caller's may be the legacy default stream, which cannot capture)
   float* xin = nullptr;     // (B, cin0, N, N) closure input: normalised q [+ latent z for gan/vae]
   int xin_c = 0; bool x_valid = false;
@@ -215,17 +218,25 @@ int net_forward(qgb_handle* h, int net, const float* x, long long x_bs, float* y
     std::string e;
     h->tcw.prof = &h->prof;
     h->tcw.prof_net = net;
+    const bool gen = h->noise_pending && net == 0 && x == h->xin;
+    h->tcw.noise_inkernel = gen; h->tcw.noise_member0 = h->cfg.member_offset; h->tcw.noise_seed = h->seed; h->tcw.noise_draw = h->d_draw;
     int rc = tc_forward(h->nets[net].tc, h->tcw, x, x_bs, y, y_bs, batch, ny, nx, softplus, accumulate, h->nsm, st, &e,
                         precision == QGB_PREC_TC_FAST);
+    h->tcw.noise_inkernel = false;
     if (rc != 0) return fail(h, rc, "%s", e.c_str());
     g_launches.fetch_add(h->tcw.last_launches, std::memory_order_relaxed);
+    if (gen) {                       // the draw has been consumed by layer 1
+      h->noise_pending = false;
+      bump_counter_kernel<<<1, 1, 0, st>>>(h->d_draw);
+      QGB_COUNT_LAUNCH();
+    }
     return QGB_OK;
   }
   return net_forward_fp32(h, h->nets[net], x, x_bs, y, y_bs, batch, ny, nx, softplus, accumulate, st);
 }
 
 template <typename T>
-int launch_latent(qgb_handle* h, T* z, long long mstride, double a, double b, int replace, cudaStream_t st) {
+int launch_latent(qgb_handle* h, T* z, long long mstride, double a, double b, int replace, cudaStream_t st, int draw_bias = 0, bool bump = true) {
   const int npix = h->ht.N * h->ht.N;
   const long long total = (long long)h->cfg.members * 2 * ((npix + 3) / 4);
   int blocks = (int)((total + 255) / 256);
@@ -233,9 +244,8 @@ int launch_latent(qgb_handle* h, T* z, long long mstride, double a, double b, in
   const T* inj = h->xi_set ? (const T*)h->xi_inj : nullptr;
   const int pi = h->prof.start(PROF_LATENT, st);
   latent_update_kernel<T><<<blocks, 256, 0, st>>>(z, mstride, npix, h->cfg.members, h->cfg.member_offset, h->seed,
-                                                   h->d_draw, (T)a, (T)b, replace, inj);
-  bump_counter_kernel<<<1, 1, 0, st>>>(h->d_draw);
-  QGB_COUNT_LAUNCH();
+                                                   h->d_draw, draw_bias, (T)a, (T)b, replace, inj);
+  if (bump) { bump_counter_kernel<<<1, 1, 0, st>>>(h->d_draw); QGB_COUNT_LAUNCH(); }
   h->prof.stop(pi, st, h->cfg.members);
   QGB_COUNT_LAUNCH();
   CUDA_TRY(h, cudaGetLastError());
@@ -243,8 +253,21 @@ int launch_latent(qgb_handle* h, T* z, long long mstride, double a, double b, in
 }
 
 // white-noise draw (+AR1 blend) into the latent storage of the active closure
-int draw_latent(qgb_handle* h, double a, double b, int replace, cudaStream_t st) {
+int draw_latent(qgb_handle* h, double a, double b, int replace, cudaStream_t st, bool allow_inkernel = false) {
   const long long npix = (long long)h->ht.N * h->ht.N;
+  h->noise_pending = false;
+  if (allow_inkernel && (replace || (a == 0.0 && b == 1.0)) && !h->xi_set && (h->kind == QGB_CLOSURE_GAN || h->kind == QGB_CLOSURE_VAE) &&
+      h->nets[0].tc.ready && tc_l1_direct_enabled() && h->ht.N % 16 == 0 && !getenv("QGB_NOISE_STORED")) {
+    const int prec = h->precision == QGB_PREC_AUTO ? (h->calibrated ? h->auto_precision : QGB_PREC_FP32) : h->precision;
+    if (prec == QGB_PREC_TC || prec == QGB_PREC_TC_FAST) {
+      // white noise, tensor-core generator: layer 1 generates z from the Philox counters while it builds its input window
+      // (north_star (4): "Philox latent noise generated in-kernel"); the draw counter is bumped after that forward pass
+      h->noise_pending = true;
+      h->noise_regen = true;
+      return QGB_OK;
+    }
+  }
+  h->noise_regen = false;
   if (h->kind == QGB_CLOSURE_GAN || h->kind == QGB_CLOSURE_VAE) {
     if (h->xi_set && h->xi_dtype != 0) return fail(h, QGB_ESTATE, "injected latent must be float32 for gan/vae");
     return launch_latent<float>(h, h->xin + 2 * npix, 4 * npix, a, b, replace, st);
@@ -399,17 +422,17 @@ int closure_update(qgb_handle* h, cudaStream_t st) {
         a = 1.0 - 1.0 / h->sampler_nsteps;
         b = std::sqrt(1.0 / h->sampler_nsteps * (2.0 - 1.0 / h->sampler_nsteps));
       }
-      int rc = draw_latent(h, a, b, 0, st);
+      int rc = draw_latent(h, a, b, 0, st, true);
       if (rc) return rc;
     } else {
-      int rc = draw_latent(h, 0.0, 1.0, 1, st);
+      int rc = draw_latent(h, 0.0, 1.0, 1, st, true);
       if (rc) return rc;
       h->noise_init = true;
     }
   } else {  // constant sampler
     if (h->noise_init) {
       if (h->const_counter % h->sampler_nsteps == 0) {
-        int rc = draw_latent(h, 0.0, 1.0, 1, st);
+        int rc = draw_latent(h, 0.0, 1.0, 1, st, true);
         if (rc) return rc;
         h->const_counter = 1;
       } else {
@@ -417,7 +440,7 @@ int closure_update(qgb_handle* h, cudaStream_t st) {
         compute = false;
       }
     } else {
-      int rc = draw_latent(h, 0.0, 1.0, 1, st);
+      int rc = draw_latent(h, 0.0, 1.0, 1, st, true);
       if (rc) return rc;
       h->noise_init = true;
       h->const_counter = 1;
@@ -871,10 +894,12 @@ int qgb_step(qgb_handle* h, int nsteps, void* stream) {
         continue;
       }
       h->graph_launches[slot] = captured;
+      h->graph_noise_regen[slot] = h->noise_regen;
     }
     CUDA_TRY(h, cudaGraphLaunch(h->step_graph[slot], st));
     g_launches.fetch_add(h->graph_launches[slot], std::memory_order_relaxed);
     h->graph_replays += 1;
+    if (h->kind != QGB_CLOSURE_NONE) h->noise_regen = h->graph_noise_regen[slot];
     // host-side bookkeeping of step_once
     if (h->kind != QGB_CLOSURE_NONE) {
       if (h->sampler == QGB_SAMPLER_CONSTANT) h->const_counter = 1;
@@ -947,6 +972,15 @@ int qgb_get(qgb_handle* h, int field, void* out, int on_device, void* stream) {
       const size_t npix = (size_t)h->ht.N * h->ht.N;
       if (h->kind == QGB_CLOSURE_GZ) { src = h->z64; bytes = nreal(h) * sizeof(double); break; }
       if (h->kind == QGB_CLOSURE_GAN || h->kind == QGB_CLOSURE_VAE) {
+        if (h->noise_regen) {        // the latest draw only ever existed inside layer 1: regenerate it from the same counters
+          const long long np2 = (long long)h->ht.N * h->ht.N;
+          const bool inj = h->xi_set;
+          h->xi_set = false;
+          int rc = launch_latent<float>(h, h->xin + 2 * np2, 4 * np2, 0.0, 1.0, 1, st, -1, false);
+          h->xi_set = inj;
+          if (rc) return rc;
+          h->noise_regen = false;
+        }
         // strided gather of channels 2,3 of the closure input
         CUDA_TRY(h, cudaMemcpy2DAsync(out, 2 * npix * sizeof(float), h->xin + 2 * npix, 4 * npix * sizeof(float),
                                       2 * npix * sizeof(float), h->cfg.members,

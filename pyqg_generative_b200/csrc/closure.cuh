@@ -9,56 +9,17 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "philox.cuh"
+
 namespace qgb {
-
-// ---------------------------------------------------------------- Philox4x32-10 -----------------------
-struct Philox {
-  __device__ static inline void round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
-    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
-    const uint32_t hi0 = __umulhi(M0, c[0]), lo0 = M0 * c[0];
-    const uint32_t hi1 = __umulhi(M1, c[2]), lo1 = M1 * c[2];
-    const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
-    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
-  }
-  __device__ static inline void gen(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                    uint32_t (&out)[4]) {
-    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-    uint32_t c[4] = {c0, c1, c2, c3};
-#pragma unroll
-    for (int i = 0; i < 10; ++i) {
-      round(c, k0, k1);
-      k0 += 0x9E3779B9u;
-      k1 += 0xBB67AE85u;
-    }
-    out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
-  }
-};
-
-// four N(0,1) samples for counter (member_global, draw, channel, quad): Box-Muller on two uniform pairs
-__device__ inline void philox_normal4(uint64_t seed, uint32_t member, uint32_t draw, uint32_t chan, uint32_t quad,
-                                      float (&z)[4]) {
-  uint32_t r[4];
-  Philox::gen(seed, quad, chan, draw, member, r);
-  const float two_pi = 6.283185307179586f;
-#pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    const float u1 = ((float)(r[2 * j] >> 8) + 0.5f) * (1.0f / 16777216.0f);  // (0,1)
-    const float u2 = ((float)(r[2 * j + 1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
-    const float rad = sqrtf(-2.0f * logf(u1));
-    float s, c;
-    sincosf(two_pi * u2, &s, &c);
-    z[2 * j] = rad * c;
-    z[2 * j + 1] = rad * s;
-  }
-}
 
 // latent update  z <- a z + b xi  (first call / constant sampler: a=0,b=1 -> z = xi).
 // T = float : z lives in channels 2,3 of the closure input (B,4,N,N);  T = double : separate (B,2,N,N) buffer.
 // xi_inj (optional) replaces Philox (parity injection).  One thread per 4 consecutive pixels.
 template <typename T>
 __global__ void latent_update_kernel(T* z, long long mstride, int npix, int members, int member_offset,
-                                     uint64_t seed, const uint32_t* __restrict__ draw_counter, T a, T b, int replace, const T* xi_inj) {
-  const uint32_t draw = *draw_counter;      // device-resident draw counter: the launch is identical every step (CUDA-graph replay)
+                                     uint64_t seed, const uint32_t* __restrict__ draw_counter, int draw_bias, T a, T b, int replace, const T* xi_inj) {
+  const uint32_t draw = *draw_counter + (uint32_t)draw_bias;      // device-resident draw counter: the launch is identical every step (CUDA-graph replay)
   const int quads = (npix + 3) / 4;
   const long long total = (long long)members * 2 * quads;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;

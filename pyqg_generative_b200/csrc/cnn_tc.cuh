@@ -43,6 +43,7 @@
 
 #include "../../include/qgb200.h"
 #include "cnn_tc_host.hpp"
+#include "philox.cuh"
 
 #ifndef QGB_TC_NW_OVERRIDE
 #define QGB_TC_NW_OVERRIDE 0
@@ -185,6 +186,8 @@ struct TcConvParams {
   float* out_f32; long long out_bs; int out_c, softplus, accumulate;
   const float* x_f32; long long x_bs;          // fused layer-1 variant: raw network input (B, cin0, ny, nx) fp32
   int ny, nx, tiles_y, tiles_x, num_tiles;
+  // direct layer 1 with the latent noise generated in the kernel (channels 2, 3 of a 4-channel input): Philox key material
+  int noise; int noise_member0; unsigned long long noise_seed; const uint32_t* noise_draw;
 };
 
 // LO8: the low halves of the activations travel as e4m3 (value * 2^11, 1 byte per element, SWIZZLE_32B rows) and their pass
@@ -711,57 +714,75 @@ __global__ void __launch_bounds__(512, 1) conv_l1_direct_kernel(const __grid_con
 
   if (warp >= 12) {
     // ===================== window builders: 4 warps, fp32 -> [a_hi | a_lo | a_hi | 0] rows, 32-byte swizzle ==============
+    // One thread per (window row, pixel quad): the 20-pixel window row x0-2 .. x0+17 is covered by the six aligned quads
+    // x0-4 .. x0+19 (x0 is a multiple of 16, so no quad straddles the periodic wrap): 120 of the 128 builder threads load one
+    // float4 per channel -- or GENERATE the two latent channels from the Philox counters of that quad, exactly what the latent
+    // kernel would have written (closure.cuh) -- and write the rows of their (up to) four pixels.
     const int bt = threadIdx.x - 384;                      // 0..127
+    const int wr = bt / 6, wq = bt - 6 * wr;               // window row 0..19 (bt < 120), quad 0..5
     uint32_t ia = 0;
     const long long cs = (long long)P.ny * P.nx;
-    auto fetch = [&](int tile, int i, float (&f)[4]) {
-      f[0] = f[1] = f[2] = f[3] = 0.f;
-      if (tile < P.num_tiles && i < HX * HX) {
+    const bool gen = F == 4 && P.noise;
+    const uint32_t draw = gen ? *P.noise_draw : 0u;
+    auto fetch = [&](int tile, float4 (&f)[4]) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) f[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (tile < P.num_tiles && bt < 120) {
         const int img = tile / tiles_per_img, r = tile - img * tiles_per_img;
         const int y0 = (r / P.tiles_x) * 16, x0 = (r % P.tiles_x) * 16;
-        int sy = y0 + i / HX - 2, sx = x0 + i % HX - 2;
+        int sy = y0 + wr - 2, sx = x0 - 4 + 4 * wq;
         sy = sy < 0 ? sy + P.ny : (sy >= P.ny ? sy - P.ny : sy);
         sx = sx < 0 ? sx + P.nx : (sx >= P.nx ? sx - P.nx : sx);
         const float* src = P.x_f32 + (long long)img * P.x_bs + (long long)sy * P.nx + sx;
-#pragma unroll
-        for (int c = 0; c < F; ++c) f[c] = src[c * cs];
+        f[0] = *reinterpret_cast<const float4*>(src);
+        f[1] = *reinterpret_cast<const float4*>(src + cs);
+        if (gen) {
+          const uint32_t quad = (uint32_t)((sy * P.nx + sx) >> 2), mem = (uint32_t)(P.noise_member0 + img);
+          float z[4];
+          philox_normal4(P.noise_seed, mem, draw, 0u, quad, z);
+          f[2] = make_float4(z[0], z[1], z[2], z[3]);
+          philox_normal4(P.noise_seed, mem, draw, 1u, quad, z);
+          f[3] = make_float4(z[0], z[1], z[2], z[3]);
+        } else if (F == 4) {
+          f[2] = *reinterpret_cast<const float4*>(src + 2 * cs);
+          f[3] = *reinterpret_cast<const float4*>(src + 3 * cs);
+        }
       }
     };
-    // window entries of this thread: bt, bt + 128, bt + 256, bt + 384 (< 400); the next tile's are fetched before this one is built
-    float nx_[4][4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) fetch(blockIdx.x, bt + 128 * e, nx_[e]);
+    float4 nxt[4];
+    fetch(blockIdx.x, nxt);
     for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x, ++ia) {
-      float cur[4][4];
+      float4 cur[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) cur[e][c] = nx_[e][c];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) fetch(tile + gridDim.x, bt + 128 * e, nx_[e]);
+      for (int c = 0; c < 4; ++c) cur[c] = nxt[c];
+      fetch(tile + gridDim.x, nxt);
       const uint32_t s = ia % kL1NA, par = (ia / kL1NA) & 1;
       ptx::mbar_wait(&a_empty[s], par ^ 1);
       unsigned char* stage = sA + s * kL1AStage;
+      if (bt < 120) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int p = bt + 128 * e;
-        if (p < HX * HX) {
-          __half hi[4], lo[4];
+        for (int j = 0; j < 4; ++j) {
+          const int wx = 4 * wq - 2 + j;                   // window column of pixel j of the quad
+          if (wx >= 0 && wx < HX) {
+            const float vals[4] = {j == 0 ? cur[0].x : j == 1 ? cur[0].y : j == 2 ? cur[0].z : cur[0].w,
+                                   j == 0 ? cur[1].x : j == 1 ? cur[1].y : j == 2 ? cur[1].z : cur[1].w,
+                                   j == 0 ? cur[2].x : j == 1 ? cur[2].y : j == 2 ? cur[2].z : cur[2].w,
+                                   j == 0 ? cur[3].x : j == 1 ? cur[3].y : j == 2 ? cur[3].z : cur[3].w};
+            __half row[16];
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            hi[c] = __float2half_rn(cur[e][c]);
-            lo[c] = __float2half_rn(cur[e][c] - __half2float(hi[c]));
+            for (int k = 0; k < 16; ++k) row[k] = __float2half_rn(0.f);
+#pragma unroll
+            for (int c = 0; c < F; ++c) {
+              const __half hi = __float2half_rn(vals[c]);
+              row[c] = hi; row[F + c] = __float2half_rn(vals[c] - __half2float(hi)); row[2 * F + c] = hi;
+            }
+            const uint4* r4 = reinterpret_cast<const uint4*>(row);
+            const int p = wr * HX + wx;
+            unsigned char* dst = stage + p * 32;
+            const int sw = (p >> 2) & 1;                    // 32-byte swizzle: 16-byte chunk ^= address bit 7
+            *reinterpret_cast<uint4*>(dst + ((0 ^ sw) << 4)) = r4[0];
+            *reinterpret_cast<uint4*>(dst + ((1 ^ sw) << 4)) = r4[1];
           }
-          __half row[16];
-#pragma unroll
-          for (int k = 0; k < 16; ++k) row[k] = __float2half_rn(0.f);
-#pragma unroll
-          for (int c = 0; c < F; ++c) { row[c] = hi[c]; row[F + c] = lo[c]; row[2 * F + c] = hi[c]; }
-          const uint4* r4 = reinterpret_cast<const uint4*>(row);
-          unsigned char* dst = stage + p * 32;
-          const int sw = (p >> 2) & 1;                      // 32-byte swizzle: 16-byte chunk ^= address bit 7
-          *reinterpret_cast<uint4*>(dst + ((0 ^ sw) << 4)) = r4[0];
-          *reinterpret_cast<uint4*>(dst + ((1 ^ sw) << 4)) = r4[1];
         }
       }
       ptx::fence_proxy_async_smem();
@@ -886,6 +907,11 @@ __global__ void __launch_bounds__(512, 1) conv_l1_direct_kernel(const __grid_con
 
 // ------------------------------------------------------------------------------------------------ host side ----
 // (TcLayer / TcNet / TcWorkspace live in cnn_tc_host.hpp)
+bool tc_l1_direct_enabled() {
+  static int mode = -1;
+  if (mode < 0) { const char* e1 = getenv("QGB_TC_L1"); mode = (e1 && std::strcmp(e1, "im2col") == 0) ? 0 : 1; }
+  return mode == 1;
+}
 void tc_free_net(TcNet& n) {
   for (auto& L : n.layers) cudaFree(L.w);
   cudaFree(n.l2_fast.w);
@@ -1205,6 +1231,7 @@ int tc_forward(const TcNet& net, TcWorkspace& ws, const float* x, long long x_bs
       P.out_f32 = nullptr; P.out_bs = 0; P.out_c = 0; P.softplus = 0; P.accumulate = 0;
       P.x_f32 = x + (long long)b0 * x_bs; P.x_bs = x_bs;
       P.out_hi = P.out_lo = nullptr; P.out_pad = 0; P.out_nch = 0;
+      P.noise = 0; P.noise_member0 = 0; P.noise_seed = 0; P.noise_draw = nullptr;
       TcTile tl = {1, 2};                                        // layer 1 (fused im2col): 16 x 16 tiles
       if (li == 1) tl = fast_l2 ? tc_pick_tile<64, 1>(ny, nx) : tc_pick_tile<64, 2>(ny, nx);
       else if (li >= 2 && li < 7) tl = tc_pick_tile<32, 3>(ny, nx, L.cin == 32);
@@ -1230,6 +1257,7 @@ int tc_forward(const TcNet& net, TcWorkspace& ws, const float* x, long long x_bs
       static int l1_mode = -1;     // QGB_TC_L1 = im2col selects the first-generation layer-1 kernel
       if (l1_mode < 0) { const char* e1 = getenv("QGB_TC_L1"); l1_mode = (e1 && std::strcmp(e1, "im2col") == 0) ? 0 : 1; }
       if (li == 0 && l1_mode == 1) {
+        if (ws.noise_inkernel && net.cin0 == 4) { P.noise = 1; P.noise_member0 = ws.noise_member0 + b0; P.noise_seed = ws.noise_seed; P.noise_draw = ws.noise_draw; }
         P.w = net.l1_direct.w; P.inv_wscale = net.l1_direct.inv_wscale;
         P.tiles_y = ny / 16; P.tiles_x = nx / 16; P.num_tiles = nb * P.tiles_y * P.tiles_x;
         if (fast_l2) e = net.cin0 == 4 ? tc_launch_l1_direct<4, TC_OUT_HI>(P, net.l1_direct.epi, nsm, st) : tc_launch_l1_direct<2, TC_OUT_HI>(P, net.l1_direct.epi, nsm, st);

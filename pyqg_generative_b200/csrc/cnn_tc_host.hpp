@@ -48,9 +48,12 @@ struct TcWorkspace {
   Profiler* prof = nullptr;
   int prof_net = 0;
   long long last_launches = 0;   // kernels launched by the latest tc_forward
+  // latent noise generated inside layer 1 (direct kernel, 4-channel input): set by api.cu for ONE forward pass
+  bool noise_inkernel = false; int noise_member0 = 0; unsigned long long noise_seed = 0; const uint32_t* noise_draw = nullptr;
 };
 
 
+bool tc_l1_direct_enabled();   // the im2col-free layer-1 kernel is in use (QGB_TC_L1=im2col switches back)
 void tc_free_net(TcNet& n);
 void tc_free_workspace(TcWorkspace& w);
 // Accepts exactly the default AndrewCNN architecture; leaves n.ready == false otherwise

@@ -189,3 +189,36 @@ def test_cuda_graph_replay_is_bit_identical_to_plain_launches(tmp_path):
         qb, rb = run(True, closure)
         assert ra >= 20 and rb == 0, (closure, ra, rb)
         assert np.array_equal(qa, qb), closure
+
+
+def test_latent_noise_generated_inside_layer_one_equals_the_stored_path(tmp_path):
+    """north_star (4): with white noise and the tensor-core generator the Philox latent field is generated inside layer 1 of the
+    network (no latent kernel, z never stored).  Reading the noise back regenerates it from the same counters; injecting that
+    field into a second model (stored-noise path) must give the bit-identical forcing, step after step."""
+    from pyqg_generative_b200 import _lib
+    from pyqg_generative_b200.models.cgan_regression import CGANRegression
+    from pyqg_generative_b200.tools.stochastic_pyqg import stochastic_QGModel
+    c = golden('closure_48.npz')
+    q0 = np.stack([c['q'].astype('float64')] * 3) * np.array([1.0, 0.9, 1.1]).reshape(3, 1, 1, 1)
+
+    def make(seed):
+        model = CGANRegression(folder=write_model_folder(tmp_path, 'gan'), nx=48, precision='tc')
+        m = stochastic_QGModel(dict(nx=48, dt=7200.0, log_level=0, tmax=1e12, tavestart=1e12, members=3, member_offset=5,
+                                    parameterization=model, precision='tc', seed=seed), 'constant', 1)
+        m.set_q(q0)
+        return m
+    a, b = make(11), make(99)
+    for step in range(3):
+        l0 = _lib.launch_count()
+        fa = a.closure_eval()
+        launched = _lib.launch_count() - l0
+        za = a.noise_sampler.noise                     # regenerated from the Philox counters
+        assert za.dtype == np.float32 and abs(za.std() - 1) < 0.05
+        b.set_latent(za)                               # stored path: latent kernel copies the injected field
+        fb = b.closure_eval()
+        assert np.array_equal(fa, fb), step
+        assert launched <= 11, launched                # 8 conv layers + epilogue + draw-counter bump (+ demean for the read-back): no latent kernel
+        a._step_forward(1)
+        b.set_latent(a.noise_sampler.noise)
+        b._step_forward(1)
+        assert np.array_equal(a.q, b.q), step
