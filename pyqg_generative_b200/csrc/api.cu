@@ -70,6 +70,7 @@ struct qgb_handle {
   float x_std[2] = {1.f, 1.f}, y_std[2] = {1.f, 1.f}; double weight = 1.0;
   int sampler = QGB_SAMPLER_AR1, sampler_nsteps = 1, n_mean = 100;
   bool noise_init = false; long long const_counter = 0; uint64_t seed = 0x5eed5eedULL;
+  bool fuse_dq = false;         // the next tensor-core forward of network 0 writes the forcing itself (closure epilogue fused)
   bool noise_pending = false;   // this evaluation's white noise is generated inside layer 1 (no latent kernel ran)
   bool noise_regen = false;     // ... so xin channels 2, 3 must be regenerated before the noise is read back
   uint32_t* d_draw = nullptr;   // Philox draw counter, device resident (read by the latent kernel, bumped after it)
@@ -219,10 +220,12 @@ int net_forward(qgb_handle* h, int net, const float* x, long long x_bs, float* y
     h->tcw.prof = &h->prof;
     h->tcw.prof_net = net;
     const bool gen = h->noise_pending && net == 0 && x == h->xin;
+    h->tcw.dq_out = (h->fuse_dq && net == 0) ? h->dq : nullptr; h->tcw.dq_ys[0] = h->y_std[0]; h->tcw.dq_ys[1] = h->y_std[1]; h->tcw.dq_weight = h->weight;
     h->tcw.noise_inkernel = gen; h->tcw.noise_member0 = h->cfg.member_offset; h->tcw.noise_seed = h->seed; h->tcw.noise_draw = h->d_draw;
     int rc = tc_forward(h->nets[net].tc, h->tcw, x, x_bs, y, y_bs, batch, ny, nx, softplus, accumulate, h->nsm, st, &e,
                         precision == QGB_PREC_TC_FAST);
     h->tcw.noise_inkernel = false;
+    h->tcw.dq_out = nullptr;
     if (rc != 0) return fail(h, rc, "%s", e.c_str());
     g_launches.fetch_add(h->tcw.last_launches, std::memory_order_relaxed);
     if (gen) {                       // the draw has been consumed by layer 1
@@ -460,8 +463,13 @@ int closure_update(qgb_handle* h, cudaStream_t st) {
     finish_gz_kernel<<<blocks, 256, 0, st>>>(h->ynet[0], h->ynet[1], h->z64, h->dq, (int)npix, total, h->y_std[0],
                                               h->y_std[1], h->weight, 1);
   } else {
+    // tensor-core generator: the last layer's epilogue writes dq = float64(y * y_std) * weight itself
+    h->fuse_dq = (prec == QGB_PREC_TC || prec == QGB_PREC_TC_FAST) && !getenv("QGB_NO_FUSED_EPILOGUE");
+    const bool fused = h->fuse_dq;
     int rc = net_forward(h, 0, h->xin, x_bs, h->ynet[0], 2 * npix, B, N, N, 0, 0, prec, st);
+    h->fuse_dq = false;
     if (rc) return rc;
+    if (fused) { CUDA_TRY(h, cudaGetLastError()); h->dq_valid = true; return QGB_OK; }
     pf = h->prof.start(PROF_FINISH, st);
     finish_plain_kernel<<<blocks, 256, 0, st>>>(h->ynet[0], h->dq, (int)npix, total, h->y_std[0], h->y_std[1],
                                                  h->weight, 1.0f);

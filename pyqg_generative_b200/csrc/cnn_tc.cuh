@@ -188,6 +188,9 @@ struct TcConvParams {
   int ny, nx, tiles_y, tiles_x, num_tiles;
   // direct layer 1 with the latent noise generated in the kernel (channels 2, 3 of a 4-channel input): Philox key material
   int noise; int noise_member0; unsigned long long noise_seed; const uint32_t* noise_draw;
+  // last layer with the closure epilogue fused: dq = float64(y * y_std) * weight (models/cgan_regression.py:157-162) straight to the
+  // forcing array (B, 2, ny, nx) instead of the fp32 network output
+  double* out_dq; float dq_ys0, dq_ys1; double dq_weight;
 };
 
 // LO8: the low halves of the activations travel as e4m3 (value * 2^11, 1 byte per element, SWIZZLE_32B rows) and their pass
@@ -619,8 +622,12 @@ __global__ void __launch_bounds__(FUSE ? 640 : 384, 1) conv_tc_kernel(const __gr
             if (n < P.out_c) {
               float a = v[i];
               if (P.softplus) a = softplus_f(a);
-              float* o = P.out_f32 + (long long)img * P.out_bs + ((long long)n * P.ny + y) * P.nx + x;
-              *o = P.accumulate ? *o + a : a;
+              if (P.out_dq) {
+                P.out_dq[((long long)img * P.out_c + n) * P.ny * P.nx + (long long)y * P.nx + x] = (double)__fmul_rn(a, n ? P.dq_ys1 : P.dq_ys0) * P.dq_weight;
+              } else {
+                float* o = P.out_f32 + (long long)img * P.out_bs + ((long long)n * P.ny + y) * P.nx + x;
+                *o = P.accumulate ? *o + a : a;
+              }
             }
           }
         } else {
@@ -1232,6 +1239,7 @@ int tc_forward(const TcNet& net, TcWorkspace& ws, const float* x, long long x_bs
       P.x_f32 = x + (long long)b0 * x_bs; P.x_bs = x_bs;
       P.out_hi = P.out_lo = nullptr; P.out_pad = 0; P.out_nch = 0;
       P.noise = 0; P.noise_member0 = 0; P.noise_seed = 0; P.noise_draw = nullptr;
+      P.out_dq = nullptr; P.dq_ys0 = P.dq_ys1 = 1.f; P.dq_weight = 1.0;
       TcTile tl = {1, 2};                                        // layer 1 (fused im2col): 16 x 16 tiles
       if (li == 1) tl = fast_l2 ? tc_pick_tile<64, 1>(ny, nx) : tc_pick_tile<64, 2>(ny, nx);
       else if (li >= 2 && li < 7) tl = tc_pick_tile<32, 3>(ny, nx, L.cin == 32);
@@ -1251,6 +1259,9 @@ int tc_forward(const TcNet& net, TcWorkspace& ws, const float* x, long long x_bs
         P.out_nch = L.cout / 32;
       } else {
         P.out_f32 = y + (long long)b0 * y_bs; P.out_bs = y_bs; P.out_c = L.real_cout; P.softplus = softplus; P.accumulate = accumulate;
+        if (ws.dq_out && L.real_cout == 2 && !softplus && !accumulate) {
+          P.out_dq = ws.dq_out + (long long)b0 * 2 * ny * nx; P.dq_ys0 = ws.dq_ys[0]; P.dq_ys1 = ws.dq_ys[1]; P.dq_weight = ws.dq_weight;
+        }
       }
       const int pi = ws.prof ? ws.prof->start(8 * ws.prof_net + li, st) : -1;
       cudaError_t e;

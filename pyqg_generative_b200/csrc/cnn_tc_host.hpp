@@ -49,6 +49,8 @@ struct TcWorkspace {
   int prof_net = 0;
   long long last_launches = 0;   // kernels launched by the latest tc_forward
   // latent noise generated inside layer 1 (direct kernel, 4-channel input): set by api.cu for ONE forward pass
+  // closure epilogue fused into the last layer (set by api.cu for ONE forward pass): dq = float64(y * y_std) * weight
+  double* dq_out = nullptr; float dq_ys[2] = {1.f, 1.f}; double dq_weight = 1.0;
   bool noise_inkernel = false; int noise_member0 = 0; unsigned long long noise_seed = 0; const uint32_t* noise_draw = nullptr;
 };
 
