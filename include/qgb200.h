@@ -165,11 +165,14 @@ int qgb_diag_spectra(qgb_handle* h, double* kespec_sum, double* ensspec_sum, int
  * QGModel._initialize_model_diagnostics / Model._initialize_diagnostics lambdas, consumed by
  * tools/comparison_tools.py:91,164-189,222-263).  out: double (QGB_BUDGET_TERMS, N, N/2+1), every term / M^2:
  * KEflux, APEflux, APEgenspec, KEfrictionspec, entspec, paramspec_KEflux, paramspec_APEflux (their sum is pyqg's
- * paramspec; zero without a closure or before its first evaluation). */
-#define QGB_BUDGET_TERMS 7
+ * paramspec; zero without a closure or before its first evaluation), then the enstrophy budget and the filter dissipation
+ * that tools/comparison_tools.py:222-225 iterates over: ENSflux, ENSgenspec, ENSfrictionspec, Dissspec, ENSDissspec,
+ * ENSparamspec.  Dissspec / ENSDissspec describe the update the next _forward_timestep performs (its Adams-Bashforth level,
+ * the tendency history as it stands), which is where pyqg's _step_forward evaluates them. */
+#define QGB_BUDGET_TERMS 13
 int qgb_diag_budget(qgb_handle* h, double* out, int on_device, void* stream);
 /* pyqg's time-averaged diagnostics (Model tavestart / taveint, _increment_diagnostics): once configured, qgb_step samples
- * KEspec (2), Ensspec (2) and the 7 budget terms before every step with t >= dt, t >= tavestart and
+ * KEspec (2), Ensspec (2) and the QGB_BUDGET_TERMS budget terms before every step with t >= dt, t >= tavestart and
  * tc % ceil(taveint/dt) == 0 and adds them (summed over the local members) to device accumulators.
  * qgb_diag_averages returns the accumulators, double (4 + QGB_BUDGET_TERMS, N, N/2+1), and the number of samples;
  * mean = sum / (nsamples * total members) after the cross-rank all-reduce.  reset != 0 clears them afterwards. */

@@ -357,6 +357,7 @@ class QGModel(object):
         M2 = self.M ** 2
         self._calc_derived_fields()
         ph, qh = self.ph, self.qh
+        hr = (self.Hi / self.H)[:, np.newaxis, np.newaxis]
         d = {
             'KEspec': self.wv2 * np.abs(ph) ** 2 / M2,
             'Ensspec': np.abs(qh) ** 2 / M2,
@@ -367,10 +368,26 @@ class QGModel(object):
                 1j * self.k * (self.del1 * ph[0] + self.del2 * ph[1]) * np.conj(ph[0] - ph[1])) / M2,
             'KEfrictionspec': -self.rek * self.del2 * self.wv2 * np.abs(ph[1]) ** 2 / M2,
             'EKE': 0.5 * (self.u ** 2 + self.v ** 2).mean(axis=(-1, -2)),
+            # Model._initialize_core_diagnostics: dissipation by bottom drag, enstrophy budget
+            'EKEdiss': self.Hi[-1] / self.H * self.rek * (self.v[-1] ** 2 + self.u[-1] ** 2).mean(),
+            'ENSflux': -(hr * np.real(np.conj(qh) * self.Jq)).sum(axis=0) / M2,
+            'ENSgenspec': -(hr * np.real(self.ikQy * np.conj(qh) * ph)).sum(axis=0) / M2,
+            'ENSfrictionspec': self.rek * self.del2 * self.wv2 * np.real(np.conj(qh[-1]) * ph[-1]) / M2,
         }
+        # Model.dissipation_spectrum: what the exponential filter removes in the coming _forward_timestep (the diagnostics are
+        # evaluated inside _step_forward after the tendencies of this step are complete)
+        if self.ablevel == 0:
+            dt1, dt2, dt3 = self.dt, 0.0, 0.0
+        elif self.ablevel == 1 or self.useAB2:
+            dt1, dt2, dt3 = 1.5 * self.dt, -0.5 * self.dt, 0.0
+        else:
+            dt1, dt2, dt3 = 23. / 12. * self.dt, -16. / 12. * self.dt, 5. / 12. * self.dt
+        diss = (self.filtr - 1.0) * (qh + dt1 * self.dqhdt + dt2 * self.dqhdt_p + dt3 * self.dqhdt_pp)
+        d['Dissspec'] = -(hr * np.real(np.conj(ph) * diss)).sum(axis=0) / self.dt / M2
+        d['ENSDissspec'] = (hr * np.real(np.conj(qh) * diss)).sum(axis=0) / self.dt / M2
         if self.q_parameterization is not None and getattr(self, 'dqh', None) is not None:
             dqh = self.dqh
-            hr = (self.Hi / self.H)[:, np.newaxis, np.newaxis]
+            d['ENSparamspec'] = np.real((hr * np.conj(qh) * dqh).sum(axis=0)) / M2
             d['paramspec'] = -np.real((hr * np.conj(ph) * dqh).sum(axis=0)) / M2
             dph = np.einsum('ij...,j...->i...', self.a, dqh)          # streamfunction tendency of the parameterization
             d['paramspec_KEflux'] = self.wv2 * (self.del1 * np.real(np.conj(ph[0]) * dph[0])
@@ -395,6 +412,7 @@ class QGModel(object):
         self.Jptpc = -self._advect(self.p[0] - self.p[1], self.del1 * self.u[0] + self.del2 * self.u[1],
                                    self.del1 * self.v[0] + self.del2 * self.v[1])
         self.Jpxi = self._advect(self.xi, self.u, self.v)
+        self.Jq = self._advect(self.q, self.u, self.v)
 
     def _advect(self, q, u=None, v=None):
         if u is None:

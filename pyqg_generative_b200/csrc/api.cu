@@ -52,6 +52,7 @@ struct qgb_handle {
   double *d_ke = nullptr, *d_cfl = nullptr; int* d_flags = nullptr;
   double *d_kespec = nullptr, *d_ensspec = nullptr;
   // spectral energy budget (PROG_BUDGET) and pyqg-style time averages of the spectral diagnostics
+  cplx* bud_tend = nullptr;          // tendency of the current state (PROG_BUDGET scratch)
   double *bud = nullptr, *bud_scr = nullptr, *bud_sum = nullptr;     // per member / scratch / summed over members
   const double* last_dq = nullptr;   // forcing used by the latest step (closure output or external), for the budget terms
   double* avg = nullptr; long long avg_n = 0; bool avg_on = false; double tavestart = 0.0, taveint = 86400.0;
@@ -641,7 +642,7 @@ void qgb_destroy(qgb_handle* h) {
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   cudaFree(h->d_draw);
   cudaFree(h->d_ke); cudaFree(h->d_cfl); cudaFree(h->d_flags); cudaFree(h->d_kespec); cudaFree(h->d_ensspec);
-  cudaFree(h->bud); cudaFree(h->bud_scr); cudaFree(h->bud_sum); cudaFree(h->avg);
+  cudaFree(h->bud); cudaFree(h->bud_tend); cudaFree(h->bud_scr); cudaFree(h->bud_sum); cudaFree(h->avg);
   cudaFree(h->xin); cudaFree(h->z64); cudaFree(h->xi_inj); cudaFree(h->ynet[0]); cudaFree(h->ynet[1]);
   cudaFree(h->yacc); cudaFree(h->dq_ext); cudaFree(h->dq); cudaFree(h->dq_dm); cudaFree(h->act[0]); cudaFree(h->act[1]);
   free_net(h->nets[0]); free_net(h->nets[1]);
@@ -714,10 +715,17 @@ int budget_sums(qgb_handle* h, const double* dq, double* out, int accumulate, cu
   if (!h->bud) {
     CUDA_TRY(h, dalloc(&h->bud, (size_t)(B * kBudgetTerms * NN)));
     CUDA_TRY(h, dalloc(&h->bud_scr, (size_t)(B * 3 * h->ht.N * h->ht.N)));
+    CUDA_TRY(h, dalloc(&h->bud_tend, (size_t)(B * 2 * NN)));
   }
   StepIO io = base_io(h);
-  io.bud_out = h->bud; io.bud_scr = h->bud_scr;
+  io.bud_out = h->bud; io.bud_scr = h->bud_scr; io.bud_tend = h->bud_tend;
   io.dq = dq;
+  // the filter-dissipation spectra see the update the NEXT call of _forward_timestep performs: its Adams-Bashforth level and the
+  // tendency history as it stands (pyqg evaluates the diagnostics inside _step_forward, before _forward_timestep)
+  io.d_p = h->hist[(h->tc + 2) % 3]; io.d_pp = h->hist[(h->tc + 1) % 3];
+  ab_coefficients(h->ablevel, h->cfg.dt, io.dt1, io.dt2, io.dt3);
+  io.bud_inv_dt = 1.0 / h->cfg.dt;
+  io.bud_demean = (dq != nullptr && dq == h->dq) ? 1 : 0;
   int rc = launch_program(h, io, PROG_BUDGET, st);
   if (rc) return rc;
   const long long n = kBudgetTerms * NN;

@@ -89,12 +89,18 @@ struct StepIO {
   double* bud_scr;
   double bud_F;         // rd^-2 del1 del2
   double bud_U;         // U1 - U2
+  cplx* bud_tend;       // (B, 2, N, NK): tendency of the current state without the forcing (for the filter-dissipation spectra)
+  double bud_inv_dt;    // 1 / dt
+  int bud_demean;       // the forcing io.dq is a closure output: its mean is removed before it is used (models/parameterization.py:25)
 };
 
 // PROG_BUDGET terms (pyqg QGModel._initialize_model_diagnostics / Model._initialize_diagnostics; all / M^2)
 enum BudgetTerm { BUD_KEFLUX = 0, BUD_APEFLUX = 1, BUD_APEGEN = 2, BUD_KEFRIC = 3, BUD_ENTSPEC = 4, BUD_PARAM_KE = 5,
-                  BUD_PARAM_APE = 6 };
-constexpr int kBudgetTerms = 7;
+                  BUD_PARAM_APE = 6,
+                  // enstrophy budget and filter dissipation (Model._initialize_core_diagnostics: ENSflux, ENSgenspec,
+                  // ENSfrictionspec, Dissspec, ENSDissspec, ENSparamspec; consumers tools/comparison_tools.py:222-225)
+                  BUD_ENSFLUX = 7, BUD_ENSGEN = 8, BUD_ENSFRIC = 9, BUD_DISS = 10, BUD_ENSDISS = 11, BUD_ENSPARAM = 12 };
+constexpr int kBudgetTerms = 13;
 
 // Per-CTA context: shared-memory views + which member this CTA owns.  CN > 0 fixes the grid size at compile time
 // (the specialised step kernels of spectral.cuh: all index divisions become shifts / multiplies); CN = 0 reads it from T.
@@ -684,6 +690,89 @@ QGB_HD void ph_bud_apeflux(const C& c, int tid, int nt) {
     out[BUD_ENTSPEC * NN + i] = m2 * (e.x * e.x + e.y * e.y);
     out[BUD_PARAM_KE * NN + i] = 0.0;
     out[BUD_PARAM_APE * NN + i] = 0.0;
+    // ENSgenspec = -sum_z del_z Re(ikQy_z conj(qh_z) ph_z) / M^2 ;  ENSfrictionspec = rek del2 wv2 Re(conj(qh_1) ph_1) / M^2
+    const double kk = c.T.kv[k];
+    out[BUD_ENSGEN * NN + i] = m2 * kk * (d1 * c.T.Qy[0] * (q0.x * p0.y - q0.y * p0.x) + d2 * c.T.Qy[1] * (q1.x * p1.y - q1.y * p1.x));
+    out[BUD_ENSFRIC * NN + i] = c.T.rek * d2 * wv2 * m2 * (q1.x * p1.x + q1.y * p1.y);
+    out[BUD_ENSPARAM * NN + i] = 0.0;
+  }
+}
+// buf = u q + i v q with the ANOMALY velocities (pyqg _calc_derived_fields: Jq = _advect(q, u, v))
+template <class C>
+QGB_HD void ph_products_anom(const C& c, int z, int tid, int nt) {
+  const int N = c.N(), P = c.P();
+  const double* q = c.io.q + ((long long)c.member * 2 + z) * N * N;
+  const double s = c.T.inv_M;
+  for (int i = tid; i < N * N; i += nt) {
+    const int y = i / N, x = i - y * N;
+    const cplx w = c.buf[y * P + x];
+    const double qq = q[i] * s;
+    c.buf[y * P + x] = cmake(w.x * qq, w.y * qq);
+  }
+}
+// ENSflux (+)= -del_z Re(conj(qh_z) Jq_z) / M^2 with Jq_z = ik F(u q) + il F(v q); the tendency of the current state follows from
+// the same Jacobian: dqhdt_z = -(Jq_z + ik U_z qh_z + ikQy_z ph_z) (+ rek wv2 ph_1), kept for the dissipation spectra
+template <class C>
+QGB_HD void ph_bud_ens(const C& c, int z, int tid, int nt) {
+  const int N = c.N(), NK = c.NK(), NN = N * NK;
+  const cplx* qh = member_qh(c);
+  double* out = c.io.bud_out + ((long long)c.member * kBudgetTerms + BUD_ENSFLUX) * NN;
+  cplx* tend = c.io.bud_tend + ((long long)c.member * 2 + z) * NN;
+  const double s = c.T.inv_M * c.T.inv_M * c.io.Hi_over_H[z];
+  for (int i = tid; i < NN; i += nt) {
+    const int l = i / NK, k = i - l * NK;
+    cplx a, b;
+    unpack_pair(c, l, k, a, b);
+    const double kv = c.T.kv[k], lv = c.T.lv[l];
+    const cplx J = cadd(cmuli(a, kv), cmuli(b, lv));
+    const cplx q = qh[z * NN + i], ph = half_ph(c, qh, z, i);
+    const double v = -s * (q.x * J.x + q.y * J.y);
+    out[i] = z == 0 ? v : out[i] + v;
+    const cplx t1 = cmuli(q, kv * c.T.Ubg[z]), t3 = cmuli(ph, kv * c.T.Qy[z]);
+    cplx r = cmake(-(J.x + t1.x + t3.x), -(J.y + t1.y + t3.y));
+    if (z == 1 && c.T.rek != 0.0) {
+      const double f = c.T.rek * (kv * kv + lv * lv);
+      r.x += f * ph.x;
+      r.y += f * ph.y;
+    }
+    tend[i] = r;
+  }
+}
+// Dissspec = -sum_z del_z Re(conj(ph_z) D_z) / (dt M^2), ENSDissspec = sum_z del_z Re(conj(qh_z) D_z) / (dt M^2) with
+// D_z = (filtr - 1) (qh_z + dt1 dqhdt_z + dt2 dqhdt_p_z + dt3 dqhdt_pp_z)  (pyqg Model: dissipation_spectrum), and
+// ENSparamspec = sum_z del_z Re(conj(qh_z) dqh_z) / M^2.  With a forcing the buffer holds its packed forward transform.
+template <class C>
+QGB_HD void ph_bud_diss(const C& c, bool has_dq, int tid, int nt) {
+  const int N = c.N(), NK = c.NK(), NN = N * NK;
+  const long long mo = (long long)c.member * 2 * NN;
+  const cplx* qh = member_qh(c);
+  const cplx* tend = c.io.bud_tend + mo;
+  const cplx* dp = c.io.d_p + mo;
+  const cplx* dpp = c.io.d_pp + mo;
+  double* out = c.io.bud_out + (long long)c.member * kBudgetTerms * NN;
+  const double m2 = c.T.inv_M * c.T.inv_M, dt1 = c.io.dt1, dt2 = c.io.dt2, dt3 = c.io.dt3;
+  const double inv_dt = c.io.bud_inv_dt;
+  for (int i = tid; i < NN; i += nt) {
+    cplx f[2] = {cmake(0, 0), cmake(0, 0)};
+    if (has_dq && !(c.io.bud_demean && i == 0)) {
+      const int l = i / NK, k = i - l * NK;
+      unpack_pair(c, l, k, f[0], f[1]);
+    }
+    const double fm = c.T.filtr[i] - 1.0;
+    double diss = 0.0, ensdiss = 0.0, ensparam = 0.0;
+    for (int z = 0; z < 2; ++z) {
+      const int j = z * NN + i;
+      const cplx q = qh[j], ph = half_ph(c, qh, z, i);
+      const cplx dd = cadd(tend[j], f[z]), a = dp[j], b = dpp[j];
+      const cplx D = cmake(fm * (q.x + dt1 * dd.x + dt2 * a.x + dt3 * b.x), fm * (q.y + dt1 * dd.y + dt2 * a.y + dt3 * b.y));
+      const double w = c.io.Hi_over_H[z];
+      diss -= w * (ph.x * D.x + ph.y * D.y);
+      ensdiss += w * (q.x * D.x + q.y * D.y);
+      ensparam += w * (q.x * f[z].x + q.y * f[z].y);
+    }
+    out[BUD_DISS * NN + i] = diss * inv_dt * m2;
+    out[BUD_ENSDISS * NN + i] = ensdiss * inv_dt * m2;
+    out[BUD_ENSPARAM * NN + i] = ensparam * m2;
   }
 }
 // parameterization terms from dqh = rfft2(dq) (the buffer holds the packed forward transform of the forcing pair)
@@ -929,11 +1018,19 @@ QGB_HD int run_program(const C& c, int prog, int phase, int tid, int nt) {
     QGB_RUN(ph_products_scr(c, 2, tid, nt));
     QGB_FFT(false);
     QGB_RUN(ph_bud_apeflux(c, tid, nt));
+    for (int z = 0; z < 2; ++z) {
+      QGB_RUN(ph_build_uv(c, z, tid, nt));
+      QGB_FFT(true);
+      QGB_RUN(ph_products_anom(c, z, tid, nt));
+      QGB_FFT(false);
+      QGB_RUN(ph_bud_ens(c, z, tid, nt));
+    }
     if (c.io.dq) {
       QGB_RUN(ph_load_pair(c, c.io.dq, tid, nt));
       QGB_FFT(false);
       QGB_RUN(ph_bud_param(c, tid, nt));
     }
+    QGB_RUN(ph_bud_diss(c, c.io.dq != nullptr, tid, nt));
   }
   return _n;
 }

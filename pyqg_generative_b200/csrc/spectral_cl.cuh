@@ -43,7 +43,8 @@ struct Cfg {
   static constexpr int PT = N + 1;              // row pitch of T' (RPC rows): A columns 0..N/2-1, B columns N/2..N-1; odd
   static constexpr int kBuf = (N * PS > RPC * PT) ? N * PS : RPC * PT;
   static constexpr size_t kSmemBytes = (size_t)(kBuf + N) * sizeof(cplx);
-  static_assert(kThreads == 512 && (G == 8 || G == 16) && 16 * G == N, "unsupported geometry");
+  static constexpr int kCtasPerSm = kThreads <= 256 ? 2 : 1;   // 128 registers per thread: 512 threads per SM either way
+  static_assert((kThreads == 512 || kThreads == 256) && (G == 8 || G == 16) && 16 * G == N, "unsupported geometry");
 };
 
 #define SCL_INL __device__ __forceinline__
@@ -391,7 +392,7 @@ SCL_INL void round(bool has_inv, int phys, bool has_fwd, const Tables& T, const 
 
 // prog: PROG_STEP, PROG_STEP_DQ, PROG_STEP_DQ_RAW, PROG_SET_Q, PROG_C2R.  One cluster of CL CTAs per member.
 template <int N_, int G_, int CL_>
-__global__ void __launch_bounds__(512, 1) qg_step_cl_kernel(const __grid_constant__ Tables T, const __grid_constant__ StepIO io,
+__global__ void __launch_bounds__((Cfg<N_, G_, CL_>::kThreads), (Cfg<N_, G_, CL_>::kCtasPerSm)) qg_step_cl_kernel(const __grid_constant__ Tables T, const __grid_constant__ StepIO io,
                                                             int prog, int members) {
   using C = Cfg<N_, G_, CL_>;
   extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -4,6 +4,8 @@
 
 #include "spectral_host.hpp"
 
+#include <cstdlib>
+
 namespace qgb {
 
 namespace {
@@ -13,6 +15,10 @@ cudaError_t launch_cl(const Tables& T, const StepIO& io, int prog, int members, 
   auto kern = scl::qg_step_cl_kernel<N, G, CL>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBytes);   // per device: set every time (cheap)
   if (e != cudaSuccess) return e;
+  if (CL > 8) {   // 16 CTAs per cluster is the opt-in (non-portable) size
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return e;
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(members * CL);
   cfg.blockDim = dim3(C::kThreads);
@@ -35,8 +41,12 @@ bool spectralcl_handles(int N, int prog) {
 }
 
 cudaError_t spectralcl_launch(const Tables& T, const StepIO& io, int prog, int members, cudaStream_t st) {
-  if (T.N == 128) return launch_cl<128, 8, 2>(T, io, prog, members, st);
-  return launch_cl<256, 16, 8>(T, io, prog, members, st);
+  // CTAs per member.  256^2: 16 CTAs of 256 threads, two per SM (normally of two different members, whose cluster barriers and
+  // DRAM waits overlap): +9 % over 8 CTAs of 512 threads on the same box (95.3 k vs 87.6 k member-steps/s, 64 members).  128^2: 2 CTAs
+  // of 512 threads (4 x 256 measured 5 % slower at 64 members, equal at 256).  QGB_SCL_ALT=1 selects the other geometry of each.
+  static const bool alt = getenv("QGB_SCL_ALT") != nullptr;
+  if (T.N == 128) return alt ? launch_cl<128, 8, 4>(T, io, prog, members, st) : launch_cl<128, 8, 2>(T, io, prog, members, st);
+  return alt ? launch_cl<256, 16, 8>(T, io, prog, members, st) : launch_cl<256, 16, 16>(T, io, prog, members, st);
 }
 
 }  // namespace qgb

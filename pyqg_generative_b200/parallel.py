@@ -121,6 +121,7 @@ def ensemble_diagnostics_device(model, reset=False):
     for i, name in enumerate(model.DIAG_BUDGET):
         out[name] = a[4 + i].copy()
     out['paramspec'] = out['paramspec_KEflux'] + out['paramspec_APEflux']
+    out.update(model.derived_scalars(out['KEspec']))
     return out, int(red[-1])
 
 

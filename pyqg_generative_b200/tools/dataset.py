@@ -10,7 +10,8 @@ Layout of one file (= one run, like the reference) :
   coords     time [days, attrs units='days'], lev [1, 2], x, y [m], l, k [rad/m]
   float32    q, u, v, psi (time, lev, y, x) [+ q_forcing_advection in forcing datasets];  Ubg, Qy (lev)
   float32    time-averaged spectral diagnostics of the LAST snapshot: KEspec, Ensspec (lev, l, k); KEflux, APEflux,
-             APEgenspec, KEfrictionspec, entspec, paramspec, paramspec_KEflux, paramspec_APEflux (l, k)
+             APEgenspec, KEfrictionspec, entspec, paramspec, paramspec_KEflux, paramspec_APEflux, ENSflux, ENSgenspec,
+             ENSfrictionspec, Dissspec, ENSDissspec, ENSparamspec (l, k); EKE (lev), EKEdiss ()
   attrs      pyqg_params (str of the dict, :144), pyqg:<name> physical parameters like pyqg's to_dataset
 ``write_netcdf`` keeps a leading ``run`` dimension instead (one file for the whole local ensemble).
 """
@@ -22,7 +23,7 @@ PHYSICAL = ('q', 'u', 'v', 'psi')
 FORCING = ('q_forcing_advection',)      # forcing datasets (generate_subgrid_forcing, tools/simulate.py:62-106) carry S next to q, u, v, psi
 LAYERED_SPECTRA = ('KEspec', 'Ensspec')
 PLANE_SPECTRA = ('KEflux', 'APEflux', 'APEgenspec', 'KEfrictionspec', 'entspec', 'paramspec', 'paramspec_KEflux',
-                 'paramspec_APEflux')
+                 'paramspec_APEflux', 'ENSflux', 'ENSgenspec', 'ENSfrictionspec', 'Dissspec', 'ENSDissspec', 'ENSparamspec')
 _ATTR_KEYS = ('nx', 'ny', 'L', 'W', 'dt', 'rek', 'filterfac', 'beta', 'rd', 'delta', 'H1', 'U1', 'U2', 'tavestart', 'taveint')
 
 
@@ -79,6 +80,10 @@ def _write(path, ds, run_index=None):
         for name in PLANE_SPECTRA:
             if name in ds:
                 _nc_var(f, name, np.asarray(ds[name], dtype=np.float32), ('l', 'k'))
+        if 'EKE' in ds:            # pyqg's scalar diagnostics (time averages like the spectra)
+            _nc_var(f, 'EKE', np.asarray(ds['EKE'], dtype=np.float32), ('lev',))
+        if 'EKEdiss' in ds:
+            _nc_var(f, 'EKEdiss', np.asarray(ds['EKEdiss'], dtype=np.float32).reshape(()), ())
         for k, v in ds.get('attrs', {}).items():
             setattr(f, k, v if isinstance(v, (int, float)) else str(v))
 

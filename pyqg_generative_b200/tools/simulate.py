@@ -53,7 +53,8 @@ def snapshot(m):
 
 
 SPECTRAL_VARS = ('KEspec', 'Ensspec', 'KEflux', 'APEflux', 'APEgenspec', 'KEfrictionspec', 'entspec', 'paramspec',
-                 'paramspec_KEflux', 'paramspec_APEflux')
+                 'paramspec_KEflux', 'paramspec_APEflux', 'ENSflux', 'ENSgenspec', 'ENSfrictionspec', 'Dissspec', 'ENSDissspec',
+                 'ENSparamspec')
 
 
 def concat_in_time(snaps):

@@ -418,7 +418,8 @@ class EnsembleQGModel(object):
 
     # ---- pyqg time-averaged diagnostics (Model tavestart / taveint; sampled on the device before each eligible step) ----
     DIAG_LAYERED = ('KEspec', 'Ensspec')
-    DIAG_BUDGET = ('KEflux', 'APEflux', 'APEgenspec', 'KEfrictionspec', 'entspec', 'paramspec_KEflux', 'paramspec_APEflux')
+    DIAG_BUDGET = ('KEflux', 'APEflux', 'APEgenspec', 'KEfrictionspec', 'entspec', 'paramspec_KEflux', 'paramspec_APEflux',
+                   'ENSflux', 'ENSgenspec', 'ENSfrictionspec', 'Dissspec', 'ENSDissspec', 'ENSparamspec')
 
     def _split_terms(self, a, first):
         a = a.reshape((-1, self.nl, self.nk))
@@ -426,8 +427,9 @@ class EnsembleQGModel(object):
 
     def budget_sums(self):
         """Spectral energy budget of the CURRENT state summed over the local members: dict name -> (nl, nk)
-        (pyqg diagnostics KEflux, APEflux, APEgenspec, KEfrictionspec, entspec, paramspec_KEflux, paramspec_APEflux;
-        consumers: tools/comparison_tools.py:91,164-189,222-263)."""
+        (pyqg diagnostics KEflux, APEflux, APEgenspec, KEfrictionspec, entspec, paramspec_KEflux, paramspec_APEflux, ENSflux,
+        ENSgenspec, ENSfrictionspec, Dissspec, ENSDissspec, ENSparamspec; consumers: tools/comparison_tools.py:91,164-189,
+        222-263)."""
         out = np.empty(len(self.DIAG_BUDGET) * self.nl * self.nk)
         _lib.check(self._lib.qgb_diag_budget(self._h, out.ctypes.data, 0, self._stream()), self._h)
         return self._split_terms(out, 0)
@@ -452,7 +454,17 @@ class EnsembleQGModel(object):
             return {}
         out = {k: v / count for k, v in d.items()}
         out['paramspec'] = out['paramspec_KEflux'] + out['paramspec_APEflux']
+        out.update(self.derived_scalars(out['KEspec']))
         return out
+
+    def derived_scalars(self, kespec):
+        """pyqg's scalar diagnostics that are linear in KEspec: ``EKE`` = 0.5 (u^2 + v^2).mean() per layer (Parseval: the
+        half-plane sum of KEspec with the k = 0 and Nyquist columns counted once, ``Model.spec_var``) and ``EKEdiss`` =
+        Hi[-1]/H rek (u_2^2 + v_2^2).mean().  Linear, so the averaged KEspec gives the averaged scalars."""
+        w = np.full(self.nk, 2.0)
+        w[0] = w[-1] = 1.0
+        eke = 0.5 * (np.asarray(kespec) * w).sum(axis=(-1, -2))
+        return {'EKE': eke, 'EKEdiss': self.Hi[-1] / self.H * self.rek * 2.0 * eke[-1]}
 
     def spectra_sums(self):
         """(KEspec_sum, Ensspec_sum, count): sums over local members and averaging times, shape (2,nl,nk);

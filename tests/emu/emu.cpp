@@ -11,7 +11,7 @@ using namespace qgb;
 extern "C" int qgbemu_run(const qgb_config* cfg, int prog, int nthreads, double* qh, double* q, double* d_cur,
                           const double* d_p, const double* d_pp, const double* dq, float* cnn_x, float xstd0,
                           float xstd1, int ablevel, double* ph_out, double* u_out, double* v_out, double* p_out,
-                          double* red_out, double* bud_out, double* bud_scr) {
+                          double* red_out, double* bud_out, double* bud_scr, int bud_demean) {
   HostTables h;
   if (!build_host_tables(*cfg, h)) return -1;
   Tables T;
@@ -25,6 +25,8 @@ extern "C" int qgbemu_run(const qgb_config* cfg, int prog, int nthreads, double*
   io.ph_out = (cplx*)ph_out; io.u_out = u_out; io.v_out = v_out; io.p_out = p_out; io.red_out = red_out;
   io.Hi_over_H[0] = h.Hi_over_H[0]; io.Hi_over_H[1] = h.Hi_over_H[1];
   io.bud_out = bud_out; io.bud_scr = bud_scr;
+  std::vector<cplx> bud_tend(bud_out ? (size_t)cfg->members * 2 * h.N * h.NK : 0);
+  io.bud_tend = bud_tend.data(); io.bud_inv_dt = 1.0 / cfg->dt; io.bud_demean = bud_demean;
   io.bud_F = h.Hi_over_H[0] * h.Hi_over_H[1] / (cfg->rd * cfg->rd); io.bud_U = cfg->U1 - cfg->U2;
   std::vector<cplx> buf((size_t)h.N * h.P), tw(h.N);
   std::vector<short> pos(h.N);

@@ -20,11 +20,11 @@ def _p(a):
 
 
 def run(lib, cfg, prog, qh, q, dcur=None, dp=None, dpp=None, dq=None, x=None, ab=2, ph=None, u=None, v=None, p=None,
-        red=None, nt=96, bud=None, scr=None):
+        red=None, nt=96, bud=None, scr=None, demean=1):
     lib.qgbemu_run.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 7 + \
-        [ctypes.c_float, ctypes.c_float, ctypes.c_int] + [ctypes.c_void_p] * 7
+        [ctypes.c_float, ctypes.c_float, ctypes.c_int] + [ctypes.c_void_p] * 7 + [ctypes.c_int]
     assert lib.qgbemu_run(ctypes.byref(cfg), prog, nt, _p(qh), _p(q), _p(dcur), _p(dp), _p(dpp), _p(dq), _p(x),
-                          7.78e-6, 1.05e-6, ab, _p(ph), _p(u), _p(v), _p(p), _p(red), _p(bud), _p(scr)) == 0
+                          7.78e-6, 1.05e-6, ab, _p(ph), _p(u), _p(v), _p(p), _p(red), _p(bud), _p(scr), demean) == 0
 
 
 def rel(a, b):
@@ -99,7 +99,8 @@ def test_raw_forcing_program_keeps_the_mean(emu_lib):
     assert abs(q[0, 0].mean() - m.q[0].mean()) < 1e-20
 
 
-BUDGET_TERMS = ['KEflux', 'APEflux', 'APEgenspec', 'KEfrictionspec', 'entspec', 'paramspec_KEflux', 'paramspec_APEflux']
+BUDGET_TERMS = ['KEflux', 'APEflux', 'APEgenspec', 'KEfrictionspec', 'entspec', 'paramspec_KEflux', 'paramspec_APEflux',
+                'ENSflux', 'ENSgenspec', 'ENSfrictionspec', 'Dissspec', 'ENSDissspec', 'ENSparamspec']
 
 
 @pytest.mark.parametrize('N,jet', [(64, False), (48, True), (32, False)])
@@ -122,9 +123,15 @@ def test_budget_program_matches_oracle(emu_lib, N, jet):
     run(emu_lib, cfg, 2, qh, q)
     bud = np.zeros((B, len(BUDGET_TERMS), N, N // 2 + 1))
     scr = np.zeros((B, 3, N, N))
-    run(emu_lib, cfg, 9, qh, q, dq=dq.copy(), bud=bud, scr=scr)               # PROG_BUDGET
+    # tendency history of an AB3 step (the filter-dissipation spectra describe the coming _forward_timestep)
+    dp = (rng.randn(B, 2, N, N // 2 + 1) + 1j * rng.randn(B, 2, N, N // 2 + 1)) * 3e-10
+    dpp = (rng.randn(B, 2, N, N // 2 + 1) + 1j * rng.randn(B, 2, N, N // 2 + 1)) * 3e-10
+    run(emu_lib, cfg, 9, qh, q, dp=dp, dpp=dpp, dq=dq.copy(), bud=bud, scr=scr, ab=2)   # PROG_BUDGET
     m.q = q0[1]
+    m.dqhdt_p, m.dqhdt_pp, m.ablevel = dp[1].copy(), dpp[1].copy(), 2
     m._invert()
+    m._do_advection()
+    m._do_friction()
     m._do_q_subgrid_parameterization()
     d = m.diagnostic_fields()
     for i, name in enumerate(BUDGET_TERMS):

@@ -186,7 +186,8 @@ def test_host_buffer_stepping_sync_and_pipelined():
     assert np.array_equal(got, ref.q)
 
 
-BUDGET = ('KEflux', 'APEflux', 'APEgenspec', 'KEfrictionspec', 'entspec', 'paramspec_KEflux', 'paramspec_APEflux')
+BUDGET = ('KEflux', 'APEflux', 'APEgenspec', 'KEfrictionspec', 'entspec', 'paramspec_KEflux', 'paramspec_APEflux',
+          'ENSflux', 'ENSgenspec', 'ENSfrictionspec', 'Dissspec', 'ENSDissspec', 'ENSparamspec')
 
 
 @pytest.mark.parametrize('N,dt,phys', [(64, 14400., {}), (48, 7200., dict(rek=7e-8, delta=0.1, beta=1e-11)), (128, 7200., {})])
@@ -203,12 +204,16 @@ def test_spectral_energy_budget_matches_oracle(N, dt, phys):
     m.set_parameterization(_OracleConst(dq), 'AR1', 1)      # host callback -> qgb_set_forcing -> PROG_STEP_DQ_RAW
     m._step_forward()
     terms = m.budget_sums()
-    q1 = m.q
     ref = {k: 0 for k in BUDGET + ('paramspec',)}
     for b in range(B):
+        # the oracle takes the same step (the dissipation spectra need its tendency history and Adams-Bashforth level), then
+        # evaluates the diagnostics where pyqg does: after the tendencies of the NEXT step are complete
         o = pyqg_shim.QGModel(nx=N, dt=dt, log_level=0, q_parameterization=_OracleConst(dq), **phys)
-        o.q = q1[b]
+        o.q = q0[b]
+        o._step_forward()
         o._invert()
+        o._do_advection()
+        o._do_friction()
         o._do_q_subgrid_parameterization()
         d = o.diagnostic_fields()
         for k in ref:
@@ -236,7 +241,8 @@ def test_time_averaged_diagnostics_follow_pyqg_sampling():
             o._step_forward()
         refs.append(o)
     assert m.diag_count == refs[0].diag_count == 4           # sampled before the steps starting at tc = 2, 4, 6, 8
-    for k in ('KEspec', 'Ensspec', 'KEflux', 'APEflux', 'APEgenspec', 'KEfrictionspec', 'entspec'):
+    for k in ('KEspec', 'Ensspec', 'KEflux', 'APEflux', 'APEgenspec', 'KEfrictionspec', 'entspec', 'ENSflux', 'ENSgenspec',
+              'ENSfrictionspec', 'Dissspec', 'ENSDissspec', 'EKE', 'EKEdiss'):
         ref = sum(o.diag[k] for o in refs) / B
         assert rel(avg[k], ref) < 1e-9, k
-    assert np.abs(avg['paramspec']).max() == 0.0
+    assert np.abs(avg['paramspec']).max() == 0.0 and np.abs(avg['ENSparamspec']).max() == 0.0

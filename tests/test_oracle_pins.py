@@ -179,3 +179,90 @@ def test_spectral_energy_budget_closes():
     # each term matters for the closure of the budget (guards against a silently dropped term)
     for k in ('KEflux', 'APEflux', 'APEgenspec', 'KEfrictionspec', 'paramspec'):
         assert np.abs(lhs - (rhs - d[k])).max() > 1e-3 * np.abs(rhs).max(), k
+
+
+def _filtered_band_model(kmax, param=None, dt=10., seed=5, nx=64):
+    """White noise truncated at |kappa| <= kmax (in units of 2 pi / L): kmax > 0.65 pi / dx puts content under the filter."""
+    rng = np.random.RandomState(seed)
+    m = pyqg_shim.QGModel(nx=nx, dt=dt, log_level=0, tavestart=1e20, q_parameterization=param)
+    qh = m.fft(rng.randn(2, nx, nx) * np.array([7e-6, 1e-6])[:, None, None])
+    qh[:, np.sqrt(m.wv2) / (2 * np.pi / m.L) > kmax] = 0
+    m.q = m.ifft(qh)
+    return m
+
+
+def _forcing_param(seed=3):
+    rng = np.random.RandomState(seed)
+    dq = rng.randn(2, 64, 64) * np.array([1e-12, 2e-13])[:, None, None]
+    dq -= dq.mean(axis=(1, 2), keepdims=True)
+
+    class Par(pyqg_shim.QParameterization):
+        def __call__(self, mm):
+            return dq
+    return Par()
+
+
+def test_modal_enstrophy_budget_closes_exactly():
+    """Enstrophy Z(k) = sum_z del_z |qh_z|^2 / (2 M^2) is quadratic, so Z(q + d) - Z(q) - Z(d) is the projection of the
+    increment d on the state: it must equal dt (ENSflux + ENSgenspec + ENSfrictionspec + ENSparamspec + ENSDissspec) to rounding,
+    with every term necessary -- signs, layer weights and the 1/dt of the dissipation spectrum included.  The state has content
+    under the exponential filter and aliases freely: the identity is algebraic."""
+    m = _filtered_band_model(26., param=_forcing_param())
+    hr = np.array([m.del1, m.del2])[:, None, None]
+    Z = lambda qh: 0.5 * (hr * np.abs(qh) ** 2).sum(axis=0) / m.M ** 2
+    ok = m.filtr > 0.5
+    for step in range(3):                                   # Euler, AB2, AB3 coefficients of the dissipation spectrum
+        m._invert(); m._do_advection(); m._do_friction(); m._do_q_subgrid_parameterization()
+        d = m.diagnostic_fields()
+        qh0, ph0 = m.qh.copy(), m.ph.copy()
+        m._forward_timestep()
+        # what the filter removed, recovered from the new state alone: qh1 = filtr X  =>  D = qh1 - qh1 / filtr
+        D = np.where(ok, m.qh - m.qh / np.where(ok, m.filtr, 1.0), 0.0)
+        ens_d = (hr * np.real(np.conj(qh0) * D)).sum(axis=0) / m.dt / m.M ** 2
+        e_d = -(hr * np.real(np.conj(ph0) * D)).sum(axis=0) / m.dt / m.M ** 2
+        assert np.abs(d['ENSDissspec'] - ens_d)[ok].max() < 1e-9 * np.abs(ens_d).max() > 0, step
+        assert np.abs(d['Dissspec'] - e_d)[ok].max() < 1e-9 * np.abs(e_d).max() > 0, step
+        if step > 0:
+            continue                                        # (a multistep increment mixes tendencies of earlier states)
+        lhs = (Z(m.qh) - Z(qh0) - Z(m.qh - qh0)) / m.dt
+        terms = ('ENSflux', 'ENSgenspec', 'ENSfrictionspec', 'ENSparamspec', 'ENSDissspec')
+        rhs = sum(d[k] for k in terms)
+        scale = np.abs(rhs).max()
+        assert np.abs(lhs - rhs).max() < 1e-9 * scale
+        for k in terms:                                     # every term is needed: dropping it leaves exactly that term
+            resid = np.abs(lhs - (rhs - d[k]))
+            assert np.abs(d[k]).max() > 0 and np.abs(resid - np.abs(d[k])).max() < 1e-9 * scale, k
+        assert (m.filtr < 0.9).any() and np.abs(d['ENSDissspec']).max() > 0.1 * scale     # the filter really acted
+
+
+def test_energy_budget_with_filter_dissipation():
+    """Same construction for the modal energy: with alias-free quadratic terms (|kappa| <= nx / 3, which still reaches under the
+    filter edge 0.65 pi / dx) the first-order change equals KEflux + APEflux + APEgenspec + KEfrictionspec + paramspec +
+    Dissspec, and Dissspec carries the budget where the filter acts."""
+    m = _filtered_band_model(64 / 3., param=_forcing_param())
+    d1, d2, F = m.del1, m.del2, m.rd ** -2 * m.del1 * m.del2
+
+    def energy(qh):
+        ph = np.einsum('ij...,j...->i...', m.a, qh)
+        return 0.5 * (d1 * m.wv2 * np.abs(ph[0]) ** 2 + d2 * m.wv2 * np.abs(ph[1]) ** 2 + F * np.abs(ph[0] - ph[1]) ** 2) / m.M ** 2
+    m._invert(); m._do_advection(); m._do_friction(); m._do_q_subgrid_parameterization()
+    d = m.diagnostic_fields()
+    qh0 = m.qh.copy()
+    m._forward_timestep()
+    lhs = (energy(m.qh) - energy(qh0) - energy(m.qh - qh0)) / m.dt
+    rhs = d['KEflux'] + d['APEflux'] + d['APEgenspec'] + d['KEfrictionspec'] + d['paramspec'] + d['Dissspec']
+    assert np.abs(lhs - rhs).max() < 2e-4 * np.abs(rhs).max()
+    ring = (m.filtr < 1.0) & (np.abs(qh0[0]) > 0)
+    assert ring.any()
+    assert np.abs(lhs - (rhs - d['Dissspec']))[ring].max() > 0.5 * np.abs(d['Dissspec'])[ring].max() > 0
+    assert np.abs(lhs - rhs)[ring].max() < 1e-3 * np.abs(d['Dissspec'])[ring].max()
+
+
+def test_eke_scalars_follow_from_kespec():
+    """EKE = 0.5 (u^2 + v^2).mean() per layer and EKEdiss = del2 rek (u_2^2 + v_2^2).mean() are the half-plane sums of KEspec
+    (Parseval): the engine derives them from the (averaged) KEspec instead of carrying two more accumulators."""
+    m = _band_limited_model()
+    d = m.diagnostic_fields()
+    eke = 0.5 * np.array([_full_plane_sum(d['KEspec'][z]) for z in range(2)])
+    assert np.abs(eke - d['EKE']).max() < 1e-12 * d['EKE'].max()
+    assert abs(m.del2 * m.rek * 2 * eke[1] - d['EKEdiss']) < 1e-12 * d['EKEdiss']
