@@ -212,6 +212,41 @@ int qgb_profile_all_end(qgb_handle* h, double* ms, int64_t* launches, int64_t* u
 int64_t qgb_launch_count(void);
 const char* qgb_version(void);
 
+/* ---- training: the AndrewCNN regression trainer on the device ---------------------------------------
+ * Reference: tools/cnn_tools.py:645-700 ``train(net, X_train, Y_train, X_test, Y_test, num_epochs, batch_size, learning_rate)``
+ * -- Adam (torch defaults), ``net.compute_loss`` = MSELoss (:177-182), BatchNorm2d in training mode -- as used by
+ * models/mean_var_model.py:41-66 (GZ two-stage fit: AndrewCNN for the mean, VarCNN = softplus(AndrewCNN) on the squared
+ * residuals) and models/ols_model.py ``fit``.  A trainer owns parameters, Adam moments, BatchNorm running statistics and
+ * activations for minibatches of up to max_batch images of ny x nx; fp32 arithmetic like the reference.
+ * Network: nlayers convolutions (circular 'same', bias), channels[0..nlayers], kernel sizes ksizes[0..nlayers-1] in {1,3,5};
+ * ReLU + BatchNorm2d after every layer but the last (tools/cnn_tools.py:79-98,125-160); softplus != 0 applies softplus to
+ * the output (VarCNN, mean_var_model.py:14-17).
+ * Flat parameter layout (qgb_train_num_params floats), per layer in order: conv weight (cout,cin,k,k), conv bias (cout),
+ * [BatchNorm weight (cout), BatchNorm bias (cout)] -- the order of ``net.parameters()``.  Flat buffer layout
+ * (qgb_train_num_buffers floats), per BatchNorm layer: running_mean (cout), running_var (cout). */
+typedef struct qgb_trainer qgb_trainer;
+int qgb_train_create(int device, int nlayers, const int32_t* channels, const int32_t* ksizes, int ny, int nx, int max_batch,
+                     int softplus, qgb_trainer** out);
+void qgb_train_destroy(qgb_trainer* t);
+const char* qgb_train_last_error(const qgb_trainer* t); /* t may be NULL: last error of a failed qgb_train_create */
+int64_t qgb_train_num_params(const qgb_trainer* t);
+int64_t qgb_train_num_buffers(const qgb_trainer* t);
+int64_t qgb_train_launch_count(const qgb_trainer* t);   /* kernels launched by this trainer so far */
+/* host pointers (either may be NULL = unchanged); reset_optimizer != 0 clears the Adam moments and step count
+ * (``optim.Adam(net.parameters(), lr)`` is created anew by every ``train`` call, cnn_tools.py:671) */
+int qgb_train_set_params(qgb_trainer* t, const float* params, const float* buffers, int reset_optimizer);
+int qgb_train_get_params(qgb_trainer* t, float* params, float* buffers);
+/* One iteration of the loop at cnn_tools.py:685-690: optimizer.zero_grad(); loss = MSE(net(x), y); loss.backward();
+ * optimizer.step() with learning rate lr.  x: float (batch, channels[0], ny, nx), y: float (batch, channels[nlayers], ny, nx),
+ * host pointers (copied on ``stream``) or device pointers (on_device != 0).  *loss (host, may be NULL) = the minibatch loss. */
+int qgb_train_step(qgb_trainer* t, const float* x, const float* y, int batch, int on_device, double lr, double* loss, void* stream);
+/* Forward (training mode) + backward without the optimizer step: grads (host, flat parameter layout) and the loss -- the hook
+ * the parity tests compare with torch autograd.  update_running == 0 leaves the BatchNorm running statistics untouched. */
+int qgb_train_grads(qgb_trainer* t, const float* x, const float* y, int batch, int on_device, float* grads, double* loss,
+                    int update_running, void* stream);
+/* ``evaluate_test`` (cnn_tools.py:624-643): eval-mode (running statistics) MSE of one minibatch. */
+int qgb_train_eval_loss(qgb_trainer* t, const float* x, const float* y, int batch, int on_device, double* loss, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -72,11 +72,22 @@ def install_stubs():
         sys.modules['pyqg_parameterization_benchmarks.utils'] = utils
 
 
+def _give_specs():
+    """torch's lazy imports probe optional packages with importlib.util.find_spec, which rejects modules without __spec__."""
+    from importlib.machinery import ModuleSpec
+    for name in ('pyqg', 'pyqg.parameterizations', 'xarray', 'gcm_filters', 'pyqg_parameterization_benchmarks',
+                 'pyqg_parameterization_benchmarks.utils'):
+        mod = sys.modules.get(name)
+        if mod is not None and getattr(mod, '__spec__', None) is None:
+            mod.__spec__ = ModuleSpec(name, None)
+
+
 def import_reference():
     """Return the reference's ``pyqg_generative`` package imported unmodified (container only)."""
     if not reference_available():
         raise RuntimeError('reference tree not present at %s' % REFERENCE_ROOT)
     install_stubs()
+    _give_specs()
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
     import pyqg_generative  # noqa: F401

@@ -72,6 +72,19 @@ SYMBOLS = {
     'qgb_profile_all_end': (_i, [_vp, ctypes.POINTER(_d), ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]),
     'qgb_launch_count': (ctypes.c_int64, []),
     'qgb_version': (ctypes.c_char_p, []),
+    # training (tools/cnn_tools.py:645-700)
+    'qgb_train_create': (_i, [_i, _i, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32), _i, _i, _i, _i,
+                              ctypes.POINTER(_vp)]),
+    'qgb_train_destroy': (None, [_vp]),
+    'qgb_train_last_error': (ctypes.c_char_p, [_vp]),
+    'qgb_train_num_params': (ctypes.c_int64, [_vp]),
+    'qgb_train_num_buffers': (ctypes.c_int64, [_vp]),
+    'qgb_train_launch_count': (ctypes.c_int64, [_vp]),
+    'qgb_train_set_params': (_i, [_vp, _vp, _vp, _i]),
+    'qgb_train_get_params': (_i, [_vp, _vp, _vp]),
+    'qgb_train_step': (_i, [_vp, _vp, _vp, _i, _i, _d, ctypes.POINTER(_d), _vp]),
+    'qgb_train_grads': (_i, [_vp, _vp, _vp, _i, _i, _vp, ctypes.POINTER(_d), _i, _vp]),
+    'qgb_train_eval_loss': (_i, [_vp, _vp, _vp, _i, _i, ctypes.POINTER(_d), _vp]),
 }
 
 _lib = None
@@ -102,6 +115,18 @@ def check(rc, handle=None):
     if rc == QGB_OK:
         return
     msg = load().qgb_last_error(handle)
+    msg = msg.decode() if msg else 'error %d' % rc
+    if rc == QGB_EINVAL:
+        raise ValueError(msg)
+    if rc == QGB_EUNSUPPORTED:
+        raise NotImplementedError(msg)
+    raise QgbError(msg)
+
+
+def check_train(rc, trainer=None):
+    if rc == QGB_OK:
+        return
+    msg = load().qgb_train_last_error(trainer)
     msg = msg.decode() if msg else 'error %d' % rc
     if rc == QGB_EINVAL:
         raise ValueError(msg)

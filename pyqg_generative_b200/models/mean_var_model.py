@@ -2,19 +2,23 @@
 
 ``net_mean`` + ``VarCNN`` (softplus head, :14-17); ``generate_latent_noise`` :102-103 (float64, (2,ny,nx));
 ``predict_snapshot = y_std * (mean + noise * sqrt(var))`` :105-109; ``predict_mean_snapshot`` :111-115;
-``predict`` :117-134.  ``fit`` (:41-66) is out of scope.
+``predict`` :117-134; ``fit`` :41-66 (two-stage: the mean network on the forcing, then the softplus network on the squared
+residuals) and ``save_model`` :68-81 on the device-side trainer (tools/cnn_tools.py ``train``).
 """
+import os
 from os.path import exists
 
 import numpy as np
+import torch
 
 from .. import _lib
-from ..tools.cnn_tools import AndrewCNN, apply_function, extract
+from ..tools.cnn_tools import AndrewCNN, apply_function, extract, prepare_PV_data, save_model_args, train, write_log
 from ._cnn_closure import CNNClosure, make_dataset
 
 
 class VarCNN(AndrewCNN):
     """AndrewCNN followed by softplus (positive variance)."""
+    softplus_output = True
 
     def forward(self, x, softplus=True, precision=None):
         return super().forward(x, softplus=True, precision=precision)
@@ -35,6 +39,31 @@ class MeanVarModel(CNNClosure):
 
     def _nets(self):
         return [self.net_mean, self.net_var]
+
+    def fit(self, ds_train, ds_test, num_epochs=50, batch_size=64, learning_rate=0.001):
+        """mean_var_model.py:41-66."""
+        os.makedirs(self.folder, exist_ok=True)
+        X_train, Y_train, X_test, Y_test, self.x_scale, self.y_scale = prepare_PV_data(ds_train, ds_test)
+        if self.load_mean(self.folder):
+            print('Net mean is loaded instead of training')
+        else:
+            train(self.net_mean, X_train, Y_train, X_test, Y_test, num_epochs, batch_size, learning_rate)
+        rsq_train = (Y_train - apply_function(self.net_mean, X_train)) ** 2
+        rsq_test = (Y_test - apply_function(self.net_mean, X_test)) ** 2
+        train(self.net_var, X_train, rsq_train, X_test, rsq_test, num_epochs, batch_size, learning_rate)
+        self.save_model()
+
+    def save_model(self):
+        """mean_var_model.py:68-81."""
+        os.makedirs(self.folder, exist_ok=True)
+        torch.save(self.net_mean.state_dict(), '%s/net_mean.pt' % self.folder)
+        torch.save(self.net_var.state_dict(), '%s/net_var.pt' % self.folder)
+        self.x_scale.write('x_scale.json', folder=self.folder)
+        self.y_scale.write('y_scale.json', folder=self.folder)
+        save_model_args('MeanVarModel', folder=self.folder, hidden_channels=self.hidden_channels)
+        if hasattr(self.net_mean, 'log_dict'):          # nothing to save if the mean network was read from file
+            write_log(self.net_mean.log_dict, '%s/stats_mean.nc' % self.folder)
+        write_log(self.net_var.log_dict, '%s/stats_var.nc' % self.folder)
 
     def load_mean(self, folder):
         if exists('%s/net_mean.pt' % folder):

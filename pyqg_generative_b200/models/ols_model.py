@@ -1,13 +1,16 @@
 """OLSModel closure (deterministic CNN): inference surface of pyqg_generative/models/ols_model.py on libqgb200.
 
-``generate_latent_noise`` returns 0 (:68-69), ``predict_snapshot`` :71-75, ``predict`` :77-97; ``fit`` is out of scope.
+``generate_latent_noise`` returns 0 (:68-69), ``predict_snapshot`` :71-75, ``predict`` :77-97; ``fit`` :36-46 and
+``save_model`` :48-57 on the device-side trainer (tools/cnn_tools.py ``train``).
 """
+import os
 from os.path import exists
 
 import numpy as np
+import torch
 
 from .. import _lib
-from ..tools.cnn_tools import AndrewCNN, apply_function, extract
+from ..tools.cnn_tools import AndrewCNN, apply_function, extract, prepare_PV_data, save_model_args, train, write_log
 from ._cnn_closure import CNNClosure, make_dataset
 
 
@@ -25,6 +28,22 @@ class OLSModel(CNNClosure):
 
     def _nets(self):
         return [self.net]
+
+    def fit(self, ds_train, ds_test, num_epochs=50, batch_size=64, learning_rate=0.001):
+        """ols_model.py:36-46."""
+        X_train, Y_train, X_test, Y_test, self.x_scale, self.y_scale = prepare_PV_data(ds_train, ds_test)
+        train(self.net, X_train, Y_train, X_test, Y_test, num_epochs, batch_size, learning_rate)
+        self.save_model()
+
+    def save_model(self):
+        """ols_model.py:48-57."""
+        os.makedirs(self.folder, exist_ok=True)
+        torch.save(self.net.state_dict(), '%s/net.pt' % self.folder)
+        self.x_scale.write('x_scale.json', folder=self.folder)
+        self.y_scale.write('y_scale.json', folder=self.folder)
+        save_model_args('OLSModel', folder=self.folder, div=self.div, batch_norm=self.batch_norm, bias=self.bias,
+                        final_activation=self.final_activation, hidden_channels=self.hidden_channels)
+        write_log(self.net.log_dict, '%s/stats.nc' % self.folder)
 
     def load_model(self, folder):
         if exists('%s/net.pt' % folder):

@@ -1,12 +1,15 @@
-"""Host-side mirror of the inference half of ``pyqg_generative/tools/cnn_tools.py``.
+"""Host-side mirror of ``pyqg_generative/tools/cnn_tools.py`` for the regression networks.
 
 Same names and argument meaning as the reference (AndrewCNN :125-182, ChannelwiseScaler :502-553,
-minibatch :607-622, apply_function :702-735) but the forward pass runs in libqgb200's sm_100a kernels
-(fp32 FFMA direct convolution or the tcgen05 implicit-GEMM path), not in torch.nn.
-Training utilities (train, DCGAN_discriminator, ...) are out of scope.
+minibatch :607-622, apply_function :702-735, train :645-700, evaluate_test :624-643, prepare_PV_data :402-421) but the
+forward pass runs in libqgb200's sm_100a kernels (fp32 FFMA direct convolution or the tcgen05 implicit-GEMM path) and the
+training step (forward with batch statistics, MSE, backward, Adam) in its device-side trainer (csrc/train.cuh), not in torch.nn.
+The adversarial / variational trainers (DCGAN_discriminator, WGAN-GP, ELBO) are not built.
 """
+import collections
 import ctypes
 import json
+from time import time
 
 import numpy as np
 import torch
@@ -107,6 +110,30 @@ class AndrewCNN(object):
     def train(self, mode=True):
         return self
 
+    softplus_output = False      # VarCNN overrides: softplus on the output, in forward() and in the loss
+
+    def parameter_names(self):
+        """state_dict keys in ``net.parameters()`` order (= the flat parameter layout of qgb_train_*)."""
+        names = []
+        for conv_idx, bn_idx, cin, cout, k in self._blocks:
+            names += ['conv.%d.weight' % conv_idx, 'conv.%d.bias' % conv_idx]
+            if bn_idx is not None:
+                names += ['conv.%d.weight' % bn_idx, 'conv.%d.bias' % bn_idx]
+        return names
+
+    def buffer_names(self):
+        names = []
+        for conv_idx, bn_idx, cin, cout, k in self._blocks:
+            if bn_idx is not None:
+                names += ['conv.%d.running_mean' % bn_idx, 'conv.%d.running_var' % bn_idx]
+        return names
+
+    def compute_loss(self, x, ytrue):
+        """cnn_tools.py:177-182 ``{'loss': MSELoss()(self.forward(x), ytrue)}`` (eval-mode forward, no gradient)."""
+        y = self.forward(x, softplus=self.softplus_output)
+        yt = torch.as_tensor(ytrue).to(y.device, torch.float32)
+        return {'loss': float(((y - yt) ** 2).mean())}
+
     def apply(self, fn):
         return self
 
@@ -196,8 +223,173 @@ class AndrewCNN(object):
 
 
 def weights_init(m):
-    """Reference cnn_tools.py:54-65 re-initialises weights for training; inference-only here: no-op."""
+    """Reference cnn_tools.py:54-65 (DCGAN initialisation, applied by the GAN / VAE constructors): conv weights N(0, 0.02),
+    BatchNorm weights N(1, 0.02) and zero bias.  Accepts our AndrewCNN; other objects are left alone."""
+    if not isinstance(m, AndrewCNN):
+        return None
+    for conv_idx, bn_idx, cin, cout, k in m._blocks:
+        m._sd['conv.%d.weight' % conv_idx] = torch.randn(cout, cin, k, k) * 0.02
+        if bn_idx is not None:
+            m._sd['conv.%d.weight' % bn_idx] = 1.0 + torch.randn(cout) * 0.02
+            m._sd['conv.%d.bias' % bn_idx] = torch.zeros(cout)
+    m._release()
     return None
+
+
+class Trainer(object):
+    """Device-side training state of one AndrewCNN (``qgb_trainer``): parameters, Adam moments, BatchNorm running statistics.
+
+    ``step(x, y, lr)`` is one iteration of the loop at cnn_tools.py:685-690; ``grads`` exposes the raw gradients for the
+    parity tests; ``sync_to(net)`` writes parameters and buffers back into the network's state_dict."""
+
+    def __init__(self, net, ny, nx, max_batch=64, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError('training needs a CUDA device: libqgb200 has no CPU fallback')
+        if not net.batch_norm:
+            raise NotImplementedError('the trainer expects ReLU + BatchNorm2d after every layer but the last')
+        self._lib = _lib.load()
+        self.net = net
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        chans = [net._blocks[0][2]] + [b[3] for b in net._blocks]
+        ks = [b[4] for b in net._blocks]
+        self.ny, self.nx, self.max_batch = int(ny), int(nx), int(max_batch)
+        self._h = ctypes.c_void_p()
+        ca = (ctypes.c_int32 * len(chans))(*chans)
+        ka = (ctypes.c_int32 * len(ks))(*ks)
+        _lib.check_train(self._lib.qgb_train_create(self.device, len(ks), ca, ka, self.ny, self.nx, self.max_batch,
+                                                    1 if net.softplus_output else 0, ctypes.byref(self._h)))
+        self.nparams = int(self._lib.qgb_train_num_params(self._h))
+        self.nbuffers = int(self._lib.qgb_train_num_buffers(self._h))
+        self.steps = 0
+        self.upload(reset_optimizer=True)
+
+    def close(self):
+        if getattr(self, '_h', None):
+            self._lib.qgb_train_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _flat(self, names):
+        sd = self.net._sd
+        return np.ascontiguousarray(np.concatenate([sd[n].numpy().astype('float32').ravel() for n in names])) if names \
+            else np.zeros(0, 'float32')
+
+    def upload(self, reset_optimizer=False):
+        p, b = self._flat(self.net.parameter_names()), self._flat(self.net.buffer_names())
+        assert p.size == self.nparams and b.size == self.nbuffers
+        _lib.check_train(self._lib.qgb_train_set_params(self._h, p.ctypes.data, b.ctypes.data if b.size else None,
+                                                        1 if reset_optimizer else 0), self._h)
+
+    def _unflat(self, flat, names):
+        out, o = {}, 0
+        for n in names:
+            shape = tuple(self.net._sd[n].shape)
+            sz = int(np.prod(shape))
+            out[n] = flat[o:o + sz].reshape(shape).copy()
+            o += sz
+        return out
+
+    def sync_to(self, net=None):
+        """Parameters, running statistics (and num_batches_tracked) -> the network's state_dict."""
+        net = net or self.net
+        p, b = np.empty(self.nparams, 'float32'), np.empty(max(self.nbuffers, 1), 'float32')
+        _lib.check_train(self._lib.qgb_train_get_params(self._h, p.ctypes.data, b.ctypes.data), self._h)
+        for n, a in self._unflat(p, net.parameter_names()).items():
+            net._sd[n] = torch.from_numpy(a)
+        for n, a in self._unflat(b, net.buffer_names()).items():
+            net._sd[n] = torch.from_numpy(a)
+        for conv_idx, bn_idx, cin, cout, k in net._blocks:
+            if bn_idx is not None:
+                key = 'conv.%d.num_batches_tracked' % bn_idx
+                net._sd[key] = torch.tensor(int(net._sd[key]) + self.steps)
+        self.steps = 0
+        net._release()
+
+    def _xy(self, x, y):
+        x = np.ascontiguousarray(np.asarray(x, dtype='float32'))
+        y = np.ascontiguousarray(np.asarray(y, dtype='float32'))
+        if x.ndim != 4 or x.shape[2:] != (self.ny, self.nx) or y.shape[0] != x.shape[0] or y.shape[2:] != x.shape[2:]:
+            raise ValueError('expected (B, C, %d, %d) minibatches, got %s and %s' % (self.ny, self.nx, x.shape, y.shape))
+        return x, y
+
+    def step(self, x, y, lr):
+        x, y = self._xy(x, y)
+        loss = ctypes.c_double(0.0)
+        _lib.check_train(self._lib.qgb_train_step(self._h, x.ctypes.data, y.ctypes.data, x.shape[0], 0, float(lr),
+                                                  ctypes.byref(loss), None), self._h)
+        self.steps += 1
+        return loss.value
+
+    def grads(self, x, y, update_running=False):
+        x, y = self._xy(x, y)
+        g = np.empty(self.nparams, 'float32')
+        loss = ctypes.c_double(0.0)
+        _lib.check_train(self._lib.qgb_train_grads(self._h, x.ctypes.data, y.ctypes.data, x.shape[0], 0, g.ctypes.data,
+                                                   ctypes.byref(loss), 1 if update_running else 0, None), self._h)
+        return self._unflat(g, self.net.parameter_names()), loss.value
+
+    def eval_loss(self, x, y):
+        x, y = self._xy(x, y)
+        loss = ctypes.c_double(0.0)
+        _lib.check_train(self._lib.qgb_train_eval_loss(self._h, x.ctypes.data, y.ctypes.data, x.shape[0], 0,
+                                                       ctypes.byref(loss), None), self._h)
+        return loss.value
+
+    def launch_count(self):
+        return int(self._lib.qgb_train_launch_count(self._h))
+
+
+def multistep_lr(learning_rate, num_epochs, epoch):
+    """Learning rate of ``epoch`` (0-based) under MultiStepLR(milestones=[E/2, 3E/4, 7E/8], gamma=0.1) stepped once per
+    epoch (cnn_tools.py:672-673,691); coinciding milestones multiply, as torch's Counter-based scheduler does."""
+    counts = collections.Counter([int(num_epochs / 2), int(num_epochs * 3 / 4), int(num_epochs * 7 / 8)])
+    return learning_rate * 0.1 ** sum(c for m, c in counts.items() if 0 < m <= epoch)
+
+
+def evaluate_test(net, *arrays, batch_size=64, postfix='_test', device=None, trainer=None):
+    """cnn_tools.py:624-643: epoch-mean eval-mode loss appended to ``net.log_dict['loss' + postfix]``."""
+    if not hasattr(net, 'log_dict'):
+        net.log_dict = {}
+    tot, cnt = 0.0, 0
+    for x, y in minibatch(*arrays, batch_size=batch_size):
+        loss = trainer.eval_loss(x.numpy(), y.numpy()) if trainer is not None else net.compute_loss(x, y)['loss']
+        tot += loss * len(x)
+        cnt += len(x)
+    net.log_dict.setdefault('loss' + postfix, []).append(tot / max(cnt, 1))
+
+
+def train(net, X_train, Y_train, X_test, Y_test, num_epochs, batch_size, learning_rate, device=None):
+    """cnn_tools.py:645-700 on the device-side trainer: Adam(lr) + MultiStepLR, shuffled minibatches, MSE through
+    ``compute_loss``, BatchNorm in training mode; epoch-mean losses in ``net.log_dict['loss' | 'loss_test']``."""
+    X_train, Y_train = np.asarray(X_train), np.asarray(Y_train)
+    print('Training starts on device %s, number of samples %d' % (torch.cuda.get_device_name(0) if torch.cuda.is_available()
+                                                                  else 'cpu', len(X_train)))
+    trainer = Trainer(net, X_train.shape[2], X_train.shape[3], max_batch=batch_size, device=device)
+    if not hasattr(net, 'log_dict'):
+        net.log_dict = {}
+    t_s = time()
+    for epoch in range(num_epochs):
+        t_e = time()
+        lr = multistep_lr(learning_rate, num_epochs, epoch)
+        tot, cnt = 0.0, 0
+        for x, y in minibatch(X_train, Y_train, batch_size=batch_size):
+            loss = trainer.step(x.numpy(), y.numpy(), lr)
+            tot += loss * len(x)
+            cnt += len(x)
+        net.log_dict.setdefault('loss', []).append(tot / max(cnt, 1))
+        evaluate_test(net, X_test, Y_test, batch_size=batch_size, trainer=trainer)
+        t = time()
+        print('[%d/%d] [%.2f/%.2f] Loss: [%.3f, %.3f]' % (epoch + 1, num_epochs, t - t_e,
+                                                          (t - t_s) * (num_epochs / (epoch + 1) - 1),
+                                                          net.log_dict['loss'][-1], net.log_dict['loss_test'][-1]))
+    trainer.sync_to(net)
+    trainer.close()
+    return net
 
 
 class ChannelwiseScaler(object):
@@ -267,6 +459,36 @@ def apply_function(net, *X, fun=None, batch_size=64, **kw):
         preds.append([yy.cpu().numpy() for yy in y])
     preds = [np.vstack(p) for p in zip(*preds)]
     return preds[0] if len(preds) == 1 else preds
+
+
+def prepare_PV_data(ds_train, ds_test):
+    """cnn_tools.py:402-421: q -> q_forcing_advection pairs, scaled by the per-channel std of the training set."""
+    X_train, Y_train = extract(ds_train, 'q'), extract(ds_train, 'q_forcing_advection')
+    X_test, Y_test = extract(ds_test, 'q'), extract(ds_test, 'q_forcing_advection')
+    x_scale, y_scale = ChannelwiseScaler(X_train), ChannelwiseScaler(Y_train)
+    return (x_scale.normalize(X_train), y_scale.normalize(Y_train), x_scale.normalize(X_test), y_scale.normalize(Y_test),
+            x_scale, y_scale)
+
+
+def write_log(log_dict, path):
+    """cnn_tools.py:12-19 ``log_to_xarray(log_dict).to_netcdf(path)`` without xarray: one float64 variable per key over the
+    coordinate ``epoch`` = 1..num_epochs (NetCDF-3, opens with xarray)."""
+    from scipy.io import netcdf_file
+    n = len(next(iter(log_dict.values())))
+    with netcdf_file(path, 'w', version=2) as f:
+        f.createDimension('epoch', n)
+        v = f.createVariable('epoch', 'i', ('epoch',))
+        v[:] = np.arange(1, n + 1, dtype=np.int32)
+        for k, series in log_dict.items():
+            v = f.createVariable(k, 'd', ('epoch',))
+            v[:] = np.asarray(series, dtype=np.float64)
+    return path
+
+
+def save_model_args(model, folder='model', **kw):
+    """cnn_tools.py:21-25."""
+    with open('%s/model_args.json' % folder, 'w') as f:
+        json.dump(dict(model=model, **kw), f)
 
 
 def extract(ds, key):

@@ -11,7 +11,7 @@ Layout of one file (= one run, like the reference) :
   float32    q, u, v, psi (time, lev, y, x) [+ q_forcing_advection in forcing datasets];  Ubg, Qy (lev)
   float32    time-averaged spectral diagnostics of the LAST snapshot: KEspec, Ensspec (lev, l, k); KEflux, APEflux,
              APEgenspec, KEfrictionspec, entspec, paramspec, paramspec_KEflux, paramspec_APEflux, ENSflux, ENSgenspec,
-             ENSfrictionspec, Dissspec, ENSDissspec, ENSparamspec (l, k); EKE (lev), EKEdiss ()
+             ENSfrictionspec, Dissspec, ENSDissspec, ENSparamspec (l, k); EKE (lev); attribute EKEdiss
   attrs      pyqg_params (str of the dict, :144), pyqg:<name> physical parameters like pyqg's to_dataset
 ``write_netcdf`` keeps a leading ``run`` dimension instead (one file for the whole local ensemble).
 """
@@ -82,8 +82,8 @@ def _write(path, ds, run_index=None):
                 _nc_var(f, name, np.asarray(ds[name], dtype=np.float32), ('l', 'k'))
         if 'EKE' in ds:            # pyqg's scalar diagnostics (time averages like the spectra)
             _nc_var(f, 'EKE', np.asarray(ds['EKE'], dtype=np.float32), ('lev',))
-        if 'EKEdiss' in ds:
-            _nc_var(f, 'EKEdiss', np.asarray(ds['EKEdiss'], dtype=np.float32).reshape(()), ())
+        if 'EKEdiss' in ds:        # (scipy's NetCDF-3 writer has no scalar variables: the time average goes to an attribute)
+            setattr(f, 'EKEdiss', float(ds['EKEdiss']))
         for k, v in ds.get('attrs', {}).items():
             setattr(f, k, v if isinstance(v, (int, float)) else str(v))
 

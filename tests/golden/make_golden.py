@@ -20,6 +20,10 @@ samplers.npz       AR1 / constant sampler sequences
 ispec.npz          calc_ispec (tools/spectral_tools.py:103-180) of seeded spectra at nx = 48, 64 for every option combination
 initial_condition.npz  set_initial_condition (tools/simulate.py:147-168) under np.random.seed for nx = 48, 64, 96 (two
                    successive members each)
+training.npz       the reference's training arithmetic on a small AndrewCNN (2 -> 16 -> 12 -> 12 -> 8 -> 2, 16 x 16 images):
+                   loss and autograd gradients of ``compute_loss`` in training mode for AndrewCNN and VarCNN (softplus head),
+                   BatchNorm running statistics after that forward, and a whole ``cnn_tools.train`` run (4 epochs, batch 8,
+                   Adam + MultiStepLR, np.random.seed(0) shuffling): final state_dict and the loss log
 """
 import os
 import shutil
@@ -231,10 +235,59 @@ def initial_condition_fixture():
     np.savez_compressed(os.path.join(HERE, 'initial_condition.npz'), **out)
 
 
+TRAIN_HIDDEN = [16, 12, 12, 8]
+
+
+def training_fixture():
+    """tools/cnn_tools.py:645-700 ``train`` and :177-182 ``compute_loss`` run as they are (CPU torch, fp32)."""
+    from pyqg_generative.models.mean_var_model import VarCNN
+    out = {}
+    rng = np.random.RandomState(11)
+    x = rng.randn(6, 2, 16, 16).astype('float32')
+    y = rng.randn(6, 2, 16, 16).astype('float32')
+    out['grad_x'], out['grad_y'] = x, y
+    for tag, cls, target in (('mean', cnn_tools.AndrewCNN, y), ('var', VarCNN, y ** 2)):
+        torch.manual_seed(3)
+        net = cls(2, 2, hidden_channels=TRAIN_HIDDEN)
+        for k, v in net.state_dict().items():
+            out['%s_init/%s' % (tag, k)] = v.numpy().copy()
+        net.train()
+        loss = net.compute_loss(torch.as_tensor(x), torch.as_tensor(target))['loss']
+        loss.backward()
+        out['%s_loss' % tag] = np.float64(loss.item())
+        for k, p in net.named_parameters():
+            out['%s_grad/%s' % (tag, k)] = p.grad.numpy().copy()
+        for k, v in net.state_dict().items():
+            if 'running' in k:
+                out['%s_after/%s' % (tag, k)] = v.numpy().copy()
+    # a whole training run
+    X_train = rng.randn(20, 2, 16, 16).astype('float32')
+    W = rng.randn(2, 2).astype('float32')
+    Y_train = (np.einsum('ij,bjyx->biyx', W, np.roll(X_train, 1, axis=-1)) + 0.3 * X_train ** 2).astype('float32')
+    X_test = rng.randn(8, 2, 16, 16).astype('float32')
+    Y_test = (np.einsum('ij,bjyx->biyx', W, np.roll(X_test, 1, axis=-1)) + 0.3 * X_test ** 2).astype('float32')
+    torch.manual_seed(4)
+    net = cnn_tools.AndrewCNN(2, 2, hidden_channels=TRAIN_HIDDEN)
+    for k, v in net.state_dict().items():
+        out['run_init/%s' % k] = v.numpy().copy()
+    np.random.seed(0)
+    cnn_tools.train(net, X_train, Y_train, X_test, Y_test, num_epochs=4, batch_size=8, learning_rate=1e-3, device='cpu')
+    for k, v in net.state_dict().items():
+        out['run_final/%s' % k] = v.numpy().copy()
+    out['run_loss'] = np.array(net.log_dict['loss'], dtype=np.float64)
+    out['run_loss_test'] = np.array(net.log_dict['loss_test'], dtype=np.float64)
+    out.update(X_train=X_train, Y_train=Y_train, X_test=X_test, Y_test=Y_test)
+    np.savez_compressed(os.path.join(HERE, 'training.npz'), **out)
+
+
 if __name__ == '__main__':
     if '--only-new' in sys.argv:       # fixtures added in round 2 (the others are unchanged)
         ispec_fixture()
         initial_condition_fixture()
+        training_fixture()
+        sys.exit(0)
+    if '--training' in sys.argv:
+        training_fixture()
         sys.exit(0)
     save_weights()
     gan, vae, gz = load_reference_models()
@@ -244,5 +297,6 @@ if __name__ == '__main__':
     samplers_fixture()
     ispec_fixture()
     initial_condition_fixture()
+    training_fixture()
     for f in sorted(os.listdir(HERE)):
         print('%10d  %s' % (os.path.getsize(os.path.join(HERE, f)), f))

@@ -266,3 +266,25 @@ def test_eke_scalars_follow_from_kespec():
     eke = 0.5 * np.array([_full_plane_sum(d['KEspec'][z]) for z in range(2)])
     assert np.abs(eke - d['EKE']).max() < 1e-12 * d['EKE'].max()
     assert abs(m.del2 * m.rek * 2 * eke[1] - d['EKEdiss']) < 1e-12 * d['EKEdiss']
+
+
+def _golden_sd(g, prefix):
+    return {k[len(prefix) + 1:]: g[k] for k in g.files if k.startswith(prefix + '/')}
+
+
+def test_training_oracle_reproduces_the_reference():
+    """oracle/train_ref.py against the unmodified reference's compute_loss / autograd / cnn_tools.train (training.npz)."""
+    from oracle import train_ref
+    g = golden('training.npz')
+    for tag, target in (('mean', g['grad_y']), ('var', g['grad_y'] ** 2)):
+        loss, grads, after = train_ref.loss_and_grads(_golden_sd(g, tag + '_init'), g['grad_x'], target, softplus=tag == 'var')
+        assert abs(loss - float(g[tag + '_loss'])) < 1e-6 * abs(float(g[tag + '_loss']))
+        for k, v in _golden_sd(g, tag + '_grad').items():
+            assert np.abs(grads[k] - v).max() <= 1e-6 * max(np.abs(v).max(), 1e-30), (tag, k)
+        for k, v in _golden_sd(g, tag + '_after').items():
+            assert np.abs(after[k] - v).max() <= 1e-6 * np.abs(v).max(), (tag, k)
+    np.random.seed(0)
+    final, log = train_ref.train(_golden_sd(g, 'run_init'), g['X_train'], g['Y_train'], g['X_test'], g['Y_test'], 4, 8, 1e-3)
+    assert np.allclose(log['loss'], g['run_loss'], rtol=1e-5) and np.allclose(log['loss_test'], g['run_loss_test'], rtol=1e-5)
+    for k, v in _golden_sd(g, 'run_final').items():
+        assert np.abs(final[k].astype('float64') - v).max() <= 1e-5 * max(np.abs(v).max(), 1e-30), k
