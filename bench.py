@@ -469,6 +469,26 @@ def run_b200(args):
     e2e_value = world * G * gm * e2e_steps / e2e_s
     nbytes = int(G * gm * 2 * NX * NX * 8)
     e2e_healthy = all(bool(np.isfinite(grp[0].diagnostics()[0]).all()) for grp in groups)
+    # same loop with the result read back as the float32 snapshot the reference stores (drop_vars, tools/simulate.py:16-36):
+    # float64 q in, one step, float32 q out converted on the device -- 3/4 of the PCIe bytes (the 8-GPU line is bound by the
+    # host's D2H fabric, profiles/r2_pcie_8gpu.json)
+    for grp in groups:
+        grp.append(torch.empty(grp[1].shape, dtype=torch.float32).pin_memory())
+
+    def e2e32_round(n):
+        for _ in range(n):
+            for grp in groups:
+                grp[0].step_host(grp[1], None, 1, stream=grp[3], wait=False)
+                grp[0].real32('q', out=grp[4], stream=grp[3], wait=False)
+        for grp in groups:
+            grp[3].synchronize()
+    e2e32_round(2)
+    barrier()
+    t0 = time.perf_counter()
+    e2e32_round(e2e_steps)
+    barrier()
+    e2e32_s = parallel.allreduce_max(time.perf_counter() - t0)
+    e2e32_value = world * G * gm * e2e_steps / e2e32_s
     del groups
     torch.cuda.empty_cache()
 
@@ -519,6 +539,9 @@ def run_b200(args):
                 'steps': e2e_steps, 'groups': G, 'state_healthy': e2e_healthy,
                 'call': 'EnsembleQGModel.step_host -> qgb_step_host_async: pinned host q in, 1 step, host q out, per group of '
                         '%d members on its own stream' % gm},
+        'e2e_f32_snapshot': {'value': e2e32_value, 'unit': UNIT, 'h2d_bytes_per_step': nbytes, 'd2h_bytes_per_step': nbytes // 2,
+                             'call': 'step_host(q_in float64, no q out) + real32(q): the float32 snapshot the reference stores, '
+                                     'converted on the device'},
         'gpu_launches': int(launches),
         'clocks': clk,
         'roofline': {'bound': 'tensor', 'kernel': 'conv layer 2 (128->64, 5x5), %s' % chosen,

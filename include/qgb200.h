@@ -76,6 +76,10 @@ int qgb_set_q(qgb_handle* h, const double* q, int on_device, void* stream);
 /* pyqg: Model._initialize_time: t=0, tc=0, Adams-Bashforth restart (Euler, AB2, AB3). */
 int qgb_reset_time(qgb_handle* h);
 int qgb_get(qgb_handle* h, int field, void* out, int on_device, void* stream);
+/* float32 copy of a real field (QGB_F_Q, _U, _V, _P): what the reference stores in its datasets (drop_vars, tools/simulate.py:
+ * 16-36 converts every float64 variable to float32) converted on the device, so half the bytes cross PCIe.  With a host
+ * destination and async != 0 the call returns without synchronising (pinned memory; the caller synchronises ``stream``). */
+int qgb_get_f32(qgb_handle* h, int field, float* out, int on_device, int async, void* stream);
 /* pyqg: PseudoSpectralKernel._invert (explicit calls tools/simulate.py:132,168; tools/operators.py:233). */
 int qgb_invert(qgb_handle* h, void* stream);
 /* pyqg: Model._step_forward x nsteps = _invert, _do_advection, _do_friction, _do_q_subgrid_parameterization

@@ -46,11 +46,12 @@ class Net(nn.Module):
         return {'loss': nn.MSELoss()(self.forward(x), ytrue)}
 
 
-def loss_and_grads(sd, x, y, softplus=False):
-    """Training-mode loss, parameter gradients and the state dict after that forward (running statistics moved)."""
-    net = Net(sd, softplus)
+def loss_and_grads(sd, x, y, softplus=False, dtype=torch.float32):
+    """Training-mode loss, parameter gradients and the state dict after that forward (running statistics moved).
+    ``dtype=torch.float64`` gives the rounding-free reference the fp32 implementations are judged against."""
+    net = Net(sd, softplus).to(dtype)
     net.train()
-    loss = net.compute_loss(torch.as_tensor(x), torch.as_tensor(y))['loss']
+    loss = net.compute_loss(torch.as_tensor(x).to(dtype), torch.as_tensor(y).to(dtype))['loss']
     loss.backward()
     grads = {k: p.grad.numpy().copy() for k, p in net.named_parameters()}
     return float(loss.item()), grads, {k: v.numpy().copy() for k, v in net.state_dict().items()}

@@ -43,6 +43,7 @@ SYMBOLS = {
     'qgb_set_q': (_i, [_vp, _vp, _i, _vp]),
     'qgb_reset_time': (_i, [_vp]),
     'qgb_get': (_i, [_vp, _i, _vp, _i, _vp]),
+    'qgb_get_f32': (_i, [_vp, _i, _vp, _i, _i, _vp]),
     'qgb_invert': (_i, [_vp, _vp]),
     'qgb_step': (_i, [_vp, _i, _vp]),
     'qgb_graph_replays': (ctypes.c_int64, [_vp]),

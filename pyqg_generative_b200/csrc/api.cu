@@ -91,6 +91,7 @@ struct qgb_handle {
   bool dq_valid = false;
   double calib_err[4] = {-1.0, -1.0, -1.0, -1.0};   // measured rel-L2 / max-norm error of tc, tc_fast against fp32
   double* dq_ext = nullptr; bool ext_set = false;  // externally supplied forcing (qgb_set_forcing)
+  float* f32_stage = nullptr;   // float32 copy of a real field on its way to the host (qgb_get_f32)
   float* act[2] = {nullptr, nullptr}; size_t act_floats = 0; int act_chunk = 0;  // fp32 path ping-pong activations
   TcWorkspace tcw;
   int nsm = 148;
@@ -642,7 +643,7 @@ void qgb_destroy(qgb_handle* h) {
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   cudaFree(h->d_draw);
   cudaFree(h->d_ke); cudaFree(h->d_cfl); cudaFree(h->d_flags); cudaFree(h->d_kespec); cudaFree(h->d_ensspec);
-  cudaFree(h->bud); cudaFree(h->bud_tend); cudaFree(h->bud_scr); cudaFree(h->bud_sum); cudaFree(h->avg);
+  cudaFree(h->f32_stage); cudaFree(h->bud); cudaFree(h->bud_tend); cudaFree(h->bud_scr); cudaFree(h->bud_sum); cudaFree(h->avg);
   cudaFree(h->xin); cudaFree(h->z64); cudaFree(h->xi_inj); cudaFree(h->ynet[0]); cudaFree(h->ynet[1]);
   cudaFree(h->yacc); cudaFree(h->dq_ext); cudaFree(h->dq); cudaFree(h->dq_dm); cudaFree(h->act[0]); cudaFree(h->act[1]);
   free_net(h->nets[0]); free_net(h->nets[1]);
@@ -1011,6 +1012,41 @@ int qgb_get(qgb_handle* h, int field, void* out, int on_device, void* stream) {
   if (!src) return fail(h, QGB_ESTATE, "field %d not available (call qgb_invert first)", field);
   CUDA_TRY(h, cudaMemcpyAsync(out, src, bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
   if (!on_device) CUDA_TRY(h, cudaStreamSynchronize(st));
+  return QGB_OK;
+}
+
+namespace {
+__global__ void f64_to_f32_kernel(const double* __restrict__ in, float* __restrict__ out, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) out[i] = (float)in[i];
+}
+}  // namespace
+
+int qgb_get_f32(qgb_handle* h, int field, float* out, int on_device, int async, void* stream) {
+  if (!h || !out) return fail(h, QGB_EINVAL, "null argument");
+  cudaStream_t st = S(stream);
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  const double* src = nullptr;
+  switch (field) {
+    case QGB_F_Q: src = h->q; break;
+    case QGB_F_U: src = h->u; break;
+    case QGB_F_V: src = h->v; break;
+    case QGB_F_P: src = h->p; break;
+    default: return fail(h, QGB_EINVAL, "qgb_get_f32: field %d is not a real (B,2,N,N) field", field);
+  }
+  if (!src) return fail(h, QGB_ESTATE, "field %d not available (call qgb_invert first)", field);
+  const long long n = (long long)nreal(h);
+  float* dst = out;
+  if (!on_device) {
+    if (!h->f32_stage) CUDA_TRY(h, dalloc(&h->f32_stage, (size_t)n));
+    dst = h->f32_stage;
+  }
+  f64_to_f32_kernel<<<h->nsm * 8, 256, 0, st>>>(src, dst, n);
+  QGB_COUNT_LAUNCH();
+  CUDA_TRY(h, cudaGetLastError());
+  if (!on_device) {
+    CUDA_TRY(h, cudaMemcpyAsync(out, dst, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (!async) CUDA_TRY(h, cudaStreamSynchronize(st));
+  }
   return QGB_OK;
 }
 

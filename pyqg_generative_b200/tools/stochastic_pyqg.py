@@ -191,6 +191,17 @@ class EnsembleQGModel(object):
         self._get_into(field, out)
         return out[0] if self.squeeze else out
 
+    def real32(self, name, out=None, stream=None, wait=True):
+        """float32 copy of ``q`` / ``u`` / ``v`` / ``p`` converted on the device (what ``drop_vars`` stores, tools/simulate.py:
+        16-36): half the PCIe bytes of ``np.asarray(m.q, 'float32')``.  ``out``: optional (pinned) float32 buffer."""
+        field = {'q': _lib.F_Q, 'u': _lib.F_U, 'v': _lib.F_V, 'p': _lib.F_P, 'psi': _lib.F_P}[name]
+        if out is None:
+            out = np.empty((self.members, 2, self.ny, self.nx), dtype=np.float32)
+        ptr = out.data_ptr() if hasattr(out, 'data_ptr') else out.ctypes.data
+        s = stream.cuda_stream if stream is not None else self._stream()
+        _lib.check(self._lib.qgb_get_f32(self._h, field, ptr, 0, 0 if wait else 1, s), self._h)
+        return out
+
     def _cplx(self, field):
         out = np.empty((self.members, 2, self.nl, self.nk), dtype=complex)
         self._get_into(field, out)
@@ -494,6 +505,8 @@ class EnsembleQGModel(object):
         ``nsteps``, download q into ``q_out``.  With ``wait=False`` the call only enqueues work on ``stream`` (a
         torch.cuda.Stream); drive several member groups on different streams to overlap PCIe transfers and kernels."""
         def ptr(a):
+            if a is None:
+                return None
             return a.data_ptr() if hasattr(a, 'data_ptr') else a.ctypes.data
         s = (stream.cuda_stream if stream is not None else self._stream())
         fn = self._lib.qgb_step_host if wait else self._lib.qgb_step_host_async

@@ -78,23 +78,28 @@ def test_train_run_matches_reference():
     assert rel(y, yref) < 1e-3
 
 
-@pytest.mark.parametrize('shape,var', [((3, 24, 40), False), ((2, 32, 32), True)])
-def test_shipped_architecture_gradients_match_oracle(shape, var):
+@pytest.mark.parametrize('shape,var,seed', [((3, 24, 40), False, 24), ((2, 32, 32), True, 102)])
+def test_shipped_architecture_gradients_match_oracle(shape, var, seed):
     """The 2 -> 128 -> 64 -> 32 x 5 -> 2 network of the GZ / OLS closures (Appendix B) on grids that are not multiples of the
-    16 x 16 tiles: every weight-gradient geometry (thin input, wide layers over several channel blocks, thin output)."""
+    16 x 16 tiles: every weight-gradient geometry (thin input, wide layers over several channel blocks, thin output).
+    The loss is only piecewise smooth: with ~7e5 ReLU inputs per evaluation one of them often lies within fp32 rounding of zero,
+    and then any two fp32 implementations (torch's own under a 1e-7 input perturbation included) differ by 3e-3 .. 3e-2 in the
+    gradient.  The data seeds here were checked on the CPU oracle to be free of such a borderline unit (16 perturbed evaluations
+    agree with float64 to 4e-6); the reference is the float64 evaluation."""
     from pyqg_generative_b200.tools.cnn_tools import Trainer
     B, ny, nx = shape
     sd = cnn_ref.random_state_dict(2, 2, seed=5)
-    rng = np.random.RandomState(ny)
+    rng = np.random.RandomState(seed)
     x = rng.randn(B, 2, ny, nx).astype('float32')
     y = (rng.randn(B, 2, ny, nx) ** (2 if var else 1)).astype('float32')
-    loss_ref, grads_ref, _ = train_ref.loss_and_grads({k: v.numpy() for k, v in sd.items()}, x, y, softplus=var)
+    loss_ref, grads_ref, _ = train_ref.loss_and_grads({k: v.numpy() for k, v in sd.items()}, x, y, softplus=var,
+                                                      dtype=torch.float64)
     net = make_net(sd, var=var, hidden=[128, 64, 32, 32, 32, 32, 32])
     tr = Trainer(net, ny, nx, max_batch=4)
     grads, loss = tr.grads(x, y)
     assert abs(loss - loss_ref) < 1e-5 * loss_ref
-    for k, ref in grads_ref.items():
-        assert rel(grads[k], ref) < GRAD_TOL, (k, rel(grads[k], ref))
+    worst = max(rel(grads[k], ref) for k, ref in grads_ref.items())
+    assert worst < 1e-4, worst          # (bar: GRAD_TOL = 1e-3; measured level ~1e-5)
     tr.close()
 
 
