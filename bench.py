@@ -422,7 +422,7 @@ def run_b200(args):
             ref = tot[o:o + sz] / tot[-1]
             dev_ = max(dev_, float(np.abs(red[k_].ravel() - ref).max() / max(np.abs(ref).max(), 1e-300)))
             o += sz
-        diag_obj = {'collective': 'all_reduce(sum, f64) of KEspec, Ensspec and 7 spectral budget terms + sample count (NCCL)',
+        diag_obj = {'collective': 'all_reduce(sum, f64) of KEspec, Ensspec and the %d spectral budget terms + sample count (NCCL)' % len(m.DIAG_BUDGET),
                     'bytes': int(flat.numel() * 8), 'ms': parallel.allreduce_max(e0.elapsed_time(e1)), 'samples_x_members': int(cnt),
                     'max_rel_dev_vs_rank_ordered_gather': dev_, 'sharding_invariant': bool(dev_ < 1e-12 and cnt == tot[-1])}
         _lib.check(lib.qgb_diag_config(h, 1e12, 86400.0), h)

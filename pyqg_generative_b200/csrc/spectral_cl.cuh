@@ -64,6 +64,17 @@ struct Cfg {
 #endif
 
 SCL_INL uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+// Execution-only cluster barrier for the write-after-read hazards ("every CTA has finished READING its buffer, peers may now
+// overwrite it"): the loads were consumed by arithmetic that precedes the barrier in program order, so no release fence is
+// needed -- the fence of the full barrier waits for every outstanding global store of the pointwise phases (15 % of the stall
+// samples of the 256^2 kernel were membar stalls, profiles/r2_cluster256_ncu.md).
+SCL_INL void cluster_sync_exec() {
+#ifdef SCL_STRICT_SYNC
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+#else
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+#endif
+}
 SCL_INL void cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -341,7 +352,7 @@ SCL_INL void round(bool has_inv, int phys, bool has_fwd, const Tables& T, const 
     fftN<C>(v, g.t, tw);
     // ---- stage out ----
     if (hp == 0) {                                     // A_y / B_y at y = out_index -> T' of the CTA that owns row y
-      cluster_sync();                                  // every CTA has read its S columns (and finished with its old T')
+      cluster_sync_exec();                             // every CTA has read its S columns (and finished with its old T')
       const int col = g.slot + (g.isB ? H : 0);
 #pragma unroll
       for (int m = 0; m < 16; ++m) {
@@ -372,7 +383,7 @@ SCL_INL void round(bool has_inv, int phys, bool has_fwd, const Tables& T, const 
         out_to_in_naming<C>(v);
       }
     } else if (hp == 2) {                              // W_y(kx), kx = out_index -> T of the CTA that owns column slot(kx)
-      cluster_sync();                                  // every CTA has read its T' rows
+      cluster_sync_exec();                             // every CTA has read its T' rows
 #pragma unroll
       for (int m = 0; m < 16; ++m) {
         const int kx = out_index<C>(m, g.t);
