@@ -182,7 +182,7 @@ struct WgGeom {
 };
 
 template <int KS, int CI_T, int CO_PER>
-__global__ void __launch_bounds__(256, 1) wgrad_ffma_kernel(const float* __restrict__ a, const float* __restrict__ dz,
+__global__ void __launch_bounds__(256, (CO_PER * KS * KS <= 60 ? 2 : 1)) wgrad_ffma_kernel(const float* __restrict__ a, const float* __restrict__ dz,
                                                             float* __restrict__ part, int batch, int Cin, int Cout, int ny, int nx,
                                                             int ci_blocks) {
   using G = WgGeom<KS>;
