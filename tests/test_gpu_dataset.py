@@ -17,12 +17,17 @@ def test_run_simulation_writes_reference_style_files(tmp_path):
     # time-averaged spectral diagnostics come with the dataset (pyqg to_dataset + concat_in_time: from the last snapshot)
     for k in ('KEspec', 'Ensspec'):
         assert ds[k].shape == (2, N, N // 2 + 1)
-    for k in ('KEflux', 'APEflux', 'APEgenspec', 'KEfrictionspec', 'entspec', 'paramspec'):
+    for k in ('KEflux', 'APEflux', 'APEgenspec', 'KEfrictionspec', 'entspec', 'paramspec', 'ENSflux', 'ENSgenspec',
+              'ENSfrictionspec', 'Dissspec', 'ENSDissspec', 'ENSparamspec'):
         assert ds[k].shape == (N, N // 2 + 1)
+    assert ds['EKE'].shape == (2,) and ds['EKE'][0] > ds['EKE'][1] > 0 and ds['EKEdiss'] > 0
     paths = dataset.write_runs(ds, str(tmp_path / 'eddy'), first=0)
     d = dataset.read_netcdf(paths[2])
     assert np.array_equal(d['q'], ds['q'][2]) and np.array_equal(d['psi'], ds['psi'][2])
     assert d['var_dims']['KEspec'] == ('lev', 'l', 'k') and np.allclose(d['KEspec'], ds['KEspec'].astype('float32'))
+    assert d['var_dims']['Dissspec'] == ('l', 'k') and np.allclose(d['Dissspec'], ds['Dissspec'].astype('float32'))
+    assert d['var_dims']['EKE'] == ('lev',) and np.allclose(d['EKE'], ds['EKE'].astype('float32'))
+    assert np.isclose(d['attrs']['EKEdiss'], ds['EKEdiss'], rtol=1e-6)
     o = pyqg_shim.QGModel(nx=N, dt=dt, log_level=0)
     assert np.allclose(d['k'], o.kk) and np.allclose(d['l'], o.ll) and np.allclose(d['Qy'], o.Qy.astype('float32'))
     assert d['attrs']['pyqg_params'] == str(dict(params, tmax=float(params['tmax'])))

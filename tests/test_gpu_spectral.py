@@ -184,6 +184,18 @@ def test_host_buffer_stepping_sync_and_pipelined():
         st.synchronize()
     got = np.concatenate([g[2].numpy() for g in groups])
     assert np.array_equal(got, ref.q)
+    # float32 snapshots converted on the device (qgb_get_f32): the same bits as the host-side cast the reference does
+    # (drop_vars, tools/simulate.py:16-36), synchronously and enqueued on a stream without a q_out
+    ref._invert()
+    for name, full in (('q', ref.q), ('u', ref.u), ('v', ref.v), ('p', ref.p)):
+        assert np.array_equal(ref.real32(name), full.astype('float32')), name
+    mg, qi, qo, st = groups[0]
+    q32 = torch.empty(qi.shape, dtype=torch.float32).pin_memory()
+    mg.step_host(qo, None, 2, stream=st, wait=False)
+    mg.real32('q', out=q32, stream=st, wait=False)
+    st.synchronize()
+    ref._step_forward(2)
+    assert np.array_equal(q32.numpy(), ref.q[:2].astype('float32'))
 
 
 BUDGET = ('KEflux', 'APEflux', 'APEgenspec', 'KEfrictionspec', 'entspec', 'paramspec_KEflux', 'paramspec_APEflux',

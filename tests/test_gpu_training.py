@@ -5,6 +5,8 @@ References: tests/golden/training.npz -- losses, autograd gradients, BatchNorm r
 -- and the oracle restatement oracle/train_ref.py (CPU torch autograd) at the shipped architecture.
 Tolerance: gradients <= 1e-3 relative per tensor (the judge's bar for the training kernels; fp32 against fp32 with a different
 summation order measures ~1e-5), weights after the Adam run <= 1e-3 of the tensor's scale."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -128,6 +130,31 @@ def test_gz_two_stage_fit(tmp_path):
     out = again.predict(ds_test, M=1)
     var = np.asarray(out['q_forcing_advection_var'])
     assert var.shape == ds_test['q'].shape and (var >= 0).all() and np.isfinite(var).all()
+
+
+def test_ols_fit_and_reload(tmp_path):
+    """OLSModel.fit (models/ols_model.py:36-46): the regression network on (q, q_forcing_advection) pairs; the saved folder
+    loads into a fresh model that reproduces the fitted network's predictions."""
+    from pyqg_generative_b200.models.ols_model import OLSModel
+    rng = np.random.RandomState(2)
+    q = rng.randn(4, 4, 2, 16, 16) * np.array([7e-6, 1e-6])[None, None, :, None, None]
+    ds = {'q': q, 'q_forcing_advection': 2e-6 * (np.roll(q, 1, axis=-2) - q)}
+    folder = str(tmp_path / 'ols')
+    os.makedirs(folder)
+    model = OLSModel(folder=folder, hidden_channels=[16, 8])
+    np.random.seed(3)
+    model.fit(ds, ds, num_epochs=5, batch_size=8, learning_rate=2e-3)
+    log = model.net.log_dict
+    assert len(log['loss']) == len(log['loss_test']) == 5 and log['loss'][-1] < log['loss'][0]
+    for f in ('net.pt', 'x_scale.json', 'y_scale.json', 'model_args.json', 'stats.nc'):
+        assert (tmp_path / 'ols' / f).exists(), f
+    again = OLSModel(folder=folder, hidden_channels=[16, 8])
+    a, b = model.predict(ds), again.predict(ds)
+    assert np.array_equal(np.asarray(a['q_forcing_advection']), np.asarray(b['q_forcing_advection']))
+    # eval-mode loss of the trainer = the loss of the network the inference engine now serves
+    X = model.x_scale.normalize(q.reshape((-1, 2, 16, 16)).astype('float32'))
+    Y = model.y_scale.normalize(ds['q_forcing_advection'].reshape((-1, 2, 16, 16)).astype('float32'))
+    assert abs(model.net.compute_loss(X[:8], Y[:8])['loss'] - float(((again.net(torch.as_tensor(X[:8]).cuda()).cpu().numpy() - Y[:8]) ** 2).mean())) < 1e-6
 
 
 def test_trainer_rejects_bad_input():
