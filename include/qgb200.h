@@ -185,13 +185,14 @@ int qgb_diag_averages(qgb_handle* h, double* out, int64_t* nsamples, int reset, 
 
 /* ---- coarse-graining operators (stateless; tools/operators.py) -------------------------------------------
  * op: 1 = Operator1 (cut_off + model filter, :204-205), 2 = Operator2 (cut_off + gaussian, :207-208),
- *     5 = Operator5 (cut_off only, :216-217, :117-132).  in: double (batch, n, n) -> out: double (batch, nc, nc). */
+ *     4 = Operator4 (model filter of Operator2, :213-214), 5 = Operator5 (cut_off only, :216-217, :117-132).
+ * in: double (batch, n, n) -> out: double (batch, nc, nc). */
 int qgb_operator(int device, int op, int n, int nc, int batch, const double* in, double* out, int on_device,
                  void* stream);
 /* PV_subgrid_forcing(q, nc, operator, pyqg_params, dealias) (tools/operators.py:283-287) for a batch of hi-res
- * snapshots q: double (batch,2,n,n).  dealias: 0 = 'none', 2 = '3/2-rule' (advect :249-268 through fft_interpolate to the
- * 3n/2 grid and back; what generate_subgrid_forcing uses, tools/simulate.py:90-92).  Outputs (batch,2,nc,nc) double, any may
- * be NULL: forcing S, and the coarse model's q, u, v, psi (apply_operator_to_model, :219-236). */
+ * snapshots q: double (batch,2,n,n).  dealias: 0 = 'none', 1 = '2/3-rule' (:253-257: q, u, v and the divergence low-passed with
+ * pyqg's filter at filterfac = 1e20), 2 = '3/2-rule' (:258-266 through fft_interpolate to the 3n/2 grid and back; what
+ * generate_subgrid_forcing uses, tools/simulate.py:90-92).  Outputs (batch,2,nc,nc) double, any may be NULL: forcing S, and the coarse model's q, u, v, psi (apply_operator_to_model, :219-236). */
 int qgb_subgrid_forcing(const qgb_config* cfg, int op, int nc, int dealias, int batch, const double* q, double* forcing,
                         double* qf, double* uf, double* vf, double* pf, int on_device, void* stream);
 /* fft_interpolate(x, n, N, truncate_2h=True) (tools/operators.py:134-190): spectral interpolation (N > n) or truncation

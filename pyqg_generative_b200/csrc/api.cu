@@ -91,6 +91,7 @@ struct qgb_handle {
   bool dq_valid = false;
   double calib_err[4] = {-1.0, -1.0, -1.0, -1.0};   // measured rel-L2 / max-norm error of tc, tc_fast against fp32
   double* dq_ext = nullptr; bool ext_set = false;  // externally supplied forcing (qgb_set_forcing)
+  float *stage_x = nullptr, *stage_y = nullptr; size_t stage_x_floats = 0, stage_y_floats = 0;   // qgb_cnn_forward host staging
   float* f32_stage = nullptr;   // float32 copy of a real field on its way to the host (qgb_get_f32)
   float* act[2] = {nullptr, nullptr}; size_t act_floats = 0; int act_chunk = 0;  // fp32 path ping-pong activations
   TcWorkspace tcw;
@@ -648,7 +649,7 @@ void qgb_destroy(qgb_handle* h) {
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   cudaFree(h->d_draw);
   cudaFree(h->d_ke); cudaFree(h->d_cfl); cudaFree(h->d_flags); cudaFree(h->d_kespec); cudaFree(h->d_ensspec);
-  cudaFree(h->f32_stage); cudaFree(h->bud); cudaFree(h->bud_tend); cudaFree(h->bud_scr); cudaFree(h->bud_sum); cudaFree(h->avg);
+  cudaFree(h->stage_x); cudaFree(h->stage_y); cudaFree(h->f32_stage); cudaFree(h->bud); cudaFree(h->bud_tend); cudaFree(h->bud_scr); cudaFree(h->bud_sum); cudaFree(h->avg);
   cudaFree(h->xin); cudaFree(h->z64); cudaFree(h->xi_inj); cudaFree(h->ynet[0]); cudaFree(h->ynet[1]);
   cudaFree(h->yacc); cudaFree(h->dq_ext); cudaFree(h->dq); cudaFree(h->dq_dm); cudaFree(h->act[0]); cudaFree(h->act[1]);
   free_net(h->nets[0]); free_net(h->nets[1]);
@@ -1246,16 +1247,24 @@ int qgb_cnn_forward(qgb_handle* h, int net, const float* x, float* y, int batch,
     precision = h->calibrated ? h->auto_precision : ((h->nets[net].tc.ready && ny % 16 == 0 && nx % 16 == 0) ? QGB_PREC_TC : QGB_PREC_FP32);
   const long long x_bs = (long long)cin * ny * nx, y_bs = (long long)cout * ny * nx;
   if (on_device) return net_forward(h, net, x, x_bs, y, y_bs, batch, ny, nx, softplus, 0, precision, st);
-  float *dx = nullptr, *dy = nullptr;
-  CUDA_TRY(h, dalloc(&dx, (size_t)batch * x_bs));
-  cudaError_t e = dalloc(&dy, (size_t)batch * y_bs);
-  if (e != cudaSuccess) { cudaFree(dx); return fail(h, QGB_ECUDA, "cudaMalloc failed: %s", cudaGetErrorString(e)); }
+  // host caller: staging buffers live in the handle and only grow (no allocation per call on the plugin path)
+  const size_t need_x = (size_t)batch * x_bs, need_y = (size_t)batch * y_bs;
+  if (h->stage_x_floats < need_x) {
+    cudaFree(h->stage_x); h->stage_x = nullptr; h->stage_x_floats = 0;
+    CUDA_TRY(h, dalloc(&h->stage_x, need_x));
+    h->stage_x_floats = need_x;
+  }
+  if (h->stage_y_floats < need_y) {
+    cudaFree(h->stage_y); h->stage_y = nullptr; h->stage_y_floats = 0;
+    CUDA_TRY(h, dalloc(&h->stage_y, need_y));
+    h->stage_y_floats = need_y;
+  }
+  float *dx = h->stage_x, *dy = h->stage_y;
   int rc = QGB_OK;
-  e = cudaMemcpyAsync(dx, x, (size_t)batch * x_bs * 4, cudaMemcpyHostToDevice, st);
+  cudaError_t e = cudaMemcpyAsync(dx, x, need_x * 4, cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) rc = net_forward(h, net, dx, x_bs, dy, y_bs, batch, ny, nx, softplus, 0, precision, st);
-  if (e == cudaSuccess && rc == QGB_OK) e = cudaMemcpyAsync(y, dy, (size_t)batch * y_bs * 4, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && rc == QGB_OK) e = cudaMemcpyAsync(y, dy, need_y * 4, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-  cudaFree(dx); cudaFree(dy);
   if (e != cudaSuccess) return fail(h, QGB_ECUDA, "cnn_forward: %s", cudaGetErrorString(e));
   return rc;
 }
@@ -1394,6 +1403,40 @@ int advect_dealiased(const qgb_config& base, int n, int B, const double* q, cons
   CUDA_TRY(nullptr, cudaStreamSynchronize(st));     // the temporary handles are released on return
   return QGB_OK;
 }
+
+// advect(var, u, v, '2/3-rule') (tools/operators.py:253-257): q, u, v low-passed with the sharp filter of
+// pyqg.QGModel(nx, filterfac=1e+20), products on the same grid, spectral divergence, low-passed again.
+// adv_h (B,2,n,n/2+1) = filtr (ik F(q~ u~) + il F(q~ v~)).
+int advect_23(const qgb_config& base, int n, int B, const double* q, const double* u, const double* v, cplx* adv_h, cudaStream_t st) {
+  qgb_config c3 = base, c2 = base;
+  c3.nx = n; c3.members = 3 * B;
+  c2.nx = n; c2.members = 2 * B;
+  HandleGuard g3, g2;
+  int rc;
+  if ((rc = g3.create(c3))) return rc;
+  if ((rc = g2.create(c2))) return rc;
+  qgb_handle *h3 = g3.h, *h2 = g2.h;
+  const size_t fn = (size_t)B * 2 * n * n;
+  const double sharp = 1e20;
+  CUDA_TRY(nullptr, cudaMemcpyAsync(h3->q, q, fn * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  CUDA_TRY(nullptr, cudaMemcpyAsync(h3->q + fn, u, fn * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  CUDA_TRY(nullptr, cudaMemcpyAsync(h3->q + 2 * fn, v, fn * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  StepIO io = base_io(h3);
+  if ((rc = launch_program(h3, io, PROG_SET_Q, st))) return fail(nullptr, rc, "%s", h3->err.c_str());
+  spectral_filter_kernel<<<grid_for((long long)6 * B * n * (n / 2 + 1)), 256, 0, st>>>(h3->qh, 6 * B, n, base.L, sharp);
+  if ((rc = launch_program(h3, io, PROG_C2R, st))) return fail(nullptr, rc, "%s", h3->err.c_str());
+  rmul_kernel<<<grid_for((long long)fn), 256, 0, st>>>(h3->q, h3->q + fn, h2->q, (long long)fn);            // q~ u~
+  rmul_kernel<<<grid_for((long long)fn), 256, 0, st>>>(h3->q, h3->q + 2 * fn, h2->q + fn, (long long)fn);   // q~ v~
+  StepIO io2 = base_io(h2);
+  if ((rc = launch_program(h2, io2, PROG_SET_Q, st))) return fail(nullptr, rc, "%s", h2->err.c_str());
+  const size_t cn = (size_t)B * 2 * n * (n / 2 + 1);
+  spectral_div_kernel<<<grid_for((long long)cn), 256, 0, st>>>(h2->qh, h2->qh + cn, adv_h, 2 * B, n, base.L);
+  spectral_filter_kernel<<<grid_for((long long)cn), 256, 0, st>>>(adv_h, 2 * B, n, base.L, sharp);
+  g_launches.fetch_add(5, std::memory_order_relaxed);
+  CUDA_TRY(nullptr, cudaGetLastError());
+  CUDA_TRY(nullptr, cudaStreamSynchronize(st));     // the temporary handles are released on return
+  return QGB_OK;
+}
 }  // namespace
 
 int qgb_fft_interpolate(int device, int n, int N, int batch, const double* in, double* out, int on_device, void* stream) {
@@ -1429,7 +1472,7 @@ int qgb_fft_interpolate(int device, int n, int N, int batch, const double* in, d
 int qgb_operator(int device, int op, int n, int nc, int batch, const double* in, double* out, int on_device,
                  void* stream) {
   if (!in || !out || batch < 1) return fail(nullptr, QGB_EINVAL, "bad argument");
-  if (op != 1 && op != 2 && op != 5) return fail(nullptr, QGB_EINVAL, "operator %d not supported (1, 2, 5)", op);
+  if (op != 1 && op != 2 && op != 4 && op != 5) return fail(nullptr, QGB_EINVAL, "operator %d not supported (1, 2, 4, 5)", op);
   if (nc % 2 != 0) return fail(nullptr, QGB_EINVAL, "nc must be even");
   if (nc > n || nc < 4) return fail(nullptr, QGB_EINVAL, "nc must satisfy 4 <= nc <= n");
   cudaStream_t st = S(stream);
@@ -1466,8 +1509,8 @@ int qgb_operator(int device, int op, int n, int nc, int batch, const double* in,
 int qgb_subgrid_forcing(const qgb_config* cfg, int op, int nc, int dealias, int batch, const double* q, double* forcing,
                         double* qf, double* uf, double* vf, double* pf, int on_device, void* stream) {
   if (!cfg || !q || batch < 1) return fail(nullptr, QGB_EINVAL, "bad argument");
-  if (dealias != 0 && dealias != 2) return fail(nullptr, QGB_EINVAL, "dealias should be none or 3/2-rule");
-  if (op != 1 && op != 2 && op != 5) return fail(nullptr, QGB_EINVAL, "operator %d not supported (1, 2, 5)", op);
+  if (dealias != 0 && dealias != 1 && dealias != 2) return fail(nullptr, QGB_EINVAL, "dealias should be none or 2/3-rule or 3/2-rule");
+  if (op != 1 && op != 2 && op != 4 && op != 5) return fail(nullptr, QGB_EINVAL, "operator %d not supported (1, 2, 4, 5)", op);
   const int n = cfg->nx;
   if (nc % 2 != 0) return fail(nullptr, QGB_EINVAL, "nc must be even");
   if (nc > n || nc < 4) return fail(nullptr, QGB_EINVAL, "nc must satisfy 4 <= nc <= n");
@@ -1500,7 +1543,8 @@ int qgb_subgrid_forcing(const qgb_config* cfg, int op, int nc, int dealias, int 
   } else {
     rc = qgb_invert(hf, stream);                                      // u, v of the fine model
     if (rc) return fail(nullptr, rc, "%s", hf->err.c_str());
-    rc = advect_dealiased(cf, n, batch, hf->q, hf->u, hf->v, hf->hist[0], st);   // hist[0] = +adv_f_h (3/2-rule)
+    rc = dealias == 1 ? advect_23(cf, n, batch, hf->q, hf->u, hf->v, hf->hist[0], st)
+                      : advect_dealiased(cf, n, batch, hf->q, hf->u, hf->v, hf->hist[0], st);   // hist[0] = +adv_f_h
     if (rc) return rc;
     fine_sign = 1.0;
   }
@@ -1518,7 +1562,8 @@ int qgb_subgrid_forcing(const qgb_config* cfg, int op, int nc, int dealias, int 
   if (dealias == 0) {
     OPRUN(hc, ioc, PROG_ADVECT, &T0c);                                // hist[0] = -adv_c_h
   } else {
-    rc = advect_dealiased(cc, nc, batch, hc->q, hc->u, hc->v, hc->hist[0], st);
+    rc = dealias == 1 ? advect_23(cc, nc, batch, hc->q, hc->u, hc->v, hc->hist[0], st)
+                      : advect_dealiased(cc, nc, batch, hc->q, hc->u, hc->v, hc->hist[0], st);
     if (rc) return rc;
     coarse_sign = 1.0;
   }

@@ -14,6 +14,7 @@ namespace qgb {
 //   with trunc[n,0] = 0 and trunc[:,n] = 0 (FILTER_2h_HARMONICS, :126-130)
 // op 1: pyqg exponential filter of a DEFAULT coarse model (model_filter :92-99 builds pyqg.QGModel(nx=nc): filterfac 23.6)
 // op 2: gauss_filter(X, nc//2) :84-90  -> exp(-wv^2 (2 dx_c)^2 / 24);   op 5: no filter
+// op 4: Operator4 = model_filter(Operator2(X, nc)) :213-214 -> the product of the two filters
 __global__ void trunc_filter_kernel(const cplx* __restrict__ in, cplx* __restrict__ out, int fields, int N, int nc, int op,
                                     double L, double sign) {
   const int NK = N / 2 + 1, nkc = nc / 2 + 1, n = nc / 2;
@@ -29,11 +30,10 @@ __global__ void trunc_filter_kernel(const cplx* __restrict__ in, cplx* __restric
       v = in[(f * N + lf) * NK + kc];
       const double kk = dk * kc, ll = dk * (lc < n ? lc : lc - nc);
       double filt = 1.0;
-      if (op == 1) {
+      if (op == 2 || op == 4) filt = exp(-(kk * kk + ll * ll) * (2.0 * dxc) * (2.0 * dxc) / 24.0);
+      if (op == 1 || op == 4) {
         const double wvx = sqrt((kk * dxc) * (kk * dxc) + (ll * dxc) * (ll * dxc));
-        if (wvx > 0.65 * pi) { const double d = wvx - 0.65 * pi; filt = exp(-23.6 * d * d * d * d); }
-      } else if (op == 2) {
-        filt = exp(-(kk * kk + ll * ll) * (2.0 * dxc) * (2.0 * dxc) / 24.0);
+        if (wvx > 0.65 * pi) { const double d = wvx - 0.65 * pi; filt *= exp(-23.6 * d * d * d * d); }
       }
       const double s = sign * filt / r2;
       v = cmake(v.x * s, v.y * s);
@@ -63,6 +63,25 @@ __global__ void resample_kernel(const cplx* __restrict__ in, cplx* __restrict__ 
       }
     }
     out[i] = v;
+  }
+}
+
+// in-place pyqg exponential filter with an arbitrary filterfac on half-plane arrays of an n-grid (pyqg _initialize_filter:
+// filtr = exp(-filterfac (wv dx - 0.65 pi)^4) above the cut-off, 1 below).  filterfac = 1e20 is the sharp cut-off of
+// advect(..., '2/3-rule') (operators.py:253-257: pyqg.QGModel(nx, filterfac=1e+20)).
+__global__ void spectral_filter_kernel(cplx* __restrict__ a, int fields, int n, double L, double filterfac) {
+  const int nk = n / 2 + 1;
+  const double pi = 3.14159265358979323846;
+  const double dk = 2.0 * pi / L, dx = L / n;
+  const long long total = (long long)fields * n * nk;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % nk), l = (int)((i / nk) % n);
+    const double kk = dk * k, ll = dk * (l < n / 2 ? l : l - n);
+    const double wvx = sqrt((kk * dx) * (kk * dx) + (ll * dx) * (ll * dx));
+    if (wvx > 0.65 * pi) {
+      const double d = wvx - 0.65 * pi, f = exp(-filterfac * d * d * d * d);
+      a[i] = cmake(a[i].x * f, a[i].y * f);
+    }
   }
 }
 

@@ -5,8 +5,8 @@
 signatures.  Inputs may be numpy arrays (2-D field, (nlev,ny,nx) like the reference's ``array_format`` numpy branch, or
 any leading batch axes) or CUDA torch tensors (processed in place on the device, a CUDA tensor is returned).
 All FFTs / truncations / Jacobians run in libqgb200 (qgb_operator, qgb_subgrid_forcing).
-``fft_interpolate`` (:134-190) and the '3/2-rule' dealiased forcing (``advect`` :258-266) are built as well.
-Not built: Operator3 (gcm_filters), Operator4, the '2/3-rule'.
+``fft_interpolate`` (:134-190), ``Operator4`` = model_filter o Operator2 (:213-214) and the dealiased forcings (``advect``
+:253-266, '2/3-rule' and '3/2-rule') are built as well.  Not built: Operator3 (gcm_filters is not a dependency here).
 """
 import ctypes
 
@@ -66,6 +66,10 @@ def Operator2(X, nc):
     return _run_operator(2, X, nc)
 
 
+def Operator4(X, nc):
+    return _run_operator(4, X, nc)
+
+
 def Operator5(X, nc):
     return _run_operator(5, X, nc)
 
@@ -90,7 +94,8 @@ def fft_interpolate(x, n, N, truncate_2h=True):
     return out
 
 
-_OP_ID = {'Operator1': 1, 'Operator2': 2, 'Operator5': 5, 'cut_off': 5}
+_OP_ID = {'Operator1': 1, 'Operator2': 2, 'Operator4': 4, 'Operator5': 5, 'cut_off': 5}
+_DEALIAS_ID = {'none': 0, '2/3-rule': 1, '3/2-rule': 2}
 
 
 def _config(pyqg_params, n):
@@ -110,14 +115,12 @@ def PV_subgrid_forcing(q, nc, operator, pyqg_params, dealias='none', return_fiel
     q, u, v, p of the coarse model, ``m`` is None (the fine model is never materialised) -- or ``(forcing, dict)`` with
     the coarse fields when ``return_fields`` is True."""
     import torch
-    if dealias not in ('none', '3/2-rule'):
-        if dealias == '2/3-rule':
-            raise NotImplementedError("dealias='2/3-rule' is not built ('none' and '3/2-rule' are)")
+    if dealias not in _DEALIAS_ID:
         raise ValueError('dealias should be none or 2/3-rule or 3/2-rule')
-    dealias_id = 0 if dealias == 'none' else 2
+    dealias_id = _DEALIAS_ID[dealias]
     op = _OP_ID.get(getattr(operator, '__name__', str(operator)))
     if op is None:
-        raise NotImplementedError('operator %r is not on the accelerated path (Operator1, Operator2, Operator5)' % (operator,))
+        raise NotImplementedError('operator %r is not on the accelerated path (Operator1, Operator2, Operator4, Operator5)' % (operator,))
     lib = _lib.load()
     cuda_in = _is_cuda_tensor(q)
     if cuda_in:

@@ -16,6 +16,7 @@ closure_48.npz     q (2,48,48), injected latent noise, and the reference classes
 coupled_48.npz     3 steps of reference ``stochastic_QGModel`` + ``CVAERegression`` (AR1 nsteps=1 and nsteps=4;
                    constant nsteps=2) with recorded noise and states
 operators_128.npz  Operator1/2/5, cut_off, fft_interpolate, PV_subgrid_forcing(none, 3/2-rule) on a 128^2 field
+operators_128_more.npz  Operator4 and PV_subgrid_forcing with the '2/3-rule' (and Operator4 with none / 3/2-rule), same field
 samplers.npz       AR1 / constant sampler sequences
 ispec.npz          calc_ispec (tools/spectral_tools.py:103-180) of seeded spectra at nx = 48, 64 for every option combination
 initial_condition.npz  set_initial_condition (tools/simulate.py:147-168) under np.random.seed for nx = 48, 64, 96 (two
@@ -174,6 +175,19 @@ def operators_fixture():
                 out['vf_%s' % opname] = mf.v
                 out['pf_%s' % opname] = mf.p
     np.savez_compressed(os.path.join(HERE, 'operators_128.npz'), **out)
+    # Operator4 (:213-214) and the '2/3-rule' of advect (:253-257) on the same field (separate file: same q as above)
+    out2 = {}
+    for nc in (32, 48, 64):
+        out2['Operator4_%d' % nc] = operators.Operator4(q, nc)
+    for opname in ('Operator1', 'Operator2', 'Operator4', 'Operator5'):
+        forcing, mf, m = operators.PV_subgrid_forcing(q, 64, getattr(operators, opname), dict(params), '2/3-rule')
+        out2['S_%s_23' % opname] = forcing
+    for dealias, tag in (('none', 'none'), ('3/2-rule', '32')):
+        forcing, mf, m = operators.PV_subgrid_forcing(q, 64, operators.Operator4, dict(params), dealias)
+        out2['S_Operator4_%s' % tag] = forcing
+        out2['qf_Operator4'] = mf.q
+        out2['uf_Operator4'] = mf.u
+    np.savez_compressed(os.path.join(HERE, 'operators_128_more.npz'), **out2)
 
 
 def samplers_fixture():
@@ -285,6 +299,9 @@ if __name__ == '__main__':
         ispec_fixture()
         initial_condition_fixture()
         training_fixture()
+        sys.exit(0)
+    if '--operators' in sys.argv:
+        operators_fixture()
         sys.exit(0)
     if '--training' in sys.argv:
         training_fixture()

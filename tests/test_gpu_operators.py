@@ -41,12 +41,30 @@ def test_subgrid_forcing_matches_reference_outputs():
         assert rel(mf.v, o['vf_%s' % name]) < TOL and rel(mf.p, o['pf_%s' % name]) < TOL
         f32, _, _ = ops.PV_subgrid_forcing(q, 64, getattr(ops, name), params, dealias='3/2-rule')
         assert rel(f32, o['S_%s_32' % name]) < 1e-9, name              # 3/2-rule: 128 -> 192 and 64 -> 96 and back
-    with pytest.raises(NotImplementedError):
-        ops.PV_subgrid_forcing(q, 64, ops.Operator1, params, dealias='2/3-rule')
+    with pytest.raises(ValueError, match='dealias should be'):
+        ops.PV_subgrid_forcing(q, 64, ops.Operator1, params, dealias='1/2-rule')
     assert rel(ops.fft_interpolate(o['interp_in'], 48, 72), o['interp_48_72']) < TOL
     assert rel(ops.fft_interpolate(o['interp_in'], 48, 32), o['interp_48_32']) < TOL
     x = np.random.RandomState(1).randn(64, 64)                        # notebooks/3-2-dealiasing.ipynb:586
     assert rel(ops.cut_off(x, 16), ops.fft_interpolate(x, 64, 16)) < 1e-13
+
+
+def test_operator4_and_two_thirds_rule_match_reference_outputs():
+    """Operator4 = model_filter(Operator2) (tools/operators.py:213-214) and advect(..., '2/3-rule') (:253-257)."""
+    from pyqg_generative_b200.tools import operators as ops
+    q = golden('operators_128.npz')['q'].astype('float64')
+    o = golden('operators_128_more.npz')
+    params = dict(dt=14400.0, tmax=1.0, tavestart=1.0)
+    for nc in (32, 48, 64):
+        assert rel(ops.Operator4(q, nc), o['Operator4_%d' % nc]) < TOL, nc
+    for name in ('Operator1', 'Operator2', 'Operator4', 'Operator5'):
+        f23, _, _ = ops.PV_subgrid_forcing(q, 64, getattr(ops, name), params, dealias='2/3-rule')
+        assert rel(f23, o['S_%s_23' % name]) < 1e-9, name
+    f, mf, _ = ops.PV_subgrid_forcing(q, 64, ops.Operator4, params)
+    assert rel(f, o['S_Operator4_none']) < 1e-9
+    assert rel(mf.q, o['qf_Operator4']) < TOL and rel(mf.u, o['uf_Operator4']) < TOL
+    f, _, _ = ops.PV_subgrid_forcing(q, 64, ops.Operator4, params, dealias='3/2-rule')
+    assert rel(f, o['S_Operator4_32']) < 1e-9
 
 
 def test_hires_256_to_64_batched_on_device():

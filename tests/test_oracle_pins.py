@@ -52,6 +52,22 @@ def test_operator_restatements_match_reference():
             assert np.abs(f - ref).max() <= 1e-12 * np.abs(ref).max(), (opn, tag)
 
 
+def test_operator4_and_two_thirds_rule_restatements_match_reference():
+    q = golden('operators_128.npz')['q'].astype('float64')
+    o = golden('operators_128_more.npz')
+    for nc in (32, 48, 64):
+        ref = o['Operator4_%d' % nc]
+        assert np.abs(opr.Operator4(q, nc) - ref).max() <= 1e-14 * np.abs(ref).max(), nc
+    for opn in ('Operator1', 'Operator2', 'Operator4', 'Operator5'):
+        f, mf, m = opr.PV_subgrid_forcing(q, 64, getattr(opr, opn), {}, '2/3-rule')
+        ref = o['S_%s_23' % opn]
+        assert np.abs(f - ref).max() <= 1e-12 * np.abs(ref).max(), opn
+    for de, tag in (('none', 'none'), ('3/2-rule', '32')):
+        f, mf, m = opr.PV_subgrid_forcing(q, 64, opr.Operator4, {}, de)
+        ref = o['S_Operator4_%s' % tag]
+        assert np.abs(f - ref).max() <= 1e-12 * np.abs(ref).max(), tag
+
+
 def test_samplers_match_reference():
     g = golden('samplers.npz')
     for n in (1, 4, -1):
