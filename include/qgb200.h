@@ -251,6 +251,22 @@ int qgb_train_grads(qgb_trainer* t, const float* x, const float* y, int batch, i
                     int update_running, void* stream);
 /* ``evaluate_test`` (cnn_tools.py:624-643): eval-mode (running statistics) MSE of one minibatch. */
 int qgb_train_eval_loss(qgb_trainer* t, const float* x, const float* y, int batch, int on_device, double* loss, void* stream);
+/* gradients left by the last backward pass (host, flat parameter layout) */
+int qgb_train_get_grads(qgb_trainer* t, float* grads);
+/* Adam betas of this trainer (torch defaults (0.9, 0.999); train_CGAN uses (0.5, 0.999), cgan_regression.py:246-247) */
+int qgb_train_set_adam(qgb_trainer* t, double beta1, double beta2);
+
+/* ---- CVAE: one iteration of train_CVAE (models/cvae_regression.py:283-289) ------------------------------------------
+ * optimizer.zero_grad(); losses = net.compute_loss(x, y, ymean = 0); losses['loss'].backward(); optimizer.step() with
+ * Adam over chain(encoder, decoder) (:268).  enc: AndrewCNN 4 -> 4 on cat[x, y] giving [mu, logvar] (:104-112); dec:
+ * AndrewCNN 4 -> 2 on cat[x, z], z = eps exp(logvar / 2) + mu (:165-175); loss = sum (yhat - y)^2 / (2 var_p B) +
+ * sum 0.5 (mu^2 + var - 1 - logvar) / B (:177-230).  x, y, eps: float (batch, 2, ny, nx), eps = the standard normal draw
+ * of ``torch.randn_like(std)``; host pointers (copied on ``stream``) or device pointers (on_device != 0).
+ * decoder_var < 0: 'adaptive' (var_p = the batch's mean squared error, held constant in the gradient), otherwise the value
+ * ('fixed' = 1).  update != 0: Adam step of both networks with learning rate lr; 0: gradients only (qgb_train_get_grads).
+ * losses (host, 6 doubles, may be NULL) = loss, loss_recon, loss_KL, MSE, var_latent, var_aggr. */
+int qgb_train_cvae_step(qgb_trainer* enc, qgb_trainer* dec, const float* x, const float* y, const float* eps, int batch,
+                        int on_device, double lr, double decoder_var, int update, double* losses, void* stream);
 
 #ifdef __cplusplus
 }

@@ -86,6 +86,10 @@ SYMBOLS = {
     'qgb_train_step': (_i, [_vp, _vp, _vp, _i, _i, _d, ctypes.POINTER(_d), _vp]),
     'qgb_train_grads': (_i, [_vp, _vp, _vp, _i, _i, _vp, ctypes.POINTER(_d), _i, _vp]),
     'qgb_train_eval_loss': (_i, [_vp, _vp, _vp, _i, _i, ctypes.POINTER(_d), _vp]),
+    'qgb_train_get_grads': (_i, [_vp, _vp]),
+    'qgb_train_set_adam': (_i, [_vp, _d, _d]),
+    # CVAE / CGAN training steps (models/cvae_regression.py:250-300, models/cgan_regression.py:227-300)
+    'qgb_train_cvae_step': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _d, _d, _i, ctypes.POINTER(_d), _vp]),
 }
 
 _lib = None

@@ -9,10 +9,12 @@
 #include <vector>
 
 #include "../../include/qgb200.h"
+#include "adv.cuh"
 #include "train.cuh"
 
 using namespace qgb;
 using namespace qgb::train;
+using namespace qgb::adv;
 
 namespace {
 std::string g_train_create_error;
@@ -31,7 +33,12 @@ struct qgb_trainer {
   float *P = nullptr, *G = nullptr, *M = nullptr, *V = nullptr, *BUF = nullptr;
   float *mean = nullptr, *invstd = nullptr, *fold_s = nullptr, *fold_t = nullptr, *ones = nullptr, *zeros = nullptr;
   float *x = nullptr, *t = nullptr;        // staged minibatch (host callers)
-  std::vector<float*> r, a;                // per layer: r_l = relu(conv) [last layer: z_L], a_l = BatchNorm output
+  std::vector<float*> r, a;                // per (slot, layer): r_l = relu(conv) [last layer: z_L], a_l = BatchNorm output
+  int nslots = 1, slot = 0;                // activation sets (the GAN step keeps two generator passes alive); slot = the one in use
+  float* Gacc = nullptr;                   // gradient accumulator over several backward passes
+  float* scr[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // scratch of the CVAE / CGAN steps (grown on demand)
+  size_t scr_floats[6] = {0, 0, 0, 0, 0, 0};
+  double* stats = nullptr;                 // loss partial sums and results of those steps
   float* d[2] = {nullptr, nullptr};        // gradient ping-pong, max channels x batch x pixels
   float* wp = nullptr;                     // packed weights of the layer at hand
   float* wg_part = nullptr; size_t wg_part_floats = 0;
@@ -63,6 +70,12 @@ template <typename T>
 cudaError_t talloc(T** p, size_t n) { return cudaMalloc((void**)p, (n ? n : 1) * sizeof(T)); }
 
 constexpr int kLossBlocks = 256;
+constexpr int kMaxSlots = 2;
+
+inline float*& R(qgb_trainer* t, int l) { return t->r[(size_t)t->slot * t->nlayers + l]; }
+inline float*& A(qgb_trainer* t, int l) { return t->a[(size_t)t->slot * t->nlayers + l]; }
+inline float* MEAN(qgb_trainer* t, const qgb_trainer::Layer& L) { return t->mean + (size_t)t->slot * t->nstat + L.stat; }
+inline float* INVSTD(qgb_trainer* t, const qgb_trainer::Layer& L) { return t->invstd + (size_t)t->slot * t->nstat + L.stat; }
 
 inline int co_pad_of(int cout) { const int ct = cout <= 4 ? 2 : 32; return (cout + ct - 1) / ct * ct; }
 
@@ -174,6 +187,23 @@ int stage(qgb_trainer* t, const float* x, const float* y, int batch, int on_devi
   return QGB_OK;
 }
 
+// a second set of saved activations (the GAN step differentiates through two generator passes of the same minibatch)
+int ensure_slots(qgb_trainer* t, int n) {
+  if (n > kMaxSlots) return tfail(t, QGB_EINVAL, "at most %d activation slots", kMaxSlots);
+  const size_t hw = (size_t)t->ny * t->nx, B = t->max_batch;
+  while (t->nslots < n) {
+    for (int l = 0; l < t->nlayers; ++l) {
+      float *r = nullptr, *a = nullptr;
+      TR_TRY(t, talloc(&r, B * t->L[l].cout * hw));
+      t->r.push_back(r);
+      if (t->L[l].bn) TR_TRY(t, talloc(&a, B * t->L[l].cout * hw));
+      t->a.push_back(a);
+    }
+    t->nslots++;
+  }
+  return QGB_OK;
+}
+
 // forward pass; training = batch statistics (and running-statistics update), else running statistics folded into the epilogue
 int forward(qgb_trainer* t, const float* xd, int batch, bool training, cudaStream_t st) {
   const int hw = t->ny * t->nx;
@@ -183,31 +213,31 @@ int forward(qgb_trainer* t, const float* xd, int batch, bool training, cudaStrea
     int rc = pack(t, L, 0, st);
     if (rc) return rc;
     if (!L.bn) {
-      rc = conv(t, in, t->r[l], t->wp, t->P + L.b, t->ones, t->zeros, L.cin, L.cout, L.ks, 0, batch, st);
+      rc = conv(t, in, R(t, l), t->wp, t->P + L.b, t->ones, t->zeros, L.cin, L.cout, L.ks, 0, batch, st);
       if (rc) return rc;
-      in = t->r[l];
+      in = R(t, l);
     } else if (training) {
-      rc = conv(t, in, t->r[l], t->wp, t->P + L.b, t->ones, t->zeros, L.cin, L.cout, L.ks, 1, batch, st);
+      rc = conv(t, in, R(t, l), t->wp, t->P + L.b, t->ones, t->zeros, L.cin, L.cout, L.ks, 1, batch, st);
       if (rc) return rc;
-      rc = chan_reduce<0>(t, t->r[l], nullptr, nullptr, nullptr, batch, L.cout, st);
+      rc = chan_reduce<0>(t, R(t, l), nullptr, nullptr, nullptr, batch, L.cout, st);
       if (rc) return rc;
       bn_stats_final_kernel<<<(L.cout + 127) / 128, 128, 0, st>>>(t->red_part, L.cout, (double)batch * hw, t->bn_eps, t->bn_momentum,
-                                                                  t->mean + L.stat, t->invstd + L.stat, t->BUF + L.rm,
+                                                                  MEAN(t, L), INVSTD(t, L), t->BUF + L.rm,
                                                                   t->BUF + L.rm + L.cout, 1);
       const long long total = (long long)batch * L.cout * hw;
-      bn_apply_kernel<<<ew_blocks(total), 256, 0, st>>>(t->r[l], t->a[l], t->P + L.g, t->P + L.be, t->mean + L.stat, t->invstd + L.stat,
+      bn_apply_kernel<<<ew_blocks(total), 256, 0, st>>>(R(t, l), A(t, l), t->P + L.g, t->P + L.be, MEAN(t, L), INVSTD(t, L),
                                                         L.cout, hw, total);
       t->launches += 2;
       TR_TRY(t, cudaGetLastError());
-      in = t->a[l];
+      in = A(t, l);
     } else {
       bn_fold_kernel<<<(L.cout + 127) / 128, 128, 0, st>>>(t->P + L.g, t->P + L.be, t->BUF + L.rm, t->BUF + L.rm + L.cout, t->bn_eps,
                                                            L.cout, t->fold_s + L.stat, t->fold_t + L.stat);
       t->launches++;
       TR_TRY(t, cudaGetLastError());
-      rc = conv(t, in, t->a[l], t->wp, t->P + L.b, t->fold_s + L.stat, t->fold_t + L.stat, L.cin, L.cout, L.ks, 1, batch, st);
+      rc = conv(t, in, A(t, l), t->wp, t->P + L.b, t->fold_s + L.stat, t->fold_t + L.stat, L.cin, L.cout, L.ks, 1, batch, st);
       if (rc) return rc;
-      in = t->a[l];
+      in = A(t, l);
     }
   }
   return QGB_OK;
@@ -216,21 +246,22 @@ int forward(qgb_trainer* t, const float* xd, int batch, bool training, cudaStrea
 int loss_and_grad(qgb_trainer* t, const float* yd, int batch, bool want_grad, cudaStream_t st) {
   const auto& L = t->L.back();
   const long long n = (long long)batch * L.cout * t->ny * t->nx;
-  mse_loss_kernel<<<kLossBlocks, 256, 0, st>>>(t->r[t->nlayers - 1], yd, want_grad ? t->d[0] : nullptr, n, t->softplus, t->loss_part);
+  mse_loss_kernel<<<kLossBlocks, 256, 0, st>>>(R(t, t->nlayers - 1), yd, want_grad ? t->d[0] : nullptr, n, t->softplus, t->loss_part);
   loss_final_kernel<<<1, 32, 0, st>>>(t->loss_part, kLossBlocks, 1.0 / (double)n, t->loss);
   t->launches += 2;
   TR_TRY(t, cudaGetLastError());
   return QGB_OK;
 }
 
-// gradients of every parameter into t->G (same flat layout as the parameters); d[0] holds dL/dz of the last layer on entry
-int backward(qgb_trainer* t, const float* xd, int batch, cudaStream_t st) {
+// gradients of every parameter into t->G (same flat layout as the parameters); d[0] holds dL/dz of the last layer on entry.
+// dx (optional): gradient with respect to the network input, (batch, cin, ny, nx).
+int backward(qgb_trainer* t, const float* xd, int batch, cudaStream_t st, float* dx = nullptr) {
   const int hw = t->ny * t->nx;
   int cur = 0;
   for (int l = t->nlayers - 1; l >= 0; --l) {
     const auto& L = t->L[l];
     float* dz = t->d[cur];
-    const float* a_in = l == 0 ? xd : t->a[l - 1];
+    const float* a_in = l == 0 ? xd : A(t, l - 1);
     // bias gradient
     int rc = chan_reduce<2>(t, dz, nullptr, nullptr, nullptr, batch, L.cout, st);
     if (rc) return rc;
@@ -240,25 +271,59 @@ int backward(qgb_trainer* t, const float* xd, int batch, cudaStream_t st) {
     // weight gradient
     rc = wgrad(t, a_in, dz, t->G + L.w, L.cin, L.cout, L.ks, batch, st);
     if (rc) return rc;
-    if (l == 0) break;
+    if (l == 0 && !dx) break;
     // data gradient: the forward kernel on the flipped, transposed weights, no bias
     rc = pack(t, L, 1, st);
     if (rc) return rc;
-    float* da = t->d[cur ^ 1];
+    float* da = l == 0 ? dx : t->d[cur ^ 1];
     rc = conv(t, dz, da, t->wp, t->zeros, t->ones, t->zeros, L.cout, L.cin, L.ks, 0, batch, st);
     if (rc) return rc;
+    if (l == 0) break;
     // BatchNorm + ReLU backward of layer l - 1
     const auto& Lp = t->L[l - 1];
-    rc = chan_reduce<1>(t, da, t->r[l - 1], t->mean + Lp.stat, t->invstd + Lp.stat, batch, Lp.cout, st);
+    rc = chan_reduce<1>(t, da, R(t, l - 1), MEAN(t, Lp), INVSTD(t, Lp), batch, Lp.cout, st);
     if (rc) return rc;
     chan_final_kernel<<<(Lp.cout + 127) / 128, 128, 0, st>>>(t->red_part, Lp.cout, t->G + Lp.be, t->G + Lp.g);
     const long long total = (long long)batch * Lp.cout * hw;
-    bn_relu_bwd_kernel<<<ew_blocks(total), 256, 0, st>>>(da, t->r[l - 1], t->P + Lp.g, t->mean + Lp.stat, t->invstd + Lp.stat,
+    bn_relu_bwd_kernel<<<ew_blocks(total), 256, 0, st>>>(da, R(t, l - 1), t->P + Lp.g, MEAN(t, Lp), INVSTD(t, Lp),
                                                          t->G + Lp.g, t->G + Lp.be, Lp.cout, hw, 1.f / ((float)batch * hw), total);
     t->launches += 2;
     TR_TRY(t, cudaGetLastError());
     cur ^= 1;
   }
+  return QGB_OK;
+}
+
+int ensure_scratch(qgb_trainer* t, int i, size_t floats) {
+  if (t->scr_floats[i] >= floats) return QGB_OK;
+  if (t->scr[i]) cudaFree(t->scr[i]);
+  t->scr[i] = nullptr; t->scr_floats[i] = 0;
+  TR_TRY(t, talloc(&t->scr[i], floats));
+  t->scr_floats[i] = floats;
+  return QGB_OK;
+}
+int ensure_stats(qgb_trainer* t) {
+  if (!t->stats) TR_TRY(t, talloc(&t->stats, (size_t)kPartBlocks * 8 + 64));
+  return QGB_OK;
+}
+// host array -> device scratch i (or borrow the device pointer)
+int stage_into(qgb_trainer* t, int i, const float* src, size_t floats, int on_device, const float** out, cudaStream_t st) {
+  if (on_device) { *out = src; return QGB_OK; }
+  int rc = ensure_scratch(t, i, floats);
+  if (rc) return rc;
+  TR_TRY(t, cudaMemcpyAsync(t->scr[i], src, floats * sizeof(float), cudaMemcpyHostToDevice, st));
+  *out = t->scr[i];
+  return QGB_OK;
+}
+
+// one Adam update of every parameter from t->G
+int adam_update(qgb_trainer* t, double lr, cudaStream_t st) {
+  t->adam_t += 1;
+  const double bc1 = 1.0 - std::pow((double)t->beta1, (double)t->adam_t), bc2 = 1.0 - std::pow((double)t->beta2, (double)t->adam_t);
+  adam_kernel<<<ew_blocks((long long)t->nparams), 256, 0, st>>>(t->P, t->G, t->M, t->V, (long long)t->nparams, (float)lr, t->beta1,
+                                                                t->beta2, t->adam_eps, (float)bc1, (float)std::sqrt(bc2));
+  t->launches++;
+  TR_TRY(t, cudaGetLastError());
   return QGB_OK;
 }
 
@@ -304,7 +369,7 @@ int qgb_train_create(int device, int nlayers, const int32_t* channels, const int
   const size_t hw = (size_t)ny * nx, B = max_batch;
   CR(talloc(&t->P, t->nparams)); CR(talloc(&t->G, t->nparams)); CR(talloc(&t->M, t->nparams)); CR(talloc(&t->V, t->nparams));
   CR(talloc(&t->BUF, t->nbuffers));
-  CR(talloc(&t->mean, t->nstat)); CR(talloc(&t->invstd, t->nstat)); CR(talloc(&t->fold_s, t->nstat)); CR(talloc(&t->fold_t, t->nstat));
+  CR(talloc(&t->mean, t->nstat * kMaxSlots)); CR(talloc(&t->invstd, t->nstat * kMaxSlots)); CR(talloc(&t->fold_s, t->nstat)); CR(talloc(&t->fold_t, t->nstat));
   CR(talloc(&t->ones, (size_t)maxc)); CR(talloc(&t->zeros, (size_t)maxc));
   CR(talloc(&t->x, B * channels[0] * hw)); CR(talloc(&t->t, B * channels[nlayers] * hw));
   for (int l = 0; l < nlayers; ++l) {
@@ -331,9 +396,11 @@ int qgb_train_create(int device, int nlayers, const int32_t* channels, const int
 void qgb_train_destroy(qgb_trainer* t) {
   if (!t) return;
   cudaSetDevice(t->device);
-  for (float* p : {t->P, t->G, t->M, t->V, t->BUF, t->mean, t->invstd, t->fold_s, t->fold_t, t->ones, t->zeros, t->x, t->t, t->d[0],
+  for (float* p : {t->Gacc, t->P, t->G, t->M, t->V, t->BUF, t->mean, t->invstd, t->fold_s, t->fold_t, t->ones, t->zeros, t->x, t->t, t->d[0],
                    t->d[1], t->wp, t->wg_part})
     if (p) cudaFree(p);
+  for (float* p : t->scr) if (p) cudaFree(p);
+  if (t->stats) cudaFree(t->stats);
   for (float* p : t->r) if (p) cudaFree(p);
   for (float* p : t->a) if (p) cudaFree(p);
   if (t->red_part) cudaFree(t->red_part);
@@ -379,12 +446,7 @@ int qgb_train_step(qgb_trainer* t, const float* x, const float* y, int batch, in
   if ((rc = forward(t, xd, batch, true, st))) return rc;
   if ((rc = loss_and_grad(t, yd, batch, true, st))) return rc;
   if ((rc = backward(t, xd, batch, st))) return rc;
-  t->adam_t += 1;
-  const double bc1 = 1.0 - std::pow((double)t->beta1, (double)t->adam_t), bc2 = 1.0 - std::pow((double)t->beta2, (double)t->adam_t);
-  adam_kernel<<<ew_blocks((long long)t->nparams), 256, 0, st>>>(t->P, t->G, t->M, t->V, (long long)t->nparams, (float)lr, t->beta1,
-                                                                t->beta2, t->adam_eps, (float)bc1, (float)std::sqrt(bc2));
-  t->launches++;
-  TR_TRY(t, cudaGetLastError());
+  if ((rc = adam_update(t, lr, st))) return rc;
   if (loss) {
     TR_TRY(t, cudaMemcpyAsync(loss, t->loss, sizeof(double), cudaMemcpyDeviceToHost, st));
     TR_TRY(t, cudaStreamSynchronize(st));
@@ -426,6 +488,74 @@ int qgb_train_eval_loss(qgb_trainer* t, const float* x, const float* y, int batc
   if ((rc = forward(t, xd, batch, false, st))) return rc;
   if ((rc = loss_and_grad(t, yd, batch, false, st))) return rc;
   TR_TRY(t, cudaMemcpyAsync(loss, t->loss, sizeof(double), cudaMemcpyDeviceToHost, st));
+  TR_TRY(t, cudaStreamSynchronize(st));
+  return QGB_OK;
+}
+
+int qgb_train_get_grads(qgb_trainer* t, float* grads) {
+  if (!t || !grads) return QGB_EINVAL;
+  TR_TRY(t, cudaSetDevice(t->device));
+  TR_TRY(t, cudaDeviceSynchronize());
+  TR_TRY(t, cudaMemcpy(grads, t->G, t->nparams * sizeof(float), cudaMemcpyDeviceToHost));
+  return QGB_OK;
+}
+
+int qgb_train_set_adam(qgb_trainer* t, double beta1, double beta2) {
+  if (!t || !(beta1 >= 0.0 && beta1 < 1.0) || !(beta2 >= 0.0 && beta2 < 1.0)) return tfail(t, QGB_EINVAL, "betas must lie in [0, 1)");
+  t->beta1 = (float)beta1; t->beta2 = (float)beta2;
+  return QGB_OK;
+}
+
+int qgb_train_cvae_step(qgb_trainer* enc, qgb_trainer* dec, const float* x, const float* y, const float* eps, int batch,
+                        int on_device, double lr, double decoder_var, int update, double* losses, void* stream) {
+  if (!enc || !dec) return QGB_EINVAL;
+  qgb_trainer* t = enc;
+  if (!x || !y || !eps) return tfail(t, QGB_EINVAL, "null minibatch");
+  if (enc->L.front().cin != 4 || enc->L.back().cout != 4 || dec->L.front().cin != 4 || dec->L.back().cout != 2)
+    return tfail(t, QGB_EINVAL, "expected an encoder 4 -> 4 ([x, y] -> [mu, logvar]) and a decoder 4 -> 2 ([x, z] -> y)");
+  if (enc->ny != dec->ny || enc->nx != dec->nx || enc->device != dec->device) return tfail(t, QGB_EINVAL, "encoder and decoder differ in grid or device");
+  if (batch < 1 || batch > enc->max_batch || batch > dec->max_batch) return tfail(t, QGB_EINVAL, "batch %d outside 1..max_batch", batch);
+  if (enc->softplus || dec->softplus) return tfail(t, QGB_EINVAL, "softplus heads are not part of the CVAE");
+  cudaStream_t st = (cudaStream_t)stream;
+  TR_TRY(t, cudaSetDevice(t->device));
+  const int hw = t->ny * t->nx;
+  const size_t f2 = (size_t)batch * 2 * hw, f4 = (size_t)batch * 4 * hw;
+  const float *xd, *yd, *ed;
+  int rc;
+  if ((rc = stage_into(t, 0, x, f2, on_device, &xd, st))) return rc;
+  if ((rc = stage_into(t, 1, y, f2, on_device, &yd, st))) return rc;
+  if ((rc = stage_into(t, 2, eps, f2, on_device, &ed, st))) return rc;
+  if ((rc = ensure_scratch(t, 3, f4)) || (rc = ensure_scratch(t, 4, f4)) || (rc = ensure_scratch(t, 5, f4)) || (rc = ensure_stats(t))) return rc;
+  float *encin = t->scr[3], *decin = t->scr[4], *ddecin = t->scr[5];
+  enc->slot = dec->slot = 0;
+  // encoder on cat[x, y]
+  cat_channels_kernel<<<ew_blocks((long long)f2), 256, 0, st>>>(xd, 2, encin, 4, 0, hw, (long long)f2);
+  cat_channels_kernel<<<ew_blocks((long long)f2), 256, 0, st>>>(yd, 2, encin, 4, 2, hw, (long long)f2);
+  t->launches += 2;
+  if ((rc = forward(enc, encin, batch, true, st))) return rc;
+  const float* encout = R(enc, enc->nlayers - 1);
+  // z = eps std + mu ; decoder on cat[x, z]
+  cvae_reparam_kernel<<<ew_blocks((long long)f2), 256, 0, st>>>(xd, encout, ed, decin, hw, (long long)f2);
+  t->launches++;
+  if ((rc = forward(dec, decin, batch, true, st))) { enc->err = dec->err; return rc; }
+  const float* yhat = R(dec, dec->nlayers - 1);
+  // losses and d loss / d yhat
+  cvae_loss_partial_kernel<<<kPartBlocks, 256, 0, st>>>(yhat, yd, encout, hw, (long long)f2, t->stats + 64);
+  cvae_loss_final_kernel<<<1, 32, 0, st>>>(t->stats + 64, kPartBlocks, (double)f2, (double)batch, decoder_var, t->stats);
+  cvae_dyhat_kernel<<<ew_blocks((long long)f2), 256, 0, st>>>(yhat, yd, t->stats, dec->d[0], (long long)f2);
+  t->launches += 3;
+  TR_TRY(t, cudaGetLastError());
+  // decoder backward down to its input, encoder backward
+  if ((rc = backward(dec, decin, batch, st, ddecin))) { enc->err = dec->err; return rc; }
+  cvae_denc_kernel<<<ew_blocks((long long)f2), 256, 0, st>>>(ddecin, encout, ed, enc->d[0], 1.f / (float)batch, hw, (long long)f2);
+  t->launches++;
+  TR_TRY(t, cudaGetLastError());
+  if ((rc = backward(enc, encin, batch, st))) return rc;
+  if (update) {
+    if ((rc = adam_update(enc, lr, st))) return rc;
+    if ((rc = adam_update(dec, lr, st))) { enc->err = dec->err; return rc; }
+  }
+  if (losses) TR_TRY(t, cudaMemcpyAsync(losses, t->stats, 6 * sizeof(double), cudaMemcpyDeviceToHost, st));
   TR_TRY(t, cudaStreamSynchronize(st));
   return QGB_OK;
 }

@@ -340,15 +340,48 @@ class Trainer(object):
                                                        ctypes.byref(loss), None), self._h)
         return loss.value
 
+    def last_grads(self):
+        """Gradients left by the last backward pass (``qgb_train_get_grads``), keyed like ``net.named_parameters()``."""
+        g = np.empty(self.nparams, 'float32')
+        _lib.check_train(self._lib.qgb_train_get_grads(self._h, g.ctypes.data), self._h)
+        return self._unflat(g, self.net.parameter_names())
+
+    def set_adam(self, beta1, beta2):
+        _lib.check_train(self._lib.qgb_train_set_adam(self._h, float(beta1), float(beta2)), self._h)
+
     def launch_count(self):
         return int(self._lib.qgb_train_launch_count(self._h))
 
 
-def multistep_lr(learning_rate, num_epochs, epoch):
-    """Learning rate of ``epoch`` (0-based) under MultiStepLR(milestones=[E/2, 3E/4, 7E/8], gamma=0.1) stepped once per
-    epoch (cnn_tools.py:672-673,691); coinciding milestones multiply, as torch's Counter-based scheduler does."""
+def multistep_lr(learning_rate, num_epochs, epoch, gamma=0.1):
+    """Learning rate of ``epoch`` (0-based) under MultiStepLR(milestones=[E/2, 3E/4, 7E/8], gamma) stepped once per
+    epoch (cnn_tools.py:672-673,691; gamma = 0.5 in train_CGAN, cgan_regression.py:248-251); coinciding milestones multiply,
+    as torch's Counter-based scheduler does."""
     counts = collections.Counter([int(num_epochs / 2), int(num_epochs * 3 / 4), int(num_epochs * 7 / 8)])
-    return learning_rate * 0.1 ** sum(c for m, c in counts.items() if 0 < m <= epoch)
+    return learning_rate * gamma ** sum(c for m, c in counts.items() if 0 < m <= epoch)
+
+
+class AverageLoss(object):
+    """cnn_tools.py:555-600: sample-weighted epoch means of a dict of losses, appended to ``log_dict`` lists."""
+
+    def __init__(self, log_dict):
+        self.init_me = True
+        self.count = {}
+
+    def accumulate(self, log_dict, losses, n):
+        if self.init_me:
+            for key in losses:
+                log_dict.setdefault(key, [])
+                self.count[key] = 0
+                log_dict[key].append(0.)
+            self.init_me = False
+        for key, value in losses.items():
+            log_dict[key][-1] += float(value) * n
+            self.count[key] += n
+
+    def average(self, log_dict):
+        for key in self.count:
+            log_dict[key][-1] = log_dict[key][-1] / self.count[key]
 
 
 def evaluate_test(net, *arrays, batch_size=64, postfix='_test', device=None, trainer=None):

@@ -21,6 +21,8 @@ samplers.npz       AR1 / constant sampler sequences
 ispec.npz          calc_ispec (tools/spectral_tools.py:103-180) of seeded spectra at nx = 48, 64 for every option combination
 initial_condition.npz  set_initial_condition (tools/simulate.py:147-168) under np.random.seed for nx = 48, 64, 96 (two
                    successive members each)
+training_cvae.npz  CVAERegression.compute_loss (ELBO, adaptive and fixed decoder variance) losses and autograd gradients of a small
+                   encoder / decoder pair with the recorded reparameterisation noise, and a whole ``train_CVAE`` run (4 epochs, batch 8)
 training.npz       the reference's training arithmetic on a small AndrewCNN (2 -> 16 -> 12 -> 12 -> 8 -> 2, 16 x 16 images):
                    loss and autograd gradients of ``compute_loss`` in training mode for AndrewCNN and VarCNN (softplus head),
                    BatchNorm running statistics after that forward, and a whole ``cnn_tools.train`` run (4 epochs, batch 8,
@@ -294,7 +296,77 @@ def training_fixture():
     np.savez_compressed(os.path.join(HERE, 'training.npz'), **out)
 
 
+def _small_cvae(decoder_var='adaptive'):
+    tmp = tempfile.mkdtemp()
+    net = CVAERegression(folder=tmp, hidden_channels=TRAIN_HIDDEN, decoder_var=decoder_var)
+    net.encoder = cnn_tools.AndrewCNN(4, 4, hidden_channels=TRAIN_HIDDEN)      # a small encoder keeps the fixture small
+    shutil.rmtree(tmp, ignore_errors=True)
+    return net
+
+
+def cvae_fixture():
+    """models/cvae_regression.py:165-230 ``forward`` / ``compute_loss`` and :250-300 ``train_CVAE`` run as they are (CPU torch, fp32)
+    on a small encoder / decoder pair; the reparameterisation draws (``torch.randn_like``) are recorded so that the device trainer can
+    be fed the same noise."""
+    from pyqg_generative.models import cvae_regression as ref_cvae
+    out = {}
+    rng = np.random.RandomState(21)
+    x = rng.randn(6, 2, 16, 16).astype('float32')
+    y = (0.5 * np.roll(x, 1, axis=-1) + 0.3 * rng.randn(6, 2, 16, 16)).astype('float32')
+    out['grad_x'], out['grad_y'] = x, y
+    drawn = []
+    real_randn_like = torch.randn_like
+
+    def recording_randn_like(t, *a, **k):
+        r = real_randn_like(t, *a, **k)
+        drawn.append(r.numpy().copy())
+        return r
+    torch.randn_like = recording_randn_like
+    try:
+        for tag, dv in (('adaptive', 'adaptive'), ('fixed01', 0.1)):
+            torch.manual_seed(5)
+            net = _small_cvae(dv)
+            for name, sub in (('enc', net.encoder), ('dec', net.decoder)):
+                for k, v in sub.state_dict().items():
+                    out['%s_%s_init/%s' % (tag, name, k)] = v.numpy().copy()
+            net.encoder.train(); net.decoder.train()
+            del drawn[:]
+            losses = net.compute_loss(torch.as_tensor(x), torch.as_tensor(y), 0 * torch.as_tensor(y))
+            losses['loss'].backward()
+            out['%s_eps' % tag] = drawn[0]
+            out['%s_losses' % tag] = np.array([float(losses[k]) for k in
+                                               ('loss', 'loss_recon', 'loss_KL', 'MSE', 'var_latent', 'var_aggr')])
+            for name, sub in (('enc', net.encoder), ('dec', net.decoder)):
+                for k, p_ in sub.named_parameters():
+                    out['%s_%s_grad/%s' % (tag, name, k)] = p_.grad.numpy().copy()
+        # a whole train_CVAE run (the per-epoch offline scores need datasets: replaced by a stub, they do not feed back)
+        X_train = rng.randn(20, 2, 16, 16).astype('float32')
+        Y_train = (0.5 * np.roll(X_train, 1, axis=-1) + 0.3 * rng.randn(20, 2, 16, 16)).astype('float32')
+        torch.manual_seed(6)
+        net = _small_cvae('adaptive')
+        for name, sub in (('enc', net.encoder), ('dec', net.decoder)):
+            for k, v in sub.state_dict().items():
+                out['run_%s_init/%s' % (name, k)] = v.numpy().copy()
+        ref_cvae.evaluate_prediction = lambda *a, **k: dict(L2_mean=0., L2_total=0., L2_residual=0., var_ratio=[0., 0.])
+        del drawn[:]
+        np.random.seed(0)
+        optim_loss, _, _ = ref_cvae.train_CVAE(net, None, None, X_train, Y_train, num_epochs=4, batch_size=8, learning_rate=1e-3)
+        out['run_eps'] = np.concatenate([d.reshape(-1) for d in drawn])
+        for name, sub in (('enc', net.encoder), ('dec', net.decoder)):
+            for k, v in sub.state_dict().items():
+                out['run_%s_final/%s' % (name, k)] = v.numpy().copy()
+        for k, v in optim_loss.items():
+            out['run_log/%s' % k] = np.array(v, dtype=np.float64)
+        out.update(X_train=X_train, Y_train=Y_train)
+    finally:
+        torch.randn_like = real_randn_like
+    np.savez_compressed(os.path.join(HERE, 'training_cvae.npz'), **out)
+
+
 if __name__ == '__main__':
+    if '--cvae' in sys.argv:
+        cvae_fixture()
+        sys.exit(0)
     if '--only-new' in sys.argv:       # fixtures added in round 2 (the others are unchanged)
         ispec_fixture()
         initial_condition_fixture()
@@ -315,5 +387,6 @@ if __name__ == '__main__':
     ispec_fixture()
     initial_condition_fixture()
     training_fixture()
+    cvae_fixture()
     for f in sorted(os.listdir(HERE)):
         print('%10d  %s' % (os.path.getsize(os.path.join(HERE, f)), f))

@@ -167,3 +167,95 @@ def test_trainer_rejects_bad_input():
     with pytest.raises(ValueError):
         tr.step(np.zeros((2, 2, 8, 16), 'float32'), np.zeros((2, 2, 8, 16), 'float32'), 1e-3)       # wrong grid
     tr.close()
+
+
+# ---- CVAE (ELBO) -----------------------------------------------------------------------------------------------------------
+def make_cvae(g, prefix, decoder_var='adaptive'):
+    from pyqg_generative_b200.models.cvae_regression import CVAERegression
+    from pyqg_generative_b200.tools.cnn_tools import AndrewCNN
+    net = CVAERegression(folder='/nonexistent', hidden_channels=HIDDEN, decoder_var=decoder_var)
+    net.encoder = AndrewCNN(4, 4, hidden_channels=HIDDEN)          # like tests/golden/make_golden.py:_small_cvae
+    net.encoder.load_state_dict(sd_of(g, prefix + '_enc_init'))
+    net.decoder.load_state_dict(sd_of(g, prefix + '_dec_init'))
+    return net
+
+
+@pytest.mark.parametrize('tag,dv', [('adaptive', 'adaptive'), ('fixed01', 0.1)])
+def test_cvae_elbo_gradients_match_reference_autograd(tag, dv):
+    """qgb_train_cvae_step against CVAERegression.compute_loss + autograd of the unmodified reference
+    (models/cvae_regression.py:165-230) with the recorded reparameterisation noise: six losses and every gradient."""
+    from pyqg_generative_b200.models.cvae_regression import CVAETrainer, LOSS_KEYS
+    g = golden('training_cvae.npz')
+    net = make_cvae(g, tag, dv)
+    tr = CVAETrainer(net, 16, 16, max_batch=8)
+    losses = tr.step(g['grad_x'], g['grad_y'], 0.0, eps=g[tag + '_eps'], update=False)
+    ref = g[tag + '_losses']
+    for k, r in zip(LOSS_KEYS, ref):
+        assert abs(losses[k] - r) < 2e-5 * abs(r), (k, losses[k], r)
+    worst = 0.0
+    for name, t in (('enc', tr.enc), ('dec', tr.dec)):
+        grads = t.last_grads()
+        for k, r in sd_of(g, '%s_%s_grad' % (tag, name)).items():
+            e = rel(grads[k], r.numpy())
+            worst = max(worst, e)
+            assert e < GRAD_TOL, (name, k, e)
+    assert worst < 3e-4, worst
+    tr.close()
+
+
+def test_cvae_train_run_matches_reference():
+    """train_CVAE (models/cvae_regression.py:250-300; 4 epochs, batch 8, Adam over encoder + decoder, MultiStepLR) from the same
+    initial weights, np.random shuffling and reparameterisation draws: loss logs and trained weights."""
+    from pyqg_generative_b200.models.cvae_regression import train_CVAE
+    g = golden('training_cvae.npz')
+    net = make_cvae(g, 'run')
+    eps_all, pos = g['run_eps'], [0]
+
+    def noise(shape):
+        n = int(np.prod(shape))
+        out = eps_all[pos[0]:pos[0] + n].reshape(shape)
+        pos[0] += n
+        return out
+    np.random.seed(0)
+    optim_loss, _, _ = train_CVAE(net, None, None, g['X_train'], g['Y_train'], num_epochs=4, batch_size=8, learning_rate=1e-3,
+                                  evaluate=False, noise=noise)
+    assert pos[0] == eps_all.size
+    for k in ('loss', 'loss_recon', 'loss_KL', 'MSE', 'var_latent', 'var_aggr'):
+        assert np.allclose(optim_loss[k], g['run_log/' + k], rtol=1e-3), (k, optim_loss[k], g['run_log/' + k])
+    for name, sub in (('enc', net.encoder), ('dec', net.decoder)):
+        final = sub.state_dict()
+        for k, r in sd_of(g, 'run_%s_final' % name).items():
+            if k.endswith('num_batches_tracked'):
+                assert int(final[k]) == int(r), (name, k)
+            else:
+                assert rel(final[k].numpy(), r.numpy()) < 2e-3, (name, k, rel(final[k].numpy(), r.numpy()))
+
+
+def test_cvae_fit_writes_reference_files(tmp_path):
+    """CVAERegression.fit (:53-91) end to end on a tiny dataset: per-epoch offline scores, files in the reference's formats, and
+    a reload that serves the same predictions."""
+    from pyqg_generative_b200.models.cvae_regression import CVAERegression
+    rng = np.random.RandomState(4)
+
+    def dataset(nrun):
+        q = rng.randn(nrun, 3, 2, 16, 16) * np.array([7e-6, 1e-6])[None, None, :, None, None]
+        s = 1e-6 * (np.roll(q, 1, axis=-1) - q) * (1 + 0.5 * rng.randn(*q.shape))
+        return {'q': q, 'q_forcing_advection': s}
+    ds_train, ds_test = dataset(6), dataset(3)
+    folder = str(tmp_path / 'vae')
+    model = CVAERegression(folder=folder, hidden_channels=[16, 8])
+    np.random.seed(5)
+    model.fit(ds_train, ds_test, num_epochs=3, batch_size=8, learning_rate=1e-3, nruns=2)
+    for f in ('encoder.pt', 'decoder.pt', 'x_scale.json', 'y_scale.json', 'model_args.json', 'stats.nc'):
+        assert (tmp_path / 'vae' / f).exists(), f
+    from scipy.io import netcdf_file
+    with netcdf_file(str(tmp_path / 'vae' / 'stats.nc'), 'r', mmap=False) as f:
+        for k in ('loss', 'loss_KL', 'MSE', 'L2_mean', 'L2_total_test', 'L2_loss', 'Epoch_opt'):
+            assert f.variables[k].shape == (3,), k
+        assert np.isfinite(f.variables['loss'][:]).all()
+    again = CVAERegression(folder=folder, hidden_channels=[16, 8])
+    for k, v in model.encoder.state_dict().items():
+        assert torch.equal(again.encoder.state_dict()[k], v), k
+    z = np.random.RandomState(0).randn(1, 2, 16, 16).astype('float32')
+    m = type('M', (), dict(q=ds_test['q'][0, 0]))()
+    assert np.array_equal(model.predict_snapshot(m, z), again.predict_snapshot(m, z))
