@@ -268,6 +268,39 @@ int qgb_train_set_adam(qgb_trainer* t, double beta1, double beta2);
 int qgb_train_cvae_step(qgb_trainer* enc, qgb_trainer* dec, const float* x, const float* y, const float* eps, int batch,
                         int on_device, double lr, double decoder_var, int update, double* losses, void* stream);
 
+/* ---- CGAN: the discriminator and one iteration of train_CGAN (models/cgan_regression.py:227-300) -------------------
+ * qgb_disc = DCGAN_discriminator(in_channels = 6, ndf, nx, bn = 'None') (tools/cnn_tools.py:212-244): four 4 x 4 / stride 2 /
+ * zero-pad 1 convolutions (in_channels -> ndf -> 2 ndf -> 4 ndf -> 8 ndf) each followed by LeakyReLU(0.2), then an
+ * (nx/16) x (nx/16) valid convolution to one number per sample; no biases.  Flat parameter layout: the five weights
+ * (cout, cin, k, k) in order -- the order of ``D.parameters()`` (state_dict keys 0.weight, 2.weight, 5.weight, 8.weight,
+ * 11.weight).  Adam with betas (0.5, 0.999) (:246).  max_batch = the minibatch size B (the object holds 4 B samples). */
+typedef struct qgb_disc qgb_disc;
+int qgb_disc_create(int device, int in_channels, int ndf, int nx, int max_batch, qgb_disc** out);
+void qgb_disc_destroy(qgb_disc* d);
+const char* qgb_disc_last_error(const qgb_disc* d);     /* d may be NULL: last error of a failed qgb_disc_create */
+int64_t qgb_disc_num_params(const qgb_disc* d);
+int64_t qgb_disc_launch_count(const qgb_disc* d);
+int qgb_disc_set_params(qgb_disc* d, const float* params, int reset_optimizer);        /* host pointer */
+int qgb_disc_get_params(qgb_disc* d, float* params, float* grads);                      /* host pointers, either may be NULL */
+/* D(x): x float (batch, 6, nx, nx), batch <= 4 max_batch -> out float (batch) */
+int qgb_disc_forward(qgb_disc* d, const float* x, int batch, int on_device, float* out, void* stream);
+/* One iteration of the loop at cgan_regression.py:256-292 (regression = 'None'):
+ *   yfake1 = G(x, z1), yfake2 = G(x, z2) (training mode: batch statistics, two running-statistics updates);
+ *   D_loss = -0.5 (mean D(x, y, yfake2) + mean D(x, yfake1, y)) + mean D(x, yfake1, yfake2);  D_drift = 1e-3 mean D(x, y, yfake2)^2;
+ *   D_grad = 10 mean_b (|dD/dy (x, yinterp)|_2 - 1)^2 with yinterp = eps ytrue_cat + (1 - eps) yfake_cat, ytrue_cat = (y, yfake2)
+ *   if coin == 0 else (yfake1, y) (gradient_penalty :173-195; its second-order term is evaluated exactly: D is piecewise
+ *   linear, so d D_grad / d W = the weight gradient of the linearised network driven by d D_grad / d(dD/dy));
+ *   (D_loss + D_grad + D_drift).backward(); optimizerD.step()  [update_d != 0, learning rate lr_d];
+ *   g_mode 1 / 2: G_loss = -mean D(x, yfake1, yfake2) with the discriminator as it now is, backward through D and both
+ *   generator passes; g_mode 2 also applies optimizerG.step() (lr_g) -- the reference does this every 5th iteration (:277).
+ * G: qgb_trainer of the generator AndrewCNN 4 -> 2 (set its betas with qgb_train_set_adam(G, 0.5, 0.999)).
+ * x, y, z1, z2: float (batch, 2, ny, nx), host or device (on_device); eps: HOST array of batch floats (torch.rand(B,1,1,1), :176);
+ * coin: np.random.randint(0, 2) (:178).  losses (host, 4 doubles, may be NULL) = D_loss, D_grad, D_drift, G_loss (G_loss only
+ * when g_mode != 0).  Gradients: qgb_disc_get_params(.., grads) and qgb_train_get_grads(G, ..). */
+int qgb_train_cgan_step(qgb_trainer* G, qgb_disc* D, const float* x, const float* y, const float* z1, const float* z2,
+                        const float* eps, int coin, int batch, int on_device, double lr_d, double lr_g, int update_d, int g_mode,
+                        double* losses, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -90,6 +90,15 @@ SYMBOLS = {
     'qgb_train_set_adam': (_i, [_vp, _d, _d]),
     # CVAE / CGAN training steps (models/cvae_regression.py:250-300, models/cgan_regression.py:227-300)
     'qgb_train_cvae_step': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _d, _d, _i, ctypes.POINTER(_d), _vp]),
+    'qgb_disc_create': (_i, [_i, _i, _i, _i, _i, ctypes.POINTER(_vp)]),
+    'qgb_disc_destroy': (None, [_vp]),
+    'qgb_disc_last_error': (ctypes.c_char_p, [_vp]),
+    'qgb_disc_num_params': (ctypes.c_int64, [_vp]),
+    'qgb_disc_launch_count': (ctypes.c_int64, [_vp]),
+    'qgb_disc_set_params': (_i, [_vp, _vp, _i]),
+    'qgb_disc_get_params': (_i, [_vp, _vp, _vp]),
+    'qgb_disc_forward': (_i, [_vp, _vp, _i, _i, _vp, _vp]),
+    'qgb_train_cgan_step': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _d, _d, _i, _i, ctypes.POINTER(_d), _vp]),
 }
 
 _lib = None
@@ -132,6 +141,18 @@ def check_train(rc, trainer=None):
     if rc == QGB_OK:
         return
     msg = load().qgb_train_last_error(trainer)
+    msg = msg.decode() if msg else 'error %d' % rc
+    if rc == QGB_EINVAL:
+        raise ValueError(msg)
+    if rc == QGB_EUNSUPPORTED:
+        raise NotImplementedError(msg)
+    raise QgbError(msg)
+
+
+def check_disc(rc, disc=None):
+    if rc == QGB_OK:
+        return
+    msg = load().qgb_disc_last_error(disc)
     msg = msg.decode() if msg else 'error %d' % rc
     if rc == QGB_EINVAL:
         raise ValueError(msg)

@@ -120,5 +120,260 @@ __global__ void axpy_kernel(float* __restrict__ y, const float* __restrict__ x, 
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) y[i] += a * x[i];
 }
 
+// ---- discriminator (DCGAN_discriminator, bn = 'None') --------------------------------------------------------------------
+// Activations are NHWC, (sample, y, x, channel), so that every convolution is one GEMM on an im2col matrix
+//   col[(b, oy, ox)][(ky, kx, ci)]        M = B OH^2 rows, K = 16 C columns (4 x 4 taps, stride 2, zero padding 1)
+// against the packed weights Wp[co][(ky, kx, ci)]: forward  z = col Wp^T,  data gradient  dcol = dz Wp,  weight gradient
+// dWp = dz^T col.  The last layer (k5 x k5 valid convolution of the k5 x k5 map) is the same GEMM on the activation itself.
+
+constexpr int kGemmTile = 64, kGemmK = 16;
+
+// C[i][j] (+ epilogue) = sum_k A(i, k) B(k, j),  A(i, k) = A[i sai + k sak],  B(k, j) = B[k sbk + j sbj].
+// blockIdx.z splits the k range into chunks of ksplit (partial results at C + z c_split); EPI 0: none, 1: LeakyReLU(0.2),
+// 2: times the LeakyReLU slope of mask[i ldc + j] (1 where mask > 0, else 0.2).
+template <int EPI>
+__global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A, long long sai, long long sak,
+                                                    const float* __restrict__ B, long long sbk, long long sbj, float* __restrict__ C,
+                                                    long long ldc, int M, int N, int K, int ksplit, long long c_split,
+                                                    const float* __restrict__ mask) {
+  __shared__ float As[kGemmK][kGemmTile + 4];
+  __shared__ float Bs[kGemmK][kGemmTile + 4];
+  const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+  const int i0 = blockIdx.y * kGemmTile, j0 = blockIdx.x * kGemmTile;
+  const int kbeg = blockIdx.z * ksplit, kend = min(K, kbeg + ksplit);
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+  const bool a_kfast = sak == 1, b_kfast = sbk == 1;
+  for (int k0 = kbeg; k0 < kend; k0 += kGemmK) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      int i, k;
+      if (a_kfast) { k = tid % 16; i = tid / 16 + 16 * r; } else { i = tid % 64; k = tid / 64 + 4 * r; }
+      const int gi = i0 + i, gk = k0 + k;
+      As[k][i] = (gi < M && gk < kend) ? A[gi * sai + gk * sak] : 0.f;
+      int j, kb;
+      if (b_kfast) { kb = tid % 16; j = tid / 16 + 16 * r; } else { j = tid % 64; kb = tid / 64 + 4 * r; }
+      const int gj = j0 + j, gkb = k0 + kb;
+      Bs[kb][j] = (gj < N && gkb < kend) ? B[gkb * sbk + gj * sbj] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kGemmK; ++k) {
+      const float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float a4[4] = {av.x, av.y, av.z, av.w}, b4[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(a4[a], b4[b], acc[a][b]);
+    }
+    __syncthreads();
+  }
+  float* Cz = C + (long long)blockIdx.z * c_split;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int gi = i0 + ty * 4 + a;
+    if (gi >= M) continue;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int gj = j0 + tx * 4 + b;
+      if (gj >= N) continue;
+      float v = acc[a][b];
+      if (EPI == 1) v = v > 0.f ? v : 0.2f * v;
+      if (EPI == 2) v *= mask[gi * ldc + gj] > 0.f ? 1.f : 0.2f;
+      Cz[gi * ldc + gj] = v;
+    }
+  }
+}
+
+// (cout, cin, ks, ks) -> Wp[co][(ky, kx, ci)]  (dir 0)  or the same permutation back (dir 1: packed gradient -> torch layout,
+// summing ``splits`` partial results ``stride`` floats apart)
+__global__ void disc_pack_kernel(const float* __restrict__ src, float* __restrict__ dst, int cout, int cin, int ks, int dir,
+                                 int splits, long long stride) {
+  const long long n = (long long)cout * cin * ks * ks;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int kx = (int)(i % ks), ky = (int)((i / ks) % ks), ci = (int)((i / (ks * ks)) % cin), co = (int)(i / ((long long)ks * ks * cin));
+    const long long ip = ((long long)co * ks * ks + ky * ks + kx) * cin + ci;
+    if (dir == 0) dst[ip] = src[i];
+    else {
+      float s = 0.f;
+      for (int k = 0; k < splits; ++k) s += src[k * stride + ip];
+      dst[i] = s;
+    }
+  }
+}
+
+// im2col of a 4 x 4 / stride 2 / pad 1 convolution, NHWC.  Samples [0, b_split) come from src0, the rest from src1 (sample
+// b - b_split): the weight gradient runs one GEMM over the ordinary samples and the linearised ones of the gradient penalty.
+__global__ void im2col_kernel(const float* __restrict__ src0, const float* __restrict__ src1, int b_split, float* __restrict__ col,
+                              int B, int H, int C, int OH) {
+  const long long total = (long long)B * OH * OH * 16 * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C), kk = (int)((i / C) % 16);
+    const long long m = i / (16LL * C);
+    const int ox = (int)(m % OH), oy = (int)((m / OH) % OH), b = (int)(m / ((long long)OH * OH));
+    const int iy = oy * 2 - 1 + kk / 4, ix = ox * 2 - 1 + kk % 4;
+    float v = 0.f;
+    if (iy >= 0 && iy < H && ix >= 0 && ix < H) {
+      const float* s = b < b_split ? src0 + (long long)b * H * H * C : src1 + (long long)(b - b_split) * H * H * C;
+      v = s[((long long)iy * H + ix) * C + c];
+    }
+    col[i] = v;
+  }
+}
+
+// transpose of im2col as a gather (deterministic): din[b][iy][ix][c] = sum of the <= 4 col entries that read this input pixel,
+// times the LeakyReLU slope of mask (the activation this gradient flows into; nullptr = none)
+__global__ void col2im_kernel(const float* __restrict__ dcol, float* __restrict__ din, const float* __restrict__ mask, int B, int H,
+                              int C, int OH) {
+  const long long total = (long long)B * H * H * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C), ix = (int)((i / C) % H), iy = (int)((i / ((long long)C * H)) % H), b = (int)(i / ((long long)C * H * H));
+    float s = 0.f;
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int ky = ((iy + 1) & 1) + 2 * a, oy = (iy + 1 - ky) / 2;
+      if (iy + 1 - ky < 0 || oy >= OH) continue;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int kx = ((ix + 1) & 1) + 2 * e, ox = (ix + 1 - kx) / 2;
+        if (ix + 1 - kx < 0 || ox >= OH) continue;
+        s += dcol[(((long long)b * OH + oy) * OH + ox) * 16 * C + (ky * 4 + kx) * C + c];
+      }
+    }
+    if (mask) s *= mask[i] > 0.f ? 1.f : 0.2f;
+    din[i] = s;
+  }
+}
+
+// discriminator input (NHWC, 6 channels) of sample block ``mode``:  0: [x, ytrue, yf2]   1: [x, yf1, ytrue]   2: [x, yf1, yf2]
+// 3: [x, eps ytrue_cat + (1 - eps) yfake_cat] with ytrue_cat = (ytrue, yf2) if coin == 0 else (yf1, ytrue), yfake_cat = (yf1, yf2)
+// (cgan_regression.py:173-185, 266-268).  x, ytrue, yf1, yf2: (B, 2, hw) NCHW.
+__global__ void disc_input_kernel(const float* __restrict__ x, const float* __restrict__ yt, const float* __restrict__ yf1,
+                                  const float* __restrict__ yf2, const float* __restrict__ eps, int coin, int mode,
+                                  float* __restrict__ out, int B, int hw) {
+  const long long total = (long long)B * hw;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(i % hw);
+    const long long b = i / hw;
+    float v[6];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const long long s = (b * 2 + c) * hw + p;
+      const float t = yt[s], f1 = yf1[s], f2 = yf2[s];
+      v[c] = x[s];
+      if (mode == 0) { v[2 + c] = t; v[4 + c] = f2; }
+      else if (mode == 1) { v[2 + c] = f1; v[4 + c] = t; }
+      else if (mode == 2) { v[2 + c] = f1; v[4 + c] = f2; }
+      else {
+        const float e = eps[b];
+        const float ta = coin == 0 ? t : f1, tb = coin == 0 ? f2 : t;
+        v[2 + c] = e * ta + (1.f - e) * f1;
+        v[4 + c] = e * tb + (1.f - e) * f2;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 6; ++c) out[i * 6 + c] = v[c];
+  }
+}
+
+// NCHW (B, C, hw) -> NHWC
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int hw, long long total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C), p = (int)((i / C) % hw);
+    const long long b = i / ((long long)C * hw);
+    out[i] = in[(b * C + c) * hw + p];
+  }
+}
+
+// channels [c0, c0 + 2) of an NHWC (B, hw, 6) array -> NCHW (B, 2, hw)
+__global__ void nhwc_extract_kernel(const float* __restrict__ in, float* __restrict__ out, int c0, int hw, long long total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(i % hw), c = (int)((i / hw) % 2);
+    const long long b = i / (2LL * hw);
+    out[i] = in[(b * hw + p) * 6 + c0 + c];
+  }
+}
+
+// WGAN losses of one iteration (cgan_regression.py:269-272) and the output gradients.  o: (4B) = D(true1), D(true2), D(fake),
+// D(interp).  stats[0] = D_loss = -0.5 (mean true1 + mean true2) + mean fake, stats[2] = D_drift = 1e-3 mean true1^2.
+// d5: d error / d o for the first 3B samples; 1 for the interpolates (their backward pass gives dD/dy, the penalty's argument).
+__global__ void disc_loss_kernel(const float* __restrict__ o, int B, double lambda_drift, float* __restrict__ d5,
+                                 double* __restrict__ stats) {
+  __shared__ double sh[3][256];
+  double s1 = 0.0, s2 = 0.0, s3 = 0.0, sq = 0.0;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const float t1 = o[b];
+    s1 += t1; s2 += o[B + b]; s3 += o[2 * B + b]; sq += (double)t1 * t1;
+    d5[b] = (float)((-0.5 + 2.0 * lambda_drift * t1) / B);
+    d5[B + b] = (float)(-0.5 / B);
+    d5[2 * B + b] = (float)(1.0 / B);
+    d5[3 * B + b] = 1.f;
+  }
+  sh[0][threadIdx.x] = -0.5 * (s1 + s2) + s3; sh[1][threadIdx.x] = sq; sh[2][threadIdx.x] = 0.0;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) { sh[0][threadIdx.x] += sh[0][threadIdx.x + w]; sh[1][threadIdx.x] += sh[1][threadIdx.x + w]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { stats[0] = sh[0][0] / B; stats[2] = lambda_drift * sh[1][0] / B; }
+}
+
+// G_loss = -mean D(x, yf1, yf2) (:279) and its output gradient -1 / B
+__global__ void gen_loss_kernel(const float* __restrict__ o, int B, float* __restrict__ d5, double* __restrict__ stats) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  double s = 0.0;
+  for (int b = 0; b < B; ++b) { s += o[b]; d5[b] = (float)(-1.0 / B); }
+  stats[3] = -s / B;
+}
+
+// e4[b][k] = d5[b] Wp5[k] times the LeakyReLU slope of h4 (data gradient of the last layer)
+__global__ void disc_last_dgrad_kernel(const float* __restrict__ d5, const float* __restrict__ wp5, const float* __restrict__ h4,
+                                       float* __restrict__ out, int K, long long total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % K);
+    const long long b = i / K;
+    out[i] = d5[b] * wp5[k] * (h4[i] > 0.f ? 1.f : 0.2f);
+  }
+}
+
+// gradient penalty (:173-195): g = dD/dy of the interpolates = channels 2..5 of e0 (B, hw, 6).  One block per sample:
+// norm_b = |g_b|_2 ; part[b] = (norm_b - 1)^2 ; coef[b] = lambda 2 (norm_b - 1) / (B norm_b)
+__global__ void __launch_bounds__(256) gp_norm_kernel(const float* __restrict__ e0, int hw, int B, double lambda_gp,
+                                                      double* __restrict__ part, float* __restrict__ coef) {
+  const int b = blockIdx.x;
+  double v[1] = {0.0};
+  for (int i = threadIdx.x; i < hw * 4; i += blockDim.x) {
+    const int p = i / 4, c = 2 + i % 4;
+    const float g = e0[((long long)b * hw + p) * 6 + c];
+    v[0] += (double)g * g;
+  }
+  __shared__ double res[1];
+  block_sum_store<1>(v, res);
+  if (threadIdx.x == 0) {
+    const double norm = sqrt(res[0]);
+    part[b] = (norm - 1.0) * (norm - 1.0);
+    coef[b] = (float)(lambda_gp * 2.0 * (norm - 1.0) / ((double)B * norm));
+  }
+}
+// stats[1] = D_grad = lambda mean_b (norm_b - 1)^2 ;  u0 = d D_grad / d g (zero on the x channels)
+__global__ void gp_seed_kernel(const float* __restrict__ e0, const float* __restrict__ coef, const double* __restrict__ part, int B,
+                               double lambda_gp, float* __restrict__ u0, int hw, double* __restrict__ stats) {
+  const long long total = (long long)B * hw * 6;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % 6);
+    const long long b = i / (6LL * hw);
+    u0[i] = c >= 2 ? coef[b] * e0[i] : 0.f;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    double s = 0.0;
+    for (int b = 0; b < B; ++b) s += part[b];
+    stats[1] = lambda_gp * s / B;
+  }
+}
+
 }  // namespace adv
 }  // namespace qgb

@@ -561,3 +561,364 @@ int qgb_train_cvae_step(qgb_trainer* enc, qgb_trainer* dec, const float* x, cons
 }
 
 }  // extern "C"
+
+// =====================================================================================================================
+// Discriminator and the WGAN-GP iteration (models/cgan_regression.py:173-195, 227-300; tools/cnn_tools.py:212-244)
+// =====================================================================================================================
+struct qgb_disc {
+  int device = 0, nx = 0, B = 0, cin = 6, ndf = 64;
+  struct Layer { int cin, cout, ks, H, OH; size_t w, K; };   // H: input side, OH: output side, K = ks^2 cin (GEMM depth)
+  Layer L[5];
+  size_t nparams = 0;
+  float *P = nullptr, *G = nullptr, *M = nullptr, *V = nullptr, *Wp = nullptr;
+  float* h[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};    // NHWC activations of up to 4B samples: input, 4 x LeakyReLU(conv)
+  float* dl[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // gradient with respect to the output of layer k (before LeakyReLU)
+  float* u[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};    // linearised pass of the gradient penalty (B samples)
+  float *o = nullptr, *e0 = nullptr, *col = nullptr, *part = nullptr, *coef = nullptr, *eps = nullptr;
+  float* dyf[2] = {nullptr, nullptr};
+  size_t col_floats = 0, part_floats = 0;
+  double* stats = nullptr;
+  long long adam_t = 0, launches = 0;
+  float beta1 = 0.5f, beta2 = 0.999f, adam_eps = 1e-8f;
+  std::string err;
+  size_t act(int k) const { return k == 0 ? (size_t)nx * nx * cin : (size_t)L[k - 1].OH * L[k - 1].OH * L[k - 1].cout; }   // per sample
+};
+
+namespace {
+std::string g_disc_create_error;
+int dfail(qgb_disc* d, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (d) d->err = buf; else g_disc_create_error = buf;
+  return code;
+}
+#define D_TRY(d, expr)                                                                                          \
+  do {                                                                                                          \
+    cudaError_t _e = (expr);                                                                                    \
+    if (_e != cudaSuccess) return dfail(d, QGB_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+template <int EPI>
+int gemm(qgb_disc* d, const float* A, long long sai, long long sak, const float* B, long long sbk, long long sbj, float* C,
+         long long ldc, int M, int N, int K, int splits, long long c_split, const float* mask, cudaStream_t st) {
+  int ksplit = (K + splits - 1) / splits;
+  ksplit = (ksplit + kGemmK - 1) / kGemmK * kGemmK;
+  splits = (K + ksplit - 1) / ksplit;
+  dim3 grid((N + kGemmTile - 1) / kGemmTile, (M + kGemmTile - 1) / kGemmTile, splits);
+  sgemm_kernel<EPI><<<grid, 256, 0, st>>>(A, sai, sak, B, sbk, sbj, C, ldc, M, N, K, ksplit, c_split, mask);
+  d->launches++;
+  D_TRY(d, cudaGetLastError());
+  return splits;       // (>= 1; errors are negative QGB codes)
+}
+
+int disc_pack(qgb_disc* d, cudaStream_t st) {
+  for (int k = 0; k < 5; ++k) {
+    const auto& L = d->L[k];
+    const long long n = (long long)L.cout * L.K;
+    disc_pack_kernel<<<ew_blocks(n), 256, 0, st>>>(d->P + L.w, d->Wp + L.w, L.cout, L.cin, L.ks, 0, 1, 0);
+    d->launches++;
+  }
+  D_TRY(d, cudaGetLastError());
+  return QGB_OK;
+}
+
+// D on samples [b0, b0 + nb) of h[0]: activations into h[1..4], outputs into o
+int disc_forward(qgb_disc* d, int b0, int nb, cudaStream_t st) {
+  for (int k = 0; k < 4; ++k) {
+    const auto& L = d->L[k];
+    const long long tot = (long long)nb * L.OH * L.OH * L.K;
+    im2col_kernel<<<ew_blocks(tot), 256, 0, st>>>(d->h[k] + b0 * d->act(k), nullptr, nb, d->col, nb, L.H, L.cin, L.OH);
+    d->launches++;
+    int rc = gemm<1>(d, d->col, (long long)L.K, 1, d->Wp + L.w, 1, (long long)L.K, d->h[k + 1] + b0 * d->act(k + 1), L.cout,
+                     nb * L.OH * L.OH, L.cout, (int)L.K, 1, 0, nullptr, st);
+    if (rc < 0) return rc;
+  }
+  const auto& L = d->L[4];
+  int rc = gemm<0>(d, d->h[4] + b0 * d->act(4), (long long)L.K, 1, d->Wp + L.w, 1, (long long)L.K, d->o + b0, 1, nb, 1, (int)L.K, 1, 0,
+                   nullptr, st);
+  return rc < 0 ? rc : QGB_OK;
+}
+
+// data gradients of samples [b0, b0 + nb) from dl[4] down to dl[0]; the gradient with respect to the input (e0, unmasked) for the
+// samples [ib0, ib0 + inb) only
+int disc_backward_data(qgb_disc* d, int b0, int nb, int ib0, int inb, cudaStream_t st) {
+  {
+    const auto& L = d->L[4];
+    const long long tot = (long long)nb * L.K;
+    disc_last_dgrad_kernel<<<ew_blocks(tot), 256, 0, st>>>(d->dl[4] + b0, d->Wp + L.w, d->h[4] + b0 * d->act(4), d->dl[3] + b0 * d->act(4),
+                                                           (int)L.K, tot);
+    d->launches++;
+  }
+  for (int k = 3; k >= 0; --k) {
+    const auto& L = d->L[k];
+    const int s0 = k == 0 ? ib0 : b0, sn = k == 0 ? inb : nb;
+    if (sn <= 0) break;
+    const int M = sn * L.OH * L.OH;
+    int rc = gemm<0>(d, d->dl[k] + s0 * d->act(k + 1), L.cout, 1, d->Wp + L.w, (long long)L.K, 1, d->col, (long long)L.K, M, (int)L.K,
+                     L.cout, 1, 0, nullptr, st);
+    if (rc < 0) return rc;
+    const long long tot = (long long)sn * d->act(k);
+    if (k > 0)
+      col2im_kernel<<<ew_blocks(tot), 256, 0, st>>>(d->col, d->dl[k - 1] + s0 * d->act(k), d->h[k] + s0 * d->act(k), sn, L.H, L.cin, L.OH);
+    else
+      col2im_kernel<<<ew_blocks(tot), 256, 0, st>>>(d->col, d->e0, nullptr, sn, L.H, L.cin, L.OH);
+    d->launches++;
+  }
+  D_TRY(d, cudaGetLastError());
+  return QGB_OK;
+}
+
+// u[k + 1] = slope(h[k + 1]) (W_k * u[k]) for the nu samples whose activations start at sample m0 of h
+int disc_linearised(qgb_disc* d, int m0, int nu, cudaStream_t st) {
+  for (int k = 0; k < 4; ++k) {
+    const auto& L = d->L[k];
+    const long long tot = (long long)nu * L.OH * L.OH * L.K;
+    im2col_kernel<<<ew_blocks(tot), 256, 0, st>>>(d->u[k], nullptr, nu, d->col, nu, L.H, L.cin, L.OH);
+    d->launches++;
+    int rc = gemm<2>(d, d->col, (long long)L.K, 1, d->Wp + L.w, 1, (long long)L.K, d->u[k + 1], L.cout, nu * L.OH * L.OH, L.cout,
+                     (int)L.K, 1, 0, d->h[k + 1] + m0 * d->act(k + 1), st);
+    if (rc < 0) return rc;
+  }
+  return QGB_OK;
+}
+
+// weight gradients into d->G: sum over the nA ordinary samples (inputs h[k]) and the nU linearised ones (inputs u[k]; their
+// output gradients follow the ordinary ones in dl[k])
+int disc_wgrad(qgb_disc* d, int nA, int nU, cudaStream_t st) {
+  const int nb = nA + nU;
+  for (int k = 0; k < 5; ++k) {
+    const auto& L = d->L[k];
+    const int OH2 = k < 4 ? L.OH * L.OH : 1;
+    const int Mred = nb * OH2;
+    if (k < 4) {
+      const long long tot = (long long)Mred * L.K;
+      im2col_kernel<<<ew_blocks(tot), 256, 0, st>>>(d->h[k], d->u[k], nA, d->col, nb, L.H, L.cin, L.OH);
+      d->launches++;
+    } else {
+      D_TRY(d, cudaMemcpyAsync(d->col, d->h[4], (size_t)nA * L.K * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      if (nU) D_TRY(d, cudaMemcpyAsync(d->col + (size_t)nA * L.K, d->u[4], (size_t)nU * L.K * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    const int tiles = ((L.cout + kGemmTile - 1) / kGemmTile) * (((int)L.K + kGemmTile - 1) / kGemmTile);
+    int splits = (2 * 148 + tiles - 1) / tiles;
+    if (splits > (Mred + kGemmK - 1) / kGemmK) splits = (Mred + kGemmK - 1) / kGemmK;
+    if (splits < 1) splits = 1;
+    const size_t n = (size_t)L.cout * L.K;
+    if (d->part_floats < n * splits) {
+      if (d->part) cudaFree(d->part);
+      d->part = nullptr; d->part_floats = 0;
+      D_TRY(d, talloc(&d->part, n * splits));
+      d->part_floats = n * splits;
+    }
+    int rc = gemm<0>(d, d->dl[k], 1, L.cout, d->col, (long long)L.K, 1, d->part, (long long)L.K, L.cout, (int)L.K, Mred, splits,
+                     (long long)n, nullptr, st);
+    if (rc < 0) return rc;
+    disc_pack_kernel<<<ew_blocks((long long)n), 256, 0, st>>>(d->part, d->G + L.w, L.cout, L.cin, L.ks, 1, rc, (long long)n);
+    d->launches++;
+  }
+  D_TRY(d, cudaGetLastError());
+  return QGB_OK;
+}
+
+int disc_adam(qgb_disc* d, double lr, cudaStream_t st) {
+  d->adam_t += 1;
+  const double bc1 = 1.0 - std::pow((double)d->beta1, (double)d->adam_t), bc2 = 1.0 - std::pow((double)d->beta2, (double)d->adam_t);
+  adam_kernel<<<ew_blocks((long long)d->nparams), 256, 0, st>>>(d->P, d->G, d->M, d->V, (long long)d->nparams, (float)lr, d->beta1,
+                                                                d->beta2, d->adam_eps, (float)bc1, (float)std::sqrt(bc2));
+  d->launches++;
+  D_TRY(d, cudaGetLastError());
+  return QGB_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int qgb_disc_create(int device, int in_channels, int ndf, int nx, int max_batch, qgb_disc** out) {
+  if (!out || in_channels != 6 || ndf < 1 || max_batch < 1)
+    return dfail(nullptr, QGB_EINVAL, "bad argument (the CGAN discriminator sees 6 channels: x, y1, y2)");
+  *out = nullptr;
+  if (nx < 16 || nx % 16 != 0) return dfail(nullptr, QGB_EUNSUPPORTED, "nx must be a multiple of 16 (four stride-2 layers, then an nx/16 kernel)");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return dfail(nullptr, QGB_ECUDA, "no CUDA device available: libqgb200 has no CPU fallback");
+  if (device < 0 || device >= ndev) return dfail(nullptr, QGB_EINVAL, "device %d out of range", device);
+  qgb_disc* d = new qgb_disc();
+  auto bail = [&](int rc) { g_disc_create_error = d->err; qgb_disc_destroy(d); return rc; };
+#define CR(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { d->err = std::string(#expr) + ": " + cudaGetErrorString(_e); return bail(QGB_ECUDA); } } while (0)
+  CR(cudaSetDevice(device));
+  d->device = device; d->nx = nx; d->B = max_batch; d->cin = in_channels; d->ndf = ndf;
+  int c = in_channels, H = nx;
+  for (int k = 0; k < 5; ++k) {
+    auto& L = d->L[k];
+    L.cin = c; L.H = H;
+    if (k < 4) { L.cout = ndf << k; L.ks = 4; L.OH = H / 2; } else { L.cout = 1; L.ks = H; L.OH = 1; }
+    L.K = (size_t)L.ks * L.ks * L.cin;
+    L.w = d->nparams; d->nparams += (size_t)L.cout * L.K;
+    c = L.cout; H = L.OH;
+  }
+  const size_t B4 = 4 * (size_t)max_batch, B1 = max_batch;
+  CR(talloc(&d->P, d->nparams)); CR(talloc(&d->G, d->nparams)); CR(talloc(&d->M, d->nparams)); CR(talloc(&d->V, d->nparams));
+  CR(talloc(&d->Wp, d->nparams));
+  for (int k = 0; k < 5; ++k) {
+    CR(talloc(&d->h[k], B4 * d->act(k)));
+    CR(talloc(&d->u[k], B1 * d->act(k)));
+    CR(talloc(&d->dl[k], B4 * (k < 4 ? d->act(k + 1) : 1)));
+    if (k < 4) { const size_t cf = B4 * d->L[k].OH * d->L[k].OH * d->L[k].K; d->col_floats = cf > d->col_floats ? cf : d->col_floats; }
+  }
+  if (d->col_floats < B4 * d->L[4].K) d->col_floats = B4 * d->L[4].K;
+  CR(talloc(&d->col, d->col_floats));
+  CR(talloc(&d->o, B4)); CR(talloc(&d->e0, B1 * d->act(0))); CR(talloc(&d->coef, B1)); CR(talloc(&d->eps, B1));
+  CR(talloc(&d->dyf[0], B1 * 2 * nx * nx)); CR(talloc(&d->dyf[1], B1 * 2 * nx * nx));
+  CR(talloc(&d->stats, (size_t)16 + B1));
+  CR(cudaMemset(d->P, 0, d->nparams * sizeof(float))); CR(cudaMemset(d->G, 0, d->nparams * sizeof(float)));
+  CR(cudaMemset(d->M, 0, d->nparams * sizeof(float))); CR(cudaMemset(d->V, 0, d->nparams * sizeof(float)));
+  CR(cudaMemset(d->stats, 0, (16 + B1) * sizeof(double)));
+  CR(cudaDeviceSynchronize());
+#undef CR
+  *out = d;
+  return QGB_OK;
+}
+
+void qgb_disc_destroy(qgb_disc* d) {
+  if (!d) return;
+  cudaSetDevice(d->device);
+  for (float* p : {d->P, d->G, d->M, d->V, d->Wp, d->o, d->e0, d->col, d->part, d->coef, d->eps, d->dyf[0], d->dyf[1]})
+    if (p) cudaFree(p);
+  for (int k = 0; k < 5; ++k) { if (d->h[k]) cudaFree(d->h[k]); if (d->u[k]) cudaFree(d->u[k]); if (d->dl[k]) cudaFree(d->dl[k]); }
+  if (d->stats) cudaFree(d->stats);
+  delete d;
+}
+
+const char* qgb_disc_last_error(const qgb_disc* d) { return d ? d->err.c_str() : g_disc_create_error.c_str(); }
+int64_t qgb_disc_num_params(const qgb_disc* d) { return d ? (int64_t)d->nparams : 0; }
+int64_t qgb_disc_launch_count(const qgb_disc* d) { return d ? (int64_t)d->launches : 0; }
+
+int qgb_disc_set_params(qgb_disc* d, const float* params, int reset_optimizer) {
+  if (!d) return QGB_EINVAL;
+  D_TRY(d, cudaSetDevice(d->device));
+  if (params) D_TRY(d, cudaMemcpy(d->P, params, d->nparams * sizeof(float), cudaMemcpyHostToDevice));
+  if (reset_optimizer) {
+    D_TRY(d, cudaMemset(d->M, 0, d->nparams * sizeof(float)));
+    D_TRY(d, cudaMemset(d->V, 0, d->nparams * sizeof(float)));
+    d->adam_t = 0;
+  }
+  return QGB_OK;
+}
+
+int qgb_disc_get_params(qgb_disc* d, float* params, float* grads) {
+  if (!d) return QGB_EINVAL;
+  D_TRY(d, cudaSetDevice(d->device));
+  D_TRY(d, cudaDeviceSynchronize());
+  if (params) D_TRY(d, cudaMemcpy(params, d->P, d->nparams * sizeof(float), cudaMemcpyDeviceToHost));
+  if (grads) D_TRY(d, cudaMemcpy(grads, d->G, d->nparams * sizeof(float), cudaMemcpyDeviceToHost));
+  return QGB_OK;
+}
+
+int qgb_disc_forward(qgb_disc* d, const float* x, int batch, int on_device, float* out, void* stream) {
+  if (!d || !x || !out) return QGB_EINVAL;
+  if (batch < 1 || batch > 4 * d->B) return dfail(d, QGB_EINVAL, "batch %d outside 1..%d", batch, 4 * d->B);
+  cudaStream_t st = (cudaStream_t)stream;
+  D_TRY(d, cudaSetDevice(d->device));
+  const size_t n = (size_t)batch * d->act(0);
+  const float* xd = x;
+  if (!on_device) {                                   // staged through the im2col scratch (>= 16 x the input)
+    D_TRY(d, cudaMemcpyAsync(d->col, x, n * sizeof(float), cudaMemcpyHostToDevice, st));
+    xd = d->col;
+  }
+  nchw_to_nhwc_kernel<<<ew_blocks((long long)n), 256, 0, st>>>(xd, d->h[0], d->cin, d->nx * d->nx, (long long)n);
+  d->launches++;
+  int rc;
+  if ((rc = disc_pack(d, st)) || (rc = disc_forward(d, 0, batch, st))) return rc;
+  D_TRY(d, cudaMemcpyAsync(out, d->o, batch * sizeof(float), on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+  D_TRY(d, cudaStreamSynchronize(st));
+  return QGB_OK;
+}
+
+int qgb_train_cgan_step(qgb_trainer* Gt, qgb_disc* D, const float* x, const float* y, const float* z1, const float* z2,
+                        const float* eps, int coin, int batch, int on_device, double lr_d, double lr_g, int update_d, int g_mode,
+                        double* losses, void* stream) {
+  if (!Gt || !D) return QGB_EINVAL;
+  qgb_trainer* t = Gt;
+  if (!x || !y || !z1 || !z2 || !eps) return tfail(t, QGB_EINVAL, "null minibatch");
+  if (Gt->L.front().cin != 4 || Gt->L.back().cout != 2 || Gt->softplus) return tfail(t, QGB_EINVAL, "expected a generator 4 -> 2 ([x, z] -> y)");
+  if (Gt->ny != D->nx || Gt->nx != D->nx || Gt->device != D->device) return tfail(t, QGB_EINVAL, "generator and discriminator differ in grid or device");
+  if (batch < 1 || batch > Gt->max_batch || batch > D->B) return tfail(t, QGB_EINVAL, "batch %d outside 1..max_batch", batch);
+  if (g_mode < 0 || g_mode > 2) return tfail(t, QGB_EINVAL, "g_mode must be 0 (skip), 1 (gradients) or 2 (gradients + Adam)");
+  cudaStream_t st = (cudaStream_t)stream;
+  TR_TRY(t, cudaSetDevice(t->device));
+  const int hw = t->ny * t->nx, B = batch;
+  const size_t f2 = (size_t)B * 2 * hw, f4 = (size_t)B * 4 * hw;
+  const double lambda_gp = 10.0, lambda_drift = 1e-3;            // LAMBDA_GP, LAMBDA_DRIFT (cgan_regression.py:18-19)
+  const float *xd, *yd, *z1d, *z2d;
+  int rc;
+  if ((rc = stage_into(t, 0, x, f2, on_device, &xd, st)) || (rc = stage_into(t, 1, y, f2, on_device, &yd, st)) ||
+      (rc = stage_into(t, 2, z1, f2, on_device, &z1d, st)) || (rc = stage_into(t, 3, z2, f2, on_device, &z2d, st)))
+    return rc;
+  if ((rc = ensure_scratch(t, 4, f4)) || (rc = ensure_scratch(t, 5, f4)) || (rc = ensure_slots(t, 2))) return rc;
+  if (!t->Gacc) TR_TRY(t, talloc(&t->Gacc, t->nparams));
+  TR_TRY(t, cudaMemcpyAsync(D->eps, eps, B * sizeof(float), cudaMemcpyHostToDevice, st));     // eps: always a host array (B floats)
+  float* gin[2] = {t->scr[4], t->scr[5]};
+  const float* zz[2] = {z1d, z2d};
+  const float* yf[2];
+  // yfake1 = G(x, z1), yfake2 = G(x, z2) in training mode (:262-263)
+  for (int s = 0; s < 2; ++s) {
+    t->slot = s;
+    cat_channels_kernel<<<ew_blocks((long long)f2), 256, 0, st>>>(xd, 2, gin[s], 4, 0, hw, (long long)f2);
+    cat_channels_kernel<<<ew_blocks((long long)f2), 256, 0, st>>>(zz[s], 2, gin[s], 4, 2, hw, (long long)f2);
+    t->launches += 2;
+    if ((rc = forward(t, gin[s], B, true, st))) { t->slot = 0; return rc; }
+    yf[s] = R(t, t->nlayers - 1);
+  }
+  t->slot = 0;
+#define DCALL(expr) do { int _rc = (expr); if (_rc) { t->err = D->err; return _rc; } } while (0)
+  // discriminator inputs: true1, true2, fake, interpolates (:266-268, 173-185)
+  for (int mode = 0; mode < 4; ++mode) {
+    disc_input_kernel<<<ew_blocks((long long)B * hw), 256, 0, st>>>(xd, yd, yf[0], yf[1], D->eps, coin, mode,
+                                                                    D->h[0] + (size_t)mode * B * D->act(0), B, hw);
+    D->launches++;
+  }
+  DCALL(disc_pack(D, st));
+  DCALL(disc_forward(D, 0, 4 * B, st));
+  // the four blocks of d5 must be B apart: the loss kernel writes them at stride ``batch``
+  disc_loss_kernel<<<1, 256, 0, st>>>(D->o, B, lambda_drift, D->dl[4], D->stats);
+  D->launches++;
+  DCALL(disc_backward_data(D, 0, 4 * B, 3 * B, B, st));
+  gp_norm_kernel<<<B, 256, 0, st>>>(D->e0, hw, B, lambda_gp, D->stats + 16, D->coef);
+  gp_seed_kernel<<<ew_blocks((long long)B * hw * 6), 256, 0, st>>>(D->e0, D->coef, D->stats + 16, B, lambda_gp, D->u[0], hw, D->stats);
+  D->launches += 2;
+  TR_TRY(t, cudaGetLastError());
+  DCALL(disc_linearised(D, 3 * B, B, st));
+  DCALL(disc_wgrad(D, 3 * B, B, st));
+  if (update_d) DCALL(disc_adam(D, lr_d, st));
+  if (g_mode) {
+    // G_loss = -mean D(x, yfake1, yfake2) with the updated discriminator (:277-282); the fake block of h[0] is still in place
+    if (update_d) DCALL(disc_pack(D, st));
+    TR_TRY(t, cudaMemcpyAsync(D->h[0], D->h[0] + (size_t)2 * B * D->act(0), (size_t)B * D->act(0) * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    DCALL(disc_forward(D, 0, B, st));
+    gen_loss_kernel<<<1, 32, 0, st>>>(D->o, B, D->dl[4], D->stats);
+    D->launches++;
+    DCALL(disc_backward_data(D, 0, B, 0, B, st));
+    nhwc_extract_kernel<<<ew_blocks((long long)f2), 256, 0, st>>>(D->e0, D->dyf[0], 2, hw, (long long)f2);
+    nhwc_extract_kernel<<<ew_blocks((long long)f2), 256, 0, st>>>(D->e0, D->dyf[1], 4, hw, (long long)f2);
+    D->launches += 2;
+    for (int s = 0; s < 2; ++s) {
+      t->slot = s;
+      TR_TRY(t, cudaMemcpyAsync(t->d[0], D->dyf[s], f2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      if ((rc = backward(t, gin[s], B, st))) { t->slot = 0; return rc; }
+      if (s == 0) TR_TRY(t, cudaMemcpyAsync(t->Gacc, t->G, t->nparams * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    t->slot = 0;
+    axpy_kernel<<<ew_blocks((long long)t->nparams), 256, 0, st>>>(t->G, t->Gacc, 1.f, (long long)t->nparams);
+    t->launches++;
+    TR_TRY(t, cudaGetLastError());
+    if (g_mode == 2 && (rc = adam_update(t, lr_g, st))) return rc;
+  }
+#undef DCALL
+  if (losses) TR_TRY(t, cudaMemcpyAsync(losses, D->stats, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  TR_TRY(t, cudaStreamSynchronize(st));
+  return QGB_OK;
+}
+
+}  // extern "C"

@@ -135,6 +135,8 @@ class AndrewCNN(object):
         return {'loss': float(((y - yt) ** 2).mean())}
 
     def apply(self, fn):
+        """``net.apply(weights_init)`` of the reference's constructors (models/cgan_regression.py:62-63)."""
+        fn(self)
         return self
 
     # ---- weight export ----------------------------------------------------------------------------------------
@@ -225,6 +227,11 @@ class AndrewCNN(object):
 def weights_init(m):
     """Reference cnn_tools.py:54-65 (DCGAN initialisation, applied by the GAN / VAE constructors): conv weights N(0, 0.02),
     BatchNorm weights N(1, 0.02) and zero bias.  Accepts our AndrewCNN; other objects are left alone."""
+    if isinstance(m, DCGAN_discriminator):
+        for key in m.KEYS:
+            m._sd[key] = torch.randn(tuple(m._sd[key].shape)) * 0.02
+        m._release()
+        return None
     if not isinstance(m, AndrewCNN):
         return None
     for conv_idx, bn_idx, cin, cout, k in m._blocks:
@@ -234,6 +241,155 @@ def weights_init(m):
             m._sd['conv.%d.bias' % bn_idx] = torch.zeros(cout)
     m._release()
     return None
+
+
+class DCGAN_discriminator(object):
+    """cnn_tools.py:212-244 with ``bn='None'`` (what CGANRegression builds, models/cgan_regression.py:57): four
+    Conv2d(4, stride 2, padding 1, bias=False) + LeakyReLU(0.2) from ``in_channels`` to ndf, 2 ndf, 4 ndf, 8 ndf, then
+    Conv2d(8 ndf, 1, nx/64*4, 1, 0).  State-dict keys as in the reference's nn.Sequential (0, 2, 5, 8, 11 .weight).
+    ``forward`` runs on the device through ``qgb_disc_forward``; training goes through ``CGANTrainer``."""
+    KEYS = ['0.weight', '2.weight', '5.weight', '8.weight', '11.weight']
+
+    def __init__(self, in_channels, ndf=64, nx=64, bn='None'):
+        if bn != 'None':
+            raise NotImplementedError("only bn='None' (the CGAN's discriminator) is built")
+        self.in_channels, self.ndf, self.nx = int(in_channels), int(ndf), int(nx)
+        k5 = int(nx / 64 * 4)
+        chans = [in_channels, ndf, ndf * 2, ndf * 4, ndf * 8]
+        g = torch.Generator().manual_seed(1)
+        self._sd = {}
+        for i, key in enumerate(self.KEYS):
+            cin, cout, k = (chans[i], chans[i + 1], 4) if i < 4 else (chans[4], 1, k5)
+            bound = 1.0 / np.sqrt(cin * k * k)
+            self._sd[key] = (torch.rand(cout, cin, k, k, generator=g) * 2 - 1) * bound
+        self._disc = None
+
+    def state_dict(self):
+        return dict(self._sd)
+
+    def load_state_dict(self, sd, strict=True):
+        missing = [k for k in self._sd if k not in sd]
+        unexpected = [k for k in sd if k not in self._sd]
+        if strict and (missing or unexpected):
+            raise RuntimeError('Error(s) in loading state_dict for DCGAN_discriminator: missing %s, unexpected %s'
+                               % (missing, unexpected))
+        for k in self._sd:
+            if k in sd:
+                v = torch.as_tensor(sd[k]).detach().cpu().float()
+                if tuple(v.shape) != tuple(self._sd[k].shape):
+                    raise RuntimeError('size mismatch for %s: %s vs %s' % (k, tuple(v.shape), tuple(self._sd[k].shape)))
+                self._sd[k] = v.clone()
+        self._release()
+        return '<All keys matched successfully>'
+
+    def to(self, device):
+        return self
+
+    def train(self, mode=True):
+        return self
+
+    def eval(self):
+        return self
+
+    def zero_grad(self):
+        return None
+
+    def apply(self, fn):
+        fn(self)
+        return self
+
+    def flat(self):
+        return np.ascontiguousarray(np.concatenate([self._sd[k].numpy().astype('float32').ravel() for k in self.KEYS]))
+
+    def unflat(self, flat):
+        out, o = {}, 0
+        for k in self.KEYS:
+            shape = tuple(self._sd[k].shape)
+            n = int(np.prod(shape))
+            out[k] = flat[o:o + n].reshape(shape).copy()
+            o += n
+        return out
+
+    def _release(self):
+        if getattr(self, '_disc', None) is not None:
+            self._disc.close()
+            self._disc = None
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
+
+    def forward(self, x):
+        """x: (B, in_channels, nx, nx) float32 tensor (CPU or CUDA) -> (B, 1, 1, 1) on the same device."""
+        xt = torch.as_tensor(x, dtype=torch.float32)
+        if self._disc is None or self._disc.max_batch * 4 < xt.shape[0]:
+            self._release()
+            self._disc = DiscState(self, max_batch=max(16, (int(xt.shape[0]) + 3) // 4))
+        out = self._disc.forward(xt)
+        return out.reshape(-1, 1, 1, 1)
+
+    __call__ = forward
+
+
+class DiscState(object):
+    """Device-side state of a DCGAN_discriminator (``qgb_disc``): parameters, Adam moments, activations of 4 x max_batch
+    samples."""
+
+    def __init__(self, net, max_batch=64, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError('the discriminator needs a CUDA device: libqgb200 has no CPU fallback')
+        self._lib = _lib.load()
+        self.net = net
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.max_batch = int(max_batch)
+        self._h = ctypes.c_void_p()
+        _lib.check_disc(self._lib.qgb_disc_create(self.device, net.in_channels, net.ndf, net.nx, self.max_batch,
+                                                  ctypes.byref(self._h)))
+        self.nparams = int(self._lib.qgb_disc_num_params(self._h))
+        self.upload(reset_optimizer=True)
+
+    def close(self):
+        if getattr(self, '_h', None):
+            self._lib.qgb_disc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload(self, reset_optimizer=False):
+        p = self.net.flat()
+        assert p.size == self.nparams
+        _lib.check_disc(self._lib.qgb_disc_set_params(self._h, p.ctypes.data, 1 if reset_optimizer else 0), self._h)
+
+    def sync_to(self, net=None):
+        net = net or self.net
+        p = np.empty(self.nparams, 'float32')
+        _lib.check_disc(self._lib.qgb_disc_get_params(self._h, p.ctypes.data, None), self._h)
+        for k, a in net.unflat(p).items():
+            net._sd[k] = torch.from_numpy(a)
+        if getattr(net, '_disc', None) is not self:
+            net._release()                 # the inference-side copy (if any) is stale now
+
+    def last_grads(self):
+        g = np.empty(self.nparams, 'float32')
+        _lib.check_disc(self._lib.qgb_disc_get_params(self._h, None, g.ctypes.data), self._h)
+        return self.net.unflat(g)
+
+    def forward(self, x):
+        dev = torch.device('cuda:%d' % self.device)
+        xd = x.to(dev).contiguous()
+        out = torch.empty(xd.shape[0], dtype=torch.float32, device=dev)
+        _lib.check_disc(self._lib.qgb_disc_forward(self._h, xd.data_ptr(), xd.shape[0], 1, out.data_ptr(),
+                                                   torch.cuda.current_stream(dev).cuda_stream), self._h)
+        return out.to(x.device)
+
+    def launch_count(self):
+        return int(self._lib.qgb_disc_launch_count(self._h))
 
 
 class Trainer(object):

@@ -23,6 +23,8 @@ initial_condition.npz  set_initial_condition (tools/simulate.py:147-168) under n
                    successive members each)
 training_cvae.npz  CVAERegression.compute_loss (ELBO, adaptive and fixed decoder variance) losses and autograd gradients of a small
                    encoder / decoder pair with the recorded reparameterisation noise, and a whole ``train_CVAE`` run (4 epochs, batch 8)
+training_cgan.npz  a whole ``train_CGAN`` run (WGAN-GP, 2 epochs x 6 iterations, small G, DCGAN_discriminator with ndf = 8 at 64 x 64) with
+                   seeded random draws: the gradients the two Adam optimizers saw in the first iteration, the loss logs, final G / D
 training.npz       the reference's training arithmetic on a small AndrewCNN (2 -> 16 -> 12 -> 12 -> 8 -> 2, 16 x 16 images):
                    loss and autograd gradients of ``compute_loss`` in training mode for AndrewCNN and VarCNN (softplus head),
                    BatchNorm running statistics after that forward, and a whole ``cnn_tools.train`` run (4 epochs, batch 8,
@@ -363,7 +365,90 @@ def cvae_fixture():
     np.savez_compressed(os.path.join(HERE, 'training_cvae.npz'), **out)
 
 
+def cgan_data(n=24, nx=64, seed=31):
+    """Synthetic (x, y) pairs of the CGAN fixture; the test regenerates them from the same seed."""
+    rng = np.random.RandomState(seed)
+    x = rng.randn(n, 2, nx, nx).astype('float32')
+    y = (0.5 * np.roll(x, 1, axis=-1) - 0.25 * np.roll(x, 2, axis=-2) + 0.3 * rng.randn(n, 2, nx, nx)).astype('float32')
+    return x, y
+
+
+class SeededDraws(object):
+    """The random draws of train_CGAN from seeded numpy streams (so that the fixture need not store them):
+    z = float32 standard normal (RandomState(77)), eps = float32 uniform (RandomState(78))."""
+
+    def __init__(self):
+        self.rz, self.re = np.random.RandomState(77), np.random.RandomState(78)
+
+    def z(self, shape):
+        return self.rz.randn(*shape).astype('float32')
+
+    def eps(self, n):
+        return self.re.rand(n).astype('float32')
+
+
+def cgan_fixture():
+    """models/cgan_regression.py:222-300 ``train_CGAN`` (with ``gradient_penalty`` :173-195) run as it is on CPU torch: a small
+    generator (4 -> 16 -> 12 -> 12 -> 8 -> 2) and DCGAN_discriminator(6, ndf=8, bn='None', nx=64), 24 samples of 64 x 64, batch 4,
+    2 epochs (generator steps at i = 0, 5).  ``torch.randn`` / ``torch.rand`` are replaced by seeded numpy streams for the duration
+    of the run (``SeededDraws``), np.random (shuffling, the coin of the gradient penalty) is seeded; a recording subclass of
+    torch.optim.Adam keeps the gradients each optimizer saw in the first iteration."""
+    from pyqg_generative.models import cgan_regression as ref_cgan
+    out = {}
+    X_train, Y_train = cgan_data()
+    torch.manual_seed(8)
+    tmp = tempfile.mkdtemp()
+    net = CGANRegression(folder=tmp, nx=64, hidden_channels=TRAIN_HIDDEN)
+    shutil.rmtree(tmp, ignore_errors=True)
+    net.D = cnn_tools.DCGAN_discriminator(6, ndf=8, bn='None', nx=64)
+    net.D.apply(cnn_tools.weights_init)
+    with torch.no_grad():                   # N(0, 0.02) leaves D(x) ~ 1e-5 with ndf = 8: scale to N(0, 0.1) so that every loss term counts
+        for p_ in net.D.parameters():
+            p_.mul_(5.0)
+    for k, v in net.G.state_dict().items():
+        out['G_init/%s' % k] = v.numpy().copy()
+    for k, v in net.D.state_dict().items():
+        out['D_init/%s' % k] = v.numpy().copy()
+    draws = SeededDraws()
+    seen = []
+
+    class RecordingAdam(torch.optim.Adam):
+        def step(self, *a, **k):
+            if len(seen) < 2:
+                seen.append([p.grad.detach().numpy().copy() for g in self.param_groups for p in g['params']])
+            return super().step(*a, **k)
+    real = (torch.randn, torch.rand, ref_cgan.optim.Adam, ref_cgan.evaluate_prediction)
+    torch.randn = lambda *shape, **k: torch.from_numpy(draws.z(tuple(shape[0]) if len(shape) == 1 and not isinstance(shape[0], int) else shape))
+    torch.rand = lambda *shape, **k: torch.from_numpy(draws.eps(shape[0]).reshape(shape))
+    ref_cgan.optim.Adam = RecordingAdam
+    ref_cgan.evaluate_prediction = lambda *a, **k: dict(L2_mean=0., L2_total=0., L2_residual=0., var_ratio=[0., 0.])
+    try:
+        np.random.seed(0)
+        optim_loss, _, _ = ref_cgan.train_CGAN(net, None, None, X_train, Y_train, num_epochs=2, batch_size=4, learning_rate=2e-4)
+    finally:
+        torch.randn, torch.rand, ref_cgan.optim.Adam, ref_cgan.evaluate_prediction = real
+    for (k, _), g in zip(net.D.named_parameters(), seen[0]):
+        out['D_grad0/%s' % k] = g
+    for (k, _), g in zip(net.G.named_parameters(), seen[1]):
+        out['G_grad0/%s' % k] = g
+    for k, v in net.G.state_dict().items():
+        out['G_final/%s' % k] = v.numpy().copy()
+    for k, v in net.D.state_dict().items():
+        out['D_final/%s' % k] = v.numpy().copy()
+    for k, v in optim_loss.items():
+        out['log/%s' % k] = np.array(v, dtype=np.float64)
+    # D on a fixed input with the initial weights (forward parity of the discriminator alone)
+    xin = np.random.RandomState(5).randn(3, 6, 64, 64).astype('float32')
+    D0 = cnn_tools.DCGAN_discriminator(6, ndf=8, bn='None', nx=64)
+    D0.load_state_dict({k[7:]: torch.as_tensor(v) for k, v in out.items() if k.startswith('D_init/')})
+    out['D_forward'] = D0(torch.as_tensor(xin)).detach().numpy().reshape(-1)
+    np.savez_compressed(os.path.join(HERE, 'training_cgan.npz'), **out)
+
+
 if __name__ == '__main__':
+    if '--cgan' in sys.argv:
+        cgan_fixture()
+        sys.exit(0)
     if '--cvae' in sys.argv:
         cvae_fixture()
         sys.exit(0)
@@ -388,5 +473,6 @@ if __name__ == '__main__':
     initial_condition_fixture()
     training_fixture()
     cvae_fixture()
+    cgan_fixture()
     for f in sorted(os.listdir(HERE)):
         print('%10d  %s' % (os.path.getsize(os.path.join(HERE, f)), f))

@@ -259,3 +259,128 @@ def test_cvae_fit_writes_reference_files(tmp_path):
     z = np.random.RandomState(0).randn(1, 2, 16, 16).astype('float32')
     m = type('M', (), dict(q=ds_test['q'][0, 0]))()
     assert np.array_equal(model.predict_snapshot(m, z), again.predict_snapshot(m, z))
+
+
+# ---- CGAN (WGAN-GP) ---------------------------------------------------------------------------------------------------------
+def cgan_data(n=24, nx=64, seed=31):           # = tests/golden/make_golden.py:cgan_data
+    rng = np.random.RandomState(seed)
+    x = rng.randn(n, 2, nx, nx).astype('float32')
+    y = (0.5 * np.roll(x, 1, axis=-1) - 0.25 * np.roll(x, 2, axis=-2) + 0.3 * rng.randn(n, 2, nx, nx)).astype('float32')
+    return x, y
+
+
+class SeededDraws(object):                      # = tests/golden/make_golden.py:SeededDraws (+ the coin from np.random, like the reference)
+    def __init__(self):
+        self.rz, self.re = np.random.RandomState(77), np.random.RandomState(78)
+
+    def z(self, shape):
+        return self.rz.randn(*shape).astype('float32')
+
+    def eps(self, n):
+        return self.re.rand(n).astype('float32')
+
+    def coin(self):
+        return int(np.random.randint(0, 2, 1)[0])
+
+
+def make_cgan(g):
+    from pyqg_generative_b200.models.cgan_regression import CGANRegression
+    from pyqg_generative_b200.tools.cnn_tools import DCGAN_discriminator
+    net = CGANRegression(folder='/nonexistent', nx=64, hidden_channels=HIDDEN)
+    net.G.load_state_dict(sd_of(g, 'G_init'))
+    net.D = DCGAN_discriminator(6, ndf=8, bn='None', nx=64)
+    net.D.load_state_dict(sd_of(g, 'D_init'))
+    return net
+
+
+def test_discriminator_forward_matches_reference():
+    g = golden('training_cgan.npz')
+    net = make_cgan(g)
+    xin = np.random.RandomState(5).randn(3, 6, 64, 64).astype('float32')
+    out = net.D(torch.as_tensor(xin)).numpy().reshape(-1)
+    assert rel(out, g['D_forward']) < 1e-5, (out, g['D_forward'])
+    out_dev = net.D(torch.as_tensor(xin).cuda())
+    assert out_dev.is_cuda and tuple(out_dev.shape) == (3, 1, 1, 1)
+
+
+def test_cgan_first_iteration_gradients_match_reference():
+    """The gradients the reference's two Adam optimizers see in the first iteration of train_CGAN (models/cgan_regression.py:256-282):
+    D: d(D_loss + D_grad + D_drift)/dW including the second-order term of the gradient penalty; G: d(-mean D(x, G(x,z1), G(x,z2)))/dW
+    through the UPDATED discriminator and both generator passes."""
+    from pyqg_generative_b200.models.cgan_regression import CGANTrainer
+    g = golden('training_cgan.npz')
+    net = make_cgan(g)
+    X, Y = cgan_data()
+    np.random.seed(0)
+    order = np.arange(len(X))
+    np.random.shuffle(order)                       # the first minibatch of the reference run
+    idx = order[:4]
+    draws = SeededDraws()
+    tr = CGANTrainer(net, 64, 64, max_batch=4)
+    losses = tr.step(X[idx], Y[idx], 2e-4, 2e-4, True, z1=draws.z((4, 2, 64, 64)), z2=draws.z((4, 2, 64, 64)), eps=draws.eps(4),
+                     coin=draws.coin())
+    assert all(np.isfinite(v) for v in losses.values()), losses
+    worst = 0.0
+    dg = tr.D.last_grads()
+    for k, r in sd_of(g, 'D_grad0').items():
+        e = rel(dg[k], r.numpy())
+        worst = max(worst, e)
+        assert e < GRAD_TOL, ('D', k, e)
+    gg = tr.G.last_grads()
+    for k, r in sd_of(g, 'G_grad0').items():
+        e = rel(gg[k], r.numpy())
+        worst = max(worst, e)
+        assert e < GRAD_TOL, ('G', k, e)
+    assert worst < 5e-4, worst
+    tr.close()
+
+
+def test_cgan_train_run_matches_reference():
+    """train_CGAN, 2 epochs x 6 iterations (generator steps at i = 0, 5), same initial weights, data, shuffling and random draws
+    as the reference run: epoch-mean losses and the final generator / discriminator."""
+    from pyqg_generative_b200.models.cgan_regression import train_CGAN
+    g = golden('training_cgan.npz')
+    net = make_cgan(g)
+    X, Y = cgan_data()
+    np.random.seed(0)
+    optim_loss, _, _ = train_CGAN(net, None, None, X, Y, num_epochs=2, batch_size=4, learning_rate=2e-4, evaluate=False,
+                                  noise=SeededDraws())
+    for k in ('D_loss', 'D_grad', 'D_drift', 'G_loss'):
+        ref = g['log/' + k]
+        assert np.allclose(optim_loss[k], ref, rtol=2e-3, atol=2e-4), (k, optim_loss[k], ref)
+    for name, sub in (('G', net.G), ('D', net.D)):
+        final = sub.state_dict()
+        for k, r in sd_of(g, name + '_final').items():
+            if k.endswith('num_batches_tracked'):
+                assert int(final[k]) == int(r), (name, k, int(final[k]), int(r))
+            else:
+                assert rel(final[k].numpy(), r.numpy()) < 2e-3, (name, k, rel(final[k].numpy(), r.numpy()))
+
+
+def test_cgan_fit_writes_reference_files(tmp_path):
+    """CGANRegression.fit (:66-107) end to end on a tiny dataset at the shipped discriminator width (ndf = 64)."""
+    from pyqg_generative_b200.models.cgan_regression import CGANRegression
+    rng = np.random.RandomState(6)
+
+    def dataset(nrun):
+        q = rng.randn(nrun, 2, 2, 32, 32) * np.array([7e-6, 1e-6])[None, None, :, None, None]
+        s = 1e-6 * (np.roll(q, 1, axis=-1) - q) * (1 + 0.5 * rng.randn(*q.shape))
+        return {'q': q, 'q_forcing_advection': s}
+    ds_train, ds_test = dataset(6), dataset(2)
+    folder = str(tmp_path / 'gan')
+    model = CGANRegression(folder=folder, nx=32, hidden_channels=[16, 8])
+    np.random.seed(7)
+    model.fit(ds_train, ds_test, num_epochs=2, batch_size=4, learning_rate=2e-4, nruns=2)
+    for f in ('G.pt', 'D.pt', 'x_scale.json', 'y_scale.json', 'model_args.json', 'stats.nc'):
+        assert (tmp_path / 'gan' / f).exists(), f
+    from scipy.io import netcdf_file
+    with netcdf_file(str(tmp_path / 'gan' / 'stats.nc'), 'r', mmap=False) as f:
+        for k in ('D_loss', 'D_grad', 'D_drift', 'G_loss', 'L2_mean', 'L2_total_test', 'loss', 'Epoch_opt'):
+            assert f.variables[k].shape == (2,), k
+        assert np.isfinite(f.variables['D_grad'][:]).all()
+    again = CGANRegression(folder=folder, nx=32, hidden_channels=[16, 8])
+    for k, v in model.G.state_dict().items():
+        assert torch.equal(again.G.state_dict()[k], v), k
+    for k, v in model.D.state_dict().items():
+        assert torch.equal(again.D.state_dict()[k], v), k
+    assert tuple(model.D.state_dict()['11.weight'].shape) == (1, 512, 2, 2)       # nx / 64 * 4 = 2
