@@ -19,7 +19,7 @@ from .. import _lib
 from ..tools.cnn_tools import AndrewCNN, AverageLoss, DCGAN_discriminator, DiscState, Trainer, apply_function, extract, \
     minibatch, multistep_lr, prepare_PV_data, save_model_args, weights_init, write_log
 from ._cnn_closure import CNNClosure, batched_mean_var, make_dataset
-from .cvae_regression import evaluate_prediction, loss_to_log
+from .cvae_regression import _to_device, evaluate_prediction, loss_to_log
 
 LAMBDA_DRIFT = 1e-3     # (applied inside qgb_train_cgan_step)
 LAMBDA_GP = 10
@@ -151,9 +151,7 @@ class CGANTrainer(object):
         torch.rand / np.random.randint like the reference).  ``g_step``: also update the generator (every 5th iteration, :277).
         ``update=False``: gradients only (both networks), no optimizer step."""
         dev = torch.device('cuda:%d' % self.G.device)
-
-        def dv(a):
-            return torch.as_tensor(np.asarray(a), dtype=torch.float32).to(dev).contiguous()
+        dv = lambda a: _to_device(a, dev)
         xd, yd = dv(x), dv(y)
         if xd.shape != yd.shape or xd.dim() != 4 or xd.shape[1] != 2:
             raise ValueError('expected x, y of shape (B, 2, ny, nx), got %s and %s' % (tuple(xd.shape), tuple(yd.shape)))

@@ -118,6 +118,12 @@ def evaluate_prediction(net, ds, nruns=None, M=16):
     return {k: scores[k] for k in ('L2_mean', 'L2_total', 'L2_residual', 'var_ratio')}
 
 
+def _to_device(a, dev):
+    """numpy array / CPU or CUDA tensor -> contiguous float32 tensor on ``dev``."""
+    t = a if isinstance(a, torch.Tensor) else torch.as_tensor(np.asarray(a))
+    return t.to(device=dev, dtype=torch.float32).contiguous()
+
+
 def _values(v):
     return np.asarray(getattr(v, 'values', v))
 
@@ -156,12 +162,11 @@ class CVAETrainer(object):
         """x, y: (B, 2, ny, nx) float32 (numpy or torch); eps: the reparameterisation draw (default torch.randn on the device).
         Returns the six losses of ``compute_loss``."""
         dev = torch.device('cuda:%d' % self.enc.device)
-        xd = torch.as_tensor(np.asarray(x), dtype=torch.float32).to(dev).contiguous()
-        yd = torch.as_tensor(np.asarray(y), dtype=torch.float32).to(dev).contiguous()
+        xd, yd = _to_device(x, dev), _to_device(y, dev)
         if xd.shape != yd.shape or xd.dim() != 4 or xd.shape[1] != 2:
             raise ValueError('expected x, y of shape (B, 2, ny, nx), got %s and %s' % (tuple(xd.shape), tuple(yd.shape)))
         ed = torch.randn(xd.shape, device=dev) if eps is None else \
-            torch.as_tensor(np.asarray(eps), dtype=torch.float32).to(dev).contiguous()
+            _to_device(eps, dev)
         out = (ctypes.c_double * 6)()
         stream = torch.cuda.current_stream(dev).cuda_stream
         _lib.check_train(self._lib.qgb_train_cvae_step(self.enc._h, self.dec._h, xd.data_ptr(), yd.data_ptr(), ed.data_ptr(),

@@ -304,3 +304,60 @@ def test_training_oracle_reproduces_the_reference():
     assert np.allclose(log['loss'], g['run_loss'], rtol=1e-5) and np.allclose(log['loss_test'], g['run_loss_test'], rtol=1e-5)
     for k, v in _golden_sd(g, 'run_final').items():
         assert np.abs(final[k].astype('float64') - v).max() <= 1e-5 * max(np.abs(v).max(), 1e-30), k
+
+
+def test_cvae_oracle_reproduces_the_reference():
+    """oracle/train_ref.py:cvae_losses against CVAERegression.compute_loss + autograd of the unmodified reference."""
+    import torch
+    from oracle import train_ref
+    g = golden('training_cvae.npz')
+    keys = ('loss', 'loss_recon', 'loss_KL', 'MSE', 'var_latent', 'var_aggr')
+    for tag, dv in (('adaptive', 'adaptive'), ('fixed01', 0.1)):
+        enc, dec = train_ref.Net(_golden_sd(g, tag + '_enc_init')), train_ref.Net(_golden_sd(g, tag + '_dec_init'))
+        enc.train(); dec.train()
+        losses = train_ref.cvae_losses(enc, dec, torch.as_tensor(g['grad_x']), torch.as_tensor(g['grad_y']),
+                                       torch.as_tensor(g[tag + '_eps']), dv)
+        losses['loss'].backward()
+        for k, r in zip(keys, g[tag + '_losses']):
+            assert abs(float(losses[k]) - r) <= 1e-6 * abs(r), (tag, k)
+        for name, net in (('enc', enc), ('dec', dec)):
+            for k, p in net.named_parameters():
+                v = g['%s_%s_grad/%s' % (tag, name, k)]
+                assert np.abs(p.grad.numpy() - v).max() <= 1e-5 * max(np.abs(v).max(), 1e-30), (tag, name, k)
+
+
+def test_cgan_oracle_reproduces_the_reference():
+    """oracle/train_ref.py:cgan_iteration against the first iteration of the unmodified reference's train_CGAN (the gradients
+    its two Adam optimizers saw) and the discriminator's forward."""
+    import torch
+    from oracle import train_ref
+    g = golden('training_cgan.npz')
+    rng = np.random.RandomState(31)                       # tests/golden/make_golden.py:cgan_data
+    X = rng.randn(24, 2, 64, 64).astype('float32')
+    Y = (0.5 * np.roll(X, 1, axis=-1) - 0.25 * np.roll(X, 2, axis=-2) + 0.3 * rng.randn(24, 2, 64, 64)).astype('float32')
+    np.random.seed(0)
+    order = np.arange(24)
+    np.random.shuffle(order)
+    idx = order[:4]
+    rz, re = np.random.RandomState(77), np.random.RandomState(78)
+    z1, z2 = (torch.as_tensor(rz.randn(4, 2, 64, 64).astype('float32')) for _ in range(2))
+    eps = torch.as_tensor(re.rand(4).astype('float32')).reshape(4, 1, 1, 1)
+    coin = int(np.random.randint(0, 2, 1)[0])
+    G, D = train_ref.Net(_golden_sd(g, 'G_init')), train_ref.Disc(_golden_sd(g, 'D_init'))
+    G.train(); D.train()
+    xin = torch.as_tensor(np.random.RandomState(5).randn(3, 6, 64, 64).astype('float32'))
+    assert np.abs(D(xin).detach().numpy().reshape(-1) - g['D_forward']).max() < 1e-6
+    optD = torch.optim.Adam(D.parameters(), lr=2e-4, betas=(0.5, 0.999))
+    recorded = {}
+    real_step = optD.step
+
+    def step():
+        recorded.update({k: p.grad.numpy().copy() for k, p in D.net.named_parameters()})
+        real_step()
+    optD.step = step
+    train_ref.cgan_iteration(G, D, optD, None, torch.as_tensor(X[idx]), torch.as_tensor(Y[idx]), z1, z2, eps, coin, True)
+    for k, v in _golden_sd(g, 'D_grad0').items():
+        assert np.abs(recorded[k] - v).max() <= 1e-5 * np.abs(v).max(), k
+    for k, p in G.named_parameters():
+        v = g['G_grad0/' + k]
+        assert np.abs(p.grad.numpy() - v).max() <= 1e-4 * np.abs(v).max(), k
