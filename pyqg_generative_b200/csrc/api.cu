@@ -193,16 +193,18 @@ int net_forward_fp32(qgb_handle* h, const DevNet& net, const float* x, long long
       const int sp = last ? softplus : 0, acc = last ? accumulate : 0;
       const bool small = L.cout <= 4;
       const int co_t = small ? 2 : 32;
-      dim3 grid(tiles_x * ((small || L.ks != 5) ? tiles_y : tiles_y2), (L.cout + co_t - 1) / co_t, nb);
+      const bool two_rows = !small && (L.ks == 5 || (L.ks == 3 && ny % kConvTileY2 == 0));   // 3 x 3: only where 32-row tiles waste nothing
+      dim3 grid(tiles_x * (two_rows ? tiles_y2 : tiles_y), (L.cout + co_t - 1) / co_t, nb);
       const int pi = h->prof.start(8 * (int)(&net - h->nets) + (int)li, st);
 #define QGB_CONV(KS, CT)                                                                                         \
   conv_ffma_kernel<KS, CT><<<grid, 256, 0, st>>>(in, in_bs, out, out_bs, L.wp, L.bias, L.bn_s, L.bn_t, L.cin, L.cout, \
                                                  L.cout_pad, ny, nx, tiles_x, L.relu_bn, sp, acc)
 #define QGB_CONV2(KS, CT)                                                                                        \
-  conv_ffma2_kernel<KS, CT><<<grid, 256, 0, st>>>(in, in_bs, out, out_bs, L.wp, L.bias, L.bn_s, L.bn_t, L.cin, L.cout, \
-                                                  L.cout_pad, ny, nx, tiles_x, L.relu_bn, sp, acc)
+  CUDA_TRY(h, (launch_conv_ffma2<KS, CT>(grid, st, in, in_bs, out, out_bs, L.wp, L.bias, L.bn_s, L.bn_t, L.cin, L.cout, \
+                                         L.cout_pad, ny, nx, tiles_x, L.relu_bn, sp, acc)))
       if (L.ks == 5 && !small) QGB_CONV2(5, 32);
       else if (L.ks == 5) QGB_CONV(5, 2);
+      else if (L.ks == 3 && two_rows) QGB_CONV2(3, 32);
       else if (L.ks == 3 && !small) QGB_CONV(3, 32);
       else if (L.ks == 3) QGB_CONV(3, 2);
       else if (L.ks == 1 && !small) QGB_CONV(1, 32);

@@ -4,6 +4,7 @@
 // computes the data gradient (a circular correlation with the flipped, transposed weights).
 #pragma once
 #include <cuda_runtime.h>
+#include <stdint.h>
 
 namespace qgb {
 
@@ -97,11 +98,38 @@ __global__ void __launch_bounds__(256) conv_ffma_kernel(const float* __restrict_
 
 
 // Two output rows per thread: one CTA = 16 (x) x 32 (y) output pixels x CO_T output channels of one image, thread (px, py) owns rows
-// py and py + 16, input channels streamed 4 at a time.  Every broadcast weight load (LDS.128) now feeds 8 FFMAs instead of 4: the
-// one-row kernel above issues 9 shared-memory wavefronts per 32 FFMAs and is bound by the LSU pipe, this one 10 per 64.  The order in
-// which the products of ONE output are accumulated (input channel ascending, taps ascending) is the same, so results are bit-identical.
+// py and py + 16, input channels streamed 4 at a time.  Every broadcast weight load (LDS.128) feeds 8 FFMAs: 10 shared-memory
+// wavefronts per 64 FFMAs.  The order in which the products of ONE output are accumulated (input channel ascending, taps ascending) is
+// the same as in conv_ffma_kernel, so results are bit-identical.
+// Staging (round 2, profiles/r2_training.md): the input tile + halo and the weight slab of the NEXT channel chunk are copied
+// global -> shared with cp.async into the second half of a double buffer while the FFMAs of the current chunk run, from source
+// offsets computed once per thread -- the synchronous fill with its div / mod / wrap index arithmetic and exposed load latency was
+// 45 % of the stall samples.  Row pitch 48 (= 16 mod 32): the two 16-pixel rows of a warp hit disjoint banks.
 constexpr int kConvCi2 = 4;
 constexpr int kConvTileY2 = 2 * kConvTile;
+constexpr int kConvPitch2 = 48;
+
+template <int KS>
+struct Conv2Geom {
+  static constexpr int TW = kConvTile + KS - 1, TH = kConvTileY2 + KS - 1;
+  static constexpr int NPOS = TH * TW, PPT = (NPOS + 255) / 256;
+  static constexpr int IN_FLOATS = kConvCi2 * TH * kConvPitch2;
+};
+template <int KS, int CO_T>
+struct Conv2Smem {
+  static constexpr int BUF = Conv2Geom<KS>::IN_FLOATS + kConvCi2 * KS * KS * CO_T;      // floats per half of the double buffer
+  static constexpr size_t BYTES = 2 * (size_t)BUF * sizeof(float);
+};
+
+__device__ __forceinline__ void cp_async4(float* dst_shared, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_shared)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(float* dst_shared, const float* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_shared)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <int KS, int CO_T>
 __global__ void __launch_bounds__(256, 2) conv_ffma2_kernel(const float* __restrict__ in, long long in_bs,
@@ -111,42 +139,70 @@ __global__ void __launch_bounds__(256, 2) conv_ffma2_kernel(const float* __restr
                                                             int Cin, int Cout, int CoutPad, int ny, int nx, int tiles_x,
                                                             int relu_bn, int softplus, int accumulate) {
   static_assert(CO_T % 4 == 0, "conv_ffma2_kernel: CO_T must be a multiple of 4");
-  constexpr int PAD = KS / 2;
-  constexpr int TW = kConvTile + KS - 1, TH = kConvTileY2 + KS - 1;
-  constexpr int TWP = TW + 1;
-  __shared__ float s_in[kConvCi2][TH][TWP];
-  __shared__ __align__(16) float s_w[kConvCi2][KS * KS][CO_T];
+  using G = Conv2Geom<KS>;
+  constexpr int PAD = KS / 2, KK = KS * KS;
+  constexpr int TW = G::TW, TH = G::TH, TWP = kConvPitch2;
+  constexpr int BUF = Conv2Smem<KS, CO_T>::BUF;
+  constexpr int NW4 = kConvCi2 * KK * (CO_T / 4);
+  extern __shared__ __align__(16) float conv2_smem[];
   const int tid = threadIdx.x;
   const int px = tid % kConvTile, py = tid / kConvTile;
   const int ty0 = (blockIdx.x / tiles_x) * kConvTileY2, tx0 = (blockIdx.x % tiles_x) * kConvTile;
   const int co0 = blockIdx.y * CO_T;
   const int b = blockIdx.z;
   const float* inb = in + (long long)b * in_bs;
+  const long long plane = (long long)ny * nx;
+  // this thread's positions of the (TH x TW) tile + halo: source offset inside a channel plane, destination offset inside s_in[ci]
+  int src[G::PPT], dst[G::PPT];
+#pragma unroll
+  for (int k = 0; k < G::PPT; ++k) {
+    const int pos = tid + 256 * k;
+    const int r = pos / TW, cc = pos % TW;
+    src[k] = pos < G::NPOS ? wrap(ty0 + r - PAD, ny) * nx + wrap(tx0 + cc - PAD, nx) : -1;
+    dst[k] = r * TWP + cc;
+  }
+  auto fill = [&](int buf, int ci0) {
+    float* s_in = conv2_smem + buf * BUF;
+    float* s_w = s_in + G::IN_FLOATS;
+#pragma unroll
+    for (int ci = 0; ci < kConvCi2; ++ci) {
+      const bool live = ci0 + ci < Cin;
+      const float* pl = inb + (long long)(ci0 + ci) * plane;
+#pragma unroll
+      for (int k = 0; k < G::PPT; ++k) {
+        if (src[k] < 0) continue;
+        float* d = s_in + ci * TH * TWP + dst[k];
+        if (live) cp_async4(d, pl + src[k]); else *d = 0.f;
+      }
+    }
+    for (int e = tid; e < NW4; e += 256) {
+      const int ci = e / (KK * (CO_T / 4)), rem = e % (KK * (CO_T / 4));
+      float* d = s_w + (ci * KK) * CO_T + rem * 4;
+      if (ci0 + ci < Cin) cp_async16(d, wp + ((long long)(ci0 + ci) * KK + rem / (CO_T / 4)) * CoutPad + co0 + (rem % (CO_T / 4)) * 4);
+      else *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    cp_async_commit();
+  };
   float acc0[CO_T], acc1[CO_T];
 #pragma unroll
   for (int j = 0; j < CO_T; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; }
 
-  for (int ci0 = 0; ci0 < Cin; ci0 += kConvCi2) {
-    for (int i = tid; i < kConvCi2 * TH * TW; i += 256) {
-      const int ci = i / (TH * TW), r = (i / TW) % TH, cc = i % TW;
-      float v = 0.f;
-      if (ci0 + ci < Cin) v = inb[((long long)(ci0 + ci) * ny + wrap(ty0 + r - PAD, ny)) * nx + wrap(tx0 + cc - PAD, nx)];
-      s_in[ci][r][cc] = v;
-    }
-    for (int i = tid; i < kConvCi2 * KS * KS * CO_T; i += 256) {
-      const int ci = i / (KS * KS * CO_T), rem = i % (KS * KS * CO_T);
-      float v = 0.f;
-      if (ci0 + ci < Cin) v = wp[((long long)(ci0 + ci) * KS * KS) * CoutPad + (long long)(rem / CO_T) * CoutPad + co0 + rem % CO_T];
-      (&s_w[ci][0][0])[rem] = v;
-    }
+  fill(0, 0);
+  int buf = 0;
+  for (int ci0 = 0; ci0 < Cin; ci0 += kConvCi2, buf ^= 1) {
+    if (ci0 + kConvCi2 < Cin) { fill(buf ^ 1, ci0 + kConvCi2); cp_async_wait<1>(); } else cp_async_wait<0>();
     __syncthreads();
+    const float* s_in = conv2_smem + buf * BUF;
+    const float* s_w = s_in + G::IN_FLOATS;
 #pragma unroll 1
     for (int ci = 0; ci < kConvCi2; ++ci) {
+      const float* si = s_in + ci * TH * TWP + py * TWP + px;
+      const float* sw = s_w + ci * KK * CO_T;
 #pragma unroll
-      for (int t = 0; t < KS * KS; ++t) {
-        const float v0 = s_in[ci][py + t / KS][px + t % KS];
-        const float v1 = s_in[ci][py + kConvTile + t / KS][px + t % KS];
-        const float4* w4 = reinterpret_cast<const float4*>(&s_w[ci][t][0]);
+      for (int t = 0; t < KK; ++t) {
+        const float v0 = si[(t / KS) * TWP + t % KS];
+        const float v1 = si[(kConvTile + t / KS) * TWP + t % KS];
+        const float4* w4 = reinterpret_cast<const float4*>(sw + t * CO_T);
 #pragma unroll
         for (int j = 0; j < CO_T / 4; ++j) {
           const float4 w = w4[j];
@@ -182,6 +238,20 @@ __global__ void __launch_bounds__(256, 2) conv_ffma2_kernel(const float* __restr
       }
     }
   }
+}
+
+// launch helper: the double buffer needs more than the 48 KB default of dynamic shared memory (attribute set on every launch: it is
+// per device and the call costs nothing next to the kernel)
+template <int KS, int CO_T>
+inline cudaError_t launch_conv_ffma2(dim3 grid, cudaStream_t st, const float* in, long long in_bs, float* out, long long out_bs,
+                                     const float* wp, const float* bias, const float* bn_s, const float* bn_t, int Cin, int Cout,
+                                     int CoutPad, int ny, int nx, int tiles_x, int relu_bn, int softplus, int accumulate) {
+  constexpr size_t smem = Conv2Smem<KS, CO_T>::BYTES;
+  cudaError_t e = cudaFuncSetAttribute(conv_ffma2_kernel<KS, CO_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  conv_ffma2_kernel<KS, CO_T><<<grid, 256, smem, st>>>(in, in_bs, out, out_bs, wp, bias, bn_s, bn_t, Cin, Cout, CoutPad, ny, nx,
+                                                       tiles_x, relu_bn, softplus, accumulate);
+  return cudaGetLastError();
 }
 
 }  // namespace qgb

@@ -181,16 +181,23 @@ struct WgGeom {
   static constexpr int D_PITCH = kWgTile * kWgTile + 1;
 };
 
-template <int KS, int CI_T, int CO_PER>
-__global__ void __launch_bounds__(256, (CO_PER * KS * KS <= 60 ? 2 : 1)) wgrad_ffma_kernel(const float* __restrict__ a, const float* __restrict__ dz,
+// DB: the input tile and the output-gradient tile of the NEXT work item are copied global -> shared with cp.async into the second
+// half of a double buffer while the FFMAs of the current item run (the synchronous fill left 42 % of the stall samples waiting on
+// those loads, profiles/r2_training.md); needs 2 x the shared memory, so one block per SM.
+__device__ __forceinline__ int wrap_near(int v, int n) {      // v within one period of [0, n) in the common case
+  if (v < 0) v += n; else if (v >= n) v -= n;
+  return (unsigned)v < (unsigned)n ? v : wrap(v, n);
+}
+
+template <int KS, int CI_T, int CO_PER, int DB>
+__global__ void __launch_bounds__(256, ((CO_PER * KS * KS <= 60 && !DB) ? 2 : 1)) wgrad_ffma_kernel(const float* __restrict__ a, const float* __restrict__ dz,
                                                             float* __restrict__ part, int batch, int Cin, int Cout, int ny, int nx,
                                                             int ci_blocks) {
   using G = WgGeom<KS>;
   constexpr int PAD = KS / 2, TW = G::TW, KK = KS * KS;
   constexpr int CG = 256 / CI_T, CO_B = CG * CO_PER;
+  constexpr int A_FLOATS = CI_T * G::CI_STRIDE, BUF = A_FLOATS + CO_B * G::D_PITCH;
   extern __shared__ float smem[];
-  float* s_a = smem;                              // [CI_T][CI_STRIDE]
-  float* s_d = smem + CI_T * G::CI_STRIDE;        // [CO_B][D_PITCH]
   const int tid = threadIdx.x;
   const int ci_l = tid % CI_T, cg = tid / CI_T;
   const int ci0 = (blockIdx.x % ci_blocks) * CI_T, co0 = (blockIdx.x / ci_blocks) * CO_B;
@@ -202,27 +209,43 @@ __global__ void __launch_bounds__(256, (CO_PER * KS * KS <= 60 ? 2 : 1)) wgrad_f
 #pragma unroll
     for (int t = 0; t < KK; ++t) acc[j][t] = 0.f;
 
-  for (int it = blockIdx.y; it < items; it += gridDim.y) {
+  auto fill = [&](int buf, int it) {
+    float* s_a = smem + buf * BUF;                  // [CI_T][CI_STRIDE]
+    float* s_d = s_a + A_FLOATS;                    // [CO_B][D_PITCH]
     const int b = it / (tiles_x * tiles_y), tt = it % (tiles_x * tiles_y);
     const int ty0 = (tt / tiles_x) * kWgTile, tx0 = (tt % tiles_x) * kWgTile;
     const float* ab = a + (long long)b * Cin * ny * nx;
     const float* db = dz + (long long)b * Cout * ny * nx;
     for (int i = tid; i < CI_T * TW * TW; i += 256) {
       const int ci = i / (TW * TW), rr = (i / TW) % TW, cc = i % TW;
-      float v = 0.f;
-      if (ci0 + ci < Cin) v = ab[((long long)(ci0 + ci) * ny + wrap(ty0 + rr - PAD, ny)) * nx + wrap(tx0 + cc - PAD, nx)];
-      s_a[ci * G::CI_STRIDE + rr * TW + cc] = v;
+      float* d = s_a + ci * G::CI_STRIDE + rr * TW + cc;
+      const bool live = ci0 + ci < Cin;
+      const float* src = ab + ((long long)(ci0 + ci) * ny + wrap_near(ty0 + rr - PAD, ny)) * nx + wrap_near(tx0 + cc - PAD, nx);
+      if (DB) { if (live) cp_async4(d, src); else *d = 0.f; }
+      else *d = live ? *src : 0.f;
     }
     for (int i = tid; i < CO_B * kWgTile * kWgTile; i += 256) {
       const int co = i / (kWgTile * kWgTile), p = i % (kWgTile * kWgTile);
       const int y = ty0 + p / kWgTile, x = tx0 + p % kWgTile;
-      float v = 0.f;
-      if (co0 + co < Cout && y < ny && x < nx) v = db[((long long)(co0 + co) * ny + y) * nx + x];
-      s_d[co * G::D_PITCH + p] = v;
+      float* d = s_d + co * G::D_PITCH + p;
+      const bool live = co0 + co < Cout && y < ny && x < nx;
+      const float* src = db + ((long long)(co0 + co) * ny + y) * nx + x;
+      if (DB) { if (live) cp_async4(d, src); else *d = 0.f; }
+      else *d = live ? *src : 0.f;
     }
+    if (DB) cp_async_commit();
+  };
+
+  int it = blockIdx.y, buf = 0;
+  if (DB && it < items) fill(0, it);
+  for (; it < items; it += gridDim.y) {
+    if (DB) {
+      const int next = it + gridDim.y;
+      if (next < items) { fill(buf ^ 1, next); cp_async_wait<1>(); } else cp_async_wait<0>();
+    } else fill(0, it);
     __syncthreads();
-    const float* sa = s_a + ci_l * G::CI_STRIDE;
-    const float* sd = s_d + (cg * CO_PER) * G::D_PITCH;
+    const float* sa = smem + buf * BUF + ci_l * G::CI_STRIDE;
+    const float* sd = smem + buf * BUF + A_FLOATS + (cg * CO_PER) * G::D_PITCH;
 #pragma unroll 1
     for (int py = 0; py < kWgTile; ++py) {
       float win[KS][KS];                             // win[ky][kx] = input at (py + ky, px + kx)
@@ -249,6 +272,7 @@ __global__ void __launch_bounds__(256, (CO_PER * KS * KS <= 60 ? 2 : 1)) wgrad_f
       }
     }
     __syncthreads();
+    if (DB) buf ^= 1;
   }
   const int ci = ci0 + ci_l;
   if (ci < Cin) {

@@ -87,12 +87,14 @@ int conv(qgb_trainer* t, const float* in, float* out, const float* wp, const flo
   const int tiles_y2 = (ny + kConvTileY2 - 1) / kConvTileY2;
   const bool small = cout <= 4;
   const int co_t = small ? 2 : 32, cpad = co_pad_of(cout);
-  dim3 grid(tiles_x * ((small || ks != 5) ? tiles_y : tiles_y2), (cout + co_t - 1) / co_t, batch);
+  const bool two_rows = !small && (ks == 5 || (ks == 3 && ny % kConvTileY2 == 0));   // 3 x 3: only where 32-row tiles waste nothing
+  dim3 grid(tiles_x * (two_rows ? tiles_y2 : tiles_y), (cout + co_t - 1) / co_t, batch);
   const long long ibs = (long long)cin * ny * nx, obs = (long long)cout * ny * nx;
 #define QGB_TCONV(KS, CT) conv_ffma_kernel<KS, CT><<<grid, 256, 0, st>>>(in, ibs, out, obs, wp, bias, s, sh, cin, cout, cpad, ny, nx, tiles_x, relu_affine, 0, 0)
-#define QGB_TCONV2(KS, CT) conv_ffma2_kernel<KS, CT><<<grid, 256, 0, st>>>(in, ibs, out, obs, wp, bias, s, sh, cin, cout, cpad, ny, nx, tiles_x, relu_affine, 0, 0)
+#define QGB_TCONV2(KS, CT) TR_TRY(t, (launch_conv_ffma2<KS, CT>(grid, st, in, ibs, out, obs, wp, bias, s, sh, cin, cout, cpad, ny, nx, tiles_x, relu_affine, 0, 0)))
   if (ks == 5 && !small) QGB_TCONV2(5, 32);
   else if (ks == 5) QGB_TCONV(5, 2);
+  else if (ks == 3 && two_rows) QGB_TCONV2(3, 32);
   else if (ks == 3 && !small) QGB_TCONV(3, 32);
   else if (ks == 3) QGB_TCONV(3, 2);
   else if (ks == 1 && !small) QGB_TCONV(1, 32);
@@ -123,12 +125,12 @@ int chan_reduce(qgb_trainer* t, const float* x, const float* r, const float* mea
   return QGB_OK;
 }
 
-template <int KS, int CI_T, int CO_PER>
+template <int KS, int CI_T, int CO_PER, int DB = 0>
 int wgrad_launch(qgb_trainer* t, const float* a, const float* dz, float* dW, int cin, int cout, int batch, cudaStream_t st) {
   using G = WgGeom<KS>;
   constexpr int CO_B = (256 / CI_T) * CO_PER;
-  const size_t smem = (size_t)(CI_T * G::CI_STRIDE + CO_B * G::D_PITCH) * sizeof(float);
-  auto kern = wgrad_ffma_kernel<KS, CI_T, CO_PER>;
+  const size_t smem = (size_t)(DB ? 2 : 1) * (CI_T * G::CI_STRIDE + CO_B * G::D_PITCH) * sizeof(float);
+  auto kern = wgrad_ffma_kernel<KS, CI_T, CO_PER, DB>;
   TR_TRY(t, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int ci_blocks = (cin + CI_T - 1) / CI_T, co_blocks = (cout + CO_B - 1) / CO_B;
   const int tiles = ((t->nx + kWgTile - 1) / kWgTile) * ((t->ny + kWgTile - 1) / kWgTile);
@@ -158,7 +160,7 @@ int wgrad(qgb_trainer* t, const float* a, const float* dz, float* dW, int cin, i
     if (thin_out) return wgrad_launch<5, 32, 1>(t, a, dz, dW, cin, cout, batch, st);
     // 4 output channels per thread, one block per SM: 4.3 ms for the 128 -> 64 layer (64 images, 64^2); the 2-channel variant with two
     // blocks per SM measured 6.2 ms
-    return wgrad_launch<5, 32, 4>(t, a, dz, dW, cin, cout, batch, st);
+    return wgrad_launch<5, 32, 4, 1>(t, a, dz, dW, cin, cout, batch, st);     // cp.async double buffer (one block per SM anyway)
   }
   if (ks == 3) {
     if (thin_in) return wgrad_launch<3, 4, 2>(t, a, dz, dW, cin, cout, batch, st);
