@@ -97,10 +97,11 @@ __global__ void __launch_bounds__(256) conv_ffma_kernel(const float* __restrict_
 }
 
 
-// Two output rows per thread: one CTA = 16 (x) x 32 (y) output pixels x CO_T output channels of one image, thread (px, py) owns rows
-// py and py + 16, input channels streamed 4 at a time.  Every broadcast weight load (LDS.128) feeds 8 FFMAs: 10 shared-memory
-// wavefronts per 64 FFMAs.  The order in which the products of ONE output are accumulated (input channel ascending, taps ascending) is
-// the same as in conv_ffma_kernel, so results are bit-identical.
+// Register-tiled variant for the wide layers: one CTA = 16 (x) x 32 (y) output pixels x CO_T output channels of one image, a thread owns
+// 4 adjacent pixels of one row x CO_T / 2 channels, input channels streamed 4 at a time.  Per input channel and tap row the thread reads
+// its 8 input values with two aligned LDS.128 and every broadcast weight load (LDS.128) feeds 16 FFMAs: 28 shared-memory wavefronts per
+// 320 FFMAs (the one-pixel kernel above: 9 per 32 and bound by the LSU pipe).  The order in which the products of ONE output are
+// accumulated (input channel ascending, taps ascending) is the same as in conv_ffma_kernel, so results are bit-identical.
 // Staging (round 2, profiles/r2_training.md): the input tile + halo and the weight slab of the NEXT channel chunk are copied
 // global -> shared with cp.async into the second half of a double buffer while the FFMAs of the current chunk run, from source
 // offsets computed once per thread -- the synchronous fill with its div / mod / wrap index arithmetic and exposed load latency was
@@ -146,7 +147,6 @@ __global__ void __launch_bounds__(256, 2) conv_ffma2_kernel(const float* __restr
   constexpr int NW4 = kConvCi2 * KK * (CO_T / 4);
   extern __shared__ __align__(16) float conv2_smem[];
   const int tid = threadIdx.x;
-  const int px = tid % kConvTile, py = tid / kConvTile;
   const int ty0 = (blockIdx.x / tiles_x) * kConvTileY2, tx0 = (blockIdx.x % tiles_x) * kConvTile;
   const int co0 = blockIdx.y * CO_T;
   const int b = blockIdx.z;
@@ -183,9 +183,15 @@ __global__ void __launch_bounds__(256, 2) conv_ffma2_kernel(const float* __restr
     }
     cp_async_commit();
   };
-  float acc0[CO_T], acc1[CO_T];
+  // thread = 4 adjacent pixels (x) of one row x 16 output channels: pixel group pxg (4 per row), row pr (32 per tile), channel half ch
+  constexpr int CH = CO_T / 2;
+  static_assert(CH % 4 == 0, "conv_ffma2_kernel: CO_T must be a multiple of 8");
+  const int pxg = tid % 4, pr = (tid / 4) % kConvTileY2, ch = tid / 128;
+  float acc[4][CH];
 #pragma unroll
-  for (int j = 0; j < CO_T; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; }
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int j = 0; j < CH; ++j) acc[p][j] = 0.f;
 
   fill(0, 0);
   int buf = 0;
@@ -196,44 +202,50 @@ __global__ void __launch_bounds__(256, 2) conv_ffma2_kernel(const float* __restr
     const float* s_w = s_in + G::IN_FLOATS;
 #pragma unroll 1
     for (int ci = 0; ci < kConvCi2; ++ci) {
-      const float* si = s_in + ci * TH * TWP + py * TWP + px;
-      const float* sw = s_w + ci * KK * CO_T;
+      const float* si = s_in + ci * TH * TWP + pr * TWP + pxg * 4;
+      const float* sw = s_w + ci * KK * CO_T + ch * CH;
 #pragma unroll
-      for (int t = 0; t < KK; ++t) {
-        const float v0 = si[(t / KS) * TWP + t % KS];
-        const float v1 = si[(kConvTile + t / KS) * TWP + t % KS];
-        const float4* w4 = reinterpret_cast<const float4*>(sw + t * CO_T);
+      for (int ky = 0; ky < KS; ++ky) {
+        // the 4 + KS - 1 <= 8 input values of this row that the thread's 4 pixels see: two aligned 16-byte loads
+        const float4 lo = *reinterpret_cast<const float4*>(si + ky * TWP);
+        const float4 hi = *reinterpret_cast<const float4*>(si + ky * TWP + 4);
+        const float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
 #pragma unroll
-        for (int j = 0; j < CO_T / 4; ++j) {
-          const float4 w = w4[j];
-          acc0[4 * j + 0] = fmaf(v0, w.x, acc0[4 * j + 0]);
-          acc0[4 * j + 1] = fmaf(v0, w.y, acc0[4 * j + 1]);
-          acc0[4 * j + 2] = fmaf(v0, w.z, acc0[4 * j + 2]);
-          acc0[4 * j + 3] = fmaf(v0, w.w, acc0[4 * j + 3]);
-          acc1[4 * j + 0] = fmaf(v1, w.x, acc1[4 * j + 0]);
-          acc1[4 * j + 1] = fmaf(v1, w.y, acc1[4 * j + 1]);
-          acc1[4 * j + 2] = fmaf(v1, w.z, acc1[4 * j + 2]);
-          acc1[4 * j + 3] = fmaf(v1, w.w, acc1[4 * j + 3]);
+        for (int kx = 0; kx < KS; ++kx) {
+          const float4* w4 = reinterpret_cast<const float4*>(sw + (ky * KS + kx) * CO_T);
+#pragma unroll
+          for (int j = 0; j < CH / 4; ++j) {
+            const float4 w = w4[j];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+              acc[p][4 * j + 0] = fmaf(v[p + kx], w.x, acc[p][4 * j + 0]);
+              acc[p][4 * j + 1] = fmaf(v[p + kx], w.y, acc[p][4 * j + 1]);
+              acc[p][4 * j + 2] = fmaf(v[p + kx], w.z, acc[p][4 * j + 2]);
+              acc[p][4 * j + 3] = fmaf(v[p + kx], w.w, acc[p][4 * j + 3]);
+            }
+          }
         }
       }
     }
     __syncthreads();
   }
-  const int x = tx0 + px;
+  const int y = ty0 + pr, x0 = tx0 + pxg * 4;
+  if (y < ny) {
+    float* ob = out + (long long)b * out_bs;
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int y = ty0 + py + h * kConvTile;
-    if (y < ny && x < nx) {
-      float* ob = out + (long long)b * out_bs;
+    for (int j = 0; j < CH; ++j) {
+      const int co = co0 + ch * CH + j;
+      if (co < Cout) {
+        const float bi = bias[co], sc = relu_bn ? bn_s[co] : 1.f, sh = relu_bn ? bn_t[co] : 0.f;
+        float* o = ob + ((long long)co * ny + y) * nx + x0;
 #pragma unroll
-      for (int j = 0; j < CO_T; ++j) {
-        const int co = co0 + j;
-        if (co < Cout) {
-          float v = (h ? acc1[j] : acc0[j]) + bias[co];
-          if (relu_bn) v = fmaxf(v, 0.f) * bn_s[co] + bn_t[co];
-          if (softplus) v = v > 20.f ? v : log1pf(expf(v));  // torch softplus, beta=1, threshold=20
-          float* o = ob + ((long long)co * ny + y) * nx + x;
-          *o = accumulate ? *o + v : v;
+        for (int p = 0; p < 4; ++p) {
+          if (x0 + p < nx) {
+            float v = acc[p][j] + bi;
+            if (relu_bn) v = fmaxf(v, 0.f) * sc + sh;
+            if (softplus) v = v > 20.f ? v : log1pf(expf(v));  // torch softplus, beta=1, threshold=20
+            o[p] = accumulate ? o[p] + v : v;
+          }
         }
       }
     }

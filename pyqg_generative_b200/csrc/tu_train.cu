@@ -165,7 +165,7 @@ int wgrad(qgb_trainer* t, const float* a, const float* dz, float* dW, int cin, i
   if (ks == 3) {
     if (thin_in) return wgrad_launch<3, 4, 2>(t, a, dz, dW, cin, cout, batch, st);
     if (thin_out) return wgrad_launch<3, 32, 1>(t, a, dz, dW, cin, cout, batch, st);
-    return wgrad_launch<3, 32, 4>(t, a, dz, dW, cin, cout, batch, st);
+    return wgrad_launch<3, 32, 4, 1>(t, a, dz, dW, cin, cout, batch, st);
   }
   if (ks == 1) {
     if (thin_in) return wgrad_launch<1, 4, 2>(t, a, dz, dW, cin, cout, batch, st);
