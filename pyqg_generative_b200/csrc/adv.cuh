@@ -126,60 +126,92 @@ __global__ void axpy_kernel(float* __restrict__ y, const float* __restrict__ x, 
 // against the packed weights Wp[co][(ky, kx, ci)]: forward  z = col Wp^T,  data gradient  dcol = dz Wp,  weight gradient
 // dWp = dz^T col.  The last layer (k5 x k5 valid convolution of the k5 x k5 map) is the same GEMM on the activation itself.
 
-constexpr int kGemmTile = 64, kGemmK = 16;
+constexpr int kGemmM = 128, kGemmK = 8, kGemmPitch = kGemmM + 4;
 
-// C[i][j] (+ epilogue) = sum_k A(i, k) B(k, j),  A(i, k) = A[i sai + k sak],  B(k, j) = B[k sbk + j sbj].
+// C[i][j] (+ epilogue) = sum_k A(i, k) B(k, j),  A(i, k) = A[i sai + k sak],  B(k, j) = B[k sbk + j sbj]  (one of each pair of
+// strides is 1: the loader walks the unit-stride direction).  Block tile 128 x BN (BN = 128 or 64), depth 8 per stage, 256 threads
+// with an 8 x (BN / 16) register tile each: per k one thread issues 2 + BN/64 LDS.128 for 8 BN/16 FFMAs.  The next stage is fetched
+// into registers while the current one is multiplied (shared memory double-buffered, one barrier per stage).
 // blockIdx.z splits the k range into chunks of ksplit (partial results at C + z c_split); EPI 0: none, 1: LeakyReLU(0.2),
 // 2: times the LeakyReLU slope of mask[i ldc + j] (1 where mask > 0, else 0.2).
-template <int EPI>
-__global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A, long long sai, long long sak,
-                                                    const float* __restrict__ B, long long sbk, long long sbj, float* __restrict__ C,
-                                                    long long ldc, int M, int N, int K, int ksplit, long long c_split,
-                                                    const float* __restrict__ mask) {
-  __shared__ float As[kGemmK][kGemmTile + 4];
-  __shared__ float Bs[kGemmK][kGemmTile + 4];
+template <int EPI, int BN>
+__global__ void __launch_bounds__(256, 2) sgemm_kernel(const float* __restrict__ A, long long sai, long long sak,
+                                                       const float* __restrict__ B, long long sbk, long long sbj, float* __restrict__ C,
+                                                       long long ldc, int M, int N, int K, int ksplit, long long c_split,
+                                                       const float* __restrict__ mask) {
+  constexpr int TN = BN / 16;                       // columns per thread
+  constexpr int NB = BN * kGemmK / 256;             // B elements fetched per thread and stage (4 or 2)
+  __shared__ __align__(16) float As[2][kGemmK][kGemmPitch];
+  __shared__ __align__(16) float Bs[2][kGemmK][BN + 4];
   const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
-  const int i0 = blockIdx.y * kGemmTile, j0 = blockIdx.x * kGemmTile;
+  const int i0 = blockIdx.y * kGemmM, j0 = blockIdx.x * BN;
   const int kbeg = blockIdx.z * ksplit, kend = min(K, kbeg + ksplit);
-  float acc[4][4];
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
   const bool a_kfast = sak == 1, b_kfast = sbk == 1;
-  for (int k0 = kbeg; k0 < kend; k0 += kGemmK) {
+  float acc[8][TN];
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int b = 0; b < TN; ++b) acc[a][b] = 0.f;
+  float ra[4], rb[NB];
+  auto fetch = [&](int k0) {
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-      int i, k;
-      if (a_kfast) { k = tid % 16; i = tid / 16 + 16 * r; } else { i = tid % 64; k = tid / 64 + 4 * r; }
+      const int k = a_kfast ? tid % 8 : tid / 128 + 2 * r, i = a_kfast ? tid / 8 + 32 * r : tid % 128;
       const int gi = i0 + i, gk = k0 + k;
-      As[k][i] = (gi < M && gk < kend) ? A[gi * sai + gk * sak] : 0.f;
-      int j, kb;
-      if (b_kfast) { kb = tid % 16; j = tid / 16 + 16 * r; } else { j = tid % 64; kb = tid / 64 + 4 * r; }
-      const int gj = j0 + j, gkb = k0 + kb;
-      Bs[kb][j] = (gj < N && gkb < kend) ? B[gkb * sbk + gj * sbj] : 0.f;
+      ra[r] = (gi < M && gk < kend) ? A[gi * sai + gk * sak] : 0.f;
     }
-    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < NB; ++r) {
+      const int k = b_kfast ? tid % 8 : tid / BN + (256 / BN) * r, j = b_kfast ? tid / 8 + 32 * r : tid % BN;
+      const int gj = j0 + j, gk = k0 + k;
+      rb[r] = (gj < N && gk < kend) ? B[gk * sbk + gj * sbj] : 0.f;
+    }
+  };
+  auto stash = [&](int buf) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int k = a_kfast ? tid % 8 : tid / 128 + 2 * r, i = a_kfast ? tid / 8 + 32 * r : tid % 128;
+      As[buf][k][i] = ra[r];
+    }
+#pragma unroll
+    for (int r = 0; r < NB; ++r) {
+      const int k = b_kfast ? tid % 8 : tid / BN + (256 / BN) * r, j = b_kfast ? tid / 8 + 32 * r : tid % BN;
+      Bs[buf][k][j] = rb[r];
+    }
+  };
+  fetch(kbeg);
+  stash(0);
+  __syncthreads();
+  int buf = 0;
+  for (int k0 = kbeg; k0 < kend; k0 += kGemmK, buf ^= 1) {
+    const bool more = k0 + kGemmK < kend;
+    if (more) fetch(k0 + kGemmK);
 #pragma unroll
     for (int k = 0; k < kGemmK; ++k) {
-      const float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
-      const float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-      const float a4[4] = {av.x, av.y, av.z, av.w}, b4[4] = {bv.x, bv.y, bv.z, bv.w};
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 8 + 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      float bv[TN];
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
+      for (int q = 0; q < TN / 4; ++q) {
+        const float4 b4 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * TN + 4 * q]);
+        bv[4 * q] = b4.x; bv[4 * q + 1] = b4.y; bv[4 * q + 2] = b4.z; bv[4 * q + 3] = b4.w;
+      }
 #pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(a4[a], b4[b], acc[a][b]);
+      for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < TN; ++b) acc[a][b] = fmaf(av[a], bv[b], acc[a][b]);
     }
-    __syncthreads();
+    if (more) { stash(buf ^ 1); __syncthreads(); }
   }
   float* Cz = C + (long long)blockIdx.z * c_split;
 #pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    const int gi = i0 + ty * 4 + a;
+  for (int a = 0; a < 8; ++a) {
+    const int gi = i0 + ty * 8 + a;
     if (gi >= M) continue;
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      const int gj = j0 + tx * 4 + b;
+    for (int b = 0; b < TN; ++b) {
+      const int gj = j0 + tx * TN + b;
       if (gj >= N) continue;
       float v = acc[a][b];
       if (EPI == 1) v = v > 0.f ? v : 0.2f * v;
@@ -187,6 +219,22 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
       Cz[gi * ldc + gj] = v;
     }
   }
+}
+
+// last layer (one output channel): out[b] = sum_k x[b][k] w[k], one block per sample (a GEMM with N = 1 would run on two blocks)
+__global__ void __launch_bounds__(256) rowdot_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ out,
+                                                     int K) {
+  const float* xb = x + (long long)blockIdx.x * K;
+  float s = 0.f;
+  for (int k = threadIdx.x; k < K; k += 256) s = fmaf(xb[k], w[k], s);
+  __shared__ float sh[256];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int h = 128; h > 0; h >>= 1) {
+    if ((int)threadIdx.x < h) sh[threadIdx.x] += sh[threadIdx.x + h];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[blockIdx.x] = sh[0];
 }
 
 // (cout, cin, ks, ks) -> Wp[co][(ky, kx, ci)]  (dir 0)  or the same permutation back (dir 1: packed gradient -> torch layout,

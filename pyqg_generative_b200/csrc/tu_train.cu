@@ -609,8 +609,13 @@ int gemm(qgb_disc* d, const float* A, long long sai, long long sak, const float*
   int ksplit = (K + splits - 1) / splits;
   ksplit = (ksplit + kGemmK - 1) / kGemmK * kGemmK;
   splits = (K + ksplit - 1) / ksplit;
-  dim3 grid((N + kGemmTile - 1) / kGemmTile, (M + kGemmTile - 1) / kGemmTile, splits);
-  sgemm_kernel<EPI><<<grid, 256, 0, st>>>(A, sai, sak, B, sbk, sbj, C, ldc, M, N, K, ksplit, c_split, mask);
+  if (N > 64) {
+    dim3 grid((N + 127) / 128, (M + kGemmM - 1) / kGemmM, splits);
+    sgemm_kernel<EPI, 128><<<grid, 256, 0, st>>>(A, sai, sak, B, sbk, sbj, C, ldc, M, N, K, ksplit, c_split, mask);
+  } else {
+    dim3 grid((N + 63) / 64, (M + kGemmM - 1) / kGemmM, splits);
+    sgemm_kernel<EPI, 64><<<grid, 256, 0, st>>>(A, sai, sak, B, sbk, sbj, C, ldc, M, N, K, ksplit, c_split, mask);
+  }
   d->launches++;
   D_TRY(d, cudaGetLastError());
   return splits;       // (>= 1; errors are negative QGB codes)
@@ -639,9 +644,10 @@ int disc_forward(qgb_disc* d, int b0, int nb, cudaStream_t st) {
     if (rc < 0) return rc;
   }
   const auto& L = d->L[4];
-  int rc = gemm<0>(d, d->h[4] + b0 * d->act(4), (long long)L.K, 1, d->Wp + L.w, 1, (long long)L.K, d->o + b0, 1, nb, 1, (int)L.K, 1, 0,
-                   nullptr, st);
-  return rc < 0 ? rc : QGB_OK;
+  rowdot_kernel<<<nb, 256, 0, st>>>(d->h[4] + b0 * d->act(4), d->Wp + L.w, d->o + b0, (int)L.K);
+  d->launches++;
+  D_TRY(d, cudaGetLastError());
+  return QGB_OK;
 }
 
 // data gradients of samples [b0, b0 + nb) from dl[4] down to dl[0]; the gradient with respect to the input (e0, unmasked) for the
@@ -703,7 +709,8 @@ int disc_wgrad(qgb_disc* d, int nA, int nU, cudaStream_t st) {
       D_TRY(d, cudaMemcpyAsync(d->col, d->h[4], (size_t)nA * L.K * sizeof(float), cudaMemcpyDeviceToDevice, st));
       if (nU) D_TRY(d, cudaMemcpyAsync(d->col + (size_t)nA * L.K, d->u[4], (size_t)nU * L.K * sizeof(float), cudaMemcpyDeviceToDevice, st));
     }
-    const int tiles = ((L.cout + kGemmTile - 1) / kGemmTile) * (((int)L.K + kGemmTile - 1) / kGemmTile);
+    const int bn = (int)L.K > 64 ? 128 : 64;
+    const int tiles = ((L.cout + kGemmM - 1) / kGemmM) * (((int)L.K + bn - 1) / bn);
     int splits = (2 * 148 + tiles - 1) / tiles;
     if (splits > (Mred + kGemmK - 1) / kGemmK) splits = (Mred + kGemmK - 1) / kGemmK;
     if (splits < 1) splits = 1;
