@@ -129,21 +129,18 @@ def _values(v):
 
 
 def loss_to_log(optim_loss, log_train, log_test, name='L2_loss'):
-    """cvae_regression.py:245-255 / cgan_regression.py:210-220 without xarray: per-epoch series of the optimisation losses, the
-    train scores, the test scores (suffix ``_test``), ``name`` = L2_total_test + L2_residual_test and the epoch (1-based) where
-    it is smallest.  var_ratio (lev,) is stored per layer as var_ratio_0 / var_ratio_1."""
+    """cvae_regression.py:245-255 / cgan_regression.py:210-220 without xarray, with the variables of the shipped
+    Google-Colab/{VAE,GAN}/stats.nc: per-epoch series of the optimisation losses, the train scores, the test scores (suffix
+    ``_test``), ``var_ratio`` (epoch, lev) -- the reference's ``ds.update`` leaves the TEST values there, the rename only covers the
+    L2 scores --, ``name`` = L2_total_test + L2_residual_test and the scalar ``Epoch_opt`` = the epoch (1-based) where it is smallest."""
     out = {k: list(v) for k, v in optim_loss.items()}
-
-    def put(logs, postfix):
-        for key in ('L2_mean', 'L2_total', 'L2_residual'):
-            out[key + postfix] = [float(l[key]) for l in logs]
-        for z in range(2):
-            out['var_ratio_%d%s' % (z, postfix)] = [float(np.asarray(l['var_ratio'])[z]) for l in logs]
-    put(log_train, '')
-    put(log_test, '_test')
+    for key in ('L2_mean', 'L2_total', 'L2_residual'):
+        out[key] = [float(l[key]) for l in log_train]
+        out[key + '_test'] = [float(l[key]) for l in log_test]
+    out['var_ratio'] = np.array([np.asarray(l['var_ratio'], dtype=np.float64).reshape(2) for l in log_test])
     out[name] = [a + b for a, b in zip(out['L2_total_test'], out['L2_residual_test'])]
     epoch_opt = int(np.argmin(out[name])) + 1
-    out['Epoch_opt'] = [float(epoch_opt)] * len(out[name])
+    out['Epoch_opt'] = float(epoch_opt)
     return out, epoch_opt
 
 

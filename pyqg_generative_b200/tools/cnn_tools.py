@@ -660,17 +660,37 @@ def prepare_PV_data(ds_train, ds_test):
 
 
 def write_log(log_dict, path):
-    """cnn_tools.py:12-19 ``log_to_xarray(log_dict).to_netcdf(path)`` without xarray: one float64 variable per key over the
-    coordinate ``epoch`` = 1..num_epochs (NetCDF-3, opens with xarray)."""
+    """cnn_tools.py:12-19 ``log_to_xarray(log_dict).to_netcdf(path)`` (and the ``stats.nc`` of the CVAE / CGAN trainers,
+    models/cvae_regression.py:245-255) without xarray, in the layout of the shipped logs (Google-Colab/{GAN,VAE}/stats.nc,
+    GZ/stats_var.nc: NetCDF-3 64-bit offset): coordinate ``epoch`` = 1..E (int32, long_name 'epoch'); one float64 variable over
+    ``epoch`` per list-valued key; 2-D arrays (E, 2) as float32 over (``epoch``, ``lev``) with the coordinate ``lev`` = [1, 2]
+    (long_name 'vertical levels'); python scalars as 0-d float64 variables.  Opens with xarray."""
     from scipy.io import netcdf_file
-    n = len(next(iter(log_dict.values())))
+    series = {k: np.asarray(v) for k, v in log_dict.items()}
+    n = max(a.shape[0] for a in series.values() if a.ndim >= 1)
     with netcdf_file(path, 'w', version=2) as f:
         f.createDimension('epoch', n)
         v = f.createVariable('epoch', 'i', ('epoch',))
         v[:] = np.arange(1, n + 1, dtype=np.int32)
-        for k, series in log_dict.items():
-            v = f.createVariable(k, 'd', ('epoch',))
-            v[:] = np.asarray(series, dtype=np.float64)
+        v.long_name = 'epoch'
+        if any(a.ndim == 2 for a in series.values()):
+            f.createDimension('lev', 2)
+            v = f.createVariable('lev', 'i', ('lev',))
+            v[:] = np.array([1, 2], dtype=np.int32)
+            v.long_name = 'vertical levels'
+        for k, a in series.items():
+            if a.ndim == 2:
+                v = f.createVariable(k, 'f', ('epoch', 'lev'))
+                v[:] = a.astype(np.float32)
+                v._FillValue = np.float32(np.nan)
+            elif a.ndim == 1:
+                v = f.createVariable(k, 'd', ('epoch',))
+                v[:] = a.astype(np.float64)
+                v._FillValue = np.float64(np.nan)
+            else:
+                v = f.createVariable(k, 'd', ())
+                v.data[...] = float(a)
+                v._FillValue = np.float64(np.nan)
     return path
 
 

@@ -25,6 +25,7 @@ training_cvae.npz  CVAERegression.compute_loss (ELBO, adaptive and fixed decoder
                    encoder / decoder pair with the recorded reparameterisation noise, and a whole ``train_CVAE`` run (4 epochs, batch 8)
 training_cgan.npz  a whole ``train_CGAN`` run (WGAN-GP, 2 epochs x 6 iterations, small G, DCGAN_discriminator with ndf = 8 at 64 x 64) with
                    seeded random draws: the gradients the two Adam optimizers saw in the first iteration, the loss logs, final G / D
+stats_layout.json  variables / dimensions / dtypes of the shipped training logs (Google-Colab/{GAN,VAE}/stats.nc, GZ/stats_var.nc)
 training.npz       the reference's training arithmetic on a small AndrewCNN (2 -> 16 -> 12 -> 12 -> 8 -> 2, 16 x 16 images):
                    loss and autograd gradients of ``compute_loss`` in training mode for AndrewCNN and VarCNN (softplus head),
                    BatchNorm running statistics after that forward, and a whole ``cnn_tools.train`` run (4 epochs, batch 8,
@@ -445,7 +446,27 @@ def cgan_fixture():
     np.savez_compressed(os.path.join(HERE, 'training_cgan.npz'), **out)
 
 
+def stats_layout_fixture():
+    """Variables, dimensions, dtypes and coordinate values of the training logs the reference ships (Google-Colab/{GAN,VAE}/stats.nc,
+    GZ/stats_var.nc; written by ``loss_to_xarray(...).to_netcdf`` / ``log_to_xarray``): what our ``write_log`` must reproduce."""
+    import json
+    from scipy.io import netcdf_file
+    out = {}
+    for tag, rel_path in (('GAN', 'GAN/stats.nc'), ('VAE', 'VAE/stats.nc'), ('GZ_var', 'GZ/stats_var.nc')):
+        with open(os.path.join(COLAB, rel_path), 'rb') as fh:
+            magic = fh.read(4)
+        with netcdf_file(os.path.join(COLAB, rel_path), 'r', mmap=False) as nc:
+            out[tag] = dict(magic=list(magic), variables={k: dict(dims=list(v.dimensions), dtype=v.data.dtype.str) for k, v in nc.variables.items()},
+                            lev=[int(x) for x in nc.variables['lev'][:]] if 'lev' in nc.variables else None,
+                            epoch_first=int(nc.variables['epoch'][0]))
+    with open(os.path.join(HERE, 'stats_layout.json'), 'w') as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+
+
 if __name__ == '__main__':
+    if '--stats-layout' in sys.argv:
+        stats_layout_fixture()
+        sys.exit(0)
     if '--cgan' in sys.argv:
         cgan_fixture()
         sys.exit(0)
@@ -474,5 +495,6 @@ if __name__ == '__main__':
     training_fixture()
     cvae_fixture()
     cgan_fixture()
+    stats_layout_fixture()
     for f in sorted(os.listdir(HERE)):
         print('%10d  %s' % (os.path.getsize(os.path.join(HERE, f)), f))

@@ -250,8 +250,13 @@ def test_cvae_fit_writes_reference_files(tmp_path):
         assert (tmp_path / 'vae' / f).exists(), f
     from scipy.io import netcdf_file
     with netcdf_file(str(tmp_path / 'vae' / 'stats.nc'), 'r', mmap=False) as f:
-        for k in ('loss', 'loss_KL', 'MSE', 'L2_mean', 'L2_total_test', 'L2_loss', 'Epoch_opt'):
-            assert f.variables[k].shape == (3,), k
+        # the variables, dimensions and dtypes of the shipped Google-Colab/VAE/stats.nc
+        for k in ('loss', 'loss_KL', 'var_aggr', 'MSE', 'loss_recon', 'var_latent', 'L2_mean', 'L2_total', 'L2_residual',
+                  'L2_mean_test', 'L2_total_test', 'L2_residual_test', 'L2_loss'):
+            assert f.variables[k].dimensions == ('epoch',) and f.variables[k].shape == (3,) and f.variables[k].data.dtype == '>f8', k
+        assert f.variables['var_ratio'].dimensions == ('epoch', 'lev') and f.variables['var_ratio'].data.dtype == '>f4'
+        assert list(f.variables['lev'][:]) == [1, 2] and list(f.variables['epoch'][:]) == [1, 2, 3]
+        assert f.variables['Epoch_opt'].shape == () and 1 <= float(f.variables['Epoch_opt'].getValue()) <= 3
         assert np.isfinite(f.variables['loss'][:]).all()
     again = CVAERegression(folder=folder, hidden_channels=[16, 8])
     for k, v in model.encoder.state_dict().items():
@@ -375,8 +380,13 @@ def test_cgan_fit_writes_reference_files(tmp_path):
         assert (tmp_path / 'gan' / f).exists(), f
     from scipy.io import netcdf_file
     with netcdf_file(str(tmp_path / 'gan' / 'stats.nc'), 'r', mmap=False) as f:
-        for k in ('D_loss', 'D_grad', 'D_drift', 'G_loss', 'L2_mean', 'L2_total_test', 'loss', 'Epoch_opt'):
-            assert f.variables[k].shape == (2,), k
+        # the variables, dimensions and dtypes of the shipped Google-Colab/GAN/stats.nc
+        for k in ('D_loss', 'D_drift', 'D_grad', 'G_loss', 'L2_mean', 'L2_total', 'L2_residual', 'L2_mean_test', 'L2_total_test',
+                  'L2_residual_test', 'loss'):
+            assert f.variables[k].dimensions == ('epoch',) and f.variables[k].shape == (2,), k
+        assert f.variables['var_ratio'].dimensions == ('epoch', 'lev') and f.variables['Epoch_opt'].shape == ()
+        assert set(f.variables) == {'var_ratio', 'epoch', 'D_loss', 'D_drift', 'D_grad', 'G_loss', 'L2_mean', 'L2_total', 'L2_residual',
+                                    'L2_mean_test', 'L2_total_test', 'L2_residual_test', 'loss', 'lev', 'Epoch_opt'}
         assert np.isfinite(f.variables['D_grad'][:]).all()
     again = CGANRegression(folder=folder, nx=32, hidden_channels=[16, 8])
     for k, v in model.G.state_dict().items():

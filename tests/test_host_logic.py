@@ -180,3 +180,31 @@ def test_netcdf_writer_layout_matches_reference_files(tmp_path):
     assert np.allclose(d['Ubg'], [0.025, 0.]) and np.allclose(d['x'], ds['coords']['x'])
     one = dataset.read_netcdf(dataset.write_netcdf(ds, str(tmp_path / 'all.nc')))
     assert one['var_dims']['q'] == ('run', 'time', 'lev', 'y', 'x') and np.array_equal(one['q'], ds['q'])
+
+
+def test_training_logs_have_the_layout_of_the_shipped_stats_files(tmp_path):
+    """write_log / loss_to_log against the layout of Google-Colab/{GAN,VAE}/stats.nc and GZ/stats_var.nc (tests/golden/stats_layout.json,
+    read from the reference's files by make_golden.py): same container, variables, dimensions, dtypes and coordinates."""
+    import json
+    from scipy.io import netcdf_file
+    from conftest import GOLDEN
+    from pyqg_generative_b200.tools.cnn_tools import write_log
+    from pyqg_generative_b200.models.cvae_regression import loss_to_log
+    layout = json.load(open(os.path.join(GOLDEN, 'stats_layout.json')))
+    scores = [dict(L2_mean=1.0, L2_total=0.5 - 0.1 * i, L2_residual=0.4, var_ratio=[0.9, 0.8]) for i in range(3)]
+    cases = {
+        'VAE': loss_to_log({k: [1., 2., 3.] for k in ('loss', 'loss_KL', 'var_aggr', 'MSE', 'loss_recon', 'var_latent')}, scores, scores)[0],
+        'GAN': loss_to_log({k: [1., 2., 3.] for k in ('D_loss', 'D_drift', 'D_grad', 'G_loss')}, scores, scores, name='loss')[0],
+        'GZ_var': {'loss': [1., 2., 3.], 'loss_test': [2., 3., 4.]},
+    }
+    for tag, log in cases.items():
+        path = str(tmp_path / (tag + '.nc'))
+        write_log(log, path)
+        assert list(open(path, 'rb').read(4)) == layout[tag]['magic'], tag
+        with netcdf_file(path, 'r', mmap=False) as nc:
+            ours = {k: dict(dims=list(v.dimensions), dtype=v.data.dtype.str) for k, v in nc.variables.items()}
+            assert ours == layout[tag]['variables'], (tag, ours)
+            assert int(nc.variables['epoch'][0]) == layout[tag]['epoch_first']
+            if layout[tag]['lev']:
+                assert [int(x) for x in nc.variables['lev'][:]] == layout[tag]['lev']
+    assert cases['VAE']['Epoch_opt'] == 3.0
