@@ -130,7 +130,8 @@ constexpr int kGemmM = 128, kGemmK = 8, kGemmPitch = kGemmM + 4;
 
 // C[i][j] (+ epilogue) = sum_k A(i, k) B(k, j),  A(i, k) = A[i sai + k sak],  B(k, j) = B[k sbk + j sbj]  (one of each pair of
 // strides is 1: the loader walks the unit-stride direction).  Block tile 128 x BN (BN = 128 or 64), depth 8 per stage, 256 threads
-// with an 8 x (BN / 16) register tile each: per k one thread issues 2 + BN/64 LDS.128 for 8 BN/16 FFMAs.  The next stage is fetched
+// with an 8 x (BN / 16) register tile each (rows ty 8 .. ty 8 + 7; columns tx 4 .. tx 4 + 3 of every 64-column group, so that the B reads of
+// a quarter warp are contiguous): per k one thread issues 2 + BN/64 LDS.128 for 8 BN/16 FFMAs.  The next stage is fetched
 // into registers while the current one is multiplied (shared memory double-buffered, one barrier per stage).
 // blockIdx.z splits the k range into chunks of ksplit (partial results at C + z c_split); EPI 0: none, 1: LeakyReLU(0.2),
 // 2: times the LeakyReLU slope of mask[i ldc + j] (1 where mask > 0, else 0.2).
@@ -194,7 +195,7 @@ __global__ void __launch_bounds__(256, 2) sgemm_kernel(const float* __restrict__
       float bv[TN];
 #pragma unroll
       for (int q = 0; q < TN / 4; ++q) {
-        const float4 b4 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * TN + 4 * q]);
+        const float4 b4 = *reinterpret_cast<const float4*>(&Bs[buf][k][q * 64 + tx * 4]);      // column groups 64 apart: conflict-free
         bv[4 * q] = b4.x; bv[4 * q + 1] = b4.y; bv[4 * q + 2] = b4.z; bv[4 * q + 3] = b4.w;
       }
 #pragma unroll
@@ -211,7 +212,7 @@ __global__ void __launch_bounds__(256, 2) sgemm_kernel(const float* __restrict__
     if (gi >= M) continue;
 #pragma unroll
     for (int b = 0; b < TN; ++b) {
-      const int gj = j0 + tx * TN + b;
+      const int gj = j0 + (b / 4) * 64 + tx * 4 + b % 4;
       if (gj >= N) continue;
       float v = acc[a][b];
       if (EPI == 1) v = v > 0.f ? v : 0.2f * v;
