@@ -154,18 +154,34 @@ __global__ void __launch_bounds__(256, 2) sgemm_kernel(const float* __restrict__
 #pragma unroll
     for (int b = 0; b < TN; ++b) acc[a][b] = 0.f;
   float ra[4], rb[NB];
+  // per-thread element pointers of the first stage (advanced by one stage per fetch) and row / column validity
+  int pa[4], pb[NB];                         // element offsets (every operand of this library is far below 2^31 elements)
+  bool va[4], vb[NB];
+  const int ka0 = a_kfast ? tid % 8 : tid / 128, dka = a_kfast ? 0 : 2;             // k index of element r of a stage: ka0 + r dka
+  const int kb0 = b_kfast ? tid % 8 : tid / BN, dkb = b_kfast ? 0 : 256 / BN;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int i = a_kfast ? tid / 8 + 32 * r : tid % 128;
+    va[r] = i0 + i < M;
+    pa[r] = (int)((long long)(i0 + i) * sai + (long long)(kbeg + ka0 + r * dka) * sak);
+  }
+#pragma unroll
+  for (int r = 0; r < NB; ++r) {
+    const int j = b_kfast ? tid / 8 + 32 * r : tid % BN;
+    vb[r] = j0 + j < N;
+    pb[r] = (int)((long long)(kbeg + kb0 + r * dkb) * sbk + (long long)(j0 + j) * sbj);
+  }
+  const int stepa = (int)(kGemmK * sak), stepb = (int)(kGemmK * sbk);
   auto fetch = [&](int k0) {
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-      const int k = a_kfast ? tid % 8 : tid / 128 + 2 * r, i = a_kfast ? tid / 8 + 32 * r : tid % 128;
-      const int gi = i0 + i, gk = k0 + k;
-      ra[r] = (gi < M && gk < kend) ? A[gi * sai + gk * sak] : 0.f;
+      ra[r] = (va[r] && k0 + ka0 + r * dka < kend) ? A[pa[r]] : 0.f;
+      pa[r] += stepa;
     }
 #pragma unroll
     for (int r = 0; r < NB; ++r) {
-      const int k = b_kfast ? tid % 8 : tid / BN + (256 / BN) * r, j = b_kfast ? tid / 8 + 32 * r : tid % BN;
-      const int gj = j0 + j, gk = k0 + k;
-      rb[r] = (gj < N && gk < kend) ? B[gk * sbk + gj * sbj] : 0.f;
+      rb[r] = (vb[r] && k0 + kb0 + r * dkb < kend) ? B[pb[r]] : 0.f;
+      pb[r] += stepb;
     }
   };
   auto stash = [&](int buf) {
