@@ -156,7 +156,7 @@ int wgrad_launch(qgb_trainer* t, const float* a, const float* dz, float* dW, int
 int wgrad(qgb_trainer* t, const float* a, const float* dz, float* dW, int cin, int cout, int ks, int batch, cudaStream_t st) {
   const bool thin_in = cin <= 4, thin_out = cout <= 8;
   if (ks == 5) {
-    if (thin_in) return wgrad_launch<5, 4, 2>(t, a, dz, dW, cin, cout, batch, st);
+    if (thin_in) return wgrad_launch<5, 4, 1, 1>(t, a, dz, dW, cin, cout, batch, st);
     if (thin_out) return wgrad_launch<5, 32, 1>(t, a, dz, dW, cin, cout, batch, st);
     // 4 output channels per thread, one block per SM: 4.3 ms for the 128 -> 64 layer (64 images, 64^2); the 2-channel variant with two
     // blocks per SM measured 6.2 ms
