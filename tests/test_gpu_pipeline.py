@@ -43,3 +43,27 @@ def test_forcing_dataset_to_trained_closure_to_online_run(tmp_path):
         states[prec] = out['q']
     # same seeds, same noise: the two precisions track each other over the 120 coupled steps
     assert np.abs(states['tc'] - states['fp32']).max() < 1e-2 * np.abs(states['fp32']).max()
+
+
+def test_train_model_cli_reads_the_forcing_files_the_simulate_cli_writes(tmp_path):
+    """tools/train_model.py (reference :11-54) on files in the layout ``simulate.py --forcing yes`` writes (one <member>.nc per run)."""
+    from pyqg_generative_b200.tools import train_model
+    from pyqg_generative_b200.tools.dataset import write_runs
+    from pyqg_generative_b200.models.ols_model import OLSModel
+    rng = np.random.RandomState(3)
+    q = (rng.randn(5, 3, 2, 16, 16) * np.array([7e-6, 1e-6])[None, None, :, None, None]).astype('float32')
+    ds = dict(q=q, u=q, v=q, psi=q, q_forcing_advection=(1e-6 * (np.roll(q, 1, axis=-1) - q)).astype('float32'),
+              time=np.arange(3.0), coords=dict(x=np.arange(16.0), y=np.arange(16.0), lev=np.array([1, 2], dtype=np.int32)), attrs={})
+    folder = str(tmp_path / 'Operator2-16')
+    paths = write_runs(ds, folder)
+    assert len(paths) == 5
+    runs = train_model.load_runs(folder + '/*.nc')
+    assert runs['q'].shape == (5, 3, 2, 16, 16) and np.array_equal(runs['q_forcing_advection'], ds['q_forcing_advection'])
+    out = str(tmp_path / 'model')
+    model = train_model.main(['--model', 'OLSModel', '--model_args', "dict(folder=%r, hidden_channels=[16, 8])" % out,
+                              '--fit_args', 'dict(num_epochs=2, batch_size=4)', '--nruns', '4', '--train_path', folder + '/*.nc'])
+    assert isinstance(model, OLSModel) and len(model.net.log_dict['loss']) == 2
+    for f in ('net.pt', 'x_scale.json', 'y_scale.json', 'model_args.json', 'stats.nc'):
+        assert (tmp_path / 'model' / f).exists(), f
+    with pytest.raises(ValueError, match='not on the accelerated path'):
+        train_model.main(['--model', 'CVAEBottleneck', '--train_path', folder + '/*.nc'])
