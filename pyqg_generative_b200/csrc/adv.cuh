@@ -273,20 +273,27 @@ __global__ void disc_pack_kernel(const float* __restrict__ src, float* __restric
 
 // im2col of a 4 x 4 / stride 2 / pad 1 convolution, NHWC.  Samples [0, b_split) come from src0, the rest from src1 (sample
 // b - b_split): the weight gradient runs one GEMM over the ordinary samples and the linearised ones of the gradient penalty.
+template <int VEC>
 __global__ void im2col_kernel(const float* __restrict__ src0, const float* __restrict__ src1, int b_split, float* __restrict__ col,
                               int B, int H, int C, int OH) {
-  const long long total = (long long)B * OH * OH * 16 * C;
+  // VEC consecutive channels per thread (VEC = 4: 16-byte accesses, C % 4 == 0)
+  const int CV = C / VEC;
+  const long long total = (long long)B * OH * OH * 16 * CV;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C), kk = (int)((i / C) % 16);
-    const long long m = i / (16LL * C);
+    const int c = (int)(i % CV) * VEC, kk = (int)((i / CV) % 16);
+    const long long m = i / (16LL * CV);
     const int ox = (int)(m % OH), oy = (int)((m / OH) % OH), b = (int)(m / ((long long)OH * OH));
     const int iy = oy * 2 - 1 + kk / 4, ix = ox * 2 - 1 + kk % 4;
-    float v = 0.f;
-    if (iy >= 0 && iy < H && ix >= 0 && ix < H) {
-      const float* s = b < b_split ? src0 + (long long)b * H * H * C : src1 + (long long)(b - b_split) * H * H * C;
-      v = s[((long long)iy * H + ix) * C + c];
+    const bool inside = iy >= 0 && iy < H && ix >= 0 && ix < H;
+    const float* s = b < b_split ? src0 + (long long)b * H * H * C : src1 + (long long)(b - b_split) * H * H * C;
+    float* d = col + (m * 16 + kk) * C + c;
+    if (VEC == 4) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (inside) v = *reinterpret_cast<const float4*>(s + ((long long)iy * H + ix) * C + c);
+      *reinterpret_cast<float4*>(d) = v;
+    } else {
+      *d = inside ? s[((long long)iy * H + ix) * C + c] : 0.f;
     }
-    col[i] = v;
   }
 }
 

@@ -632,14 +632,23 @@ int disc_pack(qgb_disc* d, cudaStream_t st) {
   return QGB_OK;
 }
 
+// im2col of samples taken from src0 (the first b_split) and src1 (the rest); 16-byte accesses where the channel count allows
+int im2col(qgb_disc* d, const float* src0, const float* src1, int b_split, int nb, int H, int C, int OH, cudaStream_t st) {
+  const long long tot = (long long)nb * OH * OH * 16 * C;
+  if (C % 4 == 0) im2col_kernel<4><<<ew_blocks(tot / 4), 256, 0, st>>>(src0, src1, b_split, d->col, nb, H, C, OH);
+  else im2col_kernel<1><<<ew_blocks(tot), 256, 0, st>>>(src0, src1, b_split, d->col, nb, H, C, OH);
+  d->launches++;
+  D_TRY(d, cudaGetLastError());
+  return QGB_OK;
+}
+
 // D on samples [b0, b0 + nb) of h[0]: activations into h[1..4], outputs into o
 int disc_forward(qgb_disc* d, int b0, int nb, cudaStream_t st) {
   for (int k = 0; k < 4; ++k) {
     const auto& L = d->L[k];
-    const long long tot = (long long)nb * L.OH * L.OH * L.K;
-    im2col_kernel<<<ew_blocks(tot), 256, 0, st>>>(d->h[k] + b0 * d->act(k), nullptr, nb, d->col, nb, L.H, L.cin, L.OH);
-    d->launches++;
-    int rc = gemm<1>(d, d->col, (long long)L.K, 1, d->Wp + L.w, 1, (long long)L.K, d->h[k + 1] + b0 * d->act(k + 1), L.cout,
+    int rc = im2col(d, d->h[k] + b0 * d->act(k), nullptr, nb, nb, L.H, L.cin, L.OH, st);
+    if (rc) return rc;
+    rc = gemm<1>(d, d->col, (long long)L.K, 1, d->Wp + L.w, 1, (long long)L.K, d->h[k + 1] + b0 * d->act(k + 1), L.cout,
                      nb * L.OH * L.OH, L.cout, (int)L.K, 1, 0, nullptr, st);
     if (rc < 0) return rc;
   }
@@ -683,10 +692,9 @@ int disc_backward_data(qgb_disc* d, int b0, int nb, int ib0, int inb, cudaStream
 int disc_linearised(qgb_disc* d, int m0, int nu, cudaStream_t st) {
   for (int k = 0; k < 4; ++k) {
     const auto& L = d->L[k];
-    const long long tot = (long long)nu * L.OH * L.OH * L.K;
-    im2col_kernel<<<ew_blocks(tot), 256, 0, st>>>(d->u[k], nullptr, nu, d->col, nu, L.H, L.cin, L.OH);
-    d->launches++;
-    int rc = gemm<2>(d, d->col, (long long)L.K, 1, d->Wp + L.w, 1, (long long)L.K, d->u[k + 1], L.cout, nu * L.OH * L.OH, L.cout,
+    int rc = im2col(d, d->u[k], nullptr, nu, nu, L.H, L.cin, L.OH, st);
+    if (rc) return rc;
+    rc = gemm<2>(d, d->col, (long long)L.K, 1, d->Wp + L.w, 1, (long long)L.K, d->u[k + 1], L.cout, nu * L.OH * L.OH, L.cout,
                      (int)L.K, 1, 0, d->h[k + 1] + m0 * d->act(k + 1), st);
     if (rc < 0) return rc;
   }
@@ -702,9 +710,8 @@ int disc_wgrad(qgb_disc* d, int nA, int nU, cudaStream_t st) {
     const int OH2 = k < 4 ? L.OH * L.OH : 1;
     const int Mred = nb * OH2;
     if (k < 4) {
-      const long long tot = (long long)Mred * L.K;
-      im2col_kernel<<<ew_blocks(tot), 256, 0, st>>>(d->h[k], d->u[k], nA, d->col, nb, L.H, L.cin, L.OH);
-      d->launches++;
+      int rc = im2col(d, d->h[k], d->u[k], nA, nb, L.H, L.cin, L.OH, st);
+      if (rc) return rc;
     } else {
       D_TRY(d, cudaMemcpyAsync(d->col, d->h[4], (size_t)nA * L.K * sizeof(float), cudaMemcpyDeviceToDevice, st));
       if (nU) D_TRY(d, cudaMemcpyAsync(d->col + (size_t)nA * L.K, d->u[4], (size_t)nU * L.K * sizeof(float), cudaMemcpyDeviceToDevice, st));
