@@ -51,14 +51,33 @@ __global__ void __launch_bounds__(256) chan_partial_kernel(const float* __restri
   double s0 = 0.0, s1 = 0.0;
   float mu = 0.f, is = 0.f;
   if (MODE == 1) { mu = mean[c]; is = invstd[c]; }
-  const long long total = (long long)batch * hw;
-  for (long long i = (long long)s * 256 + threadIdx.x; i < total; i += (long long)kRedSplit * 256) {
-    const int b = (int)(i / hw), p = (int)(i - (long long)b * hw);
-    const long long off = ((long long)b * C + c) * hw + p;
-    const float v = x[off];
-    s0 += v;
-    if (MODE == 0) s1 += (double)v * v;
-    if (MODE == 1) s1 += (double)v * ((r[off] - mu) * is);
+  if (hw % 4 == 0) {                      // 16-byte accesses (every grid of the path has an even side)
+    const int hw4 = hw / 4;
+    const long long total = (long long)batch * hw4;
+    for (long long i = (long long)s * 256 + threadIdx.x; i < total; i += (long long)kRedSplit * 256) {
+      const int b = (int)(i / hw4), p = (int)(i - (long long)b * hw4);
+      const long long off = ((long long)b * C + c) * hw + 4 * p;
+      const float4 v4 = *reinterpret_cast<const float4*>(x + off);
+      const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+      float rr[4] = {0.f, 0.f, 0.f, 0.f};
+      if (MODE == 1) { const float4 r4 = *reinterpret_cast<const float4*>(r + off); rr[0] = r4.x; rr[1] = r4.y; rr[2] = r4.z; rr[3] = r4.w; }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        s0 += v[k];
+        if (MODE == 0) s1 += (double)v[k] * v[k];
+        if (MODE == 1) s1 += (double)v[k] * ((rr[k] - mu) * is);
+      }
+    }
+  } else {
+    const long long total = (long long)batch * hw;
+    for (long long i = (long long)s * 256 + threadIdx.x; i < total; i += (long long)kRedSplit * 256) {
+      const int b = (int)(i / hw), p = (int)(i - (long long)b * hw);
+      const long long off = ((long long)b * C + c) * hw + p;
+      const float v = x[off];
+      s0 += v;
+      if (MODE == 0) s1 += (double)v * v;
+      if (MODE == 1) s1 += (double)v * ((r[off] - mu) * is);
+    }
   }
   __shared__ double sh0[256], sh1[256];
   sh0[threadIdx.x] = s0; sh1[threadIdx.x] = s1;
@@ -105,6 +124,16 @@ __global__ void chan_final_kernel(const double* __restrict__ part, int C, float*
 __global__ void bn_apply_kernel(const float* __restrict__ r, float* __restrict__ a, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ invstd,
                                 int C, int hw, long long total) {
+  if (hw % 4 == 0) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total / 4; i += (long long)gridDim.x * blockDim.x) {
+      const int c = (int)((4 * i / hw) % C);
+      const float g = gamma[c], m = mean[c], is = invstd[c], be = beta[c];
+      const float4 v = reinterpret_cast<const float4*>(r)[i];
+      reinterpret_cast<float4*>(a)[i] = make_float4(g * ((v.x - m) * is) + be, g * ((v.y - m) * is) + be, g * ((v.z - m) * is) + be,
+                                                    g * ((v.w - m) * is) + be);
+    }
+    return;
+  }
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)((i / hw) % C);
     a[i] = gamma[c] * ((r[i] - mean[c]) * invstd[c]) + beta[c];
@@ -116,12 +145,81 @@ __global__ void bn_relu_bwd_kernel(float* __restrict__ d, const float* __restric
                                    const float* __restrict__ mean, const float* __restrict__ invstd,
                                    const float* __restrict__ dgamma, const float* __restrict__ dbeta, int C, int hw, float inv_n,
                                    long long total) {
+  if (hw % 4 == 0) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total / 4; i += (long long)gridDim.x * blockDim.x) {
+      const int c = (int)((4 * i / hw) % C);
+      const float m = mean[c], is = invstd[c], ga = gamma[c], db = dbeta[c], dg = dgamma[c];
+      const float4 r4 = reinterpret_cast<const float4*>(r)[i];
+      float4 d4 = reinterpret_cast<float4*>(d)[i];
+      const float rv[4] = {r4.x, r4.y, r4.z, r4.w};
+      float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float xhat = (rv[k] - m) * is;
+        const float g = ga * is * (dv[k] - db * inv_n - xhat * dg * inv_n);      // (same expression order as the scalar path)
+        dv[k] = rv[k] > 0.f ? g : 0.f;
+      }
+      reinterpret_cast<float4*>(d)[i] = make_float4(dv[0], dv[1], dv[2], dv[3]);
+    }
+    return;
+  }
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)((i / hw) % C);
     const float rv = r[i], xhat = (rv - mean[c]) * invstd[c];
     const float g = gamma[c] * invstd[c] * (d[i] - dbeta[c] * inv_n - xhat * dgamma[c] * inv_n);
     d[i] = rv > 0.f ? g : 0.f;
   }
+}
+
+// The same backward pass organised per channel (grid (C, kRedSplit) like chan_partial_kernel) so that it also leaves the per-channel
+// sums of dz -- the bias gradient of the convolution below -- in ``part``: one pass over the tensor less than a separate reduction.
+__global__ void __launch_bounds__(256) bn_relu_bwd_chan_kernel(float* __restrict__ d, const float* __restrict__ r,
+                                                               const float* __restrict__ gamma, const float* __restrict__ mean,
+                                                               const float* __restrict__ invstd, const float* __restrict__ dgamma,
+                                                               const float* __restrict__ dbeta, int batch, int C, int hw, float inv_n,
+                                                               double* __restrict__ part) {
+  const int c = blockIdx.x, s = blockIdx.y;
+  const float m = mean[c], is = invstd[c], ga = gamma[c], db = dbeta[c], dg = dgamma[c];
+  double s0 = 0.0;
+  if (hw % 4 == 0) {
+    const int hw4 = hw / 4;
+    const long long total = (long long)batch * hw4;
+    for (long long i = (long long)s * 256 + threadIdx.x; i < total; i += (long long)kRedSplit * 256) {
+      const int b = (int)(i / hw4), p = (int)(i - (long long)b * hw4);
+      const long long off = ((long long)b * C + c) * hw + 4 * p;
+      const float4 r4 = *reinterpret_cast<const float4*>(r + off);
+      const float4 d4 = *reinterpret_cast<const float4*>(d + off);
+      const float rv[4] = {r4.x, r4.y, r4.z, r4.w};
+      float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float xhat = (rv[k] - m) * is;
+        const float g = ga * is * (dv[k] - db * inv_n - xhat * dg * inv_n);
+        dv[k] = rv[k] > 0.f ? g : 0.f;
+        s0 += dv[k];
+      }
+      *reinterpret_cast<float4*>(d + off) = make_float4(dv[0], dv[1], dv[2], dv[3]);
+    }
+  } else {
+    const long long total = (long long)batch * hw;
+    for (long long i = (long long)s * 256 + threadIdx.x; i < total; i += (long long)kRedSplit * 256) {
+      const int b = (int)(i / hw), p = (int)(i - (long long)b * hw);
+      const long long off = ((long long)b * C + c) * hw + p;
+      const float rv = r[off], xhat = (rv - m) * is;
+      const float g = ga * is * (d[off] - db * inv_n - xhat * dg * inv_n);
+      const float dz = rv > 0.f ? g : 0.f;
+      d[off] = dz;
+      s0 += dz;
+    }
+  }
+  __shared__ double sh0[256];
+  sh0[threadIdx.x] = s0;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) sh0[threadIdx.x] += sh0[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { part[((long long)c * kRedSplit + s) * 2] = sh0[0]; part[((long long)c * kRedSplit + s) * 2 + 1] = 0.0; }
 }
 
 // eval-mode BatchNorm folded into the convolution epilogue: s = gamma / sqrt(running_var + eps), t = beta - running_mean s

@@ -265,11 +265,16 @@ int backward(qgb_trainer* t, const float* xd, int batch, cudaStream_t st, float*
     float* dz = t->d[cur];
     const float* a_in = l == 0 ? xd : A(t, l - 1);
     // bias gradient
-    int rc = chan_reduce<2>(t, dz, nullptr, nullptr, nullptr, batch, L.cout, st);
-    if (rc) return rc;
-    chan_final_kernel<<<(L.cout + 127) / 128, 128, 0, st>>>(t->red_part, L.cout, t->G + L.b, nullptr);
-    t->launches++;
-    TR_TRY(t, cudaGetLastError());
+    // (bias gradient: for the last layer a reduction of its own; below it the BatchNorm / ReLU backward pass of the previous iteration of
+    // this loop has left the per-channel sums of dz with the rest of its work)
+    int rc = QGB_OK;
+    if (l == t->nlayers - 1) {
+      rc = chan_reduce<2>(t, dz, nullptr, nullptr, nullptr, batch, L.cout, st);
+      if (rc) return rc;
+      chan_final_kernel<<<(L.cout + 127) / 128, 128, 0, st>>>(t->red_part, L.cout, t->G + L.b, nullptr);
+      t->launches++;
+      TR_TRY(t, cudaGetLastError());
+    }
     // weight gradient
     rc = wgrad(t, a_in, dz, t->G + L.w, L.cin, L.cout, L.ks, batch, st);
     if (rc) return rc;
@@ -286,10 +291,10 @@ int backward(qgb_trainer* t, const float* xd, int batch, cudaStream_t st, float*
     rc = chan_reduce<1>(t, da, R(t, l - 1), MEAN(t, Lp), INVSTD(t, Lp), batch, Lp.cout, st);
     if (rc) return rc;
     chan_final_kernel<<<(Lp.cout + 127) / 128, 128, 0, st>>>(t->red_part, Lp.cout, t->G + Lp.be, t->G + Lp.g);
-    const long long total = (long long)batch * Lp.cout * hw;
-    bn_relu_bwd_kernel<<<ew_blocks(total), 256, 0, st>>>(da, R(t, l - 1), t->P + Lp.g, MEAN(t, Lp), INVSTD(t, Lp),
-                                                         t->G + Lp.g, t->G + Lp.be, Lp.cout, hw, 1.f / ((float)batch * hw), total);
-    t->launches += 2;
+    bn_relu_bwd_chan_kernel<<<dim3(Lp.cout, kRedSplit), 256, 0, st>>>(da, R(t, l - 1), t->P + Lp.g, MEAN(t, Lp), INVSTD(t, Lp), t->G + Lp.g,
+                                                                      t->G + Lp.be, batch, Lp.cout, hw, 1.f / ((float)batch * hw), t->red_part);
+    chan_final_kernel<<<(Lp.cout + 127) / 128, 128, 0, st>>>(t->red_part, Lp.cout, t->G + Lp.b, nullptr);       // bias gradient of layer l - 1
+    t->launches += 3;
     TR_TRY(t, cudaGetLastError());
     cur ^= 1;
   }
