@@ -126,10 +126,10 @@ __global__ void axpy_kernel(float* __restrict__ y, const float* __restrict__ x, 
 // against the packed weights Wp[co][(ky, kx, ci)]: forward  z = col Wp^T,  data gradient  dcol = dz Wp,  weight gradient
 // dWp = dz^T col.  The last layer (k5 x k5 valid convolution of the k5 x k5 map) is the same GEMM on the activation itself.
 
-constexpr int kGemmM = 128, kGemmK = 8, kGemmPitch = kGemmM + 4;
+constexpr int kGemmM = 128, kGemmK = 8, kGemmPitch = kGemmM + 4;     // (depth 16 spills: 8 x 8 accumulators + staging exceed 128 registers)
 
 // C[i][j] (+ epilogue) = sum_k A(i, k) B(k, j),  A(i, k) = A[i sai + k sak],  B(k, j) = B[k sbk + j sbj]  (one of each pair of
-// strides is 1: the loader walks the unit-stride direction).  Block tile 128 x BN (BN = 128 or 64), depth 8 per stage, 256 threads
+// strides is 1: the loader walks the unit-stride direction).  Block tile 128 x BN (BN = 128 or 64), depth kGemmK per stage, 256 threads
 // with an 8 x (BN / 16) register tile each (rows ty 8 .. ty 8 + 7; columns tx 4 .. tx 4 + 3 of every 64-column group, so that the B reads of
 // a quarter warp are contiguous): per k one thread issues 2 + BN/64 LDS.128 for 8 BN/16 FFMAs.  The next stage is fetched
 // into registers while the current one is multiplied (shared memory double-buffered, one barrier per stage).
@@ -153,28 +153,29 @@ __global__ void __launch_bounds__(256, 2) sgemm_kernel(const float* __restrict__
   for (int a = 0; a < 8; ++a)
 #pragma unroll
     for (int b = 0; b < TN; ++b) acc[a][b] = 0.f;
-  float ra[4], rb[NB];
+  constexpr int NA = kGemmM * kGemmK / 256, KR = 256 / kGemmK;      // A elements per thread and stage; rows per pass of the k-fast loader
+  float ra[NA], rb[NB];
   // per-thread element pointers of the first stage (advanced by one stage per fetch) and row / column validity
-  int pa[4], pb[NB];                         // element offsets (every operand of this library is far below 2^31 elements)
-  bool va[4], vb[NB];
-  const int ka0 = a_kfast ? tid % 8 : tid / 128, dka = a_kfast ? 0 : 2;             // k index of element r of a stage: ka0 + r dka
-  const int kb0 = b_kfast ? tid % 8 : tid / BN, dkb = b_kfast ? 0 : 256 / BN;
+  int pa[NA], pb[NB];                         // element offsets (every operand of this library is far below 2^31 elements)
+  bool va[NA], vb[NB];
+  const int ka0 = a_kfast ? tid % kGemmK : tid / 128, dka = a_kfast ? 0 : 2;             // k index of element r of a stage: ka0 + r dka
+  const int kb0 = b_kfast ? tid % kGemmK : tid / BN, dkb = b_kfast ? 0 : 256 / BN;
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int i = a_kfast ? tid / 8 + 32 * r : tid % 128;
+  for (int r = 0; r < NA; ++r) {
+    const int i = a_kfast ? tid / kGemmK + KR * r : tid % 128;
     va[r] = i0 + i < M;
     pa[r] = (int)((long long)(i0 + i) * sai + (long long)(kbeg + ka0 + r * dka) * sak);
   }
 #pragma unroll
   for (int r = 0; r < NB; ++r) {
-    const int j = b_kfast ? tid / 8 + 32 * r : tid % BN;
+    const int j = b_kfast ? tid / kGemmK + KR * r : tid % BN;
     vb[r] = j0 + j < N;
     pb[r] = (int)((long long)(kbeg + kb0 + r * dkb) * sbk + (long long)(j0 + j) * sbj);
   }
   const int stepa = (int)(kGemmK * sak), stepb = (int)(kGemmK * sbk);
   auto fetch = [&](int k0) {
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < NA; ++r) {
       ra[r] = (va[r] && k0 + ka0 + r * dka < kend) ? A[pa[r]] : 0.f;
       pa[r] += stepa;
     }
@@ -186,13 +187,13 @@ __global__ void __launch_bounds__(256, 2) sgemm_kernel(const float* __restrict__
   };
   auto stash = [&](int buf) {
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int k = a_kfast ? tid % 8 : tid / 128 + 2 * r, i = a_kfast ? tid / 8 + 32 * r : tid % 128;
+    for (int r = 0; r < NA; ++r) {
+      const int k = a_kfast ? tid % kGemmK : tid / 128 + 2 * r, i = a_kfast ? tid / kGemmK + KR * r : tid % 128;
       As[buf][k][i] = ra[r];
     }
 #pragma unroll
     for (int r = 0; r < NB; ++r) {
-      const int k = b_kfast ? tid % 8 : tid / BN + (256 / BN) * r, j = b_kfast ? tid / 8 + 32 * r : tid % BN;
+      const int k = b_kfast ? tid % kGemmK : tid / BN + (256 / BN) * r, j = b_kfast ? tid / kGemmK + KR * r : tid % BN;
       Bs[buf][k][j] = rb[r];
     }
   };
