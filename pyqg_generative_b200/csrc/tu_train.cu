@@ -10,6 +10,7 @@
 
 #include "../../include/qgb200.h"
 #include "adv.cuh"
+#include "tgemm.cuh"
 #include "train.cuh"
 
 using namespace qgb;
@@ -608,9 +609,29 @@ int dfail(qgb_disc* d, int code, const char* fmt, ...) {
     if (_e != cudaSuccess) return dfail(d, QGB_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
   } while (0)
 
+// tensor-core path (tgemm.cuh: tcgen05 kind::tf32, 3-term split, fp32-accurate) unless QGB_DISC_GEMM=ffma asks for the FFMA kernel
+inline bool disc_gemm_tc() {
+  static int mode = -1;
+  if (mode < 0) { const char* e = getenv("QGB_DISC_GEMM"); mode = (e && std::strcmp(e, "ffma") == 0) ? 0 : 1; }
+  return mode == 1;
+}
+
 template <int EPI>
 int gemm(qgb_disc* d, const float* A, long long sai, long long sak, const float* B, long long sbk, long long sbj, float* C,
          long long ldc, int M, int N, int K, int splits, long long c_split, const float* mask, cudaStream_t st) {
+  if (disc_gemm_tc()) {
+    int ksplit = (K + splits - 1) / splits;
+    ksplit = (ksplit + tg::BK - 1) / tg::BK * tg::BK;
+    splits = (K + ksplit - 1) / ksplit;
+    const int a_vec = sak == 1 && sai % 4 == 0 && K % 4 == 0 && ((uintptr_t)A & 15) == 0;
+    const int b_vec = sbk == 1 && sbj % 4 == 0 && K % 4 == 0 && ((uintptr_t)B & 15) == 0;
+    D_TRY(d, cudaFuncSetAttribute(tg::tgemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, tg::SMEM_BYTES));
+    dim3 grid((N + tg::BN - 1) / tg::BN, (M + tg::BM - 1) / tg::BM, splits);
+    tg::tgemm_kernel<EPI><<<grid, 256, tg::SMEM_BYTES, st>>>(A, sai, sak, B, sbk, sbj, C, ldc, M, N, K, ksplit, c_split, mask, a_vec, b_vec);
+    d->launches++;
+    D_TRY(d, cudaGetLastError());
+    return splits;
+  }
   int ksplit = (K + splits - 1) / splits;
   ksplit = (ksplit + kGemmK - 1) / kGemmK * kGemmK;
   splits = (K + ksplit - 1) / ksplit;
@@ -721,10 +742,11 @@ int disc_wgrad(qgb_disc* d, int nA, int nU, cudaStream_t st) {
       D_TRY(d, cudaMemcpyAsync(d->col, d->h[4], (size_t)nA * L.K * sizeof(float), cudaMemcpyDeviceToDevice, st));
       if (nU) D_TRY(d, cudaMemcpyAsync(d->col + (size_t)nA * L.K, d->u[4], (size_t)nU * L.K * sizeof(float), cudaMemcpyDeviceToDevice, st));
     }
-    const int bn = (int)L.K > 64 ? 128 : 64;
+    const int bn = (disc_gemm_tc() || (int)L.K > 64) ? 128 : 64;
     const int tiles = ((L.cout + kGemmM - 1) / kGemmM) * (((int)L.K + bn - 1) / bn);
     int splits = (2 * 148 + tiles - 1) / tiles;
-    if (splits > (Mred + kGemmK - 1) / kGemmK) splits = (Mred + kGemmK - 1) / kGemmK;
+    const int kq = disc_gemm_tc() ? tg::BK : kGemmK;
+    if (splits > (Mred + kq - 1) / kq) splits = (Mred + kq - 1) / kq;
     if (splits < 1) splits = 1;
     const size_t n = (size_t)L.cout * L.K;
     if (d->part_floats < n * splits) {
