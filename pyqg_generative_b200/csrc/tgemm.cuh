@@ -14,7 +14,8 @@
 // tiles from global memory into registers (16-byte loads where k is the unit-stride direction, else core-matrix-shaped scalar
 // loads), splits them and writes hi / lo planes into shared memory in the canonical K-major no-swizzle UMMA layout
 // (8 rows x 16 bytes core matrices, K-adjacent ones 128 bytes apart, 8-row groups 1024 bytes apart); after fence.proxy.async and a
-// barrier one thread issues the 12 MMAs of the stage (into one of four TMEM accumulators, see NACC) and commits them to the stage's mbarrier.  Two shared-memory stages, the
+// hand-over through an mbarrier a dedicated MMA warp issues the 12 MMAs of the stage (into one of four TMEM accumulators, see NACC) and
+// commits them to the stage's "empty" barrier.  Two shared-memory stages, the
 // global loads run two stages ahead in registers.  Epilogue: tcgen05.ld (32 lanes x 16 columns per warp), LeakyReLU / mask, global stores.
 #pragma once
 #include <cuda_runtime.h>
@@ -46,6 +47,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "bra TG_WAIT_LOOP;\n\t"
       "TG_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
       : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
@@ -143,73 +147,82 @@ struct Loader {
 
 // EPI 0: none, 1: LeakyReLU(0.2), 2: times the LeakyReLU slope of mask[i ldc + j].  blockIdx.z splits the k range into chunks of ksplit
 // (partial results at C + z c_split).
+constexpr int kThreads = 288;        // warps 0 - 7: producers (fetch, split, store) and epilogue; warp 8: MMA issue
+
 template <int EPI>
-__global__ void __launch_bounds__(256, 1) tgemm_kernel(const float* __restrict__ A, long long sai, long long sak,
-                                                       const float* __restrict__ B, long long sbk, long long sbj, float* __restrict__ C,
-                                                       long long ldc, int M, int N, int K, int ksplit, long long c_split,
-                                                       const float* __restrict__ mask, int a_vec, int b_vec) {
+__global__ void __launch_bounds__(kThreads, 1) tgemm_kernel(const float* __restrict__ A, long long sai, long long sak,
+                                                            const float* __restrict__ B, long long sbk, long long sbj, float* __restrict__ C,
+                                                            long long ldc, int M, int N, int K, int ksplit, long long c_split,
+                                                            const float* __restrict__ mask, int a_vec, int b_vec) {
   extern __shared__ unsigned char tg_smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)tg_smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * STAGE_BYTES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + 2 * STAGE_BYTES);       // [2] planes of a stage written (256 producer arrivals)
+  uint64_t* empty = full + 2;                                                 // [2] the MMAs that read a stage have completed (commit)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(empty + 2);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int i0 = blockIdx.y * BM, j0 = blockIdx.x * BN;
   const int kbeg = blockIdx.z * ksplit, kend = min(K, kbeg + ksplit);
   const int nk = (kend - kbeg + BK - 1) / BK;
-  if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_barrier_init(); }
-  if (warp == 0) tmem_alloc(tmem_slot, NACC * BN);
+  if (tid == 0) { mbar_init(&full[0], 256); mbar_init(&full[1], 256); mbar_init(&empty[0], 1); mbar_init(&empty[1], 1); fence_barrier_init(); }
+  if (warp == 8) tmem_alloc(tmem_slot, NACC * BN);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  Loader la{A + (long long)i0 * sai, sai, sak, M - i0, a_vec};
-  Loader lb{B + (long long)j0 * sbj, sbj, sbk, N - j0, b_vec};
-  // Register prefetch two stages ahead (two register sets, the loop body written out for even and odd stages): with one CTA of 8 warps
-  // per SM a fetch issued one stage ahead left the global-load latency exposed in every stage (5000 clocks per stage for 800 of MMAs).
-  float sa0[16], sb0[16], sa1[16], sb1[16];
-  la.fetch(sa0, kbeg, kend, tid);
-  lb.fetch(sb0, kbeg, kend, tid);
-  if (nk > 1) { la.fetch(sa1, kbeg + BK, kend, tid); lb.fetch(sb1, kbeg + BK, kend, tid); }
-  auto stage = [&](int it, float (&sa)[16], float (&sb)[16]) {
-    const int s = it & 1;
-    unsigned char* st = smem + s * STAGE_BYTES;
-    if (it >= 2) mbar_wait(&bars[s], (uint32_t)((it / 2 - 1) & 1));          // the MMAs that read this stage have completed
-    la.store(sa, st, st + TILE_BYTES, tid);
-    lb.store(sb, st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, tid);
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      const uint32_t base = smem_u32(st);
+  if (warp == 8) {
+    // ---- MMA warp: one lane waits for a stage, issues its 12 MMAs and commits them to the stage's "empty" barrier ----
+    if (lane == 0) {
+      for (int it = 0; it < nk; ++it) {
+        const int s = it & 1;
+        mbar_wait(&full[s], (uint32_t)((it / 2) & 1));
+        tc_fence_after();
+        const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
 #pragma unroll
-      for (int j = 0; j < BK / 8; ++j) {
-        const uint64_t ah = make_desc(base + j * 256), al = make_desc(base + TILE_BYTES + j * 256);
-        const uint64_t bh = make_desc(base + 2 * TILE_BYTES + j * 256), bl = make_desc(base + 3 * TILE_BYTES + j * 256);
-        const uint32_t acc = tmem + (uint32_t)((it % NACC) * BN);
-        mma_tf32(acc, al, bh, kIdesc, (it >= NACC || j > 0) ? 1u : 0u);          // small terms first
-        mma_tf32(acc, ah, bl, kIdesc, 1u);
-        mma_tf32(acc, ah, bh, kIdesc, 1u);
+        for (int j = 0; j < BK / 8; ++j) {
+          const uint64_t ah = make_desc(base + j * 256), al = make_desc(base + TILE_BYTES + j * 256);
+          const uint64_t bh = make_desc(base + 2 * TILE_BYTES + j * 256), bl = make_desc(base + 3 * TILE_BYTES + j * 256);
+          const uint32_t acc = tmem + (uint32_t)((it % NACC) * BN);
+          mma_tf32(acc, al, bh, kIdesc, (it >= NACC || j > 0) ? 1u : 0u);          // small terms first
+          mma_tf32(acc, ah, bl, kIdesc, 1u);
+          mma_tf32(acc, ah, bh, kIdesc, 1u);
+        }
+        tc_commit(&empty[s]);
       }
-      tc_commit(&bars[s]);
     }
-    if (it + 2 < nk) {                                                          // in flight for two stages
-      la.fetch(sa, kbeg + (it + 2) * BK, kend, tid);
-      lb.fetch(sb, kbeg + (it + 2) * BK, kend, tid);
+  } else {
+    // ---- producers: global loads two stages ahead in registers, split, planes of stage s, hand-over through the "full" barrier ----
+    Loader la{A + (long long)i0 * sai, sai, sak, M - i0, a_vec};
+    Loader lb{B + (long long)j0 * sbj, sbj, sbk, N - j0, b_vec};
+    float sa0[16], sb0[16], sa1[16], sb1[16];
+    la.fetch(sa0, kbeg, kend, tid);
+    lb.fetch(sb0, kbeg, kend, tid);
+    if (nk > 1) { la.fetch(sa1, kbeg + BK, kend, tid); lb.fetch(sb1, kbeg + BK, kend, tid); }
+    auto stage = [&](int it, float (&sa)[16], float (&sb)[16]) {
+      const int s = it & 1;
+      unsigned char* st = smem + s * STAGE_BYTES;
+      if (it >= 2) mbar_wait(&empty[s], (uint32_t)((it / 2 - 1) & 1));          // the MMAs that read this stage have completed
+      la.store(sa, st, st + TILE_BYTES, tid);
+      lb.store(sb, st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, tid);
+      fence_proxy_async_smem();
+      mbar_arrive(&full[s]);
+      if (it + 2 < nk) {
+        la.fetch(sa, kbeg + (it + 2) * BK, kend, tid);
+        lb.fetch(sb, kbeg + (it + 2) * BK, kend, tid);
+      }
+    };
+    for (int it = 0; it < nk; it += 2) {
+      stage(it, sa0, sb0);
+      if (it + 1 < nk) stage(it + 1, sa1, sb1);
     }
-  };
-  for (int it = 0; it < nk; it += 2) {
-    stage(it, sa0, sb0);
-    if (it + 1 < nk) stage(it + 1, sa1, sb1);
+    if (nk > 0) mbar_wait(&empty[(nk - 1) & 1], (uint32_t)(((nk - 1) / 2) & 1));   // commits complete in order: the last one covers all
   }
-  if (nk > 0) mbar_wait(&bars[(nk - 1) & 1], (uint32_t)(((nk - 1) / 2) & 1));     // commits complete in order: the last one covers all
   tc_fence_after();
   // epilogue: warp w reads TMEM lanes 32 (w % 4) .. + 31 (accumulator rows) and the column half w / 4
   float* Cz = C + (long long)blockIdx.z * c_split;
   const int gi = i0 + (warp & 3) * 32 + lane;
 #pragma unroll 1
-  for (int cb = 0; cb < 4; ++cb) {
+  for (int cb = 0; cb < (warp < 8 ? 4 : 0); ++cb) {
     const int col = (warp >> 2) * 64 + cb * 16;
     float sum[16];
 #pragma unroll
@@ -236,7 +249,7 @@ __global__ void __launch_bounds__(256, 1) tgemm_kernel(const float* __restrict__
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, NACC * BN);
+  if (warp == 8) tmem_dealloc(tmem, NACC * BN);
 }
 
 }  // namespace tg

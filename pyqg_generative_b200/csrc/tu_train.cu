@@ -627,7 +627,7 @@ int gemm(qgb_disc* d, const float* A, long long sai, long long sak, const float*
     const int b_vec = sbk == 1 && sbj % 4 == 0 && K % 4 == 0 && ((uintptr_t)B & 15) == 0;
     D_TRY(d, cudaFuncSetAttribute(tg::tgemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, tg::SMEM_BYTES));
     dim3 grid((N + tg::BN - 1) / tg::BN, (M + tg::BM - 1) / tg::BM, splits);
-    tg::tgemm_kernel<EPI><<<grid, 256, tg::SMEM_BYTES, st>>>(A, sai, sak, B, sbk, sbj, C, ldc, M, N, K, ksplit, c_split, mask, a_vec, b_vec);
+    tg::tgemm_kernel<EPI><<<grid, tg::kThreads, tg::SMEM_BYTES, st>>>(A, sai, sak, B, sbk, sbj, C, ldc, M, N, K, ksplit, c_split, mask, a_vec, b_vec);
     d->launches++;
     D_TRY(d, cudaGetLastError());
     return splits;
