@@ -489,3 +489,21 @@ def test_cvae_shipped_architecture_against_float64_oracle():
     print('worst relative gradient deviation from float64: %.1e' % worst)
     assert worst < 5e-2, worst
     tr.close()
+
+
+def test_discriminator_gemm_paths_agree_on_the_shipped_grid(tmp_path):
+    """The tensor-core GEMMs of the discriminator (csrc/tgemm.cuh: tcgen05 kind::tf32, 3-term split) against its FFMA GEMMs
+    (QGB_DISC_GEMM=ffma) on an odd configuration -- nx = 48 (3 x 3 last layer, the grid of the shipped models), batch 5: losses and every
+    gradient of one WGAN-GP iteration incl. the generator's.  Measured 1.7e-5; a plain TF32 product would be ~1e-3."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    script = os.path.join(ROOT, 'scripts', 'disc_paths_agree.py')
+    ref = str(tmp_path / 'tc.npz')
+    env = dict(os.environ)
+    env.pop('QGB_DISC_GEMM', None)
+    subprocess.run([sys.executable, script, 'save', ref], check=True, env=env, capture_output=True, timeout=300)
+    env['QGB_DISC_GEMM'] = 'ffma'
+    out = subprocess.run([sys.executable, script, 'cmp', ref], check=True, env=env, capture_output=True, text=True, timeout=300).stdout
+    worst = float(out.strip().splitlines()[-1].split()[-1])
+    assert worst < 1e-4, out
