@@ -273,7 +273,10 @@ int qgb_train_cvae_step(qgb_trainer* enc, qgb_trainer* dec, const float* x, cons
  * zero-pad 1 convolutions (in_channels -> ndf -> 2 ndf -> 4 ndf -> 8 ndf) each followed by LeakyReLU(0.2), then an
  * (nx/16) x (nx/16) valid convolution to one number per sample; no biases.  Flat parameter layout: the five weights
  * (cout, cin, k, k) in order -- the order of ``D.parameters()`` (state_dict keys 0.weight, 2.weight, 5.weight, 8.weight,
- * 11.weight).  Adam with betas (0.5, 0.999) (:246).  max_batch = the minibatch size B (the object holds 4 B samples). */
+ * 11.weight).  Adam with betas (0.5, 0.999) (:246).  max_batch = the minibatch size B (the object holds 4 B samples).
+ * Arithmetic: every convolution is one GEMM on an im2col matrix; the GEMMs run on the tensor cores (tcgen05 kind::tf32 with the 3-term
+ * split a b ~= a_hi b_hi + a_hi b_lo + a_lo b_hi, fp32 accumulation in TMEM: 1e-5 of float64 on the forward pass, csrc/tgemm.cuh) or,
+ * with QGB_DISC_GEMM=ffma in the environment, in fp32 FFMA (2e-6). */
 typedef struct qgb_disc qgb_disc;
 int qgb_disc_create(int device, int in_channels, int ndf, int nx, int max_batch, qgb_disc** out);
 void qgb_disc_destroy(qgb_disc* d);
