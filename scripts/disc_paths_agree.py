@@ -4,16 +4,14 @@ shipped models' grid: 3 x 3 last layer), batch 5.  Prints the gradients' relativ
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
-from oracle import cnn_ref
 from pyqg_generative_b200.models.cgan_regression import CGANRegression, CGANTrainer
 mode, path = sys.argv[1], sys.argv[2]
 B, nx = 5, 48
 rng = np.random.RandomState(3)
 x = rng.randn(B, 2, nx, nx).astype('float32'); y = rng.randn(B, 2, nx, nx).astype('float32')
 z1 = rng.randn(B, 2, nx, nx).astype('float32'); z2 = rng.randn(B, 2, nx, nx).astype('float32'); eps = rng.rand(B).astype('float32')
+torch.manual_seed(9)                                  # (the constructor's weights_init draws the generator; D below)
 net = CGANRegression(folder='/nonexistent', nx=nx)
-net.G.load_state_dict(cnn_ref.random_state_dict(4, 2, seed=2))
-torch.manual_seed(9)
 net.D.load_state_dict({k: v * 2.5 for k, v in net.D.state_dict().items()})
 tr = CGANTrainer(net, nx, nx, max_batch=8)
 losses = tr.step(x, y, 0.0, 0.0, True, z1=z1, z2=z2, eps=eps, coin=0, update=False)
