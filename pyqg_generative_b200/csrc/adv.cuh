@@ -277,7 +277,7 @@ __global__ void disc_pack_kernel(const float* __restrict__ src, float* __restric
 template <int VEC>
 __global__ void im2col_kernel(const float* __restrict__ src0, const float* __restrict__ src1, int b_split, float* __restrict__ col,
                               int B, int H, int C, int OH) {
-  // VEC consecutive channels per thread (VEC = 4: 16-byte accesses, C % 4 == 0)
+  // VEC consecutive channels per thread (VEC = 4: 16-byte accesses, C % 4 == 0; VEC = 2: the 6-channel input layer)
   const int CV = C / VEC;
   const long long total = (long long)B * OH * OH * 16 * CV;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -292,6 +292,10 @@ __global__ void im2col_kernel(const float* __restrict__ src0, const float* __res
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (inside) v = *reinterpret_cast<const float4*>(s + ((long long)iy * H + ix) * C + c);
       *reinterpret_cast<float4*>(d) = v;
+    } else if (VEC == 2) {
+      float2 v = make_float2(0.f, 0.f);
+      if (inside) v = *reinterpret_cast<const float2*>(s + ((long long)iy * H + ix) * C + c);
+      *reinterpret_cast<float2*>(d) = v;
     } else {
       *d = inside ? s[((long long)iy * H + ix) * C + c] : 0.f;
     }

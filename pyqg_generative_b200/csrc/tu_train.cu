@@ -662,6 +662,7 @@ int disc_pack(qgb_disc* d, cudaStream_t st) {
 int im2col(qgb_disc* d, const float* src0, const float* src1, int b_split, int nb, int H, int C, int OH, cudaStream_t st) {
   const long long tot = (long long)nb * OH * OH * 16 * C;
   if (C % 4 == 0) im2col_kernel<4><<<ew_blocks(tot / 4), 256, 0, st>>>(src0, src1, b_split, d->col, nb, H, C, OH);
+  else if (C % 2 == 0) im2col_kernel<2><<<ew_blocks(tot / 2), 256, 0, st>>>(src0, src1, b_split, d->col, nb, H, C, OH);
   else im2col_kernel<1><<<ew_blocks(tot), 256, 0, st>>>(src0, src1, b_split, d->col, nb, H, C, OH);
   d->launches++;
   D_TRY(d, cudaGetLastError());
