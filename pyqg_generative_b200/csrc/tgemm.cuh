@@ -235,14 +235,31 @@ __global__ void __launch_bounds__(kThreads, 1) tgemm_kernel(const float* __restr
       for (int e = 0; e < 16; ++e) sum[e] += __uint_as_float(r[e]);
     }
     if (gi < M) {
+      if ((ldc & 3) == 0 && j0 + col + 16 <= N) {                   // 16-byte stores (and mask loads): 64 contiguous bytes per lane
 #pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        const int gj = j0 + col + e;
-        if (gj < N) {
-          float v = sum[e];
-          if (EPI == 1) v = v > 0.f ? v : 0.2f * v;
-          if (EPI == 2) v *= mask[gi * ldc + gj] > 0.f ? 1.f : 0.2f;
-          Cz[gi * ldc + gj] = v;
+        for (int e = 0; e < 16; e += 4) {
+          float v[4] = {sum[e], sum[e + 1], sum[e + 2], sum[e + 3]};
+          const long long o = gi * ldc + j0 + col + e;
+          if (EPI == 1) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = v[u] > 0.f ? v[u] : 0.2f * v[u];
+          }
+          if (EPI == 2) {
+            const float4 m = *reinterpret_cast<const float4*>(mask + o);
+            v[0] *= m.x > 0.f ? 1.f : 0.2f; v[1] *= m.y > 0.f ? 1.f : 0.2f; v[2] *= m.z > 0.f ? 1.f : 0.2f; v[3] *= m.w > 0.f ? 1.f : 0.2f;
+          }
+          *reinterpret_cast<float4*>(Cz + o) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const int gj = j0 + col + e;
+          if (gj < N) {
+            float v = sum[e];
+            if (EPI == 1) v = v > 0.f ? v : 0.2f * v;
+            if (EPI == 2) v *= mask[gi * ldc + gj] > 0.f ? 1.f : 0.2f;
+            Cz[gi * ldc + gj] = v;
+          }
         }
       }
     }
