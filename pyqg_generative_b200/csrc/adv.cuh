@@ -304,12 +304,16 @@ __global__ void im2col_kernel(const float* __restrict__ src0, const float* __res
 
 // transpose of im2col as a gather (deterministic): din[b][iy][ix][c] = sum of the <= 4 col entries that read this input pixel,
 // times the LeakyReLU slope of mask (the activation this gradient flows into; nullptr = none)
+template <int VEC>
 __global__ void col2im_kernel(const float* __restrict__ dcol, float* __restrict__ din, const float* __restrict__ mask, int B, int H,
                               int C, int OH) {
-  const long long total = (long long)B * H * H * C;
+  const int CV = C / VEC;                         // VEC consecutive channels per thread (4: 16-byte accesses, 2: the 6-channel input)
+  const long long total = (long long)B * H * H * CV;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C), ix = (int)((i / C) % H), iy = (int)((i / ((long long)C * H)) % H), b = (int)(i / ((long long)C * H * H));
-    float s = 0.f;
+    const int c = (int)(i % CV) * VEC, ix = (int)((i / CV) % H), iy = (int)((i / ((long long)CV * H)) % H), b = (int)(i / ((long long)CV * H * H));
+    float s[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) s[v] = 0.f;
 #pragma unroll
     for (int a = 0; a < 2; ++a) {
       const int ky = ((iy + 1) & 1) + 2 * a, oy = (iy + 1 - ky) / 2;
@@ -318,11 +322,18 @@ __global__ void col2im_kernel(const float* __restrict__ dcol, float* __restrict_
       for (int e = 0; e < 2; ++e) {
         const int kx = ((ix + 1) & 1) + 2 * e, ox = (ix + 1 - kx) / 2;
         if (ix + 1 - kx < 0 || ox >= OH) continue;
-        s += dcol[(((long long)b * OH + oy) * OH + ox) * 16 * C + (ky * 4 + kx) * C + c];
+        const float* p = dcol + (((long long)b * OH + oy) * OH + ox) * 16 * C + (ky * 4 + kx) * C + c;
+        if (VEC == 4) { const float4 t = *reinterpret_cast<const float4*>(p); s[0] += t.x; s[1] += t.y; s[2] += t.z; s[3] += t.w; }
+        else if (VEC == 2) { const float2 t = *reinterpret_cast<const float2*>(p); s[0] += t.x; s[1] += t.y; }
+        else s[0] += *p;
       }
     }
-    if (mask) s *= mask[i] > 0.f ? 1.f : 0.2f;
-    din[i] = s;
+    const long long o = (((long long)b * H + iy) * H + ix) * C + c;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      if (mask) s[v] *= mask[o + v] > 0.f ? 1.f : 0.2f;
+      din[o + v] = s[v];
+    }
   }
 }
 

@@ -705,10 +705,11 @@ int disc_backward_data(qgb_disc* d, int b0, int nb, int ib0, int inb, cudaStream
                      L.cout, 1, 0, nullptr, st);
     if (rc < 0) return rc;
     const long long tot = (long long)sn * d->act(k);
-    if (k > 0)
-      col2im_kernel<<<ew_blocks(tot), 256, 0, st>>>(d->col, d->dl[k - 1] + s0 * d->act(k), d->h[k] + s0 * d->act(k), sn, L.H, L.cin, L.OH);
-    else
-      col2im_kernel<<<ew_blocks(tot), 256, 0, st>>>(d->col, d->e0, nullptr, sn, L.H, L.cin, L.OH);
+    float* dst = k > 0 ? d->dl[k - 1] + s0 * d->act(k) : d->e0;
+    const float* msk = k > 0 ? d->h[k] + s0 * d->act(k) : nullptr;
+    if (L.cin % 4 == 0) col2im_kernel<4><<<ew_blocks(tot / 4), 256, 0, st>>>(d->col, dst, msk, sn, L.H, L.cin, L.OH);
+    else if (L.cin % 2 == 0) col2im_kernel<2><<<ew_blocks(tot / 2), 256, 0, st>>>(d->col, dst, msk, sn, L.H, L.cin, L.OH);
+    else col2im_kernel<1><<<ew_blocks(tot), 256, 0, st>>>(d->col, dst, msk, sn, L.H, L.cin, L.OH);
     d->launches++;
   }
   D_TRY(d, cudaGetLastError());
