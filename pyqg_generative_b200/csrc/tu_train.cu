@@ -583,6 +583,8 @@ struct qgb_disc {
   float* dl[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // gradient with respect to the output of layer k (before LeakyReLU)
   float* u[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};    // linearised pass of the gradient penalty (B samples)
   float *o = nullptr, *e0 = nullptr, *col = nullptr, *part = nullptr, *coef = nullptr, *eps = nullptr;
+  float* colL[4] = {nullptr, nullptr, nullptr, nullptr};   // im2col matrices of the forward pass, kept per layer: the weight gradient
+                                                           // reuses them (the linearised pass writes its rows over the interpolates')
   float* dyf[2] = {nullptr, nullptr};
   size_t col_floats = 0, part_floats = 0;
   double* stats = nullptr;
@@ -659,11 +661,11 @@ int disc_pack(qgb_disc* d, cudaStream_t st) {
 }
 
 // im2col of samples taken from src0 (the first b_split) and src1 (the rest); 16-byte accesses where the channel count allows
-int im2col(qgb_disc* d, const float* src0, const float* src1, int b_split, int nb, int H, int C, int OH, cudaStream_t st) {
+int im2col(qgb_disc* d, const float* src0, const float* src1, int b_split, float* dst, int nb, int H, int C, int OH, cudaStream_t st) {
   const long long tot = (long long)nb * OH * OH * 16 * C;
-  if (C % 4 == 0) im2col_kernel<4><<<ew_blocks(tot / 4), 256, 0, st>>>(src0, src1, b_split, d->col, nb, H, C, OH);
-  else if (C % 2 == 0) im2col_kernel<2><<<ew_blocks(tot / 2), 256, 0, st>>>(src0, src1, b_split, d->col, nb, H, C, OH);
-  else im2col_kernel<1><<<ew_blocks(tot), 256, 0, st>>>(src0, src1, b_split, d->col, nb, H, C, OH);
+  if (C % 4 == 0) im2col_kernel<4><<<ew_blocks(tot / 4), 256, 0, st>>>(src0, src1, b_split, dst, nb, H, C, OH);
+  else if (C % 2 == 0) im2col_kernel<2><<<ew_blocks(tot / 2), 256, 0, st>>>(src0, src1, b_split, dst, nb, H, C, OH);
+  else im2col_kernel<1><<<ew_blocks(tot), 256, 0, st>>>(src0, src1, b_split, dst, nb, H, C, OH);
   d->launches++;
   D_TRY(d, cudaGetLastError());
   return QGB_OK;
@@ -673,9 +675,10 @@ int im2col(qgb_disc* d, const float* src0, const float* src1, int b_split, int n
 int disc_forward(qgb_disc* d, int b0, int nb, cudaStream_t st) {
   for (int k = 0; k < 4; ++k) {
     const auto& L = d->L[k];
-    int rc = im2col(d, d->h[k] + b0 * d->act(k), nullptr, nb, nb, L.H, L.cin, L.OH, st);
+    float* colk = d->colL[k] + (size_t)b0 * L.OH * L.OH * L.K;
+    int rc = im2col(d, d->h[k] + b0 * d->act(k), nullptr, nb, colk, nb, L.H, L.cin, L.OH, st);
     if (rc) return rc;
-    rc = gemm<1>(d, d->col, (long long)L.K, 1, d->Wp + L.w, 1, (long long)L.K, d->h[k + 1] + b0 * d->act(k + 1), L.cout,
+    rc = gemm<1>(d, colk, (long long)L.K, 1, d->Wp + L.w, 1, (long long)L.K, d->h[k + 1] + b0 * d->act(k + 1), L.cout,
                      nb * L.OH * L.OH, L.cout, (int)L.K, 1, 0, nullptr, st);
     if (rc < 0) return rc;
   }
@@ -720,9 +723,10 @@ int disc_backward_data(qgb_disc* d, int b0, int nb, int ib0, int inb, cudaStream
 int disc_linearised(qgb_disc* d, int m0, int nu, cudaStream_t st) {
   for (int k = 0; k < 4; ++k) {
     const auto& L = d->L[k];
-    int rc = im2col(d, d->u[k], nullptr, nu, nu, L.H, L.cin, L.OH, st);
+    float* colk = d->colL[k] + (size_t)m0 * L.OH * L.OH * L.K;       // over the rows of the interpolates: their forward pass is done
+    int rc = im2col(d, d->u[k], nullptr, nu, colk, nu, L.H, L.cin, L.OH, st);
     if (rc) return rc;
-    rc = gemm<2>(d, d->col, (long long)L.K, 1, d->Wp + L.w, 1, (long long)L.K, d->u[k + 1], L.cout, nu * L.OH * L.OH, L.cout,
+    rc = gemm<2>(d, colk, (long long)L.K, 1, d->Wp + L.w, 1, (long long)L.K, d->u[k + 1], L.cout, nu * L.OH * L.OH, L.cout,
                      (int)L.K, 1, 0, d->h[k + 1] + m0 * d->act(k + 1), st);
     if (rc < 0) return rc;
   }
@@ -737,9 +741,9 @@ int disc_wgrad(qgb_disc* d, int nA, int nU, cudaStream_t st) {
     const auto& L = d->L[k];
     const int OH2 = k < 4 ? L.OH * L.OH : 1;
     const int Mred = nb * OH2;
+    const float* colk = d->col;
     if (k < 4) {
-      int rc = im2col(d, d->h[k], d->u[k], nA, nb, L.H, L.cin, L.OH, st);
-      if (rc) return rc;
+      colk = d->colL[k];                  // rows [0, nA OH^2): the forward pass; rows from nA OH^2: the linearised pass (disc_linearised(nA, nU))
     } else {
       D_TRY(d, cudaMemcpyAsync(d->col, d->h[4], (size_t)nA * L.K * sizeof(float), cudaMemcpyDeviceToDevice, st));
       if (nU) D_TRY(d, cudaMemcpyAsync(d->col + (size_t)nA * L.K, d->u[4], (size_t)nU * L.K * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -757,7 +761,7 @@ int disc_wgrad(qgb_disc* d, int nA, int nU, cudaStream_t st) {
       D_TRY(d, talloc(&d->part, n * splits));
       d->part_floats = n * splits;
     }
-    int rc = gemm<0>(d, d->dl[k], 1, L.cout, d->col, (long long)L.K, 1, d->part, (long long)L.K, L.cout, (int)L.K, Mred, splits,
+    int rc = gemm<0>(d, d->dl[k], 1, L.cout, colk, (long long)L.K, 1, d->part, (long long)L.K, L.cout, (int)L.K, Mred, splits,
                      (long long)n, nullptr, st);
     if (rc < 0) return rc;
     disc_pack_kernel<<<ew_blocks((long long)n), 256, 0, st>>>(d->part, d->G + L.w, L.cout, L.cin, L.ks, 1, rc, (long long)n);
@@ -810,7 +814,11 @@ int qgb_disc_create(int device, int in_channels, int ndf, int nx, int max_batch,
     CR(talloc(&d->h[k], B4 * d->act(k)));
     CR(talloc(&d->u[k], B1 * d->act(k)));
     CR(talloc(&d->dl[k], B4 * (k < 4 ? d->act(k + 1) : 1)));
-    if (k < 4) { const size_t cf = B4 * d->L[k].OH * d->L[k].OH * d->L[k].K; d->col_floats = cf > d->col_floats ? cf : d->col_floats; }
+    if (k < 4) {
+      const size_t cf = B4 * d->L[k].OH * d->L[k].OH * d->L[k].K;
+      d->col_floats = cf > d->col_floats ? cf : d->col_floats;
+      CR(talloc(&d->colL[k], cf));
+    }
   }
   if (d->col_floats < B4 * d->L[4].K) d->col_floats = B4 * d->L[4].K;
   CR(talloc(&d->col, d->col_floats));
@@ -832,6 +840,7 @@ void qgb_disc_destroy(qgb_disc* d) {
   for (float* p : {d->P, d->G, d->M, d->V, d->Wp, d->o, d->e0, d->col, d->part, d->coef, d->eps, d->dyf[0], d->dyf[1]})
     if (p) cudaFree(p);
   for (int k = 0; k < 5; ++k) { if (d->h[k]) cudaFree(d->h[k]); if (d->u[k]) cudaFree(d->u[k]); if (d->dl[k]) cudaFree(d->dl[k]); }
+  for (int k = 0; k < 4; ++k) if (d->colL[k]) cudaFree(d->colL[k]);
   if (d->stats) cudaFree(d->stats);
   delete d;
 }
