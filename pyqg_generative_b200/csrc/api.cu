@@ -180,7 +180,6 @@ int net_forward_fp32(qgb_handle* h, const DevNet& net, const float* x, long long
     h->act_floats = per_img * chunk;
   }
   const int tiles_x = (nx + kConvTile - 1) / kConvTile, tiles_y = (ny + kConvTile - 1) / kConvTile;
-  const int tiles_y2 = (ny + kConvTileY2 - 1) / kConvTileY2;          // wide 5 x 5 layers: two output rows per thread (14 % faster there, 15 % slower for 3 x 3)
   for (int b0 = 0; b0 < batch; b0 += chunk) {
     const int nb = batch - b0 < chunk ? batch - b0 : chunk;
     const float* in = x + (long long)b0 * x_bs;
@@ -193,19 +192,17 @@ int net_forward_fp32(qgb_handle* h, const DevNet& net, const float* x, long long
       const int sp = last ? softplus : 0, acc = last ? accumulate : 0;
       const bool small = L.cout <= 4;
       const int co_t = small ? 2 : 32;
-      const bool two_rows = !small && (L.ks == 5 || (L.ks == 3 && ny % kConvTileY2 == 0));   // 3 x 3: only where 32-row tiles waste nothing
-      dim3 grid(tiles_x * (two_rows ? tiles_y2 : tiles_y), (L.cout + co_t - 1) / co_t, nb);
+      dim3 grid(tiles_x * tiles_y, (L.cout + co_t - 1) / co_t, nb);          // (the register-tiled kernel of the wide layers sizes its own grid)
       const int pi = h->prof.start(8 * (int)(&net - h->nets) + (int)li, st);
 #define QGB_CONV(KS, CT)                                                                                         \
   conv_ffma_kernel<KS, CT><<<grid, 256, 0, st>>>(in, in_bs, out, out_bs, L.wp, L.bias, L.bn_s, L.bn_t, L.cin, L.cout, \
                                                  L.cout_pad, ny, nx, tiles_x, L.relu_bn, sp, acc)
 #define QGB_CONV2(KS, CT)                                                                                        \
-  CUDA_TRY(h, (launch_conv_ffma2<KS, CT>(grid, st, in, in_bs, out, out_bs, L.wp, L.bias, L.bn_s, L.bn_t, L.cin, L.cout, \
-                                         L.cout_pad, ny, nx, tiles_x, L.relu_bn, sp, acc)))
+  CUDA_TRY(h, (launch_conv_ffma2<KS, CT>(nb, st, in, in_bs, out, out_bs, L.wp, L.bias, L.bn_s, L.bn_t, L.cin, L.cout, \
+                                         L.cout_pad, ny, nx, L.relu_bn, sp, acc)))
       if (L.ks == 5 && !small) QGB_CONV2(5, 32);
       else if (L.ks == 5) QGB_CONV(5, 2);
-      else if (L.ks == 3 && two_rows) QGB_CONV2(3, 32);
-      else if (L.ks == 3 && !small) QGB_CONV(3, 32);
+      else if (L.ks == 3 && !small) QGB_CONV2(3, 32);
       else if (L.ks == 3) QGB_CONV(3, 2);
       else if (L.ks == 1 && !small) QGB_CONV(1, 32);
       else if (L.ks == 1) QGB_CONV(1, 2);

@@ -107,18 +107,20 @@ __global__ void __launch_bounds__(256) conv_ffma_kernel(const float* __restrict_
 // offsets computed once per thread -- the synchronous fill with its div / mod / wrap index arithmetic and exposed load latency was
 // 45 % of the stall samples.  Row pitch 48 (= 16 mod 32): the two 16-pixel rows of a warp hit disjoint banks.
 constexpr int kConvCi2 = 4;
-constexpr int kConvTileY2 = 2 * kConvTile;
 constexpr int kConvPitch2 = 48;
 
-template <int KS>
+// TY = rows of the CTA tile: 32 (256 threads, two CTAs per SM) or 16 (128 threads, four per SM) -- 16 where 32-row tiles would hang over
+// the image (ny = 48, the grid of the shipped models: 3 tiles of 16 instead of 2 of 32 with a quarter of the work wasted)
+template <int KS, int TY>
 struct Conv2Geom {
-  static constexpr int TW = kConvTile + KS - 1, TH = kConvTileY2 + KS - 1;
-  static constexpr int NPOS = TH * TW, PPT = (NPOS + 255) / 256;
+  static constexpr int NT = 8 * TY;                                   // threads: 4 pixel groups per row x TY rows x 2 channel halves
+  static constexpr int TW = kConvTile + KS - 1, TH = TY + KS - 1;
+  static constexpr int NPOS = TH * TW, PPT = (NPOS + NT - 1) / NT;
   static constexpr int IN_FLOATS = kConvCi2 * TH * kConvPitch2;
 };
-template <int KS, int CO_T>
+template <int KS, int CO_T, int TY>
 struct Conv2Smem {
-  static constexpr int BUF = Conv2Geom<KS>::IN_FLOATS + kConvCi2 * KS * KS * CO_T;      // floats per half of the double buffer
+  static constexpr int BUF = Conv2Geom<KS, TY>::IN_FLOATS + kConvCi2 * KS * KS * CO_T;      // floats per half of the double buffer
   static constexpr size_t BYTES = 2 * (size_t)BUF * sizeof(float);
 };
 
@@ -132,22 +134,23 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int KS, int CO_T>
-__global__ void __launch_bounds__(256, 2) conv_ffma2_kernel(const float* __restrict__ in, long long in_bs,
+template <int KS, int CO_T, int TY>
+__global__ void __launch_bounds__(8 * TY, 64 / TY) conv_ffma2_kernel(const float* __restrict__ in, long long in_bs,
                                                             float* __restrict__ out, long long out_bs,
                                                             const float* __restrict__ wp, const float* __restrict__ bias,
                                                             const float* __restrict__ bn_s, const float* __restrict__ bn_t,
                                                             int Cin, int Cout, int CoutPad, int ny, int nx, int tiles_x,
                                                             int relu_bn, int softplus, int accumulate) {
   static_assert(CO_T % 4 == 0, "conv_ffma2_kernel: CO_T must be a multiple of 4");
-  using G = Conv2Geom<KS>;
+  using G = Conv2Geom<KS, TY>;
+  constexpr int NT = G::NT;
   constexpr int PAD = KS / 2, KK = KS * KS;
   constexpr int TW = G::TW, TH = G::TH, TWP = kConvPitch2;
-  constexpr int BUF = Conv2Smem<KS, CO_T>::BUF;
+  constexpr int BUF = Conv2Smem<KS, CO_T, TY>::BUF;
   constexpr int NW4 = kConvCi2 * KK * (CO_T / 4);
   extern __shared__ __align__(16) float conv2_smem[];
   const int tid = threadIdx.x;
-  const int ty0 = (blockIdx.x / tiles_x) * kConvTileY2, tx0 = (blockIdx.x % tiles_x) * kConvTile;
+  const int ty0 = (blockIdx.x / tiles_x) * TY, tx0 = (blockIdx.x % tiles_x) * kConvTile;
   const int co0 = blockIdx.y * CO_T;
   const int b = blockIdx.z;
   const float* inb = in + (long long)b * in_bs;
@@ -156,7 +159,7 @@ __global__ void __launch_bounds__(256, 2) conv_ffma2_kernel(const float* __restr
   int src[G::PPT], dst[G::PPT];
 #pragma unroll
   for (int k = 0; k < G::PPT; ++k) {
-    const int pos = tid + 256 * k;
+    const int pos = tid + NT * k;
     const int r = pos / TW, cc = pos % TW;
     src[k] = pos < G::NPOS ? wrap(ty0 + r - PAD, ny) * nx + wrap(tx0 + cc - PAD, nx) : -1;
     dst[k] = r * TWP + cc;
@@ -175,7 +178,7 @@ __global__ void __launch_bounds__(256, 2) conv_ffma2_kernel(const float* __restr
         if (live) cp_async4(d, pl + src[k]); else *d = 0.f;
       }
     }
-    for (int e = tid; e < NW4; e += 256) {
+    for (int e = tid; e < NW4; e += NT) {
       const int ci = e / (KK * (CO_T / 4)), rem = e % (KK * (CO_T / 4));
       float* d = s_w + (ci * KK) * CO_T + rem * 4;
       if (ci0 + ci < Cin) cp_async16(d, wp + ((long long)(ci0 + ci) * KK + rem / (CO_T / 4)) * CoutPad + co0 + (rem % (CO_T / 4)) * 4);
@@ -186,7 +189,7 @@ __global__ void __launch_bounds__(256, 2) conv_ffma2_kernel(const float* __restr
   // thread = 4 adjacent pixels (x) of one row x 16 output channels: pixel group pxg (4 per row), row pr (32 per tile), channel half ch
   constexpr int CH = CO_T / 2;
   static_assert(CH % 4 == 0, "conv_ffma2_kernel: CO_T must be a multiple of 8");
-  const int pxg = tid % 4, pr = (tid / 4) % kConvTileY2, ch = tid / 128;
+  const int pxg = tid % 4, pr = (tid / 4) % TY, ch = tid / (4 * TY);
   float acc[4][CH];
 #pragma unroll
   for (int p = 0; p < 4; ++p)
@@ -252,18 +255,31 @@ __global__ void __launch_bounds__(256, 2) conv_ffma2_kernel(const float* __restr
   }
 }
 
-// launch helper: the double buffer needs more than the 48 KB default of dynamic shared memory (attribute set on every launch: it is
-// per device and the call costs nothing next to the kernel)
-template <int KS, int CO_T>
-inline cudaError_t launch_conv_ffma2(dim3 grid, cudaStream_t st, const float* in, long long in_bs, float* out, long long out_bs,
-                                     const float* wp, const float* bias, const float* bn_s, const float* bn_t, int Cin, int Cout,
-                                     int CoutPad, int ny, int nx, int tiles_x, int relu_bn, int softplus, int accumulate) {
-  constexpr size_t smem = Conv2Smem<KS, CO_T>::BYTES;
-  cudaError_t e = cudaFuncSetAttribute(conv_ffma2_kernel<KS, CO_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+// launch helper: picks the tile height, computes the grid, raises the dynamic shared-memory limit (the double buffer needs more than
+// the 48 KB default; the attribute is per device and the call costs nothing next to the kernel)
+template <int KS, int CO_T, int TY>
+inline cudaError_t launch_conv_ffma2_ty(int nimg, cudaStream_t st, const float* in, long long in_bs, float* out, long long out_bs,
+                                        const float* wp, const float* bias, const float* bn_s, const float* bn_t, int Cin, int Cout,
+                                        int CoutPad, int ny, int nx, int relu_bn, int softplus, int accumulate) {
+  constexpr size_t smem = Conv2Smem<KS, CO_T, TY>::BYTES;
+  cudaError_t e = cudaFuncSetAttribute(conv_ffma2_kernel<KS, CO_T, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  conv_ffma2_kernel<KS, CO_T><<<grid, 256, smem, st>>>(in, in_bs, out, out_bs, wp, bias, bn_s, bn_t, Cin, Cout, CoutPad, ny, nx,
-                                                       tiles_x, relu_bn, softplus, accumulate);
+  const int tiles_x = (nx + kConvTile - 1) / kConvTile, tiles_y = (ny + TY - 1) / TY;
+  dim3 grid(tiles_x * tiles_y, (Cout + CO_T - 1) / CO_T, nimg);
+  conv_ffma2_kernel<KS, CO_T, TY><<<grid, 8 * TY, smem, st>>>(in, in_bs, out, out_bs, wp, bias, bn_s, bn_t, Cin, Cout, CoutPad, ny, nx,
+                                                              tiles_x, relu_bn, softplus, accumulate);
   return cudaGetLastError();
+}
+template <int KS, int CO_T>
+inline cudaError_t launch_conv_ffma2(int nimg, cudaStream_t st, const float* in, long long in_bs, float* out, long long out_bs,
+                                     const float* wp, const float* bias, const float* bn_s, const float* bn_t, int Cin, int Cout,
+                                     int CoutPad, int ny, int nx, int relu_bn, int softplus, int accumulate) {
+  const int rows32 = (ny + 31) / 32 * 32, rows16 = (ny + 15) / 16 * 16;       // rows computed with either tile height
+  if (rows16 < rows32)
+    return launch_conv_ffma2_ty<KS, CO_T, 16>(nimg, st, in, in_bs, out, out_bs, wp, bias, bn_s, bn_t, Cin, Cout, CoutPad, ny, nx, relu_bn,
+                                              softplus, accumulate);
+  return launch_conv_ffma2_ty<KS, CO_T, 32>(nimg, st, in, in_bs, out, out_bs, wp, bias, bn_s, bn_t, Cin, Cout, CoutPad, ny, nx, relu_bn,
+                                            softplus, accumulate);
 }
 
 }  // namespace qgb

@@ -85,18 +85,15 @@ int conv(qgb_trainer* t, const float* in, float* out, const float* wp, const flo
          int cout, int ks, int relu_affine, int batch, cudaStream_t st) {
   const int ny = t->ny, nx = t->nx;
   const int tiles_x = (nx + kConvTile - 1) / kConvTile, tiles_y = (ny + kConvTile - 1) / kConvTile;
-  const int tiles_y2 = (ny + kConvTileY2 - 1) / kConvTileY2;
   const bool small = cout <= 4;
   const int co_t = small ? 2 : 32, cpad = co_pad_of(cout);
-  const bool two_rows = !small && (ks == 5 || (ks == 3 && ny % kConvTileY2 == 0));   // 3 x 3: only where 32-row tiles waste nothing
-  dim3 grid(tiles_x * (two_rows ? tiles_y2 : tiles_y), (cout + co_t - 1) / co_t, batch);
+  dim3 grid(tiles_x * tiles_y, (cout + co_t - 1) / co_t, batch);          // (the register-tiled kernel of the wide layers sizes its own grid)
   const long long ibs = (long long)cin * ny * nx, obs = (long long)cout * ny * nx;
 #define QGB_TCONV(KS, CT) conv_ffma_kernel<KS, CT><<<grid, 256, 0, st>>>(in, ibs, out, obs, wp, bias, s, sh, cin, cout, cpad, ny, nx, tiles_x, relu_affine, 0, 0)
-#define QGB_TCONV2(KS, CT) TR_TRY(t, (launch_conv_ffma2<KS, CT>(grid, st, in, ibs, out, obs, wp, bias, s, sh, cin, cout, cpad, ny, nx, tiles_x, relu_affine, 0, 0)))
+#define QGB_TCONV2(KS, CT) TR_TRY(t, (launch_conv_ffma2<KS, CT>(batch, st, in, ibs, out, obs, wp, bias, s, sh, cin, cout, cpad, ny, nx, relu_affine, 0, 0)))
   if (ks == 5 && !small) QGB_TCONV2(5, 32);
   else if (ks == 5) QGB_TCONV(5, 2);
-  else if (ks == 3 && two_rows) QGB_TCONV2(3, 32);
-  else if (ks == 3 && !small) QGB_TCONV(3, 32);
+  else if (ks == 3 && !small) QGB_TCONV2(3, 32);
   else if (ks == 3) QGB_TCONV(3, 2);
   else if (ks == 1 && !small) QGB_TCONV(1, 32);
   else if (ks == 1) QGB_TCONV(1, 2);
