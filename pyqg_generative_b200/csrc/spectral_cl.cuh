@@ -42,8 +42,28 @@ struct Cfg {
   static constexpr int PS = 2 * SPC + 5;        // row pitch of T / S: plus | minus (A | B) columns + 4 pad columns; odd
   static constexpr int PT = N + 1;              // row pitch of T' (RPC rows): A columns 0..N/2-1, B columns N/2..N-1; odd
   static constexpr int kBuf = (N * PS > RPC * PT) ? N * PS : RPC * PT;
-  static constexpr size_t kSmemBytes = (size_t)(kBuf + N) * sizeof(cplx);
+  static constexpr size_t kSmemBytes = (size_t)(kBuf + N + 1) * sizeof(cplx);   // buffer, twiddles, hand-over mbarrier
+  // bytes that land in one CTA's buffer per transposition (T' = RPC rows x N columns, T = N rows x 2 SPC columns: N^2 / CL numbers)
+  static constexpr uint32_t kHandoverBytes = (uint32_t)(N * (N / CL) * sizeof(cplx));
+  // read-after-write hand-over of a transposition: plain remote stores and a release / acquire cluster barrier (shipped), or
+  // -DSCL_ASYNC_HANDOVER: st.async + the destination's mbarrier (complete_tx).  The second removes the barrier's MEMBAR.ALL.GPU from
+  // the loop but every 16-byte store then updates the transaction count of ONE mbarrier per destination CTA: measured on one box
+  // (scripts/ab_cluster_sync.sh) 3 % slower at 256^2 and 30 % slower at 128^2 (profiles/r2_cluster256_ncu.md).
+#ifdef SCL_ASYNC_HANDOVER
+  static constexpr bool kAsyncHandover = true;
+#else
+  static constexpr bool kAsyncHandover = false;
+#endif
+  static_assert(kHandoverBytes < (1u << 20), "mbarrier tx-count range");
   static constexpr int kCtasPerSm = kThreads <= 256 ? 2 : 1;   // 128 registers per thread: 512 threads per SM either way
+  // split the write-after-read cluster barriers around the line transform (cluster_arrive_exec / cluster_wait_exec): measured on
+  // one box (scripts/ab_cluster_sync.sh) +4.3 % at 256^2 (8 / 16 CTAs per member), -4.2 % at 128^2 (2 CTAs: the barrier is
+  // cheap there and the pinned arrive costs scheduling freedom)
+#ifdef SCL_JOINT_SYNC
+  static constexpr bool kSplitSync = false;
+#else
+  static constexpr bool kSplitSync = CL >= 8;
+#endif
   static_assert((kThreads == 512 || kThreads == 256) && (G == 8 || G == 16) && 16 * G == N, "unsupported geometry");
 };
 
@@ -63,6 +83,7 @@ struct Cfg {
 #define SCL_NB_UPD 1
 #endif
 
+
 SCL_INL uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 // Execution-only cluster barrier for the write-after-read hazards ("every CTA has finished READING its buffer, peers may now
 // overwrite it"): the loads were consumed by arithmetic that precedes the barrier in program order, so no release fence is
@@ -78,12 +99,68 @@ SCL_INL void cluster_sync_exec() {
 SCL_INL void cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// The same execution-only barrier SPLIT around the line transform: a CTA arrives as soon as its own reads of the buffer have
+// been consumed (the first 16-point FFT of fftN has every loaded value as an operand) and waits only before its first remote
+// store, so barrier latency and the skew between the CTAs of a member hide behind the transform (and, for the x pass, behind the
+// physical-space stage and a second transform) instead of following it.  ``anchor`` is a value computed from every loaded
+// number: the empty volatile asm pins that arithmetic (and so the completed loads) ahead of the arrive in program order.
+SCL_INL void cluster_arrive_exec(double& anchor) {
+  asm volatile("" : "+d"(anchor));
+#ifdef SCL_STRICT_SYNC
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+#else
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+#endif
+}
+SCL_INL void cluster_arrive_exec() {       // (after a __syncthreads: the CTA's shared-memory reads are complete)
+#ifdef SCL_STRICT_SYNC
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+#else
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+#endif
+}
+SCL_INL void cluster_wait_exec() {
+#ifdef SCL_STRICT_SYNC
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+#else
+  asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+#endif
+}
 // store a complex number into the shared memory of CTA ``rank`` of this cluster at the same offset as the local address
 SCL_INL void st_cluster(const cplx* local, uint32_t rank, cplx v) {
   const uint32_t la = (uint32_t)__cvta_generic_to_shared(local);
   uint32_t ra;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rank));
   asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};" ::"r"(ra), "d"(v.x), "d"(v.y) : "memory");
+}
+
+// Hand-over of a transposition through the DESTINATION's mbarrier: every remote store is an st.async that completes 16 bytes of
+// the transaction count of the mbarrier at the same offset in the destination CTA; the destination arms its mbarrier with the
+// N^2 / CL numbers it is about to receive and waits for the phase locally -- no cluster-wide release / acquire barrier.
+SCL_INL void st_cluster_async(const cplx* local, const uint64_t* local_bar, uint32_t rank, cplx v) {
+  const uint32_t la = (uint32_t)__cvta_generic_to_shared(local), lb = (uint32_t)__cvta_generic_to_shared(local_bar);
+  uint32_t ra, rb;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rank));
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rb) : "r"(lb), "r"(rank));
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0], {%1, %2}, [%3];" ::"r"(ra), "d"(v.x), "d"(v.y), "r"(rb)
+               : "memory");
+}
+SCL_INL void handover_init(uint64_t* bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+SCL_INL void handover_expect(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+SCL_INL void handover_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "SCL_WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra SCL_WAIT_DONE;\n\t"
+      "bra SCL_WAIT_LOOP;\n\t"
+      "SCL_WAIT_DONE:\n\t}" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity)
+      : "memory");
 }
 
 // 8-point DFT, natural order in and out (forward kernel)
@@ -103,9 +180,13 @@ SCL_INL void dft8(cplx& x0, cplx& x1, cplx& x2, cplx& x3, cplx& x4, cplx& x5, cp
 // N = 16 G point DFT of a line distributed over G lanes t = 0..G-1 (lanes lane0 + t of a warp), forward kernel:
 //   in  v[j] = x[G j + t]            out v[G i + k2] = X[t + G i + 16 k2]   (i < 16 / G, k2 < G)
 template <class C>
-SCL_INL void fftN(cplx (&v)[16], int t, const cplx* tw) {
+SCL_INL void fftN(cplx (&v)[16], int t, const cplx* tw, bool arrive = false) {
   constexpr int G = C::G, I = C::I, N = C::N;
   fft16<false>(v);                        // v[k1] = sum_j x[G j + t] w16^{j k1};  k1 = dest + G i sits at index G i + dest
+  if (C::kSplitSync && arrive) {          // (uniform) v[0] = sum of all 16 inputs: every value staged in has arrived in registers
+    cluster_arrive_exec(v[0].x);
+    asm volatile("" : "+d"(v[0].y));
+  }
   // G x G block transpose across the lanes of the line: one xor round per bit of the lane index
 #pragma unroll
   for (int p = (G == 16 ? 3 : 2); p >= 0; --p) {
@@ -295,7 +376,8 @@ SCL_INL void pointwise_phase(const Tables& T, const StepIO& io, int member, int 
 
 // One round: [inverse 2-D transform of the spectra in S] -> physical stage in registers -> [forward 2-D transform into S]
 template <class C>
-SCL_INL void round(bool has_inv, int phys, bool has_fwd, const Tables& T, const StepIO& io, int member, cplx* buf, const cplx* tw) {
+SCL_INL void round(bool has_inv, int phys, bool has_fwd, const Tables& T, const StepIO& io, int member, cplx* buf, const cplx* tw,
+                   uint64_t* hbar, uint32_t& hphase) {
   constexpr int N = C::N, G = C::G, H = C::H, SPC = C::SPC, PS = C::PS, PT = C::PT, RPC = C::RPC, NPIX = C::NPIX;
   const Geo<C> g;
   const MemberPtrs<C> P(io, member);
@@ -341,6 +423,7 @@ SCL_INL void round(bool has_inv, int phys, bool has_fwd, const Tables& T, const 
       }
     } else if (!has_inv) {                             // hp == 2 of a forward-only round: load the real pair, x = G j + t
       const double* f0 = phys == PH_LOAD_DQ ? P.dq : P.q;
+      if (C::kSplitSync) cluster_arrive_exec();        // (nothing of the buffer is read here: arrive before the global loads)
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const int i = g.y * N + G * j + g.t;
@@ -349,17 +432,24 @@ SCL_INL void round(bool has_inv, int phys, bool has_fwd, const Tables& T, const 
       }
     }
     // ---- the line transform ----
-    fftN<C>(v, g.t, tw);
+    // write-after-read barriers, split (cluster_arrive_exec): hp 0 arrives once its S columns are in registers and waits before
+    // storing into the peers' T'; the x pass arrives once its T' row has been read (hp 1; a forward-only round arrives
+    // at the top of hp 2, the pointwise phase before it ended with __syncthreads) and waits in hp 2 before storing into the peers' T
+    fftN<C>(v, g.t, tw, hp == 0 || (hp == 1 && has_fwd));
     // ---- stage out ----
     if (hp == 0) {                                     // A_y / B_y at y = out_index -> T' of the CTA that owns row y
-      cluster_sync_exec();                             // every CTA has read its S columns (and finished with its old T')
+      if (C::kSplitSync) cluster_wait_exec();          // every CTA has read its S columns (and finished with its old T')
+      else cluster_sync_exec();
       const int col = g.slot + (g.isB ? H : 0);
+      if (C::kAsyncHandover && threadIdx.x == 0) handover_expect(hbar, C::kHandoverBytes);
 #pragma unroll
       for (int m = 0; m < 16; ++m) {
         const int yy = out_index<C>(m, g.t);
-        st_cluster(buf + (yy % RPC) * PT + col, (uint32_t)(yy / RPC), cmake(v[m].x, -v[m].y));
+        if (C::kAsyncHandover) st_cluster_async(buf + (yy % RPC) * PT + col, hbar, (uint32_t)(yy / RPC), cmake(v[m].x, -v[m].y));
+        else st_cluster(buf + (yy % RPC) * PT + col, (uint32_t)(yy / RPC), cmake(v[m].x, -v[m].y));
       }
-      cluster_sync();
+      if (C::kAsyncHandover) { handover_wait(hbar, hphase); hphase ^= 1; }
+      else cluster_sync();
     } else if (hp == 1) {                              // physical row y, x = out_index (conjugate back, scale)
       conj16(v);
       if (phys == PH_EMIT) {
@@ -383,15 +473,19 @@ SCL_INL void round(bool has_inv, int phys, bool has_fwd, const Tables& T, const 
         out_to_in_naming<C>(v);
       }
     } else if (hp == 2) {                              // W_y(kx), kx = out_index -> T of the CTA that owns column slot(kx)
-      cluster_sync_exec();                             // every CTA has read its T' rows
+      if (C::kSplitSync) cluster_wait_exec();          // every CTA has read its T' rows
+      else cluster_sync_exec();
+      if (C::kAsyncHandover && threadIdx.x == 0) handover_expect(hbar, C::kHandoverBytes);
 #pragma unroll
       for (int m = 0; m < 16; ++m) {
         const int kx = out_index<C>(m, g.t);
         const bool minus = kx >= H;                    // kx = N / 2 is the "minus" partner of slot 0 (packed columns)
         const int sg = kx < H ? kx : (N - kx) & (N - 1) & (H - 1);
-        st_cluster(buf + g.y * PS + (sg % SPC) + (minus ? SPC : 0), (uint32_t)(sg / SPC), v[m]);
+        if (C::kAsyncHandover) st_cluster_async(buf + g.y * PS + (sg % SPC) + (minus ? SPC : 0), hbar, (uint32_t)(sg / SPC), v[m]);
+        else st_cluster(buf + g.y * PS + (sg % SPC) + (minus ? SPC : 0), (uint32_t)(sg / SPC), v[m]);
       }
-      cluster_sync();
+      if (C::kAsyncHandover) { handover_wait(hbar, hphase); hphase ^= 1; }
+      else cluster_sync();
     } else {                                           // hp == 3: Ahat / Bhat / packed C at l = out_index -> S (local)
       __syncthreads();                                 // the CTA's T columns have been read
 #pragma unroll
@@ -409,7 +503,10 @@ __global__ void __launch_bounds__((Cfg<N_, G_, CL_>::kThreads), (Cfg<N_, G_, CL_
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cplx* buf = reinterpret_cast<cplx*>(smem_raw);
   cplx* tw = buf + C::kBuf;
+  uint64_t* hbar = reinterpret_cast<uint64_t*>(tw + C::N);
+  uint32_t hphase = 0;
   for (int i = threadIdx.x; i < C::N; i += C::kThreads) tw[i] = T.tw[i];
+  if (C::kAsyncHandover && threadIdx.x == 0) handover_init(hbar);
   const int rank = (int)cluster_rank();
   const int ncl = gridDim.x / C::CL, cl = blockIdx.x / C::CL;
   const bool with_dq = prog == PROG_STEP_DQ || prog == PROG_STEP_DQ_RAW;
@@ -460,7 +557,7 @@ __global__ void __launch_bounds__((Cfg<N_, G_, CL_>::kThreads), (Cfg<N_, G_, CL_
         }
         __syncthreads();
       }
-      if (rnd) round<C>(inv, phys, fwd, T, io, m, buf, tw);
+      if (rnd) round<C>(inv, phys, fwd, T, io, m, buf, tw, hbar, hphase);
     }
   }
   cluster_sync();                                      // no CTA exits while a peer may still store into its shared memory
