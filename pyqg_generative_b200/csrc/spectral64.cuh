@@ -28,9 +28,11 @@
 namespace qgb {
 
 // pointwise spectral work, one bit per stage; a phase runs the selected stages on every half-plane point in array order
-enum { PW_TEND0 = 1, PW_TEND1 = 2, PW_UPDATE = 4, PW_UV0 = 8, PW_UV1 = 16, PW_STORE_QH = 32, PW_LOAD_QH = 64, PW_FORCING = 128 };
+enum { PW_TEND0 = 1, PW_TEND1 = 2, PW_UPDATE = 4, PW_UV0 = 8, PW_UV1 = 16, PW_STORE_QH = 32, PW_LOAD_QH = 64, PW_FORCING = 128,
+       PW_PSI = 256 };   // PW_PSI: streamfunctions of both layers as one pair (and io.ph_out)                    (pyqg _invert)
 // physical-space stage between the inverse and the forward x pass of a round
-enum { PH_PRODUCTS0 = 0, PH_PRODUCTS1 = 1, PH_LOAD_DQ = 2, PH_LOAD_Q = 3, PH_EMIT = 4 };
+enum { PH_PRODUCTS0 = 0, PH_PRODUCTS1 = 1, PH_LOAD_DQ = 2, PH_LOAD_Q = 3, PH_EMIT = 4,
+       PH_STORE_UV0 = 5, PH_STORE_UV1 = 6, PH_STORE_P = 7 };   // PROG_INVERT: u, v of a layer / psi of both layers to io.*_out
 
 namespace s64 {
 
@@ -266,7 +268,9 @@ S64_PHASE void pointwise_phase(const Tables& T, const StepIO& io, int member, cp
   constexpr bool kRead = (ST & (PW_TEND0 | PW_TEND1 | PW_FORCING | PW_STORE_QH)) != 0;
   constexpr bool kQh = (ST & PW_STORE_QH) == 0;
   constexpr bool kTend = (ST & (PW_TEND0 | PW_TEND1)) != 0, kUv = (ST & (PW_UV0 | PW_UV1)) != 0, kUpd = (ST & PW_UPDATE) != 0;
-  constexpr int zT = (ST & PW_TEND1) ? 1 : 0, zU = (ST & PW_UV1) ? 1 : 0;
+  constexpr bool kPsi = (ST & PW_PSI) != 0;            // inversion coefficients of layer 0 ride in aT, of layer 1 in aU
+  constexpr int zT = (ST & PW_TEND1) ? 1 : 0, zU = (ST & (PW_UV1 | PW_PSI)) ? 1 : 0;
+  static_assert(!kPsi || ST == PW_PSI, "PW_PSI runs alone");
   constexpr int NIT = (9 + NB - 1) / NB;
   const double dt1 = io.dt1, dt2 = io.dt2, dt3 = io.dt3;
 #pragma unroll 1
@@ -284,8 +288,8 @@ S64_PHASE void pointwise_phase(const Tables& T, const StepIO& io, int member, cp
       l[u] = idx[u] / NK;
       k[u] = idx[u] - l[u] * NK;
       if (kQh) { q0[u] = P.qh[idx[u]]; q1[u] = P.qh[NN + idx[u]]; }
-      if (kTend) { aT0[u] = T.a[(2 * zT) * NN + idx[u]]; aT1[u] = T.a[(2 * zT + 1) * NN + idx[u]]; }
-      if (kUv) { aU0[u] = T.a[(2 * zU) * NN + idx[u]]; aU1[u] = T.a[(2 * zU + 1) * NN + idx[u]]; }
+      if (kTend || kPsi) { aT0[u] = T.a[(2 * zT) * NN + idx[u]]; aT1[u] = T.a[(2 * zT + 1) * NN + idx[u]]; }
+      if (kUv || kPsi) { aU0[u] = T.a[(2 * zU) * NN + idx[u]]; aU1[u] = T.a[(2 * zU + 1) * NN + idx[u]]; }
       if (kUpd) {
         fl[u] = T.filtr[idx[u]];
         dc0[u] = P.d_cur[idx[u]];
@@ -337,6 +341,13 @@ S64_PHASE void pointwise_phase(const Tables& T, const StepIO& io, int member, cp
         spec_write(S, l[u], k[u], cmake(lv[u] * ph.y, -lv[u] * ph.x), cmake(-kv[u] * ph.y, kv[u] * ph.x));
       }
       if ((ST & PW_LOAD_QH) && ok[u]) spec_write(S, l[u], k[u], q0[u], q1[u]);
+      if (kPsi && ok[u]) {
+        // ph_z = a[z][0] qh_0 + a[z][1] qh_1                                                           (pyqg _invert)
+        const cplx p0 = cmake(aT0[u] * q0[u].x + aT1[u] * q1[u].x, aT0[u] * q0[u].y + aT1[u] * q1[u].y);
+        const cplx p1 = cmake(aU0[u] * q0[u].x + aU1[u] * q1[u].x, aU0[u] * q0[u].y + aU1[u] * q1[u].y);
+        spec_write(S, l[u], k[u], p0, p1);
+        if (io.ph_out) { cplx* o = io.ph_out + (long long)member * 2 * NN; o[idx[u]] = p0; o[NN + idx[u]] = p1; }
+      }
     }
   }
 }
@@ -408,7 +419,20 @@ S64_PHASE void round(bool has_inv, int phys, bool has_fwd, const Tables& T, cons
       __syncthreads();
     } else if (hp == 1) {                              // physical row y, x = t + 4 i + 16 k2 (conjugate back, scale)
       conj16(v);
-      if (phys == PH_EMIT) {
+      if (phys >= PH_STORE_UV0) {
+        // PROG_INVERT: (u, v) of layer z, or (psi_0, psi_1), scaled and stored (null outputs are skipped)
+        const long long mo = (long long)member * 2 * NPIX;
+        double* d0 = phys == PH_STORE_P ? io.p_out : io.u_out;
+        double* d1 = phys == PH_STORE_P ? io.p_out : io.v_out;
+        if (d0) d0 += mo + (phys == PH_STORE_UV1 ? NPIX : 0);
+        if (d1) d1 += mo + (phys == PH_STORE_UV0 ? 0 : NPIX);
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+          const int i = g.y * N + g.xt + 4 * (m >> 2) + 16 * (m & 3);
+          if (d0) d0[i] = v[m].x * s;
+          if (d1) d1[i] = v[m].y * s;
+        }
+      } else if (phys == PH_EMIT) {
         // q = irfft2(qh) (+ the fp32 normalised closure input  x_scale.normalize(m.q.astype('float32')))
 #pragma unroll
         for (int m = 0; m < 16; ++m) {
@@ -446,7 +470,8 @@ S64_PHASE void round(bool has_inv, int phys, bool has_fwd, const Tables& T, cons
 
 
 #ifndef S64_HELPERS_ONLY      // (spectral_cl.cuh reuses the building blocks above)
-// prog: PROG_STEP, PROG_STEP_DQ, PROG_STEP_DQ_RAW, PROG_SET_Q, PROG_C2R
+// prog: PROG_STEP, PROG_STEP_DQ, PROG_STEP_DQ_RAW, PROG_SET_Q, PROG_C2R, PROG_ADVECT (the tendencies of both layers into d_cur, no
+// update), PROG_INVERT (u, v of both layers, psi of both layers, the spectral psi -> io.u_out, v_out, p_out, ph_out)
 __global__ void __launch_bounds__(kThreads, 2) qg_step64_kernel(const __grid_constant__ Tables T, const __grid_constant__ StepIO io,
                                                                 int prog, int members) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -457,7 +482,7 @@ __global__ void __launch_bounds__(kThreads, 2) qg_step64_kernel(const __grid_con
   const bool demean = prog == PROG_STEP_DQ;
   const int nrounds = prog == PROG_C2R ? 1 : prog == PROG_SET_Q ? 2 : (with_dq ? 4 : 3);
   for (int m = blockIdx.x; m < members; m += gridDim.x) {
-    if (S64_PREFETCH) {   // pull everything this member's step reads from HBM into L2 now: the pointwise phases then see L2 latency, not DRAM's
+    if (S64_PREFETCH && prog != PROG_INVERT && prog != PROG_ADVECT) {   // pull everything this member's step reads from HBM into L2 now: the pointwise phases then see L2 latency, not DRAM's
       const MemberPtrs P(io, m);
       const int nspec = 2 * NN * (int)sizeof(cplx) / 128, nphys = 2 * NPIX * (int)sizeof(double) / 128;
       for (int i = threadIdx.x; i < nspec; i += kThreads) {
@@ -482,14 +507,22 @@ __global__ void __launch_bounds__(kThreads, 2) qg_step64_kernel(const __grid_con
       if (prog == PROG_C2R) { pw = PW_LOAD_QH; fwd = false; }
       else if (prog == PROG_SET_Q) {
         if (r == 0) { inv = false; phys = PH_LOAD_Q; } else { pw = PW_STORE_QH; rnd = false; }
+      } else if (prog == PROG_INVERT) {
+        fwd = false;
+        if (r == 0) { pw = PW_UV0; phys = PH_STORE_UV0; }
+        else if (r == 1) { pw = PW_UV1; phys = PH_STORE_UV1; }
+        else { pw = PW_PSI; phys = PH_STORE_P; rnd = io.p_out != nullptr; if (!rnd && !io.ph_out) pw = 0; }
       } else if (r == 0) { pw = PW_UV0; phys = PH_PRODUCTS0; }
       else if (r == 1) { pw = PW_TEND0 | PW_UV1; phys = PH_PRODUCTS1; }
+      else if (r == 2 && prog == PROG_ADVECT) { pw = PW_TEND1; rnd = false; }
       else if (r == 2 && with_dq) { pw = PW_TEND1; inv = false; phys = PH_LOAD_DQ; }
       else if (r == 2) { pw = PW_TEND1 | PW_UPDATE; fwd = false; }
       else { pw = PW_FORCING | PW_UPDATE; fwd = false; }
       if (pw) {
         switch (pw) {
           case PW_UV0: pointwise_phase<PW_UV0, S64_NB_UV>(T, io, m, buf, demean); break;
+          case PW_UV1: pointwise_phase<PW_UV1, S64_NB_UV>(T, io, m, buf, demean); break;
+          case PW_PSI: pointwise_phase<PW_PSI, S64_NB_UV>(T, io, m, buf, demean); break;
           case PW_TEND0 | PW_UV1: pointwise_phase<PW_TEND0 | PW_UV1, S64_NB_LIGHT>(T, io, m, buf, demean); break;
           case PW_TEND1: pointwise_phase<PW_TEND1, S64_NB_LIGHT>(T, io, m, buf, demean); break;
           case PW_TEND1 | PW_UPDATE: pointwise_phase<PW_TEND1 | PW_UPDATE, S64_NB_UPD>(T, io, m, buf, demean); break;

@@ -291,7 +291,9 @@ SCL_INL void pointwise_phase(const Tables& T, const StepIO& io, int member, int 
   constexpr bool kRead = (ST & (PW_TEND0 | PW_TEND1 | PW_FORCING | PW_STORE_QH)) != 0;
   constexpr bool kQh = (ST & PW_STORE_QH) == 0;
   constexpr bool kTend = (ST & (PW_TEND0 | PW_TEND1)) != 0, kUv = (ST & (PW_UV0 | PW_UV1)) != 0, kUpd = (ST & PW_UPDATE) != 0;
-  constexpr int zT = (ST & PW_TEND1) ? 1 : 0, zU = (ST & PW_UV1) ? 1 : 0;
+  constexpr bool kPsi = (ST & PW_PSI) != 0;            // inversion coefficients of layer 0 ride in aT, of layer 1 in aU
+  constexpr int zT = (ST & PW_TEND1) ? 1 : 0, zU = (ST & (PW_UV1 | PW_PSI)) ? 1 : 0;
+  static_assert(!kPsi || ST == PW_PSI, "PW_PSI runs alone");
   constexpr int NN = C::NN, NK = C::NK;
   constexpr int NMAIN = C::SPC * C::N / C::kThreads;         // 8 points per thread; CTA 0 adds the column k = N / 2
   constexpr int NIT = (NMAIN + 1 + NB - 1) / NB;
@@ -321,8 +323,8 @@ SCL_INL void pointwise_phase(const Tables& T, const StepIO& io, int member, int 
       }
       idx[u] = l[u] * NK + k[u];
       if (kQh) { q0[u] = P.qh[idx[u]]; q1[u] = P.qh[NN + idx[u]]; }
-      if (kTend) { aT0[u] = T.a[(2 * zT) * NN + idx[u]]; aT1[u] = T.a[(2 * zT + 1) * NN + idx[u]]; }
-      if (kUv) { aU0[u] = T.a[(2 * zU) * NN + idx[u]]; aU1[u] = T.a[(2 * zU + 1) * NN + idx[u]]; }
+      if (kTend || kPsi) { aT0[u] = T.a[(2 * zT) * NN + idx[u]]; aT1[u] = T.a[(2 * zT + 1) * NN + idx[u]]; }
+      if (kUv || kPsi) { aU0[u] = T.a[(2 * zU) * NN + idx[u]]; aU1[u] = T.a[(2 * zU + 1) * NN + idx[u]]; }
       if (kUpd) {
         fl[u] = T.filtr[idx[u]];
         dc0[u] = P.d_cur[idx[u]];
@@ -370,6 +372,12 @@ SCL_INL void pointwise_phase(const Tables& T, const StepIO& io, int member, int 
         spec_write<C>(S, l[u], k[u], kk[u], cmake(lv[u] * ph.y, -lv[u] * ph.x), cmake(-kv[u] * ph.y, kv[u] * ph.x));
       }
       if ((ST & PW_LOAD_QH) && ok[u]) spec_write<C>(S, l[u], k[u], kk[u], q0[u], q1[u]);
+      if (kPsi && ok[u]) {                               // ph_z = a[z][0] qh_0 + a[z][1] qh_1            (pyqg _invert)
+        const cplx p0 = cmake(aT0[u] * q0[u].x + aT1[u] * q1[u].x, aT0[u] * q0[u].y + aT1[u] * q1[u].y);
+        const cplx p1 = cmake(aU0[u] * q0[u].x + aU1[u] * q1[u].x, aU0[u] * q0[u].y + aU1[u] * q1[u].y);
+        spec_write<C>(S, l[u], k[u], kk[u], p0, p1);
+        if (io.ph_out) { cplx* o = io.ph_out + (long long)member * 2 * NN; o[idx[u]] = p0; o[NN + idx[u]] = p1; }
+      }
     }
   }
 }
@@ -452,7 +460,19 @@ SCL_INL void round(bool has_inv, int phys, bool has_fwd, const Tables& T, const 
       else cluster_sync();
     } else if (hp == 1) {                              // physical row y, x = out_index (conjugate back, scale)
       conj16(v);
-      if (phys == PH_EMIT) {
+      if (phys >= PH_STORE_UV0) {                      // PROG_INVERT: (u, v) of a layer or (psi_0, psi_1) -> io.*_out
+        const long long mo = (long long)member * 2 * NPIX;
+        double* d0 = phys == PH_STORE_P ? io.p_out : io.u_out;
+        double* d1 = phys == PH_STORE_P ? io.p_out : io.v_out;
+        if (d0) d0 += mo + (phys == PH_STORE_UV1 ? NPIX : 0);
+        if (d1) d1 += mo + (phys == PH_STORE_UV0 ? 0 : NPIX);
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+          const int i = g.y * N + out_index<C>(m, g.t);
+          if (d0) d0[i] = v[m].x * s;
+          if (d1) d1[i] = v[m].y * s;
+        }
+      } else if (phys == PH_EMIT) {
 #pragma unroll
         for (int m = 0; m < 16; ++m) {
           const int i = g.y * N + out_index<C>(m, g.t);
@@ -495,7 +515,7 @@ SCL_INL void round(bool has_inv, int phys, bool has_fwd, const Tables& T, const 
   }
 }
 
-// prog: PROG_STEP, PROG_STEP_DQ, PROG_STEP_DQ_RAW, PROG_SET_Q, PROG_C2R.  One cluster of CL CTAs per member.
+// prog: PROG_STEP, PROG_STEP_DQ, PROG_STEP_DQ_RAW, PROG_SET_Q, PROG_C2R, PROG_ADVECT, PROG_INVERT (spectral64.cuh).  One cluster of CL CTAs per member.
 template <int N_, int G_, int CL_>
 __global__ void __launch_bounds__((Cfg<N_, G_, CL_>::kThreads), (Cfg<N_, G_, CL_>::kCtasPerSm)) qg_step_cl_kernel(const __grid_constant__ Tables T, const __grid_constant__ StepIO io,
                                                             int prog, int members) {
@@ -540,14 +560,22 @@ __global__ void __launch_bounds__((Cfg<N_, G_, CL_>::kThreads), (Cfg<N_, G_, CL_
       if (prog == PROG_C2R) { pw = PW_LOAD_QH; fwd = false; }
       else if (prog == PROG_SET_Q) {
         if (r == 0) { inv = false; phys = PH_LOAD_Q; } else { pw = PW_STORE_QH; rnd = false; }
+      } else if (prog == PROG_INVERT) {
+        fwd = false;
+        if (r == 0) { pw = PW_UV0; phys = PH_STORE_UV0; }
+        else if (r == 1) { pw = PW_UV1; phys = PH_STORE_UV1; }
+        else { pw = PW_PSI; phys = PH_STORE_P; rnd = io.p_out != nullptr; if (!rnd && !io.ph_out) pw = 0; }
       } else if (r == 0) { pw = PW_UV0; phys = PH_PRODUCTS0; }
       else if (r == 1) { pw = PW_TEND0 | PW_UV1; phys = PH_PRODUCTS1; }
+      else if (r == 2 && prog == PROG_ADVECT) { pw = PW_TEND1; rnd = false; }
       else if (r == 2 && with_dq) { pw = PW_TEND1; inv = false; phys = PH_LOAD_DQ; }
       else if (r == 2) { pw = PW_TEND1 | PW_UPDATE; fwd = false; }
       else { pw = PW_FORCING | PW_UPDATE; fwd = false; }
       if (pw) {
         switch (pw) {
           case PW_UV0: pointwise_phase<C, PW_UV0, SCL_NB_UV>(T, io, m, rank, buf, demean); break;
+          case PW_UV1: pointwise_phase<C, PW_UV1, SCL_NB_UV>(T, io, m, rank, buf, demean); break;
+          case PW_PSI: pointwise_phase<C, PW_PSI, SCL_NB_UV>(T, io, m, rank, buf, demean); break;
           case PW_TEND0 | PW_UV1: pointwise_phase<C, PW_TEND0 | PW_UV1, SCL_NB_TEND>(T, io, m, rank, buf, demean); break;
           case PW_TEND1: pointwise_phase<C, PW_TEND1, SCL_NB_TEND>(T, io, m, rank, buf, demean); break;
           case PW_TEND1 | PW_UPDATE: pointwise_phase<C, PW_TEND1 | PW_UPDATE, SCL_NB_UPD>(T, io, m, rank, buf, demean); break;

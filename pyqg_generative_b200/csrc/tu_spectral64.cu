@@ -10,7 +10,7 @@ cudaError_t spectral64_configure() {
 }
 
 bool spectral64_handles(int prog) {
-  return prog == PROG_STEP || prog == PROG_STEP_DQ || prog == PROG_STEP_DQ_RAW || prog == PROG_SET_Q || prog == PROG_C2R;
+  return prog == PROG_STEP || prog == PROG_STEP_DQ || prog == PROG_STEP_DQ_RAW || prog == PROG_SET_Q || prog == PROG_C2R || prog == PROG_ADVECT || prog == PROG_INVERT;
 }
 
 cudaError_t spectral64_launch(const Tables& T, const StepIO& io, int prog, int members, cudaStream_t st) {

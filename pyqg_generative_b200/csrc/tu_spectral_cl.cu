@@ -37,7 +37,7 @@ cudaError_t launch_cl(const Tables& T, const StepIO& io, int prog, int members, 
 
 bool spectralcl_handles(int N, int prog) {
   return (N == 128 || N == 256) &&
-         (prog == PROG_STEP || prog == PROG_STEP_DQ || prog == PROG_STEP_DQ_RAW || prog == PROG_SET_Q || prog == PROG_C2R);
+         (prog == PROG_STEP || prog == PROG_STEP_DQ || prog == PROG_STEP_DQ_RAW || prog == PROG_SET_Q || prog == PROG_C2R || prog == PROG_ADVECT || prog == PROG_INVERT);
 }
 
 cudaError_t spectralcl_launch(const Tables& T, const StepIO& io, int prog, int members, cudaStream_t st) {
