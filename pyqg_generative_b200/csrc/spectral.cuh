@@ -163,27 +163,38 @@ __global__ void diag_finish_kernel(const double* __restrict__ red, int members, 
   }
 }
 
-// pyqg diagnostics KEspec = wv2 |ph|^2 / M^2, Ensspec = |qh|^2 / M^2, summed over the local members
-__global__ void spectra_kernel(const __grid_constant__ Tables T, const cplx* __restrict__ qh, int members,
-                               double* __restrict__ kespec, double* __restrict__ ensspec) {
+// pyqg diagnostics KEspec = wv2 |ph|^2 / M^2, Ensspec = |qh|^2 / M^2, summed over the local members.  Block = 32 spectral points x
+// kSpectraParts member slices (a warp reads 32 consecutive points of one member: 512 contiguous bytes); the slices are added in a fixed
+// order, so the sums are deterministic.  (One thread per point looping over all members ran 33 blocks for 0.31 ms at 64^2 x 1024.)
+constexpr int kSpectraParts = 8;
+__global__ void __launch_bounds__(32 * kSpectraParts) spectra_kernel(const __grid_constant__ Tables T, const cplx* __restrict__ qh, int members,
+                                                                 double* __restrict__ kespec, double* __restrict__ ensspec) {
+  __shared__ double sk[kSpectraParts][32], se[kSpectraParts][32];
   const int NN = T.N * T.NK;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= 2 * NN) return;
-  const int z = i / NN, idx = i - z * NN;
-  const int l = idx / T.NK, k = idx - l * T.NK;
-  const double wv2 = T.kv[k] * T.kv[k] + T.lv[l] * T.lv[l];
-  const double a0 = T.a[(2 * z) * NN + idx], a1 = T.a[(2 * z + 1) * NN + idx];
+  const int i = blockIdx.x * 32 + threadIdx.x, part = threadIdx.y;
   double ke = 0.0, en = 0.0;
-  for (int m = 0; m < members; ++m) {
-    const cplx q0 = qh[(long long)m * 2 * NN + idx], q1 = qh[(long long)m * 2 * NN + NN + idx];
-    const double px = a0 * q0.x + a1 * q1.x, py = a0 * q0.y + a1 * q1.y;
-    ke += wv2 * (px * px + py * py);
-    const cplx qq = z == 0 ? q0 : q1;
-    en += qq.x * qq.x + qq.y * qq.y;
+  if (i < 2 * NN) {
+    const int z = i / NN, idx = i - z * NN;
+    const int l = idx / T.NK, k = idx - l * T.NK;
+    const double wv2 = T.kv[k] * T.kv[k] + T.lv[l] * T.lv[l];
+    const double a0 = T.a[(2 * z) * NN + idx], a1 = T.a[(2 * z + 1) * NN + idx];
+    for (int m = part; m < members; m += kSpectraParts) {
+      const cplx q0 = qh[(long long)m * 2 * NN + idx], q1 = qh[(long long)m * 2 * NN + NN + idx];
+      const double px = a0 * q0.x + a1 * q1.x, py = a0 * q0.y + a1 * q1.y;
+      ke += wv2 * (px * px + py * py);
+      const cplx qq = z == 0 ? q0 : q1;
+      en += qq.x * qq.x + qq.y * qq.y;
+    }
   }
-  const double s = T.inv_M * T.inv_M;
-  if (kespec) kespec[i] = ke * s;
-  if (ensspec) ensspec[i] = en * s;
+  sk[part][threadIdx.x] = ke;
+  se[part][threadIdx.x] = en;
+  __syncthreads();
+  if (part == 0 && i < 2 * NN) {
+    for (int p = 1; p < kSpectraParts; ++p) { ke += sk[p][threadIdx.x]; en += se[p][threadIdx.x]; }
+    const double s = T.inv_M * T.inv_M;
+    if (kespec) kespec[i] = ke * s;
+    if (ensspec) ensspec[i] = en * s;
+  }
 }
 
 }  // namespace qgb

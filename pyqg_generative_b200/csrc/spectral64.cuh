@@ -32,7 +32,10 @@ enum { PW_TEND0 = 1, PW_TEND1 = 2, PW_UPDATE = 4, PW_UV0 = 8, PW_UV1 = 16, PW_ST
        PW_PSI = 256 };   // PW_PSI: streamfunctions of both layers as one pair (and io.ph_out)                    (pyqg _invert)
 // physical-space stage between the inverse and the forward x pass of a round
 enum { PH_PRODUCTS0 = 0, PH_PRODUCTS1 = 1, PH_LOAD_DQ = 2, PH_LOAD_Q = 3, PH_EMIT = 4,
-       PH_STORE_UV0 = 5, PH_STORE_UV1 = 6, PH_STORE_P = 7 };   // PROG_INVERT: u, v of a layer / psi of both layers to io.*_out
+       PH_STORE_UV0 = 5, PH_STORE_UV1 = 6, PH_STORE_P = 7,     // PROG_INVERT: u, v of a layer / psi of both layers to io.*_out
+       // PROG_BUDGET (round<true>): products of the inverse transform with scratch field 0..2 / with q_0, q_1 (values < PH_STORE_UV0 are
+       // product stages), inverse transform stored to the scratch fields 0, 1 / to scratch field 2
+       PH_SCR_STORE01 = 8, PH_SCR_STORE2 = 9, PH_SCR_PROD0 = -8, PH_SCR_PROD1 = -7, PH_SCR_PROD2 = -6, PH_ANOM0 = -4, PH_ANOM1 = -3 };
 
 namespace s64 {
 
@@ -258,6 +261,108 @@ struct MemberPtrs {
 };
 
 
+// ---- spectral energy / enstrophy budgets (PROG_BUDGET) at one half-plane point ------------------------------------------------
+// The arithmetic of qg_core.cuh ph_bud_keflux / ph_bud_apeflux / ph_bud_ens / ph_bud_param / ph_bud_diss and of its spectral
+// builders GetXi / GetUV / GetTau / GetUVbt (pyqg _calc_derived_fields + the add_diagnostic lambdas), one point at a time, for the
+// register-FFT kernels: a budget phase first consumes the pair of half-plane spectra (A, B) the last forward transform left in S
+// (BR_*), then leaves the next pair to be transformed back in S (BWR_*).
+enum { BR_NONE = 0, BR_KEFLUX0, BR_KEFLUX1, BR_APEFLUX, BR_ENS0, BR_ENS1, BR_DISS, BR_PARAM_DISS };
+enum { BWR_NONE = 0, BWR_XI, BWR_UV0, BWR_UV1, BWR_TAU, BWR_UVBT };
+
+template <int WR>
+S64_INL void bud_build(cplx p0, cplx p1, double kv, double lv, double d1, double d2, cplx& A, cplx& B) {
+  if (WR == BWR_XI) {                                  // xi_h = -wv2 ph (relative vorticity), both layers
+    const double w = -(kv * kv + lv * lv);
+    A = cscale(p0, w); B = cscale(p1, w);
+  } else if (WR == BWR_UV0 || WR == BWR_UV1) {         // uh = -il ph, vh = ik ph
+    const cplx ph = WR == BWR_UV0 ? p0 : p1;
+    A = cmake(lv * ph.y, -lv * ph.x); B = cmake(-kv * ph.y, kv * ph.x);
+  } else if (WR == BWR_TAU) {                          // tau_h = ph0 - ph1, paired with zero
+    A = csub(p0, p1); B = cmake(0.0, 0.0);
+  } else {                                             // barotropic velocities del1 u0 + del2 u1, del1 v0 + del2 v1
+    const cplx u0 = cmake(lv * p0.y, -lv * p0.x), v0 = cmake(-kv * p0.y, kv * p0.x);
+    const cplx u1 = cmake(lv * p1.y, -lv * p1.x), v1 = cmake(-kv * p1.y, kv * p1.x);
+    A = cmake(d1 * u0.x + d2 * u1.x, d1 * u0.y + d2 * u1.y);
+    B = cmake(d1 * v0.x + d2 * v1.x, d1 * v0.y + d2 * v1.y);
+  }
+}
+
+// out / tend / dp / dpp: this member's bud_out (kBudgetTerms, NN), bud_tend, dqhdt_p, dqhdt_pp; a**: inversion coefficients at idx
+template <int RD>
+S64_INL void bud_read(const Tables& T, const StepIO& io, double* out, cplx* tend, const cplx* dp, const cplx* dpp, int NN, int idx,
+                      double kv, double lv, cplx q0, cplx q1, cplx p0, cplx p1, double a00, double a01, double a10, double a11,
+                      cplx A, cplx B) {
+  const double m2 = T.inv_M * T.inv_M, d1 = io.Hi_over_H[0], d2 = io.Hi_over_H[1];
+  if (RD == BR_KEFLUX0 || RD == BR_KEFLUX1) {
+    // KEflux (+)= del_z Re(ph_z conj(Jpxi_z)) / M^2,  Jpxi_z = ik F(u xi) + il F(v xi)
+    constexpr int z = RD == BR_KEFLUX1 ? 1 : 0;
+    const cplx J = cadd(cmuli(A, kv), cmuli(B, lv));
+    const cplx ph = z ? p1 : p0;
+    const double v = (m2 * io.Hi_over_H[z]) * (ph.x * J.x + ph.y * J.y);
+    out[BUD_KEFLUX * NN + idx] = z == 0 ? v : out[BUD_KEFLUX * NN + idx] + v;
+  } else if (RD == BR_APEFLUX) {
+    const double F = io.bud_F;
+    const cplx J = cadd(cmuli(A, kv), cmuli(B, lv));                    // = -Jptpc
+    const cplx t = csub(p0, p1);
+    out[BUD_APEFLUX * NN + idx] = -F * m2 * (t.x * J.x + t.y * J.y);
+    const cplx bt = cmake(d1 * p0.x + d2 * p1.x, d1 * p0.y + d2 * p1.y);
+    const cplx ikbt = cmuli(bt, kv);
+    out[BUD_APEGEN * NN + idx] = io.bud_U * F * m2 * (ikbt.x * t.x + ikbt.y * t.y);
+    const double wv2 = kv * kv + lv * lv;
+    out[BUD_KEFRIC * NN + idx] = -T.rek * d2 * wv2 * m2 * (p1.x * p1.x + p1.y * p1.y);
+    const cplx e = cmake(d1 * q0.x + d2 * q1.x, d1 * q0.y + d2 * q1.y);
+    out[BUD_ENTSPEC * NN + idx] = m2 * (e.x * e.x + e.y * e.y);
+    out[BUD_PARAM_KE * NN + idx] = 0.0;
+    out[BUD_PARAM_APE * NN + idx] = 0.0;
+    out[BUD_ENSGEN * NN + idx] = m2 * kv * (d1 * T.Qy[0] * (q0.x * p0.y - q0.y * p0.x) + d2 * T.Qy[1] * (q1.x * p1.y - q1.y * p1.x));
+    out[BUD_ENSFRIC * NN + idx] = T.rek * d2 * wv2 * m2 * (q1.x * p1.x + q1.y * p1.y);
+    out[BUD_ENSPARAM * NN + idx] = 0.0;
+  } else if (RD == BR_ENS0 || RD == BR_ENS1) {
+    // ENSflux (+)= -del_z Re(conj(qh_z) Jq_z) / M^2; the tendency of the current state from the same Jacobian (for the dissipation spectra)
+    constexpr int z = RD == BR_ENS1 ? 1 : 0;
+    const cplx J = cadd(cmuli(A, kv), cmuli(B, lv));
+    const cplx q = z ? q1 : q0, ph = z ? p1 : p0;
+    const double v = -(m2 * io.Hi_over_H[z]) * (q.x * J.x + q.y * J.y);
+    out[BUD_ENSFLUX * NN + idx] = z == 0 ? v : out[BUD_ENSFLUX * NN + idx] + v;
+    const cplx t1 = cmuli(q, kv * T.Ubg[z]), t3 = cmuli(ph, kv * T.Qy[z]);
+    cplx r = cmake(-(J.x + t1.x + t3.x), -(J.y + t1.y + t3.y));
+    if (z == 1 && T.rek != 0.0) {
+      const double f = T.rek * (kv * kv + lv * lv);
+      r.x += f * ph.x;
+      r.y += f * ph.y;
+    }
+    tend[z * NN + idx] = r;
+  } else if (RD == BR_DISS || RD == BR_PARAM_DISS) {
+    cplx f[2] = {cmake(0.0, 0.0), cmake(0.0, 0.0)};
+    if (RD == BR_PARAM_DISS) {
+      // parameterization terms from dqh = rfft2(dq) = (A, B)
+      const cplx dp0 = cmake(a00 * A.x + a01 * B.x, a00 * A.y + a01 * B.y), dp1 = cmake(a10 * A.x + a11 * B.x, a10 * A.y + a11 * B.y);
+      const double wv2 = kv * kv + lv * lv, F = io.bud_F;
+      out[BUD_PARAM_KE * NN + idx] = wv2 * m2 * (d1 * (p0.x * dp0.x + p0.y * dp0.y) + d2 * (p1.x * dp1.x + p1.y * dp1.y));
+      const cplx t = csub(p0, p1), dtau = csub(dp0, dp1);
+      out[BUD_PARAM_APE * NN + idx] = F * m2 * (t.x * dtau.x + t.y * dtau.y);
+      if (!(io.bud_demean && idx == 0)) { f[0] = A; f[1] = B; }
+    }
+    // Dissspec / ENSDissspec from D_z = (filtr - 1)(qh_z + dt1 dqhdt_z + dt2 dqhdt_p_z + dt3 dqhdt_pp_z); ENSparamspec
+    const double fm = T.filtr[idx] - 1.0, dt1 = io.dt1, dt2 = io.dt2, dt3 = io.dt3;
+    double diss = 0.0, ensdiss = 0.0, ensparam = 0.0;
+#pragma unroll
+    for (int z = 0; z < 2; ++z) {
+      const int j = z * NN + idx;
+      const cplx q = z ? q1 : q0, ph = z ? p1 : p0;
+      const cplx dd = cadd(tend[j], f[z]), a = dp[j], b = dpp[j];
+      const cplx D = cmake(fm * (q.x + dt1 * dd.x + dt2 * a.x + dt3 * b.x), fm * (q.y + dt1 * dd.y + dt2 * a.y + dt3 * b.y));
+      const double w = io.Hi_over_H[z];
+      diss -= w * (ph.x * D.x + ph.y * D.y);
+      ensdiss += w * (q.x * D.x + q.y * D.y);
+      ensparam += w * (q.x * f[z].x + q.y * f[z].y);
+    }
+    out[BUD_DISS * NN + idx] = diss * io.bud_inv_dt * m2;
+    out[BUD_ENSDISS * NN + idx] = ensdiss * io.bud_inv_dt * m2;
+    out[BUD_ENSPARAM * NN + idx] = ensparam * m2;
+  }
+}
+
 // ST = the stages (compile time: straight-line code), NB = points in flight per thread: all global / shared loads of a batch
 // are issued before the first dependent instruction (the first version, one point at a time behind run-time stage tests, spent
 // 46 % of its stall samples waiting for these loads).
@@ -353,6 +458,7 @@ S64_PHASE void pointwise_phase(const Tables& T, const StepIO& io, int member, cp
 }
 
 // One round: [inverse 2-D transform of the spectra in S] -> physical stage in registers -> [forward 2-D transform into S].
+template <bool BUD = false>      // BUD: the physical stages of the budget program (PH_SCR_*, PH_ANOM*) are compiled in
 S64_PHASE void round(bool has_inv, int phys, bool has_fwd, const Tables& T, const StepIO& io, int member, cplx* buf, const cplx* tw) {
   const Geo g;
   const MemberPtrs P(io, member);
@@ -426,6 +532,10 @@ S64_PHASE void round(bool has_inv, int phys, bool has_fwd, const Tables& T, cons
         double* d1 = phys == PH_STORE_P ? io.p_out : io.v_out;
         if (d0) d0 += mo + (phys == PH_STORE_UV1 ? NPIX : 0);
         if (d1) d1 += mo + (phys == PH_STORE_UV0 ? 0 : NPIX);
+        if (BUD && phys >= PH_SCR_STORE01) {           // xi_0, xi_1 -> scratch fields 0, 1;  tau -> scratch field 2
+          d0 = io.bud_scr + ((long long)member * 3 + (phys == PH_SCR_STORE2 ? 2 : 0)) * NPIX;
+          d1 = phys == PH_SCR_STORE2 ? nullptr : d0 + NPIX;
+        }
 #pragma unroll
         for (int m = 0; m < 16; ++m) {
           const int i = g.y * N + g.xt + 4 * (m >> 2) + 16 * (m & 3);
@@ -446,7 +556,12 @@ S64_PHASE void round(bool has_inv, int phys, bool has_fwd, const Tables& T, cons
         // (u + Ubg) q + i v q                                            (pyqg _do_advection, physical-space products)
         const int z = phys == PH_PRODUCTS1 ? 1 : 0;
         const double* qz = P.q + z * NPIX + g.y * N + g.xt;
-        const double U = T.Ubg[z];
+        double U = T.Ubg[z];
+        if (BUD) {                                     // budget products use the ANOMALY velocities: u f + i v f
+          U = 0.0;
+          if (phys == PH_ANOM0 || phys == PH_ANOM1) qz = P.q + (phys - PH_ANOM0) * NPIX + g.y * N + g.xt;
+          else qz = io.bud_scr + ((long long)member * 3 + (phys - PH_SCR_PROD0)) * NPIX + g.y * N + g.xt;
+        }
 #pragma unroll
         for (int m = 0; m < 16; ++m) {
           const double qq = qz[4 * (m >> 2) + 16 * (m & 3)];
@@ -533,6 +648,88 @@ __global__ void __launch_bounds__(kThreads, 2) qg_step64_kernel(const __grid_con
         __syncthreads();
       }
       if (rnd) round(inv, phys, fwd, T, io, m, buf, tw);
+      if (prog == PROG_INVERT) __syncthreads();        // an inverse-only round ends with reads of T': the next phase writes S over it
+    }
+  }
+}
+
+// ---- PROG_BUDGET (qg_core.cuh run_program: 7 inverse + 5 forward packed transforms, +1 with a forcing) ---------------------------
+// RD: what the phase does with the spectra of the last forward transform; WR: the pair it leaves in S for the next inverse one.
+template <int RD, int WR, int NB>
+S64_PHASE void budget_phase(const Tables& T, const StepIO& io, int member, cplx* S) {
+  const long long mo = (long long)member * 2 * NN;
+  const cplx* qh = io.qh + mo;
+  double* out = io.bud_out + (long long)member * kBudgetTerms * NN;
+  cplx* tend = io.bud_tend + mo;
+  const cplx *dp = io.d_p + mo, *dpp = io.d_pp + mo;
+  const double dkw = T.kv[1], d1 = io.Hi_over_H[0], d2 = io.Hi_over_H[1];
+  constexpr bool kRead = RD != BR_NONE && RD != BR_DISS;
+  constexpr int NIT = (9 + NB - 1) / NB;
+#pragma unroll 1
+  for (int b = 0; b < NIT; ++b) {
+    int idx[NB], l[NB], k[NB];
+    bool ok[NB];
+    cplx q0[NB], q1[NB];
+    double a00[NB], a01[NB], a10[NB], a11[NB];
+#pragma unroll
+    for (int u = 0; u < NB; ++u) {
+      const int i = threadIdx.x + kThreads * (b * NB + u);
+      ok[u] = i < NN;
+      idx[u] = ok[u] ? i : NN - 1;
+      l[u] = idx[u] / NK;
+      k[u] = idx[u] - l[u] * NK;
+      q0[u] = qh[idx[u]]; q1[u] = qh[NN + idx[u]];
+      a00[u] = T.a[idx[u]]; a01[u] = T.a[NN + idx[u]]; a10[u] = T.a[2 * NN + idx[u]]; a11[u] = T.a[3 * NN + idx[u]];
+    }
+#pragma unroll
+    for (int u = 0; u < NB; ++u) {
+      const double kv = dkw * (double)k[u], lv = dkw * (double)(l[u] < N / 2 ? l[u] : l[u] - N);
+      const cplx p0 = cmake(a00[u] * q0[u].x + a01[u] * q1[u].x, a00[u] * q0[u].y + a01[u] * q1[u].y);
+      const cplx p1 = cmake(a10[u] * q0[u].x + a11[u] * q1[u].x, a10[u] * q0[u].y + a11[u] * q1[u].y);
+      cplx A = cmake(0.0, 0.0), B = cmake(0.0, 0.0);
+      if (kRead) spec_read(S, l[u], k[u], A, B);
+      if (RD != BR_NONE && ok[u])
+        bud_read<RD>(T, io, out, tend, dp, dpp, NN, idx[u], kv, lv, q0[u], q1[u], p0, p1, a00[u], a01[u], a10[u], a11[u], A, B);
+      if (WR != BWR_NONE && ok[u]) {
+        cplx oA, oB;
+        bud_build<WR>(p0, p1, kv, lv, d1, d2, oA, oB);
+        spec_write(S, l[u], k[u], oA, oB);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 2) qg_budget64_kernel(const __grid_constant__ Tables T, const __grid_constant__ StepIO io, int members) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx* buf = reinterpret_cast<cplx*>(smem_raw);
+  cplx* tw = buf + N * PITCH;
+  for (int i = threadIdx.x; i < N; i += kThreads) tw[i] = T.tw[i];
+  const bool has_dq = io.dq != nullptr;
+  for (int m = blockIdx.x; m < members; m += gridDim.x) {
+    __syncthreads();
+#pragma unroll 1
+    for (int r = 0; r < 9; ++r) {
+      // phase r (consume the last forward transform, build the next pair), then round r: inverse -> physical stage -> [forward]
+      int phys = PH_EMIT;
+      bool inv = true, fwd = true, rnd = true;
+      switch (r) {
+        case 0: budget_phase<BR_NONE, BWR_XI, 2>(T, io, m, buf); phys = PH_SCR_STORE01; fwd = false; break;      // xi_0, xi_1
+        case 1: budget_phase<BR_NONE, BWR_UV0, 2>(T, io, m, buf); phys = PH_SCR_PROD0; break;                    // u_0 xi_0 + i v_0 xi_0
+        case 2: budget_phase<BR_KEFLUX0, BWR_UV1, 2>(T, io, m, buf); phys = PH_SCR_PROD1; break;
+        case 3: budget_phase<BR_KEFLUX1, BWR_TAU, 2>(T, io, m, buf); phys = PH_SCR_STORE2; fwd = false; break;   // tau
+        case 4: budget_phase<BR_NONE, BWR_UVBT, 2>(T, io, m, buf); phys = PH_SCR_PROD2; break;                   // u_bt tau + i v_bt tau
+        case 5: budget_phase<BR_APEFLUX, BWR_UV0, 2>(T, io, m, buf); phys = PH_ANOM0; break;                     // u_0 q_0 + i v_0 q_0
+        case 6: budget_phase<BR_ENS0, BWR_UV1, 2>(T, io, m, buf); phys = PH_ANOM1; break;
+        case 7: budget_phase<BR_ENS1, BWR_NONE, 2>(T, io, m, buf); inv = false; phys = PH_LOAD_DQ; rnd = has_dq; break;   // rfft2(dq)
+        default:
+          if (has_dq) budget_phase<BR_PARAM_DISS, BWR_NONE, 1>(T, io, m, buf);
+          else budget_phase<BR_DISS, BWR_NONE, 1>(T, io, m, buf);
+          rnd = false;
+          break;
+      }
+      __syncthreads();
+      if (rnd) round<true>(inv, phys, fwd, T, io, m, buf, tw);
+      if (!fwd) __syncthreads();                       // an inverse-only round ends with reads of T': the next phase writes S over it
     }
   }
 }

@@ -93,7 +93,7 @@ cudaError_t launch_diag_finish(const double* red, int members, double dt_over_dx
 
 cudaError_t launch_spectra(const Tables& T, const cplx* qh, int members, double* kespec, double* ensspec, cudaStream_t st) {
   const int n = 2 * T.N * T.NK;
-  spectra_kernel<<<(n + 127) / 128, 128, 0, st>>>(T, qh, members, kespec, ensspec);
+  spectra_kernel<<<(n + 31) / 32, dim3(32, kSpectraParts), 0, st>>>(T, qh, members, kespec, ensspec);
   return cudaGetLastError();
 }
 

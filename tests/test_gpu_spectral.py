@@ -76,9 +76,9 @@ def test_many_steps_in_one_call_equal_single_steps_and_oracle_ke():
     assert abs(m.diagnostics()[0][0] - o._calc_ke()) < 1e-9 * o._calc_ke()
 
 
-def test_host_callback_parameterization_and_weighting():
+@pytest.mark.parametrize('N,dt', [(32, 14400.), (64, 14400.), (128, 7200.), (256, 3600.)])   # generic, register-FFT and cluster kernels
+def test_host_callback_parameterization_and_weighting(N, dt):
     from pyqg_generative_b200.models.parameterization import QParameterization
-    N, dt = 32, 14400.
     rng = np.random.RandomState(2)
     dq = rng.randn(2, N, N) * 1e-12 + 2e-12
 
