@@ -29,6 +29,11 @@ using s64::exchange_pair;
 using s64::fft16;
 using s64::mulw16;
 using s64::sel;
+using s64::bud_build;
+using s64::bud_read;
+using s64::BR_NONE; using s64::BR_KEFLUX0; using s64::BR_KEFLUX1; using s64::BR_APEFLUX; using s64::BR_ENS0; using s64::BR_ENS1;
+using s64::BR_DISS; using s64::BR_PARAM_DISS;
+using s64::BWR_NONE; using s64::BWR_XI; using s64::BWR_UV0; using s64::BWR_UV1; using s64::BWR_TAU; using s64::BWR_UVBT;
 
 template <int N_, int G_, int CL_>
 struct Cfg {
@@ -383,7 +388,7 @@ SCL_INL void pointwise_phase(const Tables& T, const StepIO& io, int member, int 
 }
 
 // One round: [inverse 2-D transform of the spectra in S] -> physical stage in registers -> [forward 2-D transform into S]
-template <class C>
+template <class C, bool BUD = false>      // BUD: the physical stages of the budget program (PH_SCR_*, PH_ANOM*) are compiled in
 SCL_INL void round(bool has_inv, int phys, bool has_fwd, const Tables& T, const StepIO& io, int member, cplx* buf, const cplx* tw,
                    uint64_t* hbar, uint32_t& hphase) {
   constexpr int N = C::N, G = C::G, H = C::H, SPC = C::SPC, PS = C::PS, PT = C::PT, RPC = C::RPC, NPIX = C::NPIX;
@@ -466,6 +471,10 @@ SCL_INL void round(bool has_inv, int phys, bool has_fwd, const Tables& T, const 
         double* d1 = phys == PH_STORE_P ? io.p_out : io.v_out;
         if (d0) d0 += mo + (phys == PH_STORE_UV1 ? NPIX : 0);
         if (d1) d1 += mo + (phys == PH_STORE_UV0 ? 0 : NPIX);
+        if (BUD && phys >= PH_SCR_STORE01) {           // xi_0, xi_1 -> scratch fields 0, 1;  tau -> scratch field 2
+          d0 = io.bud_scr + ((long long)member * 3 + (phys == PH_SCR_STORE2 ? 2 : 0)) * NPIX;
+          d1 = phys == PH_SCR_STORE2 ? nullptr : d0 + NPIX;
+        }
 #pragma unroll
         for (int m = 0; m < 16; ++m) {
           const int i = g.y * N + out_index<C>(m, g.t);
@@ -484,7 +493,12 @@ SCL_INL void round(bool has_inv, int phys, bool has_fwd, const Tables& T, const 
       } else {
         const int z = phys == PH_PRODUCTS1 ? 1 : 0;
         const double* qz = P.q + z * NPIX + g.y * N;
-        const double U = T.Ubg[z];
+        double U = T.Ubg[z];
+        if (BUD) {                                     // budget products use the ANOMALY velocities: u f + i v f
+          U = 0.0;
+          if (phys == PH_ANOM0 || phys == PH_ANOM1) qz = P.q + (phys - PH_ANOM0) * NPIX + g.y * N;
+          else qz = io.bud_scr + ((long long)member * 3 + (phys - PH_SCR_PROD0)) * NPIX + g.y * N;
+        }
 #pragma unroll
         for (int m = 0; m < 16; ++m) {
           const double qq = qz[out_index<C>(m, g.t)];
@@ -586,9 +600,110 @@ __global__ void __launch_bounds__((Cfg<N_, G_, CL_>::kThreads), (Cfg<N_, G_, CL_
         __syncthreads();
       }
       if (rnd) round<C>(inv, phys, fwd, T, io, m, buf, tw, hbar, hphase);
+      if (prog == PROG_INVERT) __syncthreads();        // an inverse-only round ends with reads of T': the next phase writes S over it
     }
   }
   cluster_sync();                                      // no CTA exits while a peer may still store into its shared memory
+}
+
+// ---- PROG_BUDGET on the cluster (spectral64.cuh budget_phase / qg_budget64_kernel; the per-point arithmetic is shared) -------
+template <class C, int RD, int WR, int NB>
+SCL_INL void budget_phase(const Tables& T, const StepIO& io, int member, int rank, cplx* S) {
+  constexpr int NN = C::NN, NK = C::NK;
+  constexpr int NMAIN = C::SPC * C::N / C::kThreads;
+  constexpr int NIT = (NMAIN + 1 + NB - 1) / NB;
+  constexpr bool kRead = RD != BR_NONE && RD != BR_DISS;
+  const long long mo = (long long)member * 2 * NN;
+  const cplx* qh = io.qh + mo;
+  double* out = io.bud_out + (long long)member * kBudgetTerms * NN;
+  cplx* tend = io.bud_tend + mo;
+  const cplx *dp = io.d_p + mo, *dpp = io.d_pp + mo;
+  const double dkw = T.kv[1], d1 = io.Hi_over_H[0], d2 = io.Hi_over_H[1];
+#pragma unroll 1
+  for (int b = 0; b < NIT; ++b) {
+    int idx[NB], l[NB], k[NB], kk[NB];
+    bool ok[NB];
+    cplx q0[NB], q1[NB];
+    double a00[NB], a01[NB], a10[NB], a11[NB];
+#pragma unroll
+    for (int u = 0; u < NB; ++u) {
+      const int n = b * NB + u;
+      if (n < NMAIN) {
+        const int i = threadIdx.x + C::kThreads * n;
+        ok[u] = true;
+        kk[u] = i % C::SPC;
+        l[u] = i / C::SPC;
+        k[u] = rank * C::SPC + kk[u];
+      } else {                                    // the Nyquist column k = N / 2 (CTA 0, one point for the first N threads)
+        ok[u] = n == NMAIN && rank == 0 && (int)threadIdx.x < C::N;
+        l[u] = ok[u] ? (int)threadIdx.x : 0;
+        k[u] = ok[u] ? C::H : rank * C::SPC + 1;
+        kk[u] = ok[u] ? 0 : 1;
+      }
+      idx[u] = l[u] * NK + k[u];
+      q0[u] = qh[idx[u]]; q1[u] = qh[NN + idx[u]];
+      a00[u] = T.a[idx[u]]; a01[u] = T.a[NN + idx[u]]; a10[u] = T.a[2 * NN + idx[u]]; a11[u] = T.a[3 * NN + idx[u]];
+    }
+#pragma unroll
+    for (int u = 0; u < NB; ++u) {
+      const double kv = dkw * (double)k[u], lv = dkw * (double)(l[u] < C::H ? l[u] : l[u] - C::N);
+      const cplx p0 = cmake(a00[u] * q0[u].x + a01[u] * q1[u].x, a00[u] * q0[u].y + a01[u] * q1[u].y);
+      const cplx p1 = cmake(a10[u] * q0[u].x + a11[u] * q1[u].x, a10[u] * q0[u].y + a11[u] * q1[u].y);
+      cplx A = cmake(0.0, 0.0), B = cmake(0.0, 0.0);
+      if (kRead) spec_read<C>(S, l[u], k[u], kk[u], A, B);
+      if (RD != BR_NONE && ok[u])
+        bud_read<RD>(T, io, out, tend, dp, dpp, NN, idx[u], kv, lv, q0[u], q1[u], p0, p1, a00[u], a01[u], a10[u], a11[u], A, B);
+      if (WR != BWR_NONE && ok[u]) {
+        cplx oA, oB;
+        bud_build<WR>(p0, p1, kv, lv, d1, d2, oA, oB);
+        spec_write<C>(S, l[u], k[u], kk[u], oA, oB);
+      }
+    }
+  }
+}
+
+template <int N_, int G_, int CL_>
+__global__ void __launch_bounds__((Cfg<N_, G_, CL_>::kThreads), (Cfg<N_, G_, CL_>::kCtasPerSm)) qg_budget_cl_kernel(const __grid_constant__ Tables T, const __grid_constant__ StepIO io,
+                                                              int members) {
+  using C = Cfg<N_, G_, CL_>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx* buf = reinterpret_cast<cplx*>(smem_raw);
+  cplx* tw = buf + C::kBuf;
+  uint64_t* hbar = reinterpret_cast<uint64_t*>(tw + C::N);
+  uint32_t hphase = 0;
+  for (int i = threadIdx.x; i < C::N; i += C::kThreads) tw[i] = T.tw[i];
+  if (C::kAsyncHandover && threadIdx.x == 0) handover_init(hbar);
+  const int rank = (int)cluster_rank();
+  const int ncl = gridDim.x / C::CL, cl = blockIdx.x / C::CL;
+  const bool has_dq = io.dq != nullptr;
+  cluster_sync();
+  for (int m = cl; m < members; m += ncl) {
+    __syncthreads();
+#pragma unroll 1
+    for (int r = 0; r < 9; ++r) {
+      int phys = PH_EMIT;
+      bool inv = true, fwd = true, rnd = true;
+      switch (r) {
+        case 0: budget_phase<C, BR_NONE, BWR_XI, 2>(T, io, m, rank, buf); phys = PH_SCR_STORE01; fwd = false; break;
+        case 1: budget_phase<C, BR_NONE, BWR_UV0, 2>(T, io, m, rank, buf); phys = PH_SCR_PROD0; break;
+        case 2: budget_phase<C, BR_KEFLUX0, BWR_UV1, 2>(T, io, m, rank, buf); phys = PH_SCR_PROD1; break;
+        case 3: budget_phase<C, BR_KEFLUX1, BWR_TAU, 2>(T, io, m, rank, buf); phys = PH_SCR_STORE2; fwd = false; break;
+        case 4: budget_phase<C, BR_NONE, BWR_UVBT, 2>(T, io, m, rank, buf); phys = PH_SCR_PROD2; break;
+        case 5: budget_phase<C, BR_APEFLUX, BWR_UV0, 2>(T, io, m, rank, buf); phys = PH_ANOM0; break;
+        case 6: budget_phase<C, BR_ENS0, BWR_UV1, 2>(T, io, m, rank, buf); phys = PH_ANOM1; break;
+        case 7: budget_phase<C, BR_ENS1, BWR_NONE, 2>(T, io, m, rank, buf); inv = false; phys = PH_LOAD_DQ; rnd = has_dq; break;
+        default:
+          if (has_dq) budget_phase<C, BR_PARAM_DISS, BWR_NONE, 1>(T, io, m, rank, buf);
+          else budget_phase<C, BR_DISS, BWR_NONE, 1>(T, io, m, rank, buf);
+          rnd = false;
+          break;
+      }
+      __syncthreads();
+      if (rnd) round<C, true>(inv, phys, fwd, T, io, m, buf, tw, hbar, hphase);
+      if (!fwd) __syncthreads();                       // an inverse-only round ends with reads of T': the next phase writes S over it
+    }
+  }
+  cluster_sync();
 }
 
 }  // namespace scl

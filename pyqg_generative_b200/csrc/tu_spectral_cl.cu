@@ -9,10 +9,16 @@
 namespace qgb {
 
 namespace {
+template <int N, int G, int CL, class K, class... A>
+cudaError_t launch_cl_kernel(K kern, int members, cudaStream_t st, A... args);
 template <int N, int G, int CL>
 cudaError_t launch_cl(const Tables& T, const StepIO& io, int prog, int members, cudaStream_t st) {
+  if (prog == PROG_BUDGET) return launch_cl_kernel<N, G, CL>(scl::qg_budget_cl_kernel<N, G, CL>, members, st, T, io, members);
+  return launch_cl_kernel<N, G, CL>(scl::qg_step_cl_kernel<N, G, CL>, members, st, T, io, prog, members);
+}
+template <int N, int G, int CL, class K, class... A>
+cudaError_t launch_cl_kernel(K kern, int members, cudaStream_t st, A... args) {
   using C = scl::Cfg<N, G, CL>;
-  auto kern = scl::qg_step_cl_kernel<N, G, CL>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBytes);   // per device: set every time (cheap)
   if (e != cudaSuccess) return e;
   if (CL > 8) {   // 16 CTAs per cluster is the opt-in (non-portable) size
@@ -31,13 +37,13 @@ cudaError_t launch_cl(const Tables& T, const StepIO& io, int prog, int members, 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kern, T, io, prog, members);
+  return cudaLaunchKernelEx(&cfg, kern, args...);
 }
 }  // namespace
 
 bool spectralcl_handles(int N, int prog) {
   return (N == 128 || N == 256) &&
-         (prog == PROG_STEP || prog == PROG_STEP_DQ || prog == PROG_STEP_DQ_RAW || prog == PROG_SET_Q || prog == PROG_C2R || prog == PROG_ADVECT || prog == PROG_INVERT);
+         (prog == PROG_STEP || prog == PROG_STEP_DQ || prog == PROG_STEP_DQ_RAW || prog == PROG_SET_Q || prog == PROG_C2R || prog == PROG_ADVECT || prog == PROG_INVERT || prog == PROG_BUDGET);
 }
 
 cudaError_t spectralcl_launch(const Tables& T, const StepIO& io, int prog, int members, cudaStream_t st) {
