@@ -701,14 +701,22 @@ int qgb_invert(qgb_handle* h, void* stream) {
 }
 
 namespace {
-// out[i] (+)= sum over members of per_member[m][i], in member order (deterministic, independent of the sharding)
-__global__ void reduce_members_kernel(const double* __restrict__ per_member, int members, long long n, double* __restrict__ out,
-                                      int accumulate) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+// out[i] (+)= sum over members of per_member[m][i]: eight member slices per point (a warp reads 32 consecutive points of one member),
+// added in a fixed order -- deterministic for a given number of local members
+constexpr int kReduceParts = 8;
+__global__ void __launch_bounds__(32 * kReduceParts) reduce_members_kernel(const double* __restrict__ per_member, int members, long long n,
+                                                                       double* __restrict__ out, int accumulate) {
+  __shared__ double part_sum[kReduceParts][32];
+  const long long i = (long long)blockIdx.x * 32 + threadIdx.x;
   double acc = 0.0;
-  for (int m = 0; m < members; ++m) acc += per_member[(long long)m * n + i];
-  out[i] = accumulate ? out[i] + acc : acc;
+  if (i < n)
+    for (int m = threadIdx.y; m < members; m += kReduceParts) acc += per_member[(long long)m * n + i];
+  part_sum[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && i < n) {
+    for (int p = 1; p < kReduceParts; ++p) acc += part_sum[p][threadIdx.x];
+    out[i] = accumulate ? out[i] + acc : acc;
+  }
 }
 __global__ void add_kernel(const double* __restrict__ a, long long n, double* __restrict__ out) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -735,7 +743,7 @@ int budget_sums(qgb_handle* h, const double* dq, double* out, int accumulate, cu
   int rc = launch_program(h, io, PROG_BUDGET, st);
   if (rc) return rc;
   const long long n = kBudgetTerms * NN;
-  reduce_members_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(h->bud, (int)B, n, out, accumulate);
+  reduce_members_kernel<<<(unsigned)((n + 31) / 32), dim3(32, kReduceParts), 0, st>>>(h->bud, (int)B, n, out, accumulate);
   QGB_COUNT_LAUNCH();
   CUDA_TRY(h, cudaGetLastError());
   return QGB_OK;
