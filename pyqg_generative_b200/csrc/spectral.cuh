@@ -107,6 +107,56 @@ __global__ void __launch_bounds__(NT) qg_step_fixed_kernel(const __grid_constant
   }
 }
 
+// PROG_BUDGET with the grid size at compile time (the phase list of run_program in qg_core.cuh, same phase functions): the generic
+// interpreter spent 0.93 ms per sample of 512 members at 48^2 and 4.3 ms at 96^2 (profiles/r2_diag_overhead.md)
+template <int CN, int NT>
+__global__ void __launch_bounds__(NT) qg_budget_fixed_kernel(const __grid_constant__ Tables T, const __grid_constant__ StepIO io, int members) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx* buf = reinterpret_cast<cplx*>(smem_raw);
+  cplx* tw = buf + (size_t)CN * (CN + 1);
+  short* pos = reinterpret_cast<short*>(tw + CN);
+  const int tid = threadIdx.x;
+#define QGB_BP(call) do { call; __syncthreads(); } while (0)
+  for (int m = blockIdx.x; m < members; m += gridDim.x) {
+    CtxT<CN> c{T, io, buf, tw, pos, nullptr, m};
+    QGB_BP(ph_init(c, tid, NT));
+    QGB_BP(ph_build_xi(c, tid, NT));
+    fixed_fft2d<CN, true>(c, tid, NT);
+    QGB_BP(ph_store_scr(c, 0, 2, tid, NT));
+#pragma unroll 1
+    for (int z = 0; z < 2; ++z) {
+      QGB_BP(ph_build_uv(c, z, tid, NT));
+      fixed_fft2d<CN, true>(c, tid, NT);
+      QGB_BP(ph_products_scr(c, z, tid, NT));
+      fixed_fft2d<CN, false>(c, tid, NT);
+      QGB_BP(ph_bud_keflux(c, z, tid, NT));
+    }
+    QGB_BP(ph_build_tau(c, tid, NT));
+    fixed_fft2d<CN, true>(c, tid, NT);
+    QGB_BP(ph_store_scr(c, 2, 1, tid, NT));
+    QGB_BP(ph_build_uvbt(c, tid, NT));
+    fixed_fft2d<CN, true>(c, tid, NT);
+    QGB_BP(ph_products_scr(c, 2, tid, NT));
+    fixed_fft2d<CN, false>(c, tid, NT);
+    QGB_BP(ph_bud_apeflux(c, tid, NT));
+#pragma unroll 1
+    for (int z = 0; z < 2; ++z) {
+      QGB_BP(ph_build_uv(c, z, tid, NT));
+      fixed_fft2d<CN, true>(c, tid, NT);
+      QGB_BP(ph_products_anom(c, z, tid, NT));
+      fixed_fft2d<CN, false>(c, tid, NT);
+      QGB_BP(ph_bud_ens(c, z, tid, NT));
+    }
+    if (io.dq) {
+      QGB_BP(ph_load_pair(c, io.dq, tid, NT));
+      fixed_fft2d<CN, false>(c, tid, NT);
+      QGB_BP(ph_bud_param(c, tid, NT));
+    }
+    QGB_BP(ph_bud_diss(c, io.dq != nullptr, tid, NT));
+  }
+#undef QGB_BP
+}
+
 // Large grids (N = 128, 256: the packed field is 0.26 / 1.0 MB and no longer fits one CTA's shared memory): the SAME phase
 // programs run with the working field in a per-member global-memory scratch (L2 resident: 64 members x 1 MB at 256^2)
 // and a thread-block CLUSTER of 4 or 8 CTAs per member.  Threads are numbered across the cluster, phases are separated

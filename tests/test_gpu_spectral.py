@@ -203,7 +203,7 @@ BUDGET = ('KEflux', 'APEflux', 'APEgenspec', 'KEfrictionspec', 'entspec', 'param
 
 
 @pytest.mark.parametrize('N,dt,phys', [(64, 14400., {}), (48, 7200., dict(rek=7e-8, delta=0.1, beta=1e-11)), (128, 7200., {}),
-                                      (256, 3600., dict(rek=7e-8, delta=0.1, beta=1e-11))])
+                                      (256, 3600., dict(rek=7e-8, delta=0.1, beta=1e-11)), (96, 7200., {}), (32, 14400., {})])
 def test_spectral_energy_budget_matches_oracle(N, dt, phys):
     """qgb_diag_budget (PROG_BUDGET) against the oracle's restatement of the pyqg diagnostics, with an
     external forcing standing in for the closure output (paramspec terms).  Sum over members, tolerance 1e-10."""
