@@ -90,7 +90,7 @@ class EnsembleQGModel(object):
                  rek=5.787e-7, filterfac=23.6, f=None, g=9.81, q_parameterization=None, uv_parameterization=None,
                  parameterization=None, diagnostics_list='all', ntd=1, log_level=1, logfile=None,
                  beta=1.5e-11, rd=15000.0, delta=0.25, H1=500, U1=0.025, U2=0.0,
-                 sampling_type='AR1', nsteps=1, precision='fp32', seed=None, squeeze=False, **kwargs):
+                 sampling_type='AR1', nsteps=1, precision=None, seed=None, squeeze=False, **kwargs):
         if kwargs:      # pyqg.Model.__init__ takes no **kwargs: unknown keywords are a TypeError there too
             raise TypeError("__init__() got an unexpected keyword argument '%s'" % sorted(kwargs)[0])
         if nz != 2:
@@ -321,7 +321,13 @@ class EnsembleQGModel(object):
             weight *= inner.weight
             inner = inner.param
         if isinstance(inner, DeviceClosure):
-            inner._attach(self, weight, self._precision)
+            # CNN precision of the coupled run: the model's ``precision`` keyword when given, else the one the closure's networks were
+            # built with (CGANRegression(..., precision='tc') alone must not fall back to the fp32 path), else fp32
+            prec = self._precision
+            if prec is None:
+                nets = inner._nets()
+                prec = getattr(nets[0], 'precision', None) if nets else None
+            inner._attach(self, weight, prec or 'fp32')
             self._closure = inner
             self._closure_kind = inner.closure_kind
             self._host_param = None

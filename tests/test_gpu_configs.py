@@ -134,6 +134,21 @@ def test_weighted_attached_closure_is_not_weighted_twice(tmp_path):
     assert np.abs(out[0] - ref).max() < 5e-5 * np.abs(ref).max()
 
 
+def test_coupled_run_inherits_the_precision_the_closure_was_built_with(tmp_path):
+    """README usage: ``CGANRegression(folder, precision='tc')`` + pyqg parameters WITHOUT a ``precision`` key must run the closure on
+    the tensor-core path (it used to fall back to fp32 silently); the model's own keyword still wins."""
+    from pyqg_generative_b200.models.cgan_regression import CGANRegression
+    from pyqg_generative_b200.tools.stochastic_pyqg import stochastic_QGModel
+    folder = write_model_folder(tmp_path, 'gan')
+    for closure_prec, model_prec, want in (('tc', None, 'tc'), ('fp32', None, 'fp32'), ('tc', 'fp32', 'fp32'), ('fp32', 'tc', 'tc')):
+        model = CGANRegression(folder=folder, nx=48, precision=closure_prec)
+        params = dict(nx=48, dt=7200.0, log_level=0, members=2, parameterization=model)
+        if model_prec is not None:
+            params['precision'] = model_prec
+        m = stochastic_QGModel(params, 'AR1', 1)
+        assert m.closure_precision()[0] == want, (closure_prec, model_prec, m.closure_precision())
+
+
 def test_two_devices_in_one_process_and_odd_cluster_sizes():
     """(a) function attributes are per device -- handles on two devices of one process both run the kernels that need
     > 48 KB of dynamic shared memory; (b) nx whose 8-CTA cluster split leaves a remainder (162 = 2 * 3^4) picks a cluster size
