@@ -427,6 +427,29 @@ def run_b200(args):
                     'max_rel_dev_vs_rank_ordered_gather': dev_, 'sharding_invariant': bool(dev_ < 1e-12 and cnt == tot[-1])}
         _lib.check(lib.qgb_diag_config(h, 1e12, 86400.0), h)
 
+    # ---- informational: what pyqg's time-averaged diagnostics add when they are on (the timed region runs with them off, like a
+    # run before ``tavestart``).  One sample = KEspec, Ensspec and the 13 budget terms of all local members, accumulated on the device
+    # every ``taveint`` = 1 day = 6 steps of this configuration (profiles/r2_diag_overhead.md).
+    diag_sample = None
+    if world == 1:
+        try:
+            _lib.check(lib.qgb_diag_config(h, 0.0, DT), h)               # a sample before every step
+            _lib.check(lib.qgb_step(h, 3, stream), h)
+            t_on = timed(m, 12) / 12
+            _lib.check(lib.qgb_diag_config(h, 1e12, 86400.0), h)
+            _lib.check(lib.qgb_step(h, 3, stream), h)
+            t_off = timed(m, 12) / 12
+            diag_sample = {'ms_per_sample': t_on - t_off, 'members': count, 'steps_per_sample_in_the_reference_runs': int(round(86400.0 / DT)),
+                           'ms_per_step_amortised': (t_on - t_off) / round(86400.0 / DT),
+                           'what': 'KEspec, Ensspec and the %d spectral budget terms of every member (PROG_BUDGET on the register-FFT '
+                                   'kernel) + the reduction over the members; step time with a sample before every step minus without' % len(m.DIAG_BUDGET)}
+        except Exception as e:                                   # informational: must never take the product line down
+            diag_sample = {'error': '%s: %s' % (type(e).__name__, e)}
+            try:
+                _lib.check(lib.qgb_diag_config(h, 1e12, 86400.0), h)
+            except Exception:
+                pass
+
     # ---- strong scaling of configs[2]: 1024 members IN TOTAL over the N ranks ------------------------------------------------
     strong = {'members_total': B, 'members_per_gpu': count, 'value': value, 'ms_per_step': ms / args.steps}
     if world > 1:
@@ -564,6 +587,8 @@ def run_b200(args):
     }
     if diag_obj is not None:
         line['diag_allreduce'] = diag_obj
+    if diag_sample is not None:
+        line['diag_sample'] = diag_sample
     if lib_base is not None:
         line['library_baseline'] = dict(lib_base, what='torch eager on the same GPU and workload: torch.fft.rfft2/irfft2 (cuFFT, fp64) spectral step + '
                                         'F.pad(circular) + conv2d (cuDNN) + batch_norm AndrewCNN, %d members, 3 steps' % count, unit=UNIT)
