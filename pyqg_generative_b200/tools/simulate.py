@@ -45,11 +45,15 @@ def set_initial_condition(m, rng=None):
     m._invert()
 
 
-def snapshot(m):
-    """The physical-space variables ``drop_vars(m.to_dataset())`` keeps (:16-36), float32, shape (run,lev,y,x)."""
+def snapshot(m, out=None):
+    """The physical-space variables ``drop_vars(m.to_dataset())`` keeps (:16-36), float32, shape (run,lev,y,x).  ``out``: dict of
+    preallocated (run,lev,y,x) float32 arrays the fields are downloaded into (``run_simulation`` hands out slices of the final
+    (time,run,lev,y,x) arrays, so a long ensemble run is not copied a second time when the snapshots are joined)."""
     m._invert()
     if hasattr(m, 'real32') and not getattr(m, 'squeeze', False):      # converted on the device: half the PCIe bytes
-        return dict(q=m.real32('q'), u=m.real32('u'), v=m.real32('v'), psi=m.real32('p'), time=np.float64(m.t / 86400.))
+        o = out or {}
+        return dict(q=m.real32('q', o.get('q')), u=m.real32('u', o.get('u')), v=m.real32('v', o.get('v')), psi=m.real32('p', o.get('psi')),
+                    time=np.float64(m.t / 86400.))
     return dict(q=np.asarray(m.q, 'float32'), u=np.asarray(m.u, 'float32'), v=np.asarray(m.v, 'float32'),
                 psi=np.asarray(m.p, 'float32'), time=np.float64(m.t / 86400.))
 
@@ -97,9 +101,25 @@ def run_simulation(pyqg_params, parameterization=None, q_init=None, sampling_fre
         m.set_q(np.asarray(q_init, dtype='float64'))
         m._invert()
         snaps.append(snapshot(m))
+    # the number of snapshots is known in advance: download every snapshot straight into its slot of (time,run,lev,y,x) arrays and
+    # hand out (run,time,lev,y,x) views of them (np.stack of per-snapshot arrays copied a 1024-member run a second time)
+    tsnapints = int(np.ceil(sampling_freq / m.dt))
+    n_expected = len(snaps) + int(np.ceil((m.tmax - m.t) / m.dt)) // tsnapints
+    store = None
+    if n_expected > 0 and not getattr(m, 'squeeze', False) and hasattr(m, 'real32'):
+        store = {k: np.empty((n_expected, m.members, 2, m.ny, m.nx), dtype=np.float32) for k in ('q', 'u', 'v', 'psi')}
+        for i, sn in enumerate(snaps):
+            for k in store:
+                store[k][i] = sn[k]
     for t in m.run_with_snapshots(tsnapint=sampling_freq):
-        snaps.append(snapshot(m))
-    ds = concat_in_time(snaps)
+        i = len(snaps)
+        slot = {k: a[i] for k, a in store.items()} if store is not None and i < n_expected else None
+        snaps.append(snapshot(m, slot))
+    if store is not None and len(snaps) == n_expected:
+        ds = {k: np.moveaxis(a, 0, 1) for k, a in store.items()}
+        ds['time'] = np.array([sn['time'] for sn in snaps])
+    else:
+        ds = concat_in_time(snaps)
     ds.update(m.averaged_diagnostics())      # KEspec, Ensspec, KEflux, APEflux, APEgenspec, KEfrictionspec, paramspec*, entspec
     coords, attrs = model_coords(m)
     ds['coords'] = coords
