@@ -157,6 +157,56 @@ __global__ void __launch_bounds__(NT) qg_budget_fixed_kernel(const __grid_consta
 #undef QGB_BP
 }
 
+// The q setter, irfft2, _invert and the advection operator (PROG_SET_Q, PROG_C2R, PROG_INVERT, PROG_ADVECT: snapshots and the
+// coarse-graining operators) with the grid size at compile time -- the phase lists of run_program, same phase functions
+template <int CN, int NT>
+__global__ void __launch_bounds__(NT) qg_program_fixed_kernel(const __grid_constant__ Tables T, const __grid_constant__ StepIO io, int prog,
+                                                              int members) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx* buf = reinterpret_cast<cplx*>(smem_raw);
+  cplx* tw = buf + (size_t)CN * (CN + 1);
+  short* pos = reinterpret_cast<short*>(tw + CN);
+  const int tid = threadIdx.x;
+#define QGB_BP(call) do { call; __syncthreads(); } while (0)
+  for (int m = blockIdx.x; m < members; m += gridDim.x) {
+    CtxT<CN> c{T, io, buf, tw, pos, nullptr, m};
+    QGB_BP(ph_init(c, tid, NT));
+    if (prog == PROG_SET_Q) {
+      QGB_BP(ph_load_pair(c, io.q, tid, NT));
+      fixed_fft2d<CN, false>(c, tid, NT);
+      QGB_BP(ph_store_qh(c, tid, NT));
+      if (io.cnn_x) QGB_BP(ph_emit_x_only(c, tid, NT));
+    } else if (prog == PROG_C2R) {
+      QGB_BP(ph_build_q(c, tid, NT));
+      fixed_fft2d<CN, true>(c, tid, NT);
+      QGB_BP(ph_emit_q(c, tid, NT));
+    } else if (prog == PROG_INVERT) {
+      if (io.ph_out) QGB_BP(ph_store_ph(c, tid, NT));
+#pragma unroll 1
+      for (int z = 0; z < 2; ++z) {
+        QGB_BP(ph_build_uv(c, z, tid, NT));
+        fixed_fft2d<CN, true>(c, tid, NT);
+        QGB_BP(ph_store_uv(c, z, tid, NT));
+      }
+      if (io.p_out) {
+        QGB_BP(ph_build_p(c, tid, NT));
+        fixed_fft2d<CN, true>(c, tid, NT);
+        QGB_BP(ph_store_p(c, tid, NT));
+      }
+    } else {                                           // PROG_ADVECT
+#pragma unroll 1
+      for (int z = 0; z < 2; ++z) {
+        QGB_BP(ph_build_uv(c, z, tid, NT));
+        fixed_fft2d<CN, true>(c, tid, NT);
+        QGB_BP(ph_products(c, z, tid, NT));
+        fixed_fft2d<CN, false>(c, tid, NT);
+        QGB_BP(ph_tendency(c, z, tid, NT));
+      }
+    }
+  }
+#undef QGB_BP
+}
+
 // Large grids (N = 128, 256: the packed field is 0.26 / 1.0 MB and no longer fits one CTA's shared memory): the SAME phase
 // programs run with the working field in a per-member global-memory scratch (L2 resident: 64 members x 1 MB at 256^2)
 // and a thread-block CLUSTER of 4 or 8 CTAs per member.  Threads are numbered across the cluster, phases are separated

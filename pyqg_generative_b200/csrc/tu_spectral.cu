@@ -41,6 +41,9 @@ cudaError_t spectral_configure(const SpectralPlan& p) {
       QGB_ATTR((qg_step_fixed_kernel<64, 512>), p.smem);
     }
     if (p.N == 96) QGB_ATTR((qg_step_fixed_kernel<96, 512>), p.smem);
+    if (p.N == 32) QGB_ATTR((qg_program_fixed_kernel<32, 256>), p.smem);
+    if (p.N == 48) QGB_ATTR((qg_program_fixed_kernel<48, 256>), p.smem);
+    if (p.N == 96) QGB_ATTR((qg_program_fixed_kernel<96, 512>), p.smem);
     if (p.N == 32) QGB_ATTR((qg_budget_fixed_kernel<32, 256>), p.smem);
     if (p.N == 48) QGB_ATTR((qg_budget_fixed_kernel<48, 256>), p.smem);
     if (p.N == 96) QGB_ATTR((qg_budget_fixed_kernel<96, 512>), p.smem);
@@ -89,6 +92,12 @@ cudaError_t spectral_launch(const SpectralPlan& p, const Tables& TT, const StepI
     if (p.N == 32) qg_budget_fixed_kernel<32, 256><<<p.grid, 256, p.smem, st>>>(TT, io, p.members);
     else if (p.N == 48) qg_budget_fixed_kernel<48, 256><<<p.grid, 256, p.smem, st>>>(TT, io, p.members);
     else qg_budget_fixed_kernel<96, 512><<<p.grid, 512, p.smem, st>>>(TT, io, p.members);
+    return cudaGetLastError();
+  }
+  if ((prog == PROG_SET_Q || prog == PROG_C2R || prog == PROG_INVERT || prog == PROG_ADVECT) && p.fixed && p.N != 64) {
+    if (p.N == 32) qg_program_fixed_kernel<32, 256><<<p.grid, 256, p.smem, st>>>(TT, io, prog, p.members);
+    else if (p.N == 48) qg_program_fixed_kernel<48, 256><<<p.grid, 256, p.smem, st>>>(TT, io, prog, p.members);
+    else qg_program_fixed_kernel<96, 512><<<p.grid, 512, p.smem, st>>>(TT, io, prog, p.members);
     return cudaGetLastError();
   }
   qg_program_kernel<<<p.grid, p.nthreads, p.smem, st>>>(TT, io, prog, p.members);
